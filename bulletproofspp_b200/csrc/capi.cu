@@ -1,0 +1,798 @@
+// C ABI (include/bppp_b200.h): context, device buffers, kernel launches and the host-side round
+// sequencing of the NormLinear argument.  No CPU fallback: every compute entry point launches
+// the sm_100a kernels of kernels.cuh.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/bppp_b200.h"
+#include "host_math.hpp"
+#include "kernels.cuh"
+
+using namespace bppp;
+
+struct bppp_ctx {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+};
+
+#define CK(x)                                                                                   \
+    do {                                                                                        \
+        cudaError_t e_ = (x);                                                                   \
+        if (e_ != cudaSuccess) {                                                                \
+            char buf_[256];                                                                     \
+            snprintf(buf_, sizeof buf_, "%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); \
+            ctx->err = buf_;                                                                    \
+            return BPPP_ERR_CUDA;                                                               \
+        }                                                                                       \
+    } while (0)
+#define FAIL(code, msg)  \
+    do {                 \
+        ctx->err = msg;  \
+        return code;     \
+    } while (0)
+#define LAUNCHED(n) (ctx->launches += (n))
+
+namespace {
+
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t ensure(size_t count) { return count <= n ? cudaSuccess : alloc(count); }
+};
+
+__global__ void k_bcast_point(const Affine* src, Affine* dst, size_t stride, size_t batch) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < batch) st_aff(dst + i * stride, ld_aff(src));
+}
+
+bool check_fr(const uint8_t* b, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (!host::fr_is_canonical(host::from_bytes(b + 32 * i))) return false;
+    return true;
+}
+bool check_fq(const uint8_t* b, size_t n) {
+    for (size_t i = 0; i < n; i++)
+        if (!host::fq_is_canonical(host::from_bytes(b + 32 * i))) return false;
+    return true;
+}
+
+// ----------------------------------------------------------------------------- MSM driver
+struct MsmPlan {
+    std::vector<MsmSlice> slices;
+    DBuf<MsmSlice> d_slices;
+    DBuf<Jac> d_partial;
+    size_t smem = 0;
+    void add(const Affine* pts, size_t pts_stride, const u256* sc, size_t sc_stride, size_t sc_out_stride, size_t n) {
+        for (size_t off = 0; off < n; off += MSM_MAX_CHUNK) {
+            MsmSlice s;
+            s.pts = pts + off; s.pts_stride = pts_stride;
+            s.sc = sc + off; s.sc_stride = sc_stride; s.sc_out_stride = sc_out_stride;
+            s.n = (int)std::min<size_t>(MSM_MAX_CHUNK, n - off);
+            slices.push_back(s);
+        }
+    }
+};
+size_t msm_smem_bytes(int max_n) {
+    return (size_t)(2 * MSM_W * MSM_NB + 1) * 4 + (size_t)max_n * MSM_W * 2 + 16;
+}
+bool g_attr_set = false;
+
+// runs the MSMs described by plan.slices for `batch` proofs x `n_out` outputs; result Jacobian
+// points in d_res[(p*n_out + o)]
+int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res) {
+    int nch = (int)plan.slices.size();
+    if (nch == 0) FAIL(BPPP_ERR_ARG, "empty MSM");
+    int max_n = 0;
+    for (auto& s : plan.slices) max_n = std::max(max_n, s.n);
+    CK(plan.d_slices.ensure(nch));
+    CK(cudaMemcpyAsync(plan.d_slices.p, plan.slices.data(), nch * sizeof(MsmSlice), cudaMemcpyHostToDevice, ctx->st));
+    CK(plan.d_partial.ensure(batch * n_out * nch * MSM_W));
+    if (!g_attr_set) {
+        CK(cudaFuncSetAttribute(k_msm_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)msm_smem_bytes(MSM_MAX_CHUNK)));
+        g_attr_set = true;
+    }
+    MsmArgs A;
+    A.slices = plan.d_slices.p; A.n_chunks = nch; A.partial = plan.d_partial.p; A.n_out = n_out;
+    // grid.z is limited to 65535: loop over batch slabs
+    for (size_t b0 = 0; b0 < batch; b0 += 32768) {
+        size_t nb = std::min<size_t>(32768, batch - b0);
+        MsmArgs B = A;
+        // shift per-proof bases by b0 proofs: done by offsetting the partial pointer and using a
+        // slab-local copy of the slices when b0 > 0
+        if (b0 > 0) {
+            std::vector<MsmSlice> sl = plan.slices;
+            for (auto& s : sl) { s.pts += b0 * s.pts_stride; s.sc += b0 * s.sc_stride; }
+            MsmSlice* d2;
+            CK(cudaMallocAsync((void**)&d2, nch * sizeof(MsmSlice), ctx->st));
+            CK(cudaMemcpyAsync(d2, sl.data(), nch * sizeof(MsmSlice), cudaMemcpyHostToDevice, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            B.slices = d2;
+            B.partial = A.partial + b0 * n_out * nch * MSM_W;
+            k_msm_bucket<<<dim3(nch, n_out, (unsigned)nb), MSM_THREADS, msm_smem_bytes(max_n), ctx->st>>>(B);
+            CK(cudaGetLastError());
+            CK(cudaFreeAsync(d2, ctx->st));
+        } else {
+            k_msm_bucket<<<dim3(nch, n_out, (unsigned)nb), MSM_THREADS, msm_smem_bytes(max_n), ctx->st>>>(B);
+            CK(cudaGetLastError());
+        }
+        LAUNCHED(1);
+    }
+    size_t n_msm = batch * n_out;
+    k_msm_finish<<<(unsigned)n_msm, 32, 0, ctx->st>>>(plan.d_partial.p, nch, d_res, n_msm);
+    CK(cudaGetLastError());
+    LAUNCHED(1);
+    return BPPP_OK;
+}
+
+int to_affine(bppp_ctx* ctx, const Jac* in, size_t in_stride, Affine* out, size_t out_stride, int out_off, int n_per,
+              size_t total) {
+    if (total == 0) return BPPP_OK;
+    // enough threads to fill the chip, at most 32 points per thread
+    int chunk = (int)std::min<size_t>(32, std::max<size_t>(1, total / (148 * 512)));
+    size_t threads = (total + chunk - 1) / chunk;
+    k_batch_to_affine<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->st>>>(in, in_stride, out, out_stride, out_off,
+                                                                              n_per, total, chunk);
+    CK(cudaGetLastError());
+    LAUNCHED(1);
+    return BPPP_OK;
+}
+
+}  // namespace
+
+// =============================================================================== context
+extern "C" int bppp_abi_version(void) { return 1; }
+
+extern "C" int bppp_init(int device, bppp_ctx** out) {
+    if (!out) return BPPP_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return BPPP_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return BPPP_ERR_CUDA;
+    bppp_ctx* c = new bppp_ctx();
+    c->dev = device;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return BPPP_ERR_CUDA;
+    }
+    *out = c;
+    return BPPP_OK;
+}
+extern "C" void bppp_free(bppp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->dev);
+    if (ctx->st) cudaStreamDestroy(ctx->st);
+    delete ctx;
+}
+extern "C" const char* bppp_last_error(bppp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" uint64_t bppp_launch_count(bppp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int bppp_sync(bppp_ctx* ctx) {
+    if (!ctx) return BPPP_ERR_ARG;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+
+// =============================================================================== MSM seam
+extern "C" int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8_t* scalars, const uint8_t* points,
+                              int shared_points, uint8_t* out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!scalars || !points || !out || batch == 0) FAIL(BPPP_ERR_ARG, "bppp_msm_batch: null/empty argument");
+    CK(cudaSetDevice(ctx->dev));
+    if (n == 0) {                                   // the reference's innerProduct calls `head` on []
+        memset(out, 0, batch * 64);                 // (src/Commitment.hs:328); here: the identity
+        return BPPP_OK;
+    }
+    size_t npts = shared_points ? n : batch * n;
+    if (!check_fr(scalars, batch * n)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    if (!check_fq(points, npts * 2)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    DBuf<u256> d_sc;
+    DBuf<Affine> d_pts, d_aff;
+    DBuf<Jac> d_res;
+    CK(d_sc.alloc(batch * n));
+    CK(d_pts.alloc(npts));
+    CK(d_res.alloc(batch));
+    CK(d_aff.alloc(batch));
+    CK(cudaMemcpyAsync(d_sc.p, scalars, batch * n * 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d_pts.p, points, npts * 64, cudaMemcpyHostToDevice, ctx->st));
+    MsmPlan plan;
+    plan.add(d_pts.p, shared_points ? 0 : n, d_sc.p, n, 0, n);
+    int rc = run_msm(ctx, plan, batch, 1, d_res.p);
+    if (rc) return rc;
+    rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_aff.p, batch * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+extern "C" int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t out[64]) {
+    return bppp_msm_batch(ctx, 1, n, scalars, points, 1, out);
+}
+
+// =============================================================================== pair fold
+namespace {
+int launch_pair_fold(bppp_ctx* ctx, const Affine* in, size_t in_stride, Jac* out, size_t out_stride,
+                     const PairFoldSeg* segs, int n_seg, const u256* kb, const u256* ka, const unsigned char* sgn,
+                     size_t batch) {
+    static bool attr = false;
+    const size_t smem = 4 * 16 * PF_THREADS * sizeof(uint32_t);
+    if (!attr) {
+        CK(cudaFuncSetAttribute(k_pair_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    PairFoldArgs A;
+    A.in = in; A.in_stride = in_stride; A.out = out; A.out_stride = out_stride;
+    A.n_seg = 0; A.kb = kb; A.ka = ka; A.sgn = sgn;
+    int total_blocks = 0;
+    for (int s = 0; s < n_seg; s++) {
+        A.seg[A.n_seg] = segs[s];
+        int n_out = (segs[s].n_in + 1) / 2;
+        A.blocks_per_seg[A.n_seg] = (n_out + PF_THREADS - 1) / PF_THREADS;
+        total_blocks += A.blocks_per_seg[A.n_seg];
+        A.n_seg++;
+    }
+    if (total_blocks == 0) return BPPP_OK;
+    for (size_t b0 = 0; b0 < batch; b0 += 65535) {
+        size_t nb = std::min<size_t>(65535, batch - b0);
+        PairFoldArgs B = A;
+        B.in = in + b0 * in_stride; B.out = out + b0 * out_stride;
+        B.kb = kb + b0 * n_seg; B.ka = ka + b0 * n_seg; B.sgn = sgn + b0 * n_seg;
+        k_pair_fold<<<dim3(total_blocks, (unsigned)nb), PF_THREADS, smem, ctx->st>>>(B);
+        CK(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    return BPPP_OK;
+}
+}  // namespace
+
+extern "C" int bppp_pair_fold(bppp_ctx* ctx, size_t n_in, const uint8_t a[32], int a_neg, const uint8_t b[32],
+                              int b_neg, const uint8_t* points_in, uint8_t* points_out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!a || !b || !points_in || !points_out) FAIL(BPPP_ERR_ARG, "bppp_pair_fold: null argument");
+    if (n_in == 0) return BPPP_OK;
+    CK(cudaSetDevice(ctx->dev));
+    if (!check_fq(points_in, n_in * 2)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    u256 ka = host::from_bytes(a), kb = host::from_bytes(b);
+    if (ka.v[7] >> 31 || kb.v[7] >> 31) FAIL(BPPP_ERR_RANGE, "fold scalar magnitude >= 2^255");
+    size_t n_out = (n_in + 1) / 2;
+    DBuf<Affine> d_in, d_out;
+    DBuf<Jac> d_j;
+    DBuf<u256> d_k;
+    DBuf<unsigned char> d_s;
+    CK(d_in.alloc(n_in)); CK(d_out.alloc(n_out)); CK(d_j.alloc(n_out)); CK(d_k.alloc(2)); CK(d_s.alloc(1));
+    unsigned char sg = (unsigned char)((b_neg ? 1 : 0) | (a_neg ? 2 : 0));
+    u256 ks[2] = {kb, ka};
+    CK(cudaMemcpyAsync(d_in.p, points_in, n_in * 64, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d_k.p, ks, 64, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(d_s.p, &sg, 1, cudaMemcpyHostToDevice, ctx->st));
+    PairFoldSeg seg = {0, (int)n_in, 0};
+    int rc = launch_pair_fold(ctx, d_in.p, 0, d_j.p, 0, &seg, 1, d_k.p, d_k.p + 1, d_s.p, 1);
+    if (rc) return rc;
+    rc = to_affine(ctx, d_j.p, n_out, d_out.p, n_out, 0, (int)n_out, n_out);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(points_out, d_out.p, n_out * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+
+extern "C" int bppp_rational_reduce(const uint8_t x[32], uint8_t a[32], int* a_neg, uint8_t b[32], int* b_neg) {
+    if (!x || !a || !b || !a_neg || !b_neg) return BPPP_ERR_ARG;
+    u256 xv = host::from_bytes(x);
+    if (!host::fr_is_canonical(xv)) return BPPP_ERR_RANGE;
+    host::Ratio r = host::rational_reduce(xv);
+    host::to_bytes(a, r.a); host::to_bytes(b, r.b);
+    *a_neg = r.a_neg; *b_neg = r.b_neg;
+    return BPPP_OK;
+}
+
+// =============================================================================== argument seam
+struct bppp_nl {
+    bppp_ctx* ctx;
+    int kind;
+    size_t B, N, M;                 // batch, initial lengths
+    size_t curN, curM;              // current lengths
+    size_t N2, M2, P0, P2;          // half lengths, point strides (round 0 shared / later per proof)
+    int round = 0;
+    bool have_partials = false;
+    int cur = 0;                    // which scalar buffer holds the current vectors
+    int curp = -1;                  // which per-proof point buffer is current (-1: shared base)
+    DBuf<Affine> base, pts[2], aff;
+    DBuf<u256> w[2], l[2], c[2];
+    size_t wstride[2], lstride[2];
+    DBuf<u256> sc;                  // [2][B][1+N+M] canonical MSM scalars (X then R)
+    DBuf<u256> part_n, part_l, dots, consts;
+    DBuf<unsigned char> sgn;
+    DBuf<Jac> jscratch, res;
+    MsmPlan plan;
+    int blocks_n = 1, blocks_l = 1;
+    // host state (Montgomery)
+    std::vector<u256> q, qinv, nn, nl, s, sX, sR;
+};
+
+namespace {
+enum { C_RHO = 0, C_K1, C_K2, C_AU, C_BU, C_AL, C_BL, C_AC, C_BC, C_COEF /* 8 */, C_KB = C_COEF + 8 /* 2 */,
+       C_KA = C_KB + 2 /* 2 */, C_COUNT = C_KA + 2 };
+inline u256* cptr(bppp_nl* h, int which) { return h->consts.p + (size_t)which * h->B; }
+
+int dots_blocks(size_t n_pairs) {
+    size_t b = (n_pairs + 255) / 256;
+    return (int)std::max<size_t>(1, std::min<size_t>(b, 1024));
+}
+
+// launch k_fold_dots for norm and linear vectors.  fold = 0: dots of current vectors; fold = 1:
+// fold current vectors into the other buffer and compute the dots of the result.
+int launch_fold_dots(bppp_nl* h, int fold) {
+    bppp_ctx* ctx = h->ctx;
+    int src = h->cur, dst = h->cur ^ 1;
+    if (h->curN) {
+        size_t ny = fold ? (h->curN + 1) / 2 : h->curN;
+        h->blocks_n = dots_blocks((ny + 1) / 2);
+        CK(h->part_n.ensure(h->B * h->blocks_n * 2));
+        FoldDotsArgs A;
+        A.u = A.v = h->w[src].p; A.uo = A.vo = h->w[dst].p;
+        A.in_stride = h->wstride[src]; A.out_stride = h->wstride[dst];
+        A.n_in = (int)h->curN; A.fold = fold;
+        A.au = A.av = cptr(h, C_AU); A.bu = A.bv = cptr(h, C_BU);
+        A.rho = cptr(h, C_RHO); A.m1 = 1; A.m2 = 4; A.partial = h->part_n.p;
+        k_fold_dots<<<dim3(h->blocks_n, (unsigned)h->B), 256, 0, ctx->st>>>(A);
+        CK(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    if (h->curM) {
+        size_t ny = fold ? (h->curM + 1) / 2 : h->curM;
+        h->blocks_l = dots_blocks((ny + 1) / 2);
+        CK(h->part_l.ensure(h->B * h->blocks_l * 2));
+        FoldDotsArgs A;
+        A.u = h->c[src].p; A.v = h->l[src].p; A.uo = h->c[dst].p; A.vo = h->l[dst].p;
+        A.in_stride = h->lstride[src]; A.out_stride = h->lstride[dst];
+        A.n_in = (int)h->curM; A.fold = fold;
+        A.au = cptr(h, C_AC); A.bu = cptr(h, C_BC); A.av = cptr(h, C_AL); A.bv = cptr(h, C_BL);
+        A.rho = nullptr; A.m1 = 3; A.m2 = 4; A.partial = h->part_l.p;
+        k_fold_dots<<<dim3(h->blocks_l, (unsigned)h->B), 256, 0, ctx->st>>>(A);
+        CK(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    return BPPP_OK;
+}
+int upload_consts(bppp_nl* h, int which, const std::vector<u256>& v) {
+    bppp_ctx* ctx = h->ctx;
+    CK(cudaMemcpyAsync(cptr(h, which), v.data(), v.size() * 32, cudaMemcpyHostToDevice, ctx->st));
+    return BPPP_OK;
+}
+}  // namespace
+
+extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, const uint8_t* g,
+                              const uint8_t* G, const uint8_t* H, const uint8_t* q, const uint8_t* s, const uint8_t* w,
+                              const uint8_t* l, const uint8_t* c, bppp_nl** out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!out || !g || !q || !s || batch == 0 || (N && (!G || !w)) || (M && (!H || !l || !c)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_create: null/empty argument");
+    *out = nullptr;
+    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_create: only BPPP_ARG_NL is implemented on the device path");
+    if (N + M + 1 > 0x7fffffff) FAIL(BPPP_ERR_ARG, "vector too long");
+    CK(cudaSetDevice(ctx->dev));
+    if (!check_fq(g, 2) || !check_fq(G, 2 * N) || !check_fq(H, 2 * M)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    if (!check_fr(q, batch) || !check_fr(s, batch) || !check_fr(w, batch * N) || !check_fr(l, batch * M) ||
+        !check_fr(c, batch * M))
+        FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    bppp_nl* h = new bppp_nl();
+    h->ctx = ctx; h->kind = kind; h->B = batch; h->N = N; h->M = M; h->curN = N; h->curM = M;
+    h->N2 = (N + 1) / 2; h->M2 = (M + 1) / 2; h->P0 = 1 + N + M; h->P2 = 1 + h->N2 + h->M2;
+    auto fail = [&](int rc) { bppp_nl_destroy(h); return rc; };
+#define CKH(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x ": ") + cudaGetErrorString(e_); return fail(BPPP_ERR_CUDA); } } while (0)
+    CKH(h->base.alloc(h->P0));
+    CKH(h->pts[0].alloc(batch * h->P2)); CKH(h->pts[1].alloc(batch * h->P2));
+    CKH(h->aff.alloc(batch * 2));
+    CKH(h->w[0].alloc(batch * N)); CKH(h->w[1].alloc(batch * h->N2));
+    CKH(h->l[0].alloc(batch * M)); CKH(h->l[1].alloc(batch * h->M2));
+    CKH(h->c[0].alloc(batch * M)); CKH(h->c[1].alloc(batch * h->M2));
+    h->wstride[0] = N; h->wstride[1] = h->N2; h->lstride[0] = M; h->lstride[1] = h->M2;
+    CKH(h->sc.alloc(2 * batch * h->P0));
+    CKH(h->dots.alloc(batch * 2));
+    CKH(h->consts.alloc((size_t)C_COUNT * batch));
+    CKH(h->sgn.alloc(batch * 2));
+    CKH(h->jscratch.alloc(batch * (h->N2 + h->M2)));
+    CKH(h->res.alloc(batch * 2));
+    // generators
+    CKH(cudaMemcpyAsync(h->base.p, g, 64, cudaMemcpyHostToDevice, ctx->st));
+    if (N) CKH(cudaMemcpyAsync(h->base.p + 1, G, N * 64, cudaMemcpyHostToDevice, ctx->st));
+    if (M) CKH(cudaMemcpyAsync(h->base.p + 1 + N, H, M * 64, cudaMemcpyHostToDevice, ctx->st));
+    for (int k = 0; k < 2; k++) {
+        k_bcast_point<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->st>>>(h->base.p, h->pts[k].p, h->P2, batch);
+        CKH(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    // scalars -> Montgomery on the device (staged through the scalar scratch buffer)
+    struct { const uint8_t* src; u256* dst; size_t n; } up[3] = {
+        {w, h->w[0].p, batch * N}, {l, h->l[0].p, batch * M}, {c, h->c[0].p, batch * M}};
+    for (auto& u : up) {
+        if (!u.n) continue;
+        CKH(cudaMemcpyAsync(h->sc.p, u.src, u.n * 32, cudaMemcpyHostToDevice, ctx->st));
+        k_fr_convert<<<(unsigned)((u.n + 255) / 256), 256, 0, ctx->st>>>(h->sc.p, u.dst, u.n, 1);
+        CKH(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    CKH(cudaMemsetAsync(h->sc.p, 0, 2 * batch * h->P0 * 32, ctx->st));
+    // host state
+    h->q.resize(batch); h->qinv.resize(batch); h->nn.assign(batch, fr::one()); h->nl.assign(batch, fr::one());
+    h->s.resize(batch); h->sX.resize(batch); h->sR.resize(batch);
+    for (size_t b = 0; b < batch; b++) {
+        h->q[b] = fr::to_mont(host::from_bytes(q + 32 * b));
+        h->qinv[b] = h->q[b];
+        h->s[b] = fr::to_mont(host::from_bytes(s + 32 * b));
+    }
+    host::fr_batch_inv(h->qinv.data(), batch);
+    CKH(cudaStreamSynchronize(ctx->st));
+#undef CKH
+    *out = h;
+    return BPPP_OK;
+}
+
+extern "C" void bppp_nl_destroy(bppp_nl* h) {
+    if (!h) return;
+    cudaSetDevice(h->ctx->dev);
+    cudaStreamSynchronize(h->ctx->st);
+    delete h;
+}
+
+extern "C" int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin) {
+    if (!h) return BPPP_ERR_ARG;
+    if (n_norm) *n_norm = h->curN;
+    if (n_lin) *n_lin = h->curM;
+    return BPPP_OK;
+}
+
+extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    if (!X || !R) FAIL(BPPP_ERR_ARG, "bppp_nl_round_commit: null output");
+    CK(cudaSetDevice(ctx->dev));
+    const size_t B = h->B;
+    // per-proof constants of this round (NormArgument.hs:113): rho = q^4, k1 = 2 n^2 q^3, k2 = n^2 q^4
+    std::vector<u256> rho(B), k1(B), k2(B), coef(B * 8, u256_zero());
+    for (size_t b = 0; b < B; b++) {
+        u256 q2 = fr::sqr(h->q[b]), q3 = fr::mul(q2, h->q[b]), q4 = fr::sqr(q2), n2 = fr::sqr(h->nn[b]);
+        rho[b] = q4;
+        u256 t = fr::mul(n2, q3);
+        k1[b] = fr::add(t, t);
+        k2[b] = fr::mul(n2, q4);
+        coef[b * 8 + 1] = h->q[b];          // X on gL <- q * xR
+        coef[b * 8 + 2] = h->qinv[b];       // X on gR <- q^-1 * xL
+    }
+    int rc;
+    if (!h->have_partials) {
+        if ((rc = upload_consts(h, C_RHO, rho))) return rc;
+        if ((rc = launch_fold_dots(h, 0))) return rc;
+        h->have_partials = true;
+    }
+    if ((rc = upload_consts(h, C_K1, k1))) return rc;
+    if ((rc = upload_consts(h, C_K2, k2))) return rc;
+    CK(cudaMemcpyAsync(cptr(h, C_COEF), coef.data(), B * 8 * 32, cudaMemcpyHostToDevice, ctx->st));
+    const size_t P0 = h->P0;
+    u256* xs = h->sc.p;
+    u256* rs = h->sc.p + B * P0;
+    {
+        DotsFinishArgs A;
+        memset(&A, 0, sizeof A);
+        A.n_seg = 0;
+        if (h->curN) { A.partial[A.n_seg] = h->part_n.p; A.n_blocks[A.n_seg] = h->blocks_n; A.k1[A.n_seg] = cptr(h, C_K1); A.k2[A.n_seg] = cptr(h, C_K2); A.n_seg++; }
+        if (h->curM) { A.partial[A.n_seg] = h->part_l.p; A.n_blocks[A.n_seg] = h->blocks_l; A.k1[A.n_seg] = nullptr; A.k2[A.n_seg] = nullptr; A.n_seg++; }
+        A.res = h->dots.p; A.xs = xs; A.rs = rs; A.sc_stride = P0; A.batch = (int)B;
+        k_dots_finish<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(A);
+        CK(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    const int src = h->cur;
+    if (h->curN) {
+        MsmScalarsArgs A;
+        A.x = h->w[src].p; A.in_stride = h->wstride[src]; A.n_in = (int)h->curN;
+        A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1; A.coef = cptr(h, C_COEF);
+        const unsigned char kd[8] = {0, 2, 2, 0, 0, 0, 0, 1};
+        memcpy(A.kind, kd, 8);
+        k_msm_scalars<<<dim3((unsigned)(((h->curN + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        CK(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    if (h->curM) {
+        MsmScalarsArgs A;
+        A.x = h->l[src].p; A.in_stride = h->lstride[src]; A.n_in = (int)h->curM;
+        A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1 + (int)h->curN; A.coef = cptr(h, C_COEF);
+        const unsigned char kd[8] = {0, 1, 1, 0, 0, 0, 0, 1};
+        memcpy(A.kind, kd, 8);
+        k_msm_scalars<<<dim3((unsigned)(((h->curM + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        CK(cudaGetLastError());
+        LAUNCHED(1);
+    }
+    // the two commitments: MSMs over [g | G | H] with X scalars (output 0) and R scalars (output 1)
+    h->plan.slices.clear();
+    const size_t nterms = 1 + h->curN + h->curM;
+    if (h->curp < 0) h->plan.add(h->base.p, 0, xs, P0, B * P0, nterms);
+    else h->plan.add(h->pts[h->curp].p, h->P2, xs, P0, B * P0, nterms);
+    if ((rc = run_msm(ctx, h->plan, B, 2, h->res.p))) return rc;
+    if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2))) return rc;
+    std::vector<Affine> xr(B * 2);
+    std::vector<u256> dots(B * 2);
+    CK(cudaMemcpyAsync(xr.data(), h->aff.p, B * 2 * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaMemcpyAsync(dots.data(), h->dots.p, B * 2 * 32, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (size_t b = 0; b < B; b++) {
+        memcpy(X + 64 * b, &xr[2 * b], 64);
+        memcpy(R + 64 * b, &xr[2 * b + 1], 64);
+        h->sX[b] = dots[2 * b];
+        h->sR[b] = dots[2 * b + 1];
+    }
+    return BPPP_OK;
+}
+
+extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    if (!e) FAIL(BPPP_ERR_ARG, "bppp_nl_round_fold: null challenge");
+    if (!h->have_partials) FAIL(BPPP_ERR_STATE, "bppp_nl_round_fold before bppp_nl_round_commit");
+    CK(cudaSetDevice(ctx->dev));
+    const size_t B = h->B;
+    if (!check_fr(e, B)) FAIL(BPPP_ERR_RANGE, "challenge >= group order");
+    std::vector<u256> au(B), bu(B), al(B), bl(B), ac(B), bc(B), rho(B), kk(B * 4), b0n(B), b0l(B);
+    std::vector<unsigned char> sg(B * 2);
+    std::vector<u256> em(B);
+    for (size_t b = 0; b < B; b++) {
+        em[b] = fr::to_mont(host::from_bytes(e + 32 * b));
+        // NormArgument.hs:125  (a', b') = rationalReduceScalar (e * qInv)
+        host::Ratio rn = host::rational_reduce(fr::from_mont(fr::mul(em[b], h->qinv[b])));
+        // NormArgument.hs:66   (a', b') = rationalReduceScalar e
+        host::Ratio rl = host::rational_reduce(host::from_bytes(e + 32 * b));
+        kk[b * 2 + 0] = rn.b; kk[b * 2 + 1] = rl.b;                  // kb[b][seg]
+        kk[B * 2 + b * 2 + 0] = rn.a; kk[B * 2 + b * 2 + 1] = rl.a;  // ka[b][seg]
+        sg[b * 2 + 0] = (unsigned char)((rn.b_neg ? 1 : 0) | (rn.a_neg ? 2 : 0));
+        sg[b * 2 + 1] = (unsigned char)((rl.b_neg ? 1 : 0) | (rl.a_neg ? 2 : 0));
+        b0n[b] = host::fr_from_signed(rn.b, rn.b_neg);
+        b0l[b] = host::fr_from_signed(rl.b, rl.b_neg);
+        ac[b] = b0l[b];                                              // c' = b0*cL + a0*cR
+        bc[b] = host::fr_from_signed(rl.a, rl.a_neg);
+    }
+    std::vector<u256> inv(2 * B);
+    for (size_t b = 0; b < B; b++) { inv[b] = b0n[b]; inv[B + b] = b0l[b]; }
+    host::fr_batch_inv(inv.data(), 2 * B);
+    for (size_t b = 0; b < B; b++) {
+        // x' = b0Inv*xL + e*q*b0Inv*xR   (NormArgument.hs:129);  l' = b0Inv*xL + e*b0Inv*xR  (:71)
+        au[b] = inv[b];
+        bu[b] = fr::mul(fr::mul(em[b], h->q[b]), inv[b]);
+        al[b] = inv[B + b];
+        bl[b] = fr::mul(em[b], inv[B + b]);
+        // s' = s + e*sX + (e^2 - 1)*sR   (Bulletproof.hs:352-353, makeEs NormArgument.hs:109)
+        u256 e1 = fr::sub(fr::sqr(em[b]), fr::one());
+        h->s[b] = fr::add(h->s[b], fr::add(fr::mul(em[b], h->sX[b]), fr::mul(e1, h->sR[b])));
+        // n <- n*b0*qInv ; q <- q^2 ; linear n <- n*b0
+        h->nn[b] = fr::mul(fr::mul(h->nn[b], b0n[b]), h->qinv[b]);
+        h->nl[b] = fr::mul(h->nl[b], b0l[b]);
+        h->q[b] = fr::sqr(h->q[b]);
+        h->qinv[b] = fr::sqr(h->qinv[b]);
+        rho[b] = fr::sqr(fr::sqr(h->q[b]));
+    }
+    int rc;
+    if ((rc = upload_consts(h, C_AU, au)) || (rc = upload_consts(h, C_BU, bu)) || (rc = upload_consts(h, C_AL, al)) ||
+        (rc = upload_consts(h, C_BL, bl)) || (rc = upload_consts(h, C_AC, ac)) || (rc = upload_consts(h, C_BC, bc)) ||
+        (rc = upload_consts(h, C_RHO, rho)))
+        return rc;
+    CK(cudaMemcpyAsync(cptr(h, C_KB), kk.data(), B * 4 * 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(h->sgn.p, sg.data(), B * 2, cudaMemcpyHostToDevice, ctx->st));
+    // scalar vectors (and the next round's dots)
+    if ((rc = launch_fold_dots(h, 1))) return rc;
+    // generators
+    const size_t nN = (h->curN + 1) / 2, nM = (h->curM + 1) / 2;
+    PairFoldSeg segs[2] = {{1, (int)h->curN, 0}, {1 + (int)h->curN, (int)h->curM, (int)nN}};
+    const Affine* in = h->curp < 0 ? h->base.p : h->pts[h->curp].p;
+    size_t in_stride = h->curp < 0 ? 0 : h->P2;
+    int nxt = h->curp < 0 ? 0 : (h->curp ^ 1);
+    // both segments always launched (an empty segment contributes zero blocks) so that the
+    // [batch][2] layout of kb/ka/sgn holds
+    if ((rc = launch_pair_fold(ctx, in, in_stride, h->jscratch.p, nN + nM, segs, 2, cptr(h, C_KB), cptr(h, C_KA),
+                               h->sgn.p, B)))
+        return rc;
+    if ((rc = to_affine(ctx, h->jscratch.p, nN + nM, h->pts[nxt].p, h->P2, 1, (int)(nN + nM), B * (nN + nM))))
+        return rc;
+    h->curp = nxt;
+    h->cur ^= 1;
+    h->curN = nN;
+    h->curM = nM;
+    h->round++;
+    CK(cudaStreamSynchronize(ctx->st));   // host vectors above go out of scope
+    return BPPP_OK;
+}
+
+extern "C" int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    CK(cudaSetDevice(ctx->dev));
+    const size_t B = h->B;
+    std::vector<u256> hw(h->curN), hl(h->curM);
+    for (size_t b = 0; b < B; b++) {
+        if (s) host::to_bytes(s + 32 * b, fr::from_mont(h->s[b]));
+        if (w && h->curN) {
+            CK(cudaMemcpyAsync(hw.data(), h->w[h->cur].p + b * h->wstride[h->cur], h->curN * 32, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            for (size_t i = 0; i < h->curN; i++)
+                host::to_bytes(w + 32 * (b * h->curN + i), fr::from_mont(fr::mul(h->nn[b], hw[i])));
+        }
+        if (l && h->curM) {
+            CK(cudaMemcpyAsync(hl.data(), h->l[h->cur].p + b * h->lstride[h->cur], h->curM * 32, cudaMemcpyDeviceToHost, ctx->st));
+            CK(cudaStreamSynchronize(ctx->st));
+            for (size_t i = 0; i < h->curM; i++)
+                host::to_bytes(l + 32 * (b * h->curM + i), fr::from_mont(fr::mul(h->nl[b], hl[i])));
+        }
+    }
+    return BPPP_OK;
+}
+
+// =============================================================================== verifier
+extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, size_t k, const uint8_t* g,
+                              const uint8_t* G, const uint8_t* H, const uint8_t* q, const uint8_t* s_pub,
+                              const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR,
+                              size_t n_norm, size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init,
+                              const uint8_t* init_s, const uint8_t* init_p, int* ok) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_verify: only BPPP_ARG_NL is implemented on the device path");
+    if (!g || !q || !s_pub || !ok || batch == 0 || (N && (!G || !pub_w)) || (M && (!H || !c)) || (k && (!es || !XR)) ||
+        (n_norm && !fw) || (n_lin && !fl) || (n_init && (!init_s || !init_p)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_verify: null/empty argument");
+    if (k > 30) FAIL(BPPP_ERR_ARG, "too many rounds");
+    CK(cudaSetDevice(ctx->dev));
+    const size_t B = batch, P0 = 1 + N + M, NX = n_init + 2 * k;
+    if (!check_fq(g, 2) || !check_fq(G, 2 * N) || !check_fq(H, 2 * M) || !check_fq(XR, 4 * k * B) ||
+        !check_fq(init_p, 2 * n_init * B))
+        FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    if (!check_fr(q, B) || !check_fr(s_pub, B) || !check_fr(pub_w, B * N) || !check_fr(c, B * M) || !check_fr(es, B * k) ||
+        !check_fr(fw, B * n_norm) || !check_fr(fl, B * n_lin) || !check_fr(init_s, B * n_init))
+        FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    DBuf<Affine> base, extra, aff;
+    DBuf<u256> sc, xsc, pub, cm, vs_n, vs_l, f0n, f1, f0l, tmp;
+    DBuf<Jac> res;
+    CK(base.alloc(P0)); CK(extra.alloc(B * std::max<size_t>(NX, 1))); CK(aff.alloc(B));
+    CK(sc.alloc(B * P0)); CK(xsc.alloc(B * std::max<size_t>(NX, 1)));
+    CK(pub.alloc(B * N)); CK(cm.alloc(B * M)); CK(vs_n.alloc(B * n_norm)); CK(vs_l.alloc(B * n_lin));
+    CK(f0n.alloc(B * k)); CK(f1.alloc(B * k)); CK(f0l.alloc(B * k)); CK(res.alloc(B));
+    CK(tmp.alloc(std::max(B * N, B * M)));
+    CK(cudaMemcpyAsync(base.p, g, 64, cudaMemcpyHostToDevice, ctx->st));
+    if (N) CK(cudaMemcpyAsync(base.p + 1, G, N * 64, cudaMemcpyHostToDevice, ctx->st));
+    if (M) CK(cudaMemcpyAsync(base.p + 1 + N, H, M * 64, cudaMemcpyHostToDevice, ctx->st));
+    if (N) {
+        CK(cudaMemcpyAsync(tmp.p, pub_w, B * N * 32, cudaMemcpyHostToDevice, ctx->st));
+        k_fr_convert<<<(unsigned)((B * N + 255) / 256), 256, 0, ctx->st>>>(tmp.p, pub.p, B * N, 1);
+        CK(cudaGetLastError()); LAUNCHED(1);
+    }
+    // host: challenges, tensor factors, final-witness scalar sc  (NormArgument.hs:131-145, 73-81)
+    std::vector<u256> hf0n(B * k), hf1(B * k), hf0l(B * k, fr::one()), hvn(B * n_norm), hvl(B * n_lin);
+    std::vector<u256> scn(B), hx(B * std::max<size_t>(NX, 1)), hc(B * M);
+    std::vector<Affine> hp(B * std::max<size_t>(NX, 1));
+    for (size_t b = 0; b < B; b++) {
+        u256 qq = fr::to_mont(host::from_bytes(q + 32 * b));
+        for (size_t j = 0; j < k; j++) {
+            // round j+1's challenge is es[k-1-j] (newest first)
+            hf1[b * k + j] = fr::to_mont(host::from_bytes(es + 32 * (b * k + (k - 1 - j))));
+            hf0n[b * k + j] = qq;
+            qq = fr::sqr(qq);
+        }
+        u256 qF2 = fr::sqr(qq), wgt = qF2, acc = u256_zero();      // powers' (qF^2)
+        for (size_t i = 0; i < n_norm; i++) {
+            u256 v = fr::to_mont(host::from_bytes(fw + 32 * (b * n_norm + i)));
+            hvn[b * n_norm + i] = v;
+            acc = fr::add(acc, fr::mul(wgt, fr::sqr(v)));
+            wgt = fr::mul(wgt, qF2);
+        }
+        scn[b] = acc;
+        for (size_t i = 0; i < n_lin; i++) hvl[b * n_lin + i] = fr::to_mont(host::from_bytes(fl + 32 * (b * n_lin + i)));
+        for (size_t i = 0; i < M; i++) hc[b * M + i] = fr::to_mont(host::from_bytes(c + 32 * (b * M + i)));
+        // extra terms: initCom opening, then (e0, X), (e1, R) per round, newest first (verifyWith)
+        for (size_t i = 0; i < n_init; i++) {
+            hx[b * NX + i] = host::from_bytes(init_s + 32 * (b * n_init + i));
+            memcpy(&hp[b * NX + i], init_p + 64 * (b * n_init + i), 64);
+        }
+        for (size_t r = 0; r < k; r++) {
+            u256 e = fr::to_mont(host::from_bytes(es + 32 * (b * k + r)));
+            hx[b * NX + n_init + 2 * r] = fr::from_mont(e);
+            hx[b * NX + n_init + 2 * r + 1] = fr::from_mont(fr::sub(fr::sqr(e), fr::one()));
+            memcpy(&hp[b * NX + n_init + 2 * r], XR + 64 * ((b * k + r) * 2), 128);
+        }
+    }
+    if (k) {
+        CK(cudaMemcpyAsync(f0n.p, hf0n.data(), B * k * 32, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(f1.p, hf1.data(), B * k * 32, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(f0l.p, hf0l.data(), B * k * 32, cudaMemcpyHostToDevice, ctx->st));
+    }
+    if (n_norm) CK(cudaMemcpyAsync(vs_n.p, hvn.data(), B * n_norm * 32, cudaMemcpyHostToDevice, ctx->st));
+    if (n_lin) CK(cudaMemcpyAsync(vs_l.p, hvl.data(), B * n_lin * 32, cudaMemcpyHostToDevice, ctx->st));
+    if (NX) {
+        CK(cudaMemcpyAsync(xsc.p, hx.data(), B * NX * 32, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaMemcpyAsync(extra.p, hp.data(), B * NX * 64, cudaMemcpyHostToDevice, ctx->st));
+    }
+    if (N) {
+        TensorArgs A;
+        A.pub = pub.p; A.pub_stride = N; A.vs = vs_n.p; A.n_vs = (int)n_norm; A.f0 = f0n.p; A.f1 = f1.p; A.k = (int)k;
+        A.out = sc.p; A.out_stride = P0; A.off = 1; A.n = (int)N;
+        k_tensor_expand<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        CK(cudaGetLastError()); LAUNCHED(1);
+    }
+    std::vector<u256> tl(B * M);
+    if (M) {
+        TensorArgs A;
+        A.pub = nullptr; A.pub_stride = 0; A.vs = vs_l.p; A.n_vs = (int)n_lin; A.f0 = f0l.p; A.f1 = f1.p; A.k = (int)k;
+        A.out = sc.p; A.out_stride = P0; A.off = 1 + (int)N; A.n = (int)M;
+        k_tensor_expand<<<dim3((unsigned)((M + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        CK(cudaGetLastError()); LAUNCHED(1);
+        // sc_lin = sum_j c_j * tensor_j  (contract' . tensor', NormArgument.hs:75-78); the kernel wrote -tensor_j
+        CK(cudaMemcpy2DAsync(tl.data(), M * 32, sc.p + 1 + N, P0 * 32, M * 32, B, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    std::vector<u256> s0(B);
+    for (size_t b = 0; b < B; b++) {
+        u256 acc = scn[b];
+        for (size_t j = 0; j < M; j++) acc = fr::sub(acc, fr::mul(hc[b * M + j], fr::to_mont(tl[b * M + j])));
+        s0[b] = fr::from_mont(fr::sub(fr::to_mont(host::from_bytes(s_pub + 32 * b)), acc));
+    }
+    CK(cudaMemcpy2DAsync(sc.p, P0 * 32, s0.data(), 32, 32, B, cudaMemcpyHostToDevice, ctx->st));
+    MsmPlan plan;
+    plan.add(base.p, 0, sc.p, P0, 0, P0);
+    if (NX) plan.add(extra.p, NX, xsc.p, NX, 0, NX);
+    int rc = run_msm(ctx, plan, B, 1, res.p);
+    if (rc) return rc;
+    if ((rc = to_affine(ctx, res.p, 1, aff.p, 1, 0, 1, B))) return rc;
+    std::vector<Affine> out(B);
+    CK(cudaMemcpyAsync(out.data(), aff.p, B * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (size_t b = 0; b < B; b++) ok[b] = aff_is_inf(out[b]) ? 1 : 0;
+    return BPPP_OK;
+}
+
+// =============================================================================== debug
+extern "C" int bppp_dbg_field(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    if (!ctx || !a || !b || !out) return BPPP_ERR_ARG;
+    CK(cudaSetDevice(ctx->dev));
+    DBuf<u256> da, db, dc;
+    CK(da.alloc(n)); CK(db.alloc(n)); CK(dc.alloc(n));
+    CK(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, ctx->st));
+    k_dbg_field<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(da.p, db.p, dc.p, n, op);
+    CK(cudaGetLastError()); LAUNCHED(1);
+    CK(cudaMemcpyAsync(out, dc.p, n * 32, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+extern "C" int bppp_dbg_ec(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    if (!ctx || !a || !b || !out) return BPPP_ERR_ARG;
+    CK(cudaSetDevice(ctx->dev));
+    DBuf<Affine> da, db, dd;
+    DBuf<Jac> dc;
+    CK(da.alloc(n)); CK(db.alloc(n)); CK(dc.alloc(n)); CK(dd.alloc(n));
+    CK(cudaMemcpyAsync(da.p, a, n * 64, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(db.p, b, n * 64, cudaMemcpyHostToDevice, ctx->st));
+    k_dbg_ec<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(da.p, db.p, dc.p, n, op);
+    CK(cudaGetLastError()); LAUNCHED(1);
+    int rc = to_affine(ctx, dc.p, n, dd.p, n, 0, (int)n, n);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, dd.p, n * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}

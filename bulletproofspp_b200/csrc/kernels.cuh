@@ -1,0 +1,659 @@
+// Device kernels of the Bulletproofs++ argument hot path (sm_100a).  See DESIGN.md for the
+// data layout and the roofline that bounds each kernel.
+//
+//   k_fold_dots        K1  scalar-vector fold  x' = alpha*xL + beta*xR  fused with the next
+//                          round's weighted pair dots            (NormArgument.hs:113-129, 56-71)
+//   k_msm_scalars      K2  X / R opening scalars in MSM order    (NormArgument.hs:113-118)
+//   k_pair_fold        K3  generator fold  G' = b*GL + a*GR      (Commitment.hs:343-353, collapsePoints)
+//   k_msm_bucket       K4/K5 Pippenger bucket MSM, smem lists, warp-level bucket reduction
+//                                                                 (Commitment.hs:325-335, commit)
+//   k_msm_finish           window Horner + chunk combine
+//   k_batch_to_affine  K6  Montgomery batch inversion to affine  (Commitment.hs:151-154, BatchInverse.hs)
+//   k_tensor_expand    K7  verifier challenge tensor              (Bulletproof.hs:94-95, NormArgument.hs:131-145)
+#pragma once
+#include "ec.cuh"
+
+namespace bppp {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ u256 ld_u256(const u256* p) {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    uint4 a = q[0], b = q[1];
+    u256 r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void st_u256(u256* p, const u256& r) {
+    uint4* q = reinterpret_cast<uint4*>(p);
+    q[0] = make_uint4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    q[1] = make_uint4(r.v[4], r.v[5], r.v[6], r.v[7]);
+}
+__device__ __forceinline__ Affine ld_aff(const Affine* p) {
+    Affine r;
+    r.x = ld_u256(&p->x);
+    r.y = ld_u256(&p->y);
+    return r;
+}
+__device__ __forceinline__ void st_aff(Affine* p, const Affine& r) {
+    st_u256(&p->x, r.x);
+    st_u256(&p->y, r.y);
+}
+__device__ __forceinline__ Jac ld_jac(const Jac* p) {
+    Jac r;
+    r.X = ld_u256(&p->X);
+    r.Y = ld_u256(&p->Y);
+    r.Z = ld_u256(&p->Z);
+    return r;
+}
+__device__ __forceinline__ void st_jac(Jac* p, const Jac& r) {
+    st_u256(&p->X, r.X);
+    st_u256(&p->Y, r.Y);
+    st_u256(&p->Z, r.Z);
+}
+__device__ __forceinline__ u256 shfl_u256(const u256& a, int src) {
+    u256 r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, a.v[i], src);
+    return r;
+}
+__device__ __forceinline__ Jac shfl_jac(const Jac& a, int src) {
+    Jac r;
+    r.X = shfl_u256(a.X, src);
+    r.Y = shfl_u256(a.Y, src);
+    r.Z = shfl_u256(a.Z, src);
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// Fr <-> canonical conversion
+// ------------------------------------------------------------------------------------------
+__global__ void k_fr_convert(const u256* __restrict__ in, u256* __restrict__ out, size_t n, int to_mont) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u256 a = ld_u256(in + i);
+    st_u256(out + i, to_mont ? fr::to_mont(a) : fr::from_mont(a));
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: fused scalar fold + weighted pair dots.
+//
+// For proof p (blockIdx.y) and vectors u, v (v may alias u):
+//   FOLD:  yu_i = au*u_{2i} + bu*u_{2i+1}  (written to uo),  yv likewise (written to vo if v != u)
+//   dots over adjacent pairs (yL, yR) = (y_{2t}, y_{2t+1}) of the (folded) vectors, weight rho^t:
+//     d1 += rho^t * ( m1&1 ? uL*vR : 0  +  m1&2 ? uR*vL : 0  +  m1&4 ? uR*vR : 0 )
+//     d2 likewise with m2.
+// Each thread walks pairs t = t0, t0 + T, ... (T = total threads of the proof) with a running
+// weight w *= rho^T, so a warp reads 32 consecutive pairs per step.  Block partials go to
+// `partial[(p*gridDim.x + block)*2 + {0,1}]`.
+// Norm (NL):  u=v=w, m1 = 1 (wL*wR), m2 = 4 (wR^2), rho = q^4.   Linear (NL): u=c, v=l,
+// m1 = 3, m2 = 4, rho = 1.   IP: u=a, v=b, m1 = 1, m2 = 2, rho = q^2; linear m1 = 2, m2 = 1.
+// ------------------------------------------------------------------------------------------
+struct FoldDotsArgs {
+    const u256* u; const u256* v;       // inputs (Montgomery), per-proof stride in_stride
+    u256* uo; u256* vo;                 // folded outputs (only when fold != 0)
+    size_t in_stride, out_stride;
+    int n_in;                           // current length of u and v
+    int fold;                           // 0: dots of the inputs as they are; 1: fold then dots
+    const u256* au; const u256* bu;     // per proof (Montgomery)
+    const u256* av; const u256* bv;
+    const u256* rho;                    // per proof weight base (Montgomery); nullptr -> 1
+    int m1, m2;
+    u256* partial;                      // [batch][gridDim.x][2]
+};
+
+__device__ __forceinline__ u256 fr_pow(u256 base, unsigned e) {
+    u256 acc = fr::one();
+    while (e) {
+        if (e & 1u) acc = fr::mul(acc, base);
+        e >>= 1;
+        if (e) base = fr::sqr(base);
+    }
+    return acc;
+}
+
+__global__ void __launch_bounds__(256) k_fold_dots(FoldDotsArgs A) {
+    const int p = blockIdx.y;
+    const u256* u = A.u + (size_t)p * A.in_stride;
+    const u256* v = A.v + (size_t)p * A.in_stride;
+    const bool same = (A.u == A.v);
+    const int n_y = A.fold ? (A.n_in + 1) / 2 : A.n_in;   // length of the vectors the dots see
+    const int n_pairs = (n_y + 1) / 2;
+    const unsigned T = gridDim.x * blockDim.x;
+    const unsigned t0 = blockIdx.x * blockDim.x + threadIdx.x;
+
+    u256 au, bu, av, bv;
+    if (A.fold) {
+        au = ld_u256(A.au + p); bu = ld_u256(A.bu + p);
+        av = same ? au : ld_u256(A.av + p);
+        bv = same ? bu : ld_u256(A.bv + p);
+    }
+    u256 w = fr::one(), wstep = fr::one();
+    const bool weighted = (A.rho != nullptr);
+    if (weighted) {
+        u256 rho = ld_u256(A.rho + p);
+        w = fr_pow(rho, t0);
+        wstep = fr_pow(rho, T);
+    }
+    u256 d1 = u256_zero(), d2 = u256_zero();
+    const u256 zero = u256_zero();
+    for (unsigned t = t0; t < (unsigned)n_pairs; t += T) {
+        u256 uL, uR, vL, vR;
+        if (A.fold) {
+            size_t b = (size_t)4 * t;
+            u256 x0 = ld_u256(u + b);
+            u256 x1 = (b + 1 < (size_t)A.n_in) ? ld_u256(u + b + 1) : zero;
+            u256 x2 = (b + 2 < (size_t)A.n_in) ? ld_u256(u + b + 2) : zero;
+            u256 x3 = (b + 3 < (size_t)A.n_in) ? ld_u256(u + b + 3) : zero;
+            uL = fr::add(fr::mul(au, x0), fr::mul(bu, x1));
+            uR = fr::add(fr::mul(au, x2), fr::mul(bu, x3));
+            u256* uo = A.uo + (size_t)p * A.out_stride;
+            st_u256(uo + 2 * t, uL);
+            if (2 * t + 1 < (unsigned)n_y) st_u256(uo + 2 * t + 1, uR);
+            if (!same) {
+                u256 y0 = ld_u256(v + b);
+                u256 y1 = (b + 1 < (size_t)A.n_in) ? ld_u256(v + b + 1) : zero;
+                u256 y2 = (b + 2 < (size_t)A.n_in) ? ld_u256(v + b + 2) : zero;
+                u256 y3 = (b + 3 < (size_t)A.n_in) ? ld_u256(v + b + 3) : zero;
+                vL = fr::add(fr::mul(av, y0), fr::mul(bv, y1));
+                vR = fr::add(fr::mul(av, y2), fr::mul(bv, y3));
+                u256* vo = A.vo + (size_t)p * A.out_stride;
+                st_u256(vo + 2 * t, vL);
+                if (2 * t + 1 < (unsigned)n_y) st_u256(vo + 2 * t + 1, vR);
+            } else {
+                vL = uL; vR = uR;
+            }
+        } else {
+            size_t b = (size_t)2 * t;
+            uL = ld_u256(u + b);
+            uR = (b + 1 < (size_t)A.n_in) ? ld_u256(u + b + 1) : zero;
+            if (!same) {
+                vL = ld_u256(v + b);
+                vR = (b + 1 < (size_t)A.n_in) ? ld_u256(v + b + 1) : zero;
+            } else {
+                vL = uL; vR = uR;
+            }
+        }
+        u256 s1 = zero, s2 = zero;
+        u256 pLR, pRL, pRR;
+        const int need = A.m1 | A.m2;
+        if (need & 1) pLR = fr::mul(uL, vR);
+        if (need & 2) pRL = fr::mul(uR, vL);
+        if (need & 4) pRR = fr::mul(uR, vR);
+        if (A.m1 & 1) s1 = fr::add(s1, pLR);
+        if (A.m1 & 2) s1 = fr::add(s1, pRL);
+        if (A.m1 & 4) s1 = fr::add(s1, pRR);
+        if (A.m2 & 1) s2 = fr::add(s2, pLR);
+        if (A.m2 & 2) s2 = fr::add(s2, pRL);
+        if (A.m2 & 4) s2 = fr::add(s2, pRR);
+        if (weighted) {
+            s1 = fr::mul(s1, w);
+            s2 = fr::mul(s2, w);
+            w = fr::mul(w, wstep);
+        }
+        d1 = fr::add(d1, s1);
+        d2 = fr::add(d2, s2);
+    }
+    // block reduction (warp shuffle tree, then one warp over the per-warp sums)
+    __shared__ u256 red[2][8];
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        u256 o1, o2;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            o1.v[i] = __shfl_down_sync(0xffffffffu, d1.v[i], s);
+            o2.v[i] = __shfl_down_sync(0xffffffffu, d2.v[i], s);
+        }
+        d1 = fr::add(d1, o1);
+        d2 = fr::add(d2, o2);
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = d1; red[1][warp] = d2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int nw = blockDim.x >> 5;
+        for (int i = 1; i < nw; i++) { d1 = fr::add(d1, red[0][i]); d2 = fr::add(d2, red[1][i]); }
+        u256* out = A.partial + ((size_t)p * gridDim.x + blockIdx.x) * 2;
+        st_u256(out, d1);
+        st_u256(out + 1, d2);
+    }
+}
+
+// Finish: per proof, sX = sum_seg k1[seg][p] * sum_blocks partial1, sR likewise with k2.
+// Writes Montgomery values to res[p*2 + {0,1}] and canonical values to slot 0 of the X / R
+// MSM scalar vectors.
+struct DotsFinishArgs {
+    int n_seg;
+    const u256* partial[3];
+    int n_blocks[3];
+    const u256* k1[3];          // per proof Montgomery scale (nullptr -> 1)
+    const u256* k2[3];
+    u256* res;                  // [batch][2] Montgomery
+    u256* xs; u256* rs;         // MSM scalar vectors (canonical), slot 0 written; stride sc_stride
+    size_t sc_stride;
+    int batch;
+};
+__global__ void k_dots_finish(DotsFinishArgs A) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.batch) return;
+    u256 sx = u256_zero(), sr = u256_zero();
+    for (int s = 0; s < A.n_seg; s++) {
+        u256 a = u256_zero(), b = u256_zero();
+        const u256* part = A.partial[s] + (size_t)p * A.n_blocks[s] * 2;
+        for (int i = 0; i < A.n_blocks[s]; i++) {
+            a = fr::add(a, ld_u256(part + 2 * i));
+            b = fr::add(b, ld_u256(part + 2 * i + 1));
+        }
+        if (A.k1[s]) a = fr::mul(a, ld_u256(A.k1[s] + p));
+        if (A.k2[s]) b = fr::mul(b, ld_u256(A.k2[s] + p));
+        sx = fr::add(sx, a);
+        sr = fr::add(sr, b);
+    }
+    st_u256(A.res + 2 * (size_t)p, sx);
+    st_u256(A.res + 2 * (size_t)p + 1, sr);
+    st_u256(A.xs + (size_t)p * A.sc_stride, fr::from_mont(sx));
+    st_u256(A.rs + (size_t)p * A.sc_stride, fr::from_mont(sr));
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: opening scalars in MSM order.  For pair i of vector x (Montgomery) at output offset off:
+//   X[off+2i]   = kx[0]*xL + kx[1]*xR      X[off+2i+1] = kx[2]*xL + kx[3]*xR
+//   R[off+2i]   = kr[0]*xL + kr[1]*xR      R[off+2i+1] = kr[2]*xL + kr[3]*xR
+// coefficient kinds: 0 -> zero, 1 -> one, 2 -> per-proof value coef[p*8 + slot]  (slots 0..3 = kx,
+// 4..7 = kr).  Outputs are canonical integers (what the MSM's digit extraction wants).
+// ------------------------------------------------------------------------------------------
+struct MsmScalarsArgs {
+    const u256* x; size_t in_stride; int n_in;
+    u256* xs; u256* rs; size_t sc_stride; int off;
+    const u256* coef;           // [batch][8] Montgomery
+    unsigned char kind[8];
+};
+__device__ __forceinline__ u256 lin2(int k0, int k1, const u256& c0, const u256& c1, const u256& xL, const u256& xR) {
+    u256 a = u256_zero();
+    if (k0 == 1) a = xL; else if (k0 == 2) a = fr::mul(c0, xL);
+    if (k1 == 1) a = fr::add(a, xR); else if (k1 == 2) a = fr::add(a, fr::mul(c1, xR));
+    return fr::from_mont(a);
+}
+__global__ void __launch_bounds__(256) k_msm_scalars(MsmScalarsArgs A) {
+    const int p = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int n_pairs = (A.n_in + 1) / 2;
+    if (i >= n_pairs) return;
+    const u256* x = A.x + (size_t)p * A.in_stride;
+    u256 xL = ld_u256(x + 2 * i);
+    bool hasR = (2 * i + 1 < A.n_in);
+    u256 xR = hasR ? ld_u256(x + 2 * i + 1) : u256_zero();
+    u256 c[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) c[k] = (A.kind[k] == 2) ? ld_u256(A.coef + (size_t)p * 8 + k) : u256_zero();
+    u256* xs = A.xs + (size_t)p * A.sc_stride + A.off;
+    u256* rs = A.rs + (size_t)p * A.sc_stride + A.off;
+    st_u256(xs + 2 * i, lin2(A.kind[0], A.kind[1], c[0], c[1], xL, xR));
+    st_u256(rs + 2 * i, lin2(A.kind[4], A.kind[5], c[4], c[5], xL, xR));
+    if (hasR) {
+        st_u256(xs + 2 * i + 1, lin2(A.kind[2], A.kind[3], c[2], c[3], xL, xR));
+        st_u256(rs + 2 * i + 1, lin2(A.kind[6], A.kind[7], c[6], c[7], xL, xR));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: generator fold.  out[i] = sb*|b| * P[2i] + sa*|a| * P[2i+1]  with the SAME (a, b) for a whole
+// segment of one proof (the reference's collapsePoints / projectivePairIP, 129-bit a, b from
+// rationalReduceScalar).  One thread per output point; the joint sparse form of (|b|, |a|) is
+// computed once per block into shared memory, so the double-and-add chain is divergence-free.
+// Fast path: with PL, PR finite and xL != xR the four table entries PL, PR, PL+PR, PL-PR share the
+// denominator H = xR - xL, so the whole chain runs on the isomorphic curve (x,y)->(x H^2, y H^3)
+// where all four are affine (mixed adds only); Z is multiplied by H at the end.
+// Table entries live in shared memory, limb-major ([entry][limb][thread]) -> conflict-free.
+// ------------------------------------------------------------------------------------------
+#define PF_THREADS 128
+#define PF_MAXDIG 264
+struct PairFoldSeg {
+    int in_off, n_in, out_off;   // element offsets inside one proof's point vector
+};
+struct PairFoldArgs {
+    const Affine* in; size_t in_stride;     // in_stride 0: all proofs share the input vector
+    Jac* out; size_t out_stride;            // Jacobian scratch, per proof
+    PairFoldSeg seg[3];
+    int n_seg;
+    const u256* kb; const u256* ka;         // [batch][n_seg] magnitudes (canonical integers)
+    const unsigned char* sgn;               // [batch][n_seg] bit0: b negative, bit1: a negative
+    int blocks_per_seg[3];                  // prefix layout of blockIdx.x
+};
+
+__device__ __forceinline__ void tbl_store(uint32_t* tbl, int e, const Affine& p) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        tbl[(e * 16 + i) * PF_THREADS + threadIdx.x] = p.x.v[i];
+        tbl[(e * 16 + 8 + i) * PF_THREADS + threadIdx.x] = p.y.v[i];
+    }
+}
+__device__ __forceinline__ Affine tbl_load(const uint32_t* tbl, int e) {
+    Affine p;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        p.x.v[i] = tbl[(e * 16 + i) * PF_THREADS + threadIdx.x];
+        p.y.v[i] = tbl[(e * 16 + 8 + i) * PF_THREADS + threadIdx.x];
+    }
+    return p;
+}
+
+__global__ void __launch_bounds__(PF_THREADS) k_pair_fold(PairFoldArgs A) {
+    extern __shared__ uint32_t pf_smem[];
+    uint32_t* tbl = pf_smem;                                   // 4 * 16 * PF_THREADS words
+    __shared__ unsigned char dig[PF_MAXDIG];
+    __shared__ int ndig_s;
+    const int p = blockIdx.y;
+    int s = 0, blk = blockIdx.x;
+    while (s < A.n_seg - 1 && blk >= A.blocks_per_seg[s]) { blk -= A.blocks_per_seg[s]; s++; }
+    const PairFoldSeg sg = A.seg[s];
+    const int n_out = (sg.n_in + 1) / 2;
+    const unsigned char sgn = A.sgn[(size_t)p * A.n_seg + s];
+    if (threadIdx.x == 0) {
+        u256 kb = A.kb[(size_t)p * A.n_seg + s], ka = A.ka[(size_t)p * A.n_seg + s];
+        ndig_s = jsf_recode(dig, kb, ka, PF_MAXDIG);
+    }
+    __syncthreads();
+    const int ndig = ndig_s;
+    const int i = blk * PF_THREADS + threadIdx.x;
+    if (i >= n_out) return;
+    const Affine* in = A.in + (size_t)p * A.in_stride + sg.in_off;
+    Affine PL = aff_cneg(ld_aff(in + 2 * i), sgn & 1);
+    Affine PR = (2 * i + 1 < sg.n_in) ? aff_cneg(ld_aff(in + 2 * i + 1), (sgn >> 1) & 1) : aff_inf();
+    Jac acc = jac_inf();
+    const bool fast = !aff_is_inf(PL) && !aff_is_inf(PR) && !u256_eq(PL.x, PR.x);
+    u256 H = u256_one();
+    if (fast) {
+        H = fq::sub(PR.x, PL.x);
+        u256 HH = fq::sqr(H);
+        u256 HHH = fq::mul(H, HH);
+        Affine tL, tR, tS, tD;
+        tL.x = fq::mul(PL.x, HH);  tL.y = fq::mul(PL.y, HHH);      // PL on the isomorphic curve
+        tR.x = fq::mul(PR.x, HH);  tR.y = fq::mul(PR.y, HHH);
+        u256 rp = fq::sub(PR.y, PL.y);                               // PL + PR
+        u256 V2 = fq::dbl(tL.x);
+        tS.x = fq::sub(fq::sub(fq::sqr(rp), HHH), V2);
+        tS.y = fq::sub(fq::mul(rp, fq::sub(tL.x, tS.x)), tL.y);
+        u256 rm = fq::neg(fq::add(PR.y, PL.y));                      // PL - PR
+        tD.x = fq::sub(fq::sub(fq::sqr(rm), HHH), V2);
+        tD.y = fq::sub(fq::mul(rm, fq::sub(tL.x, tD.x)), tL.y);
+        tbl_store(tbl, 0, tL); tbl_store(tbl, 1, tR); tbl_store(tbl, 2, tS); tbl_store(tbl, 3, tD);
+    } else {
+        tbl_store(tbl, 0, PL); tbl_store(tbl, 1, PR);
+    }
+    for (int j = ndig - 1; j >= 0; j--) {
+        acc = jac_dbl(acc);
+        const int d = dig[j];
+        const int u0 = (d & 3) - 1, u1 = ((d >> 2) & 3) - 1;
+        if (u0 == 0 && u1 == 0) continue;
+        if (fast) {
+            int e; bool neg;
+            if (u1 == 0) { e = 0; neg = (u0 < 0); }
+            else if (u0 == 0) { e = 1; neg = (u1 < 0); }
+            else if (u0 == u1) { e = 2; neg = (u0 < 0); }
+            else { e = 3; neg = (u0 < 0); }
+            acc = jac_madd(acc, aff_cneg(tbl_load(tbl, e), neg));
+        } else {
+            if (u0) acc = jac_madd(acc, aff_cneg(tbl_load(tbl, 0), u0 < 0));
+            if (u1) acc = jac_madd(acc, aff_cneg(tbl_load(tbl, 1), u1 < 0));
+        }
+    }
+    if (fast && !jac_is_inf(acc)) acc.Z = fq::mul(acc.Z, H);
+    st_jac(A.out + (size_t)p * A.out_stride + sg.out_off + i, acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// K6: batch Jacobian -> affine with Montgomery's trick; each thread owns `chunk` consecutive
+// points.  Flat input index f -> proof f / n_per, element f % n_per; output goes to
+// out[proof*out_stride + out_off + element].  The prefix products are parked in out[].x.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_batch_to_affine(const Jac* __restrict__ in, size_t in_stride, Affine* out,
+                                                          size_t out_stride, int out_off, int n_per, size_t total,
+                                                          int chunk) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    size_t lo = t * chunk;
+    if (lo >= total) return;
+    size_t hi = lo + chunk < total ? lo + chunk : total;
+    u256 acc = u256_one();
+    for (size_t f = lo; f < hi; f++) {
+        size_t pr = f / n_per, el = f % n_per;
+        u256 z = ld_u256(&in[pr * in_stride + el].Z);
+        st_u256(&out[pr * out_stride + out_off + el].x, acc);
+        if (!u256_is_zero(z)) acc = fq::mul(acc, z);
+    }
+    u256 inv = fq::inv(acc);
+    for (size_t f = hi; f-- > lo;) {
+        size_t pr = f / n_per, el = f % n_per;
+        Jac P = ld_jac(&in[pr * in_stride + el]);
+        Affine* o = &out[pr * out_stride + out_off + el];
+        if (u256_is_zero(P.Z)) { st_aff(o, aff_inf()); continue; }
+        u256 pre = ld_u256(&o->x);
+        u256 zi = fq::mul(inv, pre);
+        inv = fq::mul(inv, P.Z);
+        u256 zi2 = fq::sqr(zi);
+        Affine r;
+        r.x = fq::mul(P.X, zi2);
+        r.y = fq::mul(P.Y, fq::mul(zi2, zi));
+        st_aff(o, r);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4/K5: bucket MSM.  One CTA = one chunk (<= MSM_MAX_CHUNK terms) of one (proof, output) MSM,
+// all W windows of C-bit signed digits.  Phases: (1) count digits per (window, bucket) with shared
+// atomics, (2) scan, (3) fill per-bucket lists of (term index | sign) in shared memory,
+// (4) one warp per window: lane b accumulates bucket b+1 with mixed adds straight from its list,
+// then the warp forms sum_b (b+1)*B_b with a shuffle suffix-scan + tree (10 Jacobian adds) and
+// lane 0 stores the window sum.  k_msm_finish combines chunks and runs the Horner over windows.
+// ------------------------------------------------------------------------------------------
+#define MSM_C 6
+#define MSM_NB 32                      // 2^(C-1) buckets = one warp
+#define MSM_W 43                       // floor(256/6) + 1 windows
+#define MSM_THREADS 256
+#define MSM_MAX_CHUNK 2048
+
+struct MsmSlice {
+    const Affine* pts; size_t pts_stride;      // per-proof stride (0 = shared by all proofs)
+    const u256* sc; size_t sc_stride;          // canonical scalars; + output * sc_out_stride
+    size_t sc_out_stride;
+    int n;                                     // terms in this chunk
+};
+struct MsmArgs {
+    const MsmSlice* slices;                    // [n_chunks]
+    int n_chunks;
+    Jac* partial;                              // [batch][n_out][n_chunks][MSM_W]
+    int n_out;
+};
+
+__global__ void __launch_bounds__(MSM_THREADS) k_msm_bucket(MsmArgs A) {
+    extern __shared__ unsigned char msm_smem[];
+    const int chunk = blockIdx.x, o = blockIdx.y, p = blockIdx.z;
+    const MsmSlice S = A.slices[chunk];
+    const int n = S.n;
+    const Affine* pts = S.pts + (size_t)p * S.pts_stride;
+    const u256* sc = S.sc + (size_t)p * S.sc_stride + (size_t)o * S.sc_out_stride;
+
+    unsigned* offs = reinterpret_cast<unsigned*>(msm_smem);              // [W*NB + 1]
+    unsigned* cur = offs + (MSM_W * MSM_NB + 1);                          // [W*NB]
+    unsigned short* list = reinterpret_cast<unsigned short*>(cur + MSM_W * MSM_NB);   // [n*W] worst case
+    const int NL = MSM_W * MSM_NB;
+
+    for (int i = threadIdx.x; i < NL; i += blockDim.x) cur[i] = 0;
+    __syncthreads();
+    // phase 1: count
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        u256 s = ld_u256(sc + i);
+        if (u256_is_zero(s)) continue;
+        int carry = 0;
+#pragma unroll 1
+        for (int j = 0; j < MSM_W; j++) {
+            int d = signed_digit(s, j, MSM_C, carry);
+            if (d) atomicAdd(&cur[j * MSM_NB + (d < 0 ? -d : d) - 1], 1u);
+        }
+    }
+    __syncthreads();
+    // phase 2: exclusive scan of NL counters (warp 0, 32 lanes x serial segments)
+    if (threadIdx.x < 32) {
+        const int per = (NL + 31) / 32;
+        int lo = threadIdx.x * per, hi = lo + per < NL ? lo + per : NL;
+        unsigned sum = 0;
+        for (int i = lo; i < hi; i++) sum += cur[i];
+        unsigned pre = sum;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, pre, s2);
+            if ((int)threadIdx.x >= s2) pre += v;
+        }
+        unsigned run = pre - sum;
+        for (int i = lo; i < hi; i++) { unsigned c = cur[i]; offs[i] = run; cur[i] = run; run += c; }
+        if (threadIdx.x == 31) offs[NL] = pre;
+    }
+    __syncthreads();
+    // phase 3: fill
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        u256 s = ld_u256(sc + i);
+        if (u256_is_zero(s)) continue;
+        int carry = 0;
+#pragma unroll 1
+        for (int j = 0; j < MSM_W; j++) {
+            int d = signed_digit(s, j, MSM_C, carry);
+            if (d) {
+                unsigned pos = atomicAdd(&cur[j * MSM_NB + (d < 0 ? -d : d) - 1], 1u);
+                list[pos] = (unsigned short)(i | (d < 0 ? 0x8000 : 0));
+            }
+        }
+    }
+    __syncthreads();
+    // phase 4: accumulate + reduce, one warp per window
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    Jac* outp = A.partial + (((size_t)p * A.n_out + o) * A.n_chunks + chunk) * MSM_W;
+    for (int j = warp; j < MSM_W; j += nwarps) {
+        const unsigned lo = offs[j * MSM_NB + lane], hi = offs[j * MSM_NB + lane + 1];
+        unsigned len = hi - lo;
+        unsigned maxlen = len;
+#pragma unroll
+        for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+            unsigned v = __shfl_xor_sync(0xffffffffu, maxlen, s2);
+            maxlen = v > maxlen ? v : maxlen;
+        }
+        Jac acc = jac_inf();
+        if (maxlen == 0) {
+            if (lane == 0) st_jac(outp + j, acc);
+            continue;
+        }
+        for (unsigned k = 0; k < maxlen; k++) {
+            if (k < len) {
+                unsigned e = list[lo + k];
+                Affine P = ld_aff(pts + (e & 0x7fffu));
+                if (e & 0x8000u) P.y = fq::neg(P.y);
+                acc = jac_madd(acc, P);
+            }
+        }
+        // suffix sums T_b = sum_{m >= b} B_m
+#pragma unroll 1
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            Jac other = shfl_jac(acc, (lane + s2) & 31);
+            if (lane + s2 < 32) acc = jac_add(acc, other);
+        }
+        // total = sum_b T_b
+#pragma unroll 1
+        for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+            Jac other = shfl_jac(acc, (lane + s2) & 31);
+            if (lane < s2) acc = jac_add(acc, other);
+        }
+        if (lane == 0) st_jac(outp + j, acc);
+    }
+}
+
+// One warp per (proof, output): lane j sums window j (and j+32) over the chunks, then lane 0 runs
+// the Horner  sum_j 2^(C*j) W_j  from the top window down.
+__global__ void __launch_bounds__(32) k_msm_finish(const Jac* __restrict__ partial, int n_chunks, Jac* out,
+                                                   size_t n_msm) {
+    __shared__ Jac win[MSM_W];
+    size_t m = blockIdx.x;
+    if (m >= n_msm) return;
+    const int lane = threadIdx.x;
+    for (int j = lane; j < MSM_W; j += 32) {
+        Jac acc = jac_inf();
+        for (int c = 0; c < n_chunks; c++) acc = jac_add(acc, ld_jac(partial + (m * n_chunks + c) * MSM_W + j));
+        win[j] = acc;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        Jac acc = win[MSM_W - 1];
+        for (int j = MSM_W - 2; j >= 0; j--) {
+#pragma unroll 1
+            for (int k = 0; k < MSM_C; k++) acc = jac_dbl(acc);
+            acc = jac_add(acc, win[j]);
+        }
+        st_jac(out + m, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K7: verifier challenge tensor.  out[p][off+i] = canonical( pub[p][i] - vs[p][i >> k] * prod_j
+// (bit_j(i) ? f1[p][j] : f0[p][j]) ), vs index >= n_vs -> product term is 0.  (tensor', LSB <-> round 1.)
+// ------------------------------------------------------------------------------------------
+struct TensorArgs {
+    const u256* pub; size_t pub_stride;        // Montgomery; nullptr -> 0
+    const u256* vs; int n_vs;                  // [batch][n_vs] Montgomery
+    const u256* f0; const u256* f1; int k;     // [batch][k] Montgomery
+    u256* out; size_t out_stride; int off;     // canonical
+    int n;
+};
+__global__ void __launch_bounds__(256) k_tensor_expand(TensorArgs A) {
+    const int p = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    u256 acc = A.pub ? ld_u256(A.pub + (size_t)p * A.pub_stride + i) : u256_zero();
+    int b = i >> A.k;
+    if (b < A.n_vs) {
+        u256 t = ld_u256(A.vs + (size_t)p * A.n_vs + b);
+        for (int j = 0; j < A.k; j++) {
+            const u256* f = ((i >> j) & 1) ? A.f1 : A.f0;
+            t = fr::mul(t, ld_u256(f + (size_t)p * A.k + j));
+        }
+        acc = fr::sub(acc, t);
+    }
+    st_u256(A.out + (size_t)p * A.out_stride + A.off + i, fr::from_mont(acc));
+}
+
+// ------------------------------------------------------------------------------------------
+// debug / self-test kernels (exercised by tests/ through bppp_dbg_*)
+// ------------------------------------------------------------------------------------------
+__global__ void k_dbg_field(const u256* a, const u256* b, u256* out, size_t n, int op) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u256 x = ld_u256(a + i), y = ld_u256(b + i), r;
+    switch (op) {
+        case 0: r = fq::mul(x, y); break;
+        case 1: r = fq::add(x, y); break;
+        case 2: r = fq::sub(x, y); break;
+        case 3: r = fq::inv(x); break;
+        case 4: r = fr::mul(x, y); break;      // Montgomery product x*y/R
+        case 5: r = fr::add(x, y); break;
+        case 6: r = fr::sub(x, y); break;
+        case 7: r = fr::to_mont(x); break;
+        case 8: r = fr::from_mont(x); break;
+        case 9: { uint32_t t[16]; mul_wide_portable(t, x, y); r = fq::reduce512(t); break; }
+        default: r = u256_zero();
+    }
+    st_u256(out + i, r);
+}
+__global__ void k_dbg_ec(const Affine* a, const Affine* b, Jac* out, size_t n, int op) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Affine x = ld_aff(a + i), y = ld_aff(b + i);
+    Jac r;
+    switch (op) {
+        case 0: r = jac_madd(jac_from_aff(x), y); break;
+        case 1: r = jac_dbl(jac_from_aff(x)); break;
+        case 2: r = jac_add(jac_dbl(jac_from_aff(x)), jac_madd(jac_from_aff(y), x)); break;
+        default: r = jac_inf();
+    }
+    st_jac(out + i, r);
+}
+
+}  // namespace bppp

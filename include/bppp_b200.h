@@ -1,0 +1,107 @@
+/* bppp_b200 -- C ABI of the B200-native Bulletproofs++ argument hot path.
+ *
+ * The reference (Liam-Eagen/BulletproofsPP, pure Haskell) has no FFI of its own: its "plugin
+ * API" is a set of typeclasses.  These entry points are what a `foreign import ccall` shim
+ * under those classes binds; each cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - scalars and coordinates are 32-byte LITTLE-endian canonical integers (< modulus);
+ *     Fr = secp256k1 group order, Fq = secp256k1 base field;
+ *   - an affine point is x||y (64 bytes); the identity is 64 zero bytes; output points are
+ *     affine and fully reduced (the transcript hashes decimal x, y of `toA`, app/Main.hs:78-80);
+ *   - every function returns 0 on success, non-zero on error (see bppp_last_error); nothing
+ *     throws across the ABI; the reference's own convention is Maybe/panic (app/Main.hs:155-169);
+ *   - caller owns every in/out buffer; the library owns device memory behind the opaque handles;
+ *   - results are a pure function of the inputs; calls are thread-safe per ctx/handle (each call
+ *     sets the device and uses the context's own stream), so they can be imported `safe` from
+ *     a -threaded GHC RTS (package.yaml:74-78);
+ *   - there is NO CPU fallback: without a CUDA device bppp_init fails.
+ */
+#ifndef BPPP_B200_H
+#define BPPP_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bppp_ctx bppp_ctx;
+typedef struct bppp_nl bppp_nl;
+
+enum { BPPP_OK = 0, BPPP_ERR_ARG = 1, BPPP_ERR_CUDA = 2, BPPP_ERR_RANGE = 3, BPPP_ERR_STATE = 4 };
+enum { BPPP_ARG_NL = 0, BPPP_ARG_IP = 1 };
+
+int bppp_init(int device, bppp_ctx** out);
+void bppp_free(bppp_ctx* ctx);
+const char* bppp_last_error(bppp_ctx* ctx);
+/* ABI version; bumped on any signature change */
+int bppp_abi_version(void);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t bppp_launch_count(bppp_ctx* ctx);
+/* block until every queued operation of the context has finished */
+int bppp_sync(bppp_ctx* ctx);
+
+/* ---- MSM seam: `commit` = `innerProduct . openToList` (src/Commitment.hs:416-417, 325-335),
+ * i.e. FastInnerProduct.innerProduct :: [(Scalar v, v)] -> v.  out = sum_i scalars[i] * points[i]. */
+int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t out[64]);
+/* `batch` independent MSMs of n terms each.  scalars: batch*n*32 bytes.  points: n*64 bytes when
+ * shared_points != 0 (the range-proof commitments over one generator list, commitRPW,
+ * src/RangeProof/Internal.hs:43-48), else batch*n*64.  out: batch*64. */
+int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8_t* scalars, const uint8_t* points,
+                   int shared_points, uint8_t* out);
+
+/* ---- generator fold: collapsePoints b a gL gR = projectivePairIP (b, gL) (a, gR)
+ * (src/Bulletproof.hs:213-214, src/Commitment.hs:343-353), for a whole vector with one (a, b):
+ * out[i] = (+-b)*in[2i] + (+-a)*in[2i+1]; an odd tail pairs with the identity.
+ * a, b: magnitudes (ReducedScalar), *_neg their signs.  points_in: n_in*64, points_out: ceil(n_in/2)*64. */
+int bppp_pair_fold(bppp_ctx* ctx, size_t n_in, const uint8_t a[32], int a_neg, const uint8_t b[32], int b_neg,
+                   const uint8_t* points_in, uint8_t* points_out);
+
+/* ---- rationalReduceScalar (src/Commitment.hs:242-255): host half-GCD, a = b*x (mod r), a^2 <= 2r */
+int bppp_rational_reduce(const uint8_t x[32], uint8_t a[32], int* a_neg, uint8_t b[32], int* b_neg);
+
+/* ---- Argument seam: a device-resident NormLinear argument state, lock-step over `batch` proofs.
+ * Replaces NormLinearBP / BPOpening (src/Bulletproof.hs:179-207, 276-291) for
+ * NL.NormLinear (src/Bulletproof/NormArgument.hs:153-178) when kind = BPPP_ARG_NL and
+ * IP.NormLinear (src/Bulletproof/InnerProductArgument.hs:239-267) when kind = BPPP_ARG_IP.
+ *
+ * bppp_nl_create = makeNormLinearBP' 1 q cs nss ngs lss lgs + makePSV sc g:
+ *   g (64), G (N*64), H (M*64): generators, shared by the whole batch;
+ *   per proof b: q[b] (for IP: the r with q = r^4), s[b] (scalar on g), w[b][N] (norm witness),
+ *   l[b][M] (linear witness), c[b][M] (public linear coefficients). */
+int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, const uint8_t* g, const uint8_t* G,
+                   const uint8_t* H, const uint8_t* q, const uint8_t* s, const uint8_t* w, const uint8_t* l,
+                   const uint8_t* c, bppp_nl** out);
+/* makeScalarsComs + the two `commit`s of proveRoundM (src/Bulletproof.hs:346-350):
+ * X[b], R[b] (64 bytes each; L, R for the IP argument). */
+int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R);
+/* the rest of proveRoundM (src/Bulletproof.hs:351-355): s' = s + e0*sX + e1*sR and `collapse e`
+ * (NormArgument.hs:64-71,123-129 / InnerProductArgument.hs:86-101,155-170) with challenge e[b]. */
+int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e);
+/* current lengths after the folds so far (norm vector length as `getWitness` reports it) */
+int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin);
+/* scalarCP s and getWitness (NormArgument.hs:62,121 / IPA.hs:154,222-223): s[b], w[b][n_norm], l[b][n_lin] */
+int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l);
+void bppp_nl_destroy(bppp_nl* h);
+
+/* verifyBPM's collapsed check (src/Bulletproof.hs:370-378, 362-368; expandChallenges
+ * NormArgument.hs:73-81,131-145 / IPA.hs:103-124,172-181) for `batch` proofs over shared
+ * generators: ok[b] = [ (s_pub - sc)*g + sum (pub_i - tensor_i)*G_i + sum (0 - tensor_j)*H_j
+ *                       + sum_k init_s[b][k]*init_p[b][k] + sum_rounds (e0*X + e1*R) == 0 ].
+ * es[b][k]: challenges NEWEST FIRST (as verifyBPM builds them); XR[b][k][2]: responses newest
+ * first; pub_w[b][N], s_pub[b]: public norm vector / scalar; c[b][M]: public linear coefficients;
+ * fw[b][n_norm], fl[b][n_lin]: the proof's final witness scalars; init_*: the opening of initCom. */
+int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, size_t k, const uint8_t* g,
+                   const uint8_t* G, const uint8_t* H, const uint8_t* q, const uint8_t* s_pub, const uint8_t* pub_w,
+                   const uint8_t* c, const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin,
+                   const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p,
+                   int* ok);
+
+/* ---- debug / self-test entry points used by tests/ (element-wise device arithmetic) */
+int bppp_dbg_field(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);
+int bppp_dbg_ec(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out /* n*64 affine */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,206 @@
+"""GPU parity tests (run on the B200 box): every device entry point of include/bppp_b200.h
+against the CPU oracle on the same seeded inputs.  Bit-exact: all arithmetic is integer."""
+import hashlib
+import random
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import bulletproof as obp
+from oracle.curve import Secp256k1 as G
+from oracle.field import Q, R, rational_reduce_scalar
+from oracle.transcript import ZKPT
+
+
+def H(*a):
+    return int.from_bytes(hashlib.sha256(repr(a).encode()).digest(), "big")
+
+
+def test_field_ops(ctx):
+    rnd = random.Random(1)
+    edge = [0, 1, 2, Q - 1, Q - 2, 2 ** 32 + 977, 2 ** 255, (1 << 256) - 1 - (2 ** 32 + 977)]
+    a = [x % Q for x in edge] + [rnd.randrange(Q) for _ in range(2000)]
+    b = [rnd.randrange(Q) for _ in range(len(edge))] + [rnd.randrange(Q) for _ in range(1990)] + [x % Q for x in edge] + [0, Q - 1]
+    assert ctx.dbg_field(0, a, b) == [x * y % Q for x, y in zip(a, b)]
+    assert ctx.dbg_field(9, a, b) == [x * y % Q for x, y in zip(a, b)]      # portable multiply on device
+    assert ctx.dbg_field(1, a, b) == [(x + y) % Q for x, y in zip(a, b)]
+    assert ctx.dbg_field(2, a, b) == [(x - y) % Q for x, y in zip(a, b)]
+    nz = [x or 1 for x in a[:200]]
+    assert ctx.dbg_field(3, nz, nz) == [pow(x, -1, Q) for x in nz]
+    ar = [x % R for x in a]
+    br = [x % R for x in b]
+    Ri = pow(1 << 256, -1, R)
+    assert ctx.dbg_field(4, ar, br) == [x * y * Ri % R for x, y in zip(ar, br)]
+    assert ctx.dbg_field(5, ar, br) == [(x + y) % R for x, y in zip(ar, br)]
+    assert ctx.dbg_field(6, ar, br) == [(x - y) % R for x, y in zip(ar, br)]
+    assert ctx.dbg_field(7, ar, br) == [(x << 256) % R for x in ar]
+    assert ctx.dbg_field(8, ar, br) == [x * Ri % R for x in ar]
+
+
+def test_ec_ops(ctx, gens):
+    pts = gens(40)
+    a, b = pts[:39], pts[1:40]
+    a2 = a + [pts[0], pts[0], None, pts[3], None]
+    b2 = b + [pts[0], G.neg(pts[0]), pts[1], None, None]
+    assert ctx.dbg_ec(0, a2, b2) == [G.add(x, y) for x, y in zip(a2, b2)]
+    assert ctx.dbg_ec(1, a2, b2) == [G.add(x, x) for x in a2]
+    assert ctx.dbg_ec(2, a, b) == [G.add(G.add(x, x), G.add(x, y)) for x, y in zip(a, b)]
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 100, 1286, 2048, 2049, 5000])
+def test_msm_matches_oracle(ctx, gens, n):
+    pts = gens(min(n, 1300))
+    pts = [pts[i % len(pts)] for i in range(n)]          # repeated bases are legal MSM input
+    sc = [H("msm", n, i) % R for i in range(n)]
+    if n > 3:
+        sc[1] = 0
+        sc[2] = R - 1
+        sc[3] = 1
+    assert ctx.msm(zip(sc, pts)) == G.msm(zip(sc, pts))
+
+
+def test_msm_edge_cases(ctx, gens):
+    pts = gens(8)
+    assert ctx.msm([(0, pts[0])]) is None
+    assert ctx.msm([(5, None), (0, pts[1])]) is None
+    assert ctx.msm([(1, pts[0]), (R - 1, pts[0])]) is None                   # P - P
+    assert ctx.msm([(1, pts[0]), (1, pts[0])]) == G.add(pts[0], pts[0])      # same bucket, same point
+    assert ctx.msm([(7, pts[0]), (7, G.neg(pts[0])), (3, pts[2])]) == G.mul(3, pts[2])
+    assert ctx.msm([(2 ** 255, pts[4]), (R - 2, pts[5])]) == G.msm([(2 ** 255, pts[4]), (R - 2, pts[5])])
+    # small scalars (range-proof digits < 256) and zero padding like commitRPW (Internal.hs:43-48)
+    small = [(i % 256, pts[i % 8]) for i in range(64)]
+    assert ctx.msm(small) == G.msm(small)
+    assert ctx.msm([]) is None
+
+
+def test_msm_batch_shared_and_private_points(ctx, gens):
+    pts = gens(70)
+    B, n = 5, 70
+    sc = [[H("b", b, i) % R for i in range(n)] for b in range(B)]
+    sc[2] = [0] * n
+    got = ctx.msm_batch(sc, pts, shared_points=True)
+    assert got == [G.msm(zip(sc[b], pts)) for b in range(B)]
+    priv = [[pts[(i + b) % n] for i in range(n)] for b in range(B)]
+    got = ctx.msm_batch(sc, priv, shared_points=False)
+    assert got == [G.msm(zip(sc[b], priv[b])) for b in range(B)]
+
+
+def test_rational_reduce(ctx):
+    rnd = random.Random(3)
+    for x in [0, 1, R - 1, 2 ** 128, 2 ** 129] + [rnd.randrange(R) for _ in range(200)]:
+        assert ctx.rational_reduce(x) == rational_reduce_scalar(x)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 128, 129, 643])
+def test_pair_fold_matches_collapse_points(ctx, gens, n):
+    pts = gens(n)
+    a, b = rational_reduce_scalar(H("e", n) % R)
+    got = ctx.pair_fold(a, b, pts)
+    exp = [G.msm([(b, pts[2 * i]), (a, pts[2 * i + 1] if 2 * i + 1 < n else None)]) for i in range((n + 1) // 2)]
+    assert got == exp
+
+
+def test_pair_fold_degenerate_pairs(ctx, gens):
+    p = gens(6)
+    pts = [p[0], p[0], p[1], G.neg(p[1]), None, p[2], p[3], None, None, None, p[4], p[5]]
+    for a, b in [(3, 5), (-(2 ** 128 + 12345), 2 ** 127 + 99), (0, 7), (9, 0), (1, 1)]:
+        exp = [G.msm([(b, pts[2 * i]), (a, pts[2 * i + 1])]) for i in range(len(pts) // 2)]
+        assert ctx.pair_fold(a, b, pts) == exp
+
+
+def _prove_device_vs_oracle(ctx, gens, N, M, B, rounds):
+    import bulletproofspp_b200 as bp
+    pts = gens(1 + N + M)
+    g, Gs, Hs = pts[0], pts[1:1 + N], pts[1 + N:]
+    q = [H("q", N, M, b) % R for b in range(B)]
+    s0 = [H("s", N, M, b) % R for b in range(B)]
+    w = [[H("w", b, i) % R for i in range(N)] for b in range(B)]
+    l = [[H("l", b, i) % R for i in range(M)] for b in range(B)]
+    c = [[H("c", b, i) % R for i in range(M)] for b in range(B)]
+    if N > 4:
+        w[0][3] = 0
+    arg = bp.NormLinearArgument(ctx, bp.ARG_NL, g, Gs, Hs, q, s0, w, l, c)
+    zks = [ZKPT(G) for _ in range(B)]
+    coms = [obp.PSV(s0[b], g, obp.NormLinear.make("NL", G, q[b], c[b], w[b], Gs, l[b], Hs)) for b in range(B)]
+    resp = [[] for _ in range(B)]
+    for r in range(rounds):
+        X, Rr = arg.round_commit()
+        es = []
+        for b in range(B):
+            tr = []
+            coms[b], xr = obp.prove_round(G, zks[b], coms[b], tr)
+            assert X[b] == tr[0]["X"], "X differs at round %d proof %d" % (r, b)
+            assert Rr[b] == tr[0]["R"], "R differs at round %d proof %d" % (r, b)
+            es.append(tr[0]["e"])
+            resp[b].insert(0, xr)
+        arg.round_fold(es)
+        assert arg.lengths() == coms[0].vec.lengths()
+    s, fw, fl = arg.final()
+    for b in range(B):
+        assert s[b] == coms[b].s
+        assert fw[b] == coms[b].vec.norm.get_witness()
+        assert fl[b] == coms[b].vec.lin.get_witness()
+    arg.close()
+    return pts, q, s0, w, l, c, resp, zks, (s, fw, fl)
+
+
+@pytest.mark.parametrize("N,M,B", [(16, 6, 2), (11, 6, 1), (37, 5, 3), (192, 2, 1), (8, 0, 2), (64, 261, 1)])
+def test_norm_argument_rounds_match_oracle(ctx, gens, N, M, B):
+    rounds = obp.optimal_witness_size("NL", N, max(M, 1))[0] if M else obp.number_rounds_reduce(N)[0]
+    _prove_device_vs_oracle(ctx, gens, N, M, B, max(rounds, 2))
+
+
+def test_norm_argument_128by64_shape_batch(ctx, gens):
+    """N = 1024, M = 261, 9 rounds: the 128by64 shape (lengths 261 -> 131 -> ... -> 1 -> 1)."""
+    _prove_device_vs_oracle(ctx, gens, 1024, 261, 2, 9)
+
+
+def test_verify_accepts_and_rejects(ctx, gens):
+    """Device verifier (tensor expansion + one MSM) on proofs whose relation holds by construction."""
+    import bulletproofspp_b200 as bp
+    N, M, B, k = 37, 5, 3, 4
+    pts = gens(1 + N + M)
+    g, Gs, Hs = pts[0], pts[1:1 + N], pts[1 + N:]
+    q = [H("vq", b) % R for b in range(B)]
+    w = [[H("vw", b, i) % R for i in range(N)] for b in range(B)]
+    l = [[H("vl", b, i) % R for i in range(M)] for b in range(B)]
+    c = [[H("vc", b, i) % R for i in range(M)] for b in range(B)]
+    nls = [obp.NormLinear.make("NL", G, q[b], c[b], w[b], Gs, l[b], Hs) for b in range(B)]
+    s0 = [nl.eval_scalar() for nl in nls]                       # relation s = |w|^2_q + <c, l>
+    # initCom = the commitment itself (pub = 0): verifier equation commit(init) - commit(wit) ...
+    arg = bp.NormLinearArgument(ctx, bp.ARG_NL, g, Gs, Hs, q, s0, w, l, c)
+    zks = [ZKPT(G) for _ in range(B)]
+    es = [[] for _ in range(B)]
+    xr = [[] for _ in range(B)]
+    for _ in range(k):
+        X, Rr = arg.round_commit()
+        e = [zks[b].oracle([X[b], Rr[b]])[0] for b in range(B)]
+        for b in range(B):
+            es[b].insert(0, e[b])
+            xr[b].insert(0, (X[b], Rr[b]))
+        arg.round_fold(e)
+    s, fw, fl = arg.final()
+    arg.close()
+    # C = s0*g + <w,G> + <l,H>;  the verifier checks  (0 - sc)*g - tensor.G - tensor.H + C + sum(e X + (e^2-1) R) = 0
+    C0 = [G.msm([(s0[b], g)] + list(zip(w[b], Gs)) + list(zip(l[b], Hs))) for b in range(B)]
+    zero_w = [[0] * N for _ in range(B)]
+    ok = ctx.nl_verify(bp.ARG_NL, g, Gs, Hs, q, [0] * B, zero_w, c, es, xr, fw, fl, [[(1, C0[b])] for b in range(B)])
+    assert ok == [True] * B
+    # oracle's verifier agrees on the same data
+    for b in range(B):
+        zk = ZKPT(G)
+        pub = obp.PSV(0, g, obp.NormLinear.make("NL", G, q[b], c[b], [0] * N, Gs, [], Hs))
+        basis = obp.PSV(0, g, obp.NormLinear.make("NL", G, q[b], c[b], [], Gs, [], Hs))
+        opening = obp.PSV(0, None, obp.NormLinear.make("NL", G, 1, [], fw[b], [], fl[b], []))
+        good, _ = obp.verify_bpm(G, zk, [(1, C0[b])], xr[b], pub, basis, opening)
+        assert good
+    # tamper: final witness, a response point, a challenge
+    fw_bad = [list(r) for r in fw]
+    fw_bad[1][0] = (fw_bad[1][0] + 1) % R
+    assert ctx.nl_verify(bp.ARG_NL, g, Gs, Hs, q, [0] * B, zero_w, c, es, xr, fw_bad, fl,
+                         [[(1, C0[b])] for b in range(B)]) == [True, False, True]
+    xr_bad = [list(r) for r in xr]
+    xr_bad[0][2] = (xr_bad[0][2][1], xr_bad[0][2][0])
+    assert ctx.nl_verify(bp.ARG_NL, g, Gs, Hs, q, [0] * B, zero_w, c, es, xr_bad, fw, fl,
+                         [[(1, C0[b])] for b in range(B)]) == [False, True, True]
