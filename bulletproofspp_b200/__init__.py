@@ -5,7 +5,7 @@ CUDA library built from csrc/.  There is no CPU fallback: importing works anywhe
 compute call needs the built library and a CUDA device and fails loudly otherwise.
 """
 from .lib import (BpppError, Context, NormLinearArgument, load_library, library_path, int_to_le, le_to_int,
-                  point_to_bytes, bytes_to_point, ARG_NL, ARG_IP)
+                  point_to_bytes, bytes_to_point, ARG_NL, ARG_IP, RangeProofSetup)
 
 __all__ = ["BpppError", "Context", "NormLinearArgument", "load_library", "library_path", "int_to_le", "le_to_int",
-           "point_to_bytes", "bytes_to_point", "ARG_NL", "ARG_IP"]
+           "point_to_bytes", "bytes_to_point", "ARG_NL", "ARG_IP", "RangeProofSetup"]

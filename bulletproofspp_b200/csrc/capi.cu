@@ -232,6 +232,61 @@ extern "C" int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const u
     return bppp_msm_batch(ctx, 1, n, scalars, points, 1, out);
 }
 
+// =============================================================================== fixed base
+struct bppp_fb {
+    bppp_ctx* ctx;
+    size_t n_bases;
+    DBuf<Affine> tbl;
+};
+extern "C" int bppp_fb_create(bppp_ctx* ctx, size_t n_bases, const uint8_t* points, bppp_fb** out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!out || !points || n_bases == 0 || n_bases > 16) FAIL(BPPP_ERR_ARG, "bppp_fb_create: bad argument");
+    *out = nullptr;
+    CK(cudaSetDevice(ctx->dev));
+    if (!check_fq(points, 2 * n_bases)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    bppp_fb* fb = new bppp_fb();
+    fb->ctx = ctx; fb->n_bases = n_bases;
+    size_t total = n_bases * FB_WINDOWS * FB_ENTRIES;
+    DBuf<Affine> d_b;
+    DBuf<Jac> d_j;
+    cudaError_t e;
+    if ((e = d_b.alloc(n_bases)) || (e = d_j.alloc(total)) || (e = fb->tbl.alloc(total))) {
+        delete fb;
+        ctx->err = cudaGetErrorString(e);
+        return BPPP_ERR_CUDA;
+    }
+    cudaMemcpyAsync(d_b.p, points, n_bases * 64, cudaMemcpyHostToDevice, ctx->st);
+    int nt = (int)(n_bases * FB_WINDOWS);
+    k_fb_build<<<(nt + 31) / 32, 32, 0, ctx->st>>>(d_b.p, (int)n_bases, d_j.p);
+    LAUNCHED(1);
+    int rc = to_affine(ctx, d_j.p, total, fb->tbl.p, total, 0, (int)total, total);
+    if (rc == 0 && (e = cudaStreamSynchronize(ctx->st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
+    if (rc) { delete fb; return rc; }
+    *out = fb;
+    return BPPP_OK;
+}
+extern "C" int bppp_fb_msm_batch(bppp_fb* fb, size_t batch, const uint8_t* scalars, uint8_t* out) {
+    if (!fb) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = fb->ctx;
+    if (!scalars || !out || batch == 0) FAIL(BPPP_ERR_ARG, "bppp_fb_msm_batch: null/empty argument");
+    CK(cudaSetDevice(ctx->dev));
+    if (!check_fr(scalars, batch * fb->n_bases)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    DBuf<u256> d_sc;
+    DBuf<Jac> d_res;
+    DBuf<Affine> d_aff;
+    CK(d_sc.alloc(batch * fb->n_bases)); CK(d_res.alloc(batch)); CK(d_aff.alloc(batch));
+    CK(cudaMemcpyAsync(d_sc.p, scalars, batch * fb->n_bases * 32, cudaMemcpyHostToDevice, ctx->st));
+    k_fb_msm<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->st>>>(fb->tbl.p, (int)fb->n_bases, d_sc.p, d_res.p, batch);
+    CK(cudaGetLastError());
+    LAUNCHED(1);
+    int rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, d_aff.p, batch * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+extern "C" void bppp_fb_destroy(bppp_fb* fb) { delete fb; }
+
 // =============================================================================== pair fold
 namespace {
 int launch_pair_fold(bppp_ctx* ctx, const Affine* in, size_t in_stride, Jac* out, size_t out_stride,

@@ -1,0 +1,1161 @@
+// Host side of the range-proof provers / verifiers, above the device C ABI.
+//
+// The reference keeps three things on the CPU and so does this file: the Fiat-Shamir transcript,
+// the round sequencing, and the range proofs' scalar phases.  Every elliptic-curve operation goes
+// to the GPU through bppp_msm_batch / bppp_nl_* (include/bppp_b200.h); there is no CPU group law
+// here.  Mirrors, with the same names and argument meaning:
+//   src/RangeProof/Internal.hs         RPWitness, commitRPW, blindWitness, blindErrWitness,
+//                                      blindBlindingTerm, makePolyTerms
+//   src/RangeProof/TypedReciprocal.hs  makeRangeData, digits, makePhase1s, makePhase2s,
+//                                      makeSharedCoeffs, makeErrorTerms, makePublicConsts,
+//                                      inputCoeffs, setup, witnessTRRP, proveTRRPM, verifyTRRPM
+//   src/RangeProof/Binary.hs           makeRangeData, makeDigits, makePublicConsts, inputCoeffs,
+//                                      setupBRP, witnessBRP, proveBRPM, verifyBRPM
+//   src/RangeProof.hs                  RangeProof.proveM / verifyM, infoRP
+//   src/Bulletproof.hs                 proveBPM / verifyBPM round loops, optimalWitnessSize
+// A batch of proofs runs in lock-step: host phases are spread over worker threads, each device
+// call covers the whole batch.
+#include <algorithm>
+#include <atomic>
+#include <map>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../../include/bppp_b200.h"
+#include "transcript.hpp"
+
+using namespace bppp;
+using h64::Fr;
+typedef __int128 I128;
+typedef unsigned __int128 U128;
+
+namespace {
+
+// ------------------------------------------------------------------------------ utilities
+int g_threads = 0;
+int n_threads() {
+    if (g_threads > 0) return g_threads;
+    unsigned h = std::thread::hardware_concurrency();
+    return h ? (int)h : 4;
+}
+template <class F>
+void parallel_for(size_t n, F fn) {
+    int nt = (int)std::min<size_t>(n, (size_t)n_threads());
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&]() {
+            for (;;) {
+                size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                fn(i);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
+I128 load_i128(const uint8_t b[16]) {
+    U128 v = 0;
+    for (int i = 15; i >= 0; i--) v = (v << 8) | b[i];
+    return (I128)v;
+}
+Fr fr_pow(Fr b, uint64_t e) { return h64::pow_u64(b, e); }
+int integer_log(U128 b, U128 n) {            // src/Utils.hs:91-92
+    int r = 0;
+    while (n >= b) { n /= b; r++; }
+    return r;
+}
+U128 ipow(U128 b, int e) {
+    U128 r = 1;
+    while (e-- > 0) r *= b;
+    return r;
+}
+
+// ------------------------------------------------------------------------------ RPWitness
+struct RPW {                                   // Internal.hs:22-41
+    Fr sc = h64::zero();
+    std::vector<Fr> lin, nrm;
+};
+void vadd(std::vector<Fr>& a, const std::vector<Fr>& b) {
+    if (b.size() > a.size()) a.resize(b.size(), h64::zero());
+    for (size_t i = 0; i < b.size(); i++) a[i] = h64::add(a[i], b[i]);
+}
+void rpw_add(RPW& a, const RPW& b) {
+    a.sc = h64::add(a.sc, b.sc);
+    vadd(a.lin, b.lin);
+    vadd(a.nrm, b.nrm);
+}
+RPW rpw_scale(const RPW& a, const Fr& s) {
+    RPW r;
+    r.sc = h64::mul(a.sc, s);
+    r.lin.resize(a.lin.size());
+    r.nrm.resize(a.nrm.size());
+    for (size_t i = 0; i < a.lin.size(); i++) r.lin[i] = h64::mul(a.lin[i], s);
+    for (size_t i = 0; i < a.nrm.size(); i++) r.nrm[i] = h64::mul(a.nrm[i], s);
+    return r;
+}
+
+// ------------------------------------------------------------------------------ setup
+struct Range {
+    I128 mn, mx;
+    U128 base = 2;
+    bool is_shared = false, is_output = false, is_assumed = false, has_bit = false;
+    std::vector<U128> coeffs;                  // baseCoeffs
+};
+struct Public {
+    I128 amount, type;
+    bool is_output;
+};
+// Phase1 entry (TypedReciprocal.hs:51-56).  kind: 'T' typing, 'I' inline, 'S' shared
+struct Ph1 {
+    char kind;
+    int ind;
+    U128 base = 0;
+    Fr b, s;                                   // public: digit coefficient, symbol
+    bool s_zero = true;
+    bool io = false, ia = false;
+    Fr d, m;                                   // private: digit (or type), multiplicity; for 'T' v in `m`
+};
+struct Ph2 {                                   // TypedReciprocal.hs:165-166
+    bool isT;
+    Fr d, m, u, v, r, c;
+};
+
+}  // namespace
+
+struct bppp_rp {
+    bppp_ctx* ctx = nullptr;
+    bool binary = false;
+    int arg = BPPP_ARG_NL;
+    bool flag = false;                         // TRRP: hasTypes (typed || conserved); Binary: conserved
+    std::vector<Range> rds;
+    std::vector<Public> pubs;
+    I128 net_pub = 0;                          // Binary: net public amount
+    int fmt = tr::PREFIXED_P, root = tr::ROOT_EXP;
+    std::string basis_seed;
+    std::vector<U128> m_bases, sorted_bases;
+    size_t nrm_len = 0, lin_len = 0, n_inputs = 0, num_rp_coms = 4;
+    size_t rounds = 0, prover_rounds = 0, fin_n = 0, fin_l = 0, prover_fin_n = 0, prover_fin_l = 0;
+    std::vector<Affine> pts;                   // h, g, then per kind
+    Affine g;
+    std::vector<uint8_t> table;                // [g | gs | hs] as bytes (device MSM base table)
+    std::vector<uint8_t> in_pts;               // TRRP: [g, hs0, hs1]; Binary: [g, h0]
+    bppp_fb* fb = nullptr;                     // fixed-base tables over in_pts
+    std::string err;
+};
+
+namespace {
+
+// ---- round counting (src/Bulletproof.hs:300-316, NormArgument.hs:165-178)
+size_t round_reduce(size_t n) { return n / 2 + n % 2; }
+void number_rounds_reduce(size_t n, size_t& r, size_t& out) {
+    r = 0;
+    while (n >= 5) { n = round_reduce(n); r++; }
+    out = n;
+}
+void optimal_witness_size_nl(size_t n_len, size_t l_len, size_t& rounds, size_t& fn, size_t& fl) {
+    size_t nR, n1, lR, l1;
+    number_rounds_reduce(n_len, nR, n1);
+    number_rounds_reduce(l_len, lR, l1);
+    size_t r = std::max(nR, lR);
+    for (size_t i = nR; i < r; i++) n1 = round_reduce(n1);
+    for (size_t i = lR; i < r; i++) l1 = round_reduce(l1);
+    if (n1 + l1 > 5) { rounds = r + 1; fn = round_reduce(n1); fl = round_reduce(l1); }
+    else { rounds = r; fn = n1; fl = l1; }
+}
+void lengths_after(size_t n, size_t l, size_t rounds, size_t& fn, size_t& fl) {
+    for (size_t i = 0; i < rounds; i++) { n = round_reduce(n); l = round_reduce(l); }
+    fn = n; fl = l;
+}
+
+// ---- TypedReciprocal.makeRangeData (TypedReciprocal.hs:89-115)
+bool make_range_trrp(Range& rd) {
+    if (!(rd.mx > rd.mn) || rd.base <= 1) return false;
+    U128 w = (U128)(rd.mx - rd.mn);
+    U128 b = rd.base;
+    int n1 = integer_log(b, w - 1);
+    rd.has_bit = ((w - 1) % (b - 1)) != 0;
+    std::vector<U128> tail;
+    for (int i = 1; i <= n1; i++) tail.push_back(ipow(b, n1 - i));
+    std::vector<U128> bs;
+    U128 bn = ipow(b, n1);
+    if (!rd.has_bit) bs.push_back((w - bn) / (b - 1));
+    else if (w < 2 * bn) bs.push_back(w - bn);
+    else {
+        U128 bn1 = 1 + w / (2 * (b - 1)) - (bn - 1) / (b - 1);
+        bs.push_back(w - bn1 * (b - 1) - bn);
+        bs.push_back(bn1);
+    }
+    bs.insert(bs.end(), tail.begin(), tail.end());
+    rd.coeffs = rd.is_assumed ? std::vector<U128>() : bs;
+    return true;
+}
+// ---- Binary.makeRangeData (Binary.hs:48-54)
+bool make_range_bin(Range& rd) {
+    if (!(rd.mx > rd.mn)) return false;
+    U128 w = (U128)(rd.mx - rd.mn);
+    int n1 = integer_log(2, w - 1);
+    rd.base = 2;
+    rd.coeffs.clear();
+    rd.coeffs.push_back(w - ipow(2, n1));
+    for (int i = 1; i <= n1; i++) rd.coeffs.push_back(ipow(2, n1 - i));
+    return true;
+}
+
+void finish_setup(bppp_rp* s) {
+    // device base table [g | gs | hs] and the generator triple of the input commitments
+    size_t P0 = 1 + s->nrm_len + s->lin_len;
+    s->table.resize(P0 * 64);
+    size_t hs_off, gs_off;
+    if (s->binary) { hs_off = 2; gs_off = 4; }                     // [h,g,h0,h1] ++ gs (Binary.hs:147-148)
+    else { hs_off = 2; gs_off = 2 + s->lin_len; }                  // h : g : hs ++ gs (TypedReciprocal.hs:334,348-349)
+    s->g = s->pts[1];
+    memcpy(&s->table[0], &s->pts[1], 64);
+    for (size_t i = 0; i < s->nrm_len; i++) memcpy(&s->table[64 * (1 + i)], &s->pts[gs_off + i], 64);
+    for (size_t i = 0; i < s->lin_len; i++) memcpy(&s->table[64 * (1 + s->nrm_len + i)], &s->pts[hs_off + i], 64);
+    if (s->binary) {             // value on g, blind on h0 (Internal.hs:53-54, app/Main.hs:315)
+        s->in_pts.resize(2 * 64);
+        memcpy(&s->in_pts[0], &s->pts[1], 64);
+        memcpy(&s->in_pts[64], &s->pts[2], 64);
+    } else {                     // value on g, type on hs[0] (= ht), blind on hs[1] (Internal.hs:56-57)
+        s->in_pts.resize(3 * 64);
+        memcpy(&s->in_pts[0], &s->pts[1], 64);
+        memcpy(&s->in_pts[64], &s->pts[2], 64);
+        memcpy(&s->in_pts[128], &s->pts[3], 64);
+    }
+}
+
+// scalars of commitRPW over the table [g | gs | hs] (Internal.hs:43-48; dotWith pads with zeros /
+// identity points, so entries beyond the generator lists contribute nothing)
+void commit_scalars(const bppp_rp* s, const RPW& w, uint8_t* out) {
+    size_t P0 = 1 + s->nrm_len + s->lin_len;
+    memset(out, 0, P0 * 32);
+    h64::to_bytes(out, w.sc);
+    for (size_t i = 0; i < w.nrm.size() && i < s->nrm_len; i++)
+        if (!w.nrm[i].is_zero()) h64::to_bytes(out + 32 * (1 + i), w.nrm[i]);
+    for (size_t i = 0; i < w.lin.size() && i < s->lin_len; i++)
+        if (!w.lin[i].is_zero()) h64::to_bytes(out + 32 * (1 + s->nrm_len + i), w.lin[i]);
+}
+
+std::vector<Fr> q_powers(const Fr& q, size_t n) {        // NL: powers' (q^2)  (NormArgument.hs:147-148)
+    return h64::powers1(h64::sqr(q), n);
+}
+
+// ---- blinding helpers (Internal.hs:134-195)
+std::vector<Fr> pad_right(size_t n, std::vector<Fr> xs) {
+    xs.resize(n, h64::zero());
+    return xs;
+}
+RPW blind_witness(tr::Zkpt& zk, int n, int k, const std::vector<Fr>& ls, const std::vector<Fr>& ns) {
+    int n_bls = (k == 1) ? 2 * n - 1 : 2 * n - k + 1;
+    std::vector<Fr> bls;
+    for (int i = 0; i < n_bls; i++) bls.push_back(zk.random());
+    bls.insert(bls.begin() + (2 * n - k), h64::zero());
+    bls = pad_right(2 * n + 1, bls);
+    RPW w;
+    w.sc = bls[0];
+    w.lin.assign(bls.begin() + 1, bls.end());
+    w.lin.insert(w.lin.end(), ls.begin(), ls.end());
+    w.nrm = ns;
+    return w;
+}
+RPW blind_err_witness(tr::Zkpt& zk, int n, const std::vector<Fr>& es, const std::vector<Fr>& ls, const std::vector<Fr>& ns) {
+    std::vector<Fr> bls;
+    for (int i = 0; i < n + 1; i++) bls.push_back(zk.random());
+    bls.insert(bls.begin() + n, h64::zero());
+    bls.insert(bls.end(), es.begin(), es.end());
+    bls = pad_right(2 * n + 1, bls);
+    RPW w;
+    w.sc = bls[0];
+    w.lin.assign(bls.begin() + 1, bls.end());
+    w.lin.insert(w.lin.end(), ls.begin(), ls.end());
+    w.nrm = ns;
+    return w;
+}
+std::vector<Fr> scale_errs(int n, const Fr& k, const std::vector<Fr>& xs) {
+    std::vector<Fr> o = xs;
+    for (size_t i = n + 1; i < xs.size() && i < (size_t)(n + 1 + n - 2); i++) o[i] = h64::mul(k, xs[i]);
+    return o;
+}
+RPW blind_blinding_term(const RPW& bl, const Fr& tC, const Fr& r0, const Fr& r0i, const Fr& r1, const Fr& r1i,
+                        const std::vector<Fr>& errs, const std::vector<const RPW*>& wits, const Fr& input_bl) {
+    (void)r0;
+    Fr blT = bl.lin[0];
+    Fr rs_inv = h64::mul(r0i, r1i);
+    int n = (int)wits.size();
+    const RPW* wit_err = wits[n - 1];
+    auto take = [](const std::vector<Fr>& v, size_t k) {
+        return std::vector<Fr>(v.begin(), v.begin() + std::min(k, v.size()));
+    };
+    std::vector<std::vector<Fr>> rows;
+    for (int i = 0; i < n - 1; i++) {
+        std::vector<Fr> r = {wits[i]->sc};
+        auto t = take(wits[i]->lin, 2 * n);
+        r.insert(r.end(), t.begin(), t.end());
+        rows.push_back(r);
+    }
+    {
+        std::vector<Fr> r = {wit_err->sc};
+        auto t = pad_right(2 * n, take(wit_err->lin, n + 1));
+        r.insert(r.end(), t.begin(), t.end());
+        rows.push_back(r);
+    }
+    for (auto& r : rows)
+        for (size_t i = 2; i < r.size(); i++) r[i] = h64::neg(r[i]);
+    std::vector<Fr> errs1;
+    errs1.push_back(h64::neg(h64::sub(errs[0], h64::mul(tC, blT))));
+    for (size_t i = 1; i < errs.size(); i++) errs1.push_back(h64::neg(h64::mul(rs_inv, errs[i])));
+    std::vector<std::vector<Fr>> table;
+    table.push_back(errs1);
+    Fr rs_tc = h64::mul(rs_inv, tC);
+    for (auto& r : rows) {
+        std::vector<Fr> a;
+        a.push_back(h64::add(h64::mul(rs_inv, r[0]), h64::mul(rs_tc, r[1])));      // addConsts
+        a.insert(a.end(), r.begin() + 2, r.end());
+        table.push_back(scale_errs(n, r1i, a));
+    }
+    for (auto& r : table) r.insert(r.begin() + std::min<size_t>(2 * n - 1, r.size()), h64::zero());   // insertAt (2n-1) 0
+    std::map<size_t, Fr> diag;                                                     // sumDiagonals
+    for (size_t a = 0; a < table.size(); a++)
+        for (size_t b = 0; b < table[a].size(); b++) {
+            auto it = diag.find(a + b);
+            if (it == diag.end()) diag[a + b] = table[a][b];
+            else it->second = h64::add(it->second, table[a][b]);
+        }
+    std::vector<Fr> sd;
+    for (auto& kv : diag) sd.push_back(kv.second);
+    sd.erase(sd.begin() + (2 * n - 1));                                            // removeAt (2n-1)
+    sd.resize(std::min<size_t>(sd.size(), 2 * n));                                 // take (2n)
+    std::vector<Fr> bl_errs = scale_errs(n, r1, sd);
+    bl_errs.back() = h64::sub(bl_errs.back(), h64::dbl(input_bl));                 // appLast
+    RPW out;
+    out.sc = h64::neg(bl_errs[0]);
+    out.lin.push_back(blT);
+    out.lin.insert(out.lin.end(), bl_errs.begin() + 1, bl_errs.end());
+    out.lin.insert(out.lin.end(), bl.lin.begin() + 1, bl.lin.end());
+    out.nrm = bl.nrm;
+    return out;
+}
+
+// ---- TRRP phases
+std::vector<U128> digits_trrp(const Range& rd, U128 n) {                // TypedReciprocal.hs:120-122
+    std::vector<U128> out;
+    for (size_t i = 0; i < rd.coeffs.size(); i++) {
+        U128 base = (rd.has_bit && i == 0) ? 2 : rd.base;
+        U128 b = rd.coeffs[i];
+        U128 d = b ? std::min<U128>(base - 1, n / b) : (base - 1);        // n `quot` 0 never happens for valid ranges
+        n -= d * b;
+        out.push_back(d);
+    }
+    return out;
+}
+// value (Fr canonical bytes) - min as a small integer; false when out of range
+bool adjust_value(const Range& rd, const uint8_t val[32], U128& n_adj) {
+    Fr v = h64::from_bytes(val);
+    Fr a = h64::sub(v, h64::from_i128(rd.mn));
+    uint64_t c[4];
+    h64::to_canon(c, a);
+    if (c[2] | c[3]) return false;
+    n_adj = ((U128)c[1] << 64) | c[0];
+    return n_adj < (U128)(rd.mx - rd.mn);
+}
+// makePhase1s (TypedReciprocal.hs:128-152); prover = false builds the verifier's empty-witness copy
+bool make_phase1s(int ind, const Range& rd, const uint8_t* val, bool prover, std::vector<Ph1>& out, bool& has_ms,
+                  std::vector<Fr>& ms_out) {
+    has_ms = false;
+    if (rd.is_assumed) return true;
+    std::vector<U128> ds;
+    if (prover) {
+        U128 n_adj;
+        if (!adjust_value(rd, val, n_adj)) return false;
+        ds = digits_trrp(rd, n_adj);
+    } else ds.assign(rd.coeffs.size(), 0);
+    size_t base = (size_t)rd.base;
+    std::vector<U128> ms;
+    if (prover) {
+        std::vector<U128> cnt(base, 0);
+        for (size_t i = rd.has_bit ? 1 : 0; i < ds.size(); i++)
+            if (ds[i] < base) cnt[(size_t)ds[i]]++;
+        if (rd.has_bit) ms.push_back(ds[0]);
+        for (size_t v = 1; v < base; v++) ms.push_back(cnt[v]);
+    } else ms.assign(base - 1 + (rd.has_bit ? 1 : 0), 0);
+    std::vector<U128> ns;
+    if (rd.has_bit) ns.push_back(1);
+    for (size_t v = 1; v < base; v++) ns.push_back(v);
+    auto base_at = [&](size_t i) { return (rd.has_bit && i == 0) ? (U128)2 : rd.base; };
+    if (rd.is_shared) {
+        for (size_t i = 0; i < rd.coeffs.size(); i++) {
+            Ph1 p;
+            p.kind = 'S'; p.ind = ind; p.base = base_at(i);
+            p.b = h64::from_u128(rd.coeffs[i]); p.d = h64::from_u128(ds[i]); p.m = h64::zero();
+            out.push_back(p);
+        }
+        has_ms = true;
+        ms_out.clear();
+        for (auto m : ms) ms_out.push_back(h64::from_u128(m));
+        return true;
+    }
+    size_t L = std::max(std::max(rd.coeffs.size(), ds.size()), std::max(ms.size(), ns.size()));
+    for (size_t i = 0; i < L; i++) {
+        Ph1 p;
+        p.kind = 'I'; p.ind = ind; p.base = base_at(i);
+        p.b = h64::from_u128(i < rd.coeffs.size() ? rd.coeffs[i] : 0);
+        p.d = h64::from_u128(i < ds.size() ? ds[i] : 0);
+        p.m = h64::from_u128(i < ms.size() ? ms[i] : 0);
+        U128 sym = i < ns.size() ? ns[i] : 0;
+        p.s = h64::from_u128(sym);
+        p.s_zero = (sym == 0);
+        out.push_back(p);
+    }
+    return true;
+}
+std::map<U128, Fr> make_base_map(const bppp_rp* s, const Fr& x) {     // TypedReciprocal.hs:353
+    std::map<U128, Fr> m;
+    Fr x2 = h64::sqr(x), cur = h64::mul(x2, x);
+    for (auto b : s->sorted_bases) { m[b] = cur; cur = h64::mul(cur, x2); }
+    return m;
+}
+// makePhase2s (TypedReciprocal.hs:171-195)
+std::vector<Ph2> make_phase2s(bool prover, const Fr& e, const Fr& e_inv, const Fr& x, std::map<U128, Fr>& bm,
+                              const std::vector<Ph1>& ph1s) {
+    size_t n = ph1s.size();
+    std::vector<Ph2> out(n);
+    std::vector<Fr> ds(n, h64::zero()), ss(n, h64::zero()), ps(n), vs(n);
+    Fr x2 = h64::sqr(x);
+    std::map<int, Fr> xpow;                      // x^(2(ind+1)) per range index
+    for (size_t i = 0; i < n; i++) {
+        const Ph1& p = ph1s[i];
+        auto it = xpow.find(p.ind);
+        if (it == xpow.end()) it = xpow.emplace(p.ind, fr_pow(x2, (uint64_t)p.ind + 1)).first;
+        const Fr& xp = it->second;
+        Ph2& o = out[i];
+        if (p.kind == 'T') {
+            Fr xpp = p.io ? h64::neg(x) : x;
+            if (prover) ds[i] = h64::add(e, p.d);
+            ps[i] = p.m;                                           // v
+            o.isT = true; o.d = p.d; o.m = h64::zero(); o.u = p.ia ? h64::zero() : xp; o.v = xpp;
+            vs[i] = xpp;
+        } else {
+            Fr xpp = bm[p.base];
+            if (prover) ds[i] = h64::add(e, p.d);
+            if (p.kind == 'I' && !p.s_zero) ss[i] = h64::add(e, p.s);
+            ps[i] = h64::one();
+            o.isT = false; o.d = p.d; o.m = (p.kind == 'I') ? p.m : h64::zero();
+            o.u = h64::mul(xp, p.b); o.v = xpp;
+            vs[i] = xpp;
+        }
+    }
+    if (prover) h64::batch_inv(ds.data(), n);
+    h64::batch_inv(ss.data(), n);
+    for (size_t i = 0; i < n; i++) {
+        out[i].r = prover ? h64::mul(ps[i], ds[i]) : h64::zero();
+        out[i].c = ss[i].is_zero() ? h64::zero() : h64::mul(vs[i], h64::sub(e_inv, ss[i]));
+    }
+    return out;
+}
+std::vector<Fr> make_shared_coeffs(const Fr& e, const Fr& e_inv, const std::vector<U128>& m_bases, std::map<U128, Fr>& bm) {
+    std::vector<Fr> xs, ss;                                          // TypedReciprocal.hs:204-206
+    for (auto b : m_bases)
+        for (U128 s = 1; s < b; s++) { xs.push_back(bm[b]); ss.push_back(h64::add(e, h64::from_u128(s))); }
+    h64::batch_inv(ss.data(), ss.size());
+    for (size_t i = 0; i < xs.size(); i++) xs[i] = h64::mul(xs[i], h64::sub(e_inv, ss[i]));
+    return xs;
+}
+std::vector<Fr> make_error_terms(const Fr& e, const Fr& xq, const std::vector<Fr>& shared_cs, const std::vector<Fr>& bls_ms,
+                                 const std::vector<Ph2>& ph2s, const std::vector<Fr>& q2s, const std::vector<Fr>& bls) {
+    std::vector<Fr> tot(6, h64::zero());                             // TypedReciprocal.hs:217-233
+    Fr aug = h64::zero();
+    for (size_t i = 0; i < shared_cs.size() && i < bls_ms.size(); i++) aug = h64::add(aug, h64::mul(shared_cs[i], bls_ms[i]));
+    tot[3] = h64::dbl(aug);
+    using namespace h64;
+    for (size_t i = 0; i < ph2s.size() && i < q2s.size() && i < bls.size(); i++) {
+        const Ph2& o = ph2s[i];
+        const Fr& q2 = q2s[i];
+        const Fr& bl = bls[i];
+        Fr rC = o.isT ? mul(xq, add(o.u, q2)) : o.u;
+        Fr dC = add(o.v, mul(q2, e));
+        Fr qd = add(mul(q2, o.d), dC), qr = add(mul(q2, o.r), rC);
+        Fr q2bl = mul(q2, bl);
+        tot[0] = add(tot[0], mul(q2bl, bl));
+        tot[1] = add(tot[1], dbl(mul(q2bl, o.m)));
+        tot[2] = add(tot[2], add(mul(q2, sqr(o.m)), dbl(mul(bl, qd))));
+        tot[3] = add(tot[3], dbl(add(mul(bl, qr), mul(o.m, qd))));
+        tot[4] = add(tot[4], add(add(mul(q2, sqr(o.d)), dbl(mul(o.d, dC))), dbl(add(mul(bl, o.c), mul(o.m, qr)))));
+        tot[5] = add(tot[5], add(add(mul(q2, sqr(o.r)), dbl(mul(o.r, rC))), dbl(mul(o.c, o.d))));
+    }
+    return tot;
+}
+RPW make_public_consts_trrp(const bppp_rp* s, const Fr& e, const Fr& e_inv, const Fr& x, const Fr& xq, const Fr& q0,
+                            const Fr& q0_inv, const Fr& t, const std::vector<Ph2>& ph2s) {
+    using namespace h64;                                             // TypedReciprocal.hs:236-263
+    Fr t2 = sqr(t), t3 = mul(t2, t), t4 = sqr(t2), t5 = mul(t4, t);
+    Fr x2 = sqr(x), xp = x2, acc = zero();
+    for (auto& rd : s->rds) {
+        if (!rd.is_assumed) acc = add(acc, mul(from_i128(rd.mn), xp));
+        xp = mul(xp, x2);
+    }
+    Fr two_t5 = dbl(t5);
+    Fr z = neg(mul(two_t5, acc));
+    if (s->flag) {
+        std::vector<Fr> rs;
+        for (auto& p : s->pubs) rs.push_back(add(e, from_i128(p.type)));
+        batch_inv(rs.data(), rs.size());
+        Fr sum = zero();
+        for (size_t i = 0; i < s->pubs.size(); i++) {
+            Fr term = mul(rs[i], from_i128(s->pubs[i].amount));
+            sum = s->pubs[i].is_output ? sub(sum, term) : add(sum, term);
+        }
+        z = sub(z, mul(mul(two_t5, x), sum));
+    }
+    RPW out;
+    Fr q2 = q0, qi2 = q0_inv, ts0 = zero();
+    for (auto& o : ph2s) {
+        Fr rC, p2C;
+        if (o.isT) { rC = mul(xq, add(mul(qi2, o.u), one())); p2C = zero(); }
+        else { rC = mul(qi2, o.u); p2C = dbl(add(q2, mul(e_inv, o.v))); }
+        Fr p = add(add(mul(t2, add(e, mul(qi2, o.v))), mul(t3, rC)), mul(t4, mul(qi2, o.c)));
+        ts0 = add(ts0, add(mul(q2, sqr(p)), mul(t5, p2C)));
+        out.nrm.push_back(p);
+        q2 = mul(q2, q0);
+        qi2 = mul(qi2, q0_inv);
+    }
+    out.sc = add(z, ts0);
+    return out;
+}
+std::vector<Fr> input_coeffs_trrp(const bppp_rp* s, const Fr& x, const Fr& q0) {   // TypedReciprocal.hs:325-328
+    std::vector<Fr> out;
+    Fr x2 = h64::sqr(x), xp = x2, qp = q0;
+    for (auto& rd : s->rds) {
+        Fr v = rd.is_assumed ? h64::zero() : xp;
+        if (s->flag) v = h64::add(qp, v);
+        out.push_back(v);
+        xp = h64::mul(xp, x2);
+        qp = h64::mul(qp, q0);
+    }
+    return out;
+}
+std::vector<Fr> make_bp_coeffs(bool has_types, const Fr& xq, const Fr& r0, const Fr& r1, const Fr& t, const std::vector<Fr>& cs) {
+    using namespace h64;                                             // TypedReciprocal.hs:391-396
+    Fr rs = mul(r0, r1), t2 = sqr(t), t3 = mul(t2, t), t4 = sqr(t2), t6 = sqr(t3);
+    std::vector<Fr> o = {has_types ? neg(xq) : zero(), mul(rs, t), mul(rs, t2), mul(rs, t3), mul(r0, t4), mul(rs, t6)};
+    Fr two_t3 = dbl(t3);
+    for (auto& c : cs) o.push_back(mul(two_t3, c));
+    return o;
+}
+std::vector<Ph1> ph1s_verifier(const bppp_rp* s) {
+    std::vector<Ph1> out;
+    if (s->flag)
+        for (size_t i = 0; i < s->rds.size(); i++) {
+            Ph1 p;
+            p.kind = 'T'; p.ind = (int)i; p.io = s->rds[i].is_output; p.ia = s->rds[i].is_assumed;
+            p.d = p.m = h64::zero();
+            out.push_back(p);
+        }
+    for (size_t i = 0; i < s->rds.size(); i++) {
+        bool hm;
+        std::vector<Fr> ms;
+        make_phase1s((int)i, s->rds[i], nullptr, false, out, hm, ms);
+    }
+    return out;
+}
+
+// ---- Binary phases
+std::vector<Fr> input_coeffs_brp(const bppp_rp* s, const Fr& x) {     // Binary.hs:128-130
+    std::vector<Fr> out;
+    Fr x2 = h64::sqr(x), xp = x2;
+    for (auto& rd : s->rds) {
+        Fr v = rd.is_assumed ? h64::zero() : xp;
+        if (s->flag) v = h64::add(v, rd.is_output ? h64::neg(x) : x);
+        out.push_back(v);
+        xp = h64::mul(xp, x2);
+    }
+    return out;
+}
+RPW public_consts_brp(const bppp_rp* s, const Fr& x, const Fr& q0, const Fr& q0_inv) {   // Binary.hs:73-97
+    using namespace h64;
+    Fr x2 = sqr(x), xp = x2, macc = zero();
+    std::vector<Fr> bss;
+    for (auto& rd : s->rds) {
+        if (!rd.is_assumed) {
+            for (auto b : rd.coeffs) bss.push_back(mul(xp, from_u128(b)));
+            macc = add(macc, mul(from_i128(rd.mn), xp));
+        }
+        xp = mul(xp, x2);
+    }
+    Fr net = s->flag ? mul(neg(x), from_i128(s->net_pub)) : zero();
+    Fr z = neg(dbl(add(net, macc)));
+    Fr half = inv(from_u64(2));
+    RPW out;
+    Fr q2 = q0, q2i = q0_inv, sc = z;
+    for (auto& bx : bss) {
+        Fr p = sub(mul(bx, q2i), half);
+        sc = add(sc, mul(q2, sqr(p)));
+        q2 = mul(q2, q0);
+        q2i = mul(q2i, q0_inv);
+        out.nrm.push_back(p);
+    }
+    out.sc = sc;
+    return out;
+}
+
+// ------------------------------------------------------------------------------ batch state
+struct Proof {
+    tr::Zkpt zk;
+    std::vector<Ph1> ph1s;
+    std::vector<std::pair<U128, std::vector<Fr>>> base_mss;
+    std::vector<RPW> n_wits;
+    RPW dm, m, r, bl, d;
+    std::vector<Ph2> ph2s;
+    Fr e, x, r0, q, xq, r1, q0, t, e_inv, r0_inv, q_inv, q0_inv, r1_inv;
+    std::vector<Fr> shared_cs, cs, bls_lin, bls_nrm;
+    std::map<U128, Fr> base_map;
+    RPW pub, wit;
+    Fr s_bl;
+    bool ok = true;
+};
+
+int fail(bppp_rp* s, int code, const std::string& msg) {
+    s->err = msg;
+    return code;
+}
+const char* ctx_err(bppp_rp* s) { return bppp_last_error(s->ctx); }
+
+// run the argument (proveBPM, src/Bulletproof.hs:357-359) for the whole batch
+int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::vector<uint8_t>& q, const std::vector<uint8_t>& sc,
+                 const std::vector<uint8_t>& w, const std::vector<uint8_t>& l, const std::vector<uint8_t>& c,
+                 uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l) {
+    const size_t B = P.size(), N = s->nrm_len, M = s->lin_len;
+    bppp_nl* h = nullptr;
+    int rc = bppp_nl_create(s->ctx, s->arg, B, N, M, &s->table[0], &s->table[64], &s->table[64 * (1 + N)], q.data(), sc.data(),
+                            w.data(), l.data(), c.data(), &h);
+    if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(s));
+    std::vector<uint8_t> X(B * 64), R(B * 64), E(B * 32);
+    for (size_t r = 0; r < rounds; r++) {
+        rc = bppp_nl_round_commit(h, X.data(), R.data());
+        if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_commit: ") + ctx_err(s)); }
+        parallel_for(B, [&](size_t b) {
+            uint8_t xr[128];
+            memcpy(xr, &X[64 * b], 64);
+            memcpy(xr + 64, &R[64 * b], 64);
+            Fr e;
+            P[b].zk.oracle(xr, 2, &e, 1);                           // e <- head <$> oracle [ac, bc]
+            h64::to_bytes(&E[32 * b], e);
+            // responses are consed: newest first (Bulletproof.hs:357-359)
+            memcpy(responses + 128 * (b * rounds + (rounds - 1 - r)), xr, 128);
+        });
+        rc = bppp_nl_round_fold(h, E.data());
+        if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_fold: ") + ctx_err(s)); }
+    }
+    size_t cn = 0, cl = 0;
+    bppp_nl_lengths(h, &cn, &cl);
+    if (cn != fin_n || cl != fin_l) { bppp_nl_destroy(h); return fail(s, BPPP_ERR_STATE, "final witness lengths differ from infoRP"); }
+    std::vector<uint8_t> fs(B * 32), fw(B * cn * 32), fl(B * cl * 32);
+    rc = bppp_nl_final(h, fs.data(), fw.data(), fl.data());
+    bppp_nl_destroy(h);
+    if (rc) return fail(s, rc, std::string("bppp_nl_final: ") + ctx_err(s));
+    for (size_t b = 0; b < B; b++) {       // getWitness: norm scalars then linear scalars (RangeProof.hs:65)
+        memcpy(finals + 32 * b * (cn + cl), &fw[32 * b * cn], 32 * cn);
+        memcpy(finals + 32 * (b * (cn + cl) + cn), &fl[32 * b * cl], 32 * cl);
+    }
+    return BPPP_OK;
+}
+
+}  // namespace
+
+// =================================================================================== C ABI
+extern "C" {
+
+void bppp_set_host_threads(int n) { g_threads = n; }
+
+int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserved, const char* basis_seed, int show_format,
+                  int root_policy, size_t n_ranges, const bppp_range_spec* ranges, size_t n_pub, const bppp_public_spec* pubs,
+                  bppp_rp** out) {
+    if (!ctx || !out || !basis_seed || (n_ranges && !ranges) || (n_pub && !pubs)) return BPPP_ERR_ARG;
+    *out = nullptr;
+    bppp_rp* s = new bppp_rp();
+    s->ctx = ctx; s->binary = binary != 0; s->arg = arg_kind; s->flag = typed_or_conserved != 0;
+    s->fmt = show_format; s->root = root_policy; s->basis_seed = basis_seed;
+    s->n_inputs = n_ranges;
+    for (size_t i = 0; i < n_ranges; i++) {
+        Range rd;
+        rd.mn = load_i128(ranges[i].min); rd.mx = load_i128(ranges[i].max); rd.base = ranges[i].base;
+        rd.is_shared = ranges[i].is_shared; rd.is_output = ranges[i].is_output; rd.is_assumed = ranges[i].is_assumed;
+        bool ok = s->binary ? make_range_bin(rd) : make_range_trrp(rd);
+        if (!ok) { delete s; return BPPP_ERR_RANGE; }
+        s->rds.push_back(rd);
+    }
+    for (size_t i = 0; i < n_pub; i++) {
+        Public p;
+        p.amount = load_i128(pubs[i].amount); p.type = load_i128(pubs[i].type); p.is_output = pubs[i].is_output;
+        s->pubs.push_back(p);
+        s->net_pub += p.is_output ? -p.amount : p.amount;                 // app/Main.hs:314
+    }
+    size_t need;
+    if (s->binary) {                                                      // setupBRP (Binary.hs:143-156)
+        s->num_rp_coms = 2;
+        s->nrm_len = 0;
+        for (auto& rd : s->rds) s->nrm_len += rd.coeffs.size();
+        s->lin_len = 2;
+        need = 4 + s->nrm_len;
+    } else {                                                              // setup (TypedReciprocal.hs:332-359)
+        s->num_rp_coms = 4;
+        bool any_bit = false, any_shared_bit = false;
+        std::set<U128> mb, sb;
+        for (auto& rd : s->rds) {
+            if (rd.is_assumed) continue;
+            any_bit |= rd.has_bit;
+            any_shared_bit |= (rd.has_bit && rd.is_shared);
+            sb.insert(rd.base);
+            if (rd.is_shared) mb.insert(rd.base);
+        }
+        if (any_shared_bit) mb.insert(2);
+        if (any_bit) sb.insert(2);
+        s->m_bases.assign(mb.begin(), mb.end());
+        s->sorted_bases.assign(sb.begin(), sb.end());
+        s->nrm_len = 0;
+        for (auto& rd : s->rds) s->nrm_len += rd.coeffs.size() + (s->flag ? 1 : 0);
+        s->lin_len = 6;
+        for (auto b : s->m_bases) s->lin_len += (size_t)(b - 1);
+        need = 2 + s->lin_len + s->nrm_len;
+    }
+    s->pts = tr::get_points(s->basis_seed, need, s->root);
+    optimal_witness_size_nl(s->nrm_len, s->lin_len, s->rounds, s->fin_n, s->fin_l);
+    if (s->binary) {                       // the prover's own rule (Binary.hs:195)
+        s->prover_rounds = (size_t)std::max(0, integer_log(2, s->nrm_len) - 1);
+        lengths_after(s->nrm_len, s->lin_len, s->prover_rounds, s->prover_fin_n, s->prover_fin_l);
+    } else {
+        s->prover_rounds = s->rounds; s->prover_fin_n = s->fin_n; s->prover_fin_l = s->fin_l;
+    }
+    finish_setup(s);
+    int rc = bppp_fb_create(ctx, s->in_pts.size() / 64, s->in_pts.data(), &s->fb);
+    if (rc) { delete s; return rc; }
+    *out = s;
+    return BPPP_OK;
+}
+void bppp_rp_free(bppp_rp* s) {
+    if (!s) return;
+    bppp_fb_destroy(s->fb);
+    delete s;
+}
+const char* bppp_rp_last_error(bppp_rp* s) { return s ? s->err.c_str() : "null setup"; }
+
+// infoRP (TypedReciprocal.hs:292, Binary.hs:120) + optimalWitnessSize: shape of a proof
+int bppp_rp_info(bppp_rp* s, size_t* n_inputs, size_t* num_rp_coms, size_t* nrm_len, size_t* lin_len, size_t* rounds,
+                 size_t* fin_norm, size_t* fin_lin) {
+    if (!s) return BPPP_ERR_ARG;
+    if (n_inputs) *n_inputs = s->n_inputs;
+    if (num_rp_coms) *num_rp_coms = s->num_rp_coms;
+    if (nrm_len) *nrm_len = s->nrm_len;
+    if (lin_len) *lin_len = s->lin_len;
+    if (rounds) *rounds = s->prover_rounds;
+    if (fin_norm) *fin_norm = s->prover_fin_n;
+    if (fin_lin) *fin_lin = s->prover_fin_l;
+    return BPPP_OK;
+}
+// the generator list (h, g, ...) as the setup derived it: count*64 bytes
+int bppp_rp_points(bppp_rp* s, size_t count, uint8_t* out) {
+    if (!s || !out || count > s->pts.size()) return BPPP_ERR_ARG;
+    memcpy(out, s->pts.data(), count * 64);
+    return BPPP_OK;
+}
+// `hashToScalars ("Blinding " <> rn)` position j (1-based)  (app/Main.hs:86-87)
+int bppp_input_blind(const char* random_seed, uint64_t j, uint8_t out[32]) {
+    if (!random_seed || !out) return BPPP_ERR_ARG;
+    h64::to_bytes(out, tr::input_blind(random_seed, j));
+    return BPPP_OK;
+}
+
+// RangeProof.proveM (src/RangeProof.hs:95-97) for `batch` independent proofs.
+//   values/types/blinds: [batch][n_inputs] 32-byte scalars (types ignored for binary proofs;
+//   blinds == NULL derives them from the proof's randomSeed like app/Main.hs:275-276);
+//   random_seeds: [batch] NUL-terminated randomSeed strings.
+// Outputs: coms [batch][num_rp_coms + n_inputs] points in the reference's order
+//   (blCom : rCom : dmCom : mCom : nComs  /  blCom : dCom : nComs); responses [batch][rounds][2]
+//   points NEWEST FIRST; finals [batch][fin_norm + fin_lin] scalars (getWitness order).
+int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
+                        const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals) {
+    if (!s) return BPPP_ERR_ARG;
+    if (!values || !random_seeds || !coms || !responses || !finals || batch == 0) return fail(s, BPPP_ERR_ARG, "null/empty argument");
+    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
+    const size_t B = batch, n = s->n_inputs, N = s->nrm_len, M = s->lin_len, P0 = 1 + N + M, NC = s->num_rp_coms + n;
+    std::vector<Proof> P(B);
+    std::atomic<int> bad(0);
+    const size_t in_terms = s->binary ? 2 : 3;
+    std::vector<uint8_t> in_sc(B * n * in_terms * 32);
+    // ---------------- phase 1 (host): witnesses, input openings, digit commitments
+    std::vector<uint8_t> sc1(B * (s->binary ? 1 : 2) * P0 * 32);
+    parallel_for(B, [&](size_t b) {
+        Proof& p = P[b];
+        p.zk.fmt = s->fmt;
+        p.zk.seed = random_seeds[b];
+        std::vector<Fr> vals(n), tys(n), bls(n);
+        for (size_t i = 0; i < n; i++) {
+            vals[i] = h64::from_bytes(values + 32 * (b * n + i));
+            tys[i] = (types && !s->binary) ? h64::from_bytes(types + 32 * (b * n + i)) : h64::zero();
+            bls[i] = blinds ? h64::from_bytes(blinds + 32 * (b * n + i)) : tr::input_blind(p.zk.seed, i + 1);
+        }
+        if (s->binary) {
+            // witnessBRP (Binary.hs:161-168): Nothing unless conserved and balanced
+            Fr vsum = h64::from_i128(s->net_pub);
+            for (size_t i = 0; i < n; i++) vsum = s->rds[i].is_output ? h64::sub(vsum, vals[i]) : h64::add(vsum, vals[i]);
+            if (!s->flag || !vsum.is_zero()) { p.ok = false; bad++; return; }
+            std::vector<Fr> ds;
+            for (size_t i = 0; i < n; i++) {
+                const Range& rd = s->rds[i];
+                if (rd.is_assumed) continue;
+                U128 n_adj;
+                if (!adjust_value(rd, values + 32 * (b * n + i), n_adj)) { p.ok = false; bad++; return; }
+                U128 bn = rd.coeffs[0];
+                int n1 = (int)rd.coeffs.size() - 1;
+                U128 dn = 0, n2 = n_adj;
+                if (n_adj > bn) { dn = 1; n2 = n_adj - bn; }
+                std::vector<Fr> bits;                                       // baseDigits 2, MSB first
+                while (n2) { bits.insert(bits.begin(), h64::from_u64((uint64_t)(n2 & 1))); n2 >>= 1; }
+                ds.push_back(h64::from_u64((uint64_t)dn));
+                for (int k = (int)bits.size(); k < n1; k++) ds.push_back(h64::zero());   // padLeft
+                ds.insert(ds.end(), bits.begin(), bits.end());
+            }
+            for (size_t i = 0; i < n; i++) {
+                RPW w; w.sc = vals[i]; w.lin = {bls[i]};
+                p.n_wits.push_back(w);
+                h64::to_bytes(&in_sc[32 * ((b * n + i) * 2)], vals[i]);
+                h64::to_bytes(&in_sc[32 * ((b * n + i) * 2 + 1)], bls[i]);
+            }
+            p.s_bl = p.zk.random();
+            Fr l_bl0 = p.zk.random();
+            p.d.sc = p.s_bl; p.d.lin = {l_bl0, h64::zero()}; p.d.nrm = ds;
+            commit_scalars(s, p.d, &sc1[32 * b * P0]);
+            return;
+        }
+        // witnessTRRP (TypedReciprocal.hs:373-388)
+        if (s->flag) {
+            std::vector<std::pair<Fr, Fr>> sums;                            // (type, net amount)
+            auto addto = [&](const Fr& t, const Fr& v, bool negate) {
+                for (auto& kv : sums)
+                    if (kv.first == t) { kv.second = negate ? h64::sub(kv.second, v) : h64::add(kv.second, v); return; }
+                sums.push_back({t, negate ? h64::neg(v) : v});
+            };
+            for (auto& pb : s->pubs) addto(h64::from_i128(pb.type), h64::from_i128(pb.amount), pb.is_output);
+            for (size_t i = 0; i < n; i++) addto(tys[i], vals[i], s->rds[i].is_output);
+            for (auto& kv : sums)
+                if (!kv.second.is_zero()) { p.ok = false; bad++; return; }
+        }
+        std::vector<Ph1> digits_ph1;
+        std::map<U128, std::vector<Fr>> bm;
+        for (size_t i = 0; i < n; i++) {
+            bool has_ms;
+            std::vector<Fr> ms;
+            if (!make_phase1s((int)i, s->rds[i], values + 32 * (b * n + i), true, digits_ph1, has_ms, ms)) { p.ok = false; bad++; return; }
+            if (has_ms) {                                                   // baseMss (:363-367)
+                const Range& rd = s->rds[i];
+                auto merge = [&](U128 base, const std::vector<Fr>& v) {
+                    auto it = bm.find(base);
+                    if (it == bm.end()) bm[base] = v;
+                    else for (size_t k = 0; k < v.size() && k < it->second.size(); k++) it->second[k] = h64::add(it->second[k], v[k]);
+                };
+                if (rd.has_bit) {
+                    merge(2, std::vector<Fr>(ms.begin(), ms.begin() + 1));
+                    merge(rd.base, std::vector<Fr>(ms.begin() + 1, ms.end()));
+                } else merge(rd.base, ms);
+            }
+        }
+        if (s->flag)
+            for (size_t i = 0; i < n; i++) {
+                Ph1 t;
+                t.kind = 'T'; t.ind = (int)i; t.io = s->rds[i].is_output; t.ia = s->rds[i].is_assumed;
+                t.m = vals[i]; t.d = tys[i];
+                p.ph1s.push_back(t);
+            }
+        p.ph1s.insert(p.ph1s.end(), digits_ph1.begin(), digits_ph1.end());
+        for (auto& kv : bm) p.base_mss.push_back(kv);
+        // proveTRRPM phase 1 (TypedReciprocal.hs:399-410)
+        std::vector<Fr> ms_shared, ds, ms_inline;
+        for (auto& kv : p.base_mss) ms_shared.insert(ms_shared.end(), kv.second.begin(), kv.second.end());
+        for (auto& q : p.ph1s) { ds.push_back(q.d); ms_inline.push_back(q.kind == 'I' ? q.m : h64::zero()); }
+        for (size_t i = 0; i < n; i++) {
+            RPW w; w.sc = vals[i]; w.lin = {tys[i], bls[i]};
+            p.n_wits.push_back(w);
+            h64::to_bytes(&in_sc[32 * ((b * n + i) * 3)], vals[i]);
+            h64::to_bytes(&in_sc[32 * ((b * n + i) * 3 + 1)], tys[i]);
+            h64::to_bytes(&in_sc[32 * ((b * n + i) * 3 + 2)], bls[i]);
+        }
+        p.dm = blind_witness(p.zk, 3, 2, ms_shared, ds);
+        p.m = blind_witness(p.zk, 3, 1, {}, ms_inline);
+        commit_scalars(s, p.dm, &sc1[32 * (2 * b) * P0]);
+        commit_scalars(s, p.m, &sc1[32 * (2 * b + 1) * P0]);
+    });
+    if (bad.load()) return fail(s, BPPP_ERR_RANGE, "invalid witness (out of range / unbalanced)");
+    // ---------------- device: input commitments + digit commitments
+    std::vector<uint8_t> n_coms(B * n * 64), c1(B * (s->binary ? 1 : 2) * 64);
+    int rc;
+    if (n) {
+        rc = bppp_fb_msm_batch(s->fb, B * n, in_sc.data(), n_coms.data());
+        if (rc) return fail(s, rc, std::string("input commitments: ") + ctx_err(s));
+    }
+    rc = bppp_msm_batch(s->ctx, B * (s->binary ? 1 : 2), P0, sc1.data(), s->table.data(), 1, c1.data());
+    if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(s));
+    std::vector<uint8_t> q_b(B * 32), sc_b(B * 32), w_b(B * N * 32, 0), l_b(B * M * 32, 0), c_b(B * M * 32, 0);
+    std::vector<uint8_t> sc2(B * P0 * 32), c2(B * 64);
+
+    if (s->binary) {
+        // ---------------- proveBRPM (Binary.hs:171-203)
+        parallel_for(B, [&](size_t b) {
+            Proof& p = P[b];
+            uint8_t* out = coms + 64 * b * NC;
+            memcpy(out + 64, &c1[64 * b], 64);                              // dCom
+            memcpy(out + 128, &n_coms[64 * b * n], 64 * n);
+            Fr ch[3];
+            p.zk.oracle(out + 64, 1 + n, ch, 3);                            // T3 q x r <- oracle' (dCom:nComs)
+            p.q = ch[0]; p.x = ch[1]; p.r0 = ch[2];
+            Fr r_inv = h64::inv(p.r0);
+            p.q0 = h64::sqr(p.q);                                           // head (powers' (q^2))
+            p.q0_inv = h64::inv(p.q0);
+            p.pub = public_consts_brp(s, p.x, p.q0, p.q0_inv);
+            p.bls_nrm.clear();
+            for (size_t i = 0; i < N; i++) p.bls_nrm.push_back(p.zk.random());
+            Fr bl_bl = p.zk.random();
+            // makePolyTerms (qPowers q) [blsNrm, nrm (dWit + pubWit)]  (Binary.hs:188, Internal.hs:65-75)
+            std::vector<Fr> dn = p.d.nrm;
+            vadd(dn, p.pub.nrm);
+            std::vector<Fr> ws = q_powers(p.q, N);
+            Fr bl0 = h64::zero(), bl1 = h64::zero();
+            for (size_t i = 0; i < N; i++) bl0 = h64::add(bl0, h64::mul(ws[i], h64::sqr(p.bls_nrm[i])));
+            for (size_t i = 0; i < N && i < dn.size(); i++) bl1 = h64::add(bl1, h64::mul(ws[i], h64::mul(p.bls_nrm[i], dn[i])));
+            bl1 = h64::dbl(bl1);
+            p.bl.sc = bl0;
+            p.bl.lin = {bl_bl, h64::mul(r_inv, h64::sub(p.s_bl, bl1))};
+            p.bl.nrm = p.bls_nrm;
+            commit_scalars(s, p.bl, &sc2[32 * b * P0]);
+        });
+        rc = bppp_msm_batch(s->ctx, B, P0, sc2.data(), s->table.data(), 1, c2.data());
+        if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(s));
+        parallel_for(B, [&](size_t b) {
+            Proof& p = P[b];
+            uint8_t* out = coms + 64 * b * NC;
+            memcpy(out, &c2[64 * b], 64);                                   // blCom
+            p.zk.oracle(out, 1, &p.t, 1);
+            // wit' = pub' + dWit + 2t * sum coeff_i * nWit_i ; bpWit = blWit + t * wit'
+            RPW pub1 = p.pub;
+            pub1.sc = h64::mul(p.t, p.pub.sc);
+            RPW w1 = pub1;
+            rpw_add(w1, p.d);
+            std::vector<Fr> ic = input_coeffs_brp(s, p.x);
+            RPW nsum;
+            for (size_t i = 0; i < n; i++) rpw_add(nsum, rpw_scale(p.n_wits[i], ic[i]));
+            rpw_add(w1, rpw_scale(nsum, h64::dbl(p.t)));
+            RPW wit = p.bl;
+            rpw_add(wit, rpw_scale(w1, p.t));
+            h64::to_bytes(&q_b[32 * b], p.q);
+            h64::to_bytes(&sc_b[32 * b], wit.sc);
+            for (size_t i = 0; i < wit.nrm.size() && i < N; i++) h64::to_bytes(&w_b[32 * (b * N + i)], wit.nrm[i]);
+            for (size_t i = 0; i < wit.lin.size() && i < M; i++) h64::to_bytes(&l_b[32 * (b * M + i)], wit.lin[i]);
+            h64::to_bytes(&c_b[32 * (b * M + 1)], h64::mul(p.r0, p.t));     // cs' = [0, r*t]  (Binary.hs:151)
+        });
+    } else {
+        // ---------------- proveTRRPM phase 2 (TypedReciprocal.hs:412-419)
+        parallel_for(B, [&](size_t b) {
+            Proof& p = P[b];
+            uint8_t* out = coms + 64 * b * NC;
+            memcpy(out + 128, &c1[64 * (2 * b)], 64);                       // dmCom
+            memcpy(out + 192, &c1[64 * (2 * b + 1)], 64);                   // mCom
+            memcpy(out + 256, &n_coms[64 * b * n], 64 * n);
+            Fr ch[3];
+            p.zk.oracle(out + 128, 2 + n, ch, 3);                           // T3 e x r0 <- oracle' (dmCom:mCom:nComs)
+            p.e = ch[0]; p.x = ch[1]; p.r0 = ch[2];
+            Fr iv[2] = {p.e, p.r0};
+            h64::batch_inv(iv, 2);
+            p.e_inv = iv[0]; p.r0_inv = iv[1];
+            p.base_map = make_base_map(s, p.x);
+            p.ph2s = make_phase2s(true, p.e, p.e_inv, p.x, p.base_map, p.ph1s);
+            Fr e7 = h64::zero();
+            std::vector<Fr> rs;
+            for (auto& o : p.ph2s) { e7 = h64::add(e7, h64::dbl(h64::mul(o.r, o.c))); rs.push_back(o.r); }
+            Fr err7 = h64::mul(p.r0_inv, h64::neg(e7));
+            p.r = blind_err_witness(p.zk, 3, {err7}, {}, rs);
+            commit_scalars(s, p.r, &sc2[32 * b * P0]);
+        });
+        rc = bppp_msm_batch(s->ctx, B, P0, sc2.data(), s->table.data(), 1, c2.data());
+        if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(s));
+        // ---------------- phase 3 (TypedReciprocal.hs:421-434)
+        parallel_for(B, [&](size_t b) {
+            Proof& p = P[b];
+            uint8_t* out = coms + 64 * b * NC;
+            memcpy(out + 64, &c2[64 * b], 64);                              // rCom
+            Fr ch[3];
+            p.zk.oracle(out + 64, 1, ch, 3);                                // T3 q x' r1 <- oracle' [rCom]
+            p.q = ch[0]; p.xq = ch[1]; p.r1 = ch[2];
+            p.q0 = h64::sqr(p.q);
+            Fr iv[3] = {p.q, p.q0, p.r1};
+            h64::batch_inv(iv, 3);
+            p.q_inv = iv[0]; p.q0_inv = iv[1]; p.r1_inv = iv[2];
+            std::vector<U128> mb;
+            for (auto& kv : p.base_mss) mb.push_back(kv.first);
+            p.shared_cs = make_shared_coeffs(p.e, p.e_inv, mb, p.base_map);
+            Fr tC = s->flag ? p.xq : h64::zero();
+            p.bls_lin.clear(); p.bls_nrm.clear();
+            for (size_t i = 0; i + 5 < M; i++) p.bls_lin.push_back(p.zk.random());
+            for (size_t i = 0; i < N; i++) p.bls_nrm.push_back(p.zk.random());
+            std::vector<Fr> bls_ms(p.bls_lin.begin() + 1, p.bls_lin.end());
+            std::vector<Fr> ic = input_coeffs_trrp(s, p.x, p.q0);
+            RPW nsum;
+            for (size_t i = 0; i < n; i++) rpw_add(nsum, rpw_scale(p.n_wits[i], ic[i]));
+            Fr input_bl = nsum.lin.size() > 1 ? nsum.lin[1] : h64::zero();
+            std::vector<Fr> q2s = q_powers(p.q, p.ph2s.size());
+            std::vector<Fr> errs = make_error_terms(p.e, p.xq, p.shared_cs, bls_ms, p.ph2s, q2s, p.bls_nrm);
+            RPW blbl;
+            blbl.lin = p.bls_lin; blbl.nrm = p.bls_nrm;
+            std::vector<const RPW*> wits = {&p.m, &p.dm, &p.r};
+            p.bl = blind_blinding_term(blbl, tC, p.r0, p.r0_inv, p.r1, p.r1_inv, errs, wits, input_bl);
+            p.wit = nsum;                                                    // parked: nWitSum
+            commit_scalars(s, p.bl, &sc2[32 * b * P0]);
+        });
+        rc = bppp_msm_batch(s->ctx, B, P0, sc2.data(), s->table.data(), 1, c2.data());
+        if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(s));
+        // ---------------- phase 4 (TypedReciprocal.hs:435-444)
+        parallel_for(B, [&](size_t b) {
+            Proof& p = P[b];
+            uint8_t* out = coms + 64 * b * NC;
+            memcpy(out, &c2[64 * b], 64);                                   // blCom
+            p.zk.oracle(out, 1, &p.t, 1);
+            p.pub = make_public_consts_trrp(s, p.e, p.e_inv, p.x, p.xq, p.q0, p.q0_inv, p.t, p.ph2s);
+            Fr t2 = h64::sqr(p.t), t3 = h64::mul(t2, p.t), t5 = h64::mul(h64::sqr(t2), p.t);
+            RPW nsum = p.wit;
+            RPW wit = p.pub;
+            rpw_add(wit, p.bl);
+            rpw_add(wit, rpw_scale(p.m, p.t));
+            rpw_add(wit, rpw_scale(p.dm, t2));
+            rpw_add(wit, rpw_scale(p.r, t3));
+            rpw_add(wit, rpw_scale(nsum, h64::dbl(t5)));
+            p.cs = make_bp_coeffs(s->flag, p.xq, p.r0, p.r1, p.t, p.shared_cs);
+            h64::to_bytes(&q_b[32 * b], p.q);
+            h64::to_bytes(&sc_b[32 * b], wit.sc);
+            for (size_t i = 0; i < wit.nrm.size() && i < N; i++) h64::to_bytes(&w_b[32 * (b * N + i)], wit.nrm[i]);
+            for (size_t i = 0; i < wit.lin.size() && i < M; i++) h64::to_bytes(&l_b[32 * (b * M + i)], wit.lin[i]);
+            for (size_t i = 0; i < p.cs.size() && i < M; i++) h64::to_bytes(&c_b[32 * (b * M + i)], p.cs[i]);
+        });
+    }
+    return run_argument(s, P, s->prover_rounds, q_b, sc_b, w_b, l_b, c_b, responses, finals, s->prover_fin_n, s->prover_fin_l);
+}
+
+// RangeProof.verifyM (src/RangeProof.hs:99-101) for `batch` proofs; `rounds`, n_norm, n_lin
+// describe the proofs as encoded (for binary proofs the prover's round rule may differ from
+// optimalWitnessSize, src/RangeProof/Binary.hs:195 vs :218; verifyBPM ignores `rounds`).
+int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
+                         const uint8_t* responses, const uint8_t* finals, int* ok) {
+    if (!s) return BPPP_ERR_ARG;
+    if (!coms || !finals || !ok || batch == 0 || (rounds && !responses)) return fail(s, BPPP_ERR_ARG, "null/empty argument");
+    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
+    const size_t B = batch, n = s->n_inputs, N = s->nrm_len, M = s->lin_len, NC = s->num_rp_coms + n, k = rounds;
+    std::vector<uint8_t> q_b(B * 32), sp_b(B * 32), pw_b(B * N * 32, 0), c_b(B * M * 32, 0), es_b(B * k * 32);
+    std::vector<uint8_t> fw_b(B * n_norm * 32), fl_b(B * n_lin * 32), is_b(B * NC * 32), ip_b(B * NC * 64);
+    std::vector<Ph1> ph1v;
+    if (!s->binary) ph1v = ph1s_verifier(s);
+    parallel_for(B, [&](size_t b) {
+        tr::Zkpt zk;
+        zk.fmt = s->fmt;
+        zk.no_random = true;
+        const uint8_t* cm = coms + 64 * b * NC;
+        Fr q, sp;
+        RPW pub;
+        std::vector<Fr> cs, init_s;
+        if (s->binary) {                                                    // verifyBRPM (Binary.hs:205-220)
+            Fr ch[3], t;
+            zk.oracle(cm + 64, 1 + n, ch, 3);
+            q = ch[0];
+            Fr x = ch[1], r = ch[2];
+            Fr q0 = h64::sqr(q), q0_inv = h64::inv(q0);
+            zk.oracle(cm, 1, &t, 1);
+            RPW pw = public_consts_brp(s, x, q0, q0_inv);
+            // pub = t *^ RPW (t * pubSc) [] pubNrm
+            pub.sc = h64::mul(h64::sqr(t), pw.sc);
+            for (auto& v : pw.nrm) pub.nrm.push_back(h64::mul(t, v));
+            cs = {h64::zero(), h64::mul(r, t)};
+            Fr two_t2 = h64::dbl(h64::sqr(t));                              // TranscriptBRP.openWith (Binary.hs:106-110)
+            for (auto& c : input_coeffs_brp(s, x)) init_s.push_back(h64::mul(two_t2, c));
+            // opening order here: [blCom (1), dCom (t), nComs ...] matching `coms`
+            init_s.insert(init_s.begin(), t);
+            init_s.insert(init_s.begin(), h64::one());
+        } else {                                                            // verifyTRRPM (TypedReciprocal.hs:447-467)
+            Fr ch[3], ch2[3], t;
+            zk.oracle(cm + 128, 2 + n, ch, 3);
+            Fr e = ch[0], x = ch[1], r0 = ch[2];
+            zk.oracle(cm + 64, 1, ch2, 3);
+            q = ch2[0];
+            Fr xq = ch2[1], r1 = ch2[2];
+            Fr q0 = h64::sqr(q);
+            zk.oracle(cm, 1, &t, 1);
+            Fr iv[3] = {e, q, q0};
+            h64::batch_inv(iv, 3);
+            Fr e_inv = iv[0], q0_inv = iv[2];
+            std::map<U128, Fr> bm = make_base_map(s, x);
+            std::vector<Ph2> ph2s = make_phase2s(false, e, e_inv, x, bm, ph1v);
+            pub = make_public_consts_trrp(s, e, e_inv, x, xq, q0, q0_inv, t, ph2s);
+            cs = make_bp_coeffs(s->flag, xq, r0, r1, t, make_shared_coeffs(e, e_inv, s->m_bases, bm));
+            // TranscriptTRRP.openWith (TypedReciprocal.hs:279-282): [1,t,t^2,t^3] on [bl,m,dm,r]
+            Fr t2 = h64::sqr(t), t3 = h64::mul(t2, t), t5 = h64::mul(h64::sqr(t2), t);
+            init_s = {h64::one(), t3, t2, t};                               // coms order: bl, r, dm, m
+            Fr two_t5 = h64::dbl(t5);
+            for (auto& c : input_coeffs_trrp(s, x, q0)) init_s.push_back(h64::mul(two_t5, c));
+        }
+        // challenges of the argument: oldest round hashed first, list newest first (Bulletproof.hs:374)
+        for (size_t r = 0; r < k; r++) {
+            size_t idx = k - 1 - r;                                         // oldest round sits last
+            Fr e;
+            zk.oracle(responses + 128 * (b * k + idx), 2, &e, 1);
+            h64::to_bytes(&es_b[32 * (b * k + idx)], e);
+        }
+        h64::to_bytes(&q_b[32 * b], q);
+        h64::to_bytes(&sp_b[32 * b], pub.sc);
+        for (size_t i = 0; i < pub.nrm.size() && i < N; i++) h64::to_bytes(&pw_b[32 * (b * N + i)], pub.nrm[i]);
+        for (size_t i = 0; i < cs.size() && i < M; i++) h64::to_bytes(&c_b[32 * (b * M + i)], cs[i]);
+        for (size_t i = 0; i < NC; i++) h64::to_bytes(&is_b[32 * (b * NC + i)], init_s[i]);
+        memcpy(&ip_b[64 * b * NC], cm, 64 * NC);
+        memcpy(&fw_b[32 * b * n_norm], finals + 32 * b * (n_norm + n_lin), 32 * n_norm);
+        memcpy(&fl_b[32 * b * n_lin], finals + 32 * (b * (n_norm + n_lin) + n_norm), 32 * n_lin);
+    });
+    int rc = bppp_nl_verify(s->ctx, s->arg, B, N, M, k, &s->table[0], &s->table[64], &s->table[64 * (1 + N)], q_b.data(),
+                            sp_b.data(), pw_b.data(), c_b.data(), es_b.data(), responses, n_norm, n_lin, fw_b.data(), fl_b.data(),
+                            NC, is_b.data(), ip_b.data(), ok);
+    if (rc) return fail(s, rc, std::string("bppp_nl_verify: ") + ctx_err(s));
+    return BPPP_OK;
+}
+
+// self-test hooks for the CPU test-suite (no device needed)
+int bppp_host_sha256(const uint8_t* data, size_t n, uint8_t out[32]) {
+    sha::digest3(out, data, n, nullptr, 0, nullptr, 0);
+    return 0;
+}
+int bppp_host_oracle(const uint8_t* pts, size_t npts, int count, int show_format, uint8_t* out) {
+    tr::Zkpt zk;
+    zk.fmt = show_format;
+    std::vector<Fr> o(count);
+    zk.oracle(pts, npts, o.data(), count);
+    for (int i = 0; i < count; i++) h64::to_bytes(out + 32 * i, o[i]);
+    return 0;
+}
+int bppp_host_fr(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    Fr x = h64::from_bytes(a), y = h64::from_bytes(b), r;
+    switch (op) {
+        case 0: r = h64::mul(x, y); break;
+        case 1: r = h64::add(x, y); break;
+        case 2: r = h64::sub(x, y); break;
+        case 3: r = h64::inv(x); break;
+        case 4: r = h64::neg(x); break;
+        default: return 1;
+    }
+    h64::to_bytes(out, r);
+    return 0;
+}
+int bppp_host_get_points(const char* seed, size_t count, int root_policy, uint8_t* out) {
+    std::vector<Affine> p = tr::get_points(seed, count, root_policy);
+    memcpy(out, p.data(), count * 64);
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+// Host-side Fiat-Shamir transcript, RNG and generator derivation, exactly as the reference's CLI
+// wires them (the north star keeps the transcript on the host):
+//   hash / getPoints / shaOracle / hashToScalar(s)   app/Main.hs:64-87
+//   ZKPT (commitment list newest-first + random ctr)  src/ZKP.hs:68-101
+//   digest -> field element                           src/Encoding.hs:75-79
+// Two behaviours live in un-vendored packages and are policies here ("parity
+// unpinned"): how `show` renders a `Prime p` ("P <dec>" by default, or bare "<dec>") and which
+// square root `pointX` returns (rhs^((q+1)/4) by default).
+#pragma once
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../ec.cuh"
+#include "fr64.hpp"
+#include "sha256.hpp"
+
+namespace bppp {
+namespace tr {
+using h64::Fr;
+typedef unsigned __int128 u128;
+
+enum ShowFormat { PREFIXED_P = 0, BARE_DECIMAL = 1 };
+enum RootPolicy { ROOT_EXP = 0, ROOT_EVEN = 1, ROOT_SMALLER = 2 };
+
+// decimal rendering of a 256-bit little-endian integer (4 x u64)
+inline void append_decimal(std::string& out, const uint64_t v[4]) {
+    uint64_t t[4] = {v[0], v[1], v[2], v[3]};
+    uint64_t chunks[5];
+    int nc = 0;
+    const uint64_t TEN19 = 10000000000000000000ULL;
+    while (t[0] | t[1] | t[2] | t[3]) {
+        u128 rem = 0;
+        for (int i = 3; i >= 0; i--) {
+            u128 cur = (rem << 64) | t[i];
+            t[i] = (uint64_t)(cur / TEN19);
+            rem = cur % TEN19;
+        }
+        chunks[nc++] = (uint64_t)rem;
+    }
+    if (nc == 0) { out.push_back('0'); return; }
+    char buf[24];
+    int n = snprintf(buf, sizeof buf, "%llu", (unsigned long long)chunks[nc - 1]);
+    out.append(buf, n);
+    for (int i = nc - 2; i >= 0; i--) {
+        n = snprintf(buf, sizeof buf, "%019llu", (unsigned long long)chunks[i]);
+        out.append(buf, n);
+    }
+}
+inline void append_show_field(std::string& out, const uint64_t v[4], int fmt) {
+    if (fmt == PREFIXED_P) out.append("P ");
+    append_decimal(out, v);
+}
+inline void append_uint(std::string& out, uint64_t x) {
+    char buf[24];
+    int n = snprintf(buf, sizeof buf, "%llu", (unsigned long long)x);
+    out.append(buf, n);
+}
+// digest -> integer: four big-endian Word64, first word least significant (Encoding.hs:75-79)
+inline void digest_to_words(uint64_t w[4], const uint8_t d[32]) {
+    for (int i = 0; i < 4; i++) {
+        uint64_t x = 0;
+        for (int k = 0; k < 8; k++) x = (x << 8) | d[8 * i + k];
+        w[i] = x;
+    }
+}
+inline Fr hash_to_fr(const std::string& s) {
+    uint8_t d[32];
+    sha::digest(d, s);
+    uint64_t w[4];
+    digest_to_words(w, d);
+    return h64::from_wide(w);
+}
+// `coords (A x y) = show x <> show y` of an affine point given as 64 LE bytes (app/Main.hs:78-80)
+inline std::string show_point(const uint8_t p[64], int fmt) {
+    std::string s;
+    s.reserve(170);
+    uint64_t x[4], y[4];
+    memcpy(x, p, 32);
+    memcpy(y, p + 32, 32);
+    append_show_field(s, x, fmt);
+    append_show_field(s, y, fmt);
+    return s;
+}
+
+// The reference's ZKPT state for one proof.
+struct Zkpt {
+    int fmt = PREFIXED_P;
+    std::string seed;                 // randomSeed; empty + no_random => verifier
+    bool no_random = false;
+    uint64_t n_random = 0;
+    size_t n_coms = 0;
+    std::string body;                 // concat of coords, NEWEST FIRST (cs' = xs ++ cs)
+    uint64_t hashed_bytes = 0;
+
+    // `random` (ZKP.hs:90-93) with h = hashToScalar rn . show (app/Main.hs:177)
+    Fr random() {
+        std::string s = seed;
+        append_uint(s, n_random++);
+        return hash_to_fr(s);
+    }
+    // `oracle xs` -> first `count` scalars of shaOracle cs' (ZKP.hs:96-101, app/Main.hs:75-80)
+    void oracle(const uint8_t* pts, size_t npts, Fr* out, int count) {
+        std::string add;
+        add.reserve(npts * 170 + body.size());
+        for (size_t i = 0; i < npts; i++) add += show_point(pts + 64 * i, fmt);
+        add += body;
+        body.swap(add);
+        n_coms += npts;
+        std::string len;
+        append_uint(len, n_coms);
+        for (int i = 1; i <= count; i++) {
+            std::string pre;
+            append_uint(pre, (uint64_t)i);
+            pre += len;
+            uint8_t d[32];
+            sha::digest3(d, (const uint8_t*)pre.data(), pre.size(), (const uint8_t*)body.data(), body.size(), nullptr, 0);
+            hashed_bytes += pre.size() + body.size();
+            uint64_t w[4];
+            digest_to_words(w, d);
+            out[i - 1] = h64::from_wide(w);
+        }
+    }
+};
+
+// `hashToScalars ("Blinding " <> rn)` position j (1-based)  (app/Main.hs:86-87, 275-276)
+inline Fr input_blind(const std::string& random_seed, uint64_t j) {
+    std::string s = "Blinding " + random_seed;
+    append_uint(s, j);
+    return hash_to_fr(s);
+}
+
+// getPoints seed (app/Main.hs:68-72): x = hash(seed <> show n) in Fq, kept when x^3 + 7 is a square
+inline std::vector<Affine> get_points(const std::string& seed, size_t count, int root_policy) {
+    std::vector<Affine> out;
+    out.reserve(count);
+    // exponent (q + 1) / 4
+    u256 e = fq::modulus();
+    {   // (q + 1) >> 2
+        u256 one = u256_one(), t;
+        u256_add(t, e, one);           // q + 1 < 2^256
+        for (int i = 0; i < 8; i++) e.v[i] = (t.v[i] >> 2) | (i < 7 ? t.v[i + 1] << 30 : 0);
+    }
+    for (uint64_t n = 0; out.size() < count; n++) {
+        std::string s = seed;
+        append_uint(s, n);
+        uint8_t d[32];
+        sha::digest(d, s);
+        uint64_t w[4];
+        digest_to_words(w, d);
+        u256 x;
+        for (int i = 0; i < 4; i++) { x.v[2 * i] = (uint32_t)w[i]; x.v[2 * i + 1] = (uint32_t)(w[i] >> 32); }
+        x = fq::cond_sub(x, 0);                           // toP: 2^256 < 2q
+        u256 seven = u256_zero();
+        seven.v[0] = 7;
+        u256 rhs = fq::add(fq::mul(fq::sqr(x), x), seven);
+        u256 y = u256_one();
+        for (int i = 255; i >= 0; i--) {
+            y = fq::sqr(y);
+            if (u256_bit(e, i)) y = fq::mul(y, rhs);
+        }
+        if (!u256_eq(fq::sqr(y), rhs)) continue;
+        u256 ny = fq::neg(y);
+        if (root_policy == ROOT_EVEN && (y.v[0] & 1)) y = ny;
+        else if (root_policy == ROOT_SMALLER && !u256_geq(ny, y)) y = ny;
+        Affine p;
+        p.x = x; p.y = y;
+        out.push_back(p);
+    }
+    return out;
+}
+
+}  // namespace tr
+}  // namespace bppp

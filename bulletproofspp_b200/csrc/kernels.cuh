@@ -621,6 +621,45 @@ __global__ void __launch_bounds__(256) k_tensor_expand(TensorArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Fixed-base MSM for a handful of bases shared by every MSM (the range proofs' input commitments
+// value*g + type*hs0 + blind*hs1, src/RangeProof/Internal.hs:53-57): 8-bit window tables
+// tbl[(base*32 + w)*255 + d-1] = d * 2^(8w) * P, so one MSM is <= 32 mixed adds per base with no
+// doublings.  One thread per MSM.
+// ------------------------------------------------------------------------------------------
+#define FB_WINDOWS 32
+#define FB_ENTRIES 255
+__global__ void k_fb_build(const Affine* __restrict__ bases, int n_bases, Jac* __restrict__ tbl) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_bases * FB_WINDOWS) return;
+    int b = t / FB_WINDOWS, w = t % FB_WINDOWS;
+    Jac start = jac_from_aff(ld_aff(bases + b));
+    for (int i = 0; i < 8 * w; i++) start = jac_dbl(start);
+    Jac acc = start;
+    Jac* out = tbl + (size_t)t * FB_ENTRIES;
+    st_jac(out, acc);
+    for (int d = 2; d <= FB_ENTRIES; d++) {
+        acc = jac_add(acc, start);
+        st_jac(out + d - 1, acc);
+    }
+}
+__global__ void __launch_bounds__(128) k_fb_msm(const Affine* __restrict__ tbl, int n_bases,
+                                                const u256* __restrict__ sc, Jac* __restrict__ out, size_t n_msm) {
+    size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (m >= n_msm) return;
+    Jac acc = jac_inf();
+    for (int b = 0; b < n_bases; b++) {
+        u256 s = ld_u256(sc + m * n_bases + b);
+        if (u256_is_zero(s)) continue;
+#pragma unroll 1
+        for (int w = 0; w < FB_WINDOWS; w++) {
+            uint32_t d = (s.v[w >> 2] >> ((w & 3) * 8)) & 0xffu;
+            if (d) acc = jac_madd(acc, ld_aff(tbl + ((size_t)(b * FB_WINDOWS + w)) * FB_ENTRIES + d - 1));
+        }
+    }
+    st_jac(out + m, acc);
+}
+
+// ------------------------------------------------------------------------------------------
 // debug / self-test kernels (exercised by tests/ through bppp_dbg_*)
 // ------------------------------------------------------------------------------------------
 __global__ void k_dbg_field(const u256* a, const u256* b, u256* out, size_t n, int op) {

@@ -13,6 +13,10 @@ EXPORTS = [
     "bppp_msm", "bppp_msm_batch", "bppp_pair_fold", "bppp_rational_reduce",
     "bppp_nl_create", "bppp_nl_round_commit", "bppp_nl_round_fold", "bppp_nl_lengths", "bppp_nl_final",
     "bppp_nl_destroy", "bppp_nl_verify", "bppp_dbg_field", "bppp_dbg_ec",
+    "bppp_fb_create", "bppp_fb_msm_batch", "bppp_fb_destroy",
+    "bppp_rp_setup", "bppp_rp_free", "bppp_rp_last_error", "bppp_rp_info", "bppp_rp_points", "bppp_input_blind",
+    "bppp_set_host_threads", "bppp_rp_prove_batch", "bppp_rp_verify_batch",
+    "bppp_host_sha256", "bppp_host_oracle", "bppp_host_fr", "bppp_host_get_points",
 ]
 
 
@@ -58,8 +62,42 @@ def load_library():
                                    u8p, u8p, sz, u8p, u8p, C.POINTER(ip)]
     lib.bppp_dbg_field.argtypes = [vp, ip, sz, u8p, u8p, u8p]
     lib.bppp_dbg_ec.argtypes = [vp, ip, sz, u8p, u8p, u8p]
+    lib.bppp_fb_create.argtypes = [vp, sz, u8p, C.POINTER(vp)]
+    lib.bppp_fb_msm_batch.argtypes = [vp, sz, u8p, u8p]
+    lib.bppp_fb_destroy.argtypes = [vp]
+    lib.bppp_fb_destroy.restype = None
+    lib.bppp_rp_setup.argtypes = [vp, ip, ip, ip, C.c_char_p, ip, ip, sz, C.POINTER(RangeSpec), sz,
+                                  C.POINTER(PublicSpec), C.POINTER(vp)]
+    lib.bppp_rp_free.argtypes = [vp]
+    lib.bppp_rp_free.restype = None
+    lib.bppp_rp_last_error.argtypes = [vp]
+    lib.bppp_rp_last_error.restype = C.c_char_p
+    lib.bppp_rp_info.argtypes = [vp] + [C.POINTER(sz)] * 7
+    lib.bppp_rp_points.argtypes = [vp, sz, u8p]
+    lib.bppp_input_blind.argtypes = [C.c_char_p, C.c_uint64, u8p]
+    lib.bppp_set_host_threads.argtypes = [ip]
+    lib.bppp_set_host_threads.restype = None
+    lib.bppp_rp_prove_batch.argtypes = [vp, sz, u8p, u8p, u8p, C.POINTER(C.c_char_p), u8p, u8p, u8p]
+    lib.bppp_rp_verify_batch.argtypes = [vp, sz, sz, sz, sz, u8p, u8p, u8p, C.POINTER(ip)]
+    lib.bppp_host_sha256.argtypes = [u8p, sz, u8p]
+    lib.bppp_host_oracle.argtypes = [u8p, sz, ip, ip, u8p]
+    lib.bppp_host_fr.argtypes = [ip, u8p, u8p, u8p]
+    lib.bppp_host_get_points.argtypes = [C.c_char_p, sz, ip, u8p]
     _LIB = lib
     return lib
+
+
+class RangeSpec(C.Structure):
+    _fields_ = [("min", C.c_uint8 * 16), ("max", C.c_uint8 * 16), ("base", C.c_uint32), ("is_shared", C.c_int32),
+                ("is_output", C.c_int32), ("is_assumed", C.c_int32)]
+
+
+class PublicSpec(C.Structure):
+    _fields_ = [("amount", C.c_uint8 * 16), ("type", C.c_uint8 * 16), ("is_output", C.c_int32)]
+
+
+def _i128(x):
+    return (C.c_uint8 * 16)(*int(x).to_bytes(16, "little", signed=True))
 
 
 # ----------------------------------------------------------------- byte helpers
@@ -262,6 +300,132 @@ class NormLinearArgument:
     def close(self):
         if getattr(self, "h", None):
             self.ctx.lib.bppp_nl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _integer_log(b, n):
+    r = 0
+    while n >= b:
+        n //= b
+        r += 1
+    return r
+
+
+class RangeProofSetup:
+    """`SetupRP` for TypedReciprocal / Binary range proofs (src/RangeProof.hs:25-55) built from a
+    schema like the reference's CLI does (app/Parse.hs:97-172, app/Main.hs:255-335); proving and
+    verifying run batched on the device behind `prove_batch` / `verify_batch` (= proveM / verifyM)."""
+
+    def __init__(self, ctx, schema, show_format=0, root_policy=0):
+        if not isinstance(schema, dict):
+            import json
+            with open(schema) as f:
+                schema = json.load(f)
+        self.ctx, self.schema = ctx, schema
+        arg = {"ip": ARG_IP, "innerproduct": ARG_IP, "nl": ARG_NL, "normlinear": ARG_NL}[schema.get("argument", "IP").lower()]
+        self.binary = bool(schema.get("binary", False))
+        typed, con = schema.get("typed", False), schema.get("conserved", False)
+        if typed and self.binary:
+            raise BpppError("Can't make typed binary proof")
+        self.arg = arg
+        self.random_seed = schema.get("randomSeed", "default random seed")
+        rs = []
+        for r in schema["ranges"]:
+            mn, mx = r.get("min", 0), r.get("max", 2 ** 64)
+            if self.binary:
+                base = 2
+            else:
+                l = _integer_log(2, mx - mn)
+                base = r.get("base", l // max(_integer_log(2, l), 1))              # approxLogW (app/Parse.hs:193-197)
+            spec = RangeSpec(_i128(mn), _i128(mx), base, int(r.get("isShared", False)), int(r.get("isOutput", False)),
+                             int(r.get("isAssumed", False)))
+            rs += [spec] * r.get("count", 1)
+        ps = [PublicSpec(_i128(p["amount"]), _i128(p.get("type", 0)), int(p.get("isOutput", False)))
+              for p in schema.get("public", [])]
+        ra = (RangeSpec * max(len(rs), 1))(*rs)
+        pa = (PublicSpec * max(len(ps), 1))(*ps)
+        h = C.c_void_p()
+        flag = con if self.binary else (typed or con)
+        rc = ctx.lib.bppp_rp_setup(ctx.h, int(self.binary), arg, int(flag), schema.get("basisSeed", "test points").encode(),
+                                   show_format, root_policy, len(rs), ra, len(ps), pa, C.byref(h))
+        if rc:
+            raise BpppError("bppp_rp_setup failed (%d): %s" % (rc, ctx.lib.bppp_last_error(ctx.h).decode()))
+        self.h = h
+        v = [C.c_size_t() for _ in range(7)]
+        ctx.lib.bppp_rp_info(h, *[C.byref(x) for x in v])
+        (self.n_inputs, self.num_rp_coms, self.nrm_len, self.lin_len, self.rounds, self.fin_norm, self.fin_lin) = [x.value for x in v]
+
+    def _ck(self, rc, what):
+        if rc:
+            raise BpppError("%s failed (%d): %s" % (what, rc, self.ctx.lib.bppp_rp_last_error(self.h).decode()))
+
+    def points(self, count):
+        out = _buf(64 * count)
+        self._ck(self.ctx.lib.bppp_rp_points(self.h, count, out), "bppp_rp_points")
+        return bytes_to_points(out.raw[:64 * count])
+
+    def prove_batch_raw(self, batch, values, types, blinds, seeds):
+        """bytes in / bytes out (see include/bppp_b200.h)."""
+        nc = self.num_rp_coms + self.n_inputs
+        coms, resp = _buf(64 * batch * nc), _buf(128 * batch * self.rounds)
+        fin = _buf(32 * batch * (self.fin_norm + self.fin_lin))
+        sa = (C.c_char_p * batch)(*[s.encode() if isinstance(s, str) else s for s in seeds])
+        self._ck(self.ctx.lib.bppp_rp_prove_batch(self.h, batch, values, types, blinds, sa, coms, resp, fin), "bppp_rp_prove_batch")
+        return coms.raw[:64 * batch * nc], resp.raw[:128 * batch * self.rounds], fin.raw[:32 * batch * (self.fin_norm + self.fin_lin)]
+
+    def prove_batch(self, witnesses, seeds=None):
+        """witnesses: [batch][n_inputs] dicts {"amount", "type"?, "blind"?} like witness.json.
+        Returns [dict(coms, responses, finals)] in the oracle's proof shape."""
+        B, n = len(witnesses), self.n_inputs
+        seeds = seeds or [self.random_seed] * B
+        R_ = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+        vals = b"".join(int_to_le(w["amount"] % R_) for ws in witnesses for w in ws)
+        tys = b"".join(int_to_le(w.get("type", 0) % R_) for ws in witnesses for w in ws)
+        blinds = None
+        if any("blind" in w for ws in witnesses for w in ws):
+            out = _buf(32)
+            bl = []
+            for ws, sd in zip(witnesses, seeds):
+                for j, w in enumerate(ws):
+                    if "blind" in w:
+                        bl.append(int_to_le(w["blind"] % R_))
+                    else:
+                        self.ctx.lib.bppp_input_blind(sd.encode(), j + 1, out)
+                        bl.append(out.raw[:32])
+            blinds = b"".join(bl)
+        coms, resp, fin = self.prove_batch_raw(B, vals, tys, blinds, seeds)
+        nc, k, nf = self.num_rp_coms + n, self.rounds, self.fin_norm + self.fin_lin
+        out = []
+        for b in range(B):
+            cs = bytes_to_points(coms[64 * b * nc:64 * (b + 1) * nc])
+            rp = bytes_to_points(resp[128 * b * k:128 * (b + 1) * k])
+            out.append(dict(coms=cs, responses=[(rp[2 * i], rp[2 * i + 1]) for i in range(k)],
+                            finals=bytes_to_ints(fin[32 * b * nf:32 * (b + 1) * nf])))
+        return out
+
+    def verify_batch_raw(self, batch, coms, resp, fin, rounds=None, n_norm=None, n_lin=None):
+        ok = (C.c_int * batch)()
+        self._ck(self.ctx.lib.bppp_rp_verify_batch(self.h, batch, self.rounds if rounds is None else rounds,
+                                                   self.fin_norm if n_norm is None else n_norm,
+                                                   self.fin_lin if n_lin is None else n_lin, coms, resp, fin, ok),
+                 "bppp_rp_verify_batch")
+        return [bool(v) for v in ok]
+
+    def verify_batch(self, proofs):
+        coms = b"".join(points_to_bytes(p["coms"]) for p in proofs)
+        resp = b"".join(point_to_bytes(x) + point_to_bytes(r) for p in proofs for x, r in p["responses"])
+        fin = b"".join(ints_to_bytes(p["finals"]) for p in proofs)
+        return self.verify_batch_raw(len(proofs), coms, resp, fin, rounds=len(proofs[0]["responses"]))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.bppp_rp_free(self.h)
             self.h = None
 
     def __del__(self):

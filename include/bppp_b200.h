@@ -50,6 +50,15 @@ int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poi
 int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8_t* scalars, const uint8_t* points,
                    int shared_points, uint8_t* out);
 
+/* ---- fixed-base MSMs over a handful of generators shared by every call: the range proofs'
+ * input commitments value*g + type*hs0 + blind*hs1 (scalarRPW' / scalarPairRPW' + commitRPW,
+ * src/RangeProof/Internal.hs:43-57; app/Main.hs:287-288,315).  Precomputed 8-bit window tables. */
+typedef struct bppp_fb bppp_fb;
+int bppp_fb_create(bppp_ctx* ctx, size_t n_bases, const uint8_t* points, bppp_fb** out);
+/* scalars: batch*n_bases*32; out: batch*64 */
+int bppp_fb_msm_batch(bppp_fb* fb, size_t batch, const uint8_t* scalars, uint8_t* out);
+void bppp_fb_destroy(bppp_fb* fb);
+
 /* ---- generator fold: collapsePoints b a gL gR = projectivePairIP (b, gL) (a, gR)
  * (src/Bulletproof.hs:213-214, src/Commitment.hs:343-353), for a whole vector with one (a, b):
  * out[i] = (+-b)*in[2i] + (+-a)*in[2i+1]; an odd tail pairs with the identity.
@@ -96,6 +105,46 @@ int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, si
                    const uint8_t* c, const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin,
                    const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p,
                    int* ok);
+
+/* ---- Range-proof layer (host C++ above the device entry points; the Fiat-Shamir transcript,
+ * round sequencing and the scalar phases run on host threads, every group operation on the GPU).
+ * Mirrors RPOpening / RangeProof (src/RangeProof.hs:25-101) for TypedReciprocal
+ * (src/RangeProof/TypedReciprocal.hs) and Binary (src/RangeProof/Binary.hs), batched. */
+typedef struct bppp_rp bppp_rp;
+typedef struct {
+    uint8_t min[16], max[16];          /* two's-complement little-endian 128-bit integers */
+    uint32_t base;                     /* ignored for binary proofs */
+    int32_t is_shared, is_output, is_assumed;
+} bppp_range_spec;                     /* one entry per range AFTER `count` expansion (app/Parse.hs:126-165) */
+typedef struct {
+    uint8_t amount[16], type[16];
+    int32_t is_output;
+} bppp_public_spec;                    /* app/Parse.hs:210-235 */
+enum { BPPP_SHOW_PREFIXED_P = 0, BPPP_SHOW_BARE_DECIMAL = 1 };
+enum { BPPP_ROOT_EXP = 0, BPPP_ROOT_EVEN = 1, BPPP_ROOT_SMALLER = 2 };
+/* TRRP.setup (TypedReciprocal.hs:332-359) / setupBRP (Binary.hs:143-156); generators from
+ * getPoints basis_seed (app/Main.hs:68-72). */
+int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserved, const char* basis_seed,
+                  int show_format, int root_policy, size_t n_ranges, const bppp_range_spec* ranges, size_t n_pub,
+                  const bppp_public_spec* pubs, bppp_rp** out);
+void bppp_rp_free(bppp_rp* s);
+const char* bppp_rp_last_error(bppp_rp* s);
+int bppp_rp_info(bppp_rp* s, size_t* n_inputs, size_t* num_rp_coms, size_t* nrm_len, size_t* lin_len, size_t* rounds,
+                 size_t* fin_norm, size_t* fin_lin);
+int bppp_rp_points(bppp_rp* s, size_t count, uint8_t* out);
+int bppp_input_blind(const char* random_seed, uint64_t j, uint8_t out[32]);
+void bppp_set_host_threads(int n);
+/* RangeProof.proveM for `batch` independent proofs (see rp_host.cpp for the buffer layout) */
+int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
+                        const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals);
+/* RangeProof.verifyM for `batch` proofs */
+int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
+                         const uint8_t* responses, const uint8_t* finals, int* ok);
+/* host-only self-test hooks (no device needed) */
+int bppp_host_sha256(const uint8_t* data, size_t n, uint8_t out[32]);
+int bppp_host_oracle(const uint8_t* pts, size_t npts, int count, int show_format, uint8_t* out);
+int bppp_host_fr(int op, const uint8_t* a, const uint8_t* b, uint8_t* out);
+int bppp_host_get_points(const char* seed, size_t count, int root_policy, uint8_t* out);
 
 /* ---- debug / self-test entry points used by tests/ (element-wise device arithmetic) */
 int bppp_dbg_field(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out);

@@ -1,0 +1,100 @@
+"""GPU parity of the full range-proof provers / verifiers (host C++ phases + device group
+operations, through the C ABI) against the golden vectors the oracle produced and, for the small
+configs, against the oracle run live.  Bit-exact: commitments, responses and final scalars."""
+import json
+import os
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from example_configs import EXAMPLES, batched
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NL_CONFIGS = ["bin_test", "bin64", "typed_nl", "32by64", "64by64", "96by64", "128by64"]
+
+
+def load_golden(name):
+    with open(os.path.join(GOLD, name.replace("#", "_b") + ".json")) as f:
+        g = json.load(f)
+    pt = lambda p: None if p is None else (int(p[0], 16), int(p[1], 16))
+    g["coms"] = [pt(p) for p in g["coms"]]
+    g["responses"] = [(pt(x), pt(r)) for x, r in g["responses"]]
+    g["finals"] = [int(v, 16) for v in g["finals"]]
+    return g
+
+
+@pytest.mark.parametrize("name", NL_CONFIGS)
+def test_prove_matches_golden_and_verifies(ctx, name):
+    import bulletproofspp_b200 as bp
+    schema, wit = EXAMPLES[name]
+    g = load_golden(name)
+    setup = bp.RangeProofSetup(ctx, schema)
+    assert (setup.nrm_len, setup.lin_len, setup.rounds) == (g["nrm_len"], g["lin_len"], g["rounds"])
+    proof = setup.prove_batch([wit])[0]
+    assert proof["coms"] == g["coms"]
+    assert proof["responses"] == g["responses"]
+    assert proof["finals"] == g["finals"]
+    assert setup.verify_batch([proof]) == [True]
+    # tampering is rejected
+    bad = dict(proof, finals=[(proof["finals"][0] + 1) % (2 ** 200)] + proof["finals"][1:])
+    bad2 = dict(proof, coms=[proof["coms"][1], proof["coms"][0]] + proof["coms"][2:])
+    assert setup.verify_batch([bad, proof, bad2]) == [False, True, False]
+    setup.close()
+
+
+def test_batched_proofs_have_independent_transcripts(ctx):
+    import bulletproofspp_b200 as bp
+    schema, wits, seeds = batched("128by64", 3)
+    setup = bp.RangeProofSetup(ctx, schema)
+    proofs = setup.prove_batch(wits, seeds)
+    g1 = load_golden("128by64#1")
+    assert proofs[1]["coms"] == g1["coms"] and proofs[1]["responses"] == g1["responses"] and proofs[1]["finals"] == g1["finals"]
+    assert proofs[0]["responses"] != proofs[1]["responses"]
+    assert setup.verify_batch(proofs) == [True, True, True]
+    # a proof does not verify under another proof's commitments
+    mixed = dict(proofs[0], coms=proofs[1]["coms"])
+    assert setup.verify_batch([mixed]) == [False]
+    setup.close()
+
+
+def test_live_oracle_agreement_with_explicit_blinds(ctx):
+    """small config, witness with caller-supplied blinds and a custom random seed, oracle run live"""
+    import bulletproofspp_b200 as bp
+    from oracle.curve import Secp256k1 as G
+    from oracle.rangeproof import load_schema, load_witness, prove, verify
+    from oracle.transcript import ZKPT
+    schema = dict(EXAMPLES["bin64"][0], randomSeed="another seed")
+    wit = [{"amount": 10 ** 9, "blind": 123456789}]
+    so = load_schema(schema, G)
+    po = prove(so, ZKPT(G, so.random_seed), load_witness(so, wit))
+    setup = bp.RangeProofSetup(ctx, schema)
+    p = setup.prove_batch([wit])[0]
+    assert p["coms"] == po["coms"] and p["responses"] == po["responses"]
+    assert p["finals"] == po["opening"].vec.get_witness()
+    assert setup.verify_batch([p]) == [True]
+    assert verify(so, ZKPT(G, None), dict(coms=p["coms"], responses=p["responses"], opening=po["opening"]))
+    setup.close()
+
+
+def test_invalid_witness_is_rejected(ctx):
+    import bulletproofspp_b200 as bp
+    schema, wit = EXAMPLES["bin_test"]
+    setup = bp.RangeProofSetup(ctx, schema)
+    with pytest.raises(bp.BpppError):
+        setup.prove_batch([[{"amount": 125}, {"amount": 1}, {"amount": 121}]])      # unbalanced (Binary.hs:165-167)
+    setup.close()
+    schema, wit = EXAMPLES["32by64"]
+    setup = bp.RangeProofSetup(ctx, schema)
+    with pytest.raises(bp.BpppError):
+        setup.prove_batch([[{"amount": 2 ** 64}] + wit[1:]])                          # out of range
+    setup.close()
+
+
+def test_ip_argument_is_refused_loudly(ctx):
+    """the IP argument has no device path yet: it must fail, not fall back"""
+    import bulletproofspp_b200 as bp
+    setup = bp.RangeProofSetup(ctx, EXAMPLES["64bit"][0])
+    with pytest.raises(bp.BpppError):
+        setup.prove_batch([EXAMPLES["64bit"][1]])
+    setup.close()
