@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- 128by64 aggregated reciprocal range proofs proved+verified per second (BASELINE.json).
+
+A "step" is one pass of the hot path over one batch: `batch` independent 128by64 proofs
+(examples/128by64: 128 x 64-bit values, base-256 shared digits, norm argument; N = 1024,
+M = 261, 9 rounds) PROVED and then VERIFIED through the C ABI (bppp_rp_prove_batch +
+bppp_rp_verify_batch): host C++ threads run the Fiat-Shamir transcript and the scalar phases,
+every group operation runs in the sm_100a kernels.  Proof b uses randomSeed
+"default random seed#b" and values 10000 + b, so transcripts differ.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl reference]
+
+N > 1 is launched by torchrun (one rank per GPU): every rank proves+verifies its own batch
+(weak scaling, no data-path collective; NCCL only for the barrier and the max over ranks).
+`--impl reference` times the reference's own CPU algorithm (oracle port, oracle/ + oracle/c) on
+all host cores instead.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "128by64 range proofs proved+verified/sec"
+UNIT = "proofs/s"
+R_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+
+
+def workload_schema():
+    from example_configs import EXAMPLES
+    return EXAMPLES["128by64"][0]
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [c for c in sm if c >= 0.5 * mx] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm
+def _ref_worker(args):
+    idx, n = args
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from example_configs import batched
+    from oracle.curve import SecpRef
+    from oracle.rangeproof import load_schema, load_witness, prove, verify
+    from oracle.transcript import ZKPT
+    schema, wits, seeds = batched("128by64", idx + n)
+    ok = True
+    for b in range(idx, idx + n):
+        s = load_schema(dict(schema, randomSeed=seeds[b]), SecpRef, points=_ref_worker.points)
+        proof = prove(s, ZKPT(SecpRef, s.random_seed), load_witness(s, wits[b]))
+        ok = ok and verify(s, ZKPT(SecpRef, None), proof)
+    return ok
+
+
+def _ref_init():
+    sys.path.insert(0, ROOT)
+    from oracle.curve import SecpRef
+    from oracle.transcript import get_points
+    _ref_worker.points = get_points(SecpRef, "test points", 1300)
+    SecpRef.lib()
+
+
+def run_reference(args, rank, world):
+    """The reference's CPU algorithm as written (256-row Straus `innerProduct`, 129-row
+    `projectivePairIP`, zero-padded openings) via the oracle port, one proof per task on all
+    host cores.  The Haskell reference itself cannot be built here (no GHC)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_step = cores                      # one 128by64 prove+verify per core per step (~2 s each)
+    with mp.Pool(cores, initializer=_ref_init) as pool:
+        for _ in range(args.warmup):
+            pool.map(_ref_worker, [(i, 1) for i in range(min(cores, 2))])
+        t0 = time.time()
+        for k in range(args.steps):
+            oks = pool.map(_ref_worker, [(k * per_step + i, 1) for i in range(per_step)])
+            assert all(oks)
+        dt = time.time() - t0
+    value = args.steps * per_step / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u256 (Fq/Fr integers)", "data": "synthetic",
+            "config": {"workload": "examples/128by64 prove+verify, %d proofs per step (one per host core)" % per_step,
+                       "batch": per_step},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d steps x %d proofs of 128by64 prove+verify; oracle port of the reference "
+                                       "algorithm (Python scalar phases + C group law), one process per core" % (args.steps, per_step)},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(n_proofs=4):
+    """Rank-0, N=1 only: the oracle port on ONE core (the reference runs its hot path on one core:
+    parallel strategies are commented out, NormArgument.hs:71,129), bounded sample."""
+    _ref_init()
+    t0 = time.time()
+    assert _ref_worker((0, n_proofs))
+    dt = time.time() - t0
+    return {"value": n_proofs / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d proofs of 128by64 prove+verify, oracle port of the reference algorithm "
+                      "(256-row Straus MSM, 129-row pair folds, zero-padded openings), single thread" % n_proofs}
+
+
+# --------------------------------------------------------------------------- our arm
+def make_inputs(batch, offset, n_inputs):
+    """host buffers of one step: values (10000 + proof index), types (0), per-proof seeds"""
+    vals = b"".join(int(10000 + offset + b).to_bytes(32, "little") * n_inputs for b in range(batch))
+    tys = bytes(32 * n_inputs * batch)
+    seeds = ["default random seed#%d" % (offset + b) for b in range(batch)]
+    return vals, tys, seeds
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=1024, help="proofs per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-threads", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import bulletproofspp_b200 as bp
+    ctx = bp.Context(local)
+    if args.host_threads or world > 1:
+        # ranks share the host: split the cores between them
+        nt = args.host_threads or max(1, (os.cpu_count() or 1) // world)
+        ctx.lib.bppp_set_host_threads(nt)
+    setup = bp.RangeProofSetup(ctx, workload_schema())
+    B, n = args.batch, setup.n_inputs
+    assert (setup.nrm_len, setup.lin_len, setup.rounds) == (1024, 261, 9)
+
+    def barrier():
+        ctx.sync()
+        if world > 1:
+            dist.barrier()
+
+    def step(inputs):
+        vals, tys, seeds = inputs
+        coms, resp, fin = setup.prove_batch_raw(B, vals, tys, None, seeds)
+        ok = setup.verify_batch_raw(B, coms, resp, fin)
+        return coms, resp, fin, ok
+
+    base = rank * B
+    inputs = make_inputs(B, base, n)
+    for _ in range(args.warmup):
+        out = step(inputs)
+        assert all(out[3]), "a warm-up proof failed to verify"
+    # ---- timed region 1: `value` -- inputs staged before the clock starts, device-timed
+    ctx.profile_enable(True)
+    ctx.profile_reset()
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier()
+    ctx.timer_start()
+    t0 = time.time()
+    for _ in range(args.steps):
+        out = step(inputs)
+    ms = ctx.timer_stop()
+    wall = time.time() - t0
+    barrier()
+    clocks = sampler.stop()
+    assert all(out[3])
+    rep = ctx.profile_report()
+    launches = ctx.launch_count() - launches0
+    ctx.profile_enable(False)
+    # ---- timed region 2: `e2e` -- inputs built on the host every step, results parsed back
+    barrier()
+    t0 = time.time()
+    for k in range(args.steps):
+        ins = make_inputs(B, base + (k + 1) * world * B, n)
+        coms, resp, fin, ok = step(ins)
+        n_ok = sum(ok)
+        assert n_ok == B
+    barrier()
+    e2e_s = time.time() - t0
+    t_dev, t_e2e = ms / 1e3, e2e_s
+    if world > 1:
+        t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_e2e = t.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    total = world * B * args.steps
+    # ---- rooflines from the per-kernel CUDA-event times of timed region 1
+    kern = rep["kernels"]
+    tot_ms = sum(k["ms"] for k in kern.values()) or 1.0
+    shares = {name: round(k["ms"] / tot_ms, 4) for name, k in sorted(kern.items(), key=lambda kv: -kv[1]["ms"])}
+    imad_wide, imad_lo = ctx.measure_imad_peak()
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    top = max((name for name in kern if kern[name]["work"] > 0 and name != "k_fold_dots"), key=lambda nme: kern[nme]["ms"])
+    kt = kern[top]
+    ach = kt["work"] / (kt["ms"] * 1e-3) / 1e12
+    roofline = {"kernel": top, "bound": "imad", "achieved": ach, "peak": imad_wide / 1e12, "unit": "TIMAD/s",
+                "frac": ach / (imad_wide / 1e12), "traffic": None,
+                "avg_launch_ms": kt["ms"] / kt["launches"], "share_of_gpu_time": shares[top],
+                "note": "integer-pipe bound (no hbm/tensor roofline applies): achieved = algorithmic 32x32->64 IMADs "
+                        "(SURVEY 8(d) op counts) / CUDA-event time; peak = IMAD.WIDE issue rate measured in this run"}
+    rooflines = {}
+    for name in ("k_msm_bucket", "k_pair_fold"):
+        if name in kern and kern[name]["ms"] > 0:
+            a = kern[name]["work"] / (kern[name]["ms"] * 1e-3) / 1e12
+            rooflines[name] = {"bound": "imad", "achieved": a, "peak": imad_wide / 1e12, "unit": "TIMAD/s",
+                               "frac": a / (imad_wide / 1e12), "share_of_gpu_time": shares[name]}
+    if "k_fold_dots" in kern:
+        kf = kern["k_fold_dots"]
+        a = kf["work"] / (kf["ms"] * 1e-3) / 1e9
+        rooflines["k_fold_dots"] = {"bound": "hbm", "achieved": a, "peak": hbm_peak, "unit": "GB/s", "frac": a / hbm_peak,
+                                    "traffic": None, "share_of_gpu_time": shares["k_fold_dots"],
+                                    "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback 6650 GB/s"}
+    line = {"metric": METRIC, "value": total / t_dev, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u256 (Fq/Fr integers, 8x32-bit limbs)", "data": "synthetic",
+            "config": {"workload": "examples/128by64 prove+verify (N=1024, M=261, 9 rounds), %d proofs per GPU per step" % B,
+                       "batch_per_gpu": B, "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
+                       "l2": "working set per step (%.0f MB of generators+witness vectors) exceeds the 126 MB L2" % (B * 0.33),
+                       "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world)},
+            "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": rep["h2d_bytes"] // args.steps,
+                    "d2h_bytes_per_step": rep["d2h_bytes"] // args.steps,
+                    "note": "host buffers in, proofs + verdicts out through bppp_rp_prove_batch/bppp_rp_verify_batch; "
+                            "inputs rebuilt on the host every step, wall clock"},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
+            "kernel_time_shares": shares, "gpu_busy_frac": tot_ms / ms,
+            "imad_peak": {"wide_per_s": imad_wide, "lo32_per_s": imad_lo}, "wall_s_value_leg": wall}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -2,6 +2,7 @@
 // sequencing of the NormLinear argument.  No CPU fallback: every compute entry point launches
 // the sm_100a kernels of kernels.cuh.
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdio.h>
 #include <string.h>
 #include <algorithm>
@@ -14,12 +15,62 @@
 
 using namespace bppp;
 
+enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_COUNT };
+static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
+                                                   "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
+                                                   "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg"};
+struct ProfRec {
+    int id;
+    double work;                 // algorithmic units of this launch: IMADs or bytes
+    cudaEvent_t a, b;
+};
 struct bppp_ctx {
     int dev = 0;
     cudaStream_t st = nullptr;
     std::string err;
     uint64_t launches = 0;
+    uint64_t h2d = 0, d2h = 0;
+    bool prof = false;
+    std::vector<ProfRec> pending;
+    std::vector<cudaEvent_t> pool;
+    double k_ms[K_COUNT] = {0}, k_work[K_COUNT] = {0};
+    uint64_t k_n[K_COUNT] = {0};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
+static cudaEvent_t prof_event(bppp_ctx* c) {
+    cudaEvent_t e;
+    if (!c->pool.empty()) { e = c->pool.back(); c->pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {               // wraps one kernel launch with a pair of events on the launching stream
+    bppp_ctx* c;
+    ProfScope(bppp_ctx* ctx, int id, double work) : c(ctx) {
+        c->launches++;
+        if (!c->prof) return;
+        ProfRec r;
+        r.id = id; r.work = work; r.a = prof_event(c); r.b = prof_event(c);
+        cudaEventRecord(r.a, c->st);
+        c->pending.push_back(r);
+    }
+    ~ProfScope() {
+        if (c->prof) cudaEventRecord(c->pending.back().b, c->st);
+    }
+};
+static void prof_collect(bppp_ctx* c) {
+    if (c->pending.empty()) return;
+    cudaStreamSynchronize(c->st);
+    for (auto& r : c->pending) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.a, r.b);
+        c->k_ms[r.id] += ms; c->k_work[r.id] += r.work; c->k_n[r.id]++;
+        c->pool.push_back(r.a); c->pool.push_back(r.b);
+    }
+    c->pending.clear();
+}
+#define H2D(dst, src, bytes) (ctx->h2d += (bytes), cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->st))
+#define D2H(dst, src, bytes) (ctx->d2h += (bytes), cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->st))
 
 #define CK(x)                                                                                   \
     do {                                                                                        \
@@ -36,7 +87,31 @@ struct bppp_ctx {
         ctx->err = msg;  \
         return code;     \
     } while (0)
-#define LAUNCHED(n) (ctx->launches += (n))
+
+
+// algorithmic work per launch for the rooflines: IMADs (32x32->64 multiply-accumulates)
+// for the group-law kernels, bytes for the scalar fold.
+static double msm_alg_imads(double n) {          // ceil(256/c*) (n + 2^(c*-1)) * 11 * 136
+    if (n < 1) return 0;
+    int c = (int)floor(log2(n)) - 2;
+    if (c < 4) c = 4;
+    return ceil(256.0 / c) * (n + pow(2.0, c - 1)) * 11.0 * 136.0;
+}
+#define WORK_K_MSM_BUCKET g_work
+#define WORK_K_MSM_FINISH 0
+#define WORK_K_BATCH_TO_AFFINE 0
+#define WORK_K_FB_BUILD 0
+#define WORK_K_FB_MSM 0
+#define WORK_K_PAIR_FOLD g_work
+#define WORK_K_FOLD_DOTS g_work
+#define WORK_K_BCAST_POINT 0
+#define WORK_K_FR_CONVERT 0
+#define WORK_K_DOTS_FINISH 0
+#define WORK_K_MSM_SCALARS 0
+#define WORK_K_TENSOR_EXPAND 0
+#define WORK_K_DBG_FIELD 0
+#define WORK_K_DBG_EC 0
+static thread_local double g_work = 0;           // set by the caller right before a launch
 
 namespace {
 
@@ -102,13 +177,13 @@ bool g_attr_set = false;
 
 // runs the MSMs described by plan.slices for `batch` proofs x `n_out` outputs; result Jacobian
 // points in d_res[(p*n_out + o)]
-int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res) {
+int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res, double work_per_proof = 0) {
     int nch = (int)plan.slices.size();
     if (nch == 0) FAIL(BPPP_ERR_ARG, "empty MSM");
     int max_n = 0;
     for (auto& s : plan.slices) max_n = std::max(max_n, s.n);
     CK(plan.d_slices.ensure(nch));
-    CK(cudaMemcpyAsync(plan.d_slices.p, plan.slices.data(), nch * sizeof(MsmSlice), cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(plan.d_slices.p, plan.slices.data(), nch * sizeof(MsmSlice)));
     CK(plan.d_partial.ensure(batch * n_out * nch * MSM_W));
     if (!g_attr_set) {
         CK(cudaFuncSetAttribute(k_msm_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -121,6 +196,7 @@ int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res) {
     for (size_t b0 = 0; b0 < batch; b0 += 32768) {
         size_t nb = std::min<size_t>(32768, batch - b0);
         MsmArgs B = A;
+        g_work = work_per_proof * (double)nb;
         // shift per-proof bases by b0 proofs: done by offsetting the partial pointer and using a
         // slab-local copy of the slices when b0 > 0
         if (b0 > 0) {
@@ -128,23 +204,27 @@ int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res) {
             for (auto& s : sl) { s.pts += b0 * s.pts_stride; s.sc += b0 * s.sc_stride; }
             MsmSlice* d2;
             CK(cudaMallocAsync((void**)&d2, nch * sizeof(MsmSlice), ctx->st));
-            CK(cudaMemcpyAsync(d2, sl.data(), nch * sizeof(MsmSlice), cudaMemcpyHostToDevice, ctx->st));
+            CK(H2D(d2, sl.data(), nch * sizeof(MsmSlice)));
             CK(cudaStreamSynchronize(ctx->st));
             B.slices = d2;
             B.partial = A.partial + b0 * n_out * nch * MSM_W;
+            { ProfScope ps_(ctx, K_MSM_BUCKET, WORK_K_MSM_BUCKET);
             k_msm_bucket<<<dim3(nch, n_out, (unsigned)nb), MSM_THREADS, msm_smem_bytes(max_n), ctx->st>>>(B);
+            }
             CK(cudaGetLastError());
             CK(cudaFreeAsync(d2, ctx->st));
         } else {
+            { ProfScope ps_(ctx, K_MSM_BUCKET, WORK_K_MSM_BUCKET);
             k_msm_bucket<<<dim3(nch, n_out, (unsigned)nb), MSM_THREADS, msm_smem_bytes(max_n), ctx->st>>>(B);
+            }
             CK(cudaGetLastError());
         }
-        LAUNCHED(1);
     }
     size_t n_msm = batch * n_out;
+    { ProfScope ps_(ctx, K_MSM_FINISH, WORK_K_MSM_FINISH);
     k_msm_finish<<<(unsigned)n_msm, 32, 0, ctx->st>>>(plan.d_partial.p, nch, d_res, n_msm);
+    }
     CK(cudaGetLastError());
-    LAUNCHED(1);
     return BPPP_OK;
 }
 
@@ -154,10 +234,11 @@ int to_affine(bppp_ctx* ctx, const Jac* in, size_t in_stride, Affine* out, size_
     // enough threads to fill the chip, at most 32 points per thread
     int chunk = (int)std::min<size_t>(32, std::max<size_t>(1, total / (148 * 512)));
     size_t threads = (total + chunk - 1) / chunk;
+    { ProfScope ps_(ctx, K_TO_AFFINE, WORK_K_BATCH_TO_AFFINE);
     k_batch_to_affine<<<(unsigned)((threads + 127) / 128), 128, 0, ctx->st>>>(in, in_stride, out, out_stride, out_off,
                                                                               n_per, total, chunk);
+    }
     CK(cudaGetLastError());
-    LAUNCHED(1);
     return BPPP_OK;
 }
 
@@ -196,6 +277,129 @@ extern "C" int bppp_sync(bppp_ctx* ctx) {
     return BPPP_OK;
 }
 
+// =============================================================================== profiling
+extern "C" int bppp_profile_enable(bppp_ctx* ctx, int on) {
+    if (!ctx) return BPPP_ERR_ARG;
+    cudaSetDevice(ctx->dev);
+    prof_collect(ctx);
+    ctx->prof = on != 0;
+    return BPPP_OK;
+}
+extern "C" int bppp_profile_reset(bppp_ctx* ctx) {
+    if (!ctx) return BPPP_ERR_ARG;
+    cudaSetDevice(ctx->dev);
+    prof_collect(ctx);
+    for (int i = 0; i < K_COUNT; i++) { ctx->k_ms[i] = 0; ctx->k_work[i] = 0; ctx->k_n[i] = 0; }
+    ctx->h2d = ctx->d2h = 0;
+    return BPPP_OK;
+}
+// JSON: {"kernels": {"name": {"launches": n, "ms": total, "work": algorithmic units}, ...}, "h2d_bytes":.., "d2h_bytes":..}
+extern "C" int bppp_profile_report(bppp_ctx* ctx, char* out, size_t cap) {
+    if (!ctx || !out) return BPPP_ERR_ARG;
+    cudaSetDevice(ctx->dev);
+    prof_collect(ctx);
+    std::string j = "{\"kernels\": {";
+    bool first = true;
+    char buf[256];
+    for (int i = 0; i < K_COUNT; i++) {
+        if (!ctx->k_n[i]) continue;
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ",
+                 kKernelNames[i], (unsigned long long)ctx->k_n[i], ctx->k_ms[i], ctx->k_work[i]);
+        j += buf;
+        first = false;
+    }
+    snprintf(buf, sizeof buf, "}, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"launches\": %llu}", (unsigned long long)ctx->h2d,
+             (unsigned long long)ctx->d2h, (unsigned long long)ctx->launches);
+    j += buf;
+    if (j.size() + 1 > cap) FAIL(BPPP_ERR_ARG, "report buffer too small");
+    memcpy(out, j.c_str(), j.size() + 1);
+    return BPPP_OK;
+}
+// CUDA-event timer on the context's stream (the stream every kernel of this library is launched on)
+extern "C" int bppp_timer_start(bppp_ctx* ctx) {
+    if (!ctx) return BPPP_ERR_ARG;
+    CK(cudaSetDevice(ctx->dev));
+    if (!ctx->t0) { CK(cudaEventCreate(&ctx->t0)); CK(cudaEventCreate(&ctx->t1)); }
+    CK(cudaStreamSynchronize(ctx->st));
+    CK(cudaEventRecord(ctx->t0, ctx->st));
+    return BPPP_OK;
+}
+extern "C" int bppp_timer_stop(bppp_ctx* ctx, double* ms) {
+    if (!ctx || !ms || !ctx->t0) return BPPP_ERR_ARG;
+    CK(cudaSetDevice(ctx->dev));
+    CK(cudaEventRecord(ctx->t1, ctx->st));
+    CK(cudaEventSynchronize(ctx->t1));
+    float f = 0;
+    CK(cudaEventElapsedTime(&f, ctx->t0, ctx->t1));
+    *ms = f;
+    return BPPP_OK;
+}
+// Measured integer peak: dependency-free streams of 32x32->64 multiply-accumulates (the IMAD.WIDE
+// the field multiplier is made of) and of 32-bit IMADs, on every SM.  Results in ops/second.
+__global__ void k_imad_peak_wide(unsigned long long* out, unsigned a, unsigned b, int iters) {
+    unsigned long long acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
+    unsigned x = a + threadIdx.x, y = b + blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = (unsigned long long)x * y + acc[i];
+            x ^= (unsigned)acc[0];
+        }
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[i];
+    if (s == 0x1234567ULL) out[0] = s;
+}
+__global__ void k_imad_peak_lo(unsigned* out, unsigned a, unsigned b, int iters) {
+    unsigned acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[i] = threadIdx.x + i;
+    unsigned x = a + threadIdx.x, y = b + blockIdx.x;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i] = x * y + acc[i];
+            x ^= acc[0];
+        }
+    }
+    unsigned s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s ^= acc[i];
+    if (s == 0x1234567u) out[0] = s;
+}
+extern "C" int bppp_measure_imad_peak(bppp_ctx* ctx, double* wide_per_s, double* lo_per_s) {
+    if (!ctx || !wide_per_s || !lo_per_s) return BPPP_ERR_ARG;
+    CK(cudaSetDevice(ctx->dev));
+    DBuf<unsigned long long> d;
+    CK(d.alloc(4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    const int blocks = 148 * 8, threads = 256, iters = 4096;
+    double best[2] = {0, 0};
+    for (int rep = 0; rep < 4; rep++) {
+        for (int kind = 0; kind < 2; kind++) {
+            CK(cudaEventRecord(e0, ctx->st));
+            if (kind == 0) k_imad_peak_wide<<<blocks, threads, 0, ctx->st>>>(d.p, 12345u + rep, 6789u, iters);
+            else k_imad_peak_lo<<<blocks, threads, 0, ctx->st>>>((unsigned*)d.p, 12345u + rep, 6789u, iters);
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(e1, ctx->st));
+            CK(cudaEventSynchronize(e1));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, e0, e1));
+            double ops = (double)blocks * threads * iters * 64.0 / (ms * 1e-3);
+            if (rep > 0 && ops > best[kind]) best[kind] = ops;
+        }
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *wide_per_s = best[0]; *lo_per_s = best[1];
+    return BPPP_OK;
+}
+
 // =============================================================================== MSM seam
 extern "C" int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8_t* scalars, const uint8_t* points,
                               int shared_points, uint8_t* out) {
@@ -216,15 +420,15 @@ extern "C" int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8
     CK(d_pts.alloc(npts));
     CK(d_res.alloc(batch));
     CK(d_aff.alloc(batch));
-    CK(cudaMemcpyAsync(d_sc.p, scalars, batch * n * 32, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(d_pts.p, points, npts * 64, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(d_sc.p, scalars, batch * n * 32));
+    CK(H2D(d_pts.p, points, npts * 64));
     MsmPlan plan;
     plan.add(d_pts.p, shared_points ? 0 : n, d_sc.p, n, 0, n);
-    int rc = run_msm(ctx, plan, batch, 1, d_res.p);
+    int rc = run_msm(ctx, plan, batch, 1, d_res.p, msm_alg_imads((double)n));
     if (rc) return rc;
     rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, d_aff.p, batch * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(D2H(out, d_aff.p, batch * 64));
     CK(cudaStreamSynchronize(ctx->st));
     return BPPP_OK;
 }
@@ -255,10 +459,11 @@ extern "C" int bppp_fb_create(bppp_ctx* ctx, size_t n_bases, const uint8_t* poin
         ctx->err = cudaGetErrorString(e);
         return BPPP_ERR_CUDA;
     }
-    cudaMemcpyAsync(d_b.p, points, n_bases * 64, cudaMemcpyHostToDevice, ctx->st);
+    H2D(d_b.p, points, n_bases * 64);
     int nt = (int)(n_bases * FB_WINDOWS);
+    { ProfScope ps_(ctx, K_FB_BUILD, WORK_K_FB_BUILD);
     k_fb_build<<<(nt + 31) / 32, 32, 0, ctx->st>>>(d_b.p, (int)n_bases, d_j.p);
-    LAUNCHED(1);
+    }
     int rc = to_affine(ctx, d_j.p, total, fb->tbl.p, total, 0, (int)total, total);
     if (rc == 0 && (e = cudaStreamSynchronize(ctx->st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
     if (rc) { delete fb; return rc; }
@@ -275,13 +480,14 @@ extern "C" int bppp_fb_msm_batch(bppp_fb* fb, size_t batch, const uint8_t* scala
     DBuf<Jac> d_res;
     DBuf<Affine> d_aff;
     CK(d_sc.alloc(batch * fb->n_bases)); CK(d_res.alloc(batch)); CK(d_aff.alloc(batch));
-    CK(cudaMemcpyAsync(d_sc.p, scalars, batch * fb->n_bases * 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(d_sc.p, scalars, batch * fb->n_bases * 32));
+    { ProfScope ps_(ctx, K_FB_MSM, WORK_K_FB_MSM);
     k_fb_msm<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->st>>>(fb->tbl.p, (int)fb->n_bases, d_sc.p, d_res.p, batch);
+    }
     CK(cudaGetLastError());
-    LAUNCHED(1);
     int rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, d_aff.p, batch * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(D2H(out, d_aff.p, batch * 64));
     CK(cudaStreamSynchronize(ctx->st));
     return BPPP_OK;
 }
@@ -313,11 +519,17 @@ int launch_pair_fold(bppp_ctx* ctx, const Affine* in, size_t in_stride, Jac* out
     for (size_t b0 = 0; b0 < batch; b0 += 65535) {
         size_t nb = std::min<size_t>(65535, batch - b0);
         PairFoldArgs B = A;
+        {   // half-length Shamir (129 dbl * 7 + 97 add * 11 Fq mults) * 136 IMAD per folded point
+            double outs = 0;
+            for (int s2 = 0; s2 < n_seg; s2++) outs += (segs[s2].n_in + 1) / 2;
+            g_work = outs * (double)nb * (129.0 * 7 + 97.0 * 11) * 136.0;
+        }
         B.in = in + b0 * in_stride; B.out = out + b0 * out_stride;
         B.kb = kb + b0 * n_seg; B.ka = ka + b0 * n_seg; B.sgn = sgn + b0 * n_seg;
+        { ProfScope ps_(ctx, K_PAIR_FOLD, WORK_K_PAIR_FOLD);
         k_pair_fold<<<dim3(total_blocks, (unsigned)nb), PF_THREADS, smem, ctx->st>>>(B);
+        }
         CK(cudaGetLastError());
-        LAUNCHED(1);
     }
     return BPPP_OK;
 }
@@ -340,15 +552,15 @@ extern "C" int bppp_pair_fold(bppp_ctx* ctx, size_t n_in, const uint8_t a[32], i
     CK(d_in.alloc(n_in)); CK(d_out.alloc(n_out)); CK(d_j.alloc(n_out)); CK(d_k.alloc(2)); CK(d_s.alloc(1));
     unsigned char sg = (unsigned char)((b_neg ? 1 : 0) | (a_neg ? 2 : 0));
     u256 ks[2] = {kb, ka};
-    CK(cudaMemcpyAsync(d_in.p, points_in, n_in * 64, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(d_k.p, ks, 64, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(d_s.p, &sg, 1, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(d_in.p, points_in, n_in * 64));
+    CK(H2D(d_k.p, ks, 64));
+    CK(H2D(d_s.p, &sg, 1));
     PairFoldSeg seg = {0, (int)n_in, 0};
     int rc = launch_pair_fold(ctx, d_in.p, 0, d_j.p, 0, &seg, 1, d_k.p, d_k.p + 1, d_s.p, 1);
     if (rc) return rc;
     rc = to_affine(ctx, d_j.p, n_out, d_out.p, n_out, 0, (int)n_out, n_out);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(points_out, d_out.p, n_out * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(D2H(points_out, d_out.p, n_out * 64));
     CK(cudaStreamSynchronize(ctx->st));
     return BPPP_OK;
 }
@@ -412,9 +624,11 @@ int launch_fold_dots(bppp_nl* h, int fold) {
         A.n_in = (int)h->curN; A.fold = fold;
         A.au = A.av = cptr(h, C_AU); A.bu = A.bv = cptr(h, C_BU);
         A.rho = cptr(h, C_RHO); A.m1 = 1; A.m2 = 4; A.partial = h->part_n.p;
+        g_work = 32.0 * (double)h->B * (fold ? (double)(h->curN + ny) : (double)h->curN);
+        { ProfScope ps_(ctx, K_FOLD_DOTS, WORK_K_FOLD_DOTS);
         k_fold_dots<<<dim3(h->blocks_n, (unsigned)h->B), 256, 0, ctx->st>>>(A);
+        }
         CK(cudaGetLastError());
-        LAUNCHED(1);
     }
     if (h->curM) {
         size_t ny = fold ? (h->curM + 1) / 2 : h->curM;
@@ -426,15 +640,17 @@ int launch_fold_dots(bppp_nl* h, int fold) {
         A.n_in = (int)h->curM; A.fold = fold;
         A.au = cptr(h, C_AC); A.bu = cptr(h, C_BC); A.av = cptr(h, C_AL); A.bv = cptr(h, C_BL);
         A.rho = nullptr; A.m1 = 3; A.m2 = 4; A.partial = h->part_l.p;
+        g_work = 2 * 32.0 * (double)h->B * (fold ? (double)(h->curM + ny) : (double)h->curM);
+        { ProfScope ps_(ctx, K_FOLD_DOTS, WORK_K_FOLD_DOTS);
         k_fold_dots<<<dim3(h->blocks_l, (unsigned)h->B), 256, 0, ctx->st>>>(A);
+        }
         CK(cudaGetLastError());
-        LAUNCHED(1);
     }
     return BPPP_OK;
 }
 int upload_consts(bppp_nl* h, int which, const std::vector<u256>& v) {
     bppp_ctx* ctx = h->ctx;
-    CK(cudaMemcpyAsync(cptr(h, which), v.data(), v.size() * 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(cptr(h, which), v.data(), v.size() * 32));
     return BPPP_OK;
 }
 }  // namespace
@@ -472,23 +688,25 @@ extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
     CKH(h->jscratch.alloc(batch * (h->N2 + h->M2)));
     CKH(h->res.alloc(batch * 2));
     // generators
-    CKH(cudaMemcpyAsync(h->base.p, g, 64, cudaMemcpyHostToDevice, ctx->st));
-    if (N) CKH(cudaMemcpyAsync(h->base.p + 1, G, N * 64, cudaMemcpyHostToDevice, ctx->st));
-    if (M) CKH(cudaMemcpyAsync(h->base.p + 1 + N, H, M * 64, cudaMemcpyHostToDevice, ctx->st));
+    CKH(H2D(h->base.p, g, 64));
+    if (N) CKH(H2D(h->base.p + 1, G, N * 64));
+    if (M) CKH(H2D(h->base.p + 1 + N, H, M * 64));
     for (int k = 0; k < 2; k++) {
+        { ProfScope ps_(ctx, K_BCAST, WORK_K_BCAST_POINT);
         k_bcast_point<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->st>>>(h->base.p, h->pts[k].p, h->P2, batch);
+        }
         CKH(cudaGetLastError());
-        LAUNCHED(1);
     }
     // scalars -> Montgomery on the device (staged through the scalar scratch buffer)
     struct { const uint8_t* src; u256* dst; size_t n; } up[3] = {
         {w, h->w[0].p, batch * N}, {l, h->l[0].p, batch * M}, {c, h->c[0].p, batch * M}};
     for (auto& u : up) {
         if (!u.n) continue;
-        CKH(cudaMemcpyAsync(h->sc.p, u.src, u.n * 32, cudaMemcpyHostToDevice, ctx->st));
+        CKH(H2D(h->sc.p, u.src, u.n * 32));
+        { ProfScope ps_(ctx, K_FR_CONVERT, WORK_K_FR_CONVERT);
         k_fr_convert<<<(unsigned)((u.n + 255) / 256), 256, 0, ctx->st>>>(h->sc.p, u.dst, u.n, 1);
+        }
         CKH(cudaGetLastError());
-        LAUNCHED(1);
     }
     CKH(cudaMemsetAsync(h->sc.p, 0, 2 * batch * h->P0 * 32, ctx->st));
     // host state
@@ -545,7 +763,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     }
     if ((rc = upload_consts(h, C_K1, k1))) return rc;
     if ((rc = upload_consts(h, C_K2, k2))) return rc;
-    CK(cudaMemcpyAsync(cptr(h, C_COEF), coef.data(), B * 8 * 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(cptr(h, C_COEF), coef.data(), B * 8 * 32));
     const size_t P0 = h->P0;
     u256* xs = h->sc.p;
     u256* rs = h->sc.p + B * P0;
@@ -556,9 +774,10 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         if (h->curN) { A.partial[A.n_seg] = h->part_n.p; A.n_blocks[A.n_seg] = h->blocks_n; A.k1[A.n_seg] = cptr(h, C_K1); A.k2[A.n_seg] = cptr(h, C_K2); A.n_seg++; }
         if (h->curM) { A.partial[A.n_seg] = h->part_l.p; A.n_blocks[A.n_seg] = h->blocks_l; A.k1[A.n_seg] = nullptr; A.k2[A.n_seg] = nullptr; A.n_seg++; }
         A.res = h->dots.p; A.xs = xs; A.rs = rs; A.sc_stride = P0; A.batch = (int)B;
+        { ProfScope ps_(ctx, K_DOTS_FINISH, WORK_K_DOTS_FINISH);
         k_dots_finish<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(A);
+        }
         CK(cudaGetLastError());
-        LAUNCHED(1);
     }
     const int src = h->cur;
     if (h->curN) {
@@ -567,9 +786,10 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1; A.coef = cptr(h, C_COEF);
         const unsigned char kd[8] = {0, 2, 2, 0, 0, 0, 0, 1};
         memcpy(A.kind, kd, 8);
+        { ProfScope ps_(ctx, K_MSM_SCALARS, WORK_K_MSM_SCALARS);
         k_msm_scalars<<<dim3((unsigned)(((h->curN + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        }
         CK(cudaGetLastError());
-        LAUNCHED(1);
     }
     if (h->curM) {
         MsmScalarsArgs A;
@@ -577,21 +797,25 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1 + (int)h->curN; A.coef = cptr(h, C_COEF);
         const unsigned char kd[8] = {0, 1, 1, 0, 0, 0, 0, 1};
         memcpy(A.kind, kd, 8);
+        { ProfScope ps_(ctx, K_MSM_SCALARS, WORK_K_MSM_SCALARS);
         k_msm_scalars<<<dim3((unsigned)(((h->curM + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        }
         CK(cudaGetLastError());
-        LAUNCHED(1);
     }
     // the two commitments: MSMs over [g | G | H] with X scalars (output 0) and R scalars (output 1)
     h->plan.slices.clear();
     const size_t nterms = 1 + h->curN + h->curM;
     if (h->curp < 0) h->plan.add(h->base.p, 0, xs, P0, B * P0, nterms);
     else h->plan.add(h->pts[h->curp].p, h->P2, xs, P0, B * P0, nterms);
-    if ((rc = run_msm(ctx, h->plan, B, 2, h->res.p))) return rc;
+    {
+        double nX = (double)nterms, nR = 1.0 + (double)((h->curN + 1) / 2) + (double)((h->curM + 1) / 2);
+        if ((rc = run_msm(ctx, h->plan, B, 2, h->res.p, msm_alg_imads(nX) + msm_alg_imads(nR)))) return rc;
+    }
     if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2))) return rc;
     std::vector<Affine> xr(B * 2);
     std::vector<u256> dots(B * 2);
-    CK(cudaMemcpyAsync(xr.data(), h->aff.p, B * 2 * 64, cudaMemcpyDeviceToHost, ctx->st));
-    CK(cudaMemcpyAsync(dots.data(), h->dots.p, B * 2 * 32, cudaMemcpyDeviceToHost, ctx->st));
+    CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
+    CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
     CK(cudaStreamSynchronize(ctx->st));
     for (size_t b = 0; b < B; b++) {
         memcpy(X + 64 * b, &xr[2 * b], 64);
@@ -652,8 +876,8 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
         (rc = upload_consts(h, C_BL, bl)) || (rc = upload_consts(h, C_AC, ac)) || (rc = upload_consts(h, C_BC, bc)) ||
         (rc = upload_consts(h, C_RHO, rho)))
         return rc;
-    CK(cudaMemcpyAsync(cptr(h, C_KB), kk.data(), B * 4 * 32, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(h->sgn.p, sg.data(), B * 2, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(cptr(h, C_KB), kk.data(), B * 4 * 32));
+    CK(H2D(h->sgn.p, sg.data(), B * 2));
     // scalar vectors (and the next round's dots)
     if ((rc = launch_fold_dots(h, 1))) return rc;
     // generators
@@ -687,13 +911,13 @@ extern "C" int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
     for (size_t b = 0; b < B; b++) {
         if (s) host::to_bytes(s + 32 * b, fr::from_mont(h->s[b]));
         if (w && h->curN) {
-            CK(cudaMemcpyAsync(hw.data(), h->w[h->cur].p + b * h->wstride[h->cur], h->curN * 32, cudaMemcpyDeviceToHost, ctx->st));
+            CK(D2H(hw.data(), h->w[h->cur].p + b * h->wstride[h->cur], h->curN * 32));
             CK(cudaStreamSynchronize(ctx->st));
             for (size_t i = 0; i < h->curN; i++)
                 host::to_bytes(w + 32 * (b * h->curN + i), fr::from_mont(fr::mul(h->nn[b], hw[i])));
         }
         if (l && h->curM) {
-            CK(cudaMemcpyAsync(hl.data(), h->l[h->cur].p + b * h->lstride[h->cur], h->curM * 32, cudaMemcpyDeviceToHost, ctx->st));
+            CK(D2H(hl.data(), h->l[h->cur].p + b * h->lstride[h->cur], h->curM * 32));
             CK(cudaStreamSynchronize(ctx->st));
             for (size_t i = 0; i < h->curM; i++)
                 host::to_bytes(l + 32 * (b * h->curM + i), fr::from_mont(fr::mul(h->nl[b], hl[i])));
@@ -730,13 +954,15 @@ extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
     CK(pub.alloc(B * N)); CK(cm.alloc(B * M)); CK(vs_n.alloc(B * n_norm)); CK(vs_l.alloc(B * n_lin));
     CK(f0n.alloc(B * k)); CK(f1.alloc(B * k)); CK(f0l.alloc(B * k)); CK(res.alloc(B));
     CK(tmp.alloc(std::max(B * N, B * M)));
-    CK(cudaMemcpyAsync(base.p, g, 64, cudaMemcpyHostToDevice, ctx->st));
-    if (N) CK(cudaMemcpyAsync(base.p + 1, G, N * 64, cudaMemcpyHostToDevice, ctx->st));
-    if (M) CK(cudaMemcpyAsync(base.p + 1 + N, H, M * 64, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(base.p, g, 64));
+    if (N) CK(H2D(base.p + 1, G, N * 64));
+    if (M) CK(H2D(base.p + 1 + N, H, M * 64));
     if (N) {
-        CK(cudaMemcpyAsync(tmp.p, pub_w, B * N * 32, cudaMemcpyHostToDevice, ctx->st));
+        CK(H2D(tmp.p, pub_w, B * N * 32));
+        { ProfScope ps_(ctx, K_FR_CONVERT, WORK_K_FR_CONVERT);
         k_fr_convert<<<(unsigned)((B * N + 255) / 256), 256, 0, ctx->st>>>(tmp.p, pub.p, B * N, 1);
-        CK(cudaGetLastError()); LAUNCHED(1);
+        }
+        CK(cudaGetLastError());
     }
     // host: challenges, tensor factors, final-witness scalar sc  (NormArgument.hs:131-145, 73-81)
     std::vector<u256> hf0n(B * k), hf1(B * k), hf0l(B * k, fr::one()), hvn(B * n_norm), hvl(B * n_lin);
@@ -773,30 +999,34 @@ extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
         }
     }
     if (k) {
-        CK(cudaMemcpyAsync(f0n.p, hf0n.data(), B * k * 32, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaMemcpyAsync(f1.p, hf1.data(), B * k * 32, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaMemcpyAsync(f0l.p, hf0l.data(), B * k * 32, cudaMemcpyHostToDevice, ctx->st));
+        CK(H2D(f0n.p, hf0n.data(), B * k * 32));
+        CK(H2D(f1.p, hf1.data(), B * k * 32));
+        CK(H2D(f0l.p, hf0l.data(), B * k * 32));
     }
-    if (n_norm) CK(cudaMemcpyAsync(vs_n.p, hvn.data(), B * n_norm * 32, cudaMemcpyHostToDevice, ctx->st));
-    if (n_lin) CK(cudaMemcpyAsync(vs_l.p, hvl.data(), B * n_lin * 32, cudaMemcpyHostToDevice, ctx->st));
+    if (n_norm) CK(H2D(vs_n.p, hvn.data(), B * n_norm * 32));
+    if (n_lin) CK(H2D(vs_l.p, hvl.data(), B * n_lin * 32));
     if (NX) {
-        CK(cudaMemcpyAsync(xsc.p, hx.data(), B * NX * 32, cudaMemcpyHostToDevice, ctx->st));
-        CK(cudaMemcpyAsync(extra.p, hp.data(), B * NX * 64, cudaMemcpyHostToDevice, ctx->st));
+        CK(H2D(xsc.p, hx.data(), B * NX * 32));
+        CK(H2D(extra.p, hp.data(), B * NX * 64));
     }
     if (N) {
         TensorArgs A;
         A.pub = pub.p; A.pub_stride = N; A.vs = vs_n.p; A.n_vs = (int)n_norm; A.f0 = f0n.p; A.f1 = f1.p; A.k = (int)k;
         A.out = sc.p; A.out_stride = P0; A.off = 1; A.n = (int)N;
+        { ProfScope ps_(ctx, K_TENSOR, WORK_K_TENSOR_EXPAND);
         k_tensor_expand<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
-        CK(cudaGetLastError()); LAUNCHED(1);
+        }
+        CK(cudaGetLastError());
     }
     std::vector<u256> tl(B * M);
     if (M) {
         TensorArgs A;
         A.pub = nullptr; A.pub_stride = 0; A.vs = vs_l.p; A.n_vs = (int)n_lin; A.f0 = f0l.p; A.f1 = f1.p; A.k = (int)k;
         A.out = sc.p; A.out_stride = P0; A.off = 1 + (int)N; A.n = (int)M;
+        { ProfScope ps_(ctx, K_TENSOR, WORK_K_TENSOR_EXPAND);
         k_tensor_expand<<<dim3((unsigned)((M + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
-        CK(cudaGetLastError()); LAUNCHED(1);
+        }
+        CK(cudaGetLastError());
         // sc_lin = sum_j c_j * tensor_j  (contract' . tensor', NormArgument.hs:75-78); the kernel wrote -tensor_j
         CK(cudaMemcpy2DAsync(tl.data(), M * 32, sc.p + 1 + N, P0 * 32, M * 32, B, cudaMemcpyDeviceToHost, ctx->st));
     }
@@ -811,11 +1041,11 @@ extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
     MsmPlan plan;
     plan.add(base.p, 0, sc.p, P0, 0, P0);
     if (NX) plan.add(extra.p, NX, xsc.p, NX, 0, NX);
-    int rc = run_msm(ctx, plan, B, 1, res.p);
+    int rc = run_msm(ctx, plan, B, 1, res.p, msm_alg_imads((double)(P0 + NX)));
     if (rc) return rc;
     if ((rc = to_affine(ctx, res.p, 1, aff.p, 1, 0, 1, B))) return rc;
     std::vector<Affine> out(B);
-    CK(cudaMemcpyAsync(out.data(), aff.p, B * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(D2H(out.data(), aff.p, B * 64));
     CK(cudaStreamSynchronize(ctx->st));
     for (size_t b = 0; b < B; b++) ok[b] = aff_is_inf(out[b]) ? 1 : 0;
     return BPPP_OK;
@@ -827,11 +1057,13 @@ extern "C" int bppp_dbg_field(bppp_ctx* ctx, int op, size_t n, const uint8_t* a,
     CK(cudaSetDevice(ctx->dev));
     DBuf<u256> da, db, dc;
     CK(da.alloc(n)); CK(db.alloc(n)); CK(dc.alloc(n));
-    CK(cudaMemcpyAsync(da.p, a, n * 32, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(da.p, a, n * 32));
+    CK(H2D(db.p, b, n * 32));
+    { ProfScope ps_(ctx, K_DBG, WORK_K_DBG_FIELD);
     k_dbg_field<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(da.p, db.p, dc.p, n, op);
-    CK(cudaGetLastError()); LAUNCHED(1);
-    CK(cudaMemcpyAsync(out, dc.p, n * 32, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    CK(cudaGetLastError());
+    CK(D2H(out, dc.p, n * 32));
     CK(cudaStreamSynchronize(ctx->st));
     return BPPP_OK;
 }
@@ -841,13 +1073,15 @@ extern "C" int bppp_dbg_ec(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, co
     DBuf<Affine> da, db, dd;
     DBuf<Jac> dc;
     CK(da.alloc(n)); CK(db.alloc(n)); CK(dc.alloc(n)); CK(dd.alloc(n));
-    CK(cudaMemcpyAsync(da.p, a, n * 64, cudaMemcpyHostToDevice, ctx->st));
-    CK(cudaMemcpyAsync(db.p, b, n * 64, cudaMemcpyHostToDevice, ctx->st));
+    CK(H2D(da.p, a, n * 64));
+    CK(H2D(db.p, b, n * 64));
+    { ProfScope ps_(ctx, K_DBG, WORK_K_DBG_EC);
     k_dbg_ec<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(da.p, db.p, dc.p, n, op);
-    CK(cudaGetLastError()); LAUNCHED(1);
+    }
+    CK(cudaGetLastError());
     int rc = to_affine(ctx, dc.p, n, dd.p, n, 0, (int)n, n);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(out, dd.p, n * 64, cudaMemcpyDeviceToHost, ctx->st));
+    CK(D2H(out, dd.p, n * 64));
     CK(cudaStreamSynchronize(ctx->st));
     return BPPP_OK;
 }

@@ -17,6 +17,8 @@ EXPORTS = [
     "bppp_rp_setup", "bppp_rp_free", "bppp_rp_last_error", "bppp_rp_info", "bppp_rp_points", "bppp_input_blind",
     "bppp_set_host_threads", "bppp_rp_prove_batch", "bppp_rp_verify_batch",
     "bppp_host_sha256", "bppp_host_oracle", "bppp_host_fr", "bppp_host_get_points",
+    "bppp_profile_enable", "bppp_profile_reset", "bppp_profile_report", "bppp_timer_start", "bppp_timer_stop",
+    "bppp_measure_imad_peak",
 ]
 
 
@@ -62,6 +64,12 @@ def load_library():
                                    u8p, u8p, sz, u8p, u8p, C.POINTER(ip)]
     lib.bppp_dbg_field.argtypes = [vp, ip, sz, u8p, u8p, u8p]
     lib.bppp_dbg_ec.argtypes = [vp, ip, sz, u8p, u8p, u8p]
+    lib.bppp_profile_enable.argtypes = [vp, ip]
+    lib.bppp_profile_reset.argtypes = [vp]
+    lib.bppp_profile_report.argtypes = [vp, C.c_char_p, sz]
+    lib.bppp_timer_start.argtypes = [vp]
+    lib.bppp_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.bppp_measure_imad_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     lib.bppp_fb_create.argtypes = [vp, sz, u8p, C.POINTER(vp)]
     lib.bppp_fb_msm_batch.argtypes = [vp, sz, u8p, u8p]
     lib.bppp_fb_destroy.argtypes = [vp]
@@ -173,6 +181,32 @@ class Context:
 
     def sync(self):
         self._ck(self.lib.bppp_sync(self.h), "bppp_sync")
+
+    # -- measurement support
+    def profile_enable(self, on=True):
+        self._ck(self.lib.bppp_profile_enable(self.h, 1 if on else 0), "bppp_profile_enable")
+
+    def profile_reset(self):
+        self._ck(self.lib.bppp_profile_reset(self.h), "bppp_profile_reset")
+
+    def profile_report(self):
+        import json
+        buf = _buf(8192)
+        self._ck(self.lib.bppp_profile_report(self.h, buf, 8192), "bppp_profile_report")
+        return json.loads(buf.value.decode())
+
+    def timer_start(self):
+        self._ck(self.lib.bppp_timer_start(self.h), "bppp_timer_start")
+
+    def timer_stop(self):
+        ms = C.c_double()
+        self._ck(self.lib.bppp_timer_stop(self.h, C.byref(ms)), "bppp_timer_stop")
+        return ms.value
+
+    def measure_imad_peak(self):
+        a, b = C.c_double(), C.c_double()
+        self._ck(self.lib.bppp_measure_imad_peak(self.h, C.byref(a), C.byref(b)), "bppp_measure_imad_peak")
+        return a.value, b.value
 
     # -- `commit` / `innerProduct` (src/Commitment.hs:416-417, 325-335)
     def msm(self, pairs):

@@ -41,6 +41,15 @@ uint64_t bppp_launch_count(bppp_ctx* ctx);
 /* block until every queued operation of the context has finished */
 int bppp_sync(bppp_ctx* ctx);
 
+/* ---- measurement support (bench.py): per-kernel CUDA-event timing on the launching stream,
+ * host<->device copy counters, a stream timer and the measured integer peak. */
+int bppp_profile_enable(bppp_ctx* ctx, int on);
+int bppp_profile_reset(bppp_ctx* ctx);
+int bppp_profile_report(bppp_ctx* ctx, char* out_json, size_t cap);
+int bppp_timer_start(bppp_ctx* ctx);
+int bppp_timer_stop(bppp_ctx* ctx, double* ms);
+int bppp_measure_imad_peak(bppp_ctx* ctx, double* wide_per_s, double* lo_per_s);
+
 /* ---- MSM seam: `commit` = `innerProduct . openToList` (src/Commitment.hs:416-417, 325-335),
  * i.e. FastInnerProduct.innerProduct :: [(Scalar v, v)] -> v.  out = sum_i scalars[i] * points[i]. */
 int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t out[64]);

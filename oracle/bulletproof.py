@@ -110,11 +110,12 @@ class NLLinear:
         a, b = rational_reduce_scalar(self._ratio(e))
         a0, b0 = a % R, b % R
         b0i = inv(b0)
-        cs, xs, gs = [], [], []
+        cs, xs, gp = [], [], []
         for (cL, xL, gL), (cR, xR, gR) in self._pairs():
             cs.append((b0 * cL + a0 * cR) % R)
             xs.append((b0i * xL + e * b0i % R * xR) % R)
-            gs.append(self.G.msm([(b, gL), (a, gR)]))      # collapsePoints b' a' gL gR
+            gp.append((gL, gR))
+        gs = self.G.pair_ip_many(b, a, gp)                  # collapsePoints b' a' gL gR
         return type(self)(self.G, cs, xs, gs, self.n * b0)
 
     def _tensor_es(self, es):
@@ -178,10 +179,11 @@ class NLNorm:
         a, b = rational_reduce_scalar(e * qi % R)
         b0 = b % R
         b0i = inv(b0)
-        xs, gs = [], []
+        xs, gp = [], []
         for (xL, gL), (xR, gR) in halves(list(zip(self.xs, self.gs)), (0, self.G.zero)):
             xs.append((b0i * xL + e * q % R * b0i % R * xR) % R)
-            gs.append(self.G.msm([(b, gL), (a, gR)]))
+            gp.append((gL, gR))
+        gs = self.G.pair_ip_many(b, a, gp)
         return NLNorm(self.G, q * q % R, xs, gs, self.n * b0 % R * qi, qi * qi % R)
 
     def expand_challenges(self, es, pub, basis):
@@ -249,12 +251,12 @@ class IPInner:
         b0i = inv(b % R)
         c, d = rational_reduce_scalar(e)
         d0i = inv(d % R)
+        prs = self._pairs()
+        gs = self.G.pair_ip_many(b, a, [(L[1], Rr[1]) for L, Rr in prs])
+        hs = self.G.pair_ip_many(d, c, [(L[3], Rr[3]) for L, Rr in prs])
         body = []
-        for (xL, gL, yL, hL), (xR, gR, yR, hR) in self._pairs():
-            body.append(((b0i * (xL + e * q % R * xR)) % R,
-                         self.G.msm([(b, gL), (a, gR)]),
-                         (d0i * (yL + ei * yR)) % R,
-                         self.G.msm([(d, hL), (c, hR)])))
+        for ((xL, gL, yL, hL), (xR, gR, yR, hR)), g2, h2 in zip(prs, gs, hs):
+            body.append(((b0i * (xL + e * q % R * xR)) % R, g2, (d0i * (yL + ei * yR)) % R, h2))
         return IPInner(self.G, self.s, q * q % R, body, self.nx * (b % R) % R * qi,
                        self.ny * (d % R), qi * qi % R)
 

@@ -181,6 +181,11 @@ class Secp256k1:
     def msm_many(cls, list_of_pairs):
         return _to_affine_many([cls.msm_jac(list(p)) for p in list_of_pairs])
 
+    @classmethod
+    def pair_ip_many(cls, b, a, pairs):
+        """`collapsePoints b a gL gR` (src/Bulletproof.hs:213-214) for a list of pairs."""
+        return _to_affine_many([cls.msm_jac([(b, l), (a, r)]) for l, r in pairs])
+
     @staticmethod
     def coords(P):
         """Affine coordinates for the transcript (app/Main.hs:78-80)."""
@@ -259,6 +264,68 @@ def straus_reference(pairs):
     return (X * zi % _P, Y * zi % _P)
 
 
+class SecpRef(Secp256k1):
+    """secp256k1 with the reference's own algorithms for `commit` (256-row Straus, ref_msm) and
+    `collapsePoints` (129-row pair product, ref_pair_ip), from oracle/c/ref_ec.c.  Used to time
+    "the reference's CPU path as written"; results equal Secp256k1's (same group elements) unless
+    the reference's incomplete mixed add hits P + P."""
+    name = "secp256k1"
+    _lib = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            import ctypes
+            import os
+            path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libbppp_oracle.so")
+            if not os.path.exists(path):
+                raise RuntimeError("oracle C library not built: run `make -C oracle`")
+            L = ctypes.CDLL(path)
+            L.ref_msm.argtypes = [ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_size_t,
+                                  ctypes.c_char_p]
+            L.ref_pair_ip.argtypes = [ctypes.c_size_t, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int,
+                                      ctypes.c_char_p, ctypes.c_char_p]
+            cls._lib = L
+        return cls._lib
+
+    @staticmethod
+    def _pt(P):
+        return bytes(64) if P is None else P[0].to_bytes(32, "little") + P[1].to_bytes(32, "little")
+
+    @staticmethod
+    def _unpt(b):
+        x, y = int.from_bytes(b[:32], "little"), int.from_bytes(b[32:64], "little")
+        return None if x == 0 and y == 0 else (x, y)
+
+    @classmethod
+    def msm(cls, pairs):
+        import ctypes
+        pairs = list(pairs)
+        if not pairs:
+            return None
+        nz = [(reduce_scalar(s, R), p) for s, p in pairs if s % R]
+        n_pad = len(pairs) - len(nz)              # zero-scalar bases: normalised and walked, never added
+        mags = b"".join(abs(s).to_bytes(32, "little") for s, _ in nz)
+        neg = bytes(1 if s < 0 else 0 for s, _ in nz)
+        out = ctypes.create_string_buffer(64)
+        cls.lib().ref_msm(len(nz), mags, neg, b"".join(cls._pt(p) for _, p in nz), n_pad, out)
+        return cls._unpt(out.raw)
+
+    @classmethod
+    def msm_many(cls, list_of_pairs):
+        return [cls.msm(p) for p in list_of_pairs]
+
+    @classmethod
+    def pair_ip_many(cls, b, a, pairs):
+        """[b*gL + a*gR for (gL, gR) in pairs] with signed integers a, b (|.| < 2^129)."""
+        import ctypes
+        n = len(pairs)
+        out = ctypes.create_string_buffer(64 * max(n, 1))
+        cls.lib().ref_pair_ip(n, abs(b).to_bytes(32, "little"), int(b < 0), abs(a).to_bytes(32, "little"), int(a < 0),
+                              b"".join(cls._pt(l) + cls._pt(r) for l, r in pairs), out)
+        return [cls._unpt(out.raw[64 * i:64 * i + 64]) for i in range(n)]
+
+
 class Toy:
     """F_r as a vector space over itself (WrapV, src/Utils.hs:117-133)."""
     name = "toy"
@@ -289,6 +356,10 @@ class Toy:
     @classmethod
     def msm_many(cls, lp):
         return [cls.msm(p) for p in lp]
+
+    @staticmethod
+    def pair_ip_many(b, a, pairs):
+        return [(b * l + a * r) % R for l, r in pairs]
 
     @staticmethod
     def coords(P):

@@ -44,8 +44,8 @@ def sum_v(ws):
 def rpw_terms(w, g, hs, gs, G):
     """`commitRPW` opening (Internal.hs:43-48; `dotWith` pads with 0 / identity)."""
     t = [(w.sc, g)]
-    t += [(s, hs[i] if i < len(hs) else G.zero) for i, s in enumerate(w.lin)]
-    t += [(s, gs[i] if i < len(gs) else G.zero) for i, s in enumerate(w.nrm)]
+    t += [(w.lin[i] if i < len(w.lin) else 0, hs[i] if i < len(hs) else G.zero) for i in range(max(len(hs), len(w.lin)))]
+    t += [(w.nrm[i] if i < len(w.nrm) else 0, gs[i] if i < len(gs) else G.zero) for i in range(max(len(gs), len(w.nrm)))]
     return t
 
 
