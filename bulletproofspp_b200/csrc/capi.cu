@@ -11,15 +11,21 @@
 
 #include "../../include/bppp_b200.h"
 #include "host_math.hpp"
+#include "host/fr64.hpp"
+#include <atomic>
+#include <thread>
 #include "kernels.cuh"
 
 using namespace bppp;
 
+static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
+
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
-                                                   "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg"};
+                                                   "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
+                                                   "k_jac_sum", "k_gt_build"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -82,6 +88,11 @@ static void prof_collect(bppp_ctx* c) {
             return BPPP_ERR_CUDA;                                                               \
         }                                                                                       \
     } while (0)
+#define ENTER(c)                          \
+    do {                                  \
+        CK(cudaSetDevice((c)->dev));      \
+        g_alloc_stream = (c)->st;         \
+    } while (0)
 #define FAIL(code, msg)  \
     do {                 \
         ctx->err = msg;  \
@@ -113,6 +124,31 @@ static double msm_alg_imads(double n) {          // ceil(256/c*) (n
 #define WORK_K_DBG_EC 0
 static thread_local double g_work = 0;           // set by the caller right before a launch
 
+int g_capi_threads = 0;
+extern "C" void bppp_set_device_host_threads(int n) { g_capi_threads = n; }
+template <class F>
+static void host_parallel_for(size_t n, F fn) {
+    int nt = g_capi_threads > 0 ? g_capi_threads : (int)std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if ((size_t)nt > n / 16) nt = (int)(n / 16);
+    if (nt <= 1) {
+        for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    std::atomic<size_t> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&]() {
+            for (;;) {
+                size_t i0 = next.fetch_add(16);
+                if (i0 >= n) break;
+                size_t i1 = i0 + 16 < n ? i0 + 16 : n;
+                for (size_t i = i0; i < i1; i++) fn(i);
+            }
+        });
+    for (auto& t : th) t.join();
+}
+
 namespace {
 
 template <class T>
@@ -123,15 +159,17 @@ struct DBuf {
     DBuf(const DBuf&) = delete;
     DBuf& operator=(const DBuf&) = delete;
     ~DBuf() { release(); }
+    cudaStream_t st = nullptr;
     void release() {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, st);                 // stream-ordered: no device-wide sync
         p = nullptr;
         n = 0;
     }
     cudaError_t alloc(size_t count) {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        st = g_alloc_stream;
+        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), st);
         if (e == cudaSuccess) n = count;
         return e;
     }
@@ -259,6 +297,13 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
         delete c;
         return BPPP_ERR_CUDA;
     }
+    {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    }
     *out = c;
     return BPPP_OK;
 }
@@ -272,7 +317,7 @@ extern "C" const char* bppp_last_error(bppp_ctx* ctx) { return ctx ? ctx->err.c_
 extern "C" uint64_t bppp_launch_count(bppp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int bppp_sync(bppp_ctx* ctx) {
     if (!ctx) return BPPP_ERR_ARG;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     CK(cudaStreamSynchronize(ctx->st));
     return BPPP_OK;
 }
@@ -318,7 +363,7 @@ extern "C" int bppp_profile_report(bppp_ctx* ctx, char* out, size_t cap) {
 // CUDA-event timer on the context's stream (the stream every kernel of this library is launched on)
 extern "C" int bppp_timer_start(bppp_ctx* ctx) {
     if (!ctx) return BPPP_ERR_ARG;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     if (!ctx->t0) { CK(cudaEventCreate(&ctx->t0)); CK(cudaEventCreate(&ctx->t1)); }
     CK(cudaStreamSynchronize(ctx->st));
     CK(cudaEventRecord(ctx->t0, ctx->st));
@@ -326,7 +371,7 @@ extern "C" int bppp_timer_start(bppp_ctx* ctx) {
 }
 extern "C" int bppp_timer_stop(bppp_ctx* ctx, double* ms) {
     if (!ctx || !ms || !ctx->t0) return BPPP_ERR_ARG;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     CK(cudaEventRecord(ctx->t1, ctx->st));
     CK(cudaEventSynchronize(ctx->t1));
     float f = 0;
@@ -374,7 +419,7 @@ __global__ void k_imad_peak_lo(unsigned* out, unsigned a, unsigned b, int iters)
 }
 extern "C" int bppp_measure_imad_peak(bppp_ctx* ctx, double* wide_per_s, double* lo_per_s) {
     if (!ctx || !wide_per_s || !lo_per_s) return BPPP_ERR_ARG;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     DBuf<unsigned long long> d;
     CK(d.alloc(4));
     cudaEvent_t e0, e1;
@@ -405,7 +450,7 @@ extern "C" int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8
                               int shared_points, uint8_t* out) {
     if (!ctx) return BPPP_ERR_ARG;
     if (!scalars || !points || !out || batch == 0) FAIL(BPPP_ERR_ARG, "bppp_msm_batch: null/empty argument");
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     if (n == 0) {                                   // the reference's innerProduct calls `head` on []
         memset(out, 0, batch * 64);                 // (src/Commitment.hs:328); here: the identity
         return BPPP_OK;
@@ -446,7 +491,7 @@ extern "C" int bppp_fb_create(bppp_ctx* ctx, size_t n_bases, const uint8_t* poin
     if (!ctx) return BPPP_ERR_ARG;
     if (!out || !points || n_bases == 0 || n_bases > 16) FAIL(BPPP_ERR_ARG, "bppp_fb_create: bad argument");
     *out = nullptr;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     if (!check_fq(points, 2 * n_bases)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
     bppp_fb* fb = new bppp_fb();
     fb->ctx = ctx; fb->n_bases = n_bases;
@@ -474,7 +519,7 @@ extern "C" int bppp_fb_msm_batch(bppp_fb* fb, size_t batch, const uint8_t* scala
     if (!fb) return BPPP_ERR_ARG;
     bppp_ctx* ctx = fb->ctx;
     if (!scalars || !out || batch == 0) FAIL(BPPP_ERR_ARG, "bppp_fb_msm_batch: null/empty argument");
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     if (!check_fr(scalars, batch * fb->n_bases)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     DBuf<u256> d_sc;
     DBuf<Jac> d_res;
@@ -540,7 +585,7 @@ extern "C" int bppp_pair_fold(bppp_ctx* ctx, size_t n_in, const uint8_t a[32], i
     if (!ctx) return BPPP_ERR_ARG;
     if (!a || !b || !points_in || !points_out) FAIL(BPPP_ERR_ARG, "bppp_pair_fold: null argument");
     if (n_in == 0) return BPPP_OK;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     if (!check_fq(points_in, n_in * 2)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
     u256 ka = host::from_bytes(a), kb = host::from_bytes(b);
     if (ka.v[7] >> 31 || kb.v[7] >> 31) FAIL(BPPP_ERR_RANGE, "fold scalar magnitude >= 2^255");
@@ -575,9 +620,121 @@ extern "C" int bppp_rational_reduce(const uint8_t x[32], uint8_t a[32], int* a_n
     return BPPP_OK;
 }
 
+// =============================================================================== generator tables
+// The shared generator list [g | G | H] with its fixed-base window table, resident on the device.
+struct bppp_gens {
+    bppp_ctx* ctx;
+    size_t N, M, P0;
+    DBuf<Affine> base;               // [g | G | H]
+    DBuf<Affine> tbl;                // [P0][GT_W]
+    DBuf<Jac> scratch, parts;
+    std::vector<uint8_t> host;       // P0 * 64 bytes (for the bucket-kernel fallback paths)
+};
+namespace {
+size_t gt_smem_bytes(int n) { return (size_t)(2 * GT_KEYS + 1) * 4 + (size_t)n * GT_W * 2 + 16; }
+
+// fixed-base MSMs over the first n_terms generators: scalars sc[p*sc_stride + o*sc_out_stride + i];
+// result Jacobian points in d_out[p*n_out + o]
+int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride, size_t sc_out_stride, size_t batch,
+                 int n_out, Jac* d_out, double work_per_proof) {
+    bppp_ctx* ctx = g->ctx;
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(k_msm_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bytes(GT_MAX_CHUNK)));
+        attr = true;
+    }
+    int nch = (int)((n_terms + GT_MAX_CHUNK - 1) / GT_MAX_CHUNK);
+    size_t ctas = batch * n_out * nch;
+    CK(g->scratch.ensure(ctas * (GT_KEYS + 2 * GT_THREADS)));
+    Jac* parts = d_out;
+    if (nch > 1) { CK(g->parts.ensure(ctas)); parts = g->parts.p; }
+    int max_n = (int)std::min<size_t>(GT_MAX_CHUNK, n_terms);
+    for (size_t b0 = 0; b0 < batch; b0 += 32768) {
+        size_t nb = std::min<size_t>(32768, batch - b0);
+        GtArgs A;
+        A.tbl = g->tbl.p; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
+        A.n_total = (int)n_terms; A.scratch = g->scratch.p + b0 * n_out * nch * (GT_KEYS + 2 * GT_THREADS);
+        A.out = parts + b0 * n_out * nch; A.n_out = n_out; A.n_chunks = nch;
+        g_work = work_per_proof * (double)nb;
+        { ProfScope ps_(ctx, K_MSM_GENS, g_work);
+        k_msm_gens<<<dim3(nch, n_out, (unsigned)nb), GT_THREADS, gt_smem_bytes(max_n), ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+    }
+    if (nch > 1) {
+        size_t n_msm = batch * n_out;
+        { ProfScope ps_(ctx, K_JAC_SUM, 0);
+        k_jac_sum<<<(unsigned)((n_msm + 127) / 128), 128, 0, ctx->st>>>(parts, nch, nullptr, 0, d_out, n_msm);
+        }
+        CK(cudaGetLastError());
+    }
+    return BPPP_OK;
+}
+}  // namespace
+
+extern "C" int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t* g, const uint8_t* G, const uint8_t* H,
+                                bppp_gens** out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!out || !g || (N && !G) || (M && !H)) FAIL(BPPP_ERR_ARG, "bppp_gens_create: null argument");
+    *out = nullptr;
+    ENTER(ctx);
+    if (!check_fq(g, 2) || !check_fq(G, 2 * N) || !check_fq(H, 2 * M)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    bppp_gens* gg = new bppp_gens();
+    gg->ctx = ctx; gg->N = N; gg->M = M; gg->P0 = 1 + N + M;
+    gg->host.resize(gg->P0 * 64);
+    memcpy(&gg->host[0], g, 64);
+    if (N) memcpy(&gg->host[64], G, N * 64);
+    if (M) memcpy(&gg->host[64 * (1 + N)], H, M * 64);
+    DBuf<Jac> tj;
+    cudaError_t e;
+    size_t total = gg->P0 * GT_W;
+    if ((e = gg->base.alloc(gg->P0)) || (e = gg->tbl.alloc(total)) || (e = tj.alloc(total))) {
+        delete gg;
+        ctx->err = cudaGetErrorString(e);
+        return BPPP_ERR_CUDA;
+    }
+    H2D(gg->base.p, gg->host.data(), gg->P0 * 64);
+    { ProfScope ps_(ctx, K_GT_BUILD, 0);
+    k_gt_build<<<(unsigned)((gg->P0 + 63) / 64), 64, 0, ctx->st>>>(gg->base.p, gg->P0, tj.p);
+    }
+    int rc = to_affine(ctx, tj.p, total, gg->tbl.p, total, 0, (int)std::min<size_t>(total, 0x7fffffff), total);
+    if (rc == 0 && (e = cudaStreamSynchronize(ctx->st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
+    if (rc) { delete gg; return rc; }
+    *out = gg;
+    return BPPP_OK;
+}
+extern "C" void bppp_gens_destroy(bppp_gens* g) {
+    if (!g) return;
+    cudaSetDevice(g->ctx->dev);
+    cudaStreamSynchronize(g->ctx->st);
+    delete g;
+}
+// `batch` MSMs over the first n generators of the list (commitRPW over [g | gs | hs])
+extern "C" int bppp_gens_msm_batch(bppp_gens* g, size_t batch, size_t n, const uint8_t* scalars, uint8_t* out) {
+    if (!g) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = g->ctx;
+    if (!scalars || !out || batch == 0 || n == 0 || n > g->P0) FAIL(BPPP_ERR_ARG, "bppp_gens_msm_batch: bad argument");
+    ENTER(ctx);
+    if (!check_fr(scalars, batch * n)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    DBuf<u256> d_sc;
+    DBuf<Jac> d_res;
+    DBuf<Affine> d_aff;
+    CK(d_sc.alloc(batch * n)); CK(d_res.alloc(batch)); CK(d_aff.alloc(batch));
+    CK(H2D(d_sc.p, scalars, batch * n * 32));
+    int rc = run_msm_gens(g, n, d_sc.p, n, 0, batch, 1, d_res.p, msm_alg_imads((double)n));
+    if (rc) return rc;
+    if ((rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch))) return rc;
+    CK(D2H(out, d_aff.p, batch * 64));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+
 // =============================================================================== argument seam
+using h64::Fr;
 struct bppp_nl {
     bppp_ctx* ctx;
+    bppp_gens* gens = nullptr;
+    bool own_gens = false;
     int kind;
     size_t B, N, M;                 // batch, initial lengths
     size_t curN, curM;              // current lengths
@@ -585,8 +742,8 @@ struct bppp_nl {
     int round = 0;
     bool have_partials = false;
     int cur = 0;                    // which scalar buffer holds the current vectors
-    int curp = -1;                  // which per-proof point buffer is current (-1: shared base)
-    DBuf<Affine> base, pts[2], aff;
+    int curp = -1;                  // which per-proof point buffer is current (-1: shared generators)
+    DBuf<Affine> pts[2], aff;
     DBuf<u256> w[2], l[2], c[2];
     size_t wstride[2], lstride[2];
     DBuf<u256> sc;                  // [2][B][1+N+M] canonical MSM scalars (X then R)
@@ -595,18 +752,32 @@ struct bppp_nl {
     DBuf<Jac> jscratch, res;
     MsmPlan plan;
     int blocks_n = 1, blocks_l = 1;
-    // host state (Montgomery)
-    std::vector<u256> q, qinv, nn, nl, s, sX, sR;
+    // host state (Montgomery, 4 x 64-bit limbs; bit-compatible with the device's u256)
+    std::vector<Fr> q, qinv, nn, nl, s, sX, sR;
 };
 
 namespace {
 enum { C_RHO = 0, C_K1, C_K2, C_AU, C_BU, C_AL, C_BL, C_AC, C_BC, C_COEF /* 8 */, C_KB = C_COEF + 8 /* 2 */,
        C_KA = C_KB + 2 /* 2 */, C_COUNT = C_KA + 2 };
 inline u256* cptr(bppp_nl* h, int which) { return h->consts.p + (size_t)which * h->B; }
+static_assert(sizeof(Fr) == sizeof(u256), "host and device field elements share one layout");
 
 int dots_blocks(size_t n_pairs) {
     size_t b = (n_pairs + 255) / 256;
     return (int)std::max<size_t>(1, std::min<size_t>(b, 1024));
+}
+u256 fr_canon_u256(const Fr& a) {
+    u256 r;
+    uint64_t c[4];
+    h64::to_canon(c, a);
+    memcpy(r.v, c, 32);
+    return r;
+}
+Fr fr_from_mag(const u256& mag, bool neg) {
+    uint64_t c[4];
+    memcpy(c, mag.v, 32);
+    Fr m = h64::from_canon(c);
+    return neg ? h64::neg(m) : m;
 }
 
 // launch k_fold_dots for norm and linear vectors.  fold = 0: dots of current vectors; fold = 1:
@@ -625,7 +796,7 @@ int launch_fold_dots(bppp_nl* h, int fold) {
         A.au = A.av = cptr(h, C_AU); A.bu = A.bv = cptr(h, C_BU);
         A.rho = cptr(h, C_RHO); A.m1 = 1; A.m2 = 4; A.partial = h->part_n.p;
         g_work = 32.0 * (double)h->B * (fold ? (double)(h->curN + ny) : (double)h->curN);
-        { ProfScope ps_(ctx, K_FOLD_DOTS, WORK_K_FOLD_DOTS);
+        { ProfScope ps_(ctx, K_FOLD_DOTS, g_work);
         k_fold_dots<<<dim3(h->blocks_n, (unsigned)h->B), 256, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
@@ -641,40 +812,32 @@ int launch_fold_dots(bppp_nl* h, int fold) {
         A.au = cptr(h, C_AC); A.bu = cptr(h, C_BC); A.av = cptr(h, C_AL); A.bv = cptr(h, C_BL);
         A.rho = nullptr; A.m1 = 3; A.m2 = 4; A.partial = h->part_l.p;
         g_work = 2 * 32.0 * (double)h->B * (fold ? (double)(h->curM + ny) : (double)h->curM);
-        { ProfScope ps_(ctx, K_FOLD_DOTS, WORK_K_FOLD_DOTS);
+        { ProfScope ps_(ctx, K_FOLD_DOTS, g_work);
         k_fold_dots<<<dim3(h->blocks_l, (unsigned)h->B), 256, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
     }
     return BPPP_OK;
 }
-int upload_consts(bppp_nl* h, int which, const std::vector<u256>& v) {
+int upload_consts(bppp_nl* h, int which, const std::vector<Fr>& v) {
     bppp_ctx* ctx = h->ctx;
     CK(H2D(cptr(h, which), v.data(), v.size() * 32));
     return BPPP_OK;
 }
-}  // namespace
-
-extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, const uint8_t* g,
-                              const uint8_t* G, const uint8_t* H, const uint8_t* q, const uint8_t* s, const uint8_t* w,
-                              const uint8_t* l, const uint8_t* c, bppp_nl** out) {
-    if (!ctx) return BPPP_ERR_ARG;
-    if (!out || !g || !q || !s || batch == 0 || (N && (!G || !w)) || (M && (!H || !l || !c)))
-        FAIL(BPPP_ERR_ARG, "bppp_nl_create: null/empty argument");
-    *out = nullptr;
-    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_create: only BPPP_ARG_NL is implemented on the device path");
+int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint8_t* q, const uint8_t* s, const uint8_t* w,
+                   const uint8_t* l, const uint8_t* c, bppp_nl** out) {
+    bppp_ctx* ctx = gens->ctx;
+    const size_t N = gens->N, M = gens->M;
     if (N + M + 1 > 0x7fffffff) FAIL(BPPP_ERR_ARG, "vector too long");
-    CK(cudaSetDevice(ctx->dev));
-    if (!check_fq(g, 2) || !check_fq(G, 2 * N) || !check_fq(H, 2 * M)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
     if (!check_fr(q, batch) || !check_fr(s, batch) || !check_fr(w, batch * N) || !check_fr(l, batch * M) ||
         !check_fr(c, batch * M))
         FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     bppp_nl* h = new bppp_nl();
-    h->ctx = ctx; h->kind = kind; h->B = batch; h->N = N; h->M = M; h->curN = N; h->curM = M;
+    h->ctx = ctx; h->gens = gens; h->own_gens = own; h->kind = kind;
+    h->B = batch; h->N = N; h->M = M; h->curN = N; h->curM = M;
     h->N2 = (N + 1) / 2; h->M2 = (M + 1) / 2; h->P0 = 1 + N + M; h->P2 = 1 + h->N2 + h->M2;
-    auto fail = [&](int rc) { bppp_nl_destroy(h); return rc; };
+    auto fail = [&](int rc) { h->own_gens = false; bppp_nl_destroy(h); return rc; };
 #define CKH(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x ": ") + cudaGetErrorString(e_); return fail(BPPP_ERR_CUDA); } } while (0)
-    CKH(h->base.alloc(h->P0));
     CKH(h->pts[0].alloc(batch * h->P2)); CKH(h->pts[1].alloc(batch * h->P2));
     CKH(h->aff.alloc(batch * 2));
     CKH(h->w[0].alloc(batch * N)); CKH(h->w[1].alloc(batch * h->N2));
@@ -687,13 +850,9 @@ extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
     CKH(h->sgn.alloc(batch * 2));
     CKH(h->jscratch.alloc(batch * (h->N2 + h->M2)));
     CKH(h->res.alloc(batch * 2));
-    // generators
-    CKH(H2D(h->base.p, g, 64));
-    if (N) CKH(H2D(h->base.p + 1, G, N * 64));
-    if (M) CKH(H2D(h->base.p + 1 + N, H, M * 64));
     for (int k = 0; k < 2; k++) {
-        { ProfScope ps_(ctx, K_BCAST, WORK_K_BCAST_POINT);
-        k_bcast_point<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->st>>>(h->base.p, h->pts[k].p, h->P2, batch);
+        { ProfScope ps_(ctx, K_BCAST, 0);
+        k_bcast_point<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->st>>>(gens->base.p, h->pts[k].p, h->P2, batch);
         }
         CKH(cudaGetLastError());
     }
@@ -703,31 +862,59 @@ extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
     for (auto& u : up) {
         if (!u.n) continue;
         CKH(H2D(h->sc.p, u.src, u.n * 32));
-        { ProfScope ps_(ctx, K_FR_CONVERT, WORK_K_FR_CONVERT);
+        { ProfScope ps_(ctx, K_FR_CONVERT, 0);
         k_fr_convert<<<(unsigned)((u.n + 255) / 256), 256, 0, ctx->st>>>(h->sc.p, u.dst, u.n, 1);
         }
         CKH(cudaGetLastError());
     }
     CKH(cudaMemsetAsync(h->sc.p, 0, 2 * batch * h->P0 * 32, ctx->st));
-    // host state
-    h->q.resize(batch); h->qinv.resize(batch); h->nn.assign(batch, fr::one()); h->nl.assign(batch, fr::one());
+    h->q.resize(batch); h->qinv.resize(batch); h->nn.assign(batch, h64::one()); h->nl.assign(batch, h64::one());
     h->s.resize(batch); h->sX.resize(batch); h->sR.resize(batch);
-    for (size_t b = 0; b < batch; b++) {
-        h->q[b] = fr::to_mont(host::from_bytes(q + 32 * b));
+    host_parallel_for(batch, [&](size_t b) {
+        h->q[b] = h64::from_bytes(q + 32 * b);
         h->qinv[b] = h->q[b];
-        h->s[b] = fr::to_mont(host::from_bytes(s + 32 * b));
-    }
-    host::fr_batch_inv(h->qinv.data(), batch);
+        h->s[b] = h64::from_bytes(s + 32 * b);
+    });
+    h64::batch_inv(h->qinv.data(), batch);
     CKH(cudaStreamSynchronize(ctx->st));
 #undef CKH
     *out = h;
     return BPPP_OK;
+}
+}  // namespace
+
+extern "C" int bppp_nl_create_gens(bppp_gens* gens, int kind, size_t batch, const uint8_t* q, const uint8_t* s,
+                                   const uint8_t* w, const uint8_t* l, const uint8_t* c, bppp_nl** out) {
+    if (!gens) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = gens->ctx;
+    if (!out || !q || !s || batch == 0 || (gens->N && !w) || (gens->M && (!l || !c)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_create: null/empty argument");
+    *out = nullptr;
+    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_create: only BPPP_ARG_NL is implemented on the device path");
+    ENTER(ctx);
+    return nl_create_impl(gens, false, kind, batch, q, s, w, l, c, out);
+}
+extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, const uint8_t* g,
+                              const uint8_t* G, const uint8_t* H, const uint8_t* q, const uint8_t* s, const uint8_t* w,
+                              const uint8_t* l, const uint8_t* c, bppp_nl** out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!out || !g || !q || !s || batch == 0 || (N && (!G || !w)) || (M && (!H || !l || !c)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_create: null/empty argument");
+    *out = nullptr;
+    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_create: only BPPP_ARG_NL is implemented on the device path");
+    bppp_gens* gens = nullptr;
+    int rc = bppp_gens_create(ctx, N, M, g, G, H, &gens);
+    if (rc) return rc;
+    rc = nl_create_impl(gens, true, kind, batch, q, s, w, l, c, out);
+    if (rc) bppp_gens_destroy(gens);
+    return rc;
 }
 
 extern "C" void bppp_nl_destroy(bppp_nl* h) {
     if (!h) return;
     cudaSetDevice(h->ctx->dev);
     cudaStreamSynchronize(h->ctx->st);
+    if (h->own_gens) bppp_gens_destroy(h->gens);
     delete h;
 }
 
@@ -742,19 +929,18 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
     if (!X || !R) FAIL(BPPP_ERR_ARG, "bppp_nl_round_commit: null output");
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     const size_t B = h->B;
     // per-proof constants of this round (NormArgument.hs:113): rho = q^4, k1 = 2 n^2 q^3, k2 = n^2 q^4
-    std::vector<u256> rho(B), k1(B), k2(B), coef(B * 8, u256_zero());
-    for (size_t b = 0; b < B; b++) {
-        u256 q2 = fr::sqr(h->q[b]), q3 = fr::mul(q2, h->q[b]), q4 = fr::sqr(q2), n2 = fr::sqr(h->nn[b]);
+    std::vector<Fr> rho(B), k1(B), k2(B), coef(B * 8, h64::zero());
+    host_parallel_for(B, [&](size_t b) {
+        Fr q2 = h64::sqr(h->q[b]), q3 = h64::mul(q2, h->q[b]), q4 = h64::sqr(q2), n2 = h64::sqr(h->nn[b]);
         rho[b] = q4;
-        u256 t = fr::mul(n2, q3);
-        k1[b] = fr::add(t, t);
-        k2[b] = fr::mul(n2, q4);
+        k1[b] = h64::dbl(h64::mul(n2, q3));
+        k2[b] = h64::mul(n2, q4);
         coef[b * 8 + 1] = h->q[b];          // X on gL <- q * xR
         coef[b * 8 + 2] = h->qinv[b];       // X on gR <- q^-1 * xL
-    }
+    });
     int rc;
     if (!h->have_partials) {
         if ((rc = upload_consts(h, C_RHO, rho))) return rc;
@@ -774,7 +960,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         if (h->curN) { A.partial[A.n_seg] = h->part_n.p; A.n_blocks[A.n_seg] = h->blocks_n; A.k1[A.n_seg] = cptr(h, C_K1); A.k2[A.n_seg] = cptr(h, C_K2); A.n_seg++; }
         if (h->curM) { A.partial[A.n_seg] = h->part_l.p; A.n_blocks[A.n_seg] = h->blocks_l; A.k1[A.n_seg] = nullptr; A.k2[A.n_seg] = nullptr; A.n_seg++; }
         A.res = h->dots.p; A.xs = xs; A.rs = rs; A.sc_stride = P0; A.batch = (int)B;
-        { ProfScope ps_(ctx, K_DOTS_FINISH, WORK_K_DOTS_FINISH);
+        { ProfScope ps_(ctx, K_DOTS_FINISH, 0);
         k_dots_finish<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
@@ -786,7 +972,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1; A.coef = cptr(h, C_COEF);
         const unsigned char kd[8] = {0, 2, 2, 0, 0, 0, 0, 1};
         memcpy(A.kind, kd, 8);
-        { ProfScope ps_(ctx, K_MSM_SCALARS, WORK_K_MSM_SCALARS);
+        { ProfScope ps_(ctx, K_MSM_SCALARS, 0);
         k_msm_scalars<<<dim3((unsigned)(((h->curN + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
@@ -797,23 +983,26 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1 + (int)h->curN; A.coef = cptr(h, C_COEF);
         const unsigned char kd[8] = {0, 1, 1, 0, 0, 0, 0, 1};
         memcpy(A.kind, kd, 8);
-        { ProfScope ps_(ctx, K_MSM_SCALARS, WORK_K_MSM_SCALARS);
+        { ProfScope ps_(ctx, K_MSM_SCALARS, 0);
         k_msm_scalars<<<dim3((unsigned)(((h->curM + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
     }
     // the two commitments: MSMs over [g | G | H] with X scalars (output 0) and R scalars (output 1)
-    h->plan.slices.clear();
     const size_t nterms = 1 + h->curN + h->curM;
-    if (h->curp < 0) h->plan.add(h->base.p, 0, xs, P0, B * P0, nterms);
-    else h->plan.add(h->pts[h->curp].p, h->P2, xs, P0, B * P0, nterms);
-    {
-        double nX = (double)nterms, nR = 1.0 + (double)((h->curN + 1) / 2) + (double)((h->curM + 1) / 2);
-        if ((rc = run_msm(ctx, h->plan, B, 2, h->res.p, msm_alg_imads(nX) + msm_alg_imads(nR)))) return rc;
+    const double nX = (double)nterms, nR = 1.0 + (double)((h->curN + 1) / 2) + (double)((h->curM + 1) / 2);
+    const double work = msm_alg_imads(nX) + msm_alg_imads(nR);
+    if (h->curp < 0) {
+        // round 1: the generators are the shared list -> fixed-base tables
+        if ((rc = run_msm_gens(h->gens, nterms, xs, P0, B * P0, B, 2, h->res.p, work))) return rc;
+    } else {
+        h->plan.slices.clear();
+        h->plan.add(h->pts[h->curp].p, h->P2, xs, P0, B * P0, nterms);
+        if ((rc = run_msm(ctx, h->plan, B, 2, h->res.p, work))) return rc;
     }
     if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2))) return rc;
     std::vector<Affine> xr(B * 2);
-    std::vector<u256> dots(B * 2);
+    std::vector<Fr> dots(B * 2);
     CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
     CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
     CK(cudaStreamSynchronize(ctx->st));
@@ -831,46 +1020,46 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     bppp_ctx* ctx = h->ctx;
     if (!e) FAIL(BPPP_ERR_ARG, "bppp_nl_round_fold: null challenge");
     if (!h->have_partials) FAIL(BPPP_ERR_STATE, "bppp_nl_round_fold before bppp_nl_round_commit");
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     const size_t B = h->B;
     if (!check_fr(e, B)) FAIL(BPPP_ERR_RANGE, "challenge >= group order");
-    std::vector<u256> au(B), bu(B), al(B), bl(B), ac(B), bc(B), rho(B), kk(B * 4), b0n(B), b0l(B);
+    std::vector<Fr> au(B), bu(B), al(B), bl(B), ac(B), bc(B), rho(B), b0n(B), b0l(B), em(B), inv(2 * B);
+    std::vector<u256> kk(B * 4);
     std::vector<unsigned char> sg(B * 2);
-    std::vector<u256> em(B);
-    for (size_t b = 0; b < B; b++) {
-        em[b] = fr::to_mont(host::from_bytes(e + 32 * b));
+    host_parallel_for(B, [&](size_t b) {
+        em[b] = h64::from_bytes(e + 32 * b);
         // NormArgument.hs:125  (a', b') = rationalReduceScalar (e * qInv)
-        host::Ratio rn = host::rational_reduce(fr::from_mont(fr::mul(em[b], h->qinv[b])));
+        host::Ratio rn = host::rational_reduce(fr_canon_u256(h64::mul(em[b], h->qinv[b])));
         // NormArgument.hs:66   (a', b') = rationalReduceScalar e
         host::Ratio rl = host::rational_reduce(host::from_bytes(e + 32 * b));
         kk[b * 2 + 0] = rn.b; kk[b * 2 + 1] = rl.b;                  // kb[b][seg]
         kk[B * 2 + b * 2 + 0] = rn.a; kk[B * 2 + b * 2 + 1] = rl.a;  // ka[b][seg]
         sg[b * 2 + 0] = (unsigned char)((rn.b_neg ? 1 : 0) | (rn.a_neg ? 2 : 0));
         sg[b * 2 + 1] = (unsigned char)((rl.b_neg ? 1 : 0) | (rl.a_neg ? 2 : 0));
-        b0n[b] = host::fr_from_signed(rn.b, rn.b_neg);
-        b0l[b] = host::fr_from_signed(rl.b, rl.b_neg);
+        b0n[b] = fr_from_mag(rn.b, rn.b_neg);
+        b0l[b] = fr_from_mag(rl.b, rl.b_neg);
         ac[b] = b0l[b];                                              // c' = b0*cL + a0*cR
-        bc[b] = host::fr_from_signed(rl.a, rl.a_neg);
-    }
-    std::vector<u256> inv(2 * B);
-    for (size_t b = 0; b < B; b++) { inv[b] = b0n[b]; inv[B + b] = b0l[b]; }
-    host::fr_batch_inv(inv.data(), 2 * B);
-    for (size_t b = 0; b < B; b++) {
+        bc[b] = fr_from_mag(rl.a, rl.a_neg);
+        inv[b] = b0n[b];
+        inv[B + b] = b0l[b];
+    });
+    h64::batch_inv(inv.data(), 2 * B);
+    host_parallel_for(B, [&](size_t b) {
         // x' = b0Inv*xL + e*q*b0Inv*xR   (NormArgument.hs:129);  l' = b0Inv*xL + e*b0Inv*xR  (:71)
         au[b] = inv[b];
-        bu[b] = fr::mul(fr::mul(em[b], h->q[b]), inv[b]);
+        bu[b] = h64::mul(h64::mul(em[b], h->q[b]), inv[b]);
         al[b] = inv[B + b];
-        bl[b] = fr::mul(em[b], inv[B + b]);
+        bl[b] = h64::mul(em[b], inv[B + b]);
         // s' = s + e*sX + (e^2 - 1)*sR   (Bulletproof.hs:352-353, makeEs NormArgument.hs:109)
-        u256 e1 = fr::sub(fr::sqr(em[b]), fr::one());
-        h->s[b] = fr::add(h->s[b], fr::add(fr::mul(em[b], h->sX[b]), fr::mul(e1, h->sR[b])));
+        Fr e1 = h64::sub(h64::sqr(em[b]), h64::one());
+        h->s[b] = h64::add(h->s[b], h64::add(h64::mul(em[b], h->sX[b]), h64::mul(e1, h->sR[b])));
         // n <- n*b0*qInv ; q <- q^2 ; linear n <- n*b0
-        h->nn[b] = fr::mul(fr::mul(h->nn[b], b0n[b]), h->qinv[b]);
-        h->nl[b] = fr::mul(h->nl[b], b0l[b]);
-        h->q[b] = fr::sqr(h->q[b]);
-        h->qinv[b] = fr::sqr(h->qinv[b]);
-        rho[b] = fr::sqr(fr::sqr(h->q[b]));
-    }
+        h->nn[b] = h64::mul(h64::mul(h->nn[b], b0n[b]), h->qinv[b]);
+        h->nl[b] = h64::mul(h->nl[b], b0l[b]);
+        h->q[b] = h64::sqr(h->q[b]);
+        h->qinv[b] = h64::sqr(h->qinv[b]);
+        rho[b] = h64::sqr(h64::sqr(h->q[b]));
+    });
     int rc;
     if ((rc = upload_consts(h, C_AU, au)) || (rc = upload_consts(h, C_BU, bu)) || (rc = upload_consts(h, C_AL, al)) ||
         (rc = upload_consts(h, C_BL, bl)) || (rc = upload_consts(h, C_AC, ac)) || (rc = upload_consts(h, C_BC, bc)) ||
@@ -883,7 +1072,7 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     // generators
     const size_t nN = (h->curN + 1) / 2, nM = (h->curM + 1) / 2;
     PairFoldSeg segs[2] = {{1, (int)h->curN, 0}, {1 + (int)h->curN, (int)h->curM, (int)nN}};
-    const Affine* in = h->curp < 0 ? h->base.p : h->pts[h->curp].p;
+    const Affine* in = h->curp < 0 ? h->gens->base.p : h->pts[h->curp].p;
     size_t in_stride = h->curp < 0 ? 0 : h->P2;
     int nxt = h->curp < 0 ? 0 : (h->curp ^ 1);
     // both segments always launched (an empty segment contributes zero blocks) so that the
@@ -905,99 +1094,83 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
 extern "C" int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
-    CK(cudaSetDevice(ctx->dev));
-    const size_t B = h->B;
-    std::vector<u256> hw(h->curN), hl(h->curM);
+    ENTER(ctx);
+    const size_t B = h->B, cn = h->curN, cl = h->curM;
+    std::vector<Fr> hw(B * cn), hl(B * cl);
+    if (w && cn) { ctx->d2h += B * cn * 32; CK(cudaMemcpy2DAsync(hw.data(), cn * 32, h->w[h->cur].p, h->wstride[h->cur] * 32, cn * 32, B, cudaMemcpyDeviceToHost, ctx->st)); }
+    if (l && cl) { ctx->d2h += B * cl * 32; CK(cudaMemcpy2DAsync(hl.data(), cl * 32, h->l[h->cur].p, h->lstride[h->cur] * 32, cl * 32, B, cudaMemcpyDeviceToHost, ctx->st)); }
+    CK(cudaStreamSynchronize(ctx->st));
     for (size_t b = 0; b < B; b++) {
-        if (s) host::to_bytes(s + 32 * b, fr::from_mont(h->s[b]));
-        if (w && h->curN) {
-            CK(D2H(hw.data(), h->w[h->cur].p + b * h->wstride[h->cur], h->curN * 32));
-            CK(cudaStreamSynchronize(ctx->st));
-            for (size_t i = 0; i < h->curN; i++)
-                host::to_bytes(w + 32 * (b * h->curN + i), fr::from_mont(fr::mul(h->nn[b], hw[i])));
-        }
-        if (l && h->curM) {
-            CK(D2H(hl.data(), h->l[h->cur].p + b * h->lstride[h->cur], h->curM * 32));
-            CK(cudaStreamSynchronize(ctx->st));
-            for (size_t i = 0; i < h->curM; i++)
-                host::to_bytes(l + 32 * (b * h->curM + i), fr::from_mont(fr::mul(h->nl[b], hl[i])));
-        }
+        if (s) h64::to_bytes(s + 32 * b, h->s[b]);
+        if (w) for (size_t i = 0; i < cn; i++) h64::to_bytes(w + 32 * (b * cn + i), h64::mul(h->nn[b], hw[b * cn + i]));
+        if (l) for (size_t i = 0; i < cl; i++) h64::to_bytes(l + 32 * (b * cl + i), h64::mul(h->nl[b], hl[b * cl + i]));
     }
     return BPPP_OK;
 }
 
 // =============================================================================== verifier
-extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, size_t k, const uint8_t* g,
-                              const uint8_t* G, const uint8_t* H, const uint8_t* q, const uint8_t* s_pub,
-                              const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR,
-                              size_t n_norm, size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init,
-                              const uint8_t* init_s, const uint8_t* init_p, int* ok) {
-    if (!ctx) return BPPP_ERR_ARG;
-    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_verify: only BPPP_ARG_NL is implemented on the device path");
-    if (!g || !q || !s_pub || !ok || batch == 0 || (N && (!G || !pub_w)) || (M && (!H || !c)) || (k && (!es || !XR)) ||
-        (n_norm && !fw) || (n_lin && !fl) || (n_init && (!init_s || !init_p)))
-        FAIL(BPPP_ERR_ARG, "bppp_nl_verify: null/empty argument");
-    if (k > 30) FAIL(BPPP_ERR_ARG, "too many rounds");
-    CK(cudaSetDevice(ctx->dev));
+namespace {
+int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
+                   const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR, size_t n_norm,
+                   size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s,
+                   const uint8_t* init_p, int* ok) {
+    bppp_ctx* ctx = gens->ctx;
+    (void)kind;
+    const size_t N = gens->N, M = gens->M;
     const size_t B = batch, P0 = 1 + N + M, NX = n_init + 2 * k;
-    if (!check_fq(g, 2) || !check_fq(G, 2 * N) || !check_fq(H, 2 * M) || !check_fq(XR, 4 * k * B) ||
-        !check_fq(init_p, 2 * n_init * B))
-        FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    if (!check_fq(XR, 4 * k * B) || !check_fq(init_p, 2 * n_init * B)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
     if (!check_fr(q, B) || !check_fr(s_pub, B) || !check_fr(pub_w, B * N) || !check_fr(c, B * M) || !check_fr(es, B * k) ||
         !check_fr(fw, B * n_norm) || !check_fr(fl, B * n_lin) || !check_fr(init_s, B * n_init))
         FAIL(BPPP_ERR_RANGE, "scalar >= group order");
-    DBuf<Affine> base, extra, aff;
-    DBuf<u256> sc, xsc, pub, cm, vs_n, vs_l, f0n, f1, f0l, tmp;
-    DBuf<Jac> res;
-    CK(base.alloc(P0)); CK(extra.alloc(B * std::max<size_t>(NX, 1))); CK(aff.alloc(B));
+    DBuf<Affine> extra, aff;
+    DBuf<u256> sc, xsc, pub, vs_n, vs_l, f0n, f1, f0l, tmp;
+    DBuf<Jac> res, res2, resx;
+    CK(extra.alloc(B * std::max<size_t>(NX, 1))); CK(aff.alloc(B));
     CK(sc.alloc(B * P0)); CK(xsc.alloc(B * std::max<size_t>(NX, 1)));
-    CK(pub.alloc(B * N)); CK(cm.alloc(B * M)); CK(vs_n.alloc(B * n_norm)); CK(vs_l.alloc(B * n_lin));
-    CK(f0n.alloc(B * k)); CK(f1.alloc(B * k)); CK(f0l.alloc(B * k)); CK(res.alloc(B));
+    CK(pub.alloc(B * N)); CK(vs_n.alloc(B * n_norm)); CK(vs_l.alloc(B * n_lin));
+    CK(f0n.alloc(B * k)); CK(f1.alloc(B * k)); CK(f0l.alloc(B * k)); CK(res.alloc(B)); CK(res2.alloc(B)); CK(resx.alloc(B));
     CK(tmp.alloc(std::max(B * N, B * M)));
-    CK(H2D(base.p, g, 64));
-    if (N) CK(H2D(base.p + 1, G, N * 64));
-    if (M) CK(H2D(base.p + 1 + N, H, M * 64));
     if (N) {
         CK(H2D(tmp.p, pub_w, B * N * 32));
-        { ProfScope ps_(ctx, K_FR_CONVERT, WORK_K_FR_CONVERT);
+        { ProfScope ps_(ctx, K_FR_CONVERT, 0);
         k_fr_convert<<<(unsigned)((B * N + 255) / 256), 256, 0, ctx->st>>>(tmp.p, pub.p, B * N, 1);
         }
         CK(cudaGetLastError());
     }
     // host: challenges, tensor factors, final-witness scalar sc  (NormArgument.hs:131-145, 73-81)
-    std::vector<u256> hf0n(B * k), hf1(B * k), hf0l(B * k, fr::one()), hvn(B * n_norm), hvl(B * n_lin);
-    std::vector<u256> scn(B), hx(B * std::max<size_t>(NX, 1)), hc(B * M);
+    std::vector<Fr> hf0n(B * k), hf1(B * k), hf0l(B * k, h64::one()), hvn(B * n_norm), hvl(B * n_lin), scn(B), hc(B * M);
+    std::vector<u256> hx(B * std::max<size_t>(NX, 1));
     std::vector<Affine> hp(B * std::max<size_t>(NX, 1));
-    for (size_t b = 0; b < B; b++) {
-        u256 qq = fr::to_mont(host::from_bytes(q + 32 * b));
+    host_parallel_for(B, [&](size_t b) {
+        Fr qq = h64::from_bytes(q + 32 * b);
         for (size_t j = 0; j < k; j++) {
             // round j+1's challenge is es[k-1-j] (newest first)
-            hf1[b * k + j] = fr::to_mont(host::from_bytes(es + 32 * (b * k + (k - 1 - j))));
+            hf1[b * k + j] = h64::from_bytes(es + 32 * (b * k + (k - 1 - j)));
             hf0n[b * k + j] = qq;
-            qq = fr::sqr(qq);
+            qq = h64::sqr(qq);
         }
-        u256 qF2 = fr::sqr(qq), wgt = qF2, acc = u256_zero();      // powers' (qF^2)
+        Fr qF2 = h64::sqr(qq), wgt = qF2, acc = h64::zero();          // powers' (qF^2)
         for (size_t i = 0; i < n_norm; i++) {
-            u256 v = fr::to_mont(host::from_bytes(fw + 32 * (b * n_norm + i)));
+            Fr v = h64::from_bytes(fw + 32 * (b * n_norm + i));
             hvn[b * n_norm + i] = v;
-            acc = fr::add(acc, fr::mul(wgt, fr::sqr(v)));
-            wgt = fr::mul(wgt, qF2);
+            acc = h64::add(acc, h64::mul(wgt, h64::sqr(v)));
+            wgt = h64::mul(wgt, qF2);
         }
         scn[b] = acc;
-        for (size_t i = 0; i < n_lin; i++) hvl[b * n_lin + i] = fr::to_mont(host::from_bytes(fl + 32 * (b * n_lin + i)));
-        for (size_t i = 0; i < M; i++) hc[b * M + i] = fr::to_mont(host::from_bytes(c + 32 * (b * M + i)));
+        for (size_t i = 0; i < n_lin; i++) hvl[b * n_lin + i] = h64::from_bytes(fl + 32 * (b * n_lin + i));
+        for (size_t i = 0; i < M; i++) hc[b * M + i] = h64::from_bytes(c + 32 * (b * M + i));
         // extra terms: initCom opening, then (e0, X), (e1, R) per round, newest first (verifyWith)
         for (size_t i = 0; i < n_init; i++) {
             hx[b * NX + i] = host::from_bytes(init_s + 32 * (b * n_init + i));
             memcpy(&hp[b * NX + i], init_p + 64 * (b * n_init + i), 64);
         }
         for (size_t r = 0; r < k; r++) {
-            u256 e = fr::to_mont(host::from_bytes(es + 32 * (b * k + r)));
-            hx[b * NX + n_init + 2 * r] = fr::from_mont(e);
-            hx[b * NX + n_init + 2 * r + 1] = fr::from_mont(fr::sub(fr::sqr(e), fr::one()));
+            Fr e = h64::from_bytes(es + 32 * (b * k + r));
+            hx[b * NX + n_init + 2 * r] = host::from_bytes(es + 32 * (b * k + r));
+            hx[b * NX + n_init + 2 * r + 1] = fr_canon_u256(h64::sub(h64::sqr(e), h64::one()));
             memcpy(&hp[b * NX + n_init + 2 * r], XR + 64 * ((b * k + r) * 2), 128);
         }
-    }
+    });
     if (k) {
         CK(H2D(f0n.p, hf0n.data(), B * k * 32));
         CK(H2D(f1.p, hf1.data(), B * k * 32));
@@ -1013,7 +1186,7 @@ extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
         TensorArgs A;
         A.pub = pub.p; A.pub_stride = N; A.vs = vs_n.p; A.n_vs = (int)n_norm; A.f0 = f0n.p; A.f1 = f1.p; A.k = (int)k;
         A.out = sc.p; A.out_stride = P0; A.off = 1; A.n = (int)N;
-        { ProfScope ps_(ctx, K_TENSOR, WORK_K_TENSOR_EXPAND);
+        { ProfScope ps_(ctx, K_TENSOR, 0);
         k_tensor_expand<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
@@ -1023,38 +1196,80 @@ extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
         TensorArgs A;
         A.pub = nullptr; A.pub_stride = 0; A.vs = vs_l.p; A.n_vs = (int)n_lin; A.f0 = f0l.p; A.f1 = f1.p; A.k = (int)k;
         A.out = sc.p; A.out_stride = P0; A.off = 1 + (int)N; A.n = (int)M;
-        { ProfScope ps_(ctx, K_TENSOR, WORK_K_TENSOR_EXPAND);
+        { ProfScope ps_(ctx, K_TENSOR, 0);
         k_tensor_expand<<<dim3((unsigned)((M + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
         // sc_lin = sum_j c_j * tensor_j  (contract' . tensor', NormArgument.hs:75-78); the kernel wrote -tensor_j
+        ctx->d2h += B * M * 32;
         CK(cudaMemcpy2DAsync(tl.data(), M * 32, sc.p + 1 + N, P0 * 32, M * 32, B, cudaMemcpyDeviceToHost, ctx->st));
     }
     CK(cudaStreamSynchronize(ctx->st));
     std::vector<u256> s0(B);
-    for (size_t b = 0; b < B; b++) {
-        u256 acc = scn[b];
-        for (size_t j = 0; j < M; j++) acc = fr::sub(acc, fr::mul(hc[b * M + j], fr::to_mont(tl[b * M + j])));
-        s0[b] = fr::from_mont(fr::sub(fr::to_mont(host::from_bytes(s_pub + 32 * b)), acc));
-    }
+    host_parallel_for(B, [&](size_t b) {
+        Fr acc = scn[b];
+        for (size_t j = 0; j < M; j++) {
+            uint64_t cw[4];
+            memcpy(cw, tl[b * M + j].v, 32);
+            acc = h64::sub(acc, h64::mul(hc[b * M + j], h64::from_canon(cw)));
+        }
+        s0[b] = fr_canon_u256(h64::sub(h64::from_bytes(s_pub + 32 * b), acc));
+    });
+    ctx->h2d += B * 32;
     CK(cudaMemcpy2DAsync(sc.p, P0 * 32, s0.data(), 32, 32, B, cudaMemcpyHostToDevice, ctx->st));
-    MsmPlan plan;
-    plan.add(base.p, 0, sc.p, P0, 0, P0);
-    if (NX) plan.add(extra.p, NX, xsc.p, NX, 0, NX);
-    int rc = run_msm(ctx, plan, B, 1, res.p, msm_alg_imads((double)(P0 + NX)));
+    int rc = run_msm_gens(gens, P0, sc.p, P0, 0, B, 1, res.p, msm_alg_imads((double)(P0 + NX)));
     if (rc) return rc;
-    if ((rc = to_affine(ctx, res.p, 1, aff.p, 1, 0, 1, B))) return rc;
+    if (NX) {
+        MsmPlan plan;
+        plan.add(extra.p, NX, xsc.p, NX, 0, NX);
+        if ((rc = run_msm(ctx, plan, B, 1, resx.p, 0))) return rc;
+        { ProfScope ps_(ctx, K_JAC_SUM, 0);
+        k_jac_sum<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(res.p, 1, resx.p, 1, res2.p, B);
+        }
+        CK(cudaGetLastError());
+    }
+    if ((rc = to_affine(ctx, NX ? res2.p : res.p, 1, aff.p, 1, 0, 1, B))) return rc;
     std::vector<Affine> out(B);
     CK(D2H(out.data(), aff.p, B * 64));
     CK(cudaStreamSynchronize(ctx->st));
     for (size_t b = 0; b < B; b++) ok[b] = aff_is_inf(out[b]) ? 1 : 0;
     return BPPP_OK;
 }
+}  // namespace
+
+extern "C" int bppp_nl_verify_gens(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
+                                   const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR,
+                                   size_t n_norm, size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init,
+                                   const uint8_t* init_s, const uint8_t* init_p, int* ok) {
+    if (!gens) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = gens->ctx;
+    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_verify: only BPPP_ARG_NL is implemented on the device path");
+    if (!q || !s_pub || !ok || batch == 0 || (gens->N && !pub_w) || (gens->M && !c) || (k && (!es || !XR)) ||
+        (n_norm && !fw) || (n_lin && !fl) || (n_init && (!init_s || !init_p)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_verify: null/empty argument");
+    if (k > 30) FAIL(BPPP_ERR_ARG, "too many rounds");
+    ENTER(ctx);
+    return nl_verify_impl(gens, kind, batch, k, q, s_pub, pub_w, c, es, XR, n_norm, n_lin, fw, fl, n_init, init_s, init_p, ok);
+}
+extern "C" int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, size_t k, const uint8_t* g,
+                              const uint8_t* G, const uint8_t* H, const uint8_t* q, const uint8_t* s_pub,
+                              const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR,
+                              size_t n_norm, size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init,
+                              const uint8_t* init_s, const uint8_t* init_p, int* ok) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!g || (N && !G) || (M && !H)) FAIL(BPPP_ERR_ARG, "bppp_nl_verify: null generators");
+    bppp_gens* gens = nullptr;
+    int rc = bppp_gens_create(ctx, N, M, g, G, H, &gens);
+    if (rc) return rc;
+    rc = bppp_nl_verify_gens(gens, kind, batch, k, q, s_pub, pub_w, c, es, XR, n_norm, n_lin, fw, fl, n_init, init_s, init_p, ok);
+    bppp_gens_destroy(gens);
+    return rc;
+}
 
 // =============================================================================== debug
 extern "C" int bppp_dbg_field(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     if (!ctx || !a || !b || !out) return BPPP_ERR_ARG;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     DBuf<u256> da, db, dc;
     CK(da.alloc(n)); CK(db.alloc(n)); CK(dc.alloc(n));
     CK(H2D(da.p, a, n * 32));
@@ -1069,7 +1284,7 @@ extern "C" int bppp_dbg_field(bppp_ctx* ctx, int op, size_t n, const uint8_t* a,
 }
 extern "C" int bppp_dbg_ec(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     if (!ctx || !a || !b || !out) return BPPP_ERR_ARG;
-    CK(cudaSetDevice(ctx->dev));
+    ENTER(ctx);
     DBuf<Affine> da, db, dd;
     DBuf<Jac> dc;
     CK(da.alloc(n)); CK(db.alloc(n)); CK(dc.alloc(n)); CK(dd.alloc(n));

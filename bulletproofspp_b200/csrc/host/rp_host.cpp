@@ -15,6 +15,9 @@
 //   src/Bulletproof.hs                 proveBPM / verifyBPM round loops, optimalWitnessSize
 // A batch of proofs runs in lock-step: host phases are spread over worker threads, each device
 // call covers the whole batch.
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <algorithm>
 #include <atomic>
 #include <map>
@@ -34,6 +37,26 @@ typedef unsigned __int128 U128;
 namespace {
 
 // ------------------------------------------------------------------------------ utilities
+struct Timing {                                // BPPP_TIMING=1: coarse wall-clock split printed to stderr
+    std::map<std::string, double> ms;
+    bool on = getenv("BPPP_TIMING") != nullptr;
+    double last = 0;
+    static double now() {
+        struct timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    void start() { if (on) last = now(); }
+    void lap(const char* name) { if (on) { double t = now(); ms[name] += t - last; last = t; } }
+    void dump(const char* what) {
+        if (!on) return;
+        fprintf(stderr, "[bppp timing] %s:", what);
+        for (auto& kv : ms) fprintf(stderr, " %s=%.1fms", kv.first.c_str(), kv.second);
+        fprintf(stderr, "\n");
+        ms.clear();
+    }
+};
+Timing g_tm;
 int g_threads = 0;
 int n_threads() {
     if (g_threads > 0) return g_threads;
@@ -147,6 +170,7 @@ struct bppp_rp {
     std::vector<uint8_t> table;                // [g | gs | hs] as bytes (device MSM base table)
     std::vector<uint8_t> in_pts;               // TRRP: [g, hs0, hs1]; Binary: [g, h0]
     bppp_fb* fb = nullptr;                     // fixed-base tables over in_pts
+    bppp_gens* gens = nullptr;                 // resident [g | gs | hs] with window tables
     std::string err;
 };
 
@@ -632,12 +656,13 @@ int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::ve
                  uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l) {
     const size_t B = P.size(), N = s->nrm_len, M = s->lin_len;
     bppp_nl* h = nullptr;
-    int rc = bppp_nl_create(s->ctx, s->arg, B, N, M, &s->table[0], &s->table[64], &s->table[64 * (1 + N)], q.data(), sc.data(),
-                            w.data(), l.data(), c.data(), &h);
+    int rc = bppp_nl_create_gens(s->gens, s->arg, B, q.data(), sc.data(), w.data(), l.data(), c.data(), &h);
     if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(s));
     std::vector<uint8_t> X(B * 64), R(B * 64), E(B * 32);
+    g_tm.lap("nl_create");
     for (size_t r = 0; r < rounds; r++) {
         rc = bppp_nl_round_commit(h, X.data(), R.data());
+        g_tm.lap("nl_commit");
         if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_commit: ") + ctx_err(s)); }
         parallel_for(B, [&](size_t b) {
             uint8_t xr[128];
@@ -649,7 +674,9 @@ int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::ve
             // responses are consed: newest first (Bulletproof.hs:357-359)
             memcpy(responses + 128 * (b * rounds + (rounds - 1 - r)), xr, 128);
         });
+        g_tm.lap("round_hash");
         rc = bppp_nl_round_fold(h, E.data());
+        g_tm.lap("nl_fold");
         if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_fold: ") + ctx_err(s)); }
     }
     size_t cn = 0, cl = 0;
@@ -658,6 +685,8 @@ int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::ve
     std::vector<uint8_t> fs(B * 32), fw(B * cn * 32), fl(B * cl * 32);
     rc = bppp_nl_final(h, fs.data(), fw.data(), fl.data());
     bppp_nl_destroy(h);
+    g_tm.lap("nl_final");
+    g_tm.dump("prove");
     if (rc) return fail(s, rc, std::string("bppp_nl_final: ") + ctx_err(s));
     for (size_t b = 0; b < B; b++) {       // getWitness: norm scalars then linear scalars (RangeProof.hs:65)
         memcpy(finals + 32 * b * (cn + cl), &fw[32 * b * cn], 32 * cn);
@@ -671,7 +700,10 @@ int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::ve
 // =================================================================================== C ABI
 extern "C" {
 
-void bppp_set_host_threads(int n) { g_threads = n; }
+void bppp_set_host_threads(int n) {
+    g_threads = n;
+    bppp_set_device_host_threads(n);
+}
 
 int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserved, const char* basis_seed, int show_format,
                   int root_policy, size_t n_ranges, const bppp_range_spec* ranges, size_t n_pub, const bppp_public_spec* pubs,
@@ -735,12 +767,15 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
     finish_setup(s);
     int rc = bppp_fb_create(ctx, s->in_pts.size() / 64, s->in_pts.data(), &s->fb);
     if (rc) { delete s; return rc; }
+    rc = bppp_gens_create(ctx, s->nrm_len, s->lin_len, &s->table[0], &s->table[64], &s->table[64 * (1 + s->nrm_len)], &s->gens);
+    if (rc) { bppp_fb_destroy(s->fb); delete s; return rc; }
     *out = s;
     return BPPP_OK;
 }
 void bppp_rp_free(bppp_rp* s) {
     if (!s) return;
     bppp_fb_destroy(s->fb);
+    bppp_gens_destroy(s->gens);
     delete s;
 }
 const char* bppp_rp_last_error(bppp_rp* s) { return s ? s->err.c_str() : "null setup"; }
@@ -786,6 +821,7 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
     const size_t B = batch, n = s->n_inputs, N = s->nrm_len, M = s->lin_len, P0 = 1 + N + M, NC = s->num_rp_coms + n;
     std::vector<Proof> P(B);
     std::atomic<int> bad(0);
+    g_tm.start();
     const size_t in_terms = s->binary ? 2 : 3;
     std::vector<uint8_t> in_sc(B * n * in_terms * 32);
     // ---------------- phase 1 (host): witnesses, input openings, digit commitments
@@ -891,6 +927,7 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
         commit_scalars(s, p.m, &sc1[32 * (2 * b + 1) * P0]);
     });
     if (bad.load()) return fail(s, BPPP_ERR_RANGE, "invalid witness (out of range / unbalanced)");
+    g_tm.lap("host_phase1");
     // ---------------- device: input commitments + digit commitments
     std::vector<uint8_t> n_coms(B * n * 64), c1(B * (s->binary ? 1 : 2) * 64);
     int rc;
@@ -898,8 +935,9 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
         rc = bppp_fb_msm_batch(s->fb, B * n, in_sc.data(), n_coms.data());
         if (rc) return fail(s, rc, std::string("input commitments: ") + ctx_err(s));
     }
-    rc = bppp_msm_batch(s->ctx, B * (s->binary ? 1 : 2), P0, sc1.data(), s->table.data(), 1, c1.data());
+    rc = bppp_gens_msm_batch(s->gens, B * (s->binary ? 1 : 2), P0, sc1.data(), c1.data());
     if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(s));
+    g_tm.lap("msm_phase1");
     std::vector<uint8_t> q_b(B * 32), sc_b(B * 32), w_b(B * N * 32, 0), l_b(B * M * 32, 0), c_b(B * M * 32, 0);
     std::vector<uint8_t> sc2(B * P0 * 32), c2(B * 64);
 
@@ -933,7 +971,7 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
             p.bl.nrm = p.bls_nrm;
             commit_scalars(s, p.bl, &sc2[32 * b * P0]);
         });
-        rc = bppp_msm_batch(s->ctx, B, P0, sc2.data(), s->table.data(), 1, c2.data());
+        rc = bppp_gens_msm_batch(s->gens, B, P0, sc2.data(), c2.data());
         if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(s));
         parallel_for(B, [&](size_t b) {
             Proof& p = P[b];
@@ -980,8 +1018,10 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
             p.r = blind_err_witness(p.zk, 3, {err7}, {}, rs);
             commit_scalars(s, p.r, &sc2[32 * b * P0]);
         });
-        rc = bppp_msm_batch(s->ctx, B, P0, sc2.data(), s->table.data(), 1, c2.data());
+        g_tm.lap("host_phase2");
+        rc = bppp_gens_msm_batch(s->gens, B, P0, sc2.data(), c2.data());
         if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(s));
+        g_tm.lap("msm_phase2");
         // ---------------- phase 3 (TypedReciprocal.hs:421-434)
         parallel_for(B, [&](size_t b) {
             Proof& p = P[b];
@@ -1015,8 +1055,10 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
             p.wit = nsum;                                                    // parked: nWitSum
             commit_scalars(s, p.bl, &sc2[32 * b * P0]);
         });
-        rc = bppp_msm_batch(s->ctx, B, P0, sc2.data(), s->table.data(), 1, c2.data());
+        g_tm.lap("host_phase3");
+        rc = bppp_gens_msm_batch(s->gens, B, P0, sc2.data(), c2.data());
         if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(s));
+        g_tm.lap("msm_phase3");
         // ---------------- phase 4 (TypedReciprocal.hs:435-444)
         parallel_for(B, [&](size_t b) {
             Proof& p = P[b];
@@ -1040,6 +1082,7 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
             for (size_t i = 0; i < p.cs.size() && i < M; i++) h64::to_bytes(&c_b[32 * (b * M + i)], p.cs[i]);
         });
     }
+    g_tm.lap("host_phase4");
     return run_argument(s, P, s->prover_rounds, q_b, sc_b, w_b, l_b, c_b, responses, finals, s->prover_fin_n, s->prover_fin_l);
 }
 
@@ -1056,6 +1099,7 @@ int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm,
     std::vector<uint8_t> fw_b(B * n_norm * 32), fl_b(B * n_lin * 32), is_b(B * NC * 32), ip_b(B * NC * 64);
     std::vector<Ph1> ph1v;
     if (!s->binary) ph1v = ph1s_verifier(s);
+    g_tm.start();
     parallel_for(B, [&](size_t b) {
         tr::Zkpt zk;
         zk.fmt = s->fmt;
@@ -1119,9 +1163,11 @@ int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm,
         memcpy(&fw_b[32 * b * n_norm], finals + 32 * b * (n_norm + n_lin), 32 * n_norm);
         memcpy(&fl_b[32 * b * n_lin], finals + 32 * (b * (n_norm + n_lin) + n_norm), 32 * n_lin);
     });
-    int rc = bppp_nl_verify(s->ctx, s->arg, B, N, M, k, &s->table[0], &s->table[64], &s->table[64 * (1 + N)], q_b.data(),
-                            sp_b.data(), pw_b.data(), c_b.data(), es_b.data(), responses, n_norm, n_lin, fw_b.data(), fl_b.data(),
-                            NC, is_b.data(), ip_b.data(), ok);
+    g_tm.lap("verify_host");
+    int rc = bppp_nl_verify_gens(s->gens, s->arg, B, k, q_b.data(), sp_b.data(), pw_b.data(), c_b.data(), es_b.data(), responses,
+                                 n_norm, n_lin, fw_b.data(), fl_b.data(), NC, is_b.data(), ip_b.data(), ok);
+    g_tm.lap("nl_verify");
+    g_tm.dump("verify");
     if (rc) return fail(s, rc, std::string("bppp_nl_verify: ") + ctx_err(s));
     return BPPP_OK;
 }

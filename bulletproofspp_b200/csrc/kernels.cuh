@@ -621,6 +621,203 @@ __global__ void __launch_bounds__(256) k_tensor_expand(TensorArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Fixed-base bucket MSM over the SHARED generator list [g | G | H] (round 1 of every argument,
+// every range-proof commitment, the verifier's collapsed MSM).  A table
+//   T[i*GT_W + j] = 2^(GT_C*j) * P_i   (affine, resident in HBM / L2; 2.4 MB for 128by64)
+// folds all windows of a scalar into ONE bucket set:  sum_i s_i P_i = sum_m m * B_m with
+// B_m = sum over (i,j) with |digit_ij| = m of +-T[i][j]  -- no doublings, one reduction per MSM.
+// One CTA per (chunk, output, proof):
+//   (1) signed 9-bit digits counted per signed bucket key with shared atomics, (2) scan,
+//   (3) the (term,window) entries are scattered into a shared-memory list sorted by key,
+//   (4) the sorted list is cut into EQUAL ranges, one per thread (balanced whatever the digit
+//       distribution -- reciprocal witnesses repeat scalars heavily); a thread accumulates each
+//       key-run of its range with mixed adds and flushes run sums to a per-CTA scratch,
+//   (5) per key the run sums are merged, +m and -m combined, and warp 0 forms sum_m m*B_m
+//       (8 buckets per lane by running sums, then a shuffle suffix-scan + tree).
+// ------------------------------------------------------------------------------------------
+#define GT_C 9
+#define GT_W 29                        // 29 * 9 = 261 >= 257 bits (signed-digit carry)
+#define GT_NB 256                      // bucket magnitudes 1..256
+#define GT_KEYS 512                    // key = (m-1)*2 + (digit < 0)
+#define GT_THREADS 256
+#define GT_MAX_CHUNK 2048              // (term*GT_W + window) must fit 16 bits
+
+__global__ void k_gt_build(const Affine* __restrict__ bases, size_t n, Jac* __restrict__ tbl) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Jac cur = jac_from_aff(ld_aff(bases + i));
+    for (int j = 0; j < GT_W; j++) {
+        st_jac(tbl + i * GT_W + j, cur);
+        if (j + 1 < GT_W)
+            for (int k = 0; k < GT_C; k++) cur = jac_dbl(cur);
+    }
+}
+
+struct GtArgs {
+    const Affine* tbl;                 // [n_total][GT_W]
+    const u256* sc; size_t sc_stride;  // canonical scalars, per proof; + output * sc_out_stride
+    size_t sc_out_stride;
+    int n_total;                       // terms per MSM; chunk c covers [c*GT_MAX_CHUNK, ...)
+    Jac* scratch;                      // per CTA: [GT_KEYS] key sums + [2*GT_THREADS] boundary run sums
+    Jac* out;                          // [batch][n_out][n_chunks]
+    int n_out, n_chunks;
+};
+__device__ __forceinline__ int gt_digit(const u256& s, int j, int& carry) { return signed_digit(s, j, GT_C, carry); }
+
+__global__ void __launch_bounds__(GT_THREADS) k_msm_gens(GtArgs A) {
+    extern __shared__ unsigned char gt_smem[];
+    const int chunk = blockIdx.x, o = blockIdx.y, p = blockIdx.z;
+    const int base = chunk * GT_MAX_CHUNK;
+    const int n = min(GT_MAX_CHUNK, A.n_total - base);
+    const u256* sc = A.sc + (size_t)p * A.sc_stride + (size_t)o * A.sc_out_stride + base;
+    const Affine* tbl = A.tbl + (size_t)base * GT_W;
+    unsigned* offs = reinterpret_cast<unsigned*>(gt_smem);                 // [GT_KEYS + 1]
+    unsigned* cur = offs + GT_KEYS + 1;                                    // [GT_KEYS]
+    unsigned short* list = reinterpret_cast<unsigned short*>(cur + GT_KEYS);
+    const size_t cta = ((size_t)p * A.n_out + o) * A.n_chunks + chunk;
+    Jac* keysum = A.scratch + cta * (GT_KEYS + 2 * GT_THREADS);
+    Jac* slotF = keysum + GT_KEYS;
+    Jac* slotL = slotF + GT_THREADS;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < GT_KEYS; i += GT_THREADS) cur[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += GT_THREADS) {                           // (1) count
+        u256 s = ld_u256(sc + i);
+        if (u256_is_zero(s)) continue;
+        int carry = 0;
+#pragma unroll 1
+        for (int j = 0; j < GT_W; j++) {
+            int d = gt_digit(s, j, carry);
+            if (d) atomicAdd(&cur[d < 0 ? ((-d - 1) * 2 + 1) : ((d - 1) * 2)], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {                                                        // (2) exclusive scan
+        const int per = GT_KEYS / 32;
+        unsigned sum = 0;
+        for (int i = 0; i < per; i++) sum += cur[tid * per + i];
+        unsigned pre = sum;
+#pragma unroll
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            unsigned v = __shfl_up_sync(0xffffffffu, pre, s2);
+            if (tid >= s2) pre += v;
+        }
+        unsigned run = pre - sum;
+        for (int i = 0; i < per; i++) { unsigned c = cur[tid * per + i]; offs[tid * per + i] = run; cur[tid * per + i] = run; run += c; }
+        if (tid == 31) offs[GT_KEYS] = pre;
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += GT_THREADS) {                           // (3) fill
+        u256 s = ld_u256(sc + i);
+        if (u256_is_zero(s)) continue;
+        int carry = 0;
+#pragma unroll 1
+        for (int j = 0; j < GT_W; j++) {
+            int d = gt_digit(s, j, carry);
+            if (d) {
+                unsigned pos = atomicAdd(&cur[d < 0 ? ((-d - 1) * 2 + 1) : ((d - 1) * 2)], 1u);
+                list[pos] = (unsigned short)(i * GT_W + j);
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned E = offs[GT_KEYS];
+    Jac* outp = A.out + cta;
+    if (E == 0) {
+        if (tid == 0) st_jac(outp, jac_inf());
+        return;
+    }
+    const unsigned L = (E + GT_THREADS - 1) / GT_THREADS;
+    {                                                                      // (4) balanced accumulate
+        const unsigned a = min(E, tid * L), b = min(E, a + L);
+        if (a < b) {
+            int lo = 0, hi = GT_KEYS - 1;                                  // last key with offs[key] <= a
+            while (lo < hi) {
+                int mid = (lo + hi + 1) >> 1;
+                if (offs[mid] <= a) lo = mid; else hi = mid - 1;
+            }
+            int key = lo;
+            while (offs[key + 1] <= a) key++;                              // skip empty keys
+            unsigned run_end = min(offs[key + 1], b);
+            Jac acc = jac_inf();
+            for (unsigned pos = a; pos < b; pos++) {
+                if (pos == run_end) {                                      // flush the finished run
+                    const bool first = offs[key] <= a;                     // (it cannot be the last run)
+                    st_jac(first ? (slotF + tid) : (keysum + key), acc);
+                    acc = jac_inf();
+                    do { key++; } while (offs[key + 1] <= pos);
+                    run_end = min(offs[key + 1], b);
+                }
+                acc = jac_madd(acc, ld_aff(tbl + list[pos]));   // sign of the key applied once, in (5a)
+            }
+            const bool first = offs[key] <= a;
+            st_jac(first ? (slotF + tid) : (slotL + tid), acc);            // the last run ends at b
+        }
+    }
+    __threadfence_block();
+    __syncthreads();
+    {                                                                      // (5a) merge runs per key, combine signs
+        Jac bm = jac_inf();                                                // bucket magnitude tid+1
+#pragma unroll 1
+        for (int sgn = 0; sgn < 2; sgn++) {
+            const int key = tid * 2 + sgn;
+            const unsigned k0 = offs[key], k1 = offs[key + 1];
+            if (k0 == k1) continue;
+            Jac sum = jac_inf();
+            const unsigned t0 = k0 / L, t1 = (k1 - 1) / L;
+            for (unsigned t = t0; t <= t1; t++) {
+                const unsigned a = min(E, t * L), b = min(E, a + L);
+                const bool first = k0 <= a, last = k1 >= b;
+                const Jac* src = first ? (slotF + t) : (last ? (slotL + t) : (keysum + key));
+                sum = jac_add(sum, ld_jac(src));
+            }
+            bm = jac_add(bm, sgn ? jac_neg(sum) : sum);
+        }
+        __syncthreads();                                                   // everyone has read the scratch
+        st_jac(keysum + tid, bm);                                          // reuse keysum[0..255] as B_m
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid < 32) {                                                        // (5b) sum_m m * B_m
+        Jac S = jac_inf(), Wt = jac_inf();                                 // over this lane's 8 buckets (top down)
+#pragma unroll 1
+        for (int k = 7; k >= 0; k--) {
+            S = jac_add(S, ld_jac(keysum + tid * 8 + k));
+            Wt = jac_add(Wt, S);                                           // sum_k (k+1) * B_{8 tid + k}
+        }
+        // total = sum_t (8 t * S_t + Wt_t) = 8 * sum_t t*S_t + sum_t Wt_t ;  sum_t t*S_t = sum_{t>=1} suffix_t
+        Jac suf = S;
+#pragma unroll 1
+        for (int s2 = 1; s2 < 32; s2 <<= 1) {
+            Jac other = shfl_jac(suf, (tid + s2) & 31);
+            if (tid + s2 < 32) suf = jac_add(suf, other);
+        }
+        Jac acc = (tid == 0) ? jac_inf() : suf;                            // lanes 1..31 hold suffix sums
+        acc = jac_dbl(jac_dbl(jac_dbl(acc)));                              // * 8
+        acc = jac_add(acc, Wt);
+#pragma unroll 1
+        for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+            Jac other = shfl_jac(acc, (tid + s2) & 31);
+            if (tid < s2) acc = jac_add(acc, other);
+        }
+        if (tid == 0) st_jac(outp, acc);
+    }
+}
+
+// out[m] = sum_k a[m*na + k] + sum_k b[m*nb + k]  (chunk partials of the fixed-base kernel plus,
+// for the verifier, the bucket kernel's result over the per-proof points)
+__global__ void k_jac_sum(const Jac* __restrict__ a, int na, const Jac* __restrict__ b, int nb, Jac* __restrict__ out,
+                          size_t n_msm) {
+    size_t m = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (m >= n_msm) return;
+    Jac acc = jac_inf();
+    for (int k = 0; k < na; k++) acc = jac_add(acc, ld_jac(a + m * na + k));
+    for (int k = 0; k < nb; k++) acc = jac_add(acc, ld_jac(b + m * nb + k));
+    st_jac(out + m, acc);
+}
+
+// ------------------------------------------------------------------------------------------
 // Fixed-base MSM for a handful of bases shared by every MSM (the range proofs' input commitments
 // value*g + type*hs0 + blind*hs1, src/RangeProof/Internal.hs:53-57): 8-bit window tables
 // tbl[(base*32 + w)*255 + d-1] = d * 2^(8w) * P, so one MSM is <= 32 mixed adds per base with no

@@ -18,7 +18,8 @@ EXPORTS = [
     "bppp_set_host_threads", "bppp_rp_prove_batch", "bppp_rp_verify_batch",
     "bppp_host_sha256", "bppp_host_oracle", "bppp_host_fr", "bppp_host_get_points",
     "bppp_profile_enable", "bppp_profile_reset", "bppp_profile_report", "bppp_timer_start", "bppp_timer_stop",
-    "bppp_measure_imad_peak",
+    "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
+    "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
 ]
 
 
@@ -70,6 +71,15 @@ def load_library():
     lib.bppp_timer_start.argtypes = [vp]
     lib.bppp_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     lib.bppp_measure_imad_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.bppp_gens_create.argtypes = [vp, sz, sz, u8p, u8p, u8p, C.POINTER(vp)]
+    lib.bppp_gens_destroy.argtypes = [vp]
+    lib.bppp_gens_destroy.restype = None
+    lib.bppp_gens_msm_batch.argtypes = [vp, sz, sz, u8p, u8p]
+    lib.bppp_set_device_host_threads.argtypes = [ip]
+    lib.bppp_set_device_host_threads.restype = None
+    lib.bppp_nl_create_gens.argtypes = [vp, ip, sz, u8p, u8p, u8p, u8p, u8p, C.POINTER(vp)]
+    lib.bppp_nl_verify_gens.argtypes = [vp, ip, sz, sz, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz, u8p, u8p, sz, u8p, u8p,
+                                        C.POINTER(ip)]
     lib.bppp_fb_create.argtypes = [vp, sz, u8p, C.POINTER(vp)]
     lib.bppp_fb_msm_batch.argtypes = [vp, sz, u8p, u8p]
     lib.bppp_fb_destroy.argtypes = [vp]
@@ -231,6 +241,20 @@ class Context:
         self._ck(self.lib.bppp_msm_batch(self.h, batch, n, scalars_bytes, points_bytes, 1 if shared_points else 0, out),
                  "bppp_msm_batch")
         return out.raw[:64 * batch]
+
+    def gens_msm_batch(self, g, G, H, scalars):
+        """MSMs over the resident generator list [g | G | H] (fixed-base tables): scalars [batch][n]"""
+        gh = C.c_void_p()
+        self._ck(self.lib.bppp_gens_create(self.h, len(G), len(H), point_to_bytes(g), points_to_bytes(G),
+                                           points_to_bytes(H), C.byref(gh)), "bppp_gens_create")
+        try:
+            batch, n = len(scalars), len(scalars[0])
+            out = _buf(64 * batch)
+            self._ck(self.lib.bppp_gens_msm_batch(gh, batch, n, b"".join(ints_to_bytes(r) for r in scalars), out),
+                     "bppp_gens_msm_batch")
+            return bytes_to_points(out.raw[:64 * batch])
+        finally:
+            self.lib.bppp_gens_destroy(gh)
 
     # -- `collapsePoints b a gL gR` over a vector (src/Bulletproof.hs:213-214)
     def pair_fold(self, a, b, points):

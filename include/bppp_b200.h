@@ -59,6 +59,19 @@ int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* poi
 int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8_t* scalars, const uint8_t* points,
                    int shared_points, uint8_t* out);
 
+/* ---- the shared generator list [g | G | H] resident on the device with its fixed-base window
+ * table (2^(9j) * P_i): used by round 1 of every argument, every range-proof commitment
+ * (commitRPW, src/RangeProof/Internal.hs:43-48) and the verifier's collapsed MSM.  The reference's
+ * analogue is the generator cache points.bin (app/Main.hs:147,259-263). */
+typedef struct bppp_gens bppp_gens;
+int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t* g, const uint8_t* G, const uint8_t* H,
+                     bppp_gens** out);
+void bppp_gens_destroy(bppp_gens* g);
+/* `batch` MSMs over the first n generators of the list: scalars batch*n*32, out batch*64 */
+int bppp_gens_msm_batch(bppp_gens* g, size_t batch, size_t n, const uint8_t* scalars, uint8_t* out);
+/* host threads used by the round sequencing inside the device entry points (0 = all cores) */
+void bppp_set_device_host_threads(int n);
+
 /* ---- fixed-base MSMs over a handful of generators shared by every call: the range proofs'
  * input commitments value*g + type*hs0 + blind*hs1 (scalarRPW' / scalarPairRPW' + commitRPW,
  * src/RangeProof/Internal.hs:43-57; app/Main.hs:287-288,315).  Precomputed 8-bit window tables. */
@@ -90,6 +103,9 @@ int bppp_rational_reduce(const uint8_t x[32], uint8_t a[32], int* a_neg, uint8_t
 int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, const uint8_t* g, const uint8_t* G,
                    const uint8_t* H, const uint8_t* q, const uint8_t* s, const uint8_t* w, const uint8_t* l,
                    const uint8_t* c, bppp_nl** out);
+/* same, over a resident generator list (no table rebuild per call) */
+int bppp_nl_create_gens(bppp_gens* gens, int kind, size_t batch, const uint8_t* q, const uint8_t* s, const uint8_t* w,
+                        const uint8_t* l, const uint8_t* c, bppp_nl** out);
 /* makeScalarsComs + the two `commit`s of proveRoundM (src/Bulletproof.hs:346-350):
  * X[b], R[b] (64 bytes each; L, R for the IP argument). */
 int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R);
@@ -114,6 +130,11 @@ int bppp_nl_verify(bppp_ctx* ctx, int kind, size_t batch, size_t N, size_t M, si
                    const uint8_t* c, const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin,
                    const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p,
                    int* ok);
+
+int bppp_nl_verify_gens(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
+                        const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR, size_t n_norm,
+                        size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s,
+                        const uint8_t* init_p, int* ok);
 
 /* ---- Range-proof layer (host C++ above the device entry points; the Fiat-Shamir transcript,
  * round sequencing and the scalar phases run on host threads, every group operation on the GPU).

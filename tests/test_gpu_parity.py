@@ -204,3 +204,20 @@ def test_verify_accepts_and_rejects(ctx, gens):
     xr_bad[0][2] = (xr_bad[0][2][1], xr_bad[0][2][0])
     assert ctx.nl_verify(bp.ARG_NL, g, Gs, Hs, q, [0] * B, zero_w, c, es, xr_bad, fw, fl,
                          [[(1, C0[b])] for b in range(B)]) == [False, True, True]
+
+
+@pytest.mark.parametrize("n", [1, 5, 300, 1286, 2048, 2049, 4500])
+def test_fixed_base_generator_msm(ctx, gens, n):
+    """bppp_gens_msm_batch: window-table MSM over the resident generator list, incl. heavily repeated
+    scalars (reciprocal witnesses), zeros, small digits and the multi-chunk case."""
+    pts = gens(min(n, 1300))
+    pts = [pts[i % len(pts)] for i in range(n)]
+    g, Gs = pts[0], pts[1:]
+    rows = [[H("fb", n, i) % R for i in range(n)],
+            [H("rep", n, i % 3) % R for i in range(n)],                 # three distinct scalars
+            [0] * n,
+            [(i * 7) % 256 for i in range(n)],                          # digits
+            [R - 1] * n,
+            [1 if i == n - 1 else 0 for i in range(n)]]
+    got = ctx.gens_msm_batch(g, Gs, [], rows)
+    assert got == [G.msm(zip(r, pts)) for r in rows]
