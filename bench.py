@@ -184,11 +184,25 @@ def main():
         nt = args.host_threads or max(1, (os.cpu_count() or 1) // world)
         ctx.lib.bppp_set_host_threads(nt)
     setup = bp.RangeProofSetup(ctx, workload_schema())
+    lanes = setup.contexts()
     B, n = args.batch, setup.n_inputs
     assert (setup.nrm_len, setup.lin_len, setup.rounds) == (1024, 261, 9)
 
+    def merged_report():
+        tot = {"kernels": {}, "h2d_bytes": 0, "d2h_bytes": 0}
+        for c in lanes:
+            r = c.profile_report()
+            tot["h2d_bytes"] += r["h2d_bytes"]
+            tot["d2h_bytes"] += r["d2h_bytes"]
+            for name, kk in r["kernels"].items():
+                d = tot["kernels"].setdefault(name, {"launches": 0, "ms": 0.0, "work": 0.0})
+                for f in d:
+                    d[f] += kk[f]
+        return tot
+
     def barrier():
-        ctx.sync()
+        for c in lanes:
+            c.sync()
         if world > 1:
             dist.barrier()
 
@@ -204,9 +218,10 @@ def main():
         out = step(inputs)
         assert all(out[3]), "a warm-up proof failed to verify"
     # ---- timed region 1: `value` -- inputs staged before the clock starts, device-timed
-    ctx.profile_enable(True)
-    ctx.profile_reset()
-    launches0 = ctx.launch_count()
+    for c in lanes:
+        c.profile_enable(True)
+        c.profile_reset()
+    launches0 = sum(c.launch_count() for c in lanes)
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -219,9 +234,10 @@ def main():
     barrier()
     clocks = sampler.stop()
     assert all(out[3])
-    rep = ctx.profile_report()
-    launches = ctx.launch_count() - launches0
-    ctx.profile_enable(False)
+    rep = merged_report()
+    launches = sum(c.launch_count() for c in lanes) - launches0
+    for c in lanes:
+        c.profile_enable(False)
     # ---- timed region 2: `e2e` -- inputs built on the host every step, results parsed back
     barrier()
     t0 = time.time()
@@ -280,13 +296,13 @@ def main():
             "config": {"workload": "examples/128by64 prove+verify (N=1024, M=261, 9 rounds), %d proofs per GPU per step" % B,
                        "batch_per_gpu": B, "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "working set per step (%.0f MB of generators+witness vectors) exceeds the 126 MB L2" % (B * 0.33),
-                       "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world)},
+                       "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world), "lanes": len(lanes)},
             "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": rep["h2d_bytes"] // args.steps,
                     "d2h_bytes_per_step": rep["d2h_bytes"] // args.steps,
                     "note": "host buffers in, proofs + verdicts out through bppp_rp_prove_batch/bppp_rp_verify_batch; "
                             "inputs rebuilt on the host every step, wall clock"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
-            "kernel_time_shares": shares, "gpu_busy_frac": tot_ms / ms,
+            "kernel_time_shares": shares, "gpu_kernel_ms_over_step_ms": tot_ms / ms,
             "imad_peak": {"wide_per_s": imad_wide, "lo32_per_s": imad_lo}, "wall_s_value_leg": wall}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -21,11 +22,11 @@ using namespace bppp;
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
-                                                   "k_jac_sum", "k_gt_build"};
+                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -125,10 +126,13 @@ static double msm_alg_imads(double n) {          // ceil(256/c*) (n
 static thread_local double g_work = 0;           // set by the caller right before a launch
 
 int g_capi_threads = 0;
+static thread_local int t_capi_threads = 0;
 extern "C" void bppp_set_device_host_threads(int n) { g_capi_threads = n; }
+extern "C" void bppp_set_thread_host_threads(int n) { t_capi_threads = n; }
+extern "C" int bppp_ctx_device(bppp_ctx* ctx);
 template <class F>
 static void host_parallel_for(size_t n, F fn) {
-    int nt = g_capi_threads > 0 ? g_capi_threads : (int)std::thread::hardware_concurrency();
+    int nt = t_capi_threads > 0 ? t_capi_threads : (g_capi_threads > 0 ? g_capi_threads : (int)std::thread::hardware_concurrency());
     if (nt < 1) nt = 1;
     if ((size_t)nt > n / 16) nt = (int)(n / 16);
     if (nt <= 1) {
@@ -313,6 +317,7 @@ extern "C" void bppp_free(bppp_ctx* ctx) {
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
+extern "C" int bppp_ctx_device(bppp_ctx* ctx) { return ctx ? ctx->dev : -1; }
 extern "C" const char* bppp_last_error(bppp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" uint64_t bppp_launch_count(bppp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int bppp_sync(bppp_ctx* ctx) {
@@ -627,7 +632,6 @@ struct bppp_gens {
     size_t N, M, P0;
     DBuf<Affine> base;               // [g | G | H]
     DBuf<Affine> tbl;                // [P0][GT_W]
-    DBuf<Jac> scratch, parts;
     std::vector<uint8_t> host;       // P0 * 64 bytes (for the bucket-kernel fallback paths)
 };
 namespace {
@@ -645,15 +649,16 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
     }
     int nch = (int)((n_terms + GT_MAX_CHUNK - 1) / GT_MAX_CHUNK);
     size_t ctas = batch * n_out * nch;
-    CK(g->scratch.ensure(ctas * (GT_KEYS + 2 * GT_THREADS)));
+    DBuf<Jac> scratch, partsbuf;     // stream-ordered pool allocations: cheap, and safe across lanes
+    CK(scratch.alloc(ctas * (GT_KEYS + 2 * GT_THREADS)));
     Jac* parts = d_out;
-    if (nch > 1) { CK(g->parts.ensure(ctas)); parts = g->parts.p; }
+    if (nch > 1) { CK(partsbuf.alloc(ctas)); parts = partsbuf.p; }
     int max_n = (int)std::min<size_t>(GT_MAX_CHUNK, n_terms);
     for (size_t b0 = 0; b0 < batch; b0 += 32768) {
         size_t nb = std::min<size_t>(32768, batch - b0);
         GtArgs A;
         A.tbl = g->tbl.p; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
-        A.n_total = (int)n_terms; A.scratch = g->scratch.p + b0 * n_out * nch * (GT_KEYS + 2 * GT_THREADS);
+        A.n_total = (int)n_terms; A.scratch = scratch.p + b0 * n_out * nch * (GT_KEYS + 2 * GT_THREADS);
         A.out = parts + b0 * n_out * nch; A.n_out = n_out; A.n_chunks = nch;
         g_work = work_per_proof * (double)nb;
         { ProfScope ps_(ctx, K_MSM_GENS, g_work);
@@ -752,13 +757,16 @@ struct bppp_nl {
     DBuf<Jac> jscratch, res;
     MsmPlan plan;
     int blocks_n = 1, blocks_l = 1;
+    // tensor mode: no generator folding; per-generator fold coefficients + folded opening scalars
+    bool tensor = false;
+    DBuf<u256> coef, fsc;           // coef [B][N+M] (Montgomery); fsc [2][B][P0] (Montgomery)
     // host state (Montgomery, 4 x 64-bit limbs; bit-compatible with the device's u256)
     std::vector<Fr> q, qinv, nn, nl, s, sX, sR;
 };
 
 namespace {
 enum { C_RHO = 0, C_K1, C_K2, C_AU, C_BU, C_AL, C_BL, C_AC, C_BC, C_COEF /* 8 */, C_KB = C_COEF + 8 /* 2 */,
-       C_KA = C_KB + 2 /* 2 */, C_COUNT = C_KA + 2 };
+       C_KA = C_KB + 2 /* 2 */, C_A0N = C_KA + 2, C_B0N, C_A0L, C_B0L, C_COUNT };
 inline u256* cptr(bppp_nl* h, int which) { return h->consts.p + (size_t)which * h->B; }
 static_assert(sizeof(Fr) == sizeof(u256), "host and device field elements share one layout");
 
@@ -838,7 +846,19 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
     h->N2 = (N + 1) / 2; h->M2 = (M + 1) / 2; h->P0 = 1 + N + M; h->P2 = 1 + h->N2 + h->M2;
     auto fail = [&](int rc) { h->own_gens = false; bppp_nl_destroy(h); return rc; };
 #define CKH(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x ": ") + cudaGetErrorString(e_); return fail(BPPP_ERR_CUDA); } } while (0)
-    CKH(h->pts[0].alloc(batch * h->P2)); CKH(h->pts[1].alloc(batch * h->P2));
+    {
+        const char* ev = getenv("BPPP_ROUND_MODE");          // fold | tensor | auto (default)
+        if (ev && !strcmp(ev, "fold")) h->tensor = false;
+        else if (ev && !strcmp(ev, "tensor")) h->tensor = true;
+        else h->tensor = (h->P0 <= 8192);                     // few rounds: k fixed-base MSMs beat fold + bucket MSMs
+    }
+    if (h->tensor) {
+        CKH(h->coef.alloc(batch * (N + M)));
+        CKH(h->fsc.alloc(2 * batch * h->P0));
+    } else {
+        CKH(h->pts[0].alloc(batch * h->P2)); CKH(h->pts[1].alloc(batch * h->P2));
+        CKH(h->jscratch.alloc(batch * (h->N2 + h->M2)));
+    }
     CKH(h->aff.alloc(batch * 2));
     CKH(h->w[0].alloc(batch * N)); CKH(h->w[1].alloc(batch * h->N2));
     CKH(h->l[0].alloc(batch * M)); CKH(h->l[1].alloc(batch * h->M2));
@@ -848,9 +868,8 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
     CKH(h->dots.alloc(batch * 2));
     CKH(h->consts.alloc((size_t)C_COUNT * batch));
     CKH(h->sgn.alloc(batch * 2));
-    CKH(h->jscratch.alloc(batch * (h->N2 + h->M2)));
     CKH(h->res.alloc(batch * 2));
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 2 && !h->tensor; k++) {
         { ProfScope ps_(ctx, K_BCAST, 0);
         k_bcast_point<<<(unsigned)((batch + 127) / 128), 128, 0, ctx->st>>>(gens->base.p, h->pts[k].p, h->P2, batch);
         }
@@ -966,10 +985,13 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         CK(cudaGetLastError());
     }
     const int src = h->cur;
+    const bool expand = h->tensor && h->round > 0;              // folded scalars go through the coefficient vector
+    u256* fxs = expand ? h->fsc.p : xs;
+    u256* frs = expand ? h->fsc.p + B * P0 : rs;
     if (h->curN) {
         MsmScalarsArgs A;
         A.x = h->w[src].p; A.in_stride = h->wstride[src]; A.n_in = (int)h->curN;
-        A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1; A.coef = cptr(h, C_COEF);
+        A.xs = fxs; A.rs = frs; A.mont_out = expand; A.sc_stride = P0; A.off = 1; A.coef = cptr(h, C_COEF);
         const unsigned char kd[8] = {0, 2, 2, 0, 0, 0, 0, 1};
         memcpy(A.kind, kd, 8);
         { ProfScope ps_(ctx, K_MSM_SCALARS, 0);
@@ -980,7 +1002,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     if (h->curM) {
         MsmScalarsArgs A;
         A.x = h->l[src].p; A.in_stride = h->lstride[src]; A.n_in = (int)h->curM;
-        A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = 1 + (int)h->curN; A.coef = cptr(h, C_COEF);
+        A.xs = fxs; A.rs = frs; A.mont_out = expand; A.sc_stride = P0; A.off = 1 + (int)h->curN; A.coef = cptr(h, C_COEF);
         const unsigned char kd[8] = {0, 1, 1, 0, 0, 0, 0, 1};
         memcpy(A.kind, kd, 8);
         { ProfScope ps_(ctx, K_MSM_SCALARS, 0);
@@ -988,12 +1010,27 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         }
         CK(cudaGetLastError());
     }
+    if (expand) {
+        for (int seg = 0; seg < 2; seg++) {
+            const size_t n0 = seg ? h->M : h->N;
+            if (!n0) continue;
+            ExpandArgs A;
+            A.fx = fxs; A.fr_ = frs; A.f_stride = P0; A.f_off = seg ? 1 + (int)h->curN : 1;
+            A.coef = h->coef.p; A.coef_stride = h->N + h->M; A.coef_off = seg ? (int)h->N : 0;
+            A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = seg ? 1 + (int)h->N : 1;
+            A.n = (int)n0; A.shift = h->round;
+            { ProfScope ps_(ctx, K_EXPAND, 0);
+            k_expand_scalars<<<dim3((unsigned)((n0 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+            }
+            CK(cudaGetLastError());
+        }
+    }
     // the two commitments: MSMs over [g | G | H] with X scalars (output 0) and R scalars (output 1)
-    const size_t nterms = 1 + h->curN + h->curM;
+    const size_t nterms = h->tensor ? P0 : 1 + h->curN + h->curM;
     const double nX = (double)nterms, nR = 1.0 + (double)((h->curN + 1) / 2) + (double)((h->curM + 1) / 2);
     const double work = msm_alg_imads(nX) + msm_alg_imads(nR);
-    if (h->curp < 0) {
-        // round 1: the generators are the shared list -> fixed-base tables
+    if (h->curp < 0 || h->tensor) {
+        // the generators are the shared list -> fixed-base tables
         if ((rc = run_msm_gens(h->gens, nterms, xs, P0, B * P0, B, 2, h->res.p, work))) return rc;
     } else {
         h->plan.slices.clear();
@@ -1023,7 +1060,7 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     ENTER(ctx);
     const size_t B = h->B;
     if (!check_fr(e, B)) FAIL(BPPP_ERR_RANGE, "challenge >= group order");
-    std::vector<Fr> au(B), bu(B), al(B), bl(B), ac(B), bc(B), rho(B), b0n(B), b0l(B), em(B), inv(2 * B);
+    std::vector<Fr> au(B), bu(B), al(B), bl(B), ac(B), bc(B), rho(B), b0n(B), b0l(B), em(B), inv(2 * B), a0n(B);
     std::vector<u256> kk(B * 4);
     std::vector<unsigned char> sg(B * 2);
     host_parallel_for(B, [&](size_t b) {
@@ -1037,6 +1074,7 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
         sg[b * 2 + 0] = (unsigned char)((rn.b_neg ? 1 : 0) | (rn.a_neg ? 2 : 0));
         sg[b * 2 + 1] = (unsigned char)((rl.b_neg ? 1 : 0) | (rl.a_neg ? 2 : 0));
         b0n[b] = fr_from_mag(rn.b, rn.b_neg);
+        a0n[b] = fr_from_mag(rn.a, rn.a_neg);
         b0l[b] = fr_from_mag(rl.b, rl.b_neg);
         ac[b] = b0l[b];                                              // c' = b0*cL + a0*cR
         bc[b] = fr_from_mag(rl.a, rl.a_neg);
@@ -1069,8 +1107,30 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     CK(H2D(h->sgn.p, sg.data(), B * 2));
     // scalar vectors (and the next round's dots)
     if ((rc = launch_fold_dots(h, 1))) return rc;
-    // generators
     const size_t nN = (h->curN + 1) / 2, nM = (h->curM + 1) / 2;
+    if (h->tensor) {
+        // generators are not folded: update the per-generator fold coefficients instead
+        if ((rc = upload_consts(h, C_A0N, a0n)) || (rc = upload_consts(h, C_B0N, b0n)) || (rc = upload_consts(h, C_A0L, bc)) ||
+            (rc = upload_consts(h, C_B0L, b0l)))
+            return rc;
+        for (int seg = 0; seg < 2; seg++) {
+            const size_t n0 = seg ? h->M : h->N;
+            if (!n0) continue;
+            { ProfScope ps_(ctx, K_COEF, 0);
+            k_coef_update<<<dim3((unsigned)((n0 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(
+                h->coef.p, h->N + h->M, seg ? (int)h->N : 0, (int)n0, h->round, cptr(h, seg ? C_A0L : C_A0N),
+                cptr(h, seg ? C_B0L : C_B0N), 1, h->round == 0);
+            }
+            CK(cudaGetLastError());
+        }
+        h->cur ^= 1;
+        h->curN = nN;
+        h->curM = nM;
+        h->round++;
+        CK(cudaStreamSynchronize(ctx->st));
+        return BPPP_OK;
+    }
+    // generators
     PairFoldSeg segs[2] = {{1, (int)h->curN, 0}, {1 + (int)h->curN, (int)h->curM, (int)nN}};
     const Affine* in = h->curp < 0 ? h->gens->base.p : h->pts[h->curp].p;
     size_t in_stride = h->curp < 0 ? 0 : h->P2;

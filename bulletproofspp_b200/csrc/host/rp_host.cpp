@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <mutex>
 #include <set>
 #include <string>
 #include <thread>
@@ -37,6 +38,7 @@ typedef unsigned __int128 U128;
 namespace {
 
 // ------------------------------------------------------------------------------ utilities
+static bool t_lane_threads_is_main();
 struct Timing {                                // BPPP_TIMING=1: coarse wall-clock split printed to stderr
     std::map<std::string, double> ms;
     bool on = getenv("BPPP_TIMING") != nullptr;
@@ -46,10 +48,10 @@ struct Timing {                                // BPPP_TIMING=1: coarse wall-clo
         clock_gettime(CLOCK_MONOTONIC, &ts);
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     }
-    void start() { if (on) last = now(); }
-    void lap(const char* name) { if (on) { double t = now(); ms[name] += t - last; last = t; } }
+    void start() { if (on && t_lane_threads_is_main()) last = now(); }
+    void lap(const char* name) { if (on && t_lane_threads_is_main()) { double t = now(); ms[name] += t - last; last = t; } }
     void dump(const char* what) {
-        if (!on) return;
+        if (!on || !t_lane_threads_is_main()) return;
         fprintf(stderr, "[bppp timing] %s:", what);
         for (auto& kv : ms) fprintf(stderr, " %s=%.1fms", kv.first.c_str(), kv.second);
         fprintf(stderr, "\n");
@@ -57,8 +59,12 @@ struct Timing {                                // BPPP_TIMING=1: coarse wall-clo
     }
 };
 Timing g_tm;
+extern thread_local bool t_is_lane0;
+static bool t_lane_threads_is_main() { return t_is_lane0; }
 int g_threads = 0;
+extern thread_local int t_lane_threads;
 int n_threads() {
+    if (t_lane_threads > 0) return t_lane_threads;
     if (g_threads > 0) return g_threads;
     unsigned h = std::thread::hardware_concurrency();
     return h ? (int)h : 4;
@@ -89,6 +95,18 @@ I128 load_i128(const uint8_t b[16]) {
     return (I128)v;
 }
 Fr fr_pow(Fr b, uint64_t e) { return h64::pow_u64(b, e); }
+// Montgomery forms of small integers (digits, multiplicities, symbols) without a multiplication
+const Fr* small_table() {
+    static std::vector<Fr> t;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        t.resize(2048);
+        Fr acc = h64::zero(), one = h64::one();
+        for (size_t i = 0; i < t.size(); i++) { t[i] = acc; acc = h64::add(acc, one); }
+    });
+    return t.data();
+}
+inline Fr fr_small(U128 v) { return v < 2048 ? small_table()[(size_t)v] : h64::from_u128(v); }
 int integer_log(U128 b, U128 n) {            // src/Utils.hs:91-92
     int r = 0;
     while (n >= b) { n /= b; r++; }
@@ -130,6 +148,7 @@ struct Range {
     U128 base = 2;
     bool is_shared = false, is_output = false, is_assumed = false, has_bit = false;
     std::vector<U128> coeffs;                  // baseCoeffs
+    std::vector<Fr> coeffs_fr;                 // the same as field elements (cached)
 };
 struct Public {
     I128 amount, type;
@@ -169,8 +188,14 @@ struct bppp_rp {
     Affine g;
     std::vector<uint8_t> table;                // [g | gs | hs] as bytes (device MSM base table)
     std::vector<uint8_t> in_pts;               // TRRP: [g, hs0, hs1]; Binary: [g, h0]
-    bppp_fb* fb = nullptr;                     // fixed-base tables over in_pts
-    bppp_gens* gens = nullptr;                 // resident [g | gs | hs] with window tables
+    bppp_fb* fb = nullptr;                     // fixed-base tables over in_pts        (lane 0)
+    bppp_gens* gens = nullptr;                 // resident [g | gs | hs] with window tables (lane 0)
+    // extra lanes: sub-batches of one call run concurrently, each on its own context (stream) and
+    // driver thread, so the host phases of one lane overlap the device work of another
+    std::vector<bppp_ctx*> lane_ctx;
+    std::vector<bppp_fb*> lane_fb;
+    std::vector<bppp_gens*> lane_gens;
+    std::mutex err_mu;
     std::string err;
 };
 
@@ -218,6 +243,8 @@ bool make_range_trrp(Range& rd) {
     }
     bs.insert(bs.end(), tail.begin(), tail.end());
     rd.coeffs = rd.is_assumed ? std::vector<U128>() : bs;
+    rd.coeffs_fr.clear();
+    for (auto c : rd.coeffs) rd.coeffs_fr.push_back(h64::from_u128(c));
     return true;
 }
 // ---- Binary.makeRangeData (Binary.hs:48-54)
@@ -391,7 +418,7 @@ bool adjust_value(const Range& rd, const uint8_t val[32], U128& n_adj) {
 }
 // makePhase1s (TypedReciprocal.hs:128-152); prover = false builds the verifier's empty-witness copy
 bool make_phase1s(int ind, const Range& rd, const uint8_t* val, bool prover, std::vector<Ph1>& out, bool& has_ms,
-                  std::vector<Fr>& ms_out) {
+                  std::vector<U128>& ms_out) {
     has_ms = false;
     if (rd.is_assumed) return true;
     std::vector<U128> ds;
@@ -417,23 +444,22 @@ bool make_phase1s(int ind, const Range& rd, const uint8_t* val, bool prover, std
         for (size_t i = 0; i < rd.coeffs.size(); i++) {
             Ph1 p;
             p.kind = 'S'; p.ind = ind; p.base = base_at(i);
-            p.b = h64::from_u128(rd.coeffs[i]); p.d = h64::from_u128(ds[i]); p.m = h64::zero();
+            p.b = rd.coeffs_fr[i]; p.d = fr_small(ds[i]); p.m = h64::zero();
             out.push_back(p);
         }
         has_ms = true;
-        ms_out.clear();
-        for (auto m : ms) ms_out.push_back(h64::from_u128(m));
+        ms_out = ms;
         return true;
     }
     size_t L = std::max(std::max(rd.coeffs.size(), ds.size()), std::max(ms.size(), ns.size()));
     for (size_t i = 0; i < L; i++) {
         Ph1 p;
         p.kind = 'I'; p.ind = ind; p.base = base_at(i);
-        p.b = h64::from_u128(i < rd.coeffs.size() ? rd.coeffs[i] : 0);
-        p.d = h64::from_u128(i < ds.size() ? ds[i] : 0);
-        p.m = h64::from_u128(i < ms.size() ? ms[i] : 0);
+        p.b = i < rd.coeffs.size() ? rd.coeffs_fr[i] : h64::zero();
+        p.d = fr_small(i < ds.size() ? ds[i] : 0);
+        p.m = fr_small(i < ms.size() ? ms[i] : 0);
         U128 sym = i < ns.size() ? ns[i] : 0;
-        p.s = h64::from_u128(sym);
+        p.s = fr_small(sym);
         p.s_zero = (sym == 0);
         out.push_back(p);
     }
@@ -583,7 +609,7 @@ std::vector<Ph1> ph1s_verifier(const bppp_rp* s) {
         }
     for (size_t i = 0; i < s->rds.size(); i++) {
         bool hm;
-        std::vector<Fr> ms;
+        std::vector<U128> ms;
         make_phase1s((int)i, s->rds[i], nullptr, false, out, hm, ms);
     }
     return out;
@@ -645,25 +671,34 @@ struct Proof {
 };
 
 int fail(bppp_rp* s, int code, const std::string& msg) {
+    std::lock_guard<std::mutex> lk(s->err_mu);
     s->err = msg;
     return code;
 }
-const char* ctx_err(bppp_rp* s) { return bppp_last_error(s->ctx); }
+struct Lane {
+    bppp_ctx* ctx;
+    bppp_fb* fb;
+    bppp_gens* gens;
+    int threads;                               // host threads this lane may use
+};
+thread_local int t_lane_threads = 0;
+thread_local bool t_is_lane0 = true;
+const char* ctx_err(const Lane& ln) { return bppp_last_error(ln.ctx); }
 
 // run the argument (proveBPM, src/Bulletproof.hs:357-359) for the whole batch
-int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::vector<uint8_t>& q, const std::vector<uint8_t>& sc,
+int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t rounds, const std::vector<uint8_t>& q, const std::vector<uint8_t>& sc,
                  const std::vector<uint8_t>& w, const std::vector<uint8_t>& l, const std::vector<uint8_t>& c,
                  uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l) {
     const size_t B = P.size(), N = s->nrm_len, M = s->lin_len;
     bppp_nl* h = nullptr;
-    int rc = bppp_nl_create_gens(s->gens, s->arg, B, q.data(), sc.data(), w.data(), l.data(), c.data(), &h);
-    if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(s));
+    int rc = bppp_nl_create_gens(ln.gens, s->arg, B, q.data(), sc.data(), w.data(), l.data(), c.data(), &h);
+    if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(ln));
     std::vector<uint8_t> X(B * 64), R(B * 64), E(B * 32);
     g_tm.lap("nl_create");
     for (size_t r = 0; r < rounds; r++) {
         rc = bppp_nl_round_commit(h, X.data(), R.data());
         g_tm.lap("nl_commit");
-        if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_commit: ") + ctx_err(s)); }
+        if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_commit: ") + ctx_err(ln)); }
         parallel_for(B, [&](size_t b) {
             uint8_t xr[128];
             memcpy(xr, &X[64 * b], 64);
@@ -677,7 +712,7 @@ int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::ve
         g_tm.lap("round_hash");
         rc = bppp_nl_round_fold(h, E.data());
         g_tm.lap("nl_fold");
-        if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_fold: ") + ctx_err(s)); }
+        if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_fold: ") + ctx_err(ln)); }
     }
     size_t cn = 0, cl = 0;
     bppp_nl_lengths(h, &cn, &cl);
@@ -687,7 +722,7 @@ int run_argument(bppp_rp* s, std::vector<Proof>& P, size_t rounds, const std::ve
     bppp_nl_destroy(h);
     g_tm.lap("nl_final");
     g_tm.dump("prove");
-    if (rc) return fail(s, rc, std::string("bppp_nl_final: ") + ctx_err(s));
+    if (rc) return fail(s, rc, std::string("bppp_nl_final: ") + ctx_err(ln));
     for (size_t b = 0; b < B; b++) {       // getWitness: norm scalars then linear scalars (RangeProof.hs:65)
         memcpy(finals + 32 * b * (cn + cl), &fw[32 * b * cn], 32 * cn);
         memcpy(finals + 32 * (b * (cn + cl) + cn), &fl[32 * b * cl], 32 * cl);
@@ -769,6 +804,24 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
     if (rc) { delete s; return rc; }
     rc = bppp_gens_create(ctx, s->nrm_len, s->lin_len, &s->table[0], &s->table[64], &s->table[64 * (1 + s->nrm_len)], &s->gens);
     if (rc) { bppp_fb_destroy(s->fb); delete s; return rc; }
+    {   // extra lanes (BPPP_LANES, default 4 in total)
+        const char* ev = getenv("BPPP_LANES");
+        int lanes = ev ? atoi(ev) : 4;
+        int dev = bppp_ctx_device(ctx);
+        for (int i = 1; i < lanes; i++) {
+            bppp_ctx* c2 = nullptr;
+            bppp_fb* f2 = nullptr;
+            bppp_gens* g2 = nullptr;
+            if (bppp_init(dev, &c2)) break;
+            if (bppp_fb_create(c2, s->in_pts.size() / 64, s->in_pts.data(), &f2) ||
+                bppp_gens_create(c2, s->nrm_len, s->lin_len, &s->table[0], &s->table[64], &s->table[64 * (1 + s->nrm_len)], &g2)) {
+                bppp_fb_destroy(f2);
+                bppp_free(c2);
+                break;
+            }
+            s->lane_ctx.push_back(c2); s->lane_fb.push_back(f2); s->lane_gens.push_back(g2);
+        }
+    }
     *out = s;
     return BPPP_OK;
 }
@@ -776,6 +829,11 @@ void bppp_rp_free(bppp_rp* s) {
     if (!s) return;
     bppp_fb_destroy(s->fb);
     bppp_gens_destroy(s->gens);
+    for (size_t i = 0; i < s->lane_ctx.size(); i++) {
+        bppp_fb_destroy(s->lane_fb[i]);
+        bppp_gens_destroy(s->lane_gens[i]);
+        bppp_free(s->lane_ctx[i]);
+    }
     delete s;
 }
 const char* bppp_rp_last_error(bppp_rp* s) { return s ? s->err.c_str() : "null setup"; }
@@ -813,11 +871,8 @@ int bppp_input_blind(const char* random_seed, uint64_t j, uint8_t out[32]) {
 // Outputs: coms [batch][num_rp_coms + n_inputs] points in the reference's order
 //   (blCom : rCom : dmCom : mCom : nComs  /  blCom : dCom : nComs); responses [batch][rounds][2]
 //   points NEWEST FIRST; finals [batch][fin_norm + fin_lin] scalars (getWitness order).
-int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
-                        const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals) {
-    if (!s) return BPPP_ERR_ARG;
-    if (!values || !random_seeds || !coms || !responses || !finals || batch == 0) return fail(s, BPPP_ERR_ARG, "null/empty argument");
-    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
+static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
+                      const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals) {
     const size_t B = batch, n = s->n_inputs, N = s->nrm_len, M = s->lin_len, P0 = 1 + N + M, NC = s->num_rp_coms + n;
     std::vector<Proof> P(B);
     std::atomic<int> bad(0);
@@ -883,22 +938,22 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
                 if (!kv.second.is_zero()) { p.ok = false; bad++; return; }
         }
         std::vector<Ph1> digits_ph1;
-        std::map<U128, std::vector<Fr>> bm;
+        std::map<U128, std::vector<U128>> bm;                              // multiplicities summed as integers
         for (size_t i = 0; i < n; i++) {
             bool has_ms;
-            std::vector<Fr> ms;
+            std::vector<U128> ms;
             if (!make_phase1s((int)i, s->rds[i], values + 32 * (b * n + i), true, digits_ph1, has_ms, ms)) { p.ok = false; bad++; return; }
             if (has_ms) {                                                   // baseMss (:363-367)
                 const Range& rd = s->rds[i];
-                auto merge = [&](U128 base, const std::vector<Fr>& v) {
+                auto merge = [&](U128 base, const U128* v, size_t cnt) {
                     auto it = bm.find(base);
-                    if (it == bm.end()) bm[base] = v;
-                    else for (size_t k = 0; k < v.size() && k < it->second.size(); k++) it->second[k] = h64::add(it->second[k], v[k]);
+                    if (it == bm.end()) bm[base] = std::vector<U128>(v, v + cnt);
+                    else for (size_t k = 0; k < cnt && k < it->second.size(); k++) it->second[k] += v[k];
                 };
                 if (rd.has_bit) {
-                    merge(2, std::vector<Fr>(ms.begin(), ms.begin() + 1));
-                    merge(rd.base, std::vector<Fr>(ms.begin() + 1, ms.end()));
-                } else merge(rd.base, ms);
+                    merge(2, ms.data(), 1);
+                    merge(rd.base, ms.data() + 1, ms.size() - 1);
+                } else merge(rd.base, ms.data(), ms.size());
             }
         }
         if (s->flag)
@@ -909,7 +964,11 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
                 p.ph1s.push_back(t);
             }
         p.ph1s.insert(p.ph1s.end(), digits_ph1.begin(), digits_ph1.end());
-        for (auto& kv : bm) p.base_mss.push_back(kv);
+        for (auto& kv : bm) {
+            std::vector<Fr> v;
+            for (auto m : kv.second) v.push_back(fr_small(m));
+            p.base_mss.push_back({kv.first, v});
+        }
         // proveTRRPM phase 1 (TypedReciprocal.hs:399-410)
         std::vector<Fr> ms_shared, ds, ms_inline;
         for (auto& kv : p.base_mss) ms_shared.insert(ms_shared.end(), kv.second.begin(), kv.second.end());
@@ -932,11 +991,11 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
     std::vector<uint8_t> n_coms(B * n * 64), c1(B * (s->binary ? 1 : 2) * 64);
     int rc;
     if (n) {
-        rc = bppp_fb_msm_batch(s->fb, B * n, in_sc.data(), n_coms.data());
-        if (rc) return fail(s, rc, std::string("input commitments: ") + ctx_err(s));
+        rc = bppp_fb_msm_batch(ln.fb, B * n, in_sc.data(), n_coms.data());
+        if (rc) return fail(s, rc, std::string("input commitments: ") + ctx_err(ln));
     }
-    rc = bppp_gens_msm_batch(s->gens, B * (s->binary ? 1 : 2), P0, sc1.data(), c1.data());
-    if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(s));
+    rc = bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1.data(), c1.data());
+    if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(ln));
     g_tm.lap("msm_phase1");
     std::vector<uint8_t> q_b(B * 32), sc_b(B * 32), w_b(B * N * 32, 0), l_b(B * M * 32, 0), c_b(B * M * 32, 0);
     std::vector<uint8_t> sc2(B * P0 * 32), c2(B * 64);
@@ -971,8 +1030,8 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
             p.bl.nrm = p.bls_nrm;
             commit_scalars(s, p.bl, &sc2[32 * b * P0]);
         });
-        rc = bppp_gens_msm_batch(s->gens, B, P0, sc2.data(), c2.data());
-        if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(s));
+        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
+        if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(ln));
         parallel_for(B, [&](size_t b) {
             Proof& p = P[b];
             uint8_t* out = coms + 64 * b * NC;
@@ -1019,8 +1078,8 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
             commit_scalars(s, p.r, &sc2[32 * b * P0]);
         });
         g_tm.lap("host_phase2");
-        rc = bppp_gens_msm_batch(s->gens, B, P0, sc2.data(), c2.data());
-        if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(s));
+        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
+        if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(ln));
         g_tm.lap("msm_phase2");
         // ---------------- phase 3 (TypedReciprocal.hs:421-434)
         parallel_for(B, [&](size_t b) {
@@ -1056,8 +1115,8 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
             commit_scalars(s, p.bl, &sc2[32 * b * P0]);
         });
         g_tm.lap("host_phase3");
-        rc = bppp_gens_msm_batch(s->gens, B, P0, sc2.data(), c2.data());
-        if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(s));
+        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
+        if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(ln));
         g_tm.lap("msm_phase3");
         // ---------------- phase 4 (TypedReciprocal.hs:435-444)
         parallel_for(B, [&](size_t b) {
@@ -1083,17 +1142,14 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
         });
     }
     g_tm.lap("host_phase4");
-    return run_argument(s, P, s->prover_rounds, q_b, sc_b, w_b, l_b, c_b, responses, finals, s->prover_fin_n, s->prover_fin_l);
+    return run_argument(s, ln, P, s->prover_rounds, q_b, sc_b, w_b, l_b, c_b, responses, finals, s->prover_fin_n, s->prover_fin_l);
 }
 
 // RangeProof.verifyM (src/RangeProof.hs:99-101) for `batch` proofs; `rounds`, n_norm, n_lin
 // describe the proofs as encoded (for binary proofs the prover's round rule may differ from
 // optimalWitnessSize, src/RangeProof/Binary.hs:195 vs :218; verifyBPM ignores `rounds`).
-int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
-                         const uint8_t* responses, const uint8_t* finals, int* ok) {
-    if (!s) return BPPP_ERR_ARG;
-    if (!coms || !finals || !ok || batch == 0 || (rounds && !responses)) return fail(s, BPPP_ERR_ARG, "null/empty argument");
-    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
+static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
+                       const uint8_t* responses, const uint8_t* finals, int* ok) {
     const size_t B = batch, n = s->n_inputs, N = s->nrm_len, M = s->lin_len, NC = s->num_rp_coms + n, k = rounds;
     std::vector<uint8_t> q_b(B * 32), sp_b(B * 32), pw_b(B * N * 32, 0), c_b(B * M * 32, 0), es_b(B * k * 32);
     std::vector<uint8_t> fw_b(B * n_norm * 32), fl_b(B * n_lin * 32), is_b(B * NC * 32), ip_b(B * NC * 64);
@@ -1164,11 +1220,84 @@ int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm,
         memcpy(&fl_b[32 * b * n_lin], finals + 32 * (b * (n_norm + n_lin) + n_norm), 32 * n_lin);
     });
     g_tm.lap("verify_host");
-    int rc = bppp_nl_verify_gens(s->gens, s->arg, B, k, q_b.data(), sp_b.data(), pw_b.data(), c_b.data(), es_b.data(), responses,
+    int rc = bppp_nl_verify_gens(ln.gens, s->arg, B, k, q_b.data(), sp_b.data(), pw_b.data(), c_b.data(), es_b.data(), responses,
                                  n_norm, n_lin, fw_b.data(), fl_b.data(), NC, is_b.data(), ip_b.data(), ok);
     g_tm.lap("nl_verify");
     g_tm.dump("verify");
-    if (rc) return fail(s, rc, std::string("bppp_nl_verify: ") + ctx_err(s));
+    if (rc) return fail(s, rc, std::string("bppp_nl_verify: ") + ctx_err(ln));
+    return BPPP_OK;
+}
+
+}  // extern "C"
+namespace {
+std::vector<Lane> make_lanes(bppp_rp* s, size_t batch) {
+    std::vector<Lane> L;
+    L.push_back({s->ctx, s->fb, s->gens, 0});
+    for (size_t i = 0; i < s->lane_ctx.size(); i++) L.push_back({s->lane_ctx[i], s->lane_fb[i], s->lane_gens[i], 0});
+    size_t want = std::max<size_t>(1, std::min(L.size(), batch / 32));      // tiny batches: one lane
+    L.resize(want);
+    int total = g_threads > 0 ? g_threads : (int)std::thread::hardware_concurrency();
+    if (total < 1) total = 4;
+    for (auto& l : L) l.threads = std::max(1, (int)((total + L.size() - 1) / L.size()));
+    return L;
+}
+template <class F>
+int run_lanes(bppp_rp* s, size_t batch, F fn) {
+    std::vector<Lane> L = make_lanes(s, batch);
+    if (L.size() == 1) return fn(L[0], (size_t)0, batch);
+    std::vector<int> rcs(L.size(), 0);
+    std::vector<std::thread> th;
+    size_t per = (batch + L.size() - 1) / L.size();
+    for (size_t i = 0; i < L.size(); i++) {
+        size_t b0 = std::min(batch, i * per), nb = std::min(per, batch - b0);
+        if (!nb) continue;
+        th.emplace_back([&, i, b0, nb]() {
+            t_lane_threads = L[i].threads;
+            t_is_lane0 = (i == 0);
+            bppp_set_thread_host_threads(L[i].threads);
+            rcs[i] = fn(L[i], b0, nb);
+        });
+    }
+    for (auto& t : th) t.join();
+    for (int rc : rcs)
+        if (rc) return rc;
+    return BPPP_OK;
+}
+}  // namespace
+extern "C" {
+
+int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
+                        const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals) {
+    if (!s) return BPPP_ERR_ARG;
+    if (!values || !random_seeds || !coms || !responses || !finals || batch == 0) return fail(s, BPPP_ERR_ARG, "null/empty argument");
+    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
+    const size_t n = s->n_inputs, NC = s->num_rp_coms + n, nf = s->prover_fin_n + s->prover_fin_l, k = s->prover_rounds;
+    return run_lanes(s, batch, [&](const Lane& ln, size_t b0, size_t nb) {
+        return prove_impl(s, ln, nb, values + 32 * b0 * n, types ? types + 32 * b0 * n : nullptr,
+                          blinds ? blinds + 32 * b0 * n : nullptr, random_seeds + b0, coms + 64 * b0 * NC,
+                          responses + 128 * b0 * k, finals + 32 * b0 * nf);
+    });
+}
+int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
+                         const uint8_t* responses, const uint8_t* finals, int* ok) {
+    if (!s) return BPPP_ERR_ARG;
+    if (!coms || !finals || !ok || batch == 0 || (rounds && !responses)) return fail(s, BPPP_ERR_ARG, "null/empty argument");
+    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
+    const size_t NC = s->num_rp_coms + s->n_inputs;
+    return run_lanes(s, batch, [&](const Lane& ln, size_t b0, size_t nb) {
+        return verify_impl(s, ln, nb, rounds, n_norm, n_lin, coms + 64 * b0 * NC, responses + 128 * b0 * rounds,
+                           finals + 32 * b0 * (n_norm + n_lin), ok + b0);
+    });
+}
+// the contexts of all lanes (lane 0 = the setup's own): for profile / launch-count aggregation
+int bppp_rp_contexts(bppp_rp* s, bppp_ctx** out, size_t cap, size_t* count) {
+    if (!s || !count) return BPPP_ERR_ARG;
+    *count = 1 + s->lane_ctx.size();
+    if (out) {
+        if (cap < *count) return BPPP_ERR_ARG;
+        out[0] = s->ctx;
+        for (size_t i = 0; i < s->lane_ctx.size(); i++) out[1 + i] = s->lane_ctx[i];
+    }
     return BPPP_OK;
 }
 

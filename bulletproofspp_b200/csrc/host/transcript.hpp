@@ -24,27 +24,39 @@ enum RootPolicy { ROOT_EXP = 0, ROOT_EVEN = 1, ROOT_SMALLER = 2 };
 
 // decimal rendering of a 256-bit little-endian integer (4 x u64)
 inline void append_decimal(std::string& out, const uint64_t v[4]) {
+    // peel 19 decimal digits at a time (2^64 > 10^19), then emit digits two at a time
+    static const char PAIRS[] =
+        "0001020304050607080910111213141516171819202122232425262728293031323334353637383940414243444546474849"
+        "5051525354555657585960616263646566676869707172737475767778798081828384858687888990919293949596979899";
     uint64_t t[4] = {v[0], v[1], v[2], v[3]};
     uint64_t chunks[5];
     int nc = 0;
     const uint64_t TEN19 = 10000000000000000000ULL;
-    while (t[0] | t[1] | t[2] | t[3]) {
+    int top = 3;
+    while (top >= 0 && t[top] == 0) top--;
+    while (top >= 0) {
         u128 rem = 0;
-        for (int i = 3; i >= 0; i--) {
+        for (int i = top; i >= 0; i--) {
             u128 cur = (rem << 64) | t[i];
             t[i] = (uint64_t)(cur / TEN19);
             rem = cur % TEN19;
         }
         chunks[nc++] = (uint64_t)rem;
+        while (top >= 0 && t[top] == 0) top--;
     }
     if (nc == 0) { out.push_back('0'); return; }
-    char buf[24];
-    int n = snprintf(buf, sizeof buf, "%llu", (unsigned long long)chunks[nc - 1]);
-    out.append(buf, n);
-    for (int i = nc - 2; i >= 0; i--) {
-        n = snprintf(buf, sizeof buf, "%019llu", (unsigned long long)chunks[i]);
-        out.append(buf, n);
+    char buf[100];
+    char* end = buf + sizeof buf;
+    char* p = end;
+    for (int c = 0; c < nc; c++) {
+        uint64_t x = chunks[c];
+        char* stop = p - 19;                       // full chunks are zero-padded to 19 digits
+        while (x >= 100) { unsigned r = (unsigned)(x % 100); x /= 100; p -= 2; p[0] = PAIRS[2 * r]; p[1] = PAIRS[2 * r + 1]; }
+        if (x >= 10) { p -= 2; p[0] = PAIRS[2 * x]; p[1] = PAIRS[2 * x + 1]; }
+        else { *--p = (char)('0' + x); }
+        if (c + 1 < nc) while (p > stop) *--p = '0';
     }
+    out.append(p, end - p);
 }
 inline void append_show_field(std::string& out, const uint64_t v[4], int fmt) {
     if (fmt == PREFIXED_P) out.append("P ");

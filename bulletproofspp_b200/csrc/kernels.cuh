@@ -269,12 +269,14 @@ struct MsmScalarsArgs {
     u256* xs; u256* rs; size_t sc_stride; int off;
     const u256* coef;           // [batch][8] Montgomery
     unsigned char kind[8];
+    int mont_out;               // 1: keep Montgomery form (tensor mode expands them further)
 };
-__device__ __forceinline__ u256 lin2(int k0, int k1, const u256& c0, const u256& c1, const u256& xL, const u256& xR) {
+__device__ __forceinline__ u256 lin2(int k0, int k1, const u256& c0, const u256& c1, const u256& xL, const u256& xR,
+                                     int mont_out) {
     u256 a = u256_zero();
     if (k0 == 1) a = xL; else if (k0 == 2) a = fr::mul(c0, xL);
     if (k1 == 1) a = fr::add(a, xR); else if (k1 == 2) a = fr::add(a, fr::mul(c1, xR));
-    return fr::from_mont(a);
+    return mont_out ? a : fr::from_mont(a);
 }
 __global__ void __launch_bounds__(256) k_msm_scalars(MsmScalarsArgs A) {
     const int p = blockIdx.y;
@@ -290,12 +292,48 @@ __global__ void __launch_bounds__(256) k_msm_scalars(MsmScalarsArgs A) {
     for (int k = 0; k < 8; k++) c[k] = (A.kind[k] == 2) ? ld_u256(A.coef + (size_t)p * 8 + k) : u256_zero();
     u256* xs = A.xs + (size_t)p * A.sc_stride + A.off;
     u256* rs = A.rs + (size_t)p * A.sc_stride + A.off;
-    st_u256(xs + 2 * i, lin2(A.kind[0], A.kind[1], c[0], c[1], xL, xR));
-    st_u256(rs + 2 * i, lin2(A.kind[4], A.kind[5], c[4], c[5], xL, xR));
+    st_u256(xs + 2 * i, lin2(A.kind[0], A.kind[1], c[0], c[1], xL, xR, A.mont_out));
+    st_u256(rs + 2 * i, lin2(A.kind[4], A.kind[5], c[4], c[5], xL, xR, A.mont_out));
     if (hasR) {
-        st_u256(xs + 2 * i + 1, lin2(A.kind[2], A.kind[3], c[2], c[3], xL, xR));
-        st_u256(rs + 2 * i + 1, lin2(A.kind[6], A.kind[7], c[6], c[7], xL, xR));
+        st_u256(xs + 2 * i + 1, lin2(A.kind[2], A.kind[3], c[2], c[3], xL, xR, A.mont_out));
+        st_u256(rs + 2 * i + 1, lin2(A.kind[6], A.kind[7], c[6], c[7], xL, xR, A.mont_out));
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Tensor mode (batches of small proofs): instead of folding the generators, keep for every
+// ORIGINAL generator its fold coefficient  coef_idx = prod_rounds (bit_r(idx) ? a_r : b_r)  so that
+// the folded generator is  G^(r)_i = sum_{idx >> r == i} coef_idx * G_idx  (collapsePoints b a gL gR
+// = b*gL + a*gR, src/Bulletproof.hs:213-214).  A round's commitments then are fixed-base MSMs over
+// the resident generator table with scalars  fold_scalar[idx >> r] * coef_idx.
+// ------------------------------------------------------------------------------------------
+struct ExpandArgs {
+    const u256* fx; const u256* fr_;    // folded X / R opening scalars (Montgomery), stride f_stride, offset f_off
+    size_t f_stride; int f_off;
+    const u256* coef; size_t coef_stride; int coef_off;
+    u256* xs; u256* rs; size_t sc_stride; int off;     // canonical outputs
+    int n; int shift;
+};
+__global__ void __launch_bounds__(256) k_expand_scalars(ExpandArgs A) {
+    const int p = blockIdx.y;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= A.n) return;
+    u256 c = ld_u256(A.coef + (size_t)p * A.coef_stride + A.coef_off + idx);
+    size_t f = (size_t)p * A.f_stride + A.f_off + (idx >> A.shift);
+    u256 x = ld_u256(A.fx + f), r = ld_u256(A.fr_ + f);
+    size_t o = (size_t)p * A.sc_stride + A.off + idx;
+    st_u256(A.xs + o, u256_is_zero(x) ? x : fr::from_mont(fr::mul(x, c)));
+    st_u256(A.rs + o, u256_is_zero(r) ? r : fr::from_mont(fr::mul(r, c)));
+}
+// coef[p][off+idx] *= bit_shift(idx) ? a[p*ab_stride] : b[p*ab_stride];  first = 1 initialises from 1
+__global__ void __launch_bounds__(256) k_coef_update(u256* coef, size_t coef_stride, int off, int n, int shift,
+                                                     const u256* a, const u256* b, size_t ab_stride, int first) {
+    const int p = blockIdx.y;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    u256 m = ld_u256((((idx >> shift) & 1) ? a : b) + (size_t)p * ab_stride);
+    u256* c = coef + (size_t)p * coef_stride + off + idx;
+    st_u256(c, first ? m : fr::mul(ld_u256(c), m));
 }
 
 // ------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ EXPORTS = [
     "bppp_profile_enable", "bppp_profile_reset", "bppp_profile_report", "bppp_timer_start", "bppp_timer_stop",
     "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
+    "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts",
 ]
 
 
@@ -80,6 +81,8 @@ def load_library():
     lib.bppp_nl_create_gens.argtypes = [vp, ip, sz, u8p, u8p, u8p, u8p, u8p, C.POINTER(vp)]
     lib.bppp_nl_verify_gens.argtypes = [vp, ip, sz, sz, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz, u8p, u8p, sz, u8p, u8p,
                                         C.POINTER(ip)]
+    lib.bppp_rp_contexts.argtypes = [vp, C.POINTER(vp), sz, C.POINTER(sz)]
+    lib.bppp_ctx_device.argtypes = [vp]
     lib.bppp_fb_create.argtypes = [vp, sz, u8p, C.POINTER(vp)]
     lib.bppp_fb_msm_batch.argtypes = [vp, sz, u8p, u8p]
     lib.bppp_fb_destroy.argtypes = [vp]
@@ -171,10 +174,17 @@ class Context:
         self.h = h
         self.device = device
 
+    @classmethod
+    def borrowed(cls, handle, device=0):
+        """wrap a context owned by someone else (a lane of a RangeProofSetup)"""
+        self = cls.__new__(cls)
+        self.lib, self.h, self.device, self._borrowed = load_library(), handle, device, True
+        return self
+
     def close(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and not getattr(self, "_borrowed", False):
             self.lib.bppp_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -422,6 +432,14 @@ class RangeProofSetup:
     def _ck(self, rc, what):
         if rc:
             raise BpppError("%s failed (%d): %s" % (what, rc, self.ctx.lib.bppp_rp_last_error(self.h).decode()))
+
+    def contexts(self):
+        """the contexts of all concurrent lanes (lane 0 first)"""
+        n = C.c_size_t()
+        self.ctx.lib.bppp_rp_contexts(self.h, None, 0, C.byref(n))
+        arr = (C.c_void_p * n.value)()
+        self._ck(self.ctx.lib.bppp_rp_contexts(self.h, arr, n.value, C.byref(n)), "bppp_rp_contexts")
+        return [self.ctx] + [Context.borrowed(C.c_void_p(arr[i]), self.ctx.device) for i in range(1, n.value)]
 
     def points(self, count):
         out = _buf(64 * count)

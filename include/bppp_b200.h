@@ -71,6 +71,8 @@ void bppp_gens_destroy(bppp_gens* g);
 int bppp_gens_msm_batch(bppp_gens* g, size_t batch, size_t n, const uint8_t* scalars, uint8_t* out);
 /* host threads used by the round sequencing inside the device entry points (0 = all cores) */
 void bppp_set_device_host_threads(int n);
+void bppp_set_thread_host_threads(int n);   /* same, for the calling thread only */
+int bppp_ctx_device(bppp_ctx* ctx);
 
 /* ---- fixed-base MSMs over a handful of generators shared by every call: the range proofs'
  * input commitments value*g + type*hs0 + blind*hs1 (scalarRPW' / scalarPairRPW' + commitRPW,
@@ -170,6 +172,8 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
 /* RangeProof.verifyM for `batch` proofs */
 int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
                          const uint8_t* responses, const uint8_t* finals, int* ok);
+/* contexts of the concurrent lanes a setup runs its sub-batches on (BPPP_LANES, default 4) */
+int bppp_rp_contexts(bppp_rp* s, bppp_ctx** out, size_t cap, size_t* count);
 /* host-only self-test hooks (no device needed) */
 int bppp_host_sha256(const uint8_t* data, size_t n, uint8_t out[32]);
 int bppp_host_oracle(const uint8_t* pts, size_t npts, int count, int show_format, uint8_t* out);
