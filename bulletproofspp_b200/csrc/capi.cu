@@ -134,6 +134,7 @@ template <class F>
 static void host_parallel_for(size_t n, F fn) {
     int nt = t_capi_threads > 0 ? t_capi_threads : (g_capi_threads > 0 ? g_capi_threads : (int)std::thread::hardware_concurrency());
     if (nt < 1) nt = 1;
+    if (nt > 4) nt = 4;                      // short loops: a few threads suffice, lanes run concurrently
     if ((size_t)nt > n / 16) nt = (int)(n / 16);
     if (nt <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);

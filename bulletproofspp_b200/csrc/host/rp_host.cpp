@@ -69,8 +69,12 @@ int n_threads() {
     unsigned h = std::thread::hardware_concurrency();
     return h ? (int)h : 4;
 }
+// Host phases of concurrent lanes take turns on the cores (each with every core) so that one
+// lane's host phase overlaps the other lanes' device work instead of all lanes moving in lock-step.
+std::mutex g_cpu_turn;
 template <class F>
 void parallel_for(size_t n, F fn) {
+    std::lock_guard<std::mutex> turn(g_cpu_turn);
     int nt = (int)std::min<size_t>(n, (size_t)n_threads());
     if (nt <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);
@@ -804,9 +808,9 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
     if (rc) { delete s; return rc; }
     rc = bppp_gens_create(ctx, s->nrm_len, s->lin_len, &s->table[0], &s->table[64], &s->table[64 * (1 + s->nrm_len)], &s->gens);
     if (rc) { bppp_fb_destroy(s->fb); delete s; return rc; }
-    {   // extra lanes (BPPP_LANES, default 4 in total)
+    {   // extra lanes (BPPP_LANES, default 8 in total)
         const char* ev = getenv("BPPP_LANES");
-        int lanes = ev ? atoi(ev) : 4;
+        int lanes = ev ? atoi(ev) : 8;
         int dev = bppp_ctx_device(ctx);
         for (int i = 1; i < lanes; i++) {
             bppp_ctx* c2 = nullptr;
@@ -1238,7 +1242,10 @@ std::vector<Lane> make_lanes(bppp_rp* s, size_t batch) {
     L.resize(want);
     int total = g_threads > 0 ? g_threads : (int)std::thread::hardware_concurrency();
     if (total < 1) total = 4;
-    for (auto& l : L) l.threads = std::max(1, (int)((total + L.size() - 1) / L.size()));
+    // host phases take turns (g_cpu_turn), each using every core
+    const char* ev = getenv("BPPP_LANE_THREADS");
+    int per = ev ? atoi(ev) : total;
+    for (auto& l : L) l.threads = std::max(1, per);
     return L;
 }
 template <class F>

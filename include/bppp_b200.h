@@ -172,7 +172,7 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
 /* RangeProof.verifyM for `batch` proofs */
 int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
                          const uint8_t* responses, const uint8_t* finals, int* ok);
-/* contexts of the concurrent lanes a setup runs its sub-batches on (BPPP_LANES, default 4) */
+/* contexts of the concurrent lanes a setup runs its sub-batches on (BPPP_LANES, default 8) */
 int bppp_rp_contexts(bppp_rp* s, bppp_ctx** out, size_t cap, size_t* count);
 /* host-only self-test hooks (no device needed) */
 int bppp_host_sha256(const uint8_t* data, size_t n, uint8_t out[32]);

@@ -1,0 +1,178 @@
+"""CPU tests of the oracle (oracle/): what CAN be pinned is pinned here -- SHA-256 digests -> field
+elements, the secp256k1 group law against OpenSSL (`cryptography`), the CM constants of
+FastSECP256K1.hs, the proof shapes of README.md / the paper / SURVEY section 8, the reference's
+`innerProduct` / `projectivePairIP` loops against a complete group law, prove->verify
+self-consistency and the per-round invariant on every shipped example, and the committed golden
+vectors.  (PARITY UNPINNED for concrete transcript bytes: see oracle/__init__.py.)"""
+import hashlib
+import json
+import os
+import random
+
+import pytest
+
+from example_configs import EXAMPLES, batched
+from oracle import bulletproof as obp
+from oracle.curve import Secp256k1 as G, SecpRef, Toy, straus_reference
+from oracle.field import BETA, LAMBDA, Q, R, GX, GY, batch_inverse, rational_reduce_scalar
+from oracle.rangeproof import load_schema, load_witness, prove, verify, run_example
+from oracle.transcript import ZKPT, digest_to_int, get_points, hash_to, input_blinds, show_field
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_sha256_fips_vectors_and_digest_decoding():
+    assert hashlib.sha256(b"abc").hexdigest() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    d = bytes(range(32))
+    # four big-endian Word64, first word least significant (src/Encoding.hs:75-79)
+    assert digest_to_int(d) == sum(int.from_bytes(d[8 * i:8 * i + 8], "big") << (64 * i) for i in range(4))
+    assert hash_to(b"abc", R) == digest_to_int(hashlib.sha256(b"abc").digest()) % R
+    assert show_field(123) == b"P 123" and show_field(123, "BareDecimal") == b"123"
+
+
+def test_cm_constants():
+    # FastSECP256K1.hs:39,53
+    assert pow(BETA, 3, Q) == 1 and BETA != 1
+    assert pow(LAMBDA, 3, R) == 1 and LAMBDA != 1
+    lg = G.mul(LAMBDA, G.gen)
+    assert lg == (BETA * GX % Q, GY)
+
+
+def test_group_law_against_openssl():
+    from cryptography.hazmat.primitives.asymmetric import ec
+    rnd = random.Random(7)
+    for _ in range(5):
+        k = rnd.randrange(1, R)
+        pub = ec.derive_private_key(k, ec.SECP256K1()).public_key().public_numbers()
+        assert G.mul(k, G.gen) == (pub.x, pub.y)
+    a, b = rnd.randrange(R), rnd.randrange(R)
+    assert G.add(G.mul(a, G.gen), G.mul(b, G.gen)) == G.mul((a + b) % R, G.gen)
+    assert G.msm([(a, G.gen), (R - a, G.gen)]) is None
+
+
+def test_reference_straus_matches_complete_group_law():
+    pts = get_points(G, "test points", 12)
+    rnd = random.Random(3)
+    pairs = [(rnd.randrange(R), p) for p in pts] + [(0, pts[0]), (5, None)]
+    assert straus_reference(pairs) == G.msm(pairs)
+    assert SecpRef.msm(pairs) == G.msm(pairs)
+    a, b = rational_reduce_scalar(rnd.randrange(R))
+    prs = [(pts[i], pts[i + 1]) for i in range(0, 10, 2)] + [(pts[10], None)]
+    assert SecpRef.pair_ip_many(b, a, prs) == G.pair_ip_many(b, a, prs)
+
+
+def test_generators_are_on_curve_and_deterministic():
+    pts = get_points(G, "test points", 20)
+    assert all(G.on_curve(p) for p in pts) and len(set(pts)) == 20
+    assert pts == get_points(G, "test points", 20)
+    assert get_points(G, "test points", 4, "even")[0][1] % 2 == 0
+
+
+def test_rational_reduce_scalar_properties():
+    rnd = random.Random(11)
+    for x in [1, 2, R - 1, 2 ** 200] + [rnd.randrange(R) for _ in range(200)]:
+        a, b = rational_reduce_scalar(x)
+        assert (a - b * x) % R == 0 and a * a <= 2 * R and b != 0
+    assert rational_reduce_scalar(0) == (0, 1)
+
+
+def test_batch_inverse_maps_zero_to_zero():
+    xs = [3, 0, 7, R - 1, 0]
+    inv = batch_inverse(xs)
+    assert inv[1] == 0 and inv[4] == 0 and all(x * y % R == 1 for x, y in zip(xs, inv) if x)
+
+
+# SURVEY section 8 shape table: (argument, N, M, rounds, commitments, final scalars)
+SHAPES = {"64bit": ("IP", 16, 6, 3, 10, 3), "32bit": ("IP", 11, 6, 3, 10, 3), "rec_test": ("IP", 62, 24, 5, 14, 3),
+          "bin_test": ("NL", 192, 2, 6, 14, 4), "32by64": ("NL", 384, 70, 7, 18, 4), "64by64": ("NL", 512, 261, 8, 20, 4),
+          "96by64": ("NL", 768, 261, 8, 20, 5), "128by64": ("NL", 1024, 261, 9, 22, 3), "bin64": ("NL", 64, 2, 5, 12, 3)}
+
+
+@pytest.mark.parametrize("name", sorted(SHAPES))
+def test_example_proves_verifies_and_has_the_published_shape(name):
+    """toy group (the reference's WrapV): protocol algebra without EC cost"""
+    setup, proof, ok = run_example(*EXAMPLES[name], Toy)
+    arg, N, M, k, pts, sc = SHAPES[name]
+    assert ok
+    assert (setup.arg, setup.nrm_len, setup.lin_len, len(proof["responses"])) == (arg, N, M, k)
+    assert setup.num_rp_coms + 2 * k == pts
+    assert len(proof["opening"].vec.get_witness()) == sc
+    if name == "64bit":                                  # README.md:169-172 / paper: 10 points + 3 scalars = 416 B
+        assert 32 * (pts + sc) == 416
+
+
+@pytest.mark.parametrize("kind", ["NL", "IP"])
+@pytest.mark.parametrize("N,M,k", [(16, 6, 3), (11, 6, 3), (37, 5, 4), (8, 8, 2)])
+def test_round_invariant_and_tamper_rejection(kind, N, M, k):
+    """C' = C + e0*X + e1*R and s' = evalScalar(w') every round, over the toy group"""
+    rnd = random.Random(N * 100 + M)
+    gens = [rnd.randrange(1, R) for _ in range(1 + N + M)]
+    g, Gs, Hs = gens[0], gens[1:1 + N], gens[1 + N:]
+    q = rnd.randrange(1, R)
+    w, l, c = ([rnd.randrange(R) for _ in range(n)] for n in (N, M, M))
+    nl = obp.NormLinear.make(kind, Toy, q, c, w, Gs, l, Hs)
+    com = obp.PSV(nl.eval_scalar(), g, nl)
+    commit = lambda cm: Toy.msm([(cm.s, cm.g)] + cm.vec.opening())
+    zk = ZKPT(Toy)
+    resp = []
+    C0 = commit(com)
+    for _ in range(k):
+        before = commit(com)
+        tr = []
+        com, xr = obp.prove_round(Toy, zk, com, tr)
+        e0, e1 = com.vec.make_es(tr[0]["e"])
+        assert commit(com) == (before + e0 * xr[0] + e1 * xr[1]) % R
+        assert com.s == com.vec.eval_scalar()
+        resp.insert(0, xr)
+    fin = com.vec.get_witness()
+    n_n = len(com.vec.norm.get_witness())
+    opening = obp.PSV(0, 0, obp.NormLinear.make(kind, Toy, 1, [], fin[:n_n], [], fin[n_n:], []))
+    pub = obp.PSV(0, g, obp.NormLinear.make(kind, Toy, q, c, [0] * N, Gs, [], Hs))
+    basis = obp.PSV(0, g, obp.NormLinear.make(kind, Toy, q, c, [], Gs, [], Hs))
+    # verifier equation: (0 - sc) g - tensor.G - tensor.H + C0 + sum(e0 X + e1 R) == 0  (initCom = the commitment itself, pub = 0)
+    ok, _ = obp.verify_bpm(Toy, ZKPT(Toy), [(1, C0)], resp, pub, basis, opening)
+    assert ok
+    bad = obp.PSV(0, 0, obp.NormLinear.make(kind, Toy, 1, [], [(fin[0] + 1) % R] + fin[1:n_n], [], fin[n_n:], []))
+    assert not obp.verify_bpm(Toy, ZKPT(Toy), [(1, C0)], resp, pub, basis, bad)[0]
+
+
+def _golden(name):
+    with open(os.path.join(GOLD, name.replace("#", "_b") + ".json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["64bit", "32bit", "rec_test", "bin_test", "bin64", "typed_nl", "32by64", "128by64"])
+def test_oracle_reproduces_golden_vectors(name):
+    """secp256k1 with the reference's own MSM / pair-fold loops (oracle/c): same bytes as the
+    committed vectors, and the oracle's verifier accepts them"""
+    pytest.importorskip("ctypes")
+    try:
+        SecpRef.lib()
+    except RuntimeError:
+        pytest.skip("oracle C library not built (make -C oracle)")
+    g = _golden(name)
+    setup = load_schema(EXAMPLES[name][0], SecpRef)
+    proof = prove(setup, ZKPT(SecpRef, setup.random_seed), load_witness(setup, EXAMPLES[name][1]))
+    hx = lambda v: "%064x" % v
+    assert [[hx(p[0]), hx(p[1])] for p in proof["coms"]] == g["coms"]
+    assert [[[hx(x[0]), hx(x[1])], [hx(r[0]), hx(r[1])]] for x, r in proof["responses"]] == g["responses"]
+    assert [hx(v) for v in proof["opening"].vec.get_witness()] == g["finals"]
+    assert verify(setup, ZKPT(SecpRef, None), proof)
+
+
+def test_batched_seeds_change_the_transcript():
+    schema, wits, seeds = batched("bin64", 1)
+    s0 = load_schema(dict(schema, randomSeed=seeds[0]), Toy)
+    s1 = load_schema(dict(schema, randomSeed="another"), Toy)
+    p0 = prove(s0, ZKPT(Toy, s0.random_seed), load_witness(s0, wits[0]))
+    p1 = prove(s1, ZKPT(Toy, s1.random_seed), load_witness(s1, wits[0]))
+    assert p0["coms"] != p1["coms"] and input_blinds("a", 2) != input_blinds("b", 2)
+
+
+def test_invalid_witnesses_raise():
+    setup = load_schema(EXAMPLES["bin_test"][0], Toy)
+    with pytest.raises(ValueError):
+        load_witness(setup, [{"amount": 125}, {"amount": 1}, {"amount": 121}])     # unbalanced (Binary.hs:165-167)
+    setup = load_schema(EXAMPLES["64bit"][0], Toy)
+    with pytest.raises(ValueError):
+        load_witness(setup, [{"amount": 2 ** 64}])                                 # out of range
