@@ -231,6 +231,7 @@ int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res, d
     if (!g_attr_set) {
         CK(cudaFuncSetAttribute(k_msm_bucket, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)msm_smem_bytes(MSM_MAX_CHUNK)));
+        CK(cudaFuncSetAttribute(k_msm_bucket, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         g_attr_set = true;
     }
     MsmArgs A;
@@ -553,6 +554,7 @@ int launch_pair_fold(bppp_ctx* ctx, const Affine* in, size_t in_stride, Jac* out
     const size_t smem = 4 * 16 * PF_THREADS * sizeof(uint32_t);
     if (!attr) {
         CK(cudaFuncSetAttribute(k_pair_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_pair_fold, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     PairFoldArgs A;
@@ -646,6 +648,7 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
     static bool attr = false;
     if (!attr) {
         CK(cudaFuncSetAttribute(k_msm_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bytes(GT_MAX_CHUNK)));
+        CK(cudaFuncSetAttribute(k_msm_gens, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
     int nch = (int)((n_terms + GT_MAX_CHUNK - 1) / GT_MAX_CHUNK);

@@ -378,7 +378,7 @@ __device__ __forceinline__ Affine tbl_load(const uint32_t* tbl, int e) {
     return p;
 }
 
-__global__ void __launch_bounds__(PF_THREADS) k_pair_fold(PairFoldArgs A) {
+__global__ void __launch_bounds__(PF_THREADS, 4) k_pair_fold(PairFoldArgs A) {
     extern __shared__ uint32_t pf_smem[];
     uint32_t* tbl = pf_smem;                                   // 4 * 16 * PF_THREADS words
     __shared__ unsigned char dig[PF_MAXDIG];
@@ -702,7 +702,7 @@ struct GtArgs {
 };
 __device__ __forceinline__ int gt_digit(const u256& s, int j, int& carry) { return signed_digit(s, j, GT_C, carry); }
 
-__global__ void __launch_bounds__(GT_THREADS) k_msm_gens(GtArgs A) {
+__global__ void __launch_bounds__(GT_THREADS, 2) k_msm_gens(GtArgs A) {
     extern __shared__ unsigned char gt_smem[];
     const int chunk = blockIdx.x, o = blockIdx.y, p = blockIdx.z;
     const int base = chunk * GT_MAX_CHUNK;
