@@ -22,11 +22,11 @@ using namespace bppp;
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
-                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update"};
+                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -764,13 +764,19 @@ struct bppp_nl {
     // tensor mode: no generator folding; per-generator fold coefficients + folded opening scalars
     bool tensor = false;
     DBuf<u256> coef, fsc;           // coef [B][N+M] (Montgomery); fsc [2][B][P0] (Montgomery)
+    // IP argument (kind = BPPP_ARG_IP): w[] holds a (on G' = g1 + r g0), bv[] holds b (on H' = g1 - r g0);
+    // Np = ceil(N/2) pairs; coef = [coefG (Np) | coefH (Np) | coefK (M)] per proof;
+    // fsc = [fgl | fgr | fhl | fhr (Np each) | fkl | fkr (M each)] per proof
+    size_t Np = 0;
+    DBuf<u256> bv[2];
+    std::vector<Fr> rr, ny;         // basis-change scalar r (q = r^4) and the second normalisation
     // host state (Montgomery, 4 x 64-bit limbs; bit-compatible with the device's u256)
     std::vector<Fr> q, qinv, nn, nl, s, sX, sR;
 };
 
 namespace {
 enum { C_RHO = 0, C_K1, C_K2, C_AU, C_BU, C_AL, C_BL, C_AC, C_BC, C_COEF /* 8 */, C_KB = C_COEF + 8 /* 2 */,
-       C_KA = C_KB + 2 /* 2 */, C_A0N = C_KA + 2, C_B0N, C_A0L, C_B0L, C_COUNT };
+       C_KA = C_KB + 2 /* 2 */, C_A0N = C_KA + 2, C_B0N, C_A0L, C_B0L, C_AV, C_BV, C_A0H, C_B0H, C_RR, C_NX, C_NY, C_COUNT };
 inline u256* cptr(bppp_nl* h, int which) { return h->consts.p + (size_t)which * h->B; }
 static_assert(sizeof(Fr) == sizeof(u256), "host and device field elements share one layout");
 
@@ -794,20 +800,25 @@ Fr fr_from_mag(const u256& mag, bool neg) {
 
 // launch k_fold_dots for norm and linear vectors.  fold = 0: dots of current vectors; fold = 1:
 // fold current vectors into the other buffer and compute the dots of the result.
+// NL: norm u = v = w (wL*wR, wR^2), linear u = c, v = l (cL*lR + cR*lL, cR*lR).
+// IP: norm u = a, v = b (aL*bR, aR*bL), linear (cR*lL, cL*lR)   (InnerProductArgument.hs:70-81,149-152)
 int launch_fold_dots(bppp_nl* h, int fold) {
     bppp_ctx* ctx = h->ctx;
+    const bool ip = h->kind == BPPP_ARG_IP;
     int src = h->cur, dst = h->cur ^ 1;
     if (h->curN) {
         size_t ny = fold ? (h->curN + 1) / 2 : h->curN;
         h->blocks_n = dots_blocks((ny + 1) / 2);
         CK(h->part_n.ensure(h->B * h->blocks_n * 2));
         FoldDotsArgs A;
-        A.u = A.v = h->w[src].p; A.uo = A.vo = h->w[dst].p;
+        A.u = h->w[src].p; A.uo = h->w[dst].p;
+        A.v = ip ? h->bv[src].p : h->w[src].p; A.vo = ip ? h->bv[dst].p : h->w[dst].p;
         A.in_stride = h->wstride[src]; A.out_stride = h->wstride[dst];
         A.n_in = (int)h->curN; A.fold = fold;
-        A.au = A.av = cptr(h, C_AU); A.bu = A.bv = cptr(h, C_BU);
-        A.rho = cptr(h, C_RHO); A.m1 = 1; A.m2 = 4; A.partial = h->part_n.p;
-        g_work = 32.0 * (double)h->B * (fold ? (double)(h->curN + ny) : (double)h->curN);
+        A.au = cptr(h, C_AU); A.bu = cptr(h, C_BU);
+        A.av = ip ? cptr(h, C_AV) : cptr(h, C_AU); A.bv = ip ? cptr(h, C_BV) : cptr(h, C_BU);
+        A.rho = cptr(h, C_RHO); A.m1 = 1; A.m2 = ip ? 2 : 4; A.partial = h->part_n.p;
+        g_work = (ip ? 2 : 1) * 32.0 * (double)h->B * (fold ? (double)(h->curN + ny) : (double)h->curN);
         { ProfScope ps_(ctx, K_FOLD_DOTS, g_work);
         k_fold_dots<<<dim3(h->blocks_n, (unsigned)h->B), 256, 0, ctx->st>>>(A);
         }
@@ -822,7 +833,7 @@ int launch_fold_dots(bppp_nl* h, int fold) {
         A.in_stride = h->lstride[src]; A.out_stride = h->lstride[dst];
         A.n_in = (int)h->curM; A.fold = fold;
         A.au = cptr(h, C_AC); A.bu = cptr(h, C_BC); A.av = cptr(h, C_AL); A.bv = cptr(h, C_BL);
-        A.rho = nullptr; A.m1 = 3; A.m2 = 4; A.partial = h->part_l.p;
+        A.rho = nullptr; A.m1 = ip ? 2 : 3; A.m2 = ip ? 1 : 4; A.partial = h->part_l.p;
         g_work = 2 * 32.0 * (double)h->B * (fold ? (double)(h->curM + ny) : (double)h->curM);
         { ProfScope ps_(ctx, K_FOLD_DOTS, g_work);
         k_fold_dots<<<dim3(h->blocks_l, (unsigned)h->B), 256, 0, ctx->st>>>(A);
@@ -836,6 +847,267 @@ int upload_consts(bppp_nl* h, int which, const std::vector<Fr>& v) {
     CK(H2D(cptr(h, which), v.data(), v.size() * 32));
     return BPPP_OK;
 }
+}  // namespace
+// =============================================================================== IP argument
+// IP.NormLinear (src/Bulletproof/InnerProductArgument.hs) on the device, tensor style.
+namespace {
+inline u256* ip_coef(bppp_nl* h) { return h->coef.p; }
+inline size_t ip_coef_stride(bppp_nl* h) { return 2 * h->Np + h->M; }
+inline u256* ip_f(bppp_nl* h, int which) {          // 0 fgl, 1 fgr, 2 fhl, 3 fhr : [B][Np];  4 fkl, 5 fkr : [B][M]
+    return which < 4 ? h->fsc.p + (size_t)which * h->B * h->Np : h->fsc.p + 4 * h->B * h->Np + (size_t)(which - 4) * h->B * h->M;
+}
+
+int ip_create(bppp_nl* h, const uint8_t* q, const uint8_t* s, const uint8_t* w, const uint8_t* l, const uint8_t* c) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, N = h->N, M = h->M, Np = (N + 1) / 2;
+    h->Np = Np;
+    h->tensor = true;
+    const size_t Np2 = (Np + 1) / 2;
+    CK(h->aff.alloc(B * 2));
+    CK(h->w[0].alloc(B * Np)); CK(h->w[1].alloc(B * Np2));
+    CK(h->bv[0].alloc(B * Np)); CK(h->bv[1].alloc(B * Np2));
+    CK(h->l[0].alloc(B * M)); CK(h->l[1].alloc(B * h->M2));
+    CK(h->c[0].alloc(B * M)); CK(h->c[1].alloc(B * h->M2));
+    h->wstride[0] = Np; h->wstride[1] = Np2; h->lstride[0] = M; h->lstride[1] = h->M2;
+    CK(h->sc.alloc(2 * B * h->P0));
+    CK(h->dots.alloc(B * 2));
+    CK(h->consts.alloc((size_t)C_COUNT * B));
+    CK(h->res.alloc(B * 2));
+    CK(h->coef.alloc(B * (2 * Np + M)));
+    CK(h->fsc.alloc(B * (4 * Np + 2 * M)));
+    // host state: the setup's `q` is the r with q = r^4 (makeNorm, :194-197)
+    h->rr.resize(B); h->q.resize(B); h->qinv.resize(B); h->nn.assign(B, h64::one()); h->ny.assign(B, h64::one());
+    h->nl.assign(B, h64::one()); h->s.resize(B); h->sX.resize(B); h->sR.resize(B);
+    std::vector<Fr> r2inv(B), half(B);
+    const Fr two = h64::from_u64(2);
+    for (size_t b = 0; b < B; b++) {
+        h->rr[b] = h64::from_bytes(q + 32 * b);
+        Fr r2 = h64::sqr(h->rr[b]);
+        h->q[b] = h64::sqr(r2);
+        h->qinv[b] = h->q[b];
+        h->s[b] = h64::from_bytes(s + 32 * b);
+        r2inv[b] = h64::mul(two, h->rr[b]);
+        half[b] = two;
+    }
+    h64::batch_inv(h->qinv.data(), B);
+    h64::batch_inv(r2inv.data(), B);
+    h64::batch_inv(half.data(), B);
+    CK(H2D(cptr(h, C_AU), r2inv.data(), B * 32));
+    CK(H2D(cptr(h, C_BU), half.data(), B * 32));
+    CK(H2D(cptr(h, C_RR), h->rr.data(), B * 32));
+    // witness -> Montgomery, then the basis change of the norm part
+    DBuf<u256> wm;
+    CK(wm.alloc(B * N));
+    struct { const uint8_t* src; u256* dst; size_t n; } up[3] = {{w, wm.p, B * N}, {l, h->l[0].p, B * M}, {c, h->c[0].p, B * M}};
+    for (auto& u : up) {
+        if (!u.n) continue;
+        CK(H2D(h->sc.p, u.src, u.n * 32));
+        { ProfScope ps_(ctx, K_FR_CONVERT, 0);
+        k_fr_convert<<<(unsigned)((u.n + 255) / 256), 256, 0, ctx->st>>>(h->sc.p, u.dst, u.n, 1);
+        }
+        CK(cudaGetLastError());
+    }
+    if (N) {
+        { ProfScope ps_(ctx, K_IP_MISC, 0);
+        k_ip_make_norm<<<dim3((unsigned)((Np + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(
+            wm.p, N, (int)N, h->w[0].p, h->bv[0].p, Np, cptr(h, C_AU), cptr(h, C_BU));
+        }
+        CK(cudaGetLastError());
+    }
+    {
+        size_t nc = B * (2 * Np + M);
+        ProfScope ps_(ctx, K_IP_MISC, 0);
+        k_fill_one<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->st>>>(h->coef.p, nc);
+        CK(cudaGetLastError());
+    }
+    CK(cudaMemsetAsync(h->sc.p, 0, 2 * B * h->P0 * 32, ctx->st));
+    h->curN = Np;
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+
+int ip_round_commit(bppp_nl* h, uint8_t* Lout, uint8_t* Rout) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, P0 = h->P0, Np = h->Np, M = h->M;
+    // sL = s q nx ny sum (q^2)^t aL bR ; sR = s q^2 nx ny sum (q^2)^t aR bL   (:70-81), s = 4 (:195)
+    std::vector<Fr> rho(B), k1(B), k2(B), coef(B * 8, h64::zero());
+    const Fr four = h64::from_u64(4);
+    host_parallel_for(B, [&](size_t b) {
+        Fr q2 = h64::sqr(h->q[b]);
+        Fr k = h64::mul(four, h64::mul(h->nn[b], h->ny[b]));
+        rho[b] = q2;
+        k1[b] = h64::mul(k, h->q[b]);
+        k2[b] = h64::mul(k, q2);
+        coef[b * 8 + 2] = h->qinv[b];       // L on gR <- q^-1 * aL
+        coef[b * 8 + 5] = h->q[b];          // R on gL <- q * aR
+    });
+    int rc;
+    if (!h->have_partials) {
+        if ((rc = upload_consts(h, C_RHO, rho))) return rc;
+        if ((rc = launch_fold_dots(h, 0))) return rc;
+        h->have_partials = true;
+    }
+    if ((rc = upload_consts(h, C_K1, k1)) || (rc = upload_consts(h, C_K2, k2))) return rc;
+    CK(H2D(cptr(h, C_COEF), coef.data(), B * 8 * 32));
+    u256* ls = h->sc.p;
+    u256* rs = h->sc.p + B * P0;
+    {
+        DotsFinishArgs A;
+        memset(&A, 0, sizeof A);
+        if (h->curN) { A.partial[A.n_seg] = h->part_n.p; A.n_blocks[A.n_seg] = h->blocks_n; A.k1[A.n_seg] = cptr(h, C_K1); A.k2[A.n_seg] = cptr(h, C_K2); A.n_seg++; }
+        if (h->curM) { A.partial[A.n_seg] = h->part_l.p; A.n_blocks[A.n_seg] = h->blocks_l; A.n_seg++; }
+        A.res = h->dots.p; A.xs = ls; A.rs = rs; A.sc_stride = P0; A.batch = (int)B;
+        { ProfScope ps_(ctx, K_DOTS_FINISH, 0);
+        k_dots_finish<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+    }
+    const int src = h->cur;
+    struct { const u256* x; size_t stride; size_t n; u256* o0; u256* o1; size_t ostride; unsigned char kd[8]; } jobs[3] = {
+        // a on G':  L: gR <- qInv*aL ; R: gL <- q*aR          (:78-80)
+        {h->w[src].p, h->wstride[src], h->curN, ip_f(h, 0), ip_f(h, 1), Np, {0, 0, 2, 0, 0, 2, 0, 0}},
+        // b on H':  L: hL <- bR ; R: hR <- bL
+        {h->bv[src].p, h->wstride[src], h->curN, ip_f(h, 2), ip_f(h, 3), Np, {0, 1, 0, 0, 0, 0, 1, 0}},
+        // l on K:   L: kR <- lL ; R: kL <- lR                  (:149-152)
+        {h->l[src].p, h->lstride[src], h->curM, ip_f(h, 4), ip_f(h, 5), M, {0, 0, 1, 0, 0, 1, 0, 0}}};
+    for (auto& j : jobs) {
+        if (!j.n) continue;
+        MsmScalarsArgs A;
+        A.x = j.x; A.in_stride = j.stride; A.n_in = (int)j.n;
+        A.xs = j.o0; A.rs = j.o1; A.mont_out = 1; A.sc_stride = j.ostride; A.off = 0; A.coef = cptr(h, C_COEF);
+        memcpy(A.kind, j.kd, 8);
+        { ProfScope ps_(ctx, K_MSM_SCALARS, 0);
+        k_msm_scalars<<<dim3((unsigned)(((j.n + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+    }
+    if (h->N) {
+        IpExpandArgs A;
+        A.fgl = ip_f(h, 0); A.fgr = ip_f(h, 1); A.fhl = ip_f(h, 2); A.fhr = ip_f(h, 3); A.f_stride = Np;
+        A.cg = ip_coef(h); A.ch = ip_coef(h) + Np; A.c_stride = ip_coef_stride(h);
+        A.r = cptr(h, C_RR); A.ls = ls; A.rs = rs; A.sc_stride = P0; A.off = 1; A.n = (int)h->N; A.shift = h->round;
+        { ProfScope ps_(ctx, K_EXPAND, 0);
+        k_ip_expand<<<dim3((unsigned)((Np + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+    }
+    if (M) {
+        ExpandArgs A;
+        A.fx = ip_f(h, 4); A.fr_ = ip_f(h, 5); A.f_stride = M; A.f_off = 0;
+        A.coef = ip_coef(h); A.coef_stride = ip_coef_stride(h); A.coef_off = (int)(2 * Np);
+        A.xs = ls; A.rs = rs; A.sc_stride = P0; A.off = 1 + (int)h->N; A.n = (int)M; A.shift = h->round;
+        { ProfScope ps_(ctx, K_EXPAND, 0);
+        k_expand_scalars<<<dim3((unsigned)((M + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+    }
+    if ((rc = run_msm_gens(h->gens, P0, ls, P0, B * P0, B, 2, h->res.p, 2 * msm_alg_imads((double)P0)))) return rc;
+    if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2))) return rc;
+    std::vector<Affine> xr(B * 2);
+    std::vector<Fr> dots(B * 2);
+    CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
+    CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
+    CK(cudaStreamSynchronize(ctx->st));
+    for (size_t b = 0; b < B; b++) {
+        memcpy(Lout + 64 * b, &xr[2 * b], 64);
+        memcpy(Rout + 64 * b, &xr[2 * b + 1], 64);
+        h->sX[b] = dots[2 * b];
+        h->sR[b] = dots[2 * b + 1];
+    }
+    return BPPP_OK;
+}
+
+int ip_round_fold(bppp_nl* h, const uint8_t* e) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, Np = h->Np, M = h->M;
+    std::vector<Fr> em(B), ei(B);
+    for (size_t b = 0; b < B; b++) { em[b] = h64::from_bytes(e + 32 * b); ei[b] = em[b]; }
+    h64::batch_inv(ei.data(), B);
+    std::vector<Fr> aG(B), bG(B), cH(B), dH(B), aK(B), bK(B), inv(3 * B), rho(B);
+    host_parallel_for(B, [&](size_t b) {
+        // :89 (a', b') = rationalReduceScalar (qInv * eInv) ; :93 (c', d') = rationalReduceScalar e ;
+        // linear :158 rationalReduceScalar (recip e)
+        host::Ratio rg = host::rational_reduce(fr_canon_u256(h64::mul(h->qinv[b], ei[b])));
+        host::Ratio rh = host::rational_reduce(host::from_bytes(e + 32 * b));
+        host::Ratio rk = host::rational_reduce(fr_canon_u256(ei[b]));
+        aG[b] = fr_from_mag(rg.a, rg.a_neg); bG[b] = fr_from_mag(rg.b, rg.b_neg);
+        cH[b] = fr_from_mag(rh.a, rh.a_neg); dH[b] = fr_from_mag(rh.b, rh.b_neg);
+        aK[b] = fr_from_mag(rk.a, rk.a_neg); bK[b] = fr_from_mag(rk.b, rk.b_neg);
+        inv[b] = bG[b]; inv[B + b] = dH[b]; inv[2 * B + b] = bK[b];
+    });
+    h64::batch_inv(inv.data(), 3 * B);
+    std::vector<Fr> au(B), bu(B), av(B), bvv(B), al(B), bl(B);
+    host_parallel_for(B, [&](size_t b) {
+        au[b] = inv[b];                                            // x' = b0Inv (xL + e q xR)      (:97)
+        bu[b] = h64::mul(h64::mul(em[b], h->q[b]), inv[b]);
+        av[b] = inv[B + b];                                        // y' = d0Inv (yL + eInv yR)
+        bvv[b] = h64::mul(ei[b], inv[B + b]);
+        al[b] = inv[2 * B + b];                                    // l' = b0Inv xL + e b0Inv xR    (:165)
+        bl[b] = h64::mul(em[b], inv[2 * B + b]);
+        // s' = s + eInv sL + e sR   (makeEs = (recip e, e), :68)
+        h->s[b] = h64::add(h->s[b], h64::add(h64::mul(ei[b], h->sX[b]), h64::mul(em[b], h->sR[b])));
+        h->nn[b] = h64::mul(h64::mul(h->nn[b], bG[b]), h->qinv[b]);   // nx * b0 * qInv
+        h->ny[b] = h64::mul(h->ny[b], dH[b]);
+        h->nl[b] = h64::mul(h->nl[b], bK[b]);
+        h->q[b] = h64::sqr(h->q[b]);
+        h->qinv[b] = h64::sqr(h->qinv[b]);
+        rho[b] = h64::sqr(h->q[b]);
+    });
+    int rc;
+    if ((rc = upload_consts(h, C_AU, au)) || (rc = upload_consts(h, C_BU, bu)) || (rc = upload_consts(h, C_AV, av)) ||
+        (rc = upload_consts(h, C_BV, bvv)) || (rc = upload_consts(h, C_AL, al)) || (rc = upload_consts(h, C_BL, bl)) ||
+        (rc = upload_consts(h, C_AC, bK)) || (rc = upload_consts(h, C_BC, aK)) || (rc = upload_consts(h, C_RHO, rho)) ||
+        (rc = upload_consts(h, C_A0N, aG)) || (rc = upload_consts(h, C_B0N, bG)) || (rc = upload_consts(h, C_A0H, cH)) ||
+        (rc = upload_consts(h, C_B0H, dH)) || (rc = upload_consts(h, C_A0L, aK)) || (rc = upload_consts(h, C_B0L, bK)))
+        return rc;
+    if ((rc = launch_fold_dots(h, 1))) return rc;
+    struct { int off; size_t n; int ca, cb; } segs[3] = {{0, Np, C_A0N, C_B0N}, {(int)Np, Np, C_A0H, C_B0H}, {(int)(2 * Np), M, C_A0L, C_B0L}};
+    for (auto& sg : segs) {
+        if (!sg.n) continue;
+        { ProfScope ps_(ctx, K_COEF, 0);
+        k_coef_update<<<dim3((unsigned)((sg.n + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(
+            ip_coef(h), ip_coef_stride(h), sg.off, (int)sg.n, h->round, cptr(h, sg.ca), cptr(h, sg.cb), 1, 0);
+        }
+        CK(cudaGetLastError());
+    }
+    h->cur ^= 1;
+    h->curN = (h->curN + 1) / 2;
+    h->curM = (h->curM + 1) / 2;
+    h->round++;
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+
+int ip_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, cn = h->curN, cl = h->curM;
+    if (s) for (size_t b = 0; b < B; b++) h64::to_bytes(s + 32 * b, h->s[b]);
+    if (w && cn) {
+        DBuf<u256> out;
+        CK(out.alloc(B * cn * 2));
+        CK(H2D(cptr(h, C_NX), h->nn.data(), B * 32));
+        CK(H2D(cptr(h, C_NY), h->ny.data(), B * 32));
+        { ProfScope ps_(ctx, K_IP_MISC, 0);
+        k_ip_final<<<dim3((unsigned)((cn + 127) / 128), (unsigned)B), 128, 0, ctx->st>>>(
+            h->w[h->cur].p, h->bv[h->cur].p, h->wstride[h->cur], (int)cn, cptr(h, C_NX), cptr(h, C_NY), out.p);
+        }
+        CK(cudaGetLastError());
+        CK(D2H(w, out.p, B * cn * 2 * 32));
+        CK(cudaStreamSynchronize(ctx->st));
+    }
+    if (l && cl) {
+        std::vector<Fr> hl(B * cl);
+        ctx->d2h += B * cl * 32;
+        CK(cudaMemcpy2DAsync(hl.data(), cl * 32, h->l[h->cur].p, h->lstride[h->cur] * 32, cl * 32, B, cudaMemcpyDeviceToHost, ctx->st));
+        CK(cudaStreamSynchronize(ctx->st));
+        for (size_t b = 0; b < B; b++)
+            for (size_t i = 0; i < cl; i++) h64::to_bytes(l + 32 * (b * cl + i), h64::mul(h->nl[b], hl[b * cl + i]));
+    }
+    return BPPP_OK;
+}
+}  // namespace
+
+namespace {
 int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint8_t* q, const uint8_t* s, const uint8_t* w,
                    const uint8_t* l, const uint8_t* c, bppp_nl** out) {
     bppp_ctx* ctx = gens->ctx;
@@ -849,6 +1121,12 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
     h->B = batch; h->N = N; h->M = M; h->curN = N; h->curM = M;
     h->N2 = (N + 1) / 2; h->M2 = (M + 1) / 2; h->P0 = 1 + N + M; h->P2 = 1 + h->N2 + h->M2;
     auto fail = [&](int rc) { h->own_gens = false; bppp_nl_destroy(h); return rc; };
+    if (kind == BPPP_ARG_IP) {
+        int rc = ip_create(h, q, s, w, l, c);
+        if (rc) return fail(rc);
+        *out = h;
+        return BPPP_OK;
+    }
 #define CKH(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x ": ") + cudaGetErrorString(e_); return fail(BPPP_ERR_CUDA); } } while (0)
     {
         const char* ev = getenv("BPPP_ROUND_MODE");          // fold | tensor | auto (default)
@@ -913,7 +1191,7 @@ extern "C" int bppp_nl_create_gens(bppp_gens* gens, int kind, size_t batch, cons
     if (!out || !q || !s || batch == 0 || (gens->N && !w) || (gens->M && (!l || !c)))
         FAIL(BPPP_ERR_ARG, "bppp_nl_create: null/empty argument");
     *out = nullptr;
-    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_create: only BPPP_ARG_NL is implemented on the device path");
+    if (kind != BPPP_ARG_NL && kind != BPPP_ARG_IP) FAIL(BPPP_ERR_ARG, "bppp_nl_create: unknown argument kind");
     ENTER(ctx);
     return nl_create_impl(gens, false, kind, batch, q, s, w, l, c, out);
 }
@@ -924,7 +1202,7 @@ extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
     if (!out || !g || !q || !s || batch == 0 || (N && (!G || !w)) || (M && (!H || !l || !c)))
         FAIL(BPPP_ERR_ARG, "bppp_nl_create: null/empty argument");
     *out = nullptr;
-    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_create: only BPPP_ARG_NL is implemented on the device path");
+    if (kind != BPPP_ARG_NL && kind != BPPP_ARG_IP) FAIL(BPPP_ERR_ARG, "bppp_nl_create: unknown argument kind");
     bppp_gens* gens = nullptr;
     int rc = bppp_gens_create(ctx, N, M, g, G, H, &gens);
     if (rc) return rc;
@@ -943,7 +1221,7 @@ extern "C" void bppp_nl_destroy(bppp_nl* h) {
 
 extern "C" int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin) {
     if (!h) return BPPP_ERR_ARG;
-    if (n_norm) *n_norm = h->curN;
+    if (n_norm) *n_norm = h->kind == BPPP_ARG_IP ? 2 * h->curN : h->curN;   // IP.Norm.getWitness: two scalars per element
     if (n_lin) *n_lin = h->curM;
     return BPPP_OK;
 }
@@ -953,6 +1231,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     bppp_ctx* ctx = h->ctx;
     if (!X || !R) FAIL(BPPP_ERR_ARG, "bppp_nl_round_commit: null output");
     ENTER(ctx);
+    if (h->kind == BPPP_ARG_IP) return ip_round_commit(h, X, R);
     const size_t B = h->B;
     // per-proof constants of this round (NormArgument.hs:113): rho = q^4, k1 = 2 n^2 q^3, k2 = n^2 q^4
     std::vector<Fr> rho(B), k1(B), k2(B), coef(B * 8, h64::zero());
@@ -1064,6 +1343,7 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     ENTER(ctx);
     const size_t B = h->B;
     if (!check_fr(e, B)) FAIL(BPPP_ERR_RANGE, "challenge >= group order");
+    if (h->kind == BPPP_ARG_IP) return ip_round_fold(h, e);
     std::vector<Fr> au(B), bu(B), al(B), bl(B), ac(B), bc(B), rho(B), b0n(B), b0l(B), em(B), inv(2 * B), a0n(B);
     std::vector<u256> kk(B * 4);
     std::vector<unsigned char> sg(B * 2);
@@ -1159,6 +1439,7 @@ extern "C" int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
     ENTER(ctx);
+    if (h->kind == BPPP_ARG_IP) return ip_final(h, s, w, l);
     const size_t B = h->B, cn = h->curN, cl = h->curM;
     std::vector<Fr> hw(B * cn), hl(B * cl);
     if (w && cn) { ctx->d2h += B * cn * 32; CK(cudaMemcpy2DAsync(hw.data(), cn * 32, h->w[h->cur].p, h->wstride[h->cur] * 32, cn * 32, B, cudaMemcpyDeviceToHost, ctx->st)); }
@@ -1179,7 +1460,6 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
                    size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s,
                    const uint8_t* init_p, int* ok) {
     bppp_ctx* ctx = gens->ctx;
-    (void)kind;
     const size_t N = gens->N, M = gens->M;
     const size_t B = batch, P0 = 1 + N + M, NX = n_init + 2 * k;
     if (!check_fq(XR, 4 * k * B) || !check_fq(init_p, 2 * n_init * B)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
@@ -1201,24 +1481,50 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
         }
         CK(cudaGetLastError());
     }
-    // host: challenges, tensor factors, final-witness scalar sc  (NormArgument.hs:131-145, 73-81)
-    std::vector<Fr> hf0n(B * k), hf1(B * k), hf0l(B * k, h64::one()), hvn(B * n_norm), hvl(B * n_lin), scn(B), hc(B * M);
+    // host: challenges, tensor factors, final-witness scalar sc
+    //   NL: NormArgument.hs:131-145, 73-81        IP: InnerProductArgument.hs:103-124, 172-181
+    const bool ip = kind == BPPP_ARG_IP;
+    const size_t nvs = ip ? n_norm / 2 : n_norm;
+    if (ip && (n_norm & 1)) FAIL(BPPP_ERR_ARG, "IP final norm witness has an even number of scalars");
+    std::vector<Fr> hf0n(B * k), hf1(B * k), hf0l(B * k, h64::one()), hvn(B * std::max<size_t>(nvs, 1)), hvl(B * n_lin), scn(B), hc(B * M);
+    std::vector<Fr> hf1y(B * k), hvy(B * std::max<size_t>(nvs, 1)), hr(B), einv(B * std::max<size_t>(k, 1));
     std::vector<u256> hx(B * std::max<size_t>(NX, 1));
     std::vector<Affine> hp(B * std::max<size_t>(NX, 1));
+    if (ip) {
+        for (size_t i = 0; i < B * k; i++) einv[i] = h64::from_bytes(es + 32 * i);
+        h64::batch_inv(einv.data(), B * k);
+    }
+    const Fr half = h64::inv(h64::from_u64(2)), four = h64::from_u64(4);
     host_parallel_for(B, [&](size_t b) {
         Fr qq = h64::from_bytes(q + 32 * b);
+        if (ip) { hr[b] = qq; qq = h64::sqr(h64::sqr(qq)); }          // q = r^4  (makeNorm :196)
         for (size_t j = 0; j < k; j++) {
             // round j+1's challenge is es[k-1-j] (newest first)
-            hf1[b * k + j] = h64::from_bytes(es + 32 * (b * k + (k - 1 - j)));
+            const size_t ei = b * k + (k - 1 - j);
+            hf1[b * k + j] = ip ? einv[ei] : h64::from_bytes(es + 32 * ei);       // IP: esX = recip <$> esY
+            if (ip) hf1y[b * k + j] = h64::from_bytes(es + 32 * ei);
             hf0n[b * k + j] = qq;
             qq = h64::sqr(qq);
         }
-        Fr qF2 = h64::sqr(qq), wgt = qF2, acc = h64::zero();          // powers' (qF^2)
-        for (size_t i = 0; i < n_norm; i++) {
-            Fr v = h64::from_bytes(fw + 32 * (b * n_norm + i));
-            hvn[b * n_norm + i] = v;
-            acc = h64::add(acc, h64::mul(wgt, h64::sqr(v)));
-            wgt = h64::mul(wgt, qF2);
+        Fr acc = h64::zero();
+        if (ip) {
+            Fr wgt = qq;                                                          // powers' qF
+            for (size_t i = 0; i < nvs; i++) {
+                Fr s0 = h64::from_bytes(fw + 32 * (b * n_norm + 2 * i)), s1 = h64::from_bytes(fw + 32 * (b * n_norm + 2 * i + 1));
+                Fr vx = h64::mul(half, h64::add(s0, s1)), vy = h64::mul(half, h64::sub(s1, s0));   // makeNorm 1 (RangeProof.hs:80)
+                hvn[b * nvs + i] = vx; hvy[b * nvs + i] = vy;
+                acc = h64::add(acc, h64::mul(wgt, h64::mul(vx, vy)));
+                wgt = h64::mul(wgt, qq);
+            }
+            acc = h64::mul(four, acc);                                            // sIP = 4
+        } else {
+            Fr qF2 = h64::sqr(qq), wgt = qF2;                                     // powers' (qF^2)
+            for (size_t i = 0; i < n_norm; i++) {
+                Fr v = h64::from_bytes(fw + 32 * (b * n_norm + i));
+                hvn[b * n_norm + i] = v;
+                acc = h64::add(acc, h64::mul(wgt, h64::sqr(v)));
+                wgt = h64::mul(wgt, qF2);
+            }
         }
         scn[b] = acc;
         for (size_t i = 0; i < n_lin; i++) hvl[b * n_lin + i] = h64::from_bytes(fl + 32 * (b * n_lin + i));
@@ -1230,23 +1536,44 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
         }
         for (size_t r = 0; r < k; r++) {
             Fr e = h64::from_bytes(es + 32 * (b * k + r));
-            hx[b * NX + n_init + 2 * r] = host::from_bytes(es + 32 * (b * k + r));
-            hx[b * NX + n_init + 2 * r + 1] = fr_canon_u256(h64::sub(h64::sqr(e), h64::one()));
+            if (ip) {                                                             // makeEs = (recip e, e)
+                hx[b * NX + n_init + 2 * r] = fr_canon_u256(einv[b * k + r]);
+                hx[b * NX + n_init + 2 * r + 1] = host::from_bytes(es + 32 * (b * k + r));
+            } else {                                                              // makeEs = (e, e^2 - 1)
+                hx[b * NX + n_init + 2 * r] = host::from_bytes(es + 32 * (b * k + r));
+                hx[b * NX + n_init + 2 * r + 1] = fr_canon_u256(h64::sub(h64::sqr(e), h64::one()));
+            }
             memcpy(&hp[b * NX + n_init + 2 * r], XR + 64 * ((b * k + r) * 2), 128);
         }
     });
+    DBuf<u256> vs_y, f1y, rdev;
+    if (ip) {
+        CK(vs_y.alloc(B * std::max<size_t>(nvs, 1))); CK(f1y.alloc(B * std::max<size_t>(k, 1))); CK(rdev.alloc(B));
+        if (nvs) CK(H2D(vs_y.p, hvy.data(), B * nvs * 32));
+        if (k) CK(H2D(f1y.p, hf1y.data(), B * k * 32));
+        CK(H2D(rdev.p, hr.data(), B * 32));
+    }
     if (k) {
         CK(H2D(f0n.p, hf0n.data(), B * k * 32));
         CK(H2D(f1.p, hf1.data(), B * k * 32));
         CK(H2D(f0l.p, hf0l.data(), B * k * 32));
     }
-    if (n_norm) CK(H2D(vs_n.p, hvn.data(), B * n_norm * 32));
+    if (nvs) CK(H2D(vs_n.p, hvn.data(), B * nvs * 32));
     if (n_lin) CK(H2D(vs_l.p, hvl.data(), B * n_lin * 32));
     if (NX) {
         CK(H2D(xsc.p, hx.data(), B * NX * 32));
         CK(H2D(extra.p, hp.data(), B * NX * 64));
     }
-    if (N) {
+    if (N && ip) {
+        IpVerifyArgs A;
+        A.pub = pub.p; A.pub_stride = N; A.vx = vs_n.p; A.vy = vs_y.p; A.n_vs = (int)nvs;
+        A.f0x = f0n.p; A.f1x = f1.p; A.f1y = f1y.p; A.k = (int)k; A.r = rdev.p;
+        A.out = sc.p; A.out_stride = P0; A.off = 1; A.n = (int)N;
+        { ProfScope ps_(ctx, K_TENSOR, 0);
+        k_ip_verify_scalars<<<dim3((unsigned)(((N + 1) / 2 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+    } else if (N) {
         TensorArgs A;
         A.pub = pub.p; A.pub_stride = N; A.vs = vs_n.p; A.n_vs = (int)n_norm; A.f0 = f0n.p; A.f1 = f1.p; A.k = (int)k;
         A.out = sc.p; A.out_stride = P0; A.off = 1; A.n = (int)N;
@@ -1307,7 +1634,7 @@ extern "C" int bppp_nl_verify_gens(bppp_gens* gens, int kind, size_t batch, size
                                    const uint8_t* init_s, const uint8_t* init_p, int* ok) {
     if (!gens) return BPPP_ERR_ARG;
     bppp_ctx* ctx = gens->ctx;
-    if (kind != BPPP_ARG_NL) FAIL(BPPP_ERR_ARG, "bppp_nl_verify: only BPPP_ARG_NL is implemented on the device path");
+    if (kind != BPPP_ARG_NL && kind != BPPP_ARG_IP) FAIL(BPPP_ERR_ARG, "bppp_nl_verify: unknown argument kind");
     if (!q || !s_pub || !ok || batch == 0 || (gens->N && !pub_w) || (gens->M && !c) || (k && (!es || !XR)) ||
         (n_norm && !fw) || (n_lin && !fl) || (n_init && (!init_s || !init_p)))
         FAIL(BPPP_ERR_ARG, "bppp_nl_verify: null/empty argument");

@@ -222,6 +222,18 @@ void optimal_witness_size_nl(size_t n_len, size_t l_len, size_t& rounds, size_t&
     if (n1 + l1 > 5) { rounds = r + 1; fn = round_reduce(n1); fl = round_reduce(l1); }
     else { rounds = r; fn = n1; fl = l1; }
 }
+// IP.NormLinear.optimalWitnessSize (InnerProductArgument.hs:253-267): nLen is the norm length
+void optimal_witness_size_ip(size_t n_len, size_t l_len, size_t& rounds, size_t& fn, size_t& fl) {
+    size_t n_even = (n_len + (n_len % 2)) / 2, nR, n1, lR, l1;
+    number_rounds_reduce(n_even, nR, n1);                       // numberRoundsReduce' (Bulletproof.hs:306-308)
+    if (n1 > 2) { nR++; n1 = round_reduce(n1); }
+    number_rounds_reduce(l_len, lR, l1);
+    size_t r = std::max(nR, lR);
+    for (size_t i = nR; i < r; i++) n1 = round_reduce(n1);
+    for (size_t i = lR; i < r; i++) l1 = round_reduce(l1);
+    if (2 * n1 + l1 > 5) { rounds = r + 1; fn = 2 * round_reduce(n1); fl = round_reduce(l1); }
+    else { rounds = r; fn = 2 * n1; fl = l1; }
+}
 void lengths_after(size_t n, size_t l, size_t rounds, size_t& fn, size_t& fl) {
     for (size_t i = 0; i < rounds; i++) { n = round_reduce(n); l = round_reduce(l); }
     fn = n; fl = l;
@@ -298,9 +310,10 @@ void commit_scalars(const bppp_rp* s, const RPW& w, uint8_t* out) {
         if (!w.lin[i].is_zero()) h64::to_bytes(out + 32 * (1 + s->nrm_len + i), w.lin[i]);
 }
 
-std::vector<Fr> q_powers(const Fr& q, size_t n) {        // NL: powers' (q^2)  (NormArgument.hs:147-148)
-    return h64::powers1(h64::sqr(q), n);
-}
+// qPowers' of the Weighted instances: NL powers' (q^2) (NormArgument.hs:147-148);
+// IP norm powers' (-(q^2)) (InnerProductArgument.hs:230-231)
+Fr q0_of(int arg, const Fr& q) { return arg == BPPP_ARG_IP ? h64::neg(h64::sqr(q)) : h64::sqr(q); }
+std::vector<Fr> q_powers(int arg, const Fr& q, size_t n) { return h64::powers1(q0_of(arg, q), n); }
 
 // ---- blinding helpers (Internal.hs:134-195)
 std::vector<Fr> pad_right(size_t n, std::vector<Fr> xs) {
@@ -796,9 +809,15 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
         need = 2 + s->lin_len + s->nrm_len;
     }
     s->pts = tr::get_points(s->basis_seed, need, s->root);
-    optimal_witness_size_nl(s->nrm_len, s->lin_len, s->rounds, s->fin_n, s->fin_l);
+    if (s->arg == BPPP_ARG_IP) optimal_witness_size_ip(s->nrm_len, s->lin_len, s->rounds, s->fin_n, s->fin_l);
+    else optimal_witness_size_nl(s->nrm_len, s->lin_len, s->rounds, s->fin_n, s->fin_l);
     if (s->binary) {                       // the prover's own rule (Binary.hs:195)
         s->prover_rounds = (size_t)std::max(0, integer_log(2, s->nrm_len) - 1);
+        if (s->arg == BPPP_ARG_IP) {
+            size_t a = (s->nrm_len + 1) / 2, l2 = s->lin_len;
+            for (size_t i = 0; i < s->prover_rounds; i++) { a = round_reduce(a); l2 = round_reduce(l2); }
+            s->prover_fin_n = 2 * a; s->prover_fin_l = l2;
+        } else
         lengths_after(s->nrm_len, s->lin_len, s->prover_rounds, s->prover_fin_n, s->prover_fin_l);
     } else {
         s->prover_rounds = s->rounds; s->prover_fin_n = s->fin_n; s->prover_fin_l = s->fin_l;
@@ -1015,7 +1034,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             p.zk.oracle(out + 64, 1 + n, ch, 3);                            // T3 q x r <- oracle' (dCom:nComs)
             p.q = ch[0]; p.x = ch[1]; p.r0 = ch[2];
             Fr r_inv = h64::inv(p.r0);
-            p.q0 = h64::sqr(p.q);                                           // head (powers' (q^2))
+            p.q0 = q0_of(s->arg, p.q);                                      // head (qPowers q)
             p.q0_inv = h64::inv(p.q0);
             p.pub = public_consts_brp(s, p.x, p.q0, p.q0_inv);
             p.bls_nrm.clear();
@@ -1024,7 +1043,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             // makePolyTerms (qPowers q) [blsNrm, nrm (dWit + pubWit)]  (Binary.hs:188, Internal.hs:65-75)
             std::vector<Fr> dn = p.d.nrm;
             vadd(dn, p.pub.nrm);
-            std::vector<Fr> ws = q_powers(p.q, N);
+            std::vector<Fr> ws = q_powers(s->arg, p.q, N);
             Fr bl0 = h64::zero(), bl1 = h64::zero();
             for (size_t i = 0; i < N; i++) bl0 = h64::add(bl0, h64::mul(ws[i], h64::sqr(p.bls_nrm[i])));
             for (size_t i = 0; i < N && i < dn.size(); i++) bl1 = h64::add(bl1, h64::mul(ws[i], h64::mul(p.bls_nrm[i], dn[i])));
@@ -1093,7 +1112,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             Fr ch[3];
             p.zk.oracle(out + 64, 1, ch, 3);                                // T3 q x' r1 <- oracle' [rCom]
             p.q = ch[0]; p.xq = ch[1]; p.r1 = ch[2];
-            p.q0 = h64::sqr(p.q);
+            p.q0 = q0_of(s->arg, p.q);
             Fr iv[3] = {p.q, p.q0, p.r1};
             h64::batch_inv(iv, 3);
             p.q_inv = iv[0]; p.q0_inv = iv[1]; p.r1_inv = iv[2];
@@ -1109,7 +1128,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             RPW nsum;
             for (size_t i = 0; i < n; i++) rpw_add(nsum, rpw_scale(p.n_wits[i], ic[i]));
             Fr input_bl = nsum.lin.size() > 1 ? nsum.lin[1] : h64::zero();
-            std::vector<Fr> q2s = q_powers(p.q, p.ph2s.size());
+            std::vector<Fr> q2s = q_powers(s->arg, p.q, p.ph2s.size());
             std::vector<Fr> errs = make_error_terms(p.e, p.xq, p.shared_cs, bls_ms, p.ph2s, q2s, p.bls_nrm);
             RPW blbl;
             blbl.lin = p.bls_lin; blbl.nrm = p.bls_nrm;
@@ -1173,7 +1192,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             zk.oracle(cm + 64, 1 + n, ch, 3);
             q = ch[0];
             Fr x = ch[1], r = ch[2];
-            Fr q0 = h64::sqr(q), q0_inv = h64::inv(q0);
+            Fr q0 = q0_of(s->arg, q), q0_inv = h64::inv(q0);
             zk.oracle(cm, 1, &t, 1);
             RPW pw = public_consts_brp(s, x, q0, q0_inv);
             // pub = t *^ RPW (t * pubSc) [] pubNrm
@@ -1192,7 +1211,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             zk.oracle(cm + 64, 1, ch2, 3);
             q = ch2[0];
             Fr xq = ch2[1], r1 = ch2[2];
-            Fr q0 = h64::sqr(q);
+            Fr q0 = q0_of(s->arg, q);
             zk.oracle(cm, 1, &t, 1);
             Fr iv[3] = {e, q, q0};
             h64::batch_inv(iv, 3);
@@ -1277,7 +1296,6 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
                         const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals) {
     if (!s) return BPPP_ERR_ARG;
     if (!values || !random_seeds || !coms || !responses || !finals || batch == 0) return fail(s, BPPP_ERR_ARG, "null/empty argument");
-    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
     const size_t n = s->n_inputs, NC = s->num_rp_coms + n, nf = s->prover_fin_n + s->prover_fin_l, k = s->prover_rounds;
     return run_lanes(s, batch, [&](const Lane& ln, size_t b0, size_t nb) {
         return prove_impl(s, ln, nb, values + 32 * b0 * n, types ? types + 32 * b0 * n : nullptr,
@@ -1289,7 +1307,6 @@ int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm,
                          const uint8_t* responses, const uint8_t* finals, int* ok) {
     if (!s) return BPPP_ERR_ARG;
     if (!coms || !finals || !ok || batch == 0 || (rounds && !responses)) return fail(s, BPPP_ERR_ARG, "null/empty argument");
-    if (s->arg != BPPP_ARG_NL) return fail(s, BPPP_ERR_ARG, "only the NL (norm) argument runs on the device path");
     const size_t NC = s->num_rp_coms + s->n_inputs;
     return run_lanes(s, batch, [&](const Lane& ln, size_t b0, size_t nb) {
         return verify_impl(s, ln, nb, rounds, n_norm, n_lin, coms + 64 * b0 * NC, responses + 128 * b0 * rounds,

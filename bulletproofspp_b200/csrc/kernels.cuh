@@ -856,6 +856,109 @@ __global__ void k_jac_sum(const Jac* __restrict__ a, int na, const Jac* __restri
 }
 
 // ------------------------------------------------------------------------------------------
+// IP (weighted inner-product) argument, InnerProductArgument.hs.  The norm witness pairs
+// (s0, s1) on (g0, g1) become a = s0/2r + s1/2 on G' = g1 + r*g0 and b = -s0/2r + s1/2 on
+// H' = g1 - r*g0 (makeNorm, :194-206).  The device never builds G', H': a term xs*G'_j + ys*H'_j
+// is (xs + ys)*g1_j + r*(xs - ys)*g0_j over the ORIGINAL generators, and folded generators are
+// tracked by per-pair coefficients (tensor mode), so every commitment is a fixed-base MSM.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ip_make_norm(const u256* __restrict__ w, size_t w_stride, int n, u256* a, u256* b,
+                                                       size_t ab_stride, const u256* __restrict__ r2inv,
+                                                       const u256* __restrict__ half) {
+    const int p = blockIdx.y;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int np = (n + 1) / 2;
+    if (j >= np) return;
+    const u256* wp = w + (size_t)p * w_stride;
+    u256 s0 = ld_u256(wp + 2 * j);
+    u256 s1 = (2 * j + 1 < n) ? ld_u256(wp + 2 * j + 1) : u256_zero();
+    u256 t0 = fr::mul(ld_u256(r2inv + p), s0), t1 = fr::mul(ld_u256(half + p), s1);
+    st_u256(a + (size_t)p * ab_stride + j, fr::add(t0, t1));
+    st_u256(b + (size_t)p * ab_stride + j, fr::sub(t1, t0));
+}
+// L / R opening scalars over the original norm generators from the folded openings on G', H'.
+struct IpExpandArgs {
+    const u256* fgl; const u256* fgr;   // folded L / R opening scalars on G' (Montgomery) [batch][f_stride]
+    const u256* fhl; const u256* fhr;   // ... on H'
+    size_t f_stride;
+    const u256* cg; const u256* ch;     // per-pair fold coefficients [batch][c_stride]
+    size_t c_stride;
+    const u256* r;                      // per proof basis-change scalar (Montgomery)
+    u256* ls; u256* rs; size_t sc_stride; int off;   // canonical outputs over the original generators
+    int n;                              // original norm length
+    int shift;
+};
+__global__ void __launch_bounds__(256) k_ip_expand(IpExpandArgs A) {
+    const int p = blockIdx.y;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int np = (A.n + 1) / 2;
+    if (j >= np) return;
+    const size_t f = (size_t)p * A.f_stride + (j >> A.shift);
+    const u256 cg = ld_u256(A.cg + (size_t)p * A.c_stride + j), ch = ld_u256(A.ch + (size_t)p * A.c_stride + j);
+    const u256 r = ld_u256(A.r + p);
+    u256* outs[2] = {A.ls, A.rs};
+    const u256* fg[2] = {A.fgl, A.fgr};
+    const u256* fh[2] = {A.fhl, A.fhr};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        u256 xg = fr::mul(ld_u256(fg[k] + f), cg), yh = fr::mul(ld_u256(fh[k] + f), ch);
+        u256* o = outs[k] + (size_t)p * A.sc_stride + A.off;
+        st_u256(o + 2 * j, fr::from_mont(fr::mul(r, fr::sub(xg, yh))));           // on g0
+        if (2 * j + 1 < A.n) st_u256(o + 2 * j + 1, fr::from_mont(fr::add(xg, yh)));   // on g1
+    }
+}
+// final witness of IP.Norm (getWitness, :222-223): (nx*x - ny*y, nx*x + ny*y) per element, canonical
+__global__ void k_ip_final(const u256* a, const u256* b, size_t stride, int n, const u256* nx, const u256* ny, u256* out) {
+    const int p = blockIdx.y;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    u256 x = fr::mul(ld_u256(nx + p), ld_u256(a + (size_t)p * stride + j));
+    u256 y = fr::mul(ld_u256(ny + p), ld_u256(b + (size_t)p * stride + j));
+    st_u256(out + ((size_t)p * n + j) * 2, fr::from_mont(fr::sub(x, y)));
+    st_u256(out + ((size_t)p * n + j) * 2 + 1, fr::from_mont(fr::add(x, y)));
+}
+// verifier scalars over the original norm generators (expandChallenges, :103-124):
+//   tX_j = vsX[j >> k] * prod (bit ? 1/e : q^(2^i)),  tY_j = vsY[j >> k] * prod (bit ? e : 1)
+//   out[2j] = pub[2j] - r*(tX - tY),  out[2j+1] = pub[2j+1] - (tX + tY)
+struct IpVerifyArgs {
+    const u256* pub; size_t pub_stride;      // Montgomery [batch][N]
+    const u256* vx; const u256* vy; int n_vs;
+    const u256* f0x; const u256* f1x; const u256* f1y; int k;   // [batch][k]
+    const u256* r;
+    u256* out; size_t out_stride; int off; int n;
+};
+__global__ void __launch_bounds__(256) k_ip_verify_scalars(IpVerifyArgs A) {
+    const int p = blockIdx.y;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    int np = (A.n + 1) / 2;
+    if (j >= np) return;
+    u256 tx = u256_zero(), ty = u256_zero();
+    int b = j >> A.k;
+    if (b < A.n_vs) {
+        tx = ld_u256(A.vx + (size_t)p * A.n_vs + b);
+        ty = ld_u256(A.vy + (size_t)p * A.n_vs + b);
+        for (int i = 0; i < A.k; i++) {
+            if ((j >> i) & 1) {
+                tx = fr::mul(tx, ld_u256(A.f1x + (size_t)p * A.k + i));
+                ty = fr::mul(ty, ld_u256(A.f1y + (size_t)p * A.k + i));
+            } else {
+                tx = fr::mul(tx, ld_u256(A.f0x + (size_t)p * A.k + i));
+            }
+        }
+    }
+    const u256* pub = A.pub + (size_t)p * A.pub_stride;
+    u256* o = A.out + (size_t)p * A.out_stride + A.off;
+    u256 d = fr::mul(ld_u256(A.r + p), fr::sub(tx, ty));
+    st_u256(o + 2 * j, fr::from_mont(fr::sub(ld_u256(pub + 2 * j), d)));
+    if (2 * j + 1 < A.n) st_u256(o + 2 * j + 1, fr::from_mont(fr::sub(ld_u256(pub + 2 * j + 1), fr::add(tx, ty))));
+}
+// fill with the Montgomery one
+__global__ void k_fill_one(u256* p, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) st_u256(p + i, fr::one());
+}
+
+// ------------------------------------------------------------------------------------------
 // Fixed-base MSM for a handful of bases shared by every MSM (the range proofs' input commitments
 // value*g + type*hs0 + blind*hs1, src/RangeProof/Internal.hs:53-57): 8-bit window tables
 // tbl[(base*32 + w)*255 + d-1] = d * 2^(8w) * P, so one MSM is <= 32 mixed adds per base with no

@@ -109,7 +109,7 @@ def test_pair_fold_degenerate_pairs(ctx, gens):
         assert ctx.pair_fold(a, b, pts) == exp
 
 
-def _prove_device_vs_oracle(ctx, gens, N, M, B, rounds):
+def _prove_device_vs_oracle(ctx, gens, N, M, B, rounds, kind="NL"):
     import bulletproofspp_b200 as bp
     pts = gens(1 + N + M)
     g, Gs, Hs = pts[0], pts[1:1 + N], pts[1 + N:]
@@ -120,9 +120,9 @@ def _prove_device_vs_oracle(ctx, gens, N, M, B, rounds):
     c = [[H("c", b, i) % R for i in range(M)] for b in range(B)]
     if N > 4:
         w[0][3] = 0
-    arg = bp.NormLinearArgument(ctx, bp.ARG_NL, g, Gs, Hs, q, s0, w, l, c)
+    arg = bp.NormLinearArgument(ctx, bp.ARG_NL if kind == "NL" else bp.ARG_IP, g, Gs, Hs, q, s0, w, l, c)
     zks = [ZKPT(G) for _ in range(B)]
-    coms = [obp.PSV(s0[b], g, obp.NormLinear.make("NL", G, q[b], c[b], w[b], Gs, l[b], Hs)) for b in range(B)]
+    coms = [obp.PSV(s0[b], g, obp.NormLinear.make(kind, G, q[b], c[b], w[b], Gs, l[b], Hs)) for b in range(B)]
     resp = [[] for _ in range(B)]
     for r in range(rounds):
         X, Rr = arg.round_commit()
@@ -135,7 +135,8 @@ def _prove_device_vs_oracle(ctx, gens, N, M, B, rounds):
             es.append(tr[0]["e"])
             resp[b].insert(0, xr)
         arg.round_fold(es)
-        assert arg.lengths() == coms[0].vec.lengths()
+        nl_, ll_ = coms[0].vec.lengths()
+        assert arg.lengths() == ((2 * nl_, ll_) if kind == "IP" else (nl_, ll_))
     s, fw, fl = arg.final()
     for b in range(B):
         assert s[b] == coms[b].s
@@ -149,6 +150,12 @@ def _prove_device_vs_oracle(ctx, gens, N, M, B, rounds):
 def test_norm_argument_rounds_match_oracle(ctx, gens, N, M, B):
     rounds = obp.optimal_witness_size("NL", N, max(M, 1))[0] if M else obp.number_rounds_reduce(N)[0]
     _prove_device_vs_oracle(ctx, gens, N, M, B, max(rounds, 2))
+
+
+@pytest.mark.parametrize("N,M,B,rounds", [(16, 6, 2, 3), (11, 6, 1, 3), (62, 24, 2, 5), (37, 5, 3, 4), (192, 2, 1, 6), (8, 0, 1, 2)])
+def test_inner_product_argument_rounds_match_oracle(ctx, gens, N, M, B, rounds):
+    """IP.NormLinear (InnerProductArgument.hs): basis change, L/R commitments, folds, final witness"""
+    _prove_device_vs_oracle(ctx, gens, N, M, B, rounds, kind="IP")
 
 
 def test_norm_argument_128by64_shape_batch(ctx, gens):

@@ -12,6 +12,7 @@ from example_configs import EXAMPLES, batched
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 NL_CONFIGS = ["bin_test", "bin64", "typed_nl", "32by64", "64by64", "96by64", "128by64"]
+IP_CONFIGS = ["64bit", "32bit", "rec_test"]          # reciprocal proofs over the IP argument (app/Parse.hs:100 default)
 
 
 def load_golden(name):
@@ -24,7 +25,7 @@ def load_golden(name):
     return g
 
 
-@pytest.mark.parametrize("name", NL_CONFIGS)
+@pytest.mark.parametrize("name", NL_CONFIGS + IP_CONFIGS)
 def test_prove_matches_golden_and_verifies(ctx, name):
     import bulletproofspp_b200 as bp
     schema, wit = EXAMPLES[name]
@@ -91,10 +92,14 @@ def test_invalid_witness_is_rejected(ctx):
     setup.close()
 
 
-def test_ip_argument_is_refused_loudly(ctx):
-    """the IP argument has no device path yet: it must fail, not fall back"""
+def test_ip_and_nl_give_different_proofs_for_the_same_statement(ctx):
     import bulletproofspp_b200 as bp
-    setup = bp.RangeProofSetup(ctx, EXAMPLES["64bit"][0])
-    with pytest.raises(bp.BpppError):
-        setup.prove_batch([EXAMPLES["64bit"][1]])
-    setup.close()
+    schema, wit = EXAMPLES["64bit"]
+    ip = bp.RangeProofSetup(ctx, schema)
+    nl = bp.RangeProofSetup(ctx, dict(schema, argument="NL"))
+    p_ip, p_nl = ip.prove_batch([wit])[0], nl.prove_batch([wit])[0]
+    assert p_ip["coms"][2:] == p_nl["coms"][2:]            # digit / multiplicity / input commitments do not depend on q
+    assert p_ip["responses"] != p_nl["responses"]
+    assert ip.verify_batch([p_ip]) == [True] and nl.verify_batch([p_nl]) == [True]
+    ip.close()
+    nl.close()
