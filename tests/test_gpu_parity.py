@@ -228,3 +228,38 @@ def test_fixed_base_generator_msm(ctx, gens, n):
             [1 if i == n - 1 else 0 for i in range(n)]]
     got = ctx.gens_msm_batch(g, Gs, [], rows)
     assert got == [G.msm(zip(r, pts)) for r in rows]
+
+
+def test_large_argument_fold_mode_rounds_and_verify(ctx, gens):
+    """N = 4096 (+6 linear), fold mode with multi-chunk MSMs: first rounds against the oracle (the
+    reference's own Straus / pair-fold loops in C), then the whole 10-round argument prove -> verify
+    on the device (size-independent property)."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import bulletproofspp_b200 as bp
+    from bulletproofspp_b200 import lib as L
+    from oracle.curve import SecpRef
+    import sweep
+    out = sweep.run(ctx, 12, profile=False)
+    assert out["verifies"] and out["rounds"] == 10 and out["final"] == [4, 1]
+    # oracle comparison of rounds 1..3 on the same inputs
+    N, M = 4096, 6
+    pts = gens(1 + N + M)
+    q = L.le_to_int(sweep.scalars("q12", 1))
+    w, l, c = (L.bytes_to_ints(sweep.scalars(t + "12", n)) for t, n in (("w", N), ("l", M), ("c", M)))
+    try:
+        SecpRef.lib()
+        Gr = SecpRef
+    except RuntimeError:
+        Gr = G
+    com = obp.PSV(0, pts[0], obp.NormLinear.make("NL", Gr, q, c, w, pts[1:1 + N], l, pts[1 + N:]))
+    arg = bp.NormLinearArgument(ctx, bp.ARG_NL, pts[0], pts[1:1 + N], pts[1 + N:], [q], [0], [w], [l], [c])
+    zk = ZKPT(G)
+    for r in range(3):
+        X, Rr = arg.round_commit()
+        tr = []
+        com, _ = obp.prove_round(Gr, zk, com, tr)
+        assert (X[0], Rr[0]) == (tr[0]["X"], tr[0]["R"]), "round %d" % r
+        arg.round_fold([tr[0]["e"]])
+    arg.close()
