@@ -296,6 +296,10 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
     *out = nullptr;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return BPPP_ERR_CUDA;
+    // host threads waiting for the device sleep instead of spinning: the cores are needed by the
+    // host phases of the other lanes (ignored if the primary context is already active)
+    cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+    cudaGetLastError();
     if (cudaSetDevice(device) != cudaSuccess) return BPPP_ERR_CUDA;
     bppp_ctx* c = new bppp_ctx();
     c->dev = device;

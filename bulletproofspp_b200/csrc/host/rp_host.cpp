@@ -59,6 +59,27 @@ struct Timing {                                // BPPP_TIMING=1: coarse wall-clo
     }
 };
 Timing g_tm;
+// fine-grained per-proof section timers (summed over threads), BPPP_TIMING=1
+enum { S_WITNESS, S_RANDOM, S_SCALARS, S_ORACLE, S_PHASE2, S_COEFFS, S_ERRTERMS, S_BLIND, S_PUB, S_COMBINE, S_TOBYTES, S_V_ORACLE,
+       S_V_PHASE2, S_V_PUB, S_V_MISC, S_COUNT };
+const char* const kSectNames[S_COUNT] = {"witness", "random", "commit_scalars", "oracle", "phase2", "coeffs", "errterms", "blind",
+                                          "pub", "combine", "tobytes", "v_oracle", "v_phase2", "v_pub", "v_misc"};
+std::atomic<uint64_t> g_sect[S_COUNT];
+struct Sect {
+    double t;
+    bool on;
+    Sect() : t(0), on(g_tm.on) { if (on) t = Timing::now(); }
+    void lap(int id) { if (on) { double n = Timing::now(); g_sect[id] += (uint64_t)((n - t) * 1e6); t = n; } }
+};
+void dump_sections(const char* what, size_t proofs) {
+    if (!g_tm.on) return;
+    fprintf(stderr, "[bppp sections] %s (us per proof):", what);
+    for (int i = 0; i < S_COUNT; i++) {
+        uint64_t v = g_sect[i].exchange(0);
+        if (v) fprintf(stderr, " %s=%.0f", kSectNames[i], v / 1e3 / (double)proofs);
+    }
+    fprintf(stderr, "\n");
+}
 extern thread_local bool t_is_lane0;
 static bool t_lane_threads_is_main() { return t_is_lane0; }
 int g_threads = 0;
@@ -141,8 +162,8 @@ RPW rpw_scale(const RPW& a, const Fr& s) {
     r.sc = h64::mul(a.sc, s);
     r.lin.resize(a.lin.size());
     r.nrm.resize(a.nrm.size());
-    for (size_t i = 0; i < a.lin.size(); i++) r.lin[i] = h64::mul(a.lin[i], s);
-    for (size_t i = 0; i < a.nrm.size(); i++) r.nrm[i] = h64::mul(a.nrm[i], s);
+    for (size_t i = 0; i < a.lin.size(); i++) r.lin[i] = a.lin[i].is_zero() ? a.lin[i] : h64::mul(a.lin[i], s);
+    for (size_t i = 0; i < a.nrm.size(); i++) r.nrm[i] = a.nrm[i].is_zero() ? a.nrm[i] : h64::mul(a.nrm[i], s);
     return r;
 }
 
@@ -167,10 +188,14 @@ struct Ph1 {
     bool s_zero = true;
     bool io = false, ia = false;
     Fr d, m;                                   // private: digit (or type), multiplicity; for 'T' v in `m`
+    int di = -1;                               // the digit as a small integer (< 2048) when it is one, else -1
+    bool m_zero = true;                        // multiplicity known to be zero (shared digits, typing)
 };
 struct Ph2 {                                   // TypedReciprocal.hs:165-166
     bool isT;
     Fr d, m, u, v, r, c;
+    bool m_zero = true, c_zero = true;         // known zeros let the per-entry sums skip multiplications
+    int di = -1;
 };
 
 }  // namespace
@@ -191,6 +216,7 @@ struct bppp_rp {
     std::vector<Affine> pts;                   // h, g, then per kind
     Affine g;
     std::vector<uint8_t> table;                // [g | gs | hs] as bytes (device MSM base table)
+    std::vector<std::vector<Ph1>> ph1_tmpl;    // per range: the public part of its Phase-1 entries (shared digits)
     std::vector<uint8_t> in_pts;               // TRRP: [g, hs0, hs1]; Binary: [g, h0]
     bppp_fb* fb = nullptr;                     // fixed-base tables over in_pts        (lane 0)
     bppp_gens* gens = nullptr;                 // resident [g | gs | hs] with window tables (lane 0)
@@ -462,6 +488,7 @@ bool make_phase1s(int ind, const Range& rd, const uint8_t* val, bool prover, std
             Ph1 p;
             p.kind = 'S'; p.ind = ind; p.base = base_at(i);
             p.b = rd.coeffs_fr[i]; p.d = fr_small(ds[i]); p.m = h64::zero();
+            p.di = ds[i] < 2048 ? (int)ds[i] : -1;
             out.push_back(p);
         }
         has_ms = true;
@@ -475,6 +502,8 @@ bool make_phase1s(int ind, const Range& rd, const uint8_t* val, bool prover, std
         p.b = i < rd.coeffs.size() ? rd.coeffs_fr[i] : h64::zero();
         p.d = fr_small(i < ds.size() ? ds[i] : 0);
         p.m = fr_small(i < ms.size() ? ms[i] : 0);
+        p.m_zero = p.m.is_zero();
+        { U128 dv = i < ds.size() ? ds[i] : 0; p.di = dv < 2048 ? (int)dv : -1; }
         U128 sym = i < ns.size() ? ns[i] : 0;
         p.s = fr_small(sym);
         p.s_zero = (sym == 0);
@@ -493,36 +522,69 @@ std::vector<Ph2> make_phase2s(bool prover, const Fr& e, const Fr& e_inv, const F
                               const std::vector<Ph1>& ph1s) {
     size_t n = ph1s.size();
     std::vector<Ph2> out(n);
-    std::vector<Fr> ds(n, h64::zero()), ss(n, h64::zero()), ps(n), vs(n);
+    std::vector<Fr> ss(n, h64::zero()), vs(n);
     Fr x2 = h64::sqr(x);
     std::map<int, Fr> xpow;                      // x^(2(ind+1)) per range index
+    // reciprocals 1/(e + d): digits are small integers, so invert the distinct denominators once
+    // (batchInverse over all entries in the reference, TypedReciprocal.hs:194); entries whose
+    // denominator is not a small digit (types) are inverted individually.
+    int dmax = -1;
+    std::vector<size_t> slow;
+    std::vector<Fr> slow_den;
+    bool any_ss = false;
+    int last_ind = -1;
+    Fr last_xp = h64::zero();
+    U128 last_base = 0;
+    Fr last_v = h64::zero();
     for (size_t i = 0; i < n; i++) {
         const Ph1& p = ph1s[i];
-        auto it = xpow.find(p.ind);
-        if (it == xpow.end()) it = xpow.emplace(p.ind, fr_pow(x2, (uint64_t)p.ind + 1)).first;
-        const Fr& xp = it->second;
+        if (p.ind != last_ind) {
+            auto it = xpow.find(p.ind);
+            if (it == xpow.end()) it = xpow.emplace(p.ind, fr_pow(x2, (uint64_t)p.ind + 1)).first;
+            last_ind = p.ind;
+            last_xp = it->second;
+        }
+        const Fr& xp = last_xp;
         Ph2& o = out[i];
         if (p.kind == 'T') {
             Fr xpp = p.io ? h64::neg(x) : x;
-            if (prover) ds[i] = h64::add(e, p.d);
-            ps[i] = p.m;                                           // v
+            if (prover) { slow.push_back(i); slow_den.push_back(h64::add(e, p.d)); }
             o.isT = true; o.d = p.d; o.m = h64::zero(); o.u = p.ia ? h64::zero() : xp; o.v = xpp;
             vs[i] = xpp;
         } else {
-            Fr xpp = bm[p.base];
-            if (prover) ds[i] = h64::add(e, p.d);
-            if (p.kind == 'I' && !p.s_zero) ss[i] = h64::add(e, p.s);
-            ps[i] = h64::one();
+            if (p.base != last_base) { last_base = p.base; last_v = bm[p.base]; }
+            if (prover) {
+                if (p.di >= 0) dmax = std::max(dmax, p.di);
+                else { slow.push_back(i); slow_den.push_back(h64::add(e, p.d)); }
+            }
+            if (p.kind == 'I' && !p.s_zero) { ss[i] = h64::add(e, p.s); any_ss = true; }
             o.isT = false; o.d = p.d; o.m = (p.kind == 'I') ? p.m : h64::zero();
-            o.u = h64::mul(xp, p.b); o.v = xpp;
-            vs[i] = xpp;
+            o.m_zero = (p.kind != 'I') || p.m_zero;
+            o.di = p.di;
+            o.u = h64::mul(xp, p.b); o.v = last_v;
+            vs[i] = last_v;
         }
     }
-    if (prover) h64::batch_inv(ds.data(), n);
-    h64::batch_inv(ss.data(), n);
+    std::vector<Fr> tab;
+    if (prover) {
+        tab.resize(dmax + 1);
+        Fr cur = e;
+        const Fr one = h64::one();
+        for (int d = 0; d <= dmax; d++) { tab[d] = cur; cur = h64::add(cur, one); }
+        h64::batch_inv(tab.data(), tab.size());
+        h64::batch_inv(slow_den.data(), slow_den.size());
+    }
+    if (any_ss) h64::batch_inv(ss.data(), n);
     for (size_t i = 0; i < n; i++) {
-        out[i].r = prover ? h64::mul(ps[i], ds[i]) : h64::zero();
-        out[i].c = ss[i].is_zero() ? h64::zero() : h64::mul(vs[i], h64::sub(e_inv, ss[i]));
+        const Ph1& p = ph1s[i];
+        out[i].r = h64::zero();
+        if (prover && p.kind != 'T' && p.di >= 0) out[i].r = tab[p.di];            // ps = 1
+        out[i].c_zero = ss[i].is_zero();
+        out[i].c = out[i].c_zero ? h64::zero() : h64::mul(vs[i], h64::sub(e_inv, ss[i]));
+    }
+    for (size_t k = 0; k < slow.size(); k++) {
+        const Ph1& p = ph1s[slow[k]];
+        out[slow[k]].r = (p.kind == 'T') ? h64::mul(p.m, slow_den[k]) : slow_den[k];   // T: ps = v (the amount)
     }
     return out;
 }
@@ -541,21 +603,41 @@ std::vector<Fr> make_error_terms(const Fr& e, const Fr& xq, const std::vector<Fr
     for (size_t i = 0; i < shared_cs.size() && i < bls_ms.size(); i++) aug = h64::add(aug, h64::mul(shared_cs[i], bls_ms[i]));
     tot[3] = h64::dbl(aug);
     using namespace h64;
+    // the doubled parts are accumulated undoubled and doubled once at the end
+    Fr h1 = zero(), h2 = zero(), h3 = zero(), h4 = zero(), h5 = zero();
     for (size_t i = 0; i < ph2s.size() && i < q2s.size() && i < bls.size(); i++) {
         const Ph2& o = ph2s[i];
         const Fr& q2 = q2s[i];
         const Fr& bl = bls[i];
         Fr rC = o.isT ? mul(xq, add(o.u, q2)) : o.u;
-        Fr dC = add(o.v, mul(q2, e));
-        Fr qd = add(mul(q2, o.d), dC), qr = add(mul(q2, o.r), rC);
+        Fr q2e = mul(q2, e);
+        Fr dC = add(o.v, q2e);
+        Fr q2d = mul(q2, o.d), q2r = mul(q2, o.r);
+        Fr qd = add(q2d, dC), qr = add(q2r, rC);
         Fr q2bl = mul(q2, bl);
-        tot[0] = add(tot[0], mul(q2bl, bl));
-        tot[1] = add(tot[1], dbl(mul(q2bl, o.m)));
-        tot[2] = add(tot[2], add(mul(q2, sqr(o.m)), dbl(mul(bl, qd))));
-        tot[3] = add(tot[3], dbl(add(mul(bl, qr), mul(o.m, qd))));
-        tot[4] = add(tot[4], add(add(mul(q2, sqr(o.d)), dbl(mul(o.d, dC))), dbl(add(mul(bl, o.c), mul(o.m, qr)))));
-        tot[5] = add(tot[5], add(add(mul(q2, sqr(o.r)), dbl(mul(o.r, rC))), dbl(mul(o.c, o.d))));
+        tot[0] = add(tot[0], mul(q2bl, bl));                                   // err0 = q2 bl^2
+        h2 = add(h2, mul(bl, qd));                                             // err2 = q2 m^2 + 2 bl qd
+        h3 = add(h3, mul(bl, qr));                                             // err3 = 2 (bl qr + m qd)
+        // err4 = (q2 d^2 + 2 d dC) + 2 (bl c + m qr) = d (q2 d + 2 dC) + ...
+        tot[4] = add(tot[4], mul(o.d, add(q2d, dbl(dC))));
+        // err6 = (q2 r^2 + 2 r rC) + 2 c d = r (q2 r + 2 rC) + 2 c d
+        tot[5] = add(tot[5], mul(o.r, add(q2r, dbl(rC))));
+        if (!o.m_zero) {
+            h1 = add(h1, mul(q2bl, o.m));                                      // err1 = 2 q2 m bl
+            tot[2] = add(tot[2], mul(q2, sqr(o.m)));
+            h3 = add(h3, mul(o.m, qd));
+            h4 = add(h4, mul(o.m, qr));
+        }
+        if (!o.c_zero) {
+            h4 = add(h4, mul(bl, o.c));
+            h5 = add(h5, mul(o.c, o.d));
+        }
     }
+    tot[1] = add(tot[1], dbl(h1));
+    tot[2] = add(tot[2], dbl(h2));
+    tot[3] = add(tot[3], dbl(h3));
+    tot[4] = add(tot[4], dbl(h4));
+    tot[5] = add(tot[5], dbl(h5));
     return tot;
 }
 RPW make_public_consts_trrp(const bppp_rp* s, const Fr& e, const Fr& e_inv, const Fr& x, const Fr& xq, const Fr& q0,
@@ -580,18 +662,28 @@ RPW make_public_consts_trrp(const bppp_rp* s, const Fr& e, const Fr& e_inv, cons
         }
         z = sub(z, mul(mul(two_t5, x), sum));
     }
+    // p_i = t^2 (e + qi2 v) + t^3 rC + t^4 qi2 c  with rC = qi2 u (digits) or x'(qi2 u + 1) (types)
+    //     = const + qi2 * (t^2 v + t^3 u' + t^4 c),   u' = u or x' u,  const = t^2 e (+ t^3 x' for types)
+    // sum_i t^5 p2C_i = 2 t^5 (sum q2_i + eInv sum v_i) over the digit entries
     RPW out;
-    Fr q2 = q0, qi2 = q0_inv, ts0 = zero();
+    out.nrm.reserve(ph2s.size());
+    const Fr t2e = mul(t2, e), t3xq = mul(t3, xq), constT = add(t2e, t3xq);
+    Fr q2 = q0, qi2 = q0_inv, ts0 = zero(), sum_q2 = zero(), sum_v = zero();
+    Fr last_v = zero(), last_t2v = zero();
+    bool have_v = false;
     for (auto& o : ph2s) {
-        Fr rC, p2C;
-        if (o.isT) { rC = mul(xq, add(mul(qi2, o.u), one())); p2C = zero(); }
-        else { rC = mul(qi2, o.u); p2C = dbl(add(q2, mul(e_inv, o.v))); }
-        Fr p = add(add(mul(t2, add(e, mul(qi2, o.v))), mul(t3, rC)), mul(t4, mul(qi2, o.c)));
-        ts0 = add(ts0, add(mul(q2, sqr(p)), mul(t5, p2C)));
+        if (!have_v || !(o.v == last_v)) { last_v = o.v; last_t2v = mul(t2, o.v); have_v = true; }
+        Fr inner = last_t2v;
+        if (!o.u.is_zero()) inner = add(inner, mul(o.isT ? t3xq : t3, o.u));
+        if (!o.c_zero) inner = add(inner, mul(t4, o.c));
+        Fr p = add(o.isT ? constT : t2e, mul(qi2, inner));
+        ts0 = add(ts0, mul(q2, sqr(p)));
+        if (!o.isT) { sum_q2 = add(sum_q2, q2); sum_v = add(sum_v, o.v); }
         out.nrm.push_back(p);
         q2 = mul(q2, q0);
         qi2 = mul(qi2, q0_inv);
     }
+    ts0 = add(ts0, mul(two_t5, add(sum_q2, mul(e_inv, sum_v))));
     out.sc = add(z, ts0);
     return out;
 }
@@ -721,7 +813,9 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
             memcpy(xr, &X[64 * b], 64);
             memcpy(xr + 64, &R[64 * b], 64);
             Fr e;
+            Sect sect;
             P[b].zk.oracle(xr, 2, &e, 1);                           // e <- head <$> oracle [ac, bc]
+            sect.lap(S_ORACLE);
             h64::to_bytes(&E[32 * b], e);
             // responses are consed: newest first (Bulletproof.hs:357-359)
             memcpy(responses + 128 * (b * rounds + (rounds - 1 - r)), xr, 128);
@@ -739,6 +833,7 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
     bppp_nl_destroy(h);
     g_tm.lap("nl_final");
     g_tm.dump("prove");
+    if (t_lane_threads_is_main()) dump_sections("prove, all lanes", B);
     if (rc) return fail(s, rc, std::string("bppp_nl_final: ") + ctx_err(ln));
     for (size_t b = 0; b < B; b++) {       // getWitness: norm scalars then linear scalars (RangeProof.hs:65)
         memcpy(finals + 32 * b * (cn + cl), &fw[32 * b * cn], 32 * cn);
@@ -822,6 +917,19 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
     } else {
         s->prover_rounds = s->rounds; s->prover_fin_n = s->fin_n; s->prover_fin_l = s->fin_l;
     }
+    if (!s->binary)
+        for (size_t i = 0; i < s->rds.size(); i++) {
+            std::vector<Ph1> t;
+            const Range& rd = s->rds[i];
+            if (rd.is_shared && !rd.is_assumed)
+                for (size_t k = 0; k < rd.coeffs.size(); k++) {
+                    Ph1 p;
+                    p.kind = 'S'; p.ind = (int)i; p.base = (rd.has_bit && k == 0) ? (U128)2 : rd.base;
+                    p.b = rd.coeffs_fr[k]; p.d = p.m = p.s = h64::zero();
+                    t.push_back(p);
+                }
+            s->ph1_tmpl.push_back(t);
+        }
     finish_setup(s);
     int rc = bppp_fb_create(ctx, s->in_pts.size() / 64, s->in_pts.data(), &s->fb);
     if (rc) { delete s; return rc; }
@@ -906,6 +1014,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
     std::vector<uint8_t> sc1(B * (s->binary ? 1 : 2) * P0 * 32);
     parallel_for(B, [&](size_t b) {
         Proof& p = P[b];
+        Sect sect;
         p.zk.fmt = s->fmt;
         p.zk.seed = random_seeds[b];
         std::vector<Fr> vals(n), tys(n), bls(n);
@@ -962,7 +1071,34 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
         }
         std::vector<Ph1> digits_ph1;
         std::map<U128, std::vector<U128>> bm;                              // multiplicities summed as integers
+        digits_ph1.reserve(s->nrm_len);
         for (size_t i = 0; i < n; i++) {
+            const Range& rdi = s->rds[i];
+            if (rdi.is_shared && !rdi.is_assumed) {
+                // fast path of makePhase1s for shared digits: template entries + digits, multiplicities
+                // counted straight into the per-base integer arrays (baseMss, :363-367)
+                U128 left;
+                if (!adjust_value(rdi, values + 32 * (b * n + i), left)) { p.ok = false; bad++; return; }
+                const size_t off = digits_ph1.size();
+                digits_ph1.insert(digits_ph1.end(), s->ph1_tmpl[i].begin(), s->ph1_tmpl[i].end());
+                std::vector<U128>& arr = bm[rdi.base];
+                if (arr.empty()) arr.assign((size_t)rdi.base - 1, 0);
+                for (size_t k = 0; k < rdi.coeffs.size(); k++) {
+                    const bool bit = rdi.has_bit && k == 0;
+                    const U128 basek = bit ? (U128)2 : rdi.base, cf = rdi.coeffs[k];
+                    U128 d = cf ? std::min<U128>(basek - 1, left / cf) : (basek - 1);
+                    left -= d * cf;
+                    Ph1& e1 = digits_ph1[off + k];
+                    e1.d = fr_small(d);
+                    e1.di = d < 2048 ? (int)d : -1;
+                    if (bit) {
+                        std::vector<U128>& a2 = bm[2];
+                        if (a2.empty()) a2.assign(1, 0);
+                        a2[0] += d;
+                    } else if (d >= 1 && d < rdi.base) arr[(size_t)d - 1] += 1;
+                }
+                continue;
+            }
             bool has_ms;
             std::vector<U128> ms;
             if (!make_phase1s((int)i, s->rds[i], values + 32 * (b * n + i), true, digits_ph1, has_ms, ms)) { p.ok = false; bad++; return; }
@@ -987,6 +1123,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
                 p.ph1s.push_back(t);
             }
         p.ph1s.insert(p.ph1s.end(), digits_ph1.begin(), digits_ph1.end());
+        sect.lap(S_WITNESS);
         for (auto& kv : bm) {
             std::vector<Fr> v;
             for (auto m : kv.second) v.push_back(fr_small(m));
@@ -1003,10 +1140,13 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             h64::to_bytes(&in_sc[32 * ((b * n + i) * 3 + 1)], tys[i]);
             h64::to_bytes(&in_sc[32 * ((b * n + i) * 3 + 2)], bls[i]);
         }
+        sect.lap(S_TOBYTES);
         p.dm = blind_witness(p.zk, 3, 2, ms_shared, ds);
         p.m = blind_witness(p.zk, 3, 1, {}, ms_inline);
+        sect.lap(S_RANDOM);
         commit_scalars(s, p.dm, &sc1[32 * (2 * b) * P0]);
         commit_scalars(s, p.m, &sc1[32 * (2 * b + 1) * P0]);
+        sect.lap(S_SCALARS);
     });
     if (bad.load()) return fail(s, BPPP_ERR_RANGE, "invalid witness (out of range / unbalanced)");
     g_tm.lap("host_phase1");
@@ -1086,7 +1226,9 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             memcpy(out + 192, &c1[64 * (2 * b + 1)], 64);                   // mCom
             memcpy(out + 256, &n_coms[64 * b * n], 64 * n);
             Fr ch[3];
+            Sect sect;
             p.zk.oracle(out + 128, 2 + n, ch, 3);                           // T3 e x r0 <- oracle' (dmCom:mCom:nComs)
+            sect.lap(S_ORACLE);
             p.e = ch[0]; p.x = ch[1]; p.r0 = ch[2];
             Fr iv[2] = {p.e, p.r0};
             h64::batch_inv(iv, 2);
@@ -1097,8 +1239,11 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             std::vector<Fr> rs;
             for (auto& o : p.ph2s) { e7 = h64::add(e7, h64::dbl(h64::mul(o.r, o.c))); rs.push_back(o.r); }
             Fr err7 = h64::mul(p.r0_inv, h64::neg(e7));
+            sect.lap(S_PHASE2);
             p.r = blind_err_witness(p.zk, 3, {err7}, {}, rs);
+            sect.lap(S_RANDOM);
             commit_scalars(s, p.r, &sc2[32 * b * P0]);
+            sect.lap(S_SCALARS);
         });
         g_tm.lap("host_phase2");
         rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
@@ -1110,7 +1255,9 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             uint8_t* out = coms + 64 * b * NC;
             memcpy(out + 64, &c2[64 * b], 64);                              // rCom
             Fr ch[3];
+            Sect sect;
             p.zk.oracle(out + 64, 1, ch, 3);                                // T3 q x' r1 <- oracle' [rCom]
+            sect.lap(S_ORACLE);
             p.q = ch[0]; p.xq = ch[1]; p.r1 = ch[2];
             p.q0 = q0_of(s->arg, p.q);
             Fr iv[3] = {p.q, p.q0, p.r1};
@@ -1120,22 +1267,28 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             for (auto& kv : p.base_mss) mb.push_back(kv.first);
             p.shared_cs = make_shared_coeffs(p.e, p.e_inv, mb, p.base_map);
             Fr tC = s->flag ? p.xq : h64::zero();
+            sect.lap(S_COEFFS);
             p.bls_lin.clear(); p.bls_nrm.clear();
             for (size_t i = 0; i + 5 < M; i++) p.bls_lin.push_back(p.zk.random());
             for (size_t i = 0; i < N; i++) p.bls_nrm.push_back(p.zk.random());
+            sect.lap(S_RANDOM);
             std::vector<Fr> bls_ms(p.bls_lin.begin() + 1, p.bls_lin.end());
             std::vector<Fr> ic = input_coeffs_trrp(s, p.x, p.q0);
             RPW nsum;
             for (size_t i = 0; i < n; i++) rpw_add(nsum, rpw_scale(p.n_wits[i], ic[i]));
             Fr input_bl = nsum.lin.size() > 1 ? nsum.lin[1] : h64::zero();
             std::vector<Fr> q2s = q_powers(s->arg, p.q, p.ph2s.size());
+            sect.lap(S_COMBINE);
             std::vector<Fr> errs = make_error_terms(p.e, p.xq, p.shared_cs, bls_ms, p.ph2s, q2s, p.bls_nrm);
+            sect.lap(S_ERRTERMS);
             RPW blbl;
             blbl.lin = p.bls_lin; blbl.nrm = p.bls_nrm;
             std::vector<const RPW*> wits = {&p.m, &p.dm, &p.r};
             p.bl = blind_blinding_term(blbl, tC, p.r0, p.r0_inv, p.r1, p.r1_inv, errs, wits, input_bl);
             p.wit = nsum;                                                    // parked: nWitSum
+            sect.lap(S_BLIND);
             commit_scalars(s, p.bl, &sc2[32 * b * P0]);
+            sect.lap(S_SCALARS);
         });
         g_tm.lap("host_phase3");
         rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
@@ -1146,8 +1299,11 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             Proof& p = P[b];
             uint8_t* out = coms + 64 * b * NC;
             memcpy(out, &c2[64 * b], 64);                                   // blCom
+            Sect sect;
             p.zk.oracle(out, 1, &p.t, 1);
+            sect.lap(S_ORACLE);
             p.pub = make_public_consts_trrp(s, p.e, p.e_inv, p.x, p.xq, p.q0, p.q0_inv, p.t, p.ph2s);
+            sect.lap(S_PUB);
             Fr t2 = h64::sqr(p.t), t3 = h64::mul(t2, p.t), t5 = h64::mul(h64::sqr(t2), p.t);
             RPW nsum = p.wit;
             RPW wit = p.pub;
@@ -1157,11 +1313,13 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             rpw_add(wit, rpw_scale(p.r, t3));
             rpw_add(wit, rpw_scale(nsum, h64::dbl(t5)));
             p.cs = make_bp_coeffs(s->flag, p.xq, p.r0, p.r1, p.t, p.shared_cs);
+            sect.lap(S_COMBINE);
             h64::to_bytes(&q_b[32 * b], p.q);
             h64::to_bytes(&sc_b[32 * b], wit.sc);
             for (size_t i = 0; i < wit.nrm.size() && i < N; i++) h64::to_bytes(&w_b[32 * (b * N + i)], wit.nrm[i]);
             for (size_t i = 0; i < wit.lin.size() && i < M; i++) h64::to_bytes(&l_b[32 * (b * M + i)], wit.lin[i]);
             for (size_t i = 0; i < p.cs.size() && i < M; i++) h64::to_bytes(&c_b[32 * (b * M + i)], p.cs[i]);
+            sect.lap(S_TOBYTES);
         });
     }
     g_tm.lap("host_phase4");
@@ -1181,6 +1339,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
     g_tm.start();
     parallel_for(B, [&](size_t b) {
         tr::Zkpt zk;
+        Sect sect;
         zk.fmt = s->fmt;
         zk.no_random = true;
         const uint8_t* cm = coms + 64 * b * NC;
@@ -1213,12 +1372,15 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             Fr xq = ch2[1], r1 = ch2[2];
             Fr q0 = q0_of(s->arg, q);
             zk.oracle(cm, 1, &t, 1);
+            sect.lap(S_V_ORACLE);
             Fr iv[3] = {e, q, q0};
             h64::batch_inv(iv, 3);
             Fr e_inv = iv[0], q0_inv = iv[2];
             std::map<U128, Fr> bm = make_base_map(s, x);
             std::vector<Ph2> ph2s = make_phase2s(false, e, e_inv, x, bm, ph1v);
+            sect.lap(S_V_PHASE2);
             pub = make_public_consts_trrp(s, e, e_inv, x, xq, q0, q0_inv, t, ph2s);
+            sect.lap(S_V_PUB);
             cs = make_bp_coeffs(s->flag, xq, r0, r1, t, make_shared_coeffs(e, e_inv, s->m_bases, bm));
             // TranscriptTRRP.openWith (TypedReciprocal.hs:279-282): [1,t,t^2,t^3] on [bl,m,dm,r]
             Fr t2 = h64::sqr(t), t3 = h64::mul(t2, t), t5 = h64::mul(h64::sqr(t2), t);
@@ -1226,6 +1388,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             Fr two_t5 = h64::dbl(t5);
             for (auto& c : input_coeffs_trrp(s, x, q0)) init_s.push_back(h64::mul(two_t5, c));
         }
+        sect.lap(S_V_MISC);
         // challenges of the argument: oldest round hashed first, list newest first (Bulletproof.hs:374)
         for (size_t r = 0; r < k; r++) {
             size_t idx = k - 1 - r;                                         // oldest round sits last
@@ -1233,6 +1396,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             zk.oracle(responses + 128 * (b * k + idx), 2, &e, 1);
             h64::to_bytes(&es_b[32 * (b * k + idx)], e);
         }
+        sect.lap(S_V_ORACLE);
         h64::to_bytes(&q_b[32 * b], q);
         h64::to_bytes(&sp_b[32 * b], pub.sc);
         for (size_t i = 0; i < pub.nrm.size() && i < N; i++) h64::to_bytes(&pw_b[32 * (b * N + i)], pub.nrm[i]);
@@ -1241,12 +1405,14 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         memcpy(&ip_b[64 * b * NC], cm, 64 * NC);
         memcpy(&fw_b[32 * b * n_norm], finals + 32 * b * (n_norm + n_lin), 32 * n_norm);
         memcpy(&fl_b[32 * b * n_lin], finals + 32 * (b * (n_norm + n_lin) + n_norm), 32 * n_lin);
+        sect.lap(S_TOBYTES);
     });
     g_tm.lap("verify_host");
     int rc = bppp_nl_verify_gens(ln.gens, s->arg, B, k, q_b.data(), sp_b.data(), pw_b.data(), c_b.data(), es_b.data(), responses,
                                  n_norm, n_lin, fw_b.data(), fl_b.data(), NC, is_b.data(), ip_b.data(), ok);
     g_tm.lap("nl_verify");
     g_tm.dump("verify");
+    if (t_lane_threads_is_main()) dump_sections("verify, all lanes", B);
     if (rc) return fail(s, rc, std::string("bppp_nl_verify: ") + ctx_err(ln));
     return BPPP_OK;
 }
