@@ -324,6 +324,15 @@ extern "C" void bppp_free(bppp_ctx* ctx) {
     delete ctx;
 }
 extern "C" int bppp_ctx_device(bppp_ctx* ctx) { return ctx ? ctx->dev : -1; }
+// page-locked host staging memory (async H2D/D2H at full PCIe speed); caller frees with bppp_pinned_free
+extern "C" int bppp_pinned_alloc(size_t bytes, void** out) {
+    if (!out) return BPPP_ERR_ARG;
+    *out = nullptr;
+    return cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable) == cudaSuccess ? BPPP_OK : BPPP_ERR_CUDA;
+}
+extern "C" void bppp_pinned_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
 extern "C" const char* bppp_last_error(bppp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" uint64_t bppp_launch_count(bppp_ctx* ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int bppp_sync(bppp_ctx* ctx) {

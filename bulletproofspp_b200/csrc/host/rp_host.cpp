@@ -95,7 +95,9 @@ int n_threads() {
 std::mutex g_cpu_turn;
 template <class F>
 void parallel_for(size_t n, F fn) {
-    std::lock_guard<std::mutex> turn(g_cpu_turn);
+    static const bool turns = !(getenv("BPPP_CPU_TURNS") && atoi(getenv("BPPP_CPU_TURNS")) == 0);
+    std::unique_lock<std::mutex> turn(g_cpu_turn, std::defer_lock);
+    if (turns) turn.lock();
     int nt = (int)std::min<size_t>(n, (size_t)n_threads());
     if (nt <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);
@@ -222,6 +224,9 @@ struct bppp_rp {
     bppp_gens* gens = nullptr;                 // resident [g | gs | hs] with window tables (lane 0)
     // extra lanes: sub-batches of one call run concurrently, each on its own context (stream) and
     // driver thread, so the host phases of one lane overlap the device work of another
+    // page-locked staging buffers, one set per lane, grown on demand and reused across calls
+    struct Pinned { void* p = nullptr; size_t cap = 0; };
+    std::vector<std::vector<Pinned>> pinned;
     std::vector<bppp_ctx*> lane_ctx;
     std::vector<bppp_fb*> lane_fb;
     std::vector<bppp_gens*> lane_gens;
@@ -789,23 +794,41 @@ struct Lane {
     bppp_fb* fb;
     bppp_gens* gens;
     int threads;                               // host threads this lane may use
+    int index;                                 // which set of staging buffers
 };
+enum { PB_IN = 0, PB_SC1, PB_SC2, PB_C1, PB_C2, PB_NCOMS, PB_Q, PB_S, PB_W, PB_L, PB_C, PB_X, PB_R, PB_E, PB_V0, PB_V1, PB_V2, PB_V3,
+       PB_V4, PB_V5, PB_V6, PB_V7, PB_V8, PB_COUNT };
+// uninitialised page-locked buffer `slot` of the lane, at least `bytes` long
+uint8_t* lane_buf(bppp_rp* s, const Lane& ln, int slot, size_t bytes) {
+    auto& pb = s->pinned[ln.index][slot];
+    if (pb.cap < bytes) {
+        bppp_pinned_free(pb.p);
+        pb.p = nullptr;
+        pb.cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        if (bppp_pinned_alloc(want, &pb.p)) { pb.p = malloc(want); }     // fall back to pageable memory
+        pb.cap = want;
+    }
+    return (uint8_t*)pb.p;
+}
 thread_local int t_lane_threads = 0;
 thread_local bool t_is_lane0 = true;
 const char* ctx_err(const Lane& ln) { return bppp_last_error(ln.ctx); }
 
 // run the argument (proveBPM, src/Bulletproof.hs:357-359) for the whole batch
-int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t rounds, const std::vector<uint8_t>& q, const std::vector<uint8_t>& sc,
-                 const std::vector<uint8_t>& w, const std::vector<uint8_t>& l, const std::vector<uint8_t>& c,
+int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t rounds, const uint8_t* q, const uint8_t* sc,
+                 const uint8_t* w, const uint8_t* l, const uint8_t* c,
                  uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l) {
     const size_t B = P.size(), N = s->nrm_len, M = s->lin_len;
     bppp_nl* h = nullptr;
-    int rc = bppp_nl_create_gens(ln.gens, s->arg, B, q.data(), sc.data(), w.data(), l.data(), c.data(), &h);
+    int rc = bppp_nl_create_gens(ln.gens, s->arg, B, q, sc, w, l, c, &h);
     if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(ln));
-    std::vector<uint8_t> X(B * 64), R(B * 64), E(B * 32);
+    uint8_t* X = lane_buf(s, ln, PB_X, B * 64);
+    uint8_t* R = lane_buf(s, ln, PB_R, B * 64);
+    uint8_t* E = lane_buf(s, ln, PB_E, B * 32);
     g_tm.lap("nl_create");
     for (size_t r = 0; r < rounds; r++) {
-        rc = bppp_nl_round_commit(h, X.data(), R.data());
+        rc = bppp_nl_round_commit(h, X, R);
         g_tm.lap("nl_commit");
         if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_commit: ") + ctx_err(ln)); }
         parallel_for(B, [&](size_t b) {
@@ -821,7 +844,7 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
             memcpy(responses + 128 * (b * rounds + (rounds - 1 - r)), xr, 128);
         });
         g_tm.lap("round_hash");
-        rc = bppp_nl_round_fold(h, E.data());
+        rc = bppp_nl_round_fold(h, E);
         g_tm.lap("nl_fold");
         if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_fold: ") + ctx_err(ln)); }
     }
@@ -960,6 +983,8 @@ void bppp_rp_free(bppp_rp* s) {
     if (!s) return;
     bppp_fb_destroy(s->fb);
     bppp_gens_destroy(s->gens);
+    for (auto& lane : s->pinned)
+        for (auto& pb : lane) bppp_pinned_free(pb.p);
     for (size_t i = 0; i < s->lane_ctx.size(); i++) {
         bppp_fb_destroy(s->lane_fb[i]);
         bppp_gens_destroy(s->lane_gens[i]);
@@ -1009,9 +1034,9 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
     std::atomic<int> bad(0);
     g_tm.start();
     const size_t in_terms = s->binary ? 2 : 3;
-    std::vector<uint8_t> in_sc(B * n * in_terms * 32);
+    uint8_t* in_sc = lane_buf(s, ln, PB_IN, B * n * in_terms * 32);
     // ---------------- phase 1 (host): witnesses, input openings, digit commitments
-    std::vector<uint8_t> sc1(B * (s->binary ? 1 : 2) * P0 * 32);
+    uint8_t* sc1 = lane_buf(s, ln, PB_SC1, B * (s->binary ? 1 : 2) * P0 * 32);
     parallel_for(B, [&](size_t b) {
         Proof& p = P[b];
         Sect sect;
@@ -1151,17 +1176,23 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
     if (bad.load()) return fail(s, BPPP_ERR_RANGE, "invalid witness (out of range / unbalanced)");
     g_tm.lap("host_phase1");
     // ---------------- device: input commitments + digit commitments
-    std::vector<uint8_t> n_coms(B * n * 64), c1(B * (s->binary ? 1 : 2) * 64);
+    uint8_t* n_coms = lane_buf(s, ln, PB_NCOMS, B * n * 64);
+    uint8_t* c1 = lane_buf(s, ln, PB_C1, B * (s->binary ? 1 : 2) * 64);
     int rc;
     if (n) {
-        rc = bppp_fb_msm_batch(ln.fb, B * n, in_sc.data(), n_coms.data());
+        rc = bppp_fb_msm_batch(ln.fb, B * n, in_sc, n_coms);
         if (rc) return fail(s, rc, std::string("input commitments: ") + ctx_err(ln));
     }
-    rc = bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1.data(), c1.data());
+    rc = bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1, c1);
     if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(ln));
     g_tm.lap("msm_phase1");
-    std::vector<uint8_t> q_b(B * 32), sc_b(B * 32), w_b(B * N * 32, 0), l_b(B * M * 32, 0), c_b(B * M * 32, 0);
-    std::vector<uint8_t> sc2(B * P0 * 32), c2(B * 64);
+    uint8_t* q_b = lane_buf(s, ln, PB_Q, B * 32);
+    uint8_t* sc_b = lane_buf(s, ln, PB_S, B * 32);
+    uint8_t* w_b = lane_buf(s, ln, PB_W, B * N * 32);
+    uint8_t* l_b = lane_buf(s, ln, PB_L, B * M * 32);
+    uint8_t* c_b = lane_buf(s, ln, PB_C, B * M * 32);
+    uint8_t* sc2 = lane_buf(s, ln, PB_SC2, B * P0 * 32);
+    uint8_t* c2 = lane_buf(s, ln, PB_C2, B * 64);
 
     if (s->binary) {
         // ---------------- proveBRPM (Binary.hs:171-203)
@@ -1193,7 +1224,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             p.bl.nrm = p.bls_nrm;
             commit_scalars(s, p.bl, &sc2[32 * b * P0]);
         });
-        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
+        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2, c2);
         if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(ln));
         parallel_for(B, [&](size_t b) {
             Proof& p = P[b];
@@ -1211,6 +1242,9 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             rpw_add(w1, rpw_scale(nsum, h64::dbl(p.t)));
             RPW wit = p.bl;
             rpw_add(wit, rpw_scale(w1, p.t));
+            memset(&w_b[32 * b * N], 0, 32 * N);
+            memset(&l_b[32 * b * M], 0, 32 * M);
+            memset(&c_b[32 * b * M], 0, 32 * M);
             h64::to_bytes(&q_b[32 * b], p.q);
             h64::to_bytes(&sc_b[32 * b], wit.sc);
             for (size_t i = 0; i < wit.nrm.size() && i < N; i++) h64::to_bytes(&w_b[32 * (b * N + i)], wit.nrm[i]);
@@ -1246,7 +1280,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             sect.lap(S_SCALARS);
         });
         g_tm.lap("host_phase2");
-        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
+        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2, c2);
         if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(ln));
         g_tm.lap("msm_phase2");
         // ---------------- phase 3 (TypedReciprocal.hs:421-434)
@@ -1291,7 +1325,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             sect.lap(S_SCALARS);
         });
         g_tm.lap("host_phase3");
-        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2.data(), c2.data());
+        rc = bppp_gens_msm_batch(ln.gens, B, P0, sc2, c2);
         if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(ln));
         g_tm.lap("msm_phase3");
         // ---------------- phase 4 (TypedReciprocal.hs:435-444)
@@ -1314,6 +1348,9 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             rpw_add(wit, rpw_scale(nsum, h64::dbl(t5)));
             p.cs = make_bp_coeffs(s->flag, p.xq, p.r0, p.r1, p.t, p.shared_cs);
             sect.lap(S_COMBINE);
+            memset(&w_b[32 * b * N], 0, 32 * N);
+            memset(&l_b[32 * b * M], 0, 32 * M);
+            memset(&c_b[32 * b * M], 0, 32 * M);
             h64::to_bytes(&q_b[32 * b], p.q);
             h64::to_bytes(&sc_b[32 * b], wit.sc);
             for (size_t i = 0; i < wit.nrm.size() && i < N; i++) h64::to_bytes(&w_b[32 * (b * N + i)], wit.nrm[i]);
@@ -1332,8 +1369,15 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
 static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
                        const uint8_t* responses, const uint8_t* finals, int* ok) {
     const size_t B = batch, n = s->n_inputs, N = s->nrm_len, M = s->lin_len, NC = s->num_rp_coms + n, k = rounds;
-    std::vector<uint8_t> q_b(B * 32), sp_b(B * 32), pw_b(B * N * 32, 0), c_b(B * M * 32, 0), es_b(B * k * 32);
-    std::vector<uint8_t> fw_b(B * n_norm * 32), fl_b(B * n_lin * 32), is_b(B * NC * 32), ip_b(B * NC * 64);
+    uint8_t* q_b = lane_buf(s, ln, PB_V0, B * 32);
+    uint8_t* sp_b = lane_buf(s, ln, PB_V1, B * 32);
+    uint8_t* pw_b = lane_buf(s, ln, PB_V2, B * N * 32);
+    uint8_t* c_b = lane_buf(s, ln, PB_V3, B * M * 32);
+    uint8_t* es_b = lane_buf(s, ln, PB_V4, B * k * 32);
+    uint8_t* fw_b = lane_buf(s, ln, PB_V5, B * n_norm * 32);
+    uint8_t* fl_b = lane_buf(s, ln, PB_V6, B * n_lin * 32);
+    uint8_t* is_b = lane_buf(s, ln, PB_V7, B * NC * 32);
+    uint8_t* ip_b = lane_buf(s, ln, PB_V8, B * NC * 64);
     std::vector<Ph1> ph1v;
     if (!s->binary) ph1v = ph1s_verifier(s);
     g_tm.start();
@@ -1397,6 +1441,8 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             h64::to_bytes(&es_b[32 * (b * k + idx)], e);
         }
         sect.lap(S_V_ORACLE);
+        memset(&pw_b[32 * b * N], 0, 32 * N);
+        memset(&c_b[32 * b * M], 0, 32 * M);
         h64::to_bytes(&q_b[32 * b], q);
         h64::to_bytes(&sp_b[32 * b], pub.sc);
         for (size_t i = 0; i < pub.nrm.size() && i < N; i++) h64::to_bytes(&pw_b[32 * (b * N + i)], pub.nrm[i]);
@@ -1408,8 +1454,8 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         sect.lap(S_TOBYTES);
     });
     g_tm.lap("verify_host");
-    int rc = bppp_nl_verify_gens(ln.gens, s->arg, B, k, q_b.data(), sp_b.data(), pw_b.data(), c_b.data(), es_b.data(), responses,
-                                 n_norm, n_lin, fw_b.data(), fl_b.data(), NC, is_b.data(), ip_b.data(), ok);
+    int rc = bppp_nl_verify_gens(ln.gens, s->arg, B, k, q_b, sp_b, pw_b, c_b, es_b, responses,
+                                 n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, ok);
     g_tm.lap("nl_verify");
     g_tm.dump("verify");
     if (t_lane_threads_is_main()) dump_sections("verify, all lanes", B);
@@ -1421,8 +1467,9 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
 namespace {
 std::vector<Lane> make_lanes(bppp_rp* s, size_t batch) {
     std::vector<Lane> L;
-    L.push_back({s->ctx, s->fb, s->gens, 0});
-    for (size_t i = 0; i < s->lane_ctx.size(); i++) L.push_back({s->lane_ctx[i], s->lane_fb[i], s->lane_gens[i], 0});
+    L.push_back({s->ctx, s->fb, s->gens, 0, 0});
+    for (size_t i = 0; i < s->lane_ctx.size(); i++) L.push_back({s->lane_ctx[i], s->lane_fb[i], s->lane_gens[i], 0, (int)i + 1});
+    if (s->pinned.size() < L.size()) s->pinned.resize(L.size(), std::vector<bppp_rp::Pinned>(PB_COUNT));
     size_t want = std::max<size_t>(1, std::min(L.size(), batch / 32));      // tiny batches: one lane
     L.resize(want);
     int total = g_threads > 0 ? g_threads : (int)std::thread::hardware_concurrency();

@@ -20,7 +20,7 @@ EXPORTS = [
     "bppp_profile_enable", "bppp_profile_reset", "bppp_profile_report", "bppp_timer_start", "bppp_timer_stop",
     "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
-    "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts",
+    "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free",
 ]
 
 
@@ -83,6 +83,9 @@ def load_library():
                                         C.POINTER(ip)]
     lib.bppp_rp_contexts.argtypes = [vp, C.POINTER(vp), sz, C.POINTER(sz)]
     lib.bppp_ctx_device.argtypes = [vp]
+    lib.bppp_pinned_alloc.argtypes = [sz, C.POINTER(vp)]
+    lib.bppp_pinned_free.argtypes = [vp]
+    lib.bppp_pinned_free.restype = None
     lib.bppp_fb_create.argtypes = [vp, sz, u8p, C.POINTER(vp)]
     lib.bppp_fb_msm_batch.argtypes = [vp, sz, u8p, u8p]
     lib.bppp_fb_destroy.argtypes = [vp]

@@ -73,6 +73,9 @@ int bppp_gens_msm_batch(bppp_gens* g, size_t batch, size_t n, const uint8_t* sca
 void bppp_set_device_host_threads(int n);
 void bppp_set_thread_host_threads(int n);   /* same, for the calling thread only */
 int bppp_ctx_device(bppp_ctx* ctx);
+/* page-locked host staging memory for the in/out buffers of the batch entry points */
+int bppp_pinned_alloc(size_t bytes, void** out);
+void bppp_pinned_free(void* p);
 
 /* ---- fixed-base MSMs over a handful of generators shared by every call: the range proofs'
  * input commitments value*g + type*hs0 + blind*hs1 (scalarRPW' / scalarPairRPW' + commitRPW,
