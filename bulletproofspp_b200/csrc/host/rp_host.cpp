@@ -29,6 +29,7 @@
 
 #include "../../../include/bppp_b200.h"
 #include "transcript.hpp"
+#include "../host_math.hpp"
 
 using namespace bppp;
 using h64::Fr;
@@ -1535,6 +1536,119 @@ int bppp_rp_contexts(bppp_rp* s, bppp_ctx** out, size_t cap, size_t* count) {
         out[0] = s->ctx;
         for (size_t i = 0; i < s->lane_ctx.size(); i++) out[1 + i] = s->lane_ctx[i];
     }
+    return BPPP_OK;
+}
+
+// ---- wire format (src/Encoding.hs:75-134, src/RangeProof.hs:60-85)
+namespace {
+void put_field_be(uint8_t* out, const uint8_t le[32]) {          // four big-endian Word64, least significant word first
+    for (int w = 0; w < 4; w++)
+        for (int k = 0; k < 8; k++) out[8 * w + k] = le[8 * w + 7 - k];
+}
+bool y_is_larger(const uint8_t y_le[32]) {                        // y > q - y  (getXAndSign, Encoding.hs:117-122)
+    u256 y = host::from_bytes(y_le), ny = fq::neg(y);
+    return !u256_geq(ny, y);
+}
+size_t put_commitments(uint8_t* out, const uint8_t* const* pts, size_t n) {
+    size_t ns = (n + 7) / 8;
+    memset(out, 0, ns);
+    for (size_t i = 0; i < n; i++) {
+        if (y_is_larger(pts[i] + 32)) out[i / 8] |= (uint8_t)(1u << (i % 8));
+        put_field_be(out + ns + 32 * i, pts[i]);
+    }
+    return ns + 32 * n;
+}
+}  // namespace
+
+// size in bytes of proof.bin / commits.bin for this setup
+int bppp_rp_encoded_sizes(bppp_rp* s, size_t* proof_bytes, size_t* commits_bytes) {
+    if (!s) return BPPP_ERR_ARG;
+    size_t npts = s->num_rp_coms + 2 * s->prover_rounds, nsc = s->prover_fin_n + s->prover_fin_l;
+    if (proof_bytes) *proof_bytes = 32 * nsc + (npts + 7) / 8 + 32 * npts;
+    if (commits_bytes) *commits_bytes = (s->n_inputs + 7) / 8 + 32 * s->n_inputs;
+    return BPPP_OK;
+}
+// encodeProof' (src/RangeProof.hs:60-66): proof.bin = scalars ++ signs ++ xs of (rpComs ++ bpComs),
+// commits.bin = signs ++ xs of the input commitments.  Inputs in the layout of bppp_rp_prove_batch.
+int bppp_rp_encode_batch(bppp_rp* s, size_t batch, const uint8_t* coms, const uint8_t* responses, const uint8_t* finals,
+                         uint8_t* proof_bin, uint8_t* commits_bin) {
+    if (!s || !coms || !responses || !finals || !proof_bin || !commits_bin) return BPPP_ERR_ARG;
+    const size_t n = s->n_inputs, k = s->num_rp_coms, NC = k + n, rounds = s->prover_rounds;
+    const size_t nsc = s->prover_fin_n + s->prover_fin_l, npts = k + 2 * rounds;
+    size_t pb, cb;
+    bppp_rp_encoded_sizes(s, &pb, &cb);
+    parallel_for(batch, [&](size_t b) {
+        uint8_t* out = proof_bin + b * pb;
+        for (size_t i = 0; i < nsc; i++) put_field_be(out + 32 * i, finals + 32 * (b * nsc + i));
+        std::vector<const uint8_t*> pts;
+        for (size_t i = 0; i < k; i++) pts.push_back(coms + 64 * (b * NC + i));
+        for (size_t i = 0; i < 2 * rounds; i++) pts.push_back(responses + 64 * (b * 2 * rounds + i));
+        put_commitments(out + 32 * nsc, pts.data(), npts);
+        pts.clear();
+        for (size_t i = 0; i < n; i++) pts.push_back(coms + 64 * (b * NC + k + i));
+        put_commitments(commits_bin + b * cb, pts.data(), n);
+    });
+    return BPPP_OK;
+}
+// decodeProof' (src/RangeProof.hs:68-85) + decodeCommitments / fromXWithSign (Encoding.hs:97-128):
+// x-only points are decompressed with one Fq square root each (host; batchable on the device later).
+// ok[b] = 0 when some x is not on the curve or a scalar is not canonical.
+int bppp_rp_decode_batch(bppp_rp* s, size_t batch, const uint8_t* proof_bin, const uint8_t* commits_bin, uint8_t* coms,
+                         uint8_t* responses, uint8_t* finals, int* ok) {
+    if (!s || !proof_bin || !commits_bin || !coms || !responses || !finals || !ok) return BPPP_ERR_ARG;
+    const size_t n = s->n_inputs, k = s->num_rp_coms, NC = k + n, rounds = s->prover_rounds;
+    const size_t nsc = s->prover_fin_n + s->prover_fin_l, npts = k + 2 * rounds;
+    size_t pb, cb;
+    bppp_rp_encoded_sizes(s, &pb, &cb);
+    u256 e4 = fq::modulus();                                       // (q + 1) / 4
+    {
+        u256 t;
+        u256_add(t, e4, u256_one());
+        for (int i = 0; i < 8; i++) e4.v[i] = (t.v[i] >> 2) | (i < 7 ? t.v[i + 1] << 30 : 0);
+    }
+    auto get_field = [](const uint8_t* in, uint8_t le[32]) {
+        for (int w = 0; w < 4; w++)
+            for (int kk = 0; kk < 8; kk++) le[8 * w + 7 - kk] = in[8 * w + kk];
+    };
+    auto decompress = [&](const uint8_t* xin, bool larger, uint8_t* out) -> bool {
+        uint8_t le[32];
+        get_field(xin, le);
+        u256 x = host::from_bytes(le);
+        x = fq::cond_sub(x, 0);                                    // toP
+        u256 seven = u256_zero();
+        seven.v[0] = 7;
+        u256 rhs = fq::add(fq::mul(fq::sqr(x), x), seven), y = u256_one();
+        for (int i = 255; i >= 0; i--) { y = fq::sqr(y); if (u256_bit(e4, i)) y = fq::mul(y, rhs); }
+        if (!u256_eq(fq::sqr(y), rhs)) return false;
+        u256 ny = fq::neg(y);
+        bool y_larger = !u256_geq(ny, y);
+        if (y_larger != larger) y = ny;
+        host::to_bytes(out, x);
+        host::to_bytes(out + 32, y);
+        return true;
+    };
+    parallel_for(batch, [&](size_t b) {
+        const uint8_t* in = proof_bin + b * pb;
+        bool good = true;
+        for (size_t i = 0; i < nsc; i++) {
+            uint8_t le[32];
+            get_field(in + 32 * i, le);
+            uint64_t c[4];
+            memcpy(c, le, 32);
+            h64::Fr v = h64::from_wide(c);                          // toP (mod r)
+            h64::to_bytes(finals + 32 * (b * nsc + i), v);
+        }
+        const uint8_t* sg = in + 32 * nsc;
+        const uint8_t* xs = sg + (npts + 7) / 8;
+        for (size_t i = 0; i < npts; i++) {
+            uint8_t* dst = i < k ? coms + 64 * (b * NC + i) : responses + 64 * (b * 2 * rounds + (i - k));
+            good &= decompress(xs + 32 * i, (sg[i / 8] >> (i % 8)) & 1, dst);
+        }
+        const uint8_t* cs = commits_bin + b * cb;
+        const uint8_t* cx = cs + (n + 7) / 8;
+        for (size_t i = 0; i < n; i++) good &= decompress(cx + 32 * i, (cs[i / 8] >> (i % 8)) & 1, coms + 64 * (b * NC + k + i));
+        ok[b] = good ? 1 : 0;
+    });
     return BPPP_OK;
 }
 

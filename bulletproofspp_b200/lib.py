@@ -20,7 +20,7 @@ EXPORTS = [
     "bppp_profile_enable", "bppp_profile_reset", "bppp_profile_report", "bppp_timer_start", "bppp_timer_stop",
     "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
-    "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free",
+    "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free", "bppp_rp_encoded_sizes", "bppp_rp_encode_batch", "bppp_rp_decode_batch",
 ]
 
 
@@ -83,6 +83,9 @@ def load_library():
                                         C.POINTER(ip)]
     lib.bppp_rp_contexts.argtypes = [vp, C.POINTER(vp), sz, C.POINTER(sz)]
     lib.bppp_ctx_device.argtypes = [vp]
+    lib.bppp_rp_encoded_sizes.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
+    lib.bppp_rp_encode_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p, u8p]
+    lib.bppp_rp_decode_batch.argtypes = [vp, sz, u8p, u8p, u8p, u8p, u8p, C.POINTER(ip)]
     lib.bppp_pinned_alloc.argtypes = [sz, C.POINTER(vp)]
     lib.bppp_pinned_free.argtypes = [vp]
     lib.bppp_pinned_free.restype = None
@@ -487,6 +490,22 @@ class RangeProofSetup:
             out.append(dict(coms=cs, responses=[(rp[2 * i], rp[2 * i + 1]) for i in range(k)],
                             finals=bytes_to_ints(fin[32 * b * nf:32 * (b + 1) * nf])))
         return out
+
+    def encode_batch_raw(self, batch, coms, resp, fin):
+        """-> (proof.bin images, commits.bin images), one fixed-size record per proof (encodeProof')"""
+        pb, cb = C.c_size_t(), C.c_size_t()
+        self.ctx.lib.bppp_rp_encoded_sizes(self.h, C.byref(pb), C.byref(cb))
+        po, co = _buf(pb.value * batch), _buf(cb.value * batch)
+        self._ck(self.ctx.lib.bppp_rp_encode_batch(self.h, batch, coms, resp, fin, po, co), "bppp_rp_encode_batch")
+        return po.raw[:pb.value * batch], co.raw[:cb.value * batch], pb.value, cb.value
+
+    def decode_batch_raw(self, batch, proof_bin, commits_bin):
+        """decodeProof': -> (coms, responses, finals, ok[])"""
+        nc, k, nf = self.num_rp_coms + self.n_inputs, self.rounds, self.fin_norm + self.fin_lin
+        coms, resp, fin = _buf(64 * batch * nc), _buf(128 * batch * k), _buf(32 * batch * nf)
+        ok = (C.c_int * batch)()
+        self._ck(self.ctx.lib.bppp_rp_decode_batch(self.h, batch, proof_bin, commits_bin, coms, resp, fin, ok), "bppp_rp_decode_batch")
+        return coms.raw[:64 * batch * nc], resp.raw[:128 * batch * k], fin.raw[:32 * batch * nf], [bool(v) for v in ok]
 
     def verify_batch_raw(self, batch, coms, resp, fin, rounds=None, n_norm=None, n_lin=None):
         ok = (C.c_int * batch)()

@@ -175,6 +175,13 @@ int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const u
 /* RangeProof.verifyM for `batch` proofs */
 int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
                          const uint8_t* responses, const uint8_t* finals, int* ok);
+/* wire format: encodeProof' / decodeProof' (src/RangeProof.hs:60-85) over encodeScalarsCurvePoints /
+ * decodeCommitments (src/Encoding.hs:75-134): proof.bin and commits.bin images per proof */
+int bppp_rp_encoded_sizes(bppp_rp* s, size_t* proof_bytes, size_t* commits_bytes);
+int bppp_rp_encode_batch(bppp_rp* s, size_t batch, const uint8_t* coms, const uint8_t* responses, const uint8_t* finals,
+                         uint8_t* proof_bin, uint8_t* commits_bin);
+int bppp_rp_decode_batch(bppp_rp* s, size_t batch, const uint8_t* proof_bin, const uint8_t* commits_bin, uint8_t* coms,
+                         uint8_t* responses, uint8_t* finals, int* ok);
 /* contexts of the concurrent lanes a setup runs its sub-batches on (BPPP_LANES, default 8) */
 int bppp_rp_contexts(bppp_rp* s, bppp_ctx** out, size_t cap, size_t* count);
 /* host-only self-test hooks (no device needed) */

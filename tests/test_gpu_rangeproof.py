@@ -103,3 +103,37 @@ def test_ip_and_nl_give_different_proofs_for_the_same_statement(ctx):
     assert ip.verify_batch([p_ip]) == [True] and nl.verify_batch([p_nl]) == [True]
     ip.close()
     nl.close()
+
+
+@pytest.mark.parametrize("name", ["64bit", "bin_test", "128by64"])
+def test_wire_format_roundtrip_and_oracle_bytes(ctx, name):
+    """encodeProof' / decodeProof' (src/RangeProof.hs:60-85, src/Encoding.hs): the bytes equal the
+    oracle's encoding of the golden proof; decode -> verify accepts; a flipped sign bit is rejected."""
+    import bulletproofspp_b200 as bp
+    from bulletproofspp_b200 import lib as L
+    from oracle.encoding import encode_commitments, put_field
+    schema, wit = EXAMPLES[name]
+    g = load_golden(name)
+    setup = bp.RangeProofSetup(ctx, schema)
+    B = 2
+    n = setup.n_inputs
+    vals = b"".join(L.int_to_le(w["amount"]) for w in wit) * B
+    tys = b"".join(L.int_to_le(w.get("type", 0)) for w in wit) * B
+    coms, resp, fin = setup.prove_batch_raw(B, vals, tys, None, [setup.random_seed] * B)
+    proof_bin, commits_bin, pb, cb = setup.encode_batch_raw(B, coms, resp, fin)
+    k = setup.num_rp_coms
+    exp_proof = b"".join(put_field(v) for v in g["finals"]) + encode_commitments(g["coms"][:k] + [p for xr in g["responses"] for p in xr])
+    exp_commits = encode_commitments(g["coms"][k:])
+    assert proof_bin[:pb] == exp_proof and proof_bin[pb:] == exp_proof
+    assert commits_bin[:cb] == exp_commits
+    if name == "64bit":
+        assert pb == 418                                     # the paper's published size on secp256k1
+    c2, r2, f2, ok = setup.decode_batch_raw(B, proof_bin, commits_bin)
+    assert ok == [True, True] and (c2, r2, f2) == (coms, resp, fin)
+    assert setup.verify_batch_raw(B, c2, r2, f2) == [True, True]
+    nsc = setup.fin_norm + setup.fin_lin
+    bad = bytearray(proof_bin)
+    bad[32 * nsc] ^= 1                                       # flip the sign bit of the first commitment
+    c3, r3, f3, ok3 = setup.decode_batch_raw(B, bytes(bad), commits_bin)
+    assert ok3 == [True, True] and setup.verify_batch_raw(B, c3, r3, f3) == [False, True]
+    setup.close()

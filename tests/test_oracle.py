@@ -176,3 +176,26 @@ def test_invalid_witnesses_raise():
     setup = load_schema(EXAMPLES["64bit"][0], Toy)
     with pytest.raises(ValueError):
         load_witness(setup, [{"amount": 2 ** 64}])                                 # out of range
+
+
+def test_wire_format_sizes_match_the_published_proof_sizes():
+    """README.md:169-177 / paper: 1x64 reciprocal proof = 10 points + 3 scalars = 416 B + 2 sign bytes
+    = 418 B on secp256k1; SURVEY section 8: 128by64 = 22 points + 3 scalars = 800 B + 3 sign bytes."""
+    from oracle.encoding import encode_proof, decode_commitments, get_field
+    try:
+        SecpRef.lib()
+        Gx = SecpRef
+    except RuntimeError:
+        Gx = G
+    for name, size in [("64bit", 418), ("bin64", 32 * 3 + 2 + 32 * 12)]:
+        setup = load_schema(EXAMPLES[name][0], Gx)
+        proof = prove(setup, ZKPT(Gx, setup.random_seed), load_witness(setup, EXAMPLES[name][1]))
+        commits_bin, proof_bin = encode_proof(setup, proof)
+        assert len(proof_bin) == size
+        nsc = len(proof["opening"].vec.get_witness())
+        pts = proof["coms"][:setup.num_rp_coms] + [p for xr in proof["responses"] for p in xr]
+        assert decode_commitments(proof_bin[32 * nsc:], len(pts)) == pts
+        assert [get_field(proof_bin[32 * i:32 * i + 32], R) for i in range(nsc)] == proof["opening"].vec.get_witness()
+        assert decode_commitments(commits_bin, len(proof["coms"]) - setup.num_rp_coms) == proof["coms"][setup.num_rp_coms:]
+    g = _golden("128by64")
+    assert 32 * len(g["finals"]) + (len(g["coms"]) - 128 + 2 * g["rounds"] + 7) // 8 + 32 * (len(g["coms"]) - 128 + 2 * g["rounds"]) == 803
