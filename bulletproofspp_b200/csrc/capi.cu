@@ -774,6 +774,7 @@ struct bppp_nl {
     DBuf<Jac> jscratch, res;
     MsmPlan plan;
     int blocks_n = 1, blocks_l = 1;
+    size_t shard_lo = 0;            // index of this handle's first norm element inside the whole (sharded) vector
     // tensor mode: no generator folding; per-generator fold coefficients + folded opening scalars
     bool tensor = false;
     DBuf<u256> coef, fsc;           // coef [B][N+M] (Montgomery); fsc [2][B][P0] (Montgomery)
@@ -1232,6 +1233,84 @@ extern "C" void bppp_nl_destroy(bppp_nl* h) {
     delete h;
 }
 
+// Sharding one large argument over several handles / GPUs: this handle holds the
+// contiguous slice of the norm vector that starts at element `first_element` (a multiple of
+// 2^rounds); only the weights q^(4i) of the scalar sums depend on the position.
+extern "C" int bppp_nl_set_shard(bppp_nl* h, size_t first_element) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    if (h->kind != BPPP_ARG_NL || h->round != 0) FAIL(BPPP_ERR_STATE, "bppp_nl_set_shard: NL argument before the first round only");
+    h->shard_lo = first_element;
+    return BPPP_OK;
+}
+// Current state in stored form (fold mode): normalisations nn[b], nl[b], the generator vectors
+// [G (n_norm) | H (n_lin)] and the public coefficients c[b][n_lin] as the handle holds them
+// (G_true = G / nn, c_true = c / nl; the witness in true terms is bppp_nl_final's).
+extern "C" int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* points, uint8_t* c) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    if (h->kind != BPPP_ARG_NL) FAIL(BPPP_ERR_STATE, "bppp_nl_export: NL argument only");
+    ENTER(ctx);
+    const size_t B = h->B, cn = h->curN, cl = h->curM;
+    if (h->tensor && points && cn + cl) {
+        // tensor mode keeps fold coefficients instead of folded generators: materialise
+        // G^(r)_i = sum_{idx >> r == i} coef_idx * G_idx with fixed-base MSMs (meant for the few
+        // elements left when a sharded argument is gathered)
+        const size_t P0 = h->P0, NO = cn + cl, NM = h->N + h->M;
+        if (B * NO * P0 > ((size_t)1 << 26)) FAIL(BPPP_ERR_ARG, "bppp_nl_export: state too large to materialise in tensor mode");
+        std::vector<Fr> hc(B * NM);
+        if (h->round > 0) {
+            CK(D2H(hc.data(), h->coef.p, B * NM * 32));
+            CK(cudaStreamSynchronize(ctx->st));
+        } else {
+            for (auto& v : hc) v = h64::one();
+        }
+        std::vector<u256> sc(B * NO * P0, u256_zero());
+        for (size_t b = 0; b < B; b++)
+            for (size_t idx = 0; idx < NM; idx++) {
+                const bool lin = idx >= h->N;
+                const size_t local = lin ? idx - h->N : idx;
+                const size_t j = (local >> h->round) + (lin ? cn : 0);
+                sc[(b * NO + j) * P0 + 1 + idx] = fr_canon_u256(hc[b * NM + idx]);
+            }
+        DBuf<u256> d_sc;
+        DBuf<Jac> d_res;
+        DBuf<Affine> d_aff;
+        CK(d_sc.alloc(sc.size())); CK(d_res.alloc(B * NO)); CK(d_aff.alloc(B * NO));
+        CK(H2D(d_sc.p, sc.data(), sc.size() * 32));
+        int rc = run_msm_gens(h->gens, P0, d_sc.p, P0, 0, B * NO, 1, d_res.p, 0);
+        if (rc) return rc;
+        if ((rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, B * NO))) return rc;
+        CK(D2H(points, d_aff.p, B * NO * 64));
+        CK(cudaStreamSynchronize(ctx->st));
+        points = nullptr;                                   // done
+    }
+    for (size_t b = 0; b < B; b++) {
+        if (nn) h64::to_bytes(nn + 32 * b, h->nn[b]);
+        if (nl) h64::to_bytes(nl + 32 * b, h->nl[b]);
+    }
+    if (points && cn + cl) {
+        const Affine* src = h->curp < 0 ? h->gens->base.p + 1 : h->pts[h->curp].p + 1;
+        size_t stride = h->curp < 0 ? 0 : h->P2;
+        ctx->d2h += B * (cn + cl) * 64;
+        for (size_t b = 0; b < B; b++)
+            CK(cudaMemcpyAsync(points + 64 * b * (cn + cl), src + b * stride, (cn + cl) * 64, cudaMemcpyDeviceToHost, ctx->st));
+    }
+    if (c && cl) {
+        DBuf<u256> tmp;
+        CK(tmp.alloc(B * cl));
+        for (size_t b = 0; b < B; b++) {
+            { ProfScope ps_(ctx, K_FR_CONVERT, 0);
+            k_fr_convert<<<(unsigned)((cl + 255) / 256), 256, 0, ctx->st>>>(h->c[h->cur].p + b * h->lstride[h->cur], tmp.p + b * cl, cl, 0);
+            }
+            CK(cudaGetLastError());
+        }
+        CK(D2H(c, tmp.p, B * cl * 32));
+    }
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+
 extern "C" int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin) {
     if (!h) return BPPP_ERR_ARG;
     if (n_norm) *n_norm = h->kind == BPPP_ARG_IP ? 2 * h->curN : h->curN;   // IP.Norm.getWitness: two scalars per element
@@ -1253,6 +1332,11 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         rho[b] = q4;
         k1[b] = h64::dbl(h64::mul(n2, q3));
         k2[b] = h64::mul(n2, q4);
+        if (h->shard_lo) {              // weights of a shard start at (q^4)^(first pair index)
+            Fr off = h64::pow_u64(q4, (uint64_t)(h->shard_lo >> (h->round + 1)));
+            k1[b] = h64::mul(k1[b], off);
+            k2[b] = h64::mul(k2[b], off);
+        }
         coef[b * 8 + 1] = h->q[b];          // X on gL <- q * xR
         coef[b * 8 + 2] = h->qinv[b];       // X on gR <- q^-1 * xL
     });

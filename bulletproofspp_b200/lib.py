@@ -20,7 +20,7 @@ EXPORTS = [
     "bppp_profile_enable", "bppp_profile_reset", "bppp_profile_report", "bppp_timer_start", "bppp_timer_stop",
     "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
-    "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free", "bppp_rp_encoded_sizes", "bppp_rp_encode_batch", "bppp_rp_decode_batch",
+    "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free", "bppp_nl_set_shard", "bppp_nl_export", "bppp_rp_encoded_sizes", "bppp_rp_encode_batch", "bppp_rp_decode_batch",
 ]
 
 
@@ -60,6 +60,8 @@ def load_library():
     lib.bppp_nl_round_fold.argtypes = [vp, u8p]
     lib.bppp_nl_lengths.argtypes = [vp, C.POINTER(sz), C.POINTER(sz)]
     lib.bppp_nl_final.argtypes = [vp, u8p, u8p, u8p]
+    lib.bppp_nl_set_shard.argtypes = [vp, sz]
+    lib.bppp_nl_export.argtypes = [vp, u8p, u8p, u8p, u8p]
     lib.bppp_nl_destroy.argtypes = [vp]
     lib.bppp_nl_destroy.restype = None
     lib.bppp_nl_verify.argtypes = [vp, ip, sz, sz, sz, sz, u8p, u8p, u8p, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz,
@@ -357,6 +359,20 @@ class NormLinearArgument:
     def round_fold(self, es):
         eb = es if isinstance(es, (bytes, bytearray)) else ints_to_bytes(es)
         self.ctx._ck(self.ctx.lib.bppp_nl_round_fold(self.h, eb), "bppp_nl_round_fold")
+
+    def set_shard(self, first_element):
+        self.ctx._ck(self.ctx.lib.bppp_nl_set_shard(self.h, first_element), "bppp_nl_set_shard")
+
+    def export(self):
+        """stored-form state: (nn[b], nl[b], points [b][n+m], c [b][m]) -- see bppp_nl_export"""
+        n, m = self.lengths()
+        nn, nl = _buf(32 * self.B), _buf(32 * self.B)
+        pts, c = _buf(64 * self.B * (n + m)), _buf(32 * self.B * m)
+        self.ctx._ck(self.ctx.lib.bppp_nl_export(self.h, nn, nl, pts, c), "bppp_nl_export")
+        P = bytes_to_points(pts.raw[:64 * self.B * (n + m)])
+        cs = bytes_to_ints(c.raw[:32 * self.B * m])
+        return (bytes_to_ints(nn.raw[:32 * self.B]), bytes_to_ints(nl.raw[:32 * self.B]),
+                [P[b * (n + m):(b + 1) * (n + m)] for b in range(self.B)], [cs[b * m:(b + 1) * m] for b in range(self.B)])
 
     def lengths(self):
         a, b = C.c_size_t(), C.c_size_t()

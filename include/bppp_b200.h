@@ -117,6 +117,10 @@ int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R);
 /* the rest of proveRoundM (src/Bulletproof.hs:351-355): s' = s + e0*sX + e1*sR and `collapse e`
  * (NormArgument.hs:64-71,123-129 / InnerProductArgument.hs:86-101,155-170) with challenge e[b]. */
 int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e);
+/* sharding one large argument: this handle holds the slice of the norm vector that
+ * starts at `first_element`; bppp_nl_export hands the stored-form state to the rank that finishes */
+int bppp_nl_set_shard(bppp_nl* h, size_t first_element);
+int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* points, uint8_t* c);
 /* current lengths after the folds so far (norm vector length as `getWitness` reports it) */
 int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin);
 /* scalarCP s and getWitness (NormArgument.hs:62,121 / IPA.hs:154,222-223): s[b], w[b][n_norm], l[b][n_lin] */

@@ -263,3 +263,33 @@ def test_large_argument_fold_mode_rounds_and_verify(ctx, gens):
         assert (X[0], Rr[0]) == (tr[0]["X"], tr[0]["R"]), "round %d" % r
         arg.round_fold([tr[0]["e"]])
     arg.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_argument_equals_unsharded(ctx, gens, world):
+    """one argument split into `world` contiguous shards (emulated as `world` handles on
+    one GPU; the collective is a local list): every round's X, R, the final scalar and the final
+    witness equal the unsharded device run and the oracle.  world = 8 exercises the gathered tail."""
+    import bulletproofspp_b200 as bp
+    from bulletproofspp_b200.sharded import Shard, prove_sharded
+    N, M, k = 64, 6, 4
+    pts = gens(1 + N + M)
+    g, Gs, Hs = pts[0], pts[1:1 + N], pts[1 + N:]
+    q, s0 = H("sq") % R, H("ss") % R
+    w = [H("sw", i) % R for i in range(N)]
+    l = [H("sl", i) % R for i in range(M)]
+    c = [H("sc", i) % R for i in range(M)]
+    zk = ZKPT(G)
+    com = obp.PSV(s0, g, obp.NormLinear.make("NL", G, q, c, w, Gs, l, Hs))
+    exp = []
+    for _ in range(k):
+        tr = []
+        com, xr = obp.prove_round(G, zk, com, tr)
+        exp.insert(0, xr)
+    zk2 = ZKPT(G)
+    oracle = lambda X, Rr: zk2.oracle([X, Rr])[0]
+    L_ = N // world
+    shards = [Shard(ctx, r, world, N, g, Gs[r * L_:(r + 1) * L_], Hs, q, s0, w[r * L_:(r + 1) * L_], l, c) for r in range(world)]
+    resp, s_fin, fw, fl = prove_sharded(shards, lambda vals: vals, k, oracle, q, M)
+    assert resp == exp
+    assert s_fin == com.s and fw == com.vec.norm.get_witness() and fl == com.vec.lin.get_witness()
