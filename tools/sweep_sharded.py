@@ -32,11 +32,25 @@ w = L.bytes_to_ints(sweep.scalars("w%d" % e, N)[32 * rank * Ls:32 * (rank + 1) *
 l, c = L.bytes_to_ints(sweep.scalars("l%d" % e, M)), L.bytes_to_ints(sweep.scalars("c%d" % e, M))
 
 
+_buf = torch.empty(128, dtype=torch.uint8, device="cuda")
+_all = torch.empty(world * 128, dtype=torch.uint8, device="cuda")
+
+
 def gather(vals):
+    """per-round partial commitments: one 128-byte CUDA tensor per rank through ncclAllGather;
+    the (rare) state hand-offs go through all_gather_object"""
     if world == 1:
         return vals
+    v = vals[0]
+    if isinstance(v, tuple) and len(v) == 2 and len(v[0]) == 1 and (v[0][0] is None or isinstance(v[0][0], tuple)):
+        payload = L.point_to_bytes(v[0][0]) + L.point_to_bytes(v[1][0])
+        _buf.copy_(torch.frombuffer(bytearray(payload), dtype=torch.uint8))
+        dist.all_gather_into_tensor(_all, _buf)
+        raw = bytes(_all.cpu().numpy())
+        return [([L.bytes_to_point(raw[128 * r:128 * r + 64])], [L.bytes_to_point(raw[128 * r + 64:128 * r + 128])])
+                for r in range(world)]
     out = [None] * world
-    dist.all_gather_object(out, vals[0])
+    dist.all_gather_object(out, v)
     return out
 
 
@@ -49,6 +63,15 @@ if world > 1:
     dist.barrier()
 ctx.sync()
 t0 = time.time()
+round_t = []
+_orc = oracle
+
+
+def oracle(X, Rr):
+    round_t.append(time.time())
+    return _orc(X, Rr)
+
+
 resp, s_fin, fw, fl = prove_sharded([sh], gather, k, oracle, q, M)
 ctx.sync()
 dt = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
@@ -57,6 +80,7 @@ if world > 1:
 if rank == 0:
     chk = hashlib.sha256(repr((resp, s_fin, fw, fl)).encode()).hexdigest()[:16]
     print(json.dumps({"workload": "sharded norm argument prove", "e": e, "N": N, "M": M, "rounds": k, "n_gpus": world,
-                      "prove_s": round(dt.item(), 4), "proof_checksum": chk, "final": [len(fw), len(fl)]}), flush=True)
+                      "prove_s": round(dt.item(), 4), "proof_checksum": chk, "final": [len(fw), len(fl)],
+                      "round_ms": [round((b - a) * 1e3, 2) for a, b in zip([t0] + round_t[:-1], round_t)]}), flush=True)
 if world > 1:
     dist.destroy_process_group()
