@@ -15,12 +15,15 @@
 //   src/Bulletproof.hs                 proveBPM / verifyBPM round loops, optimalWitnessSize
 // A batch of proofs runs in lock-step: host phases are spread over worker threads, each device
 // call covers the whole batch.
+#include <malloc.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <time.h>
 #include <algorithm>
 #include <atomic>
 #include <map>
+#include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <set>
 #include <string>
@@ -93,15 +96,87 @@ int n_threads() {
 }
 // Host phases of concurrent lanes take turns on the cores (each with every core) so that one
 // lane's host phase overlaps the other lanes' device work instead of all lanes moving in lock-step.
+// The workers are persistent (a phase is only a few milliseconds long).
 std::mutex g_cpu_turn;
+class WorkerPool {
+  public:
+    explicit WorkerPool(int n) {
+        for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~WorkerPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int size() const { return (int)th_.size(); }
+    // runs fn(i) for i in [0, n) on up to `workers` pool threads plus the caller
+    void run(size_t n, int workers, const std::function<void(size_t)>& fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            fn_ = &fn; n_ = n; next_.store(0); pending_ = std::min(workers, (int)th_.size()); wanted_ = pending_;
+            gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+
+  private:
+    void work() {
+        for (;;) {
+            size_t i = next_.fetch_add(1);
+            if (i >= n_) break;
+            (*fn_)(i);
+        }
+    }
+    void loop() {
+        uint64_t seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || (gen_ != seen && wanted_ > 0); });
+                if (stop_) return;
+                seen = gen_;
+                wanted_--;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(size_t)>* fn_ = nullptr;
+    size_t n_ = 0;
+    std::atomic<size_t> next_{0};
+    int pending_ = 0, wanted_ = 0;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+};
+WorkerPool& pool() {
+    static WorkerPool p(std::max(1, (int)std::thread::hardware_concurrency() - 1));
+    return p;
+}
 template <class F>
 void parallel_for(size_t n, F fn) {
     static const bool turns = !(getenv("BPPP_CPU_TURNS") && atoi(getenv("BPPP_CPU_TURNS")) == 0);
-    std::unique_lock<std::mutex> turn(g_cpu_turn, std::defer_lock);
-    if (turns) turn.lock();
     int nt = (int)std::min<size_t>(n, (size_t)n_threads());
     if (nt <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);
+        return;
+    }
+    if (turns) {
+        std::lock_guard<std::mutex> turn(g_cpu_turn);
+        std::function<void(size_t)> f = fn;
+        pool().run(n, nt - 1, f);
         return;
     }
     std::atomic<size_t> next(0);
@@ -881,6 +956,15 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
                   bppp_rp** out) {
     if (!ctx || !out || !basis_seed || (n_ranges && !ranges) || (n_pub && !pubs)) return BPPP_ERR_ARG;
     *out = nullptr;
+    {   // the per-proof scratch vectors of 16 host threads add up to ~1 MB per proof: keep freed
+        // memory in the arenas instead of mmap/munmap + page-faulting it back for every proof
+        static std::once_flag once;
+        std::call_once(once, [] {
+            mallopt(M_MMAP_THRESHOLD, 1 << 30);
+            mallopt(M_TRIM_THRESHOLD, 0x7fffffff);
+            mallopt(M_TOP_PAD, 256 << 20);
+        });
+    }
     bppp_rp* s = new bppp_rp();
     s->ctx = ctx; s->binary = binary != 0; s->arg = arg_kind; s->flag = typed_or_conserved != 0;
     s->fmt = show_format; s->root = root_policy; s->basis_seed = basis_seed;
