@@ -22,11 +22,11 @@ using namespace bppp;
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
-                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc"};
+                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -769,7 +769,7 @@ struct bppp_nl {
     DBuf<u256> w[2], l[2], c[2];
     size_t wstride[2], lstride[2];
     DBuf<u256> sc;                  // [2][B][1+N+M] canonical MSM scalars (X then R)
-    DBuf<u256> part_n, part_l, dots, consts;
+    DBuf<u256> part_n, part_l, dots, consts, pw;   // pw: [B][32] powers rho^(2^j) for the dot weights
     DBuf<unsigned char> sgn;
     DBuf<Jac> jscratch, res;
     MsmPlan plan;
@@ -794,9 +794,17 @@ enum { C_RHO = 0, C_K1, C_K2, C_AU, C_BU, C_AL, C_BL, C_AC, C_BC, C_COEF /* 8 */
 inline u256* cptr(bppp_nl* h, int which) { return h->consts.p + (size_t)which * h->B; }
 static_assert(sizeof(Fr) == sizeof(u256), "host and device field elements share one layout");
 
+// blocks of 256 threads per proof: a power of two (so rho^T is a table entry), about 4 pairs per
+// thread for long vectors, at most 2^18 threads
 int dots_blocks(size_t n_pairs) {
-    size_t b = (n_pairs + 255) / 256;
-    return (int)std::max<size_t>(1, std::min<size_t>(b, 1024));
+    size_t b = 1;
+    while (b * 256 * 4 < n_pairs && b < 1024) b <<= 1;
+    return (int)b;
+}
+int ilog2(size_t x) {
+    int l = 0;
+    while ((x >> l) > 1) l++;
+    return l;
 }
 u256 fr_canon_u256(const Fr& a) {
     u256 r;
@@ -831,7 +839,12 @@ int launch_fold_dots(bppp_nl* h, int fold) {
         A.n_in = (int)h->curN; A.fold = fold;
         A.au = cptr(h, C_AU); A.bu = cptr(h, C_BU);
         A.av = ip ? cptr(h, C_AV) : cptr(h, C_AU); A.bv = ip ? cptr(h, C_BV) : cptr(h, C_BU);
-        A.rho = cptr(h, C_RHO); A.m1 = 1; A.m2 = ip ? 2 : 4; A.partial = h->part_n.p;
+        A.rho = cptr(h, C_RHO); A.pw = h->pw.p; A.log2T = ilog2((size_t)h->blocks_n * 256);
+        A.m1 = 1; A.m2 = ip ? 2 : 4; A.partial = h->part_n.p;
+        { ProfScope ps_(ctx, K_POW_TABLE, 0);
+        k_pow_table<<<(unsigned)((h->B + 127) / 128), 128, 0, ctx->st>>>(cptr(h, C_RHO), h->pw.p, (int)h->B);
+        }
+        CK(cudaGetLastError());
         g_work = (ip ? 2 : 1) * 32.0 * (double)h->B * (fold ? (double)(h->curN + ny) : (double)h->curN);
         { ProfScope ps_(ctx, K_FOLD_DOTS, g_work);
         k_fold_dots<<<dim3(h->blocks_n, (unsigned)h->B), 256, 0, ctx->st>>>(A);
@@ -847,7 +860,7 @@ int launch_fold_dots(bppp_nl* h, int fold) {
         A.in_stride = h->lstride[src]; A.out_stride = h->lstride[dst];
         A.n_in = (int)h->curM; A.fold = fold;
         A.au = cptr(h, C_AC); A.bu = cptr(h, C_BC); A.av = cptr(h, C_AL); A.bv = cptr(h, C_BL);
-        A.rho = nullptr; A.m1 = ip ? 2 : 3; A.m2 = ip ? 1 : 4; A.partial = h->part_l.p;
+        A.rho = nullptr; A.pw = nullptr; A.log2T = 0; A.m1 = ip ? 2 : 3; A.m2 = ip ? 1 : 4; A.partial = h->part_l.p;
         g_work = 2 * 32.0 * (double)h->B * (fold ? (double)(h->curM + ny) : (double)h->curM);
         { ProfScope ps_(ctx, K_FOLD_DOTS, g_work);
         k_fold_dots<<<dim3(h->blocks_l, (unsigned)h->B), 256, 0, ctx->st>>>(A);
@@ -885,6 +898,7 @@ int ip_create(bppp_nl* h, const uint8_t* q, const uint8_t* s, const uint8_t* w, 
     h->wstride[0] = Np; h->wstride[1] = Np2; h->lstride[0] = M; h->lstride[1] = h->M2;
     CK(h->sc.alloc(2 * B * h->P0));
     CK(h->dots.alloc(B * 2));
+    CK(h->pw.alloc(B * 32));
     CK(h->consts.alloc((size_t)C_COUNT * B));
     CK(h->res.alloc(B * 2));
     CK(h->coef.alloc(B * (2 * Np + M)));
@@ -1162,6 +1176,7 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
     h->wstride[0] = N; h->wstride[1] = h->N2; h->lstride[0] = M; h->lstride[1] = h->M2;
     CKH(h->sc.alloc(2 * batch * h->P0));
     CKH(h->dots.alloc(batch * 2));
+    CKH(h->pw.alloc(batch * 32));
     CKH(h->consts.alloc((size_t)C_COUNT * batch));
     CKH(h->sgn.alloc(batch * 2));
     CKH(h->res.alloc(batch * 2));

@@ -401,10 +401,43 @@ BP_HD u256 redc(uint32_t t[16]) {
     for (int i = 0; i < 8; i++) r.v[i] = t[8 + i];
     return cond_sub(r, top);
 }
+#if defined(__CUDA_ARCH__)
+// Montgomery reduction with the same carry-chained mad.lo.cc / madc.hi.cc rows as the multiplier:
+// row i adds m_i * r at limb offset i as an even chain (limbs of r with even index, positions
+// i..i+7) and an odd chain (positions i+1..i+8); the carry out of each chain is counted in cnt[]
+// (one level above the chain) and folded in once at the end.
+BP_D u256 redc_dev(uint32_t t[16]) {
+    const uint32_t N0 = 0xD0364141u, N1 = 0xBFD25E8Cu, N2 = 0xAF48A03Bu, N3 = 0xBAAEDCE6u, N4 = 0xFFFFFFFEu,
+                   N5 = 0xFFFFFFFFu, N6 = 0xFFFFFFFFu, N7 = 0xFFFFFFFFu;
+    uint32_t cnt[18];
+    uint32_t tt[18];
+#pragma unroll
+    for (int i = 0; i < 16; i++) tt[i] = t[i];
+    tt[16] = 0; tt[17] = 0;
+#pragma unroll
+    for (int i = 0; i < 18; i++) cnt[i] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        uint32_t m = tt[i] * BP_FR_N0INV;
+        madc_row(tt[i], tt[i + 1], tt[i + 2], tt[i + 3], tt[i + 4], tt[i + 5], tt[i + 6], tt[i + 7], cnt[i + 8], N0, N2, N4, N6, m);
+        madc_row(tt[i + 1], tt[i + 2], tt[i + 3], tt[i + 4], tt[i + 5], tt[i + 6], tt[i + 7], tt[i + 8], cnt[i + 9], N1, N3, N5, N7, m);
+    }
+    u256 r, c;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { r.v[i] = tt[8 + i]; c.v[i] = cnt[8 + i]; }
+    u256 s;
+    uint32_t top = u256_add(s, r, c) + cnt[16];
+    return cond_sub(s, top ? 1u : 0u);
+}
+#endif
 BP_HD u256 mul(const u256& a, const u256& b) {
     uint32_t t[16];
     mul_wide(t, a, b);
+#if defined(__CUDA_ARCH__)
+    return redc_dev(t);
+#else
     return redc(t);
+#endif
 }
 BP_HD u256 sqr(const u256& a) { return mul(a, a); }
 BP_HD u256 to_mont(const u256& a) { return mul(a, r2()); }

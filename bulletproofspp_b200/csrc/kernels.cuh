@@ -100,9 +100,21 @@ struct FoldDotsArgs {
     const u256* au; const u256* bu;     // per proof (Montgomery)
     const u256* av; const u256* bv;
     const u256* rho;                    // per proof weight base (Montgomery); nullptr -> 1
+    const u256* pw;                     // per proof table rho^(2^j), j < 32 (Montgomery); used when rho != nullptr
+    int log2T;                          // total threads per proof = 2^log2T (so rho^T = pw[log2T])
     int m1, m2;
     u256* partial;                      // [batch][gridDim.x][2]
 };
+// pw[p][j] = rho[p]^(2^j)
+__global__ void k_pow_table(const u256* __restrict__ rho, u256* __restrict__ pw, int batch) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= batch) return;
+    u256 x = ld_u256(rho + p);
+    for (int j = 0; j < 32; j++) {
+        st_u256(pw + (size_t)p * 32 + j, x);
+        x = fr::sqr(x);
+    }
+}
 
 __device__ __forceinline__ u256 fr_pow(u256 base, unsigned e) {
     u256 acc = fr::one();
@@ -133,9 +145,16 @@ __global__ void __launch_bounds__(256) k_fold_dots(FoldDotsArgs A) {
     u256 w = fr::one(), wstep = fr::one();
     const bool weighted = (A.rho != nullptr);
     if (weighted) {
-        u256 rho = ld_u256(A.rho + p);
-        w = fr_pow(rho, t0);
-        wstep = fr_pow(rho, T);
+        // rho^t0 from the per-proof table of rho^(2^j): popcount(t0) multiplications; rho^T is one entry
+        const u256* pw = A.pw + (size_t)p * 32;
+        bool first = true;
+        for (unsigned e = t0, j = 0; e; e >>= 1, j++)
+            if (e & 1u) {
+                u256 f = ld_u256(pw + j);
+                w = first ? f : fr::mul(w, f);
+                first = false;
+            }
+        wstep = ld_u256(pw + A.log2T);
     }
     u256 d1 = u256_zero(), d2 = u256_zero();
     const u256 zero = u256_zero();
@@ -176,25 +195,24 @@ __global__ void __launch_bounds__(256) k_fold_dots(FoldDotsArgs A) {
                 vL = uL; vR = uR;
             }
         }
-        u256 s1 = zero, s2 = zero;
-        u256 pLR, pRL, pRR;
+        // weighted dots: fold the weight into one operand first (saves a multiplication per sum)
         const int need = A.m1 | A.m2;
-        if (need & 1) pLR = fr::mul(uL, vR);
-        if (need & 2) pRL = fr::mul(uR, vL);
-        if (need & 4) pRR = fr::mul(uR, vR);
-        if (A.m1 & 1) s1 = fr::add(s1, pLR);
-        if (A.m1 & 2) s1 = fr::add(s1, pRL);
-        if (A.m1 & 4) s1 = fr::add(s1, pRR);
-        if (A.m2 & 1) s2 = fr::add(s2, pLR);
-        if (A.m2 & 2) s2 = fr::add(s2, pRL);
-        if (A.m2 & 4) s2 = fr::add(s2, pRR);
+        u256 wvR = vR, wvL = vL;
         if (weighted) {
-            s1 = fr::mul(s1, w);
-            s2 = fr::mul(s2, w);
-            w = fr::mul(w, wstep);
+            if (need & 5) wvR = fr::mul(w, vR);
+            if (need & 2) wvL = fr::mul(w, vL);
         }
-        d1 = fr::add(d1, s1);
-        d2 = fr::add(d2, s2);
+        u256 pLR, pRL, pRR;
+        if (need & 1) pLR = fr::mul(uL, wvR);
+        if (need & 2) pRL = fr::mul(uR, wvL);
+        if (need & 4) pRR = fr::mul(uR, wvR);
+        if (A.m1 & 1) d1 = fr::add(d1, pLR);
+        if (A.m1 & 2) d1 = fr::add(d1, pRL);
+        if (A.m1 & 4) d1 = fr::add(d1, pRR);
+        if (A.m2 & 1) d2 = fr::add(d2, pLR);
+        if (A.m2 & 2) d2 = fr::add(d2, pRL);
+        if (A.m2 & 4) d2 = fr::add(d2, pRR);
+        if (weighted && t + T < (unsigned)n_pairs) w = fr::mul(w, wstep);
     }
     // block reduction (warp shuffle tree, then one warp over the per-warp sums)
     __shared__ u256 red[2][8];

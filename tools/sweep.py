@@ -65,13 +65,23 @@ def run(ctx, e, M=6, verify=True, profile=True):
     arg = bp.NormLinearArgument.from_bytes(ctx, bp.ARG_NL, 1, N, M, g, Gb, Hb, q, L.int_to_le(s0), w, l, c)
     t_create = time.time() - t0
     es, xr = [], []
+    per_round = []
+
+    def snap():
+        kk = ctx.profile_report()["kernels"] if profile else {}
+        return {n: (v["ms"], v["work"]) for n, v in kk.items()}
     t0 = time.time()
     for r in range(k):
         X, Rr = arg.round_commit_raw()
         ev = int.from_bytes(hashlib.sha256(X + Rr + bytes([r])).digest(), "big") % R
         es.insert(0, ev)
         xr.insert(0, (L.bytes_to_point(X), L.bytes_to_point(Rr)))
+        before = snap() if profile and r < 4 else None
         arg.round_fold(L.int_to_le(ev))
+        if before is not None:
+            after = snap()
+            d = {n: (after[n][0] - before.get(n, (0, 0))[0], after[n][1] - before.get(n, (0, 0))[1]) for n in after}
+            per_round.append(d)
     s, fw, fl = arg.final()
     t_prove = time.time() - t0
     arg.close()
@@ -107,6 +117,16 @@ def run(ctx, e, M=6, verify=True, profile=True):
             # generator fold: 96 bytes per input pair element (64 in + 32 out per point pair -> 96*(N_k+M_k))
             out["fold_points_TIMADps"] = round(kp["work"] / (kp["ms"] * 1e-3) / 1e12, 3)
         out["proofs_per_s"] = round(1.0 / (t_prove + out.get("verify_s", 0)), 3)
+        # the first fold is the one that streams the full-length vectors: bytes / CUDA-event time
+        if per_round:
+            d = per_round[0]
+            if "k_fold_dots" in d and d["k_fold_dots"][0] > 0:
+                out["fold1_scalar_GBps"] = round(d["k_fold_dots"][1] / (d["k_fold_dots"][0] * 1e-3) / 1e9, 1)
+                out["fold1_scalar_ms"] = round(d["k_fold_dots"][0], 4)
+            if "k_pair_fold" in d and d["k_pair_fold"][0] > 0:
+                out["fold1_points_TIMADps"] = round(d["k_pair_fold"][1] / (d["k_pair_fold"][0] * 1e-3) / 1e12, 3)
+                out["fold1_points_GBps"] = round(96.0 * (N + M) / (d["k_pair_fold"][0] * 1e-3) / 1e9, 2)
+                out["fold1_points_ms"] = round(d["k_pair_fold"][0], 3)
     return out
 
 
