@@ -193,6 +193,87 @@ BP_D void mul_wide_dev(uint32_t t[16], const u256& a, const u256& b) {
         : "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[8]), "r"(O[9]),
           "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]), "r"(c1));
 }
+
+// shorter carry chains for the squaring schedule: x[0..2n-1] += {a...} * b, carry into x[2n]
+BP_D void madc_row3(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t& x4, uint32_t& x5,
+                    uint32_t& x6, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t b) {
+    asm("mad.lo.cc.u32 %0,%7,%10,%0; madc.hi.cc.u32 %1,%7,%10,%1;"
+        "madc.lo.cc.u32 %2,%8,%10,%2; madc.hi.cc.u32 %3,%8,%10,%3;"
+        "madc.lo.cc.u32 %4,%9,%10,%4; madc.hi.cc.u32 %5,%9,%10,%5;"
+        "addc.u32 %6,%6,0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4), "+r"(x5), "+r"(x6)
+        : "r"(a0), "r"(a1), "r"(a2), "r"(b));
+}
+BP_D void madc_row2(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t& x3, uint32_t& x4, uint32_t a0,
+                    uint32_t a1, uint32_t b) {
+    asm("mad.lo.cc.u32 %0,%5,%7,%0; madc.hi.cc.u32 %1,%5,%7,%1;"
+        "madc.lo.cc.u32 %2,%6,%7,%2; madc.hi.cc.u32 %3,%6,%7,%3;"
+        "addc.u32 %4,%4,0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2), "+r"(x3), "+r"(x4)
+        : "r"(a0), "r"(a1), "r"(b));
+}
+BP_D void madc_row1(uint32_t& x0, uint32_t& x1, uint32_t& x2, uint32_t a0, uint32_t b) {
+    asm("mad.lo.cc.u32 %0,%3,%4,%0; madc.hi.cc.u32 %1,%3,%4,%1; addc.u32 %2,%2,0;"
+        : "+r"(x0), "+r"(x1), "+r"(x2)
+        : "r"(a0), "r"(b));
+}
+
+// 256-bit square: the 28 cross products a_i*a_j (i<j) once, doubled by a one-bit shift, plus the
+// 8 diagonal squares.  Row i sends the products with odd i+j to O (index 2i) and the ones with
+// even i+j to E (index 2i+2); every chain's carry lands in a limb that is still 0 or 1.
+BP_D void sqr_wide_dev(uint32_t t[16], const u256& a) {
+    uint32_t E[16], O[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) { E[i] = 0; O[i] = 0; }
+    const uint32_t* v = a.v;
+    mul_row(O[0], O[1], O[2], O[3], O[4], O[5], O[6], O[7], v[1], v[3], v[5], v[7], v[0]);
+    madc_row3(E[2], E[3], E[4], E[5], E[6], E[7], E[8], v[2], v[4], v[6], v[0]);
+    madc_row3(O[2], O[3], O[4], O[5], O[6], O[7], O[8], v[2], v[4], v[6], v[1]);
+    madc_row3(E[4], E[5], E[6], E[7], E[8], E[9], E[10], v[3], v[5], v[7], v[1]);
+    madc_row3(O[4], O[5], O[6], O[7], O[8], O[9], O[10], v[3], v[5], v[7], v[2]);
+    madc_row2(E[6], E[7], E[8], E[9], E[10], v[4], v[6], v[2]);
+    madc_row2(O[6], O[7], O[8], O[9], O[10], v[4], v[6], v[3]);
+    madc_row2(E[8], E[9], E[10], E[11], E[12], v[5], v[7], v[3]);
+    madc_row2(O[8], O[9], O[10], O[11], O[12], v[5], v[7], v[4]);
+    madc_row1(E[10], E[11], E[12], v[6], v[4]);
+    madc_row1(O[10], O[11], O[12], v[6], v[5]);
+    madc_row1(E[12], E[13], E[14], v[7], v[5]);
+    madc_row1(O[12], O[13], O[14], v[7], v[6]);
+    // s = E + (O << 32)   (fits 511 bits: it is half of a^2 - diagonal)
+    uint32_t s[16];
+    s[0] = 0;                                   // E[0] is never written
+    uint32_t c1;
+    asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
+        "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24;"
+        "addc.u32 %8,0,0;"
+        : "=r"(s[1]), "=r"(s[2]), "=r"(s[3]), "=r"(s[4]), "=r"(s[5]), "=r"(s[6]), "=r"(s[7]), "=r"(s[8]), "=r"(c1)
+        : "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]), "r"(E[8]), "r"(O[0]),
+          "r"(O[1]), "r"(O[2]), "r"(O[3]), "r"(O[4]), "r"(O[5]), "r"(O[6]), "r"(O[7]));
+    uint32_t dummy;
+    asm("add.cc.u32 %7,%22,0xffffffff; addc.cc.u32 %0,%8,%15; addc.cc.u32 %1,%9,%16; addc.cc.u32 %2,%10,%17;"
+        "addc.cc.u32 %3,%11,%18; addc.cc.u32 %4,%12,%19; addc.cc.u32 %5,%13,%20; addc.u32 %6,%14,%21;"
+        : "=r"(s[9]), "=r"(s[10]), "=r"(s[11]), "=r"(s[12]), "=r"(s[13]), "=r"(s[14]), "=r"(s[15]), "=r"(dummy)
+        : "r"(E[9]), "r"(E[10]), "r"(E[11]), "r"(E[12]), "r"(E[13]), "r"(E[14]), "r"(E[15]), "r"(O[8]), "r"(O[9]),
+          "r"(O[10]), "r"(O[11]), "r"(O[12]), "r"(O[13]), "r"(O[14]), "r"(c1));
+    // t = 2*s + diag
+    uint32_t d[16];
+    d[0] = 0;
+#pragma unroll
+    for (int k = 1; k < 16; k++) d[k] = __funnelshift_l(s[k - 1], s[k], 1);
+    uint32_t D[16];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { D[2 * i] = v[i] * v[i]; D[2 * i + 1] = __umulhi(v[i], v[i]); }
+    asm("add.cc.u32 %0,%8,%16; addc.cc.u32 %1,%9,%17; addc.cc.u32 %2,%10,%18; addc.cc.u32 %3,%11,%19;"
+        "addc.cc.u32 %4,%12,%20; addc.cc.u32 %5,%13,%21; addc.cc.u32 %6,%14,%22; addc.cc.u32 %7,%15,%23;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7])
+        : "r"(d[0]), "r"(d[1]), "r"(d[2]), "r"(d[3]), "r"(d[4]), "r"(d[5]), "r"(d[6]), "r"(d[7]), "r"(D[0]),
+          "r"(D[1]), "r"(D[2]), "r"(D[3]), "r"(D[4]), "r"(D[5]), "r"(D[6]), "r"(D[7]));
+    asm("addc.cc.u32 %0,%8,%16; addc.cc.u32 %1,%9,%17; addc.cc.u32 %2,%10,%18; addc.cc.u32 %3,%11,%19;"
+        "addc.cc.u32 %4,%12,%20; addc.cc.u32 %5,%13,%21; addc.cc.u32 %6,%14,%22; addc.u32 %7,%15,%23;"
+        : "=r"(t[8]), "=r"(t[9]), "=r"(t[10]), "=r"(t[11]), "=r"(t[12]), "=r"(t[13]), "=r"(t[14]), "=r"(t[15])
+        : "r"(d[8]), "r"(d[9]), "r"(d[10]), "r"(d[11]), "r"(d[12]), "r"(d[13]), "r"(d[14]), "r"(d[15]), "r"(D[8]),
+          "r"(D[9]), "r"(D[10]), "r"(D[11]), "r"(D[12]), "r"(D[13]), "r"(D[14]), "r"(D[15]));
+}
 #endif
 
 BP_HD void mul_wide(uint32_t t[16], const u256& a, const u256& b) {
@@ -281,12 +362,39 @@ BP_HD u256 reduce512(const uint32_t t[16]) {
     // value = out + c*2^256 with c in {0,1}; if c then out is tiny (< 2^45) so out + C < q
     return cond_sub(out, (uint32_t)c);
 }
+#if defined(__CUDA_ARCH__) && !defined(BPPP_FQ_INLINE)
+// On the device the product and the square are real functions (ptxas keeps the operands in
+// registers across the call).  Fully inlined, one mixed add is ~35 KB of SASS and k_msm_gens
+// ~800 KB: the hot loop ran out of the 32 KB L1.5 instruction cache and a third of its stall
+// samples were "no instruction".  As calls the loop body fits the instruction caches.
+static __device__ __noinline__ u256 mul_call(u256 a, u256 b) {
+    uint32_t t[16];
+    mul_wide_dev(t, a, b);
+    return reduce512(t);
+}
+static __device__ __noinline__ u256 sqr_call(u256 a) {
+    uint32_t t[16];
+    sqr_wide_dev(t, a);
+    return reduce512(t);
+}
+BP_D u256 mul(const u256& a, const u256& b) { return mul_call(a, b); }
+BP_D u256 sqr(const u256& a) { return sqr_call(a); }
+#else
 BP_HD u256 mul(const u256& a, const u256& b) {
     uint32_t t[16];
     mul_wide(t, a, b);
     return reduce512(t);
 }
-BP_HD u256 sqr(const u256& a) { return mul(a, a); }
+BP_HD u256 sqr(const u256& a) {
+#if defined(__CUDA_ARCH__)
+    uint32_t t[16];
+    sqr_wide_dev(t, a);
+    return reduce512(t);
+#else
+    return mul(a, a);
+#endif
+}
+#endif
 BP_HD u256 mul_small(const u256& a, uint32_t k) {   // k < 2^16
     uint64_t c = 0;
     u256 r;

@@ -1033,6 +1033,7 @@ __global__ void k_dbg_field(const u256* a, const u256* b, u256* out, size_t n, i
         case 7: r = fr::to_mont(x); break;
         case 8: r = fr::from_mont(x); break;
         case 9: { uint32_t t[16]; mul_wide_portable(t, x, y); r = fq::reduce512(t); break; }
+        case 10: r = fq::sqr(x); break;        // dedicated squaring schedule
         default: r = u256_zero();
     }
     st_u256(out + i, r);

@@ -24,6 +24,8 @@ def test_field_ops(ctx):
     b = [rnd.randrange(Q) for _ in range(len(edge))] + [rnd.randrange(Q) for _ in range(1990)] + [x % Q for x in edge] + [0, Q - 1]
     assert ctx.dbg_field(0, a, b) == [x * y % Q for x, y in zip(a, b)]
     assert ctx.dbg_field(9, a, b) == [x * y % Q for x, y in zip(a, b)]      # portable multiply on device
+    sq = a + [x % Q for x in (2 ** 256 - 1, 2 ** 224 - 1, 0xFFFFFFFF, 0xFFFFFFFF << 224)]
+    assert ctx.dbg_field(10, sq, sq) == [x * x % Q for x in sq]
     assert ctx.dbg_field(1, a, b) == [(x + y) % Q for x, y in zip(a, b)]
     assert ctx.dbg_field(2, a, b) == [(x - y) % Q for x, y in zip(a, b)]
     nz = [x or 1 for x in a[:200]]
