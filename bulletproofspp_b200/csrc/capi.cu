@@ -22,11 +22,11 @@ using namespace bppp;
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
-                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table"};
+                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -1137,11 +1137,11 @@ int ip_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
 
 namespace {
 int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint8_t* q, const uint8_t* s, const uint8_t* w,
-                   const uint8_t* l, const uint8_t* c, bppp_nl** out) {
+                   const uint8_t* l, const uint8_t* c, bppp_nl** out, const u256* w_dev = nullptr) {
     bppp_ctx* ctx = gens->ctx;
     const size_t N = gens->N, M = gens->M;
     if (N + M + 1 > 0x7fffffff) FAIL(BPPP_ERR_ARG, "vector too long");
-    if (!check_fr(q, batch) || !check_fr(s, batch) || !check_fr(w, batch * N) || !check_fr(l, batch * M) ||
+    if (!check_fr(q, batch) || !check_fr(s, batch) || (!w_dev && !check_fr(w, batch * N)) || !check_fr(l, batch * M) ||
         !check_fr(c, batch * M))
         FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     bppp_nl* h = new bppp_nl();
@@ -1189,6 +1189,10 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
     // scalars -> Montgomery on the device (staged through the scalar scratch buffer)
     struct { const uint8_t* src; u256* dst; size_t n; } up[3] = {
         {w, h->w[0].p, batch * N}, {l, h->l[0].p, batch * M}, {c, h->c[0].p, batch * M}};
+    if (w_dev) {                    // the witness was produced on the device (Montgomery form already)
+        CKH(cudaMemcpyAsync(h->w[0].p, w_dev, batch * N * 32, cudaMemcpyDeviceToDevice, ctx->st));
+        up[0].n = 0;
+    }
     for (auto& u : up) {
         if (!u.n) continue;
         CKH(H2D(h->sc.p, u.src, u.n * 32));
@@ -1238,6 +1242,207 @@ extern "C" int bppp_nl_create(bppp_ctx* ctx, int kind, size_t batch, size_t N, s
     rc = nl_create_impl(gens, true, kind, batch, q, s, w, l, c, out);
     if (rc) bppp_gens_destroy(gens);
     return rc;
+}
+
+// =============================================================================== TypedReciprocal scalar phases
+// Device side of proveTRRPM's phases 1-4 for a batch of proofs on one lane (see kernels.cuh).
+struct bppp_trrp {
+    bppp_gens* gens;
+    size_t n_ent, n_ranges, n_bases;
+    DBuf<TrrpEnt> ent;
+    DBuf<u256> eb, es;                 // static per-entry b, s (Montgomery)
+    size_t B = 0;
+    DBuf<u256> scA, scR, scBL, amounts, chal2, chal3, chal4, xp, vt, r, c, bl, w, small;
+    DBuf<Jac> res;
+    DBuf<Affine> aff;
+    int phase = 0;
+};
+namespace {
+TrrpStatic trrp_static(bppp_trrp* h) {
+    TrrpStatic st;
+    st.ent = h->ent.p; st.b = h->eb.p; st.s = h->es.p;
+    st.n_ent = (int)h->n_ent; st.n_ranges = (int)h->n_ranges; st.n_bases = (int)h->n_bases;
+    return st;
+}
+// MSM of `n_msm` scalar rows of length P0 (device resident, canonical) over the lane's generators -> affine, host
+int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out) {
+    bppp_ctx* ctx = h->gens->ctx;
+    const size_t P0 = h->gens->P0;
+    CK(h->res.ensure(n_msm)); CK(h->aff.ensure(n_msm));
+    int rc = run_msm_gens(h->gens, P0, sc, P0, 0, n_msm, 1, h->res.p, msm_alg_imads((double)P0));
+    if (rc) return rc;
+    if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, n_msm))) return rc;
+    CK(D2H(out, h->aff.p, n_msm * 64));
+    CK(cudaStreamSynchronize(ctx->st));
+    return BPPP_OK;
+}
+}  // namespace
+
+extern "C" int bppp_trrp_create(bppp_gens* gens, size_t n_entries, const uint8_t* ent_desc, const uint8_t* ent_b,
+                                const uint8_t* ent_s, size_t n_ranges, size_t n_bases, bppp_trrp** out) {
+    if (!gens) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = gens->ctx;
+    if (!out || !ent_desc || !ent_b || !ent_s || n_entries == 0 || n_entries != gens->N || n_ranges == 0)
+        FAIL(BPPP_ERR_ARG, "bppp_trrp_create: bad argument");
+    *out = nullptr;
+    ENTER(ctx);
+    if (!check_fr(ent_b, n_entries) || !check_fr(ent_s, n_entries)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    for (size_t i = 0; i < n_entries; i++) {
+        TrrpEnt e;
+        memcpy(&e, ent_desc + 16 * i, 16);
+        if (e.ind < 0 || (size_t)e.ind >= n_ranges || (!(e.flags & TE_T) && (e.base_idx < 0 || (size_t)e.base_idx >= n_bases)))
+            FAIL(BPPP_ERR_ARG, "bppp_trrp_create: entry descriptor out of range");
+    }
+    bppp_trrp* h = new bppp_trrp();
+    h->gens = gens; h->n_ent = n_entries; h->n_ranges = n_ranges; h->n_bases = n_bases ? n_bases : 1;
+    auto fail = [&](cudaError_t e) { ctx->err = std::string("bppp_trrp_create: ") + cudaGetErrorString(e); delete h; return BPPP_ERR_CUDA; };
+    cudaError_t e;
+    if ((e = h->ent.alloc(n_entries)) || (e = h->eb.alloc(n_entries)) || (e = h->es.alloc(n_entries)) || (e = h->small.alloc(2 * n_entries)))
+        return fail(e);
+    if ((e = cudaMemcpyAsync(h->ent.p, ent_desc, n_entries * 16, cudaMemcpyHostToDevice, ctx->st))) return fail(e);
+    if ((e = cudaMemcpyAsync(h->small.p, ent_b, n_entries * 32, cudaMemcpyHostToDevice, ctx->st))) return fail(e);
+    if ((e = cudaMemcpyAsync(h->small.p + n_entries, ent_s, n_entries * 32, cudaMemcpyHostToDevice, ctx->st))) return fail(e);
+    k_fr_convert<<<(unsigned)((n_entries + 255) / 256), 256, 0, ctx->st>>>(h->small.p, h->eb.p, n_entries, 1);
+    k_fr_convert<<<(unsigned)((n_entries + 255) / 256), 256, 0, ctx->st>>>(h->small.p + n_entries, h->es.p, n_entries, 1);
+    if ((e = cudaStreamSynchronize(ctx->st))) return fail(e);
+    *out = h;
+    return BPPP_OK;
+}
+extern "C" void bppp_trrp_destroy(bppp_trrp* h) {
+    if (!h) return;
+    cudaSetDevice(h->gens->ctx->dev);
+    g_alloc_stream = h->gens->ctx->st;
+    delete h;
+}
+// phase 1 (TypedReciprocal.hs:399-410): scalars of the digit/multiplicity commitments, [batch][2][P0]
+// canonical (dm row, m row), and the committed values [batch][n_ranges]; coms = [batch][2] points
+extern "C" int bppp_trrp_phase1(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, uint8_t* coms) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!sc_dm_m || !amounts || !coms || batch == 0) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase1: null/empty argument");
+    ENTER(ctx);
+    const size_t P0 = h->gens->P0;
+    if (!check_fr(sc_dm_m, batch * 2 * P0) || !check_fr(amounts, batch * h->n_ranges)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    h->B = batch;
+    CK(h->scA.ensure(batch * 2 * P0)); CK(h->scR.ensure(batch * P0)); CK(h->scBL.ensure(batch * P0));
+    CK(h->amounts.ensure(batch * h->n_ranges));
+    CK(h->chal2.ensure(batch * 4)); CK(h->chal3.ensure(batch * 2)); CK(h->chal4.ensure(batch * 2));
+    CK(h->xp.ensure(batch * h->n_ranges)); CK(h->vt.ensure(batch * h->n_bases));
+    CK(h->r.ensure(batch * h->n_ent)); CK(h->c.ensure(batch * h->n_ent)); CK(h->bl.ensure(batch * h->n_ent));
+    CK(h->w.ensure(batch * h->n_ent)); CK(h->small.ensure(batch * 8));
+    CK(H2D(h->scA.p, sc_dm_m, batch * 2 * P0 * 32));
+    CK(H2D(h->amounts.p, amounts, batch * h->n_ranges * 32));
+    h->phase = 1;
+    return trrp_commit(h, h->scA.p, 2 * batch, coms);
+}
+// phase 2 (:412-419): chal = [batch][4] (e, 1/e, x, 1/r0); r_sclin = [batch][1 + M] scalar and linear
+// slots of the reciprocal witness with the err7 slot zero; err7_slot indexes the linear part.
+// Out: rcom [batch] points, err7 [batch] scalars.
+extern "C" int bppp_trrp_phase2(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
+                                uint8_t* err7) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!chal || !r_sclin || !rcom || !err7 || err7_slot >= h->gens->M) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase2: bad argument");
+    if (h->phase != 1) FAIL(BPPP_ERR_STATE, "bppp_trrp_phase2: call phase1 first");
+    ENTER(ctx);
+    const size_t B = h->B, P0 = h->gens->P0, N = h->gens->N, M = h->gens->M;
+    if (!check_fr(chal, B * 4) || !check_fr(r_sclin, B * (1 + M))) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    CK(H2D(h->chal2.p, chal, B * 4 * 32));
+    // sc -> slot 0, lin -> slots 1+N.. of each scalar row
+    CK(cudaMemcpy2DAsync(h->scR.p, P0 * 32, r_sclin, (1 + M) * 32, 32, B, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpy2DAsync(h->scR.p + 1 + N, P0 * 32, r_sclin + 32, (1 + M) * 32, M * 32, B, cudaMemcpyHostToDevice, ctx->st));
+    ctx->h2d += B * (1 + M) * 32;
+    { ProfScope ps_(ctx, K_TRRP, 0);
+    k_trrp_tables<<<(unsigned)((B + 63) / 64), 64, 0, ctx->st>>>(h->chal2.p, 4, 2, (int)h->n_ranges, (int)h->n_bases, h->xp.p, h->vt.p, (int)B);
+    }
+    CK(cudaGetLastError());
+    TrrpP2Args A;
+    A.st = trrp_static(h); A.chal = h->chal2.p; A.scA = h->scA.p; A.P0 = P0; A.amounts = h->amounts.p;
+    A.xp = h->xp.p; A.vt = h->vt.p; A.r = h->r.p; A.c = h->c.p; A.scR = h->scR.p;
+    A.err7_slot = (int)(1 + N + err7_slot); A.err7 = h->small.p;
+    { ProfScope ps_(ctx, K_TRRP, 0);
+    k_trrp_phase2<<<(unsigned)B, TRRP_THREADS, 0, ctx->st>>>(A);
+    }
+    CK(cudaGetLastError());
+    CK(D2H(err7, h->small.p, B * 32));
+    h->phase = 2;
+    return trrp_commit(h, h->scR.p, B, rcom);
+}
+// phase 3, first half (:421-433): chal = [batch][2] (q-power base q0, x'); bls_nrm = [batch][N] blinders
+// of the norm part.  Out: errs [batch][6] error terms over the norm entries.
+extern "C" int bppp_trrp_phase3(bppp_trrp* h, const uint8_t* chal, const uint8_t* bls_nrm, uint8_t* errs) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!chal || !bls_nrm || !errs) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase3: null argument");
+    if (h->phase != 2) FAIL(BPPP_ERR_STATE, "bppp_trrp_phase3: call phase2 first");
+    ENTER(ctx);
+    const size_t B = h->B, P0 = h->gens->P0, N = h->gens->N;
+    if (!check_fr(chal, B * 2) || !check_fr(bls_nrm, B * N)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    CK(H2D(h->chal3.p, chal, B * 2 * 32));
+    CK(H2D(h->bl.p, bls_nrm, B * N * 32));
+    TrrpP3Args A;
+    A.st = trrp_static(h); A.chal2 = h->chal2.p; A.chal3 = h->chal3.p; A.scA = h->scA.p; A.P0 = P0;
+    A.r = h->r.p; A.c = h->c.p; A.bl = h->bl.p; A.xp = h->xp.p; A.vt = h->vt.p; A.errs = h->small.p;
+    { ProfScope ps_(ctx, K_TRRP, 0);
+    k_trrp_errterms<<<(unsigned)B, TRRP_THREADS, 0, ctx->st>>>(A);
+    }
+    CK(cudaGetLastError());
+    CK(D2H(errs, h->small.p, B * 6 * 32));
+    CK(cudaStreamSynchronize(ctx->st));
+    h->phase = 3;
+    return BPPP_OK;
+}
+// phase 3, second half (:434): bl_sclin = [batch][1 + M] scalar and linear slots of the blinding
+// witness (its norm part is the bls_nrm of phase 3).  Out: blcom [batch] points.
+extern "C" int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!bl_sclin || !blcom) FAIL(BPPP_ERR_ARG, "bppp_trrp_commit_bl: null argument");
+    if (h->phase != 3) FAIL(BPPP_ERR_STATE, "bppp_trrp_commit_bl: call phase3 first");
+    ENTER(ctx);
+    const size_t B = h->B, P0 = h->gens->P0, N = h->gens->N, M = h->gens->M;
+    if (!check_fr(bl_sclin, B * (1 + M))) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    CK(cudaMemcpy2DAsync(h->scBL.p, P0 * 32, bl_sclin, (1 + M) * 32, 32, B, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpy2DAsync(h->scBL.p + 1 + N, P0 * 32, bl_sclin + 32, (1 + M) * 32, M * 32, B, cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpy2DAsync(h->scBL.p + 1, P0 * 32, h->bl.p, N * 32, N * 32, B, cudaMemcpyDeviceToDevice, ctx->st));
+    ctx->h2d += B * (1 + M) * 32;
+    h->phase = 4;
+    return trrp_commit(h, h->scBL.p, B, blcom);
+}
+// phase 4 (:435-444): chal = [batch][2] (t, 1/q0).  The norm part of the argument witness stays on
+// the device; out: sums [batch][3] = (sum q2_i p_i^2, sum q2_i over digit entries, sum v_i over digit entries)
+extern "C" int bppp_trrp_phase4(bppp_trrp* h, const uint8_t* chal, uint8_t* sums) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!chal || !sums) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase4: null argument");
+    if (h->phase != 4) FAIL(BPPP_ERR_STATE, "bppp_trrp_phase4: call commit_bl first");
+    ENTER(ctx);
+    const size_t B = h->B, P0 = h->gens->P0;
+    if (!check_fr(chal, B * 2)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    CK(H2D(h->chal4.p, chal, B * 2 * 32));
+    TrrpP4Args A;
+    A.st = trrp_static(h); A.chal2 = h->chal2.p; A.chal3 = h->chal3.p; A.chal4 = h->chal4.p; A.scA = h->scA.p; A.P0 = P0;
+    A.r = h->r.p; A.c = h->c.p; A.bl = h->bl.p; A.xp = h->xp.p; A.vt = h->vt.p; A.w = h->w.p; A.sums = h->small.p;
+    { ProfScope ps_(ctx, K_TRRP, 0);
+    k_trrp_phase4<<<(unsigned)B, TRRP_THREADS, 0, ctx->st>>>(A);
+    }
+    CK(cudaGetLastError());
+    CK(D2H(sums, h->small.p, B * 3 * 32));
+    CK(cudaStreamSynchronize(ctx->st));
+    h->phase = 5;
+    return BPPP_OK;
+}
+// the norm-linear argument over the device-resident witness of phase 4 (q, s, l, c as in bppp_nl_create)
+extern "C" int bppp_nl_create_trrp(bppp_trrp* h, const uint8_t* q, const uint8_t* s, const uint8_t* l, const uint8_t* c,
+                                   bppp_nl** out) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!out || !q || !s || (h->gens->M && (!l || !c))) FAIL(BPPP_ERR_ARG, "bppp_nl_create_trrp: null argument");
+    if (h->phase != 5) FAIL(BPPP_ERR_STATE, "bppp_nl_create_trrp: call phase4 first");
+    *out = nullptr;
+    ENTER(ctx);
+    h->phase = 0;
+    return nl_create_impl(h->gens, false, BPPP_ARG_NL, h->B, q, s, nullptr, l, c, out, h->w.p);
 }
 
 extern "C" void bppp_nl_destroy(bppp_nl* h) {

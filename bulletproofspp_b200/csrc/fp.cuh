@@ -538,6 +538,14 @@ BP_D u256 redc_dev(uint32_t t[16]) {
     return cond_sub(s, top ? 1u : 0u);
 }
 #endif
+#if defined(__CUDA_ARCH__) && !defined(BPPP_FQ_INLINE)
+static __device__ __noinline__ u256 mul_call(u256 a, u256 b) {      // a call, like fq::mul (code size)
+    uint32_t t[16];
+    mul_wide_dev(t, a, b);
+    return redc_dev(t);
+}
+BP_D u256 mul(const u256& a, const u256& b) { return mul_call(a, b); }
+#else
 BP_HD u256 mul(const u256& a, const u256& b) {
     uint32_t t[16];
     mul_wide(t, a, b);
@@ -547,6 +555,7 @@ BP_HD u256 mul(const u256& a, const u256& b) {
     return redc(t);
 #endif
 }
+#endif
 BP_HD u256 sqr(const u256& a) { return mul(a, a); }
 BP_HD u256 to_mont(const u256& a) { return mul(a, r2()); }
 BP_HD u256 from_mont(const u256& a) {
@@ -554,6 +563,22 @@ BP_HD u256 from_mont(const u256& a) {
 #pragma unroll
     for (int i = 0; i < 8; i++) { t[i] = a.v[i]; t[8 + i] = 0; }
     return redc(t);
+}
+BP_HD u256 dbl(const u256& a) { return add(a, a); }
+// a^(r-2) in Montgomery form, 4-bit windows; inv(0) = 0 (batchInverse maps 0 to 0, BatchInverse.hs:14-24)
+BP_HD u256 inv(const u256& a) {
+    const uint32_t E[8] = {0xD036413Fu, 0xBFD25E8Cu, 0xAF48A03Bu, 0xBAAEDCE6u, 0xFFFFFFFEu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+    u256 tb[16];
+    tb[0] = one();
+    tb[1] = a;
+    for (int i = 2; i < 16; i++) tb[i] = mul(tb[i - 1], a);
+    u256 acc = tb[15];                                   // top nibble of r-2 is 0xF
+    for (int k = 62; k >= 0; k--) {
+        acc = sqr(sqr(sqr(sqr(acc))));
+        uint32_t nib = (E[k >> 3] >> ((k & 7) * 4)) & 15u;
+        if (nib) acc = mul(acc, tb[nib]);
+    }
+    return acc;
 }
 }  // namespace fr
 

@@ -67,8 +67,8 @@ inline Fr sub(const Fr& a, const Fr& b) {
     return r;
 }
 inline Fr neg(const Fr& a) { return a.is_zero() ? a : sub(zero(), a); }
-// CIOS Montgomery product
-inline Fr mul(const Fr& a, const Fr& b) {
+// CIOS Montgomery product (portable form; the reference point for the MULX/ADX one below)
+inline Fr mul_portable(const Fr& a, const Fr& b) {
     uint64_t t[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
         u128 c = 0;
@@ -96,6 +96,44 @@ inline Fr mul(const Fr& a, const Fr& b) {
     if (t[4] || geq_n(r.v)) sub_n(r.v);
     return r;
 }
+#if defined(__x86_64__) && !defined(BPPP_HOST_PORTABLE_FR)
+#define BPPP_HOST_FR_ADX 1
+// One row  (t0..t5) += x[0..3] * y  with MULX and the two carry chains of ADCX / ADOX
+// (BMI2 + ADX; bppp_init refuses to start on a CPU without them).  t5 collects both carry-outs.
+#define BPPP_FR_ROW(T0, T1, T2, T3, T4, T5, X0, X1, X2, X3, Y)                                        \
+    asm("xorl %%eax, %%eax\n\t"                                                                       \
+        "mulx %[x0], %%r8, %%r9\n\t adcx %%r8, %[t0]\n\t adox %%r9, %[t1]\n\t"                        \
+        "mulx %[x1], %%r8, %%r9\n\t adcx %%r8, %[t1]\n\t adox %%r9, %[t2]\n\t"                        \
+        "mulx %[x2], %%r8, %%r9\n\t adcx %%r8, %[t2]\n\t adox %%r9, %[t3]\n\t"                        \
+        "mulx %[x3], %%r8, %%r9\n\t adcx %%r8, %[t3]\n\t adox %%r9, %[t4]\n\t"                        \
+        "adcx %%rax, %[t4]\n\t adox %%rax, %[t5]\n\t adcx %%rax, %[t5]\n\t"                            \
+        : [t0] "+r"(T0), [t1] "+r"(T1), [t2] "+r"(T2), [t3] "+r"(T3), [t4] "+r"(T4), [t5] "+r"(T5)      \
+        : [x0] "rm"(X0), [x1] "rm"(X1), [x2] "rm"(X2), [x3] "rm"(X3), "d"(Y)                            \
+        : "rax", "r8", "r9", "cc")
+inline Fr mul(const Fr& a, const Fr& b) {
+    uint64_t t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0, t5 = 0, t6 = 0, t7 = 0, t8 = 0, t9 = 0;
+    const uint64_t a0 = a.v[0], a1 = a.v[1], a2 = a.v[2], a3 = a.v[3];
+    const uint64_t n0 = N[0], n1 = N[1], n2 = N[2], n3 = N[3];
+    // each outer step adds a*b_i, then m*N (which zeroes the lowest limb) and moves up one limb;
+    // the running value stays below 2N, so the limb above the window is 0 or 1
+    BPPP_FR_ROW(t0, t1, t2, t3, t4, t5, a0, a1, a2, a3, b.v[0]);
+    BPPP_FR_ROW(t0, t1, t2, t3, t4, t5, n0, n1, n2, n3, t0 * N0INV);
+    BPPP_FR_ROW(t1, t2, t3, t4, t5, t6, a0, a1, a2, a3, b.v[1]);
+    BPPP_FR_ROW(t1, t2, t3, t4, t5, t6, n0, n1, n2, n3, t1 * N0INV);
+    BPPP_FR_ROW(t2, t3, t4, t5, t6, t7, a0, a1, a2, a3, b.v[2]);
+    BPPP_FR_ROW(t2, t3, t4, t5, t6, t7, n0, n1, n2, n3, t2 * N0INV);
+    BPPP_FR_ROW(t3, t4, t5, t6, t7, t8, a0, a1, a2, a3, b.v[3]);
+    BPPP_FR_ROW(t3, t4, t5, t6, t7, t8, n0, n1, n2, n3, t3 * N0INV);
+    (void)t9;
+    Fr r = {{t4, t5, t6, t7}};
+    if (t8 || geq_n(r.v)) sub_n(r.v);
+    return r;
+}
+inline bool host_cpu_ok() { return __builtin_cpu_supports("bmi2") && __builtin_cpu_supports("adx"); }
+#else
+inline Fr mul(const Fr& a, const Fr& b) { return mul_portable(a, b); }
+inline bool host_cpu_ok() { return true; }
+#endif
 inline Fr sqr(const Fr& a) { return mul(a, a); }
 inline Fr dbl(const Fr& a) { return add(a, a); }
 inline Fr from_canon(const uint64_t c[4]) {

@@ -43,17 +43,33 @@ namespace {
 
 // ------------------------------------------------------------------------------ utilities
 static bool t_lane_threads_is_main();
+extern thread_local int t_lane_id;
+struct TraceEv { int lane; const char* name; double t0, t1; };
 struct Timing {                                // BPPP_TIMING=1: coarse wall-clock split printed to stderr
     std::map<std::string, double> ms;
     bool on = getenv("BPPP_TIMING") != nullptr;
-    double last = 0;
+    bool trace = getenv("BPPP_TRACE") != nullptr;   // BPPP_TRACE=1: every lane's phases as (lane, name, start, end)
+    std::mutex tmu;
+    std::vector<TraceEv> evs;
     static double now() {
         struct timespec ts;
         clock_gettime(CLOCK_MONOTONIC, &ts);
         return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
     }
-    void start() { if (on && t_lane_threads_is_main()) last = now(); }
-    void lap(const char* name) { if (on && t_lane_threads_is_main()) { double t = now(); ms[name] += t - last; last = t; } }
+    void start() {
+        t_progress() = 0;
+        if (trace) t_last() = now();
+        if (on && t_lane_threads_is_main()) last = now();
+    }
+    void lap(const char* name) {
+        t_progress()++;
+        if (trace) {
+            double t = now();
+            { std::lock_guard<std::mutex> lk(tmu); evs.push_back({t_lane_id, name, t_last(), t}); }
+            t_last() = t;
+        }
+        if (on && t_lane_threads_is_main()) { double t = now(); ms[name] += t - last; last = t; }
+    }
     void dump(const char* what) {
         if (!on || !t_lane_threads_is_main()) return;
         fprintf(stderr, "[bppp timing] %s:", what);
@@ -61,6 +77,16 @@ struct Timing {                                // BPPP_TIMING=1: coarse wall-clo
         fprintf(stderr, "\n");
         ms.clear();
     }
+    void dump_trace(const char* what) {
+        if (!trace) return;
+        std::lock_guard<std::mutex> lk(tmu);
+        for (auto& e : evs) fprintf(stderr, "[bppp trace] %s lane=%d %s %.3f %.3f\n", what, e.lane, e.name, e.t0, e.t1);
+        evs.clear();
+    }
+    double last = 0;
+    static double& t_last() { static thread_local double v = 0; return v; }
+    // phase boundaries passed by this lane in the current call (its place in the pipeline)
+    static int& t_progress() { static thread_local int v = 0; return v; }
 };
 Timing g_tm;
 // fine-grained per-proof section timers (summed over threads), BPPP_TIMING=1
@@ -75,6 +101,7 @@ struct Sect {
     Sect() : t(0), on(g_tm.on) { if (on) t = Timing::now(); }
     void lap(int id) { if (on) { double n = Timing::now(); g_sect[id] += (uint64_t)((n - t) * 1e6); t = n; } }
 };
+extern std::atomic<uint64_t> g_turn_wait_us, g_turn_hold_us, g_turn_calls;
 void dump_sections(const char* what, size_t proofs) {
     if (!g_tm.on) return;
     fprintf(stderr, "[bppp sections] %s (us per proof):", what);
@@ -83,6 +110,8 @@ void dump_sections(const char* what, size_t proofs) {
         if (v) fprintf(stderr, " %s=%.0f", kSectNames[i], v / 1e3 / (double)proofs);
     }
     fprintf(stderr, "\n");
+    fprintf(stderr, "[bppp turns] %s: calls=%llu hold=%.1fms wait(sum over lanes)=%.1fms\n", what,
+            (unsigned long long)g_turn_calls.exchange(0), g_turn_hold_us.exchange(0) / 1e3, g_turn_wait_us.exchange(0) / 1e3);
 }
 extern thread_local bool t_is_lane0;
 static bool t_lane_threads_is_main() { return t_is_lane0; }
@@ -97,7 +126,37 @@ int n_threads() {
 // Host phases of concurrent lanes take turns on the cores (each with every core) so that one
 // lane's host phase overlaps the other lanes' device work instead of all lanes moving in lock-step.
 // The workers are persistent (a phase is only a few milliseconds long).
-std::mutex g_cpu_turn;
+// The turn goes to the waiting lane that is FURTHEST along (ties: lowest lane): lanes that start
+// together then leave their host phases one after the other instead of all at once, so the first
+// lane's device rounds overlap the later lanes' host phases, and a lane in its argument rounds
+// (short transcript hashes that gate device work) never queues behind a long host phase.
+class TurnLock {
+  public:
+    void lock(int64_t prio) {
+        std::unique_lock<std::mutex> lk(mu_);
+        const std::pair<int64_t, uint64_t> key(-prio, seq_++);
+        waiters_.insert(key);
+        cv_.wait(lk, [&] { return !busy_ && *waiters_.begin() == key; });
+        waiters_.erase(waiters_.begin());
+        busy_ = true;
+    }
+    void unlock() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            busy_ = false;
+        }
+        cv_.notify_all();
+    }
+
+  private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::set<std::pair<int64_t, uint64_t>> waiters_;
+    uint64_t seq_ = 0;
+    bool busy_ = false;
+};
+TurnLock g_cpu_turn;
+std::atomic<uint64_t> g_turn_wait_us{0}, g_turn_hold_us{0}, g_turn_calls{0};   // BPPP_TIMING=1
 class WorkerPool {
   public:
     explicit WorkerPool(int n) {
@@ -174,9 +233,17 @@ void parallel_for(size_t n, F fn) {
         return;
     }
     if (turns) {
-        std::lock_guard<std::mutex> turn(g_cpu_turn);
+        double t0 = g_tm.on ? Timing::now() : 0;
+        g_cpu_turn.lock((int64_t)Timing::t_progress() * 1024 - t_lane_id);
+        double t1 = g_tm.on ? Timing::now() : 0;
         std::function<void(size_t)> f = fn;
         pool().run(n, nt - 1, f);
+        g_cpu_turn.unlock();
+        if (g_tm.on) {
+            g_turn_wait_us += (uint64_t)((t1 - t0) * 1e3);
+            g_turn_hold_us += (uint64_t)((Timing::now() - t1) * 1e3);
+            g_turn_calls++;
+        }
         return;
     }
     std::atomic<size_t> next(0);
@@ -306,6 +373,9 @@ struct bppp_rp {
     std::vector<bppp_ctx*> lane_ctx;
     std::vector<bppp_fb*> lane_fb;
     std::vector<bppp_gens*> lane_gens;
+    bppp_trrp* trrp = nullptr;                 // device scalar phases, lane 0 / other lanes
+    std::vector<bppp_trrp*> lane_trrp;
+    bool dev_phases = false;
     std::mutex err_mu;
     std::string err;
 };
@@ -721,16 +791,14 @@ std::vector<Fr> make_error_terms(const Fr& e, const Fr& xq, const std::vector<Fr
     tot[5] = add(tot[5], dbl(h5));
     return tot;
 }
-RPW make_public_consts_trrp(const bppp_rp* s, const Fr& e, const Fr& e_inv, const Fr& x, const Fr& xq, const Fr& q0,
-                            const Fr& q0_inv, const Fr& t, const std::vector<Ph2>& ph2s) {
-    using namespace h64;                                             // TypedReciprocal.hs:236-263
-    Fr t2 = sqr(t), t3 = mul(t2, t), t4 = sqr(t2), t5 = mul(t4, t);
+// the part of makePublicConsts' scalar that does not involve the norm entries (range minima, public amounts)
+Fr public_consts_z_trrp(const bppp_rp* s, const Fr& e, const Fr& x, const Fr& two_t5) {
+    using namespace h64;
     Fr x2 = sqr(x), xp = x2, acc = zero();
     for (auto& rd : s->rds) {
         if (!rd.is_assumed) acc = add(acc, mul(from_i128(rd.mn), xp));
         xp = mul(xp, x2);
     }
-    Fr two_t5 = dbl(t5);
     Fr z = neg(mul(two_t5, acc));
     if (s->flag) {
         std::vector<Fr> rs;
@@ -743,6 +811,14 @@ RPW make_public_consts_trrp(const bppp_rp* s, const Fr& e, const Fr& e_inv, cons
         }
         z = sub(z, mul(mul(two_t5, x), sum));
     }
+    return z;
+}
+RPW make_public_consts_trrp(const bppp_rp* s, const Fr& e, const Fr& e_inv, const Fr& x, const Fr& xq, const Fr& q0,
+                            const Fr& q0_inv, const Fr& t, const std::vector<Ph2>& ph2s) {
+    using namespace h64;                                             // TypedReciprocal.hs:236-263
+    Fr t2 = sqr(t), t3 = mul(t2, t), t4 = sqr(t2), t5 = mul(t4, t);
+    Fr two_t5 = dbl(t5);
+    Fr z = public_consts_z_trrp(s, e, x, two_t5);
     // p_i = t^2 (e + qi2 v) + t^3 rC + t^4 qi2 c  with rC = qi2 u (digits) or x'(qi2 u + 1) (types)
     //     = const + qi2 * (t^2 v + t^3 u' + t^4 c),   u' = u or x' u,  const = t^2 e (+ t^3 x' for types)
     // sum_i t^5 p2C_i = 2 t^5 (sum q2_i + eInv sum v_i) over the digit entries
@@ -871,9 +947,10 @@ struct Lane {
     bppp_gens* gens;
     int threads;                               // host threads this lane may use
     int index;                                 // which set of staging buffers
+    bppp_trrp* trrp = nullptr;                 // device scalar phases (TypedReciprocal + norm-linear argument)
 };
 enum { PB_IN = 0, PB_SC1, PB_SC2, PB_C1, PB_C2, PB_NCOMS, PB_Q, PB_S, PB_W, PB_L, PB_C, PB_X, PB_R, PB_E, PB_V0, PB_V1, PB_V2, PB_V3,
-       PB_V4, PB_V5, PB_V6, PB_V7, PB_V8, PB_COUNT };
+       PB_V4, PB_V5, PB_V6, PB_V7, PB_V8, PB_CH, PB_SCLIN, PB_BLN, PB_SMALL, PB_COUNT };
 // uninitialised page-locked buffer `slot` of the lane, at least `bytes` long
 uint8_t* lane_buf(bppp_rp* s, const Lane& ln, int slot, size_t bytes) {
     auto& pb = s->pinned[ln.index][slot];
@@ -888,16 +965,17 @@ uint8_t* lane_buf(bppp_rp* s, const Lane& ln, int slot, size_t bytes) {
     return (uint8_t*)pb.p;
 }
 thread_local int t_lane_threads = 0;
+thread_local int t_lane_id = 0;
 thread_local bool t_is_lane0 = true;
 const char* ctx_err(const Lane& ln) { return bppp_last_error(ln.ctx); }
 
 // run the argument (proveBPM, src/Bulletproof.hs:357-359) for the whole batch
 int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t rounds, const uint8_t* q, const uint8_t* sc,
                  const uint8_t* w, const uint8_t* l, const uint8_t* c,
-                 uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l) {
+                 uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l, bool device_witness = false) {
     const size_t B = P.size(), N = s->nrm_len, M = s->lin_len;
     bppp_nl* h = nullptr;
-    int rc = bppp_nl_create_gens(ln.gens, s->arg, B, q, sc, w, l, c, &h);
+    int rc = device_witness ? bppp_nl_create_trrp(ln.trrp, q, sc, l, c, &h) : bppp_nl_create_gens(ln.gens, s->arg, B, q, sc, w, l, c, &h);
     if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(ln));
     uint8_t* X = lane_buf(s, ln, PB_X, B * 64);
     uint8_t* R = lane_buf(s, ln, PB_R, B * 64);
@@ -907,17 +985,23 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
         rc = bppp_nl_round_commit(h, X, R);
         g_tm.lap("nl_commit");
         if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_commit: ") + ctx_err(ln)); }
-        parallel_for(B, [&](size_t b) {
-            uint8_t xr[128];
-            memcpy(xr, &X[64 * b], 64);
-            memcpy(xr + 64, &R[64 * b], 64);
-            Fr e;
+        parallel_for((B + 1) / 2, [&](size_t pi) {                  // two transcripts per task (two-stream SHA)
+            const size_t b0 = 2 * pi, nb = std::min<size_t>(2, B - b0);
+            uint8_t xr[2][128];
+            Fr e[2];
             Sect sect;
-            P[b].zk.oracle(xr, 2, &e, 1);                           // e <- head <$> oracle [ac, bc]
+            for (size_t j = 0; j < nb; j++) {
+                memcpy(xr[j], &X[64 * (b0 + j)], 64);
+                memcpy(xr[j] + 64, &R[64 * (b0 + j)], 64);
+            }
+            if (nb == 2) tr::Zkpt::oracle_pair(P[b0].zk, xr[0], P[b0 + 1].zk, xr[1], 2, &e[0], &e[1]);
+            else P[b0].zk.oracle(xr[0], 2, &e[0], 1);                // e <- head <$> oracle [ac, bc]
             sect.lap(S_ORACLE);
-            h64::to_bytes(&E[32 * b], e);
-            // responses are consed: newest first (Bulletproof.hs:357-359)
-            memcpy(responses + 128 * (b * rounds + (rounds - 1 - r)), xr, 128);
+            for (size_t j = 0; j < nb; j++) {
+                h64::to_bytes(&E[32 * (b0 + j)], e[j]);
+                // responses are consed: newest first (Bulletproof.hs:357-359)
+                memcpy(responses + 128 * ((b0 + j) * rounds + (rounds - 1 - r)), xr[j], 128);
+            }
         });
         g_tm.lap("round_hash");
         rc = bppp_nl_round_fold(h, E);
@@ -956,6 +1040,10 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
                   bppp_rp** out) {
     if (!ctx || !out || !basis_seed || (n_ranges && !ranges) || (n_pub && !pubs)) return BPPP_ERR_ARG;
     *out = nullptr;
+    if (!h64::host_cpu_ok()) {
+        fprintf(stderr, "bppp_rp_setup: this build's host field arithmetic needs BMI2 + ADX (rebuild with -DBPPP_HOST_PORTABLE_FR)\n");
+        return BPPP_ERR_STATE;
+    }
     {   // the per-proof scratch vectors of 16 host threads add up to ~1 MB per proof: keep freed
         // memory in the arenas instead of mmap/munmap + page-faulting it back for every proof
         static std::once_flag once;
@@ -1061,11 +1149,43 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
             s->lane_ctx.push_back(c2); s->lane_fb.push_back(f2); s->lane_gens.push_back(g2);
         }
     }
+    // device scalar phases: TypedReciprocal proofs over the norm-linear argument (BPPP_RP_HOST_PHASES=1
+    // keeps them on the host; binary proofs and the inner-product argument always run them there)
+    if (!s->binary && s->arg == BPPP_ARG_NL && !(getenv("BPPP_RP_HOST_PHASES") && atoi(getenv("BPPP_RP_HOST_PHASES")))) {
+        std::vector<Ph1> tp = ph1s_verifier(s);
+        if (tp.size() == s->nrm_len) {
+            const size_t ne = tp.size();
+            std::vector<uint8_t> desc(16 * ne), eb(32 * ne), es(32 * ne);
+            for (size_t i = 0; i < ne; i++) {
+                const Ph1& p = tp[i];
+                uint32_t flags = (p.kind == 'T' ? 1u : 0u) | (p.io ? 2u : 0u) | (p.ia ? 4u : 0u) | (p.kind == 'I' ? 8u : 0u) |
+                                 (p.s_zero ? 0u : 16u);
+                int32_t ind = p.ind, bi = -1, pad = 0;
+                if (p.kind != 'T')
+                    for (size_t j = 0; j < s->sorted_bases.size(); j++)
+                        if (s->sorted_bases[j] == p.base) bi = (int32_t)j;
+                memcpy(&desc[16 * i], &flags, 4); memcpy(&desc[16 * i + 4], &ind, 4);
+                memcpy(&desc[16 * i + 8], &bi, 4); memcpy(&desc[16 * i + 12], &pad, 4);
+                h64::to_bytes(&eb[32 * i], p.kind == 'T' ? h64::zero() : p.b);
+                h64::to_bytes(&es[32 * i], p.s_zero ? h64::zero() : p.s);
+            }
+            int rc2 = bppp_trrp_create(s->gens, ne, desc.data(), eb.data(), es.data(), s->rds.size(), s->sorted_bases.size(), &s->trrp);
+            for (size_t i = 0; !rc2 && i < s->lane_gens.size(); i++) {
+                bppp_trrp* t = nullptr;
+                rc2 = bppp_trrp_create(s->lane_gens[i], ne, desc.data(), eb.data(), es.data(), s->rds.size(), s->sorted_bases.size(), &t);
+                if (!rc2) s->lane_trrp.push_back(t);
+            }
+            if (rc2) { bppp_rp_free(s); return rc2; }
+            s->dev_phases = true;
+        }
+    }
     *out = s;
     return BPPP_OK;
 }
 void bppp_rp_free(bppp_rp* s) {
     if (!s) return;
+    bppp_trrp_destroy(s->trrp);                 // before the generator sets / contexts they refer to
+    for (auto t : s->lane_trrp) bppp_trrp_destroy(t);
     bppp_fb_destroy(s->fb);
     bppp_gens_destroy(s->gens);
     for (auto& lane : s->pinned)
@@ -1100,9 +1220,162 @@ int bppp_rp_points(bppp_rp* s, size_t count, uint8_t* out) {
 }
 // `hashToScalars ("Blinding " <> rn)` position j (1-based)  (app/Main.hs:86-87)
 int bppp_input_blind(const char* random_seed, uint64_t j, uint8_t out[32]) {
+    if (!h64::host_cpu_ok()) return BPPP_ERR_STATE;
     if (!random_seed || !out) return BPPP_ERR_ARG;
     h64::to_bytes(out, tr::input_blind(random_seed, j));
     return BPPP_OK;
+}
+
+// proveTRRPM phases 2-4 (TypedReciprocal.hs:412-444) with the norm-entry arithmetic on the device
+// (bppp_trrp_*): the host keeps the transcript, the blinders, the scalar/linear slots and the few
+// per-proof constants; reciprocals, error terms, public constants and the combined witness never
+// leave the GPU.
+static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, uint8_t* coms, uint8_t* responses, uint8_t* finals,
+                             const uint8_t* c1, const uint8_t* n_coms) {
+    const size_t B = P.size(), n = s->n_inputs, N = s->nrm_len, M = s->lin_len, NC = s->num_rp_coms + n;
+    uint8_t* ch = lane_buf(s, ln, PB_CH, B * 4 * 32);
+    uint8_t* sclin = lane_buf(s, ln, PB_SCLIN, B * (1 + M) * 32);
+    uint8_t* bln = lane_buf(s, ln, PB_BLN, B * N * 32);
+    uint8_t* small = lane_buf(s, ln, PB_SMALL, B * 6 * 32);
+    uint8_t* c2 = lane_buf(s, ln, PB_C2, B * 64);
+    uint8_t* q_b = lane_buf(s, ln, PB_Q, B * 32);
+    uint8_t* sc_b = lane_buf(s, ln, PB_S, B * 32);
+    uint8_t* l_b = lane_buf(s, ln, PB_L, B * M * 32);
+    uint8_t* c_b = lane_buf(s, ln, PB_C, B * M * 32);
+    auto put_sclin = [&](size_t b, const RPW& w) {
+        uint8_t* o = sclin + 32 * b * (1 + M);
+        memset(o, 0, 32 * (1 + M));
+        h64::to_bytes(o, w.sc);
+        for (size_t i = 0; i < w.lin.size() && i < M; i++)
+            if (!w.lin[i].is_zero()) h64::to_bytes(o + 32 * (1 + i), w.lin[i]);
+    };
+    const size_t ERR7_SLOT = 4;                                            // blindErrWitness 3 [err7]: lin = [b1, b2, 0, b3, err7, 0]
+    // ---------------- phase 2
+    parallel_for(B, [&](size_t b) {
+        Proof& p = P[b];
+        uint8_t* out = coms + 64 * b * NC;
+        memcpy(out + 128, &c1[64 * (2 * b)], 64);                           // dmCom
+        memcpy(out + 192, &c1[64 * (2 * b + 1)], 64);                       // mCom
+        memcpy(out + 256, &n_coms[64 * b * n], 64 * n);
+        Fr chs[3];
+        Sect sect;
+        p.zk.oracle(out + 128, 2 + n, chs, 3);                              // T3 e x r0 <- oracle' (dmCom:mCom:nComs)
+        sect.lap(S_ORACLE);
+        p.e = chs[0]; p.x = chs[1]; p.r0 = chs[2];
+        Fr iv[2] = {p.e, p.r0};
+        h64::batch_inv(iv, 2);
+        p.e_inv = iv[0]; p.r0_inv = iv[1];
+        p.base_map = make_base_map(s, p.x);
+        p.dm.nrm.clear(); p.m.nrm.clear(); p.ph1s.clear();                  // the norm parts live on the device
+        p.r = blind_err_witness(p.zk, 3, {h64::zero()}, {}, {});            // err7 is filled in by the device
+        sect.lap(S_RANDOM);
+        put_sclin(b, p.r);
+        h64::to_bytes(ch + 32 * (4 * b), p.e); h64::to_bytes(ch + 32 * (4 * b + 1), p.e_inv);
+        h64::to_bytes(ch + 32 * (4 * b + 2), p.x); h64::to_bytes(ch + 32 * (4 * b + 3), p.r0_inv);
+        sect.lap(S_SCALARS);
+    });
+    g_tm.lap("host_phase2");
+    int rc = bppp_trrp_phase2(ln.trrp, ch, sclin, ERR7_SLOT, c2, small);
+    if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(ln));
+    g_tm.lap("msm_phase2");
+    // ---------------- phase 3
+    parallel_for(B, [&](size_t b) {
+        Proof& p = P[b];
+        uint8_t* out = coms + 64 * b * NC;
+        memcpy(out + 64, &c2[64 * b], 64);                                  // rCom
+        p.r.lin[ERR7_SLOT] = h64::from_bytes(small + 32 * b);
+        Fr chs[3];
+        Sect sect;
+        p.zk.oracle(out + 64, 1, chs, 3);                                   // T3 q x' r1 <- oracle' [rCom]
+        sect.lap(S_ORACLE);
+        p.q = chs[0]; p.xq = chs[1]; p.r1 = chs[2];
+        p.q0 = q0_of(s->arg, p.q);
+        Fr iv[3] = {p.q, p.q0, p.r1};
+        h64::batch_inv(iv, 3);
+        p.q_inv = iv[0]; p.q0_inv = iv[1]; p.r1_inv = iv[2];
+        std::vector<U128> mb;
+        for (auto& kv : p.base_mss) mb.push_back(kv.first);
+        p.shared_cs = make_shared_coeffs(p.e, p.e_inv, mb, p.base_map);
+        sect.lap(S_COEFFS);
+        p.bls_lin.resize(M > 5 ? M - 5 : 0);
+        p.zk.random_fill(p.bls_lin.data(), p.bls_lin.size());
+        p.zk.random_fill_canonical(bln + 32 * b * N, N);
+        sect.lap(S_RANDOM);
+        h64::to_bytes(ch + 32 * (2 * b), p.q0); h64::to_bytes(ch + 32 * (2 * b + 1), p.xq);
+        std::vector<Fr> ic = input_coeffs_trrp(s, p.x, p.q0);
+        RPW nsum;
+        for (size_t i = 0; i < n; i++) rpw_add(nsum, rpw_scale(p.n_wits[i], ic[i]));
+        p.wit = nsum;                                                       // parked: nWitSum
+        sect.lap(S_COMBINE);
+    });
+    g_tm.lap("host_phase3");
+    rc = bppp_trrp_phase3(ln.trrp, ch, bln, small);
+    if (rc) return fail(s, rc, std::string("error terms: ") + ctx_err(ln));
+    g_tm.lap("msm_phase3");
+    parallel_for(B, [&](size_t b) {
+        Proof& p = P[b];
+        Sect sect;
+        std::vector<Fr> errs(6);
+        for (int i = 0; i < 6; i++) errs[i] = h64::from_bytes(small + 32 * (6 * b + i));
+        Fr aug = h64::zero();                                               // 2 sum cs_i bls_i over the shared multiplicities
+        for (size_t i = 0; i < p.shared_cs.size() && i + 1 < p.bls_lin.size(); i++)
+            aug = h64::add(aug, h64::mul(p.shared_cs[i], p.bls_lin[i + 1]));
+        errs[3] = h64::add(errs[3], h64::dbl(aug));
+        sect.lap(S_ERRTERMS);
+        Fr tC = s->flag ? p.xq : h64::zero();
+        Fr input_bl = p.wit.lin.size() > 1 ? p.wit.lin[1] : h64::zero();
+        RPW blbl;
+        blbl.lin = p.bls_lin;
+        std::vector<const RPW*> wits = {&p.m, &p.dm, &p.r};
+        p.bl = blind_blinding_term(blbl, tC, p.r0, p.r0_inv, p.r1, p.r1_inv, errs, wits, input_bl);
+        sect.lap(S_BLIND);
+        put_sclin(b, p.bl);
+        sect.lap(S_SCALARS);
+    });
+    g_tm.lap("host_phase3");
+    rc = bppp_trrp_commit_bl(ln.trrp, sclin, c2);
+    if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(ln));
+    g_tm.lap("msm_phase3");
+    // ---------------- phase 4
+    parallel_for(B, [&](size_t b) {
+        Proof& p = P[b];
+        uint8_t* out = coms + 64 * b * NC;
+        memcpy(out, &c2[64 * b], 64);                                       // blCom
+        Sect sect;
+        p.zk.oracle(out, 1, &p.t, 1);
+        sect.lap(S_ORACLE);
+        h64::to_bytes(ch + 32 * (2 * b), p.t); h64::to_bytes(ch + 32 * (2 * b + 1), p.q0_inv);
+    });
+    g_tm.lap("host_phase4");
+    rc = bppp_trrp_phase4(ln.trrp, ch, small);
+    if (rc) return fail(s, rc, std::string("public constants: ") + ctx_err(ln));
+    g_tm.lap("msm_phase4");
+    parallel_for(B, [&](size_t b) {
+        Proof& p = P[b];
+        Sect sect;
+        using namespace h64;
+        const Fr ts0 = from_bytes(small + 32 * (3 * b)), sum_q2 = from_bytes(small + 32 * (3 * b + 1)), sum_v = from_bytes(small + 32 * (3 * b + 2));
+        const Fr t2 = sqr(p.t), t3 = mul(t2, p.t), t5 = mul(sqr(t2), p.t), two_t5 = dbl(t5);
+        RPW wit;                                                            // scalar + linear slots only
+        wit.sc = add(public_consts_z_trrp(s, p.e, p.x, two_t5), add(ts0, mul(two_t5, add(sum_q2, mul(p.e_inv, sum_v)))));
+        sect.lap(S_PUB);
+        rpw_add(wit, p.bl);
+        rpw_add(wit, rpw_scale(p.m, p.t));
+        rpw_add(wit, rpw_scale(p.dm, t2));
+        rpw_add(wit, rpw_scale(p.r, t3));
+        rpw_add(wit, rpw_scale(p.wit, two_t5));
+        p.cs = make_bp_coeffs(s->flag, p.xq, p.r0, p.r1, p.t, p.shared_cs);
+        sect.lap(S_COMBINE);
+        memset(&l_b[32 * b * M], 0, 32 * M);
+        memset(&c_b[32 * b * M], 0, 32 * M);
+        to_bytes(&q_b[32 * b], p.q);
+        to_bytes(&sc_b[32 * b], wit.sc);
+        for (size_t i = 0; i < wit.lin.size() && i < M; i++) to_bytes(&l_b[32 * (b * M + i)], wit.lin[i]);
+        for (size_t i = 0; i < p.cs.size() && i < M; i++) to_bytes(&c_b[32 * (b * M + i)], p.cs[i]);
+        sect.lap(S_TOBYTES);
+    });
+    g_tm.lap("host_phase4");
+    return run_argument(s, ln, P, s->prover_rounds, q_b, sc_b, nullptr, l_b, c_b, responses, finals, s->prover_fin_n, s->prover_fin_l, true);
 }
 
 // RangeProof.proveM (src/RangeProof.hs:95-97) for `batch` independent proofs.
@@ -1268,9 +1541,11 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
         rc = bppp_fb_msm_batch(ln.fb, B * n, in_sc, n_coms);
         if (rc) return fail(s, rc, std::string("input commitments: ") + ctx_err(ln));
     }
-    rc = bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1, c1);
+    const bool dev = s->dev_phases && ln.trrp;
+    rc = dev ? bppp_trrp_phase1(ln.trrp, B, sc1, values, c1) : bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1, c1);
     if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(ln));
     g_tm.lap("msm_phase1");
+    if (dev) return prove_trrp_device(s, ln, P, coms, responses, finals, c1, n_coms);
     uint8_t* q_b = lane_buf(s, ln, PB_Q, B * 32);
     uint8_t* sc_b = lane_buf(s, ln, PB_S, B * 32);
     uint8_t* w_b = lane_buf(s, ln, PB_W, B * N * 32);
@@ -1294,7 +1569,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             p.q0_inv = h64::inv(p.q0);
             p.pub = public_consts_brp(s, p.x, p.q0, p.q0_inv);
             p.bls_nrm.clear();
-            for (size_t i = 0; i < N; i++) p.bls_nrm.push_back(p.zk.random());
+            { size_t n0 = p.bls_nrm.size(); p.bls_nrm.resize(n0 + N); p.zk.random_fill(p.bls_nrm.data() + n0, N); }
             Fr bl_bl = p.zk.random();
             // makePolyTerms (qPowers q) [blsNrm, nrm (dWit + pubWit)]  (Binary.hs:188, Internal.hs:65-75)
             std::vector<Fr> dn = p.d.nrm;
@@ -1388,8 +1663,10 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
             Fr tC = s->flag ? p.xq : h64::zero();
             sect.lap(S_COEFFS);
             p.bls_lin.clear(); p.bls_nrm.clear();
-            for (size_t i = 0; i + 5 < M; i++) p.bls_lin.push_back(p.zk.random());
-            for (size_t i = 0; i < N; i++) p.bls_nrm.push_back(p.zk.random());
+            p.bls_lin.resize(M > 5 ? M - 5 : 0);
+            p.bls_nrm.resize(N);
+            p.zk.random_fill(p.bls_lin.data(), p.bls_lin.size());
+            p.zk.random_fill(p.bls_nrm.data(), N);
             sect.lap(S_RANDOM);
             std::vector<Fr> bls_ms(p.bls_lin.begin() + 1, p.bls_lin.end());
             std::vector<Fr> ic = input_coeffs_trrp(s, p.x, p.q0);
@@ -1519,11 +1796,12 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         }
         sect.lap(S_V_MISC);
         // challenges of the argument: oldest round hashed first, list newest first (Bulletproof.hs:374)
-        for (size_t r = 0; r < k; r++) {
-            size_t idx = k - 1 - r;                                         // oldest round sits last
-            Fr e;
-            zk.oracle(responses + 128 * (b * k + idx), 2, &e, 1);
-            h64::to_bytes(&es_b[32 * (b * k + idx)], e);
+        {
+            std::vector<const uint8_t*> rp(k);
+            std::vector<Fr> es(k);
+            for (size_t r = 0; r < k; r++) rp[r] = responses + 128 * (b * k + (k - 1 - r));   // oldest round sits last
+            zk.oracle_rounds(rp.data(), k, es.data());
+            for (size_t r = 0; r < k; r++) h64::to_bytes(&es_b[32 * (b * k + (k - 1 - r))], es[r]);
         }
         sect.lap(S_V_ORACLE);
         memset(&pw_b[32 * b * N], 0, 32 * N);
@@ -1552,8 +1830,9 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
 namespace {
 std::vector<Lane> make_lanes(bppp_rp* s, size_t batch) {
     std::vector<Lane> L;
-    L.push_back({s->ctx, s->fb, s->gens, 0, 0});
-    for (size_t i = 0; i < s->lane_ctx.size(); i++) L.push_back({s->lane_ctx[i], s->lane_fb[i], s->lane_gens[i], 0, (int)i + 1});
+    L.push_back({s->ctx, s->fb, s->gens, 0, 0, s->trrp});
+    for (size_t i = 0; i < s->lane_ctx.size(); i++)
+        L.push_back({s->lane_ctx[i], s->lane_fb[i], s->lane_gens[i], 0, (int)i + 1, i < s->lane_trrp.size() ? s->lane_trrp[i] : nullptr});
     if (s->pinned.size() < L.size()) s->pinned.resize(L.size(), std::vector<bppp_rp::Pinned>(PB_COUNT));
     size_t want = std::max<size_t>(1, std::min(L.size(), batch / 32));      // tiny batches: one lane
     L.resize(want);
@@ -1577,12 +1856,14 @@ int run_lanes(bppp_rp* s, size_t batch, F fn) {
         if (!nb) continue;
         th.emplace_back([&, i, b0, nb]() {
             t_lane_threads = L[i].threads;
+            t_lane_id = (int)i;
             t_is_lane0 = (i == 0);
             bppp_set_thread_host_threads(L[i].threads);
             rcs[i] = fn(L[i], b0, nb);
         });
     }
     for (auto& t : th) t.join();
+    g_tm.dump_trace("lanes");
     for (int rc : rcs)
         if (rc) return rc;
     return BPPP_OK;
@@ -1742,6 +2023,7 @@ int bppp_host_sha256(const uint8_t* data, size_t n, uint8_t out[32]) {
     return 0;
 }
 int bppp_host_oracle(const uint8_t* pts, size_t npts, int count, int show_format, uint8_t* out) {
+    if (!h64::host_cpu_ok()) return BPPP_ERR_STATE;
     tr::Zkpt zk;
     zk.fmt = show_format;
     std::vector<Fr> o(count);
@@ -1750,6 +2032,7 @@ int bppp_host_oracle(const uint8_t* pts, size_t npts, int count, int show_format
     return 0;
 }
 int bppp_host_fr(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
+    if (!h64::host_cpu_ok()) return BPPP_ERR_STATE;
     Fr x = h64::from_bytes(a), y = h64::from_bytes(b), r;
     switch (op) {
         case 0: r = h64::mul(x, y); break;

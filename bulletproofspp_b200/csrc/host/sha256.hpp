@@ -82,6 +82,59 @@ __attribute__((target("sha,sse4.1,ssse3"))) inline void compress_shani(uint32_t 
     _mm_storeu_si128((__m128i*)&st[0], STATE0);
     _mm_storeu_si128((__m128i*)&st[4], STATE1);
 }
+// two independent messages, block for block: SHA256RNDS2 is latency-bound, so interleaving a
+// second stream nearly doubles the throughput of one core (used for pairs of transcripts)
+__attribute__((target("sha,sse4.1,ssse3"))) inline void compress_shani_x2(uint32_t sa[8], const uint8_t* pa, uint32_t sb[8],
+                                                                           const uint8_t* pb, size_t nblk) {
+    const __m128i MASK = _mm_set_epi64x(0x0c0d0e0f08090a0bULL, 0x0405060700010203ULL);
+    __m128i TA = _mm_shuffle_epi32(_mm_loadu_si128((const __m128i*)&sa[0]), 0xB1);
+    __m128i A1 = _mm_shuffle_epi32(_mm_loadu_si128((const __m128i*)&sa[4]), 0x1B);
+    __m128i A0 = _mm_alignr_epi8(TA, A1, 8);
+    A1 = _mm_blend_epi16(A1, TA, 0xF0);
+    __m128i TB = _mm_shuffle_epi32(_mm_loadu_si128((const __m128i*)&sb[0]), 0xB1);
+    __m128i B1 = _mm_shuffle_epi32(_mm_loadu_si128((const __m128i*)&sb[4]), 0x1B);
+    __m128i B0 = _mm_alignr_epi8(TB, B1, 8);
+    B1 = _mm_blend_epi16(B1, TB, 0xF0);
+    for (; nblk; nblk--, pa += 64, pb += 64) {
+        const __m128i SA0 = A0, SA1 = A1, SB0 = B0, SB1 = B1;
+        __m128i MA[4], MB[4];
+        for (int i = 0; i < 4; i++) {
+            MA[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(pa + 16 * i)), MASK);
+            MB[i] = _mm_shuffle_epi8(_mm_loadu_si128((const __m128i*)(pb + 16 * i)), MASK);
+        }
+#pragma GCC unroll 16
+        for (int r = 0; r < 16; r++) {
+            const __m128i k = _mm_loadu_si128((const __m128i*)&K[4 * r]);
+            __m128i ma = _mm_add_epi32(MA[r & 3], k), mb = _mm_add_epi32(MB[r & 3], k);
+            A1 = _mm_sha256rnds2_epu32(A1, A0, ma);
+            B1 = _mm_sha256rnds2_epu32(B1, B0, mb);
+            if (r >= 3 && r < 15) {
+                __m128i ta = _mm_alignr_epi8(MA[r & 3], MA[(r + 3) & 3], 4);
+                __m128i tb = _mm_alignr_epi8(MB[r & 3], MB[(r + 3) & 3], 4);
+                MA[(r + 1) & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(MA[(r + 1) & 3], ta), MA[r & 3]);
+                MB[(r + 1) & 3] = _mm_sha256msg2_epu32(_mm_add_epi32(MB[(r + 1) & 3], tb), MB[r & 3]);
+            }
+            ma = _mm_shuffle_epi32(ma, 0x0E);
+            mb = _mm_shuffle_epi32(mb, 0x0E);
+            A0 = _mm_sha256rnds2_epu32(A0, A1, ma);
+            B0 = _mm_sha256rnds2_epu32(B0, B1, mb);
+            if (r >= 1 && r < 13) {
+                MA[(r + 3) & 3] = _mm_sha256msg1_epu32(MA[(r + 3) & 3], MA[r & 3]);
+                MB[(r + 3) & 3] = _mm_sha256msg1_epu32(MB[(r + 3) & 3], MB[r & 3]);
+            }
+        }
+        A0 = _mm_add_epi32(A0, SA0); A1 = _mm_add_epi32(A1, SA1);
+        B0 = _mm_add_epi32(B0, SB0); B1 = _mm_add_epi32(B1, SB1);
+    }
+    TA = _mm_shuffle_epi32(A0, 0x1B);
+    A1 = _mm_shuffle_epi32(A1, 0xB1);
+    _mm_storeu_si128((__m128i*)&sa[0], _mm_blend_epi16(TA, A1, 0xF0));
+    _mm_storeu_si128((__m128i*)&sa[4], _mm_alignr_epi8(A1, TA, 8));
+    TB = _mm_shuffle_epi32(B0, 0x1B);
+    B1 = _mm_shuffle_epi32(B1, 0xB1);
+    _mm_storeu_si128((__m128i*)&sb[0], _mm_blend_epi16(TB, B1, 0xF0));
+    _mm_storeu_si128((__m128i*)&sb[4], _mm_alignr_epi8(B1, TB, 8));
+}
 inline bool has_shani() {
     static int cached = -1;
     if (cached < 0) {
@@ -134,6 +187,91 @@ inline void digest3(uint8_t out[32], const uint8_t* a, size_t na, const uint8_t*
     for (int i = 0; i < 8; i++) {
         out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
         out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+    }
+}
+// Streaming form used for PAIRS of messages: both are cut into pieces (prefix, body, ...) and
+// advanced together with the two-stream compressor; whatever does not line up falls back to the
+// single-stream one.
+struct Stream {
+    uint32_t st[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint8_t buf[128];
+    size_t fill = 0;
+    uint64_t total = 0;
+    const uint8_t* p = nullptr;          // current piece
+    size_t n = 0;
+    void piece(const uint8_t* q, size_t len) { p = q; n = len; total += len; }
+    // top up the partial block from the current piece; true when a full block sits in buf
+    void top_up() {
+        if (fill) {
+            size_t take = 64 - fill < n ? 64 - fill : n;
+            memcpy(buf + fill, p, take);
+            fill += take; p += take; n -= take;
+            if (fill == 64) { compress(st, buf, 1); fill = 0; }
+        }
+    }
+    void stash() { if (n) { memcpy(buf + fill, p, n); fill += n; p += n; n = 0; } }
+    void finish(uint8_t out[32]) {
+        buf[fill++] = 0x80;
+        size_t padto = fill <= 56 ? 64 : 128;
+        memset(buf + fill, 0, padto - fill);
+        uint64_t bits = total * 8;
+        for (int i = 0; i < 8; i++) buf[padto - 1 - i] = (uint8_t)(bits >> (8 * i));
+        compress(st, buf, padto / 64);
+        for (int i = 0; i < 8; i++) {
+            out[4 * i] = (uint8_t)(st[i] >> 24); out[4 * i + 1] = (uint8_t)(st[i] >> 16);
+            out[4 * i + 2] = (uint8_t)(st[i] >> 8); out[4 * i + 3] = (uint8_t)st[i];
+        }
+    }
+};
+// digests of (a0 | a1) and (b0 | b1)
+inline void digest2x2(uint8_t outa[32], const uint8_t* a0, size_t na0, const uint8_t* a1, size_t na1, uint8_t outb[32],
+                      const uint8_t* b0, size_t nb0, const uint8_t* b1, size_t nb1) {
+    Stream A, B;
+    const uint8_t* pa[2] = {a0, a1};
+    const uint8_t* pb[2] = {b0, b1};
+    size_t la[2] = {na0, na1}, lb[2] = {nb0, nb1};
+    for (int k = 0; k < 2; k++) {
+        A.piece(pa[k], la[k]);
+        B.piece(pb[k], lb[k]);
+        A.top_up();
+        B.top_up();
+        size_t blk = (A.n < B.n ? A.n : B.n) / 64;
+#if defined(__x86_64__)
+        if (blk && has_shani()) {
+            compress_shani_x2(A.st, A.p, B.st, B.p, blk);
+            A.p += blk * 64; A.n -= blk * 64;
+            B.p += blk * 64; B.n -= blk * 64;
+        }
+#endif
+        if (A.n >= 64) { size_t b = A.n / 64; compress(A.st, A.p, b); A.p += b * 64; A.n -= b * 64; }
+        if (B.n >= 64) { size_t b = B.n / 64; compress(B.st, B.p, b); B.p += b * 64; B.n -= b * 64; }
+        A.stash();
+        B.stash();
+    }
+    A.finish(outa);
+    B.finish(outb);
+}
+// two messages of at most 55 bytes each (one padded block): the RNG's hash(seed <> show counter)
+inline void digest_short_x2(uint8_t outa[32], const uint8_t* a, size_t na, uint8_t outb[32], const uint8_t* b, size_t nb) {
+    static const uint32_t IV[8] = {0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19};
+    uint32_t sa[8], sb[8];
+    memcpy(sa, IV, 32);
+    memcpy(sb, IV, 32);
+    uint8_t ba[64], bb[64];
+    memset(ba, 0, 64);
+    memset(bb, 0, 64);
+    memcpy(ba, a, na); ba[na] = 0x80; ba[62] = (uint8_t)((na * 8) >> 8); ba[63] = (uint8_t)(na * 8);
+    memcpy(bb, b, nb); bb[nb] = 0x80; bb[62] = (uint8_t)((nb * 8) >> 8); bb[63] = (uint8_t)(nb * 8);
+#if defined(__x86_64__)
+    if (has_shani()) compress_shani_x2(sa, ba, sb, bb, 1);
+    else
+#endif
+    { compress_portable(sa, ba, 1); compress_portable(sb, bb, 1); }
+    for (int i = 0; i < 8; i++) {
+        outa[4 * i] = (uint8_t)(sa[i] >> 24); outa[4 * i + 1] = (uint8_t)(sa[i] >> 16);
+        outa[4 * i + 2] = (uint8_t)(sa[i] >> 8); outa[4 * i + 3] = (uint8_t)sa[i];
+        outb[4 * i] = (uint8_t)(sb[i] >> 24); outb[4 * i + 1] = (uint8_t)(sb[i] >> 16);
+        outb[4 * i + 2] = (uint8_t)(sb[i] >> 8); outb[4 * i + 3] = (uint8_t)sb[i];
     }
 }
 inline void digest(uint8_t out[32], const std::string& s) {

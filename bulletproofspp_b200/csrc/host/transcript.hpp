@@ -62,10 +62,17 @@ inline void append_show_field(std::string& out, const uint64_t v[4], int fmt) {
     if (fmt == PREFIXED_P) out.append("P ");
     append_decimal(out, v);
 }
+inline int format_uint(char* dst, uint64_t x) {        // decimal, no terminator; returns the length (<= 20)
+    char buf[24];
+    char* p = buf + sizeof buf;
+    do { *--p = (char)('0' + x % 10); x /= 10; } while (x);
+    int n = (int)(buf + sizeof buf - p);
+    memcpy(dst, p, n);
+    return n;
+}
 inline void append_uint(std::string& out, uint64_t x) {
     char buf[24];
-    int n = snprintf(buf, sizeof buf, "%llu", (unsigned long long)x);
-    out.append(buf, n);
+    out.append(buf, format_uint(buf, x));
 }
 // digest -> integer: four big-endian Word64, first word least significant (Encoding.hs:75-79)
 inline void digest_to_words(uint64_t w[4], const uint8_t d[32]) {
@@ -110,27 +117,148 @@ struct Zkpt {
         append_uint(s, n_random++);
         return hash_to_fr(s);
     }
+    // the next n values of `random`, two one-block hashes at a time when seed <> counter fits a block
+    void random_fill(Fr* out, size_t n) {
+        size_t i = 0;
+        if (seed.size() + 20 <= 55) {
+            uint8_t m0[64], m1[64], d0[32], d1[32];
+            memcpy(m0, seed.data(), seed.size());
+            memcpy(m1, seed.data(), seed.size());
+            for (; i + 1 < n; i += 2) {
+                size_t l0 = seed.size() + format_uint((char*)m0 + seed.size(), n_random++);
+                size_t l1 = seed.size() + format_uint((char*)m1 + seed.size(), n_random++);
+                sha::digest_short_x2(d0, m0, l0, d1, m1, l1);
+                uint64_t w[4];
+                digest_to_words(w, d0);
+                out[i] = h64::from_wide(w);
+                digest_to_words(w, d1);
+                out[i + 1] = h64::from_wide(w);
+            }
+        }
+        for (; i < n; i++) out[i] = random();
+    }
+    // the same values as canonical 32-byte little-endian scalars (for blinders that go straight to the device)
+    void random_fill_canonical(uint8_t* out, size_t n) {
+        size_t i = 0;
+        auto put = [](uint8_t* dst, const uint8_t d[32]) {
+            uint64_t w[4];
+            digest_to_words(w, d);
+            if (h64::geq_n(w)) h64::sub_n(w);                 // 2^256 < 2r
+            memcpy(dst, w, 32);
+        };
+        if (seed.size() + 20 <= 55) {
+            uint8_t m0[64], m1[64], d0[32], d1[32];
+            memcpy(m0, seed.data(), seed.size());
+            memcpy(m1, seed.data(), seed.size());
+            for (; i + 1 < n; i += 2) {
+                size_t l0 = seed.size() + format_uint((char*)m0 + seed.size(), n_random++);
+                size_t l1 = seed.size() + format_uint((char*)m1 + seed.size(), n_random++);
+                sha::digest_short_x2(d0, m0, l0, d1, m1, l1);
+                put(out + 32 * i, d0);
+                put(out + 32 * (i + 1), d1);
+            }
+        }
+        for (; i < n; i++) {
+            std::string s = seed;
+            append_uint(s, n_random++);
+            uint8_t d[32];
+            sha::digest(d, s);
+            put(out + 32 * i, d);
+        }
+    }
     // `oracle xs` -> first `count` scalars of shaOracle cs' (ZKP.hs:96-101, app/Main.hs:75-80)
-    void oracle(const uint8_t* pts, size_t npts, Fr* out, int count) {
+    void absorb(const uint8_t* pts, size_t npts) {
         std::string add;
         add.reserve(npts * 170 + body.size());
         for (size_t i = 0; i < npts; i++) add += show_point(pts + 64 * i, fmt);
         add += body;
         body.swap(add);
         n_coms += npts;
-        std::string len;
-        append_uint(len, n_coms);
-        for (int i = 1; i <= count; i++) {
-            std::string pre;
-            append_uint(pre, (uint64_t)i);
-            pre += len;
+    }
+    // scalar i (1-based) of the current transcript: hash(show i <> show (length cs) <> coords)
+    static std::string prefix_of(uint64_t i, uint64_t n_coms) {
+        std::string pre;
+        append_uint(pre, i);
+        append_uint(pre, n_coms);
+        return pre;
+    }
+    static Fr digest_to_fr(const uint8_t d[32]) {
+        uint64_t w[4];
+        digest_to_words(w, d);
+        return h64::from_wide(w);
+    }
+    void squeeze(Fr* out, int count) {
+        int i = 1;
+        for (; i + 1 <= count; i += 2) {                  // two challenges at a time (two-stream SHA)
+            std::string p0 = prefix_of(i, n_coms), p1 = prefix_of(i + 1, n_coms);
+            uint8_t d0[32], d1[32];
+            sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), (const uint8_t*)body.data(), body.size(), d1,
+                           (const uint8_t*)p1.data(), p1.size(), (const uint8_t*)body.data(), body.size());
+            hashed_bytes += p0.size() + p1.size() + 2 * body.size();
+            out[i - 1] = digest_to_fr(d0);
+            out[i] = digest_to_fr(d1);
+        }
+        if (i <= count) {
+            std::string pre = prefix_of(i, n_coms);
             uint8_t d[32];
             sha::digest3(d, (const uint8_t*)pre.data(), pre.size(), (const uint8_t*)body.data(), body.size(), nullptr, 0);
             hashed_bytes += pre.size() + body.size();
-            uint64_t w[4];
-            digest_to_words(w, d);
-            out[i - 1] = h64::from_wide(w);
+            out[i - 1] = digest_to_fr(d);
         }
+    }
+    void oracle(const uint8_t* pts, size_t npts, Fr* out, int count) {
+        absorb(pts, npts);
+        squeeze(out, count);
+    }
+    // the first challenge of two different transcripts, hashed together
+    static void oracle_pair(Zkpt& a, const uint8_t* pa, Zkpt& b, const uint8_t* pb, size_t npts, Fr* ea, Fr* eb) {
+        a.absorb(pa, npts);
+        b.absorb(pb, npts);
+        std::string p0 = prefix_of(1, a.n_coms), p1 = prefix_of(1, b.n_coms);
+        uint8_t d0[32], d1[32];
+        sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), (const uint8_t*)a.body.data(), a.body.size(), d1,
+                       (const uint8_t*)p1.data(), p1.size(), (const uint8_t*)b.body.data(), b.body.size());
+        a.hashed_bytes += p0.size() + a.body.size();
+        b.hashed_bytes += p1.size() + b.body.size();
+        *ea = digest_to_fr(d0);
+        *eb = digest_to_fr(d1);
+    }
+    // Verifier side of proveBPM's challenges: all k round messages are known up front, and the
+    // transcript after round r is a SUFFIX of the final one (newest first).  pts = the (X,R) pairs
+    // in hashing order (oldest round first); out[r] = challenge of round r.
+    void oracle_rounds(const uint8_t* const* round_pts, size_t k, Fr* out) {
+        if (!k) return;
+        std::vector<std::string> shown(k);
+        size_t total = body.size();
+        for (size_t r = 0; r < k; r++) {
+            shown[r] = show_point(round_pts[r], fmt) + show_point(round_pts[r] + 64, fmt);
+            total += shown[r].size();
+        }
+        std::string fin;
+        fin.reserve(total);
+        std::vector<size_t> off(k);                        // offset of round r's transcript inside fin
+        for (size_t r = k; r-- > 0;) { off[r] = fin.size(); fin += shown[r]; }
+        fin += body;
+        const uint8_t* base = (const uint8_t*)fin.data();
+        size_t r = 0;
+        for (; r + 1 < k; r += 2) {
+            std::string p0 = prefix_of(1, n_coms + 2 * (r + 1)), p1 = prefix_of(1, n_coms + 2 * (r + 2));
+            uint8_t d0[32], d1[32];
+            sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), base + off[r], fin.size() - off[r], d1,
+                           (const uint8_t*)p1.data(), p1.size(), base + off[r + 1], fin.size() - off[r + 1]);
+            hashed_bytes += p0.size() + p1.size() + 2 * fin.size() - off[r] - off[r + 1];
+            out[r] = digest_to_fr(d0);
+            out[r + 1] = digest_to_fr(d1);
+        }
+        if (r < k) {
+            std::string pre = prefix_of(1, n_coms + 2 * (r + 1));
+            uint8_t d[32];
+            sha::digest3(d, (const uint8_t*)pre.data(), pre.size(), base + off[r], fin.size() - off[r], nullptr, 0);
+            hashed_bytes += pre.size() + fin.size() - off[r];
+            out[r] = digest_to_fr(d);
+        }
+        body.swap(fin);
+        n_coms += 2 * k;
     }
 };
 

@@ -1016,6 +1016,286 @@ __global__ void __launch_bounds__(128) k_fb_msm(const Affine* __restrict__ tbl, 
 }
 
 // ------------------------------------------------------------------------------------------
+// TypedReciprocal scalar phases (proveTRRPM phases 2-4, TypedReciprocal.hs:412-444): the per-entry
+// ("norm" part) vector arithmetic of the range proof -- reciprocals, error terms, public
+// constants and the combined argument witness -- one thread per group of 4 Phase-1 entries, one
+// CTA per proof.  The host keeps the transcript, the blinders and the few "linear" slots.
+//   entry i:  d_i (digit, or the type for a typing entry), m_i (inline multiplicity),
+//             u_i = x^(2(ind+1)) * b_i (typing: x^(2(ind+1)) or 0), v_i = x^(3+2*baseidx) (typing: +-x)
+//             r_i = ps_i / (e + d_i),  c_i = v_i (1/e - 1/(e + s_i))            (makePhase2s, :171-195)
+// ------------------------------------------------------------------------------------------
+struct TrrpEnt { uint32_t flags; int32_t ind; int32_t base_idx; int32_t pad; };
+enum { TE_T = 1, TE_IO = 2, TE_IA = 4, TE_I = 8, TE_S = 16 };
+struct TrrpStatic {
+    const TrrpEnt* ent; const u256* b; const u256* s;   // [n_ent]; b, s Montgomery
+    int n_ent, n_ranges, n_bases;
+};
+#define TRRP_THREADS 256
+#define TRRP_PER 4
+
+__device__ __forceinline__ u256 shfl_down_u256(const u256& a, int off) {
+    u256 r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], off);
+    return r;
+}
+// sum over the CTA (all threads must call); the result is valid in thread 0
+__device__ __noinline__ u256 trrp_block_sum(u256 v, u256* sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+    for (int off = 16; off >= 1; off >>= 1) v = fr::add(v, shfl_down_u256(v, off));
+    __syncthreads();
+    if (lane == 0) sm[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0)
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = fr::add(v, sm[w]);
+    return v;
+}
+__device__ __noinline__ u256 trrp_pow(u256 base, unsigned e) {      // base^e, e >= 1
+    u256 acc = base;
+    int top = 31 - __clz(e);
+    for (int k = top - 1; k >= 0; k--) {
+        acc = fr::sqr(acc);
+        if ((e >> k) & 1) acc = fr::mul(acc, base);
+    }
+    return acc;
+}
+// x-power tables: xp[p][ind] = x^(2(ind+1)), vt[p][j] = x^(3+2j)   (TypedReciprocal.hs:353, :181)
+__global__ void k_trrp_tables(const u256* __restrict__ chal, int chal_stride, int x_idx, int n_ranges, int n_bases,
+                              u256* __restrict__ xp, u256* __restrict__ vt, int B) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= B) return;
+    u256 x = fr::to_mont(ld_u256(chal + (size_t)p * chal_stride + x_idx));
+    u256 x2 = fr::sqr(x), cur = x2;
+    for (int i = 0; i < n_ranges; i++) { st_u256(xp + (size_t)p * n_ranges + i, cur); cur = fr::mul(cur, x2); }
+    cur = fr::mul(x2, x);
+    for (int j = 0; j < n_bases; j++) { st_u256(vt + (size_t)p * n_bases + j, cur); cur = fr::mul(cur, x2); }
+}
+struct TrrpEntry { u256 d, m, u, v; bool isT, live; };
+__device__ __forceinline__ void trrp_load_entry(TrrpEntry& o, const TrrpStatic& st, int i, const u256* scA_dm, const u256* scA_m,
+                                                const u256* xp, const u256* vt, const u256& x, bool want_m) {
+    o.live = i < st.n_ent;
+    if (!o.live) return;
+    const TrrpEnt en = st.ent[i];
+    o.isT = en.flags & TE_T;
+    o.d = fr::to_mont(ld_u256(scA_dm + 1 + i));
+    o.m = want_m ? fr::to_mont(ld_u256(scA_m + 1 + i)) : u256_zero();
+    const u256 xpi = ld_u256(xp + en.ind);
+    if (o.isT) {
+        o.u = (en.flags & TE_IA) ? u256_zero() : xpi;
+        o.v = (en.flags & TE_IO) ? fr::neg(x) : x;
+    } else {
+        o.u = fr::mul(xpi, ld_u256(st.b + i));
+        o.v = ld_u256(vt + en.base_idx);
+    }
+}
+
+struct TrrpP2Args {
+    TrrpStatic st;
+    const u256* chal;                  // [B][4] canonical: e, 1/e, x, 1/r0
+    const u256* scA; size_t P0;        // [B][2][P0] canonical: dm scalars, m scalars
+    const u256* amounts;               // [B][n_ranges] canonical (the committed values)
+    const u256* xp; const u256* vt;
+    u256* r; u256* c;                  // [B][n_ent] Montgomery
+    u256* scR;                         // [B][P0] canonical scalars of the reciprocal commitment
+    int err7_slot;                     // index inside a scR row
+    u256* err7;                        // [B] canonical
+};
+__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_phase2(TrrpP2Args A) {
+    __shared__ u256 sm[TRRP_THREADS / 32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const u256 e = fr::to_mont(ld_u256(A.chal + (size_t)p * 4 + 0));
+    const u256 e_inv = fr::to_mont(ld_u256(A.chal + (size_t)p * 4 + 1));
+    const u256 r0_inv = fr::to_mont(ld_u256(A.chal + (size_t)p * 4 + 3));
+    const u256* dm = A.scA + (size_t)p * 2 * A.P0;
+    const u256* vt = A.vt + (size_t)p * A.st.n_bases;
+    u256 e7 = u256_zero();
+    for (int i0 = tid * TRRP_PER; i0 < A.st.n_ent; i0 += TRRP_THREADS * TRRP_PER) {
+        u256 den[2 * TRRP_PER], pre[2 * TRRP_PER];
+        bool use[2 * TRRP_PER];
+        u256 acc = fr::one();
+#pragma unroll
+        for (int j = 0; j < TRRP_PER; j++) {
+            const int i = i0 + j;
+            use[j] = use[TRRP_PER + j] = false;
+            if (i < A.st.n_ent) {
+                const TrrpEnt en = A.st.ent[i];
+                den[j] = fr::add(e, fr::to_mont(ld_u256(dm + 1 + i)));
+                use[j] = !u256_is_zero(den[j]);
+                if ((en.flags & TE_I) && (en.flags & TE_S)) {
+                    den[TRRP_PER + j] = fr::add(e, ld_u256(A.st.s + i));
+                    use[TRRP_PER + j] = !u256_is_zero(den[TRRP_PER + j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2 * TRRP_PER; k++)
+            if (use[k]) { pre[k] = acc; acc = fr::mul(acc, den[k]); }
+        u256 inv = fr::inv(acc);
+#pragma unroll
+        for (int k = 2 * TRRP_PER - 1; k >= 0; k--)
+            if (use[k]) { u256 t = fr::mul(inv, pre[k]); inv = fr::mul(inv, den[k]); den[k] = t; }
+            else den[k] = u256_zero();
+#pragma unroll
+        for (int j = 0; j < TRRP_PER; j++) {
+            const int i = i0 + j;
+            if (i >= A.st.n_ent) continue;
+            const TrrpEnt en = A.st.ent[i];
+            u256 r = den[j];
+            if (en.flags & TE_T) r = fr::mul(r, fr::to_mont(ld_u256(A.amounts + (size_t)p * A.st.n_ranges + en.ind)));
+            u256 c = u256_zero();
+            if (use[TRRP_PER + j]) {
+                const u256 v = ld_u256(vt + en.base_idx);
+                c = fr::mul(v, fr::sub(e_inv, den[TRRP_PER + j]));
+                e7 = fr::add(e7, fr::dbl(fr::mul(r, c)));
+            }
+            st_u256(A.r + (size_t)p * A.st.n_ent + i, r);
+            st_u256(A.c + (size_t)p * A.st.n_ent + i, c);
+            st_u256(A.scR + (size_t)p * A.P0 + 1 + i, fr::from_mont(r));
+        }
+    }
+    e7 = trrp_block_sum(e7, sm);
+    if (tid == 0) {
+        const u256 err7 = fr::from_mont(fr::mul(r0_inv, fr::neg(e7)));
+        st_u256(A.err7 + p, err7);
+        st_u256(A.scR + (size_t)p * A.P0 + A.err7_slot, err7);
+    }
+}
+
+struct TrrpP3Args {
+    TrrpStatic st;
+    const u256* chal2;                 // [B][4] (phase 2): e, 1/e, x, 1/r0
+    const u256* chal3;                 // [B][2] canonical: q0 (= the q-power base), x'
+    const u256* scA; size_t P0;
+    const u256* r; const u256* c;
+    const u256* bl;                    // [B][n_ent] canonical blinders of the norm part
+    const u256* xp; const u256* vt;
+    u256* errs;                        // [B][6] canonical (without the shared-multiplicity term of err3)
+};
+// makeErrorTerms (TypedReciprocal.hs:217-233) over the norm entries
+__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_errterms(TrrpP3Args A) {
+    __shared__ u256 sm[TRRP_THREADS / 32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const u256 e = fr::to_mont(ld_u256(A.chal2 + (size_t)p * 4 + 0));
+    const u256 x = fr::to_mont(ld_u256(A.chal2 + (size_t)p * 4 + 2));
+    const u256 q0 = fr::to_mont(ld_u256(A.chal3 + (size_t)p * 2 + 0));
+    const u256 xq = fr::to_mont(ld_u256(A.chal3 + (size_t)p * 2 + 1));
+    const u256* dm = A.scA + (size_t)p * 2 * A.P0;
+    const u256* mm = dm + A.P0;
+    const u256* xp = A.xp + (size_t)p * A.st.n_ranges;
+    const u256* vt = A.vt + (size_t)p * A.st.n_bases;
+    u256 t0 = u256_zero(), h1 = t0, t2 = t0, h2 = t0, h3 = t0, t4 = t0, h4 = t0, t5 = t0, h5 = t0;
+    for (int i0 = tid * TRRP_PER; i0 < A.st.n_ent; i0 += TRRP_THREADS * TRRP_PER) {
+        u256 q2 = trrp_pow(q0, (unsigned)i0 + 1);
+#pragma unroll 1
+        for (int j = 0; j < TRRP_PER; j++) {
+            const int i = i0 + j;
+            if (i >= A.st.n_ent) break;
+            if (j) q2 = fr::mul(q2, q0);
+            TrrpEntry o;
+            trrp_load_entry(o, A.st, i, dm, mm, xp, vt, x, true);
+            const u256 r = ld_u256(A.r + (size_t)p * A.st.n_ent + i);
+            const u256 c = ld_u256(A.c + (size_t)p * A.st.n_ent + i);
+            const u256 bl = fr::to_mont(ld_u256(A.bl + (size_t)p * A.st.n_ent + i));
+            const u256 rC = o.isT ? fr::mul(xq, fr::add(o.u, q2)) : o.u;
+            const u256 dC = fr::add(o.v, fr::mul(q2, e));
+            const u256 q2d = fr::mul(q2, o.d), q2r = fr::mul(q2, r);
+            const u256 qd = fr::add(q2d, dC), qr = fr::add(q2r, rC);
+            const u256 q2bl = fr::mul(q2, bl);
+            t0 = fr::add(t0, fr::mul(q2bl, bl));
+            h2 = fr::add(h2, fr::mul(bl, qd));
+            h3 = fr::add(h3, fr::mul(bl, qr));
+            t4 = fr::add(t4, fr::mul(o.d, fr::add(q2d, fr::dbl(dC))));
+            t5 = fr::add(t5, fr::mul(r, fr::add(q2r, fr::dbl(rC))));
+            if (!u256_is_zero(o.m)) {
+                h1 = fr::add(h1, fr::mul(q2bl, o.m));
+                t2 = fr::add(t2, fr::mul(q2, fr::sqr(o.m)));
+                h3 = fr::add(h3, fr::mul(o.m, qd));
+                h4 = fr::add(h4, fr::mul(o.m, qr));
+            }
+            if (!u256_is_zero(c)) {
+                h4 = fr::add(h4, fr::mul(bl, c));
+                h5 = fr::add(h5, fr::mul(c, o.d));
+            }
+        }
+    }
+    t0 = trrp_block_sum(t0, sm); h1 = trrp_block_sum(h1, sm); t2 = trrp_block_sum(t2, sm);
+    h2 = trrp_block_sum(h2, sm); h3 = trrp_block_sum(h3, sm); t4 = trrp_block_sum(t4, sm);
+    h4 = trrp_block_sum(h4, sm); t5 = trrp_block_sum(t5, sm); h5 = trrp_block_sum(h5, sm);
+    if (tid == 0) {
+        u256* out = A.errs + (size_t)p * 6;
+        st_u256(out + 0, fr::from_mont(t0));
+        st_u256(out + 1, fr::from_mont(fr::dbl(h1)));
+        st_u256(out + 2, fr::from_mont(fr::add(t2, fr::dbl(h2))));
+        st_u256(out + 3, fr::from_mont(fr::dbl(h3)));
+        st_u256(out + 4, fr::from_mont(fr::add(t4, fr::dbl(h4))));
+        st_u256(out + 5, fr::from_mont(fr::add(t5, fr::dbl(h5))));
+    }
+}
+
+struct TrrpP4Args {
+    TrrpStatic st;
+    const u256* chal2; const u256* chal3;
+    const u256* chal4;                 // [B][2] canonical: t, 1/q0
+    const u256* scA; size_t P0;
+    const u256* r; const u256* c; const u256* bl;
+    const u256* xp; const u256* vt;
+    u256* w;                           // [B][n_ent] Montgomery: norm part of the argument witness
+    u256* sums;                        // [B][3] canonical: sum q2 p^2, sum q2 (digits), sum v (digits)
+};
+// makePublicConsts' norm part (TypedReciprocal.hs:236-263) fused with the witness combination
+//   wit = pub + bl + t m + t^2 dm + t^3 r   (:439; the inputs have no norm part)
+__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_phase4(TrrpP4Args A) {
+    __shared__ u256 sm[TRRP_THREADS / 32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const u256 e = fr::to_mont(ld_u256(A.chal2 + (size_t)p * 4 + 0));
+    const u256 x = fr::to_mont(ld_u256(A.chal2 + (size_t)p * 4 + 2));
+    const u256 q0 = fr::to_mont(ld_u256(A.chal3 + (size_t)p * 2 + 0));
+    const u256 xq = fr::to_mont(ld_u256(A.chal3 + (size_t)p * 2 + 1));
+    const u256 t = fr::to_mont(ld_u256(A.chal4 + (size_t)p * 2 + 0));
+    const u256 q0_inv = fr::to_mont(ld_u256(A.chal4 + (size_t)p * 2 + 1));
+    const u256 t2 = fr::sqr(t), t3 = fr::mul(t2, t), t4 = fr::sqr(t2);
+    const u256 t2e = fr::mul(t2, e), t3xq = fr::mul(t3, xq), constT = fr::add(t2e, t3xq);
+    const u256* dm = A.scA + (size_t)p * 2 * A.P0;
+    const u256* mm = dm + A.P0;
+    const u256* xp = A.xp + (size_t)p * A.st.n_ranges;
+    const u256* vt = A.vt + (size_t)p * A.st.n_bases;
+    u256 ts0 = u256_zero(), sq2 = ts0, sv = ts0;
+    for (int i0 = tid * TRRP_PER; i0 < A.st.n_ent; i0 += TRRP_THREADS * TRRP_PER) {
+        u256 q2 = trrp_pow(q0, (unsigned)i0 + 1), qi2 = trrp_pow(q0_inv, (unsigned)i0 + 1);
+#pragma unroll 1
+        for (int j = 0; j < TRRP_PER; j++) {
+            const int i = i0 + j;
+            if (i >= A.st.n_ent) break;
+            if (j) { q2 = fr::mul(q2, q0); qi2 = fr::mul(qi2, q0_inv); }
+            TrrpEntry o;
+            trrp_load_entry(o, A.st, i, dm, mm, xp, vt, x, true);
+            const u256 r = ld_u256(A.r + (size_t)p * A.st.n_ent + i);
+            const u256 c = ld_u256(A.c + (size_t)p * A.st.n_ent + i);
+            const u256 bl = fr::to_mont(ld_u256(A.bl + (size_t)p * A.st.n_ent + i));
+            u256 inner = fr::mul(t2, o.v);
+            if (!u256_is_zero(o.u)) inner = fr::add(inner, fr::mul(o.isT ? t3xq : t3, o.u));
+            if (!u256_is_zero(c)) inner = fr::add(inner, fr::mul(t4, c));
+            const u256 pi = fr::add(o.isT ? constT : t2e, fr::mul(qi2, inner));
+            ts0 = fr::add(ts0, fr::mul(q2, fr::sqr(pi)));
+            if (!o.isT) { sq2 = fr::add(sq2, q2); sv = fr::add(sv, o.v); }
+            u256 w = fr::add(pi, bl);
+            if (!u256_is_zero(o.m)) w = fr::add(w, fr::mul(t, o.m));
+            w = fr::add(w, fr::mul(t2, o.d));
+            w = fr::add(w, fr::mul(t3, r));
+            st_u256(A.w + (size_t)p * A.st.n_ent + i, w);
+        }
+    }
+    ts0 = trrp_block_sum(ts0, sm); sq2 = trrp_block_sum(sq2, sm); sv = trrp_block_sum(sv, sm);
+    if (tid == 0) {
+        u256* out = A.sums + (size_t)p * 3;
+        st_u256(out + 0, fr::from_mont(ts0));
+        st_u256(out + 1, fr::from_mont(sq2));
+        st_u256(out + 2, fr::from_mont(sv));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // debug / self-test kernels (exercised by tests/ through bppp_dbg_*)
 // ------------------------------------------------------------------------------------------
 __global__ void k_dbg_field(const u256* a, const u256* b, u256* out, size_t n, int op) {

@@ -145,6 +145,43 @@ int bppp_nl_verify_gens(bppp_gens* gens, int kind, size_t batch, size_t k, const
                         size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s,
                         const uint8_t* init_p, int* ok);
 
+/* ---- TypedReciprocal scalar phases on the device.
+ * Replaces the per-entry ("norm" part, one slot per Phase-1 entry) arithmetic of proveTRRPM,
+ * src/RangeProof/TypedReciprocal.hs:399-444: makePhase2s' reciprocals r_i = ps_i/(e+d_i) and
+ * c_i (:171-195), makeErrorTerms (:217-233), makePublicConsts (:236-263) and the witness
+ * combination pub + bl + t m + t^2 dm + t^3 r (:439).  The transcript, the blinders and the few
+ * scalar/"linear" slots stay with the caller.  Static per-entry description (from the schema):
+ *   ent_desc[i] = {u32 flags, i32 range index, i32 shared-base index (x^(3+2j), bases sorted), i32 0}
+ *   flags: 1 typing entry, 2 output, 4 assumed, 8 inline digit, 16 symbol s_i != 0
+ *   ent_b[i] = digit coefficient b_i, ent_s[i] = symbol s_i        (32-byte canonical scalars)
+ * Calls must follow phase1 -> phase2 -> phase3 -> commit_bl -> phase4 -> bppp_nl_create_trrp;
+ * n_entries must equal the generator set's N.  All scalars are 32-byte little-endian canonical. */
+typedef struct bppp_trrp bppp_trrp;
+int bppp_trrp_create(bppp_gens* gens, size_t n_entries, const uint8_t* ent_desc, const uint8_t* ent_b,
+                     const uint8_t* ent_s, size_t n_ranges, size_t n_bases, bppp_trrp** out);
+void bppp_trrp_destroy(bppp_trrp* h);
+/* phase 1 (:399-410): sc_dm_m = [batch][2][1+N+M] commitment scalars of the digit and multiplicity
+ * witnesses (scalar slot, norm slots, linear slots); amounts = [batch][n_ranges] committed values.
+ * coms = [batch][2] points (dmCom, mCom). */
+int bppp_trrp_phase1(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, uint8_t* coms);
+/* phase 2 (:412-419): chal = [batch][4] = (e, 1/e, x, 1/r0); r_sclin = [batch][1+M] scalar slot and
+ * linear slots of the reciprocal witness (blindErrWitness, Internal.hs:142-152) with the err7 slot
+ * zero; err7_slot = its index in the linear part.  rcom = [batch] points, err7 = [batch] scalars. */
+int bppp_trrp_phase2(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
+                     uint8_t* err7);
+/* phase 3a (:421-433): chal = [batch][2] = (q-power base, x'); bls_nrm = [batch][N] norm-part
+ * blinders.  errs = [batch][6] error terms summed over the norm entries (the caller adds the
+ * shared-multiplicity term 2 sum cs_i bls_i to errs[3]). */
+int bppp_trrp_phase3(bppp_trrp* h, const uint8_t* chal, const uint8_t* bls_nrm, uint8_t* errs);
+/* phase 3b (:434): bl_sclin = [batch][1+M] scalar and linear slots of the blinding witness. */
+int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom);
+/* phase 4 (:435-444): chal = [batch][2] = (t, 1/q0).  sums = [batch][3] = (sum q2_i p_i^2 over all
+ * entries, sum q2_i and sum v_i over the digit entries); the combined witness stays on the device. */
+int bppp_trrp_phase4(bppp_trrp* h, const uint8_t* chal, uint8_t* sums);
+/* the norm-linear argument (bppp_nl_create_gens) over the device-resident witness of phase 4 */
+int bppp_nl_create_trrp(bppp_trrp* h, const uint8_t* q, const uint8_t* s, const uint8_t* l, const uint8_t* c,
+                        bppp_nl** out);
+
 /* ---- Range-proof layer (host C++ above the device entry points; the Fiat-Shamir transcript,
  * round sequencing and the scalar phases run on host threads, every group operation on the GPU).
  * Mirrors RPOpening / RangeProof (src/RangeProof.hs:25-101) for TypedReciprocal
