@@ -155,6 +155,10 @@ def make_inputs(batch, offset, n_inputs):
     return vals, tys, seeds
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/README.md)
+NCU_TRAFFIC_BYTES = {"k_msm_gens": 52996352 + 64272640}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,8 +245,7 @@ def main():
     assert run_steps(lambda k: inputs, args.warmup) == B * args.warmup, "a warm-up proof failed to verify"
     # ---- timed region 1: `value` -- inputs staged before the clock starts, device-timed
     for c in lanes:
-        c.profile_enable(True)
-        c.profile_reset()
+        c.profile_reset()               # zero the H2D / D2H byte counters
     launches0 = sum(c.launch_count() for c in lanes)
     sampler = ClockSampler(local)
     sampler.start()
@@ -257,10 +260,8 @@ def main():
     barrier()
     clocks = sampler.stop()
     assert n_ok == B * args.steps
-    rep = merged_report()
     launches = sum(c.launch_count() for c in lanes) - launches0
-    for c in lanes:
-        c.profile_enable(False)
+    h2d0 = merged_report()      # byte counters are always on; kernel events only when profiling is enabled
     # ---- timed region 2: `e2e` -- inputs built on the host every step, verdicts read back
     barrier()
     t0 = time.time()
@@ -269,6 +270,27 @@ def main():
     barrier()
     e2e_s = time.time() - t0
     t_dev, t_e2e = ms / 1e3, e2e_s
+    # ---- per-kernel times for the rooflines: ONE lane's share of a step (B / lanes proofs, prove then
+    # verify) on a single stream with a CUDA-event pair around every launch.  In the timed regions the
+    # lanes' streams overlap, so an event pair there also times other lanes' kernels; serialised, the
+    # shares line up with the ncu launch list in profiles/.
+    lanes_per_setup = len(setup.contexts())
+    Bp = max(1, B // lanes_per_setup)
+    os.environ["BPPP_LANES"] = "1"
+    pctx = bp.Context(local)
+    psetup = bp.RangeProofSetup(pctx, workload_schema())
+    pin = make_inputs(Bp, base, n)
+    proof = psetup.prove_batch_raw(Bp, pin[0], pin[1], None, pin[2])            # warm-up (tables, pools)
+    pctx.profile_enable(True)
+    pctx.profile_reset()
+    tp0 = time.time()
+    proof = psetup.prove_batch_raw(Bp, pin[0], pin[1], None, pin[2])
+    assert sum(psetup.verify_batch_raw(Bp, *proof)) == Bp
+    pctx.sync()
+    prof_wall = time.time() - tp0
+    rep = pctx.profile_report()
+    pctx.profile_enable(False)
+    rep["h2d_bytes"], rep["d2h_bytes"] = h2d0["h2d_bytes"], h2d0["d2h_bytes"]
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,13 +316,17 @@ def main():
     kt = kern[top]
     ach = kt["work"] / (kt["ms"] * 1e-3) / 1e12
     roofline = {"kernel": top, "bound": "imad", "achieved": ach, "peak": imad_wide / 1e12, "unit": "TIMAD/s",
-                "frac": ach / (imad_wide / 1e12), "traffic": None,
+                "frac": ach / (imad_wide / 1e12), "traffic": NCU_TRAFFIC_BYTES.get(top),
+                "traffic_note": "dram read+write bytes of one 512-proof launch, ncu --set full (profiles/), ~0.3 % of what HBM "
+                                "could move in the launch time: the kernel is integer-pipe bound",
                 "avg_launch_ms": kt["ms"] / kt["launches"], "share_of_gpu_time": shares[top],
-                "note": "integer-pipe bound (no hbm/tensor roofline applies): achieved = algorithmic 32x32->64 IMADs "
-                        "(SURVEY 8(d) op counts) / CUDA-event time; peak = IMAD.WIDE issue rate measured in this run"}
+                "note": "integer-pipe bound (no hbm/tensor roofline applies): achieved = algorithmic 32x32->64 IMADs in the "
+                        "reference's units (SURVEY 8(d): Pippenger MSMs over each round's CURRENT lengths + the half-length "
+                        "generator folds this kernel absorbs) / CUDA-event time; peak = IMAD.WIDE issue rate measured in this run. "
+                        "The kernel executes ~1.5x that work (full-length fixed-base MSMs every round, DESIGN.md)"}
     rooflines = {}
     for name in ("k_msm_bucket", "k_pair_fold"):
-        if name in kern and kern[name]["ms"] > 0:
+        if name in kern and kern[name]["ms"] > 0 and kern[name]["work"] > 0:
             a = kern[name]["work"] / (kern[name]["ms"] * 1e-3) / 1e12
             rooflines[name] = {"bound": "imad", "achieved": a, "peak": imad_wide / 1e12, "unit": "TIMAD/s",
                                "frac": a / (imad_wide / 1e12), "share_of_gpu_time": shares[name]}
@@ -322,7 +348,11 @@ def main():
                     "note": "host buffers in, proofs + verdicts out through bppp_rp_prove_batch/bppp_rp_verify_batch; "
                             "inputs rebuilt on the host every step, wall clock"},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "rooflines": rooflines,
-            "kernel_time_shares": shares, "gpu_kernel_ms_over_step_ms": tot_ms / ms,
+            "kernel_time_shares": shares,
+            "gpu_busy_estimate": tot_ms * lanes_per_setup / (1e3 * t_dev / args.steps),
+            "profile_pass": {"proofs": Bp, "kernel_ms": tot_ms, "wall_s": prof_wall,
+                             "note": "one lane's share of a step (prove then verify) on a single stream with a CUDA-event pair "
+                                     "around every launch, run after the timed regions; gpu_busy_estimate = kernel_ms x lanes / ms_per_step"},
             "imad_peak": {"wide_per_s": imad_wide, "lo32_per_s": imad_lo}, "wall_s_value_leg": wall}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()

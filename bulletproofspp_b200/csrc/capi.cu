@@ -103,12 +103,15 @@ static void prof_collect(bppp_ctx* c) {
 
 // algorithmic work per launch for the rooflines: IMADs (32x32->64 multiply-accumulates)
 // for the group-law kernels, bytes for the scalar fold.
-static double msm_alg_imads(double n) {          // ceil(256/c*) (n + 2^(c*-1)) * 11 * 136
+static double msm_alg_imads(double n, double bits = 256.0) {   // ceil(bits/c*) (n + 2^(c*-1)) * 11 * 136
     if (n < 1) return 0;
     int c = (int)floor(log2(n)) - 2;
     if (c < 4) c = 4;
-    return ceil(256.0 / c) * (n + pow(2.0, c - 1)) * 11.0 * 136.0;
+    return ceil(bits / c) * (n + pow(2.0, c - 1)) * 11.0 * 136.0;
 }
+// one folded generator = 3.9k Fq-mul * 136 = 5.3e5 IMAD with 256-bit scalars; the
+// half-length (a, b) of rationalReduceScalar halve it
+static double fold_alg_imads(double n_points) { return n_points * 0.5 * 3.9e3 * 136.0; }
 #define WORK_K_MSM_BUCKET g_work
 #define WORK_K_MSM_FINISH 0
 #define WORK_K_BATCH_TO_AFFINE 0
@@ -1265,11 +1268,11 @@ TrrpStatic trrp_static(bppp_trrp* h) {
     return st;
 }
 // MSM of `n_msm` scalar rows of length P0 (device resident, canonical) over the lane's generators -> affine, host
-int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out) {
+int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double scalar_bits = 256.0) {
     bppp_ctx* ctx = h->gens->ctx;
     const size_t P0 = h->gens->P0;
     CK(h->res.ensure(n_msm)); CK(h->aff.ensure(n_msm));
-    int rc = run_msm_gens(h->gens, P0, sc, P0, 0, n_msm, 1, h->res.p, msm_alg_imads((double)P0));
+    int rc = run_msm_gens(h->gens, P0, sc, P0, 0, n_msm, 1, h->res.p, msm_alg_imads((double)P0, scalar_bits));
     if (rc) return rc;
     if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, n_msm))) return rc;
     CK(D2H(out, h->aff.p, n_msm * 64));
@@ -1333,7 +1336,7 @@ extern "C" int bppp_trrp_phase1(bppp_trrp* h, size_t batch, const uint8_t* sc_dm
     CK(H2D(h->scA.p, sc_dm_m, batch * 2 * P0 * 32));
     CK(H2D(h->amounts.p, amounts, batch * h->n_ranges * 32));
     h->phase = 1;
-    return trrp_commit(h, h->scA.p, 2 * batch, coms);
+    return trrp_commit(h, h->scA.p, 2 * batch, coms, 16.0);    // digits and multiplicities: short scalars
 }
 // phase 2 (:412-419): chal = [batch][4] (e, 1/e, x, 1/r0); r_sclin = [batch][1 + M] scalar and linear
 // slots of the reciprocal witness with the err7 slot zero; err7_slot indexes the linear part.
@@ -1627,8 +1630,12 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     }
     // the two commitments: MSMs over [g | G | H] with X scalars (output 0) and R scalars (output 1)
     const size_t nterms = h->tensor ? P0 : 1 + h->curN + h->curM;
-    const double nX = (double)nterms, nR = 1.0 + (double)((h->curN + 1) / 2) + (double)((h->curM + 1) / 2);
-    const double work = msm_alg_imads(nX) + msm_alg_imads(nR);
+    // algorithmic work of this round in the reference's units: the X and R MSMs over the
+    // CURRENT lengths, plus -- in tensor mode, where the launch below also does the job of the
+    // previous round's generator fold (the folded generators are never materialised) -- that fold
+    const double nX = 1.0 + (double)h->curN + (double)h->curM, nR = 1.0 + (double)((h->curN + 1) / 2) + (double)((h->curM + 1) / 2);
+    double work = msm_alg_imads(nX) + msm_alg_imads(nR);
+    if (h->tensor && h->round > 0) work += fold_alg_imads((double)(h->curN + h->curM));
     if (h->curp < 0 || h->tensor) {
         // the generators are the shared list -> fixed-base tables
         if ((rc = run_msm_gens(h->gens, nterms, xs, P0, B * P0, B, 2, h->res.p, work))) return rc;

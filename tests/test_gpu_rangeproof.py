@@ -137,3 +137,23 @@ def test_wire_format_roundtrip_and_oracle_bytes(ctx, name):
     c3, r3, f3, ok3 = setup.decode_batch_raw(B, bytes(bad), commits_bin)
     assert ok3 == [True, True] and setup.verify_batch_raw(B, c3, r3, f3) == [False, True]
     setup.close()
+
+
+@pytest.mark.parametrize("name", ["typed_nl", "32by64", "128by64"])
+def test_device_scalar_phases_match_host_phases(ctx, name, monkeypatch):
+    """The TypedReciprocal scalar phases run on the device by default (bppp_trrp_*); with
+    BPPP_RP_HOST_PHASES=1 the same proofs come from the host implementation of those phases.
+    Both must be bit-identical (and equal to the golden vectors, checked above).  A batch of 70
+    proofs spreads over several lanes."""
+    import bulletproofspp_b200 as bp
+    schema, wits, seeds = batched(name, {"32by64": 70, "128by64": 3}.get(name, 1))   # typed proofs must stay balanced
+    dev = bp.RangeProofSetup(ctx, schema)
+    p_dev = dev.prove_batch(wits, seeds)
+    monkeypatch.setenv("BPPP_RP_HOST_PHASES", "1")
+    host = bp.RangeProofSetup(ctx, schema)
+    monkeypatch.delenv("BPPP_RP_HOST_PHASES")
+    p_host = host.prove_batch(wits, seeds)
+    assert p_dev == p_host
+    assert all(dev.verify_batch(p_host)) and all(host.verify_batch(p_dev))
+    dev.close()
+    host.close()
