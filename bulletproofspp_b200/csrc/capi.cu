@@ -22,11 +22,11 @@ using namespace bppp;
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
-                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases"};
+                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -670,7 +670,7 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
     int nch = (int)((n_terms + GT_MAX_CHUNK - 1) / GT_MAX_CHUNK);
     size_t ctas = batch * n_out * nch;
     DBuf<Jac> scratch, partsbuf;     // stream-ordered pool allocations: cheap, and safe across lanes
-    CK(scratch.alloc(ctas * (GT_KEYS + 2 * GT_THREADS)));
+    CK(scratch.alloc(ctas * GT_SCRATCH(GT_THREADS)));
     Jac* parts = d_out;
     if (nch > 1) { CK(partsbuf.alloc(ctas)); parts = partsbuf.p; }
     int max_n = (int)std::min<size_t>(GT_MAX_CHUNK, n_terms);
@@ -678,11 +678,18 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         size_t nb = std::min<size_t>(32768, batch - b0);
         GtArgs A;
         A.tbl = g->tbl.p; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
-        A.n_total = (int)n_terms; A.scratch = scratch.p + b0 * n_out * nch * (GT_KEYS + 2 * GT_THREADS);
-        A.out = parts + b0 * n_out * nch; A.n_out = n_out; A.n_chunks = nch;
+        A.n_total = (int)n_terms; A.term0 = 0; A.chunk_terms = GT_MAX_CHUNK;
+        A.scratch = scratch.p + b0 * n_out * nch * GT_SCRATCH(GT_THREADS);
+        A.out = parts + b0 * n_out * nch; A.out_pstride = (size_t)n_out * nch; A.n_out = n_out; A.n_chunks = nch;
         g_work = work_per_proof * (double)nb;
         { ProfScope ps_(ctx, K_MSM_GENS, g_work);
         k_msm_gens<<<dim3(nch, n_out, (unsigned)nb), GT_THREADS, gt_smem_bytes(max_n), ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+        const size_t n_cta = nb * n_out * nch;
+        { ProfScope ps_(ctx, K_MSM_REDUCE, 0);
+        k_msm_gens_reduce<<<(unsigned)((n_cta + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH(GT_THREADS), A.out, A.out_pstride,
+                                                                           n_out, nch, n_cta);
         }
         CK(cudaGetLastError());
     }
@@ -690,6 +697,45 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         size_t n_msm = batch * n_out;
         { ProfScope ps_(ctx, K_JAC_SUM, 0);
         k_jac_sum<<<(unsigned)((n_msm + 127) / 128), 128, 0, ctx->st>>>(parts, nch, nullptr, 0, d_out, n_msm);
+        }
+        CK(cudaGetLastError());
+    }
+    return BPPP_OK;
+}
+// One small fixed-base MSM per GROUP of `group` consecutive generators [term0 + j*group, ...) of every
+// proof (scalars sc[p*sc_stride + term]): out[p*out_pstride + j], j < ceil(n_terms/group).  Used to
+// materialise the folded generators of a tensor-mode argument (G'_j = sum over its block of
+// coef_i * G_i) when it switches to folding.
+int run_msm_groups(bppp_gens* g, const u256* sc, size_t sc_stride, size_t batch, size_t term0, size_t n_terms, size_t group,
+                   Jac* out, size_t out_pstride) {
+    bppp_ctx* ctx = g->ctx;
+    if (n_terms == 0) return BPPP_OK;
+    static bool attr = false;
+    if (!attr) {
+        CK(cudaFuncSetAttribute(k_msm_gens_small, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        attr = true;
+    }
+    if (group > 512) FAIL(BPPP_ERR_ARG, "run_msm_groups: group too large");
+    const size_t ng = (n_terms + group - 1) / group;
+    const size_t smem = gt_smem_bytes((int)group);
+    // the per-CTA scratch is large (61 KB): launch in slices of proofs
+    size_t per = std::max<size_t>(1, std::min<size_t>(batch, 4096 / std::max<size_t>(1, ng)));
+    per = std::min<size_t>(per, 32768);
+    DBuf<Jac> scratch;
+    CK(scratch.alloc(per * ng * GT_SCRATCH(GT_THREADS_SMALL)));
+    for (size_t b0 = 0; b0 < batch; b0 += per) {
+        const size_t nb = std::min(per, batch - b0);
+        GtArgs A;
+        A.tbl = g->tbl.p; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = 0;
+        A.n_total = (int)n_terms; A.term0 = (int)term0; A.chunk_terms = (int)group;
+        A.scratch = scratch.p; A.out = out + b0 * out_pstride; A.out_pstride = out_pstride; A.n_out = 1; A.n_chunks = (int)ng;
+        { ProfScope ps_(ctx, K_MSM_GROUPS, 0);
+        k_msm_gens_small<<<dim3((unsigned)ng, 1, (unsigned)nb), GT_THREADS_SMALL, smem, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+        { ProfScope ps_(ctx, K_MSM_REDUCE, 0);
+        k_msm_gens_reduce<<<(unsigned)((nb * ng + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH(GT_THREADS_SMALL), A.out, A.out_pstride,
+                                                                            1, (int)ng, nb * ng);
         }
         CK(cudaGetLastError());
     }
@@ -1659,6 +1705,50 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     return BPPP_OK;
 }
 
+namespace {
+// BPPP_HYBRID_MAX=n: a tensor-mode argument switches to folding once at most n generators are left
+// (default 0 = never).  From there on a round needs a handful of pair folds and two tiny MSMs
+// instead of two full-length fixed-base MSMs -- about a quarter less arithmetic per 128by64 proof --
+// but the small-size kernels (k_msm_gens_small, k_pair_fold, k_msm_bucket on <= 96 points) are
+// latency-bound, and measured end to end the switch loses (6380 -> 4224..5592 proofs/s for n = 96..24),
+// so it stays opt-in until those kernels are reworked.  Results are bit-identical either way (tested).
+size_t hybrid_limit() {
+    const char* ev = getenv("BPPP_HYBRID_MAX");
+    return ev ? (size_t)atoll(ev) : (size_t)0;
+}
+// Materialise the folded generators G^(r)_j = sum_{idx >> r == j} coef_idx * G_idx of every proof (one
+// small fixed-base MSM per block of 2^r original generators) and continue in fold mode.
+int nl_switch_to_fold(bppp_nl* h) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, N = h->N, M = h->M, P0 = h->P0, cn = h->curN, cl = h->curM, group = (size_t)1 << h->round;
+    CK(h->pts[0].ensure(B * h->P2)); CK(h->pts[1].ensure(B * h->P2));
+    CK(h->jscratch.ensure(B * (h->N2 + h->M2)));
+    u256* sc = h->sc.p;                                   // free between rounds: canonical coefficients in scalar-row layout
+    for (int seg = 0; seg < 2; seg++) {
+        const size_t n0 = seg ? M : N;
+        if (!n0) continue;
+        { ProfScope ps_(ctx, K_FR_CONVERT, 0);
+        k_fr_from_mont_rows<<<dim3((unsigned)((n0 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(
+            h->coef.p + (seg ? N : 0), N + M, sc, P0, 1 + (int)(seg ? N : 0), (int)n0);
+        }
+        CK(cudaGetLastError());
+    }
+    int rc;
+    if ((rc = run_msm_groups(h->gens, sc, P0, B, 1, N, group, h->jscratch.p, cn + cl))) return rc;
+    if ((rc = run_msm_groups(h->gens, sc, P0, B, 1 + N, M, group, h->jscratch.p + cn, cn + cl))) return rc;
+    if ((rc = to_affine(ctx, h->jscratch.p, cn + cl, h->pts[0].p, h->P2, 1, (int)(cn + cl), B * (cn + cl)))) return rc;
+    for (int k = 0; k < 2; k++) {
+        { ProfScope ps_(ctx, K_BCAST, 0);
+        k_bcast_point<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(h->gens->base.p, h->pts[k].p, h->P2, B);
+        }
+        CK(cudaGetLastError());
+    }
+    h->tensor = false;
+    h->curp = 0;
+    return BPPP_OK;
+}
+}  // namespace
+
 extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
@@ -1735,6 +1825,8 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
         h->curN = nN;
         h->curM = nM;
         h->round++;
+        if (hybrid_limit() && !h->shard_lo && nN + nM <= hybrid_limit() && nN + nM >= 12 && h->round <= 9 && (rc = nl_switch_to_fold(h)))
+            return rc;
         CK(cudaStreamSynchronize(ctx->st));
         return BPPP_OK;
     }

@@ -77,6 +77,15 @@ __global__ void k_fr_convert(const u256* __restrict__ in, u256* __restrict__ out
     st_u256(out + i, to_mont ? fr::to_mont(a) : fr::from_mont(a));
 }
 
+// out[p*out_stride + out_off + i] = canonical(in[p*in_stride + i])   (Montgomery -> integer, strided rows)
+__global__ void k_fr_from_mont_rows(const u256* __restrict__ in, size_t in_stride, u256* __restrict__ out, size_t out_stride,
+                                    int out_off, int n) {
+    const int p = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_u256(out + (size_t)p * out_stride + out_off + i, fr::from_mont(ld_u256(in + (size_t)p * in_stride + i)));
+}
+
 // ------------------------------------------------------------------------------------------
 // K1: fused scalar fold + weighted pair dots.
 //
@@ -713,32 +722,38 @@ struct GtArgs {
     const Affine* tbl;                 // [n_total][GT_W]
     const u256* sc; size_t sc_stride;  // canonical scalars, per proof; + output * sc_out_stride
     size_t sc_out_stride;
-    int n_total;                       // terms per MSM; chunk c covers [c*GT_MAX_CHUNK, ...)
-    Jac* scratch;                      // per CTA: [GT_KEYS] key sums + [2*GT_THREADS] boundary run sums
-    Jac* out;                          // [batch][n_out][n_chunks]
+    int n_total;                       // terms of this launch: [term0, term0 + n_total)
+    int term0;                         // first term (index into the generator list / scalar row)
+    int chunk_terms;                   // terms per CTA (<= GT_MAX_CHUNK): chunk c covers [term0 + c*chunk_terms, ...)
+    Jac* scratch;                      // per CTA: [GT_KEYS] key sums + [GT_NB] bucket sums + [2*T] boundary run sums
+    Jac* out;                          // out[p*out_pstride + o*n_chunks + chunk]
+    size_t out_pstride;
     int n_out, n_chunks;
 };
 __device__ __forceinline__ int gt_digit(const u256& s, int j, int& carry) { return signed_digit(s, j, GT_C, carry); }
+#define GT_SCRATCH(T) (GT_KEYS + GT_NB + 2 * (T))
 
-__global__ void __launch_bounds__(GT_THREADS, 2) k_msm_gens(GtArgs A) {
+template <int T>
+__device__ __forceinline__ void msm_gens_body(const GtArgs& A) {
     extern __shared__ unsigned char gt_smem[];
     const int chunk = blockIdx.x, o = blockIdx.y, p = blockIdx.z;
-    const int base = chunk * GT_MAX_CHUNK;
-    const int n = min(GT_MAX_CHUNK, A.n_total - base);
+    const int base = A.term0 + chunk * A.chunk_terms;
+    const int n = min(A.chunk_terms, A.term0 + A.n_total - base);
     const u256* sc = A.sc + (size_t)p * A.sc_stride + (size_t)o * A.sc_out_stride + base;
     const Affine* tbl = A.tbl + (size_t)base * GT_W;
     unsigned* offs = reinterpret_cast<unsigned*>(gt_smem);                 // [GT_KEYS + 1]
     unsigned* cur = offs + GT_KEYS + 1;                                    // [GT_KEYS]
     unsigned short* list = reinterpret_cast<unsigned short*>(cur + GT_KEYS);
     const size_t cta = ((size_t)p * A.n_out + o) * A.n_chunks + chunk;
-    Jac* keysum = A.scratch + cta * (GT_KEYS + 2 * GT_THREADS);
-    Jac* slotF = keysum + GT_KEYS;
-    Jac* slotL = slotF + GT_THREADS;
+    Jac* keysum = A.scratch + cta * GT_SCRATCH(T);
+    Jac* bsum = keysum + GT_KEYS;
+    Jac* slotF = bsum + GT_NB;
+    Jac* slotL = slotF + T;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < GT_KEYS; i += GT_THREADS) cur[i] = 0;
+    for (int i = tid; i < GT_KEYS; i += T) cur[i] = 0;
     __syncthreads();
-    for (int i = tid; i < n; i += GT_THREADS) {                           // (1) count
+    for (int i = tid; i < n; i += T) {                                    // (1) count
         u256 s = ld_u256(sc + i);
         if (u256_is_zero(s)) continue;
         int carry = 0;
@@ -764,7 +779,7 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_msm_gens(GtArgs A) {
         if (tid == 31) offs[GT_KEYS] = pre;
     }
     __syncthreads();
-    for (int i = tid; i < n; i += GT_THREADS) {                           // (3) fill
+    for (int i = tid; i < n; i += T) {                                    // (3) fill
         u256 s = ld_u256(sc + i);
         if (u256_is_zero(s)) continue;
         int carry = 0;
@@ -779,12 +794,11 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_msm_gens(GtArgs A) {
     }
     __syncthreads();
     const unsigned E = offs[GT_KEYS];
-    Jac* outp = A.out + cta;
     if (E == 0) {
-        if (tid == 0) st_jac(outp, jac_inf());
+        for (int m = tid; m < GT_NB; m += T) st_jac(bsum + m, jac_inf());
         return;
     }
-    const unsigned L = (E + GT_THREADS - 1) / GT_THREADS;
+    const unsigned L = (E + T - 1) / T;
     {                                                                      // (4) balanced accumulate
         const unsigned a = min(E, tid * L), b = min(E, a + L);
         if (a < b) {
@@ -813,11 +827,12 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_msm_gens(GtArgs A) {
     }
     __threadfence_block();
     __syncthreads();
-    {                                                                      // (5a) merge runs per key, combine signs
-        Jac bm = jac_inf();                                                // bucket magnitude tid+1
+#pragma unroll 1
+    for (int m = tid; m < GT_NB; m += T) {                                 // (5a) merge runs per key, combine signs
+        Jac bm = jac_inf();                                                // bucket magnitude m+1
 #pragma unroll 1
         for (int sgn = 0; sgn < 2; sgn++) {
-            const int key = tid * 2 + sgn;
+            const int key = m * 2 + sgn;
             const unsigned k0 = offs[key], k1 = offs[key + 1];
             if (k0 == k1) continue;
             Jac sum = jac_inf();
@@ -830,34 +845,51 @@ __global__ void __launch_bounds__(GT_THREADS, 2) k_msm_gens(GtArgs A) {
             }
             bm = jac_add(bm, sgn ? jac_neg(sum) : sum);
         }
-        __syncthreads();                                                   // everyone has read the scratch
-        st_jac(keysum + tid, bm);                                          // reuse keysum[0..255] as B_m
+        st_jac(bsum + m, bm);
     }
-    __threadfence_block();
-    __syncthreads();
-    if (tid < 32) {                                                        // (5b) sum_m m * B_m
-        Jac S = jac_inf(), Wt = jac_inf();                                 // over this lane's 8 buckets (top down)
+    // (5b) sum_m m * B_m is a 30-addition dependency chain that only one warp can work on: it runs in
+    // k_msm_gens_reduce (one warp per MSM, every SM full) instead of idling 7 of this CTA's 8 warps.
+}
+__global__ void __launch_bounds__(GT_THREADS, 2) k_msm_gens(GtArgs A) { msm_gens_body<GT_THREADS>(A); }
+// the same MSM for many SMALL chunks (a few dozen terms each: the folded generators of a hybrid
+// argument): 64 threads per CTA so that 8 CTAs share an SM while warp 0 runs the bucket reduction
+#define GT_THREADS_SMALL 64
+__global__ void __launch_bounds__(GT_THREADS_SMALL, 8) k_msm_gens_small(GtArgs A) { msm_gens_body<GT_THREADS_SMALL>(A); }
+
+// Second half of the fixed-base MSM: out = sum_m m * B_m over the 256 bucket sums each k_msm_gens CTA
+// left in its scratch.  One WARP per MSM: 8 buckets per lane by running sums, then a shuffle
+// suffix-scan and a tree.  cta = (p*n_out + o)*n_chunks + chunk as in the first kernel.
+__global__ void __launch_bounds__(256) k_msm_gens_reduce(const Jac* __restrict__ scratch, size_t scratch_stride, Jac* __restrict__ out,
+                                                         size_t out_pstride, int n_out, int n_chunks, size_t n_cta) {
+    const size_t cta = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (cta >= n_cta) return;
+    const int tid = threadIdx.x & 31;
+    const Jac* bsum = scratch + cta * scratch_stride + GT_KEYS;
+    Jac S = jac_inf(), Wt = jac_inf();                                     // over this lane's 8 buckets (top down)
 #pragma unroll 1
-        for (int k = 7; k >= 0; k--) {
-            S = jac_add(S, ld_jac(keysum + tid * 8 + k));
-            Wt = jac_add(Wt, S);                                           // sum_k (k+1) * B_{8 tid + k}
-        }
-        // total = sum_t (8 t * S_t + Wt_t) = 8 * sum_t t*S_t + sum_t Wt_t ;  sum_t t*S_t = sum_{t>=1} suffix_t
-        Jac suf = S;
+    for (int k = 7; k >= 0; k--) {
+        S = jac_add(S, ld_jac(bsum + tid * 8 + k));
+        Wt = jac_add(Wt, S);                                               // sum_k (k+1) * B_{8 tid + k}
+    }
+    // total = sum_t (8 t * S_t + Wt_t) = 8 * sum_t t*S_t + sum_t Wt_t ;  sum_t t*S_t = sum_{t>=1} suffix_t
+    Jac suf = S;
 #pragma unroll 1
-        for (int s2 = 1; s2 < 32; s2 <<= 1) {
-            Jac other = shfl_jac(suf, (tid + s2) & 31);
-            if (tid + s2 < 32) suf = jac_add(suf, other);
-        }
-        Jac acc = (tid == 0) ? jac_inf() : suf;                            // lanes 1..31 hold suffix sums
-        acc = jac_dbl(jac_dbl(jac_dbl(acc)));                              // * 8
-        acc = jac_add(acc, Wt);
+    for (int s2 = 1; s2 < 32; s2 <<= 1) {
+        Jac other = shfl_jac(suf, (tid + s2) & 31);
+        if (tid + s2 < 32) suf = jac_add(suf, other);
+    }
+    Jac acc = (tid == 0) ? jac_inf() : suf;                                // lanes 1..31 hold suffix sums
+    acc = jac_dbl(jac_dbl(jac_dbl(acc)));                                  // * 8
+    acc = jac_add(acc, Wt);
 #pragma unroll 1
-        for (int s2 = 16; s2 >= 1; s2 >>= 1) {
-            Jac other = shfl_jac(acc, (tid + s2) & 31);
-            if (tid < s2) acc = jac_add(acc, other);
-        }
-        if (tid == 0) st_jac(outp, acc);
+    for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+        Jac other = shfl_jac(acc, (tid + s2) & 31);
+        if (tid < s2) acc = jac_add(acc, other);
+    }
+    if (tid == 0) {
+        const size_t chunk = cta % (size_t)n_chunks, t = cta / (size_t)n_chunks;
+        const size_t o = t % (size_t)n_out, p = t / (size_t)n_out;
+        st_jac(out + p * out_pstride + o * (size_t)n_chunks + chunk, acc);
     }
 }
 

@@ -157,3 +157,21 @@ def test_device_scalar_phases_match_host_phases(ctx, name, monkeypatch):
     assert all(dev.verify_batch(p_host)) and all(host.verify_batch(p_dev))
     dev.close()
     host.close()
+
+
+def test_hybrid_round_mode_is_bit_identical(ctx, monkeypatch):
+    """BPPP_HYBRID_MAX switches a tensor-mode argument to generator folding for its last rounds (the
+    folded generators are materialised by one small fixed-base MSM per block).  Same proof bits."""
+    import bulletproofspp_b200 as bp
+    schema, wits, seeds = batched("128by64", 2)
+    g1 = load_golden("128by64#1")
+    setup = bp.RangeProofSetup(ctx, schema)
+    plain = setup.prove_batch(wits, seeds)
+    monkeypatch.setenv("BPPP_HYBRID_MAX", "96")
+    proofs = setup.prove_batch(wits, seeds)
+    monkeypatch.delenv("BPPP_HYBRID_MAX")
+    assert proofs == plain
+    p = proofs[1]
+    assert p["coms"] == g1["coms"] and p["responses"] == g1["responses"] and p["finals"] == g1["finals"]
+    assert setup.verify_batch(proofs) == [True, True]
+    setup.close()
