@@ -233,16 +233,29 @@ void parallel_for(size_t n, F fn) {
         return;
     }
     if (turns) {
-        double t0 = g_tm.on ? Timing::now() : 0;
-        g_cpu_turn.lock((int64_t)Timing::t_progress() * 1024 - t_lane_id);
-        double t1 = g_tm.on ? Timing::now() : 0;
-        std::function<void(size_t)> f = fn;
-        pool().run(n, nt - 1, f);
-        g_cpu_turn.unlock();
-        if (g_tm.on) {
-            g_turn_wait_us += (uint64_t)((t1 - t0) * 1e3);
-            g_turn_hold_us += (uint64_t)((Timing::now() - t1) * 1e3);
-            g_turn_calls++;
+        // A turn is not preemptible, so a long phase is cut into slices of about 1.5 ms: a lane whose
+        // device rounds wait for a few hundred microseconds of transcript hashing gets the cores at
+        // the next slice boundary instead of after a 20 ms host phase of another lane.
+        std::function<void(size_t)> whole = fn;
+        const int64_t prio = (int64_t)Timing::t_progress() * 1024 - t_lane_id;
+        size_t i0 = 0, slice = std::min<size_t>(n, (size_t)4 * nt);
+        while (i0 < n) {
+            const size_t cnt = std::min(slice, n - i0);
+            std::function<void(size_t)> f = [&whole, i0](size_t i) { whole(i0 + i); };
+            double t0 = Timing::now();
+            g_cpu_turn.lock(prio);
+            double t1 = Timing::now();
+            pool().run(cnt, nt - 1, f);
+            g_cpu_turn.unlock();
+            double t2 = Timing::now();
+            if (g_tm.on) {
+                g_turn_wait_us += (uint64_t)((t1 - t0) * 1e3);
+                g_turn_hold_us += (uint64_t)((t2 - t1) * 1e3);
+                g_turn_calls++;
+            }
+            i0 += cnt;
+            const double ms = std::max(t2 - t1, 0.02);
+            slice = (size_t)std::max<double>((double)nt, std::min<double>((double)n, (double)cnt * 1.5 / ms));
         }
         return;
     }
