@@ -178,11 +178,11 @@ def main():
 
     import torch
     import torch.distributed as dist
+    import bulletproofspp_b200 as bp
+    ctx = bp.Context(local)             # before torch creates the primary context: bppp_init asks for blocking syncs
     if world > 1:
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    import bulletproofspp_b200 as bp
-    ctx = bp.Context(local)
     if args.host_threads or world > 1:
         # ranks share the host: split the cores between them
         nt = args.host_threads or max(1, (os.cpu_count() or 1) // world)

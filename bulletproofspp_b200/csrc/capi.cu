@@ -44,7 +44,18 @@ struct bppp_ctx {
     double k_ms[K_COUNT] = {0}, k_work[K_COUNT] = {0};
     uint64_t k_n[K_COUNT] = {0};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaEvent_t sync_ev = nullptr;   // blocking-sync event: waiting host threads sleep whatever the device's schedule flags
 };
+// Wait for everything queued on the context's stream.  An event created with cudaEventBlockingSync
+// makes the calling thread sleep even when the primary context was created by someone else (torch,
+// the embedding application) without cudaDeviceScheduleBlockingSync: the lanes' driver threads
+// must not spin on the cores the host phases need.
+static cudaError_t ctx_sync(bppp_ctx* c) {
+    if (!c->sync_ev) return cudaStreamSynchronize(c->st);
+    cudaError_t e = cudaEventRecord(c->sync_ev, c->st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(c->sync_ev);
+}
 static cudaEvent_t prof_event(bppp_ctx* c) {
     cudaEvent_t e;
     if (!c->pool.empty()) { e = c->pool.back(); c->pool.pop_back(); return e; }
@@ -252,7 +263,7 @@ int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res, d
             MsmSlice* d2;
             CK(cudaMallocAsync((void**)&d2, nch * sizeof(MsmSlice), ctx->st));
             CK(H2D(d2, sl.data(), nch * sizeof(MsmSlice)));
-            CK(cudaStreamSynchronize(ctx->st));
+            CK(ctx_sync(ctx));
             B.slices = d2;
             B.partial = A.partial + b0 * n_out * nch * MSM_W;
             { ProfScope ps_(ctx, K_MSM_BUCKET, WORK_K_MSM_BUCKET);
@@ -310,6 +321,7 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
         delete c;
         return BPPP_ERR_CUDA;
     }
+    if (cudaEventCreateWithFlags(&c->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming) != cudaSuccess) c->sync_ev = nullptr;
     {   // keep freed blocks in the stream-ordered pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -323,6 +335,7 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
 extern "C" void bppp_free(bppp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->dev);
+    if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -341,7 +354,7 @@ extern "C" uint64_t bppp_launch_count(bppp_ctx* ctx) { return ctx ? ctx->launche
 extern "C" int bppp_sync(bppp_ctx* ctx) {
     if (!ctx) return BPPP_ERR_ARG;
     ENTER(ctx);
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 
@@ -388,7 +401,7 @@ extern "C" int bppp_timer_start(bppp_ctx* ctx) {
     if (!ctx) return BPPP_ERR_ARG;
     ENTER(ctx);
     if (!ctx->t0) { CK(cudaEventCreate(&ctx->t0)); CK(cudaEventCreate(&ctx->t1)); }
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     CK(cudaEventRecord(ctx->t0, ctx->st));
     return BPPP_OK;
 }
@@ -497,7 +510,7 @@ extern "C" int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8
     rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch);
     if (rc) return rc;
     CK(D2H(out, d_aff.p, batch * 64));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 extern "C" int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t out[64]) {
@@ -533,7 +546,7 @@ extern "C" int bppp_fb_create(bppp_ctx* ctx, size_t n_bases, const uint8_t* poin
     k_fb_build<<<(nt + 31) / 32, 32, 0, ctx->st>>>(d_b.p, (int)n_bases, d_j.p);
     }
     int rc = to_affine(ctx, d_j.p, total, fb->tbl.p, total, 0, (int)total, total);
-    if (rc == 0 && (e = cudaStreamSynchronize(ctx->st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
+    if (rc == 0 && (e = ctx_sync(ctx)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
     if (rc) { delete fb; return rc; }
     *out = fb;
     return BPPP_OK;
@@ -556,7 +569,7 @@ extern "C" int bppp_fb_msm_batch(bppp_fb* fb, size_t batch, const uint8_t* scala
     int rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch);
     if (rc) return rc;
     CK(D2H(out, d_aff.p, batch * 64));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 extern "C" void bppp_fb_destroy(bppp_fb* fb) { delete fb; }
@@ -630,7 +643,7 @@ extern "C" int bppp_pair_fold(bppp_ctx* ctx, size_t n_in, const uint8_t a[32], i
     rc = to_affine(ctx, d_j.p, n_out, d_out.p, n_out, 0, (int)n_out, n_out);
     if (rc) return rc;
     CK(D2H(points_out, d_out.p, n_out * 64));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 
@@ -769,7 +782,7 @@ extern "C" int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t
     k_gt_build<<<(unsigned)((gg->P0 + 63) / 64), 64, 0, ctx->st>>>(gg->base.p, gg->P0, tj.p);
     }
     int rc = to_affine(ctx, tj.p, total, gg->tbl.p, total, 0, (int)std::min<size_t>(total, 0x7fffffff), total);
-    if (rc == 0 && (e = cudaStreamSynchronize(ctx->st)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
+    if (rc == 0 && (e = ctx_sync(ctx)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
     if (rc) { delete gg; return rc; }
     *out = gg;
     return BPPP_OK;
@@ -796,7 +809,7 @@ extern "C" int bppp_gens_msm_batch(bppp_gens* g, size_t batch, size_t n, const u
     if (rc) return rc;
     if ((rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, batch))) return rc;
     CK(D2H(out, d_aff.p, batch * 64));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 
@@ -999,7 +1012,7 @@ int ip_create(bppp_nl* h, const uint8_t* q, const uint8_t* s, const uint8_t* w, 
     }
     CK(cudaMemsetAsync(h->sc.p, 0, 2 * B * h->P0 * 32, ctx->st));
     h->curN = Np;
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 
@@ -1084,7 +1097,7 @@ int ip_round_commit(bppp_nl* h, uint8_t* Lout, uint8_t* Rout) {
     std::vector<Fr> dots(B * 2);
     CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
     CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     for (size_t b = 0; b < B; b++) {
         memcpy(Lout + 64 * b, &xr[2 * b], 64);
         memcpy(Rout + 64 * b, &xr[2 * b + 1], 64);
@@ -1151,7 +1164,7 @@ int ip_round_fold(bppp_nl* h, const uint8_t* e) {
     h->curN = (h->curN + 1) / 2;
     h->curM = (h->curM + 1) / 2;
     h->round++;
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 
@@ -1170,13 +1183,13 @@ int ip_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
         }
         CK(cudaGetLastError());
         CK(D2H(w, out.p, B * cn * 2 * 32));
-        CK(cudaStreamSynchronize(ctx->st));
+        CK(ctx_sync(ctx));
     }
     if (l && cl) {
         std::vector<Fr> hl(B * cl);
         ctx->d2h += B * cl * 32;
         CK(cudaMemcpy2DAsync(hl.data(), cl * 32, h->l[h->cur].p, h->lstride[h->cur] * 32, cl * 32, B, cudaMemcpyDeviceToHost, ctx->st));
-        CK(cudaStreamSynchronize(ctx->st));
+        CK(ctx_sync(ctx));
         for (size_t b = 0; b < B; b++)
             for (size_t i = 0; i < cl; i++) h64::to_bytes(l + 32 * (b * cl + i), h64::mul(h->nl[b], hl[b * cl + i]));
     }
@@ -1259,7 +1272,7 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
         h->s[b] = h64::from_bytes(s + 32 * b);
     });
     h64::batch_inv(h->qinv.data(), batch);
-    CKH(cudaStreamSynchronize(ctx->st));
+    CKH(ctx_sync(ctx));
 #undef CKH
     *out = h;
     return BPPP_OK;
@@ -1322,7 +1335,7 @@ int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double
     if (rc) return rc;
     if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, n_msm))) return rc;
     CK(D2H(out, h->aff.p, n_msm * 64));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 }  // namespace
@@ -1353,7 +1366,7 @@ extern "C" int bppp_trrp_create(bppp_gens* gens, size_t n_entries, const uint8_t
     if ((e = cudaMemcpyAsync(h->small.p + n_entries, ent_s, n_entries * 32, cudaMemcpyHostToDevice, ctx->st))) return fail(e);
     k_fr_convert<<<(unsigned)((n_entries + 255) / 256), 256, 0, ctx->st>>>(h->small.p, h->eb.p, n_entries, 1);
     k_fr_convert<<<(unsigned)((n_entries + 255) / 256), 256, 0, ctx->st>>>(h->small.p + n_entries, h->es.p, n_entries, 1);
-    if ((e = cudaStreamSynchronize(ctx->st))) return fail(e);
+    if ((e = ctx_sync(ctx))) return fail(e);
     *out = h;
     return BPPP_OK;
 }
@@ -1437,7 +1450,7 @@ extern "C" int bppp_trrp_phase3(bppp_trrp* h, const uint8_t* chal, const uint8_t
     }
     CK(cudaGetLastError());
     CK(D2H(errs, h->small.p, B * 6 * 32));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     h->phase = 3;
     return BPPP_OK;
 }
@@ -1477,7 +1490,7 @@ extern "C" int bppp_trrp_phase4(bppp_trrp* h, const uint8_t* chal, uint8_t* sums
     }
     CK(cudaGetLastError());
     CK(D2H(sums, h->small.p, B * 3 * 32));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     h->phase = 5;
     return BPPP_OK;
 }
@@ -1530,7 +1543,7 @@ extern "C" int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* poi
         std::vector<Fr> hc(B * NM);
         if (h->round > 0) {
             CK(D2H(hc.data(), h->coef.p, B * NM * 32));
-            CK(cudaStreamSynchronize(ctx->st));
+            CK(ctx_sync(ctx));
         } else {
             for (auto& v : hc) v = h64::one();
         }
@@ -1551,7 +1564,7 @@ extern "C" int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* poi
         if (rc) return rc;
         if ((rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, B * NO))) return rc;
         CK(D2H(points, d_aff.p, B * NO * 64));
-        CK(cudaStreamSynchronize(ctx->st));
+        CK(ctx_sync(ctx));
         points = nullptr;                                   // done
     }
     for (size_t b = 0; b < B; b++) {
@@ -1576,7 +1589,7 @@ extern "C" int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* poi
         }
         CK(D2H(c, tmp.p, B * cl * 32));
     }
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 
@@ -1695,7 +1708,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     std::vector<Fr> dots(B * 2);
     CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
     CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     for (size_t b = 0; b < B; b++) {
         memcpy(X + 64 * b, &xr[2 * b], 64);
         memcpy(R + 64 * b, &xr[2 * b + 1], 64);
@@ -1827,7 +1840,7 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
         h->round++;
         if (hybrid_limit() && !h->shard_lo && nN + nM <= hybrid_limit() && nN + nM >= 12 && h->round <= 9 && (rc = nl_switch_to_fold(h)))
             return rc;
-        CK(cudaStreamSynchronize(ctx->st));
+        CK(ctx_sync(ctx));
         return BPPP_OK;
     }
     // generators
@@ -1847,7 +1860,7 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     h->curN = nN;
     h->curM = nM;
     h->round++;
-    CK(cudaStreamSynchronize(ctx->st));   // host vectors above go out of scope
+    CK(ctx_sync(ctx));   // host vectors above go out of scope
     return BPPP_OK;
 }
 
@@ -1860,7 +1873,7 @@ extern "C" int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
     std::vector<Fr> hw(B * cn), hl(B * cl);
     if (w && cn) { ctx->d2h += B * cn * 32; CK(cudaMemcpy2DAsync(hw.data(), cn * 32, h->w[h->cur].p, h->wstride[h->cur] * 32, cn * 32, B, cudaMemcpyDeviceToHost, ctx->st)); }
     if (l && cl) { ctx->d2h += B * cl * 32; CK(cudaMemcpy2DAsync(hl.data(), cl * 32, h->l[h->cur].p, h->lstride[h->cur] * 32, cl * 32, B, cudaMemcpyDeviceToHost, ctx->st)); }
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     for (size_t b = 0; b < B; b++) {
         if (s) h64::to_bytes(s + 32 * b, h->s[b]);
         if (w) for (size_t i = 0; i < cn; i++) h64::to_bytes(w + 32 * (b * cn + i), h64::mul(h->nn[b], hw[b * cn + i]));
@@ -2011,7 +2024,7 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
         ctx->d2h += B * M * 32;
         CK(cudaMemcpy2DAsync(tl.data(), M * 32, sc.p + 1 + N, P0 * 32, M * 32, B, cudaMemcpyDeviceToHost, ctx->st));
     }
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     std::vector<u256> s0(B);
     host_parallel_for(B, [&](size_t b) {
         Fr acc = scn[b];
@@ -2038,7 +2051,7 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     if ((rc = to_affine(ctx, NX ? res2.p : res.p, 1, aff.p, 1, 0, 1, B))) return rc;
     std::vector<Affine> out(B);
     CK(D2H(out.data(), aff.p, B * 64));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     for (size_t b = 0; b < B; b++) ok[b] = aff_is_inf(out[b]) ? 1 : 0;
     return BPPP_OK;
 }
@@ -2086,7 +2099,7 @@ extern "C" int bppp_dbg_field(bppp_ctx* ctx, int op, size_t n, const uint8_t* a,
     }
     CK(cudaGetLastError());
     CK(D2H(out, dc.p, n * 32));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 extern "C" int bppp_dbg_ec(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
@@ -2104,6 +2117,6 @@ extern "C" int bppp_dbg_ec(bppp_ctx* ctx, int op, size_t n, const uint8_t* a, co
     int rc = to_affine(ctx, dc.p, n, dd.p, n, 0, (int)n, n);
     if (rc) return rc;
     CK(D2H(out, dd.p, n * 64));
-    CK(cudaStreamSynchronize(ctx->st));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }

@@ -1871,7 +1871,9 @@ int run_lanes(bppp_rp* s, size_t batch, F fn) {
             t_lane_threads = L[i].threads;
             t_lane_id = (int)i;
             t_is_lane0 = (i == 0);
-            bppp_set_thread_host_threads(L[i].threads);
+            // the short per-proof loops inside the device calls (round constants, rationalReduceScalar):
+            // the lanes already run side by side, so each gets its share of the cores, not all of them
+            bppp_set_thread_host_threads(std::max(1, L[i].threads / (int)L.size()));
             rcs[i] = fn(L[i], b0, nb);
         });
     }
@@ -2043,6 +2045,41 @@ int bppp_host_oracle(const uint8_t* pts, size_t npts, int count, int show_format
     zk.oracle(pts, npts, o.data(), count);
     for (int i = 0; i < count; i++) h64::to_bytes(out + 32 * i, o[i]);
     return 0;
+}
+// A prover-style transcript run through the batched paths the range-proof layer uses: `n_random`
+// values of `random` (two-stream one-block hashing; canonical form), then the commitments `pts`,
+// then `rounds` (X, R) pairs whose challenges come from oracle_rounds (verifier style) and, on a
+// second transcript, from oracle_pair (prover style, two transcripts at a time).
+// out: [n_random] randoms | [rounds] challenges (oracle_rounds) | [rounds] challenges (oracle_pair); 32 B each
+int bppp_host_transcript(const char* seed, int show_format, size_t n_random, const uint8_t* pts, size_t npts,
+                         const uint8_t* round_pts, size_t rounds, uint8_t* out) {
+    if (!h64::host_cpu_ok()) return BPPP_ERR_STATE;
+    if (!seed || !out || (npts && !pts) || (rounds && !round_pts)) return BPPP_ERR_ARG;
+    tr::Zkpt a, b, c;
+    a.fmt = b.fmt = c.fmt = show_format;
+    a.seed = b.seed = c.seed = seed;
+    std::vector<Fr> rnd(n_random);
+    a.random_fill(rnd.data(), n_random);
+    std::vector<uint8_t> canon(32 * n_random);
+    b.random_fill_canonical(canon.data(), n_random);
+    for (size_t i = 0; i < n_random; i++) {
+        h64::to_bytes(out + 32 * i, rnd[i]);
+        if (memcmp(out + 32 * i, &canon[32 * i], 32)) return BPPP_ERR_STATE;
+    }
+    Fr ch;
+    if (npts) { a.oracle(pts, npts, &ch, 1); b.oracle(pts, npts, &ch, 1); c.oracle(pts, npts, &ch, 1); }
+    std::vector<const uint8_t*> rp(rounds);
+    for (size_t r = 0; r < rounds; r++) rp[r] = round_pts + 128 * r;
+    std::vector<Fr> es(rounds);
+    a.oracle_rounds(rp.data(), rounds, es.data());
+    for (size_t r = 0; r < rounds; r++) h64::to_bytes(out + 32 * (n_random + r), es[r]);
+    for (size_t r = 0; r < rounds; r++) {
+        Fr eb, ec;
+        tr::Zkpt::oracle_pair(b, rp[r], c, rp[r], 2, &eb, &ec);
+        if (!(eb == ec)) return BPPP_ERR_STATE;
+        h64::to_bytes(out + 32 * (n_random + rounds + r), eb);
+    }
+    return BPPP_OK;
 }
 int bppp_host_fr(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     if (!h64::host_cpu_ok()) return BPPP_ERR_STATE;

@@ -161,3 +161,29 @@ def test_pair_fold_chain_incl_degenerate_pairs(ht):
         o = C.create_string_buffer(64)
         ht.ht_pair_fold(le(kb), int(bn), le(ka), int(an), pb(pl), pb(pr), o)
         assert unpt(o.raw) == G.msm([(-kb if bn else kb, pl), (-ka if an else ka, pr)])
+
+
+def test_batched_transcript_paths_match_oracle(lib):
+    """Round challenges via oracle_rounds (all rounds at once, suffix hashing) and oracle_pair (two
+    transcripts per task), and the bulk RNG (two one-block hashes at a time) against the oracle's
+    plain ZKPT, for both `show` policies and odd / even counts."""
+    from bulletproofspp_b200 import lib as L
+    pts = get_points(G, "test points", 40)
+    lib.bppp_host_transcript.argtypes = [C.c_char_p, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_char_p]
+    for fmt, name in [(0, "PrefixedP"), (1, "BareDecimal")]:
+        for seed, n_random, npts, rounds in [("default random seed", 7, 5, 4), ("s", 1, 0, 1), ("seed#12", 10, 3, 9),
+                                             ("a much longer random seed string than one SHA block can take with a counter", 3, 2, 3)]:
+            z = ZKPT(G, seed, name)
+            exp = [z.random() for _ in range(n_random)]
+            if npts:
+                z.oracle(pts[:npts], 1)
+            rp = [(pts[10 + 2 * r], pts[11 + 2 * r]) for r in range(rounds)]
+            es = [z.oracle([x, y], 1)[0] for x, y in rp]
+            out = C.create_string_buffer(32 * (n_random + 2 * rounds))
+            rc = lib.bppp_host_transcript(seed.encode(), fmt, n_random, L.points_to_bytes(pts[:npts]), npts,
+                                          L.points_to_bytes([p for xy in rp for p in xy]), rounds, out)
+            assert rc == 0
+            got = L.bytes_to_ints(out.raw)
+            assert got[:n_random] == exp
+            assert got[n_random:n_random + rounds] == es
+            assert got[n_random + rounds:] == es
