@@ -252,11 +252,14 @@ def main():
     barrier()
     ctx.timer_start()
     t0 = time.time()
+    cpu0 = os.times()
     n_ok = run_steps(lambda k: inputs, args.steps)
     for c in lanes:
         c.sync()
     ms = ctx.timer_stop()
     wall = time.time() - t0
+    cpu1 = os.times()
+    host_cpu_s = (cpu1.user - cpu0.user) + (cpu1.system - cpu0.system)
     barrier()
     clocks = sampler.stop()
     assert n_ok == B * args.steps
@@ -353,7 +356,11 @@ def main():
             "profile_pass": {"proofs": Bp, "kernel_ms": tot_ms, "wall_s": prof_wall,
                              "note": "one lane's share of a step (prove then verify) on a single stream with a CUDA-event pair "
                                      "around every launch, run after the timed regions; gpu_busy_estimate = kernel_ms x lanes / ms_per_step"},
-            "imad_peak": {"wide_per_s": imad_wide, "lo32_per_s": imad_lo}, "wall_s_value_leg": wall}
+            "imad_peak": {"wide_per_s": imad_wide, "lo32_per_s": imad_lo}, "wall_s_value_leg": wall,
+            "host": {"cpu_ms_per_proof": 1e3 * host_cpu_s / (B * args.steps), "cores_busy": host_cpu_s / wall,
+                     "cores_available": (os.cpu_count() or 1) / world,
+                     "note": "rank 0's process CPU time over the value leg (transcript hashing, blinders, linear slots, "
+                             "round sequencing); the Fiat-Shamir transcript stays on the host by design"}}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()
     print(json.dumps(line), flush=True)

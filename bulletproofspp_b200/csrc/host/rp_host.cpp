@@ -110,8 +110,8 @@ void dump_sections(const char* what, size_t proofs) {
         if (v) fprintf(stderr, " %s=%.0f", kSectNames[i], v / 1e3 / (double)proofs);
     }
     fprintf(stderr, "\n");
-    fprintf(stderr, "[bppp turns] %s: calls=%llu hold=%.1fms wait(sum over lanes)=%.1fms\n", what,
-            (unsigned long long)g_turn_calls.exchange(0), g_turn_hold_us.exchange(0) / 1e3, g_turn_wait_us.exchange(0) / 1e3);
+    fprintf(stderr, "[bppp jobs] %s: host jobs=%llu, lane-time inside them (sum over lanes)=%.1fms\n", what,
+            (unsigned long long)g_turn_calls.exchange(0), g_turn_hold_us.exchange(0) / 1e3);
 }
 extern thread_local bool t_is_lane0;
 static bool t_lane_threads_is_main() { return t_is_lane0; }
@@ -123,153 +123,95 @@ int n_threads() {
     unsigned h = std::thread::hardware_concurrency();
     return h ? (int)h : 4;
 }
-// Host phases of concurrent lanes take turns on the cores (each with every core) so that one
-// lane's host phase overlaps the other lanes' device work instead of all lanes moving in lock-step.
-// The workers are persistent (a phase is only a few milliseconds long).
-// The turn goes to the waiting lane that is FURTHEST along (ties: lowest lane): lanes that start
-// together then leave their host phases one after the other instead of all at once, so the first
-// lane's device rounds overlap the later lanes' host phases, and a lane in its argument rounds
-// (short transcript hashes that gate device work) never queues behind a long host phase.
-class TurnLock {
-  public:
-    void lock(int64_t prio) {
-        std::unique_lock<std::mutex> lk(mu_);
-        const std::pair<int64_t, uint64_t> key(-prio, seq_++);
-        waiters_.insert(key);
-        cv_.wait(lk, [&] { return !busy_ && *waiters_.begin() == key; });
-        waiters_.erase(waiters_.begin());
-        busy_ = true;
-    }
-    void unlock() {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            busy_ = false;
-        }
-        cv_.notify_all();
-    }
-
-  private:
-    std::mutex mu_;
-    std::condition_variable cv_;
-    std::set<std::pair<int64_t, uint64_t>> waiters_;
-    uint64_t seq_ = 0;
-    bool busy_ = false;
-};
-TurnLock g_cpu_turn;
+// Host phases of the concurrent lanes run on ONE pool of worker threads (as many as the host threads
+// this process may use).  A phase is a job of per-proof items; workers always take the next items
+// of the pending job whose lane is FURTHEST along (ties: lowest lane, then first come).  So
+//  * lanes that start together leave their host phases one after the other instead of all at
+//    once, and the first lane's device rounds overlap the later lanes' host phases;
+//  * a lane in its argument rounds -- a few hundred microseconds of transcript hashing that gate
+//    its next device launch -- is served at the next item boundary, never behind a long phase;
+//  * the pool is work-conserving: when the preferred job has no items left to hand out, idle
+//    workers start on the next one (no gap while a phase drains).
+// The lanes' own threads only sequence device calls and sleep while their job runs.
 std::atomic<uint64_t> g_turn_wait_us{0}, g_turn_hold_us{0}, g_turn_calls{0};   // BPPP_TIMING=1
-class WorkerPool {
+class Scheduler {
   public:
-    explicit WorkerPool(int n) {
-        for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
+    explicit Scheduler(int workers) {
+        for (int i = 0; i < workers; i++) th_.emplace_back([this] { loop(); });
     }
-    ~WorkerPool() {
+    ~Scheduler() {
         {
             std::lock_guard<std::mutex> lk(mu_);
             stop_ = true;
         }
-        cv_.notify_all();
+        work_.notify_all();
         for (auto& t : th_) t.join();
     }
-    int size() const { return (int)th_.size(); }
-    // runs fn(i) for i in [0, n) on up to `workers` pool threads plus the caller
-    void run(size_t n, int workers, const std::function<void(size_t)>& fn) {
-        {
-            std::lock_guard<std::mutex> lk(mu_);
-            fn_ = &fn; n_ = n; next_.store(0); pending_ = std::min(workers, (int)th_.size()); wanted_ = pending_;
-            gen_++;
-        }
-        cv_.notify_all();
-        work();
+    int workers() const { return (int)th_.size(); }
+    // fn(i) for i in [0, n); returns when all are done
+    void run(size_t n, int64_t prio, const std::function<void(size_t)>& fn) {
+        if (n == 0) return;
+        Job j;
+        j.prio = prio; j.n = n; j.fn = &fn;
+        j.grain = std::max<size_t>(1, std::min<size_t>(4, n / ((size_t)th_.size() * 16 + 1)));
         std::unique_lock<std::mutex> lk(mu_);
-        done_.wait(lk, [this] { return pending_ == 0; });
-        fn_ = nullptr;
+        j.seq = seq_++;
+        auto pos = jobs_.begin();
+        while (pos != jobs_.end() && ((*pos)->prio > j.prio || ((*pos)->prio == j.prio && (*pos)->seq < j.seq))) ++pos;
+        jobs_.insert(pos, &j);
+        work_.notify_all();
+        j.cv.wait(lk, [&] { return j.done == j.n; });
     }
 
   private:
-    void work() {
-        for (;;) {
-            size_t i = next_.fetch_add(1);
-            if (i >= n_) break;
-            (*fn_)(i);
-        }
-    }
+    struct Job {
+        int64_t prio = 0;
+        uint64_t seq = 0;
+        size_t n = 0, next = 0, done = 0, grain = 1;
+        const std::function<void(size_t)>* fn = nullptr;
+        std::condition_variable cv;
+    };
     void loop() {
-        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(mu_);
         for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || (gen_ != seen && wanted_ > 0); });
-                if (stop_) return;
-                seen = gen_;
-                wanted_--;
-            }
-            work();
-            {
-                std::lock_guard<std::mutex> lk(mu_);
-                if (--pending_ == 0) done_.notify_all();
-            }
+            work_.wait(lk, [&] { return stop_ || !jobs_.empty(); });
+            if (stop_) return;
+            Job* j = jobs_.front();                         // highest priority job that still has items to hand out
+            const size_t i0 = j->next, i1 = std::min(j->n, i0 + j->grain);
+            j->next = i1;
+            if (i1 == j->n) jobs_.erase(jobs_.begin());
+            lk.unlock();
+            for (size_t i = i0; i < i1; i++) (*j->fn)(i);
+            lk.lock();
+            j->done += i1 - i0;
+            if (j->done == j->n) j->cv.notify_one();        // the job object lives until its owner wakes up
         }
     }
     std::vector<std::thread> th_;
     std::mutex mu_;
-    std::condition_variable cv_, done_;
-    const std::function<void(size_t)>* fn_ = nullptr;
-    size_t n_ = 0;
-    std::atomic<size_t> next_{0};
-    int pending_ = 0, wanted_ = 0;
-    uint64_t gen_ = 0;
+    std::condition_variable work_;
+    std::vector<Job*> jobs_;                                // sorted: priority descending, then submission order
+    uint64_t seq_ = 0;
     bool stop_ = false;
 };
-WorkerPool& pool() {
-    static WorkerPool p(std::max(1, (int)std::thread::hardware_concurrency() - 1));
+Scheduler& pool() {
+    static Scheduler p(std::max(1, g_threads > 0 ? g_threads : (int)std::thread::hardware_concurrency()));
     return p;
 }
 template <class F>
 void parallel_for(size_t n, F fn) {
-    static const bool turns = !(getenv("BPPP_CPU_TURNS") && atoi(getenv("BPPP_CPU_TURNS")) == 0);
     int nt = (int)std::min<size_t>(n, (size_t)n_threads());
     if (nt <= 1) {
         for (size_t i = 0; i < n; i++) fn(i);
         return;
     }
-    if (turns) {
-        // A turn is not preemptible, so a long phase is cut into slices of about 1.5 ms: a lane whose
-        // device rounds wait for a few hundred microseconds of transcript hashing gets the cores at
-        // the next slice boundary instead of after a 20 ms host phase of another lane.
-        std::function<void(size_t)> whole = fn;
-        const int64_t prio = (int64_t)Timing::t_progress() * 1024 - t_lane_id;
-        size_t i0 = 0, slice = std::min<size_t>(n, (size_t)4 * nt);
-        while (i0 < n) {
-            const size_t cnt = std::min(slice, n - i0);
-            std::function<void(size_t)> f = [&whole, i0](size_t i) { whole(i0 + i); };
-            double t0 = Timing::now();
-            g_cpu_turn.lock(prio);
-            double t1 = Timing::now();
-            pool().run(cnt, nt - 1, f);
-            g_cpu_turn.unlock();
-            double t2 = Timing::now();
-            if (g_tm.on) {
-                g_turn_wait_us += (uint64_t)((t1 - t0) * 1e3);
-                g_turn_hold_us += (uint64_t)((t2 - t1) * 1e3);
-                g_turn_calls++;
-            }
-            i0 += cnt;
-            const double ms = std::max(t2 - t1, 0.02);
-            slice = (size_t)std::max<double>((double)nt, std::min<double>((double)n, (double)cnt * 1.5 / ms));
-        }
-        return;
+    std::function<void(size_t)> f = fn;
+    const double t0 = g_tm.on ? Timing::now() : 0;
+    pool().run(n, (int64_t)Timing::t_progress() * 1024 - t_lane_id, f);
+    if (g_tm.on) {
+        g_turn_hold_us += (uint64_t)((Timing::now() - t0) * 1e3);
+        g_turn_calls++;
     }
-    std::atomic<size_t> next(0);
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++)
-        th.emplace_back([&]() {
-            for (;;) {
-                size_t i = next.fetch_add(1);
-                if (i >= n) break;
-                fn(i);
-            }
-        });
-    for (auto& t : th) t.join();
 }
 
 I128 load_i128(const uint8_t b[16]) {
@@ -1851,7 +1793,7 @@ std::vector<Lane> make_lanes(bppp_rp* s, size_t batch) {
     L.resize(want);
     int total = g_threads > 0 ? g_threads : (int)std::thread::hardware_concurrency();
     if (total < 1) total = 4;
-    // host phases take turns (g_cpu_turn), each using every core
+    // every lane may use all host threads: its phases are jobs on the shared worker pool
     const char* ev = getenv("BPPP_LANE_THREADS");
     int per = ev ? atoi(ev) : total;
     for (auto& l : L) l.threads = std::max(1, per);
