@@ -1314,7 +1314,7 @@ struct bppp_trrp {
     DBuf<TrrpEnt> ent;
     DBuf<u256> eb, es;                 // static per-entry b, s (Montgomery)
     size_t B = 0;
-    DBuf<u256> scA, scR, scBL, amounts, chal2, chal3, chal4, xp, vt, r, c, bl, w, small;
+    DBuf<u256> scA, scR, scBL, amounts, chal2, chal3, chal4, chalv, xp, vt, r, c, bl, w, small;
     DBuf<Jac> res;
     DBuf<Affine> aff;
     int phase = 0;
@@ -1887,12 +1887,12 @@ namespace {
 int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
                    const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR, size_t n_norm,
                    size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s,
-                   const uint8_t* init_p, int* ok) {
+                   const uint8_t* init_p, int* ok, const u256* pub_dev = nullptr) {
     bppp_ctx* ctx = gens->ctx;
     const size_t N = gens->N, M = gens->M;
     const size_t B = batch, P0 = 1 + N + M, NX = n_init + 2 * k;
     if (!check_fq(XR, 4 * k * B) || !check_fq(init_p, 2 * n_init * B)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
-    if (!check_fr(q, B) || !check_fr(s_pub, B) || !check_fr(pub_w, B * N) || !check_fr(c, B * M) || !check_fr(es, B * k) ||
+    if (!check_fr(q, B) || !check_fr(s_pub, B) || (!pub_dev && !check_fr(pub_w, B * N)) || !check_fr(c, B * M) || !check_fr(es, B * k) ||
         !check_fr(fw, B * n_norm) || !check_fr(fl, B * n_lin) || !check_fr(init_s, B * n_init))
         FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     DBuf<Affine> extra, aff;
@@ -1900,16 +1900,18 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     DBuf<Jac> res, res2, resx;
     CK(extra.alloc(B * std::max<size_t>(NX, 1))); CK(aff.alloc(B));
     CK(sc.alloc(B * P0)); CK(xsc.alloc(B * std::max<size_t>(NX, 1)));
-    CK(pub.alloc(B * N)); CK(vs_n.alloc(B * n_norm)); CK(vs_l.alloc(B * n_lin));
+    if (!pub_dev) CK(pub.alloc(B * N));
+    CK(vs_n.alloc(B * n_norm)); CK(vs_l.alloc(B * n_lin));
     CK(f0n.alloc(B * k)); CK(f1.alloc(B * k)); CK(f0l.alloc(B * k)); CK(res.alloc(B)); CK(res2.alloc(B)); CK(resx.alloc(B));
     CK(tmp.alloc(std::max(B * N, B * M)));
-    if (N) {
+    if (N && !pub_dev) {
         CK(H2D(tmp.p, pub_w, B * N * 32));
         { ProfScope ps_(ctx, K_FR_CONVERT, 0);
         k_fr_convert<<<(unsigned)((B * N + 255) / 256), 256, 0, ctx->st>>>(tmp.p, pub.p, B * N, 1);
         }
         CK(cudaGetLastError());
     }
+    const u256* pubp = pub_dev ? pub_dev : pub.p;            // Montgomery, [B][N]
     // host: challenges, tensor factors, final-witness scalar sc
     //   NL: NormArgument.hs:131-145, 73-81        IP: InnerProductArgument.hs:103-124, 172-181
     const bool ip = kind == BPPP_ARG_IP;
@@ -1995,7 +1997,7 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     }
     if (N && ip) {
         IpVerifyArgs A;
-        A.pub = pub.p; A.pub_stride = N; A.vx = vs_n.p; A.vy = vs_y.p; A.n_vs = (int)nvs;
+        A.pub = pubp; A.pub_stride = N; A.vx = vs_n.p; A.vy = vs_y.p; A.n_vs = (int)nvs;
         A.f0x = f0n.p; A.f1x = f1.p; A.f1y = f1y.p; A.k = (int)k; A.r = rdev.p;
         A.out = sc.p; A.out_stride = P0; A.off = 1; A.n = (int)N;
         { ProfScope ps_(ctx, K_TENSOR, 0);
@@ -2004,7 +2006,7 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
         CK(cudaGetLastError());
     } else if (N) {
         TensorArgs A;
-        A.pub = pub.p; A.pub_stride = N; A.vs = vs_n.p; A.n_vs = (int)n_norm; A.f0 = f0n.p; A.f1 = f1.p; A.k = (int)k;
+        A.pub = pubp; A.pub_stride = N; A.vs = vs_n.p; A.n_vs = (int)n_norm; A.f0 = f0n.p; A.f1 = f1.p; A.k = (int)k;
         A.out = sc.p; A.out_stride = P0; A.off = 1; A.n = (int)N;
         { ProfScope ps_(ctx, K_TENSOR, 0);
         k_tensor_expand<<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
@@ -2056,6 +2058,48 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     return BPPP_OK;
 }
 }  // namespace
+
+// verifier: chal = [batch][8] = (e, 1/e, x, x', q0, 1/q0, t, 0).  The norm part of the public constants
+// (makePublicConsts, TypedReciprocal.hs:236-263) stays on the device for bppp_nl_verify_trrp;
+// sums = [batch][3] as in bppp_trrp_phase4.
+extern "C" int bppp_trrp_verify_pub(bppp_trrp* h, size_t batch, const uint8_t* chal, uint8_t* sums) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!chal || !sums || batch == 0) FAIL(BPPP_ERR_ARG, "bppp_trrp_verify_pub: null/empty argument");
+    ENTER(ctx);
+    if (!check_fr(chal, batch * 8)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    h->B = batch;
+    CK(h->chalv.ensure(batch * 8)); CK(h->xp.ensure(batch * h->n_ranges)); CK(h->vt.ensure(batch * h->n_bases));
+    CK(h->w.ensure(batch * h->n_ent)); CK(h->small.ensure(batch * 8));
+    CK(H2D(h->chalv.p, chal, batch * 8 * 32));
+    { ProfScope ps_(ctx, K_TRRP, 0);
+    k_trrp_tables<<<(unsigned)((batch + 63) / 64), 64, 0, ctx->st>>>(h->chalv.p, 8, 2, (int)h->n_ranges, (int)h->n_bases, h->xp.p, h->vt.p, (int)batch);
+    }
+    CK(cudaGetLastError());
+    TrrpVArgs A;
+    A.st = trrp_static(h); A.chal = h->chalv.p; A.xp = h->xp.p; A.vt = h->vt.p; A.pub = h->w.p; A.sums = h->small.p;
+    { ProfScope ps_(ctx, K_TRRP, 0);
+    k_trrp_verify_pub<<<(unsigned)batch, TRRP_THREADS, 0, ctx->st>>>(A);
+    }
+    CK(cudaGetLastError());
+    CK(D2H(sums, h->small.p, batch * 3 * 32));
+    CK(ctx_sync(ctx));
+    h->phase = 10;
+    return BPPP_OK;
+}
+// bppp_nl_verify_gens with the public vector of bppp_trrp_verify_pub (norm-linear argument)
+extern "C" int bppp_nl_verify_trrp(bppp_trrp* h, size_t k, const uint8_t* q, const uint8_t* s_pub, const uint8_t* c,
+                                   const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin, const uint8_t* fw,
+                                   const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p, int* ok) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (h->phase != 10) FAIL(BPPP_ERR_STATE, "bppp_nl_verify_trrp: call bppp_trrp_verify_pub first");
+    if (!q || !s_pub || !ok || (h->gens->M && !c) || (k && (!es || !XR)) || (n_norm && !fw) || (n_lin && !fl) || (n_init && (!init_s || !init_p)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_verify_trrp: null argument");
+    ENTER(ctx);
+    h->phase = 0;
+    return nl_verify_impl(h->gens, BPPP_ARG_NL, h->B, k, q, s_pub, nullptr, c, es, XR, n_norm, n_lin, fw, fl, n_init, init_s, init_p, ok, h->w.p);
+}
 
 extern "C" int bppp_nl_verify_gens(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
                                    const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR,

@@ -21,6 +21,10 @@
 #include <time.h>
 #include <algorithm>
 #include <atomic>
+#include <dlfcn.h>
+#include <signal.h>
+#include <sys/time.h>
+#include <ucontext.h>
 #include <map>
 #include <condition_variable>
 #include <functional>
@@ -982,6 +986,48 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
 
 }  // namespace
 
+// BPPP_SAMPLE=file: a SIGPROF sampling profiler of the whole process (1 kHz of CPU time, program
+// counters only) for finding where the host cores go on a box without perf; tools/sample_report.py
+// resolves the counts against the library's symbol table.
+namespace {
+std::atomic<size_t> g_ns{0};
+void** g_samples = nullptr;
+const size_t kMaxSamples = 1 << 20;
+void sample_handler(int, siginfo_t*, void* uc) {
+    size_t i = g_ns.fetch_add(1, std::memory_order_relaxed);
+    if (i < kMaxSamples) g_samples[i] = (void*)((ucontext_t*)uc)->uc_mcontext.gregs[REG_RIP];
+}
+void sample_dump() {
+    const char* path = getenv("BPPP_SAMPLE");
+    FILE* f = path ? fopen(path, "w") : nullptr;
+    if (!f) return;
+    struct itimerval off = {};
+    setitimer(ITIMER_PROF, &off, nullptr);
+    size_t n = std::min(g_ns.load(), kMaxSamples);
+    for (size_t i = 0; i < n; i++) {
+        Dl_info di;
+        if (dladdr(g_samples[i], &di) && di.dli_fname)
+            fprintf(f, "%s %lx %s\n", di.dli_fname, (unsigned long)((char*)g_samples[i] - (char*)di.dli_fbase), di.dli_sname ? di.dli_sname : "?");
+        else fprintf(f, "? %lx ?\n", (unsigned long)g_samples[i]);
+    }
+    fclose(f);
+}
+void sample_start() {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        if (!getenv("BPPP_SAMPLE")) return;
+        g_samples = (void**)calloc(kMaxSamples, sizeof(void*));
+        struct sigaction sa = {};
+        sa.sa_sigaction = sample_handler;
+        sa.sa_flags = SA_SIGINFO | SA_RESTART;
+        sigaction(SIGPROF, &sa, nullptr);
+        struct itimerval it = {{0, 1000}, {0, 1000}};
+        setitimer(ITIMER_PROF, &it, nullptr);
+        atexit(sample_dump);
+    });
+}
+}  // namespace
+
 // =================================================================================== C ABI
 extern "C" {
 
@@ -995,6 +1041,7 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
                   bppp_rp** out) {
     if (!ctx || !out || !basis_seed || (n_ranges && !ranges) || (n_pub && !pubs)) return BPPP_ERR_ARG;
     *out = nullptr;
+    sample_start();
     if (!h64::host_cpu_ok()) {
         fprintf(stderr, "bppp_rp_setup: this build's host field arithmetic needs BMI2 + ADX (rebuild with -DBPPP_HOST_PORTABLE_FR)\n");
         return BPPP_ERR_STATE;
@@ -1695,9 +1742,82 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
     uint8_t* fl_b = lane_buf(s, ln, PB_V6, B * n_lin * 32);
     uint8_t* is_b = lane_buf(s, ln, PB_V7, B * NC * 32);
     uint8_t* ip_b = lane_buf(s, ln, PB_V8, B * NC * 64);
+    g_tm.start();
+    if (s->dev_phases && ln.trrp) {
+        // verifyTRRPM (TypedReciprocal.hs:447-467) with the norm part of the public constants on the device
+        struct VP { Fr q, e, e_inv, x, xq, r0, r1, q0, q0_inv, t; };
+        std::vector<VP> V(B);
+        uint8_t* ch = lane_buf(s, ln, PB_CH, B * 8 * 32);
+        uint8_t* small = lane_buf(s, ln, PB_SMALL, B * 6 * 32);
+        parallel_for(B, [&](size_t b) {
+            tr::Zkpt zk;
+            Sect sect;
+            zk.fmt = s->fmt;
+            zk.no_random = true;
+            const uint8_t* cm = coms + 64 * b * NC;
+            VP& v = V[b];
+            Fr c1[3], c2[3];
+            zk.oracle(cm + 128, 2 + n, c1, 3);
+            v.e = c1[0]; v.x = c1[1]; v.r0 = c1[2];
+            zk.oracle(cm + 64, 1, c2, 3);
+            v.q = c2[0]; v.xq = c2[1]; v.r1 = c2[2];
+            v.q0 = q0_of(s->arg, v.q);
+            zk.oracle(cm, 1, &v.t, 1);
+            // challenges of the argument: oldest round hashed first, list newest first (Bulletproof.hs:374)
+            std::vector<const uint8_t*> rp(k);
+            std::vector<Fr> es(k);
+            for (size_t r = 0; r < k; r++) rp[r] = responses + 128 * (b * k + (k - 1 - r));
+            zk.oracle_rounds(rp.data(), k, es.data());
+            for (size_t r = 0; r < k; r++) h64::to_bytes(&es_b[32 * (b * k + (k - 1 - r))], es[r]);
+            sect.lap(S_V_ORACLE);
+            Fr iv[2] = {v.e, v.q0};
+            h64::batch_inv(iv, 2);
+            v.e_inv = iv[0]; v.q0_inv = iv[1];
+            uint8_t* o = ch + 32 * 8 * b;
+            h64::to_bytes(o, v.e); h64::to_bytes(o + 32, v.e_inv); h64::to_bytes(o + 64, v.x); h64::to_bytes(o + 96, v.xq);
+            h64::to_bytes(o + 128, v.q0); h64::to_bytes(o + 160, v.q0_inv); h64::to_bytes(o + 192, v.t);
+            memset(o + 224, 0, 32);
+            sect.lap(S_V_MISC);
+        });
+        g_tm.lap("verify_host");
+        int rc = bppp_trrp_verify_pub(ln.trrp, B, ch, small);
+        if (rc) return fail(s, rc, std::string("bppp_trrp_verify_pub: ") + ctx_err(ln));
+        g_tm.lap("verify_pub");
+        parallel_for(B, [&](size_t b) {
+            using namespace h64;
+            Sect sect;
+            const VP& v = V[b];
+            const uint8_t* cm = coms + 64 * b * NC;
+            const Fr ts0 = from_bytes(small + 32 * (3 * b)), sum_q2 = from_bytes(small + 32 * (3 * b + 1)), sum_v = from_bytes(small + 32 * (3 * b + 2));
+            const Fr t2 = sqr(v.t), t3 = mul(t2, v.t), t5 = mul(sqr(t2), v.t), two_t5 = dbl(t5);
+            const Fr sp = add(public_consts_z_trrp(s, v.e, v.x, two_t5), add(ts0, mul(two_t5, add(sum_q2, mul(v.e_inv, sum_v)))));
+            sect.lap(S_V_PUB);
+            std::map<U128, Fr> bm = make_base_map(s, v.x);
+            std::vector<Fr> cs = make_bp_coeffs(s->flag, v.xq, v.r0, v.r1, v.t, make_shared_coeffs(v.e, v.e_inv, s->m_bases, bm));
+            // TranscriptTRRP.openWith (TypedReciprocal.hs:279-282): [1,t,t^2,t^3] on [bl,m,dm,r]
+            std::vector<Fr> init_s = {one(), t3, t2, v.t};                  // coms order: bl, r, dm, m
+            for (auto& c : input_coeffs_trrp(s, v.x, v.q0)) init_s.push_back(mul(two_t5, c));
+            sect.lap(S_V_MISC);
+            memset(&c_b[32 * b * M], 0, 32 * M);
+            to_bytes(&q_b[32 * b], v.q);
+            to_bytes(&sp_b[32 * b], sp);
+            for (size_t i = 0; i < cs.size() && i < M; i++) to_bytes(&c_b[32 * (b * M + i)], cs[i]);
+            for (size_t i = 0; i < NC; i++) to_bytes(&is_b[32 * (b * NC + i)], init_s[i]);
+            memcpy(&ip_b[64 * b * NC], cm, 64 * NC);
+            memcpy(&fw_b[32 * b * n_norm], finals + 32 * b * (n_norm + n_lin), 32 * n_norm);
+            memcpy(&fl_b[32 * b * n_lin], finals + 32 * (b * (n_norm + n_lin) + n_norm), 32 * n_lin);
+            sect.lap(S_TOBYTES);
+        });
+        g_tm.lap("verify_host");
+        rc = bppp_nl_verify_trrp(ln.trrp, k, q_b, sp_b, c_b, es_b, responses, n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, ok);
+        g_tm.lap("nl_verify");
+        g_tm.dump("verify");
+        if (t_lane_threads_is_main()) dump_sections("verify, all lanes", B);
+        if (rc) return fail(s, rc, std::string("bppp_nl_verify: ") + ctx_err(ln));
+        return BPPP_OK;
+    }
     std::vector<Ph1> ph1v;
     if (!s->binary) ph1v = ph1s_verifier(s);
-    g_tm.start();
     parallel_for(B, [&](size_t b) {
         tr::Zkpt zk;
         Sect sect;

@@ -1327,6 +1327,67 @@ __global__ void __launch_bounds__(TRRP_THREADS) k_trrp_phase4(TrrpP4Args A) {
     }
 }
 
+struct TrrpVArgs {
+    TrrpStatic st;
+    const u256* chal;                  // [B][8] canonical: e, 1/e, x, x', q0, 1/q0, t, (unused)
+    const u256* xp; const u256* vt;
+    u256* pub;                         // [B][n_ent] Montgomery: norm part of the public constants
+    u256* sums;                        // [B][3] canonical: sum q2 p^2, sum q2 (digits), sum v (digits)
+};
+// The verifier's makePublicConsts (TypedReciprocal.hs:236-263, called from verifyTRRPM :447-467):
+// the same p_i as the prover's phase 4, from public data only (u_i, v_i and the symbol term c_i)
+__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_verify_pub(TrrpVArgs A) {
+    __shared__ u256 sm[TRRP_THREADS / 32];
+    const int p = blockIdx.x, tid = threadIdx.x;
+    const u256* ch = A.chal + (size_t)p * 8;
+    const u256 e = fr::to_mont(ld_u256(ch + 0)), e_inv = fr::to_mont(ld_u256(ch + 1)), x = fr::to_mont(ld_u256(ch + 2));
+    const u256 xq = fr::to_mont(ld_u256(ch + 3)), q0 = fr::to_mont(ld_u256(ch + 4)), q0_inv = fr::to_mont(ld_u256(ch + 5));
+    const u256 t = fr::to_mont(ld_u256(ch + 6));
+    const u256 t2 = fr::sqr(t), t3 = fr::mul(t2, t), t4 = fr::sqr(t2);
+    const u256 t2e = fr::mul(t2, e), t3xq = fr::mul(t3, xq), constT = fr::add(t2e, t3xq);
+    const u256* xp = A.xp + (size_t)p * A.st.n_ranges;
+    const u256* vt = A.vt + (size_t)p * A.st.n_bases;
+    u256 ts0 = u256_zero(), sq2 = ts0, sv = ts0;
+    for (int i0 = tid * TRRP_PER; i0 < A.st.n_ent; i0 += TRRP_THREADS * TRRP_PER) {
+        u256 q2 = trrp_pow(q0, (unsigned)i0 + 1), qi2 = trrp_pow(q0_inv, (unsigned)i0 + 1);
+#pragma unroll 1
+        for (int j = 0; j < TRRP_PER; j++) {
+            const int i = i0 + j;
+            if (i >= A.st.n_ent) break;
+            if (j) { q2 = fr::mul(q2, q0); qi2 = fr::mul(qi2, q0_inv); }
+            const TrrpEnt en = A.st.ent[i];
+            const bool isT = en.flags & TE_T;
+            const u256 xpi = ld_u256(xp + en.ind);
+            u256 u, v, c = u256_zero();
+            if (isT) {
+                u = (en.flags & TE_IA) ? u256_zero() : xpi;
+                v = (en.flags & TE_IO) ? fr::neg(x) : x;
+            } else {
+                u = fr::mul(xpi, ld_u256(A.st.b + i));
+                v = ld_u256(vt + en.base_idx);
+                if ((en.flags & TE_I) && (en.flags & TE_S)) {          // c = v (1/e - 1/(e + s)); 1/0 = 0 -> c = 0
+                    const u256 den = fr::add(e, ld_u256(A.st.s + i));
+                    if (!u256_is_zero(den)) c = fr::mul(v, fr::sub(e_inv, fr::inv(den)));
+                }
+            }
+            u256 inner = fr::mul(t2, v);
+            if (!u256_is_zero(u)) inner = fr::add(inner, fr::mul(isT ? t3xq : t3, u));
+            if (!u256_is_zero(c)) inner = fr::add(inner, fr::mul(t4, c));
+            const u256 pi = fr::add(isT ? constT : t2e, fr::mul(qi2, inner));
+            ts0 = fr::add(ts0, fr::mul(q2, fr::sqr(pi)));
+            if (!isT) { sq2 = fr::add(sq2, q2); sv = fr::add(sv, v); }
+            st_u256(A.pub + (size_t)p * A.st.n_ent + i, pi);
+        }
+    }
+    ts0 = trrp_block_sum(ts0, sm); sq2 = trrp_block_sum(sq2, sm); sv = trrp_block_sum(sv, sm);
+    if (tid == 0) {
+        u256* out = A.sums + (size_t)p * 3;
+        st_u256(out + 0, fr::from_mont(ts0));
+        st_u256(out + 1, fr::from_mont(sq2));
+        st_u256(out + 2, fr::from_mont(sv));
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // debug / self-test kernels (exercised by tests/ through bppp_dbg_*)
 // ------------------------------------------------------------------------------------------

@@ -22,7 +22,7 @@ EXPORTS = [
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
     "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free", "bppp_nl_set_shard", "bppp_nl_export", "bppp_rp_encoded_sizes", "bppp_rp_encode_batch", "bppp_rp_decode_batch",
     "bppp_trrp_create", "bppp_trrp_destroy", "bppp_trrp_phase1", "bppp_trrp_phase2", "bppp_trrp_phase3", "bppp_trrp_commit_bl",
-    "bppp_trrp_phase4", "bppp_nl_create_trrp",
+    "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
 ]
 
 

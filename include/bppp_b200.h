@@ -178,6 +178,13 @@ int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom);
 /* phase 4 (:435-444): chal = [batch][2] = (t, 1/q0).  sums = [batch][3] = (sum q2_i p_i^2 over all
  * entries, sum q2_i and sum v_i over the digit entries); the combined witness stays on the device. */
 int bppp_trrp_phase4(bppp_trrp* h, const uint8_t* chal, uint8_t* sums);
+/* verifier (verifyTRRPM, :447-467): chal = [batch][8] = (e, 1/e, x, x', q-power base q0, 1/q0, t, 0).
+ * sums as in phase 4; the norm part of makePublicConsts stays on the device for bppp_nl_verify_trrp,
+ * which is bppp_nl_verify_gens (norm-linear argument) without the pub_w argument. */
+int bppp_trrp_verify_pub(bppp_trrp* h, size_t batch, const uint8_t* chal, uint8_t* sums);
+int bppp_nl_verify_trrp(bppp_trrp* h, size_t k, const uint8_t* q, const uint8_t* s_pub, const uint8_t* c,
+                        const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin, const uint8_t* fw,
+                        const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p, int* ok);
 /* the norm-linear argument (bppp_nl_create_gens) over the device-resident witness of phase 4 */
 int bppp_nl_create_trrp(bppp_trrp* h, const uint8_t* q, const uint8_t* s, const uint8_t* l, const uint8_t* c,
                         bppp_nl** out);
