@@ -35,13 +35,21 @@ inline void append_decimal(std::string& out, const uint64_t v[4]) {
     int top = 3;
     while (top >= 0 && t[top] == 0) top--;
     while (top >= 0) {
-        u128 rem = 0;
+        uint64_t rem = 0;
         for (int i = top; i >= 0; i--) {
-            u128 cur = (rem << 64) | t[i];
+#if defined(__x86_64__)
+            // 128 / 64 -> 64 division in one instruction (rem < 10^19, so the quotient fits)
+            uint64_t qd, rd;
+            asm("divq %4" : "=a"(qd), "=d"(rd) : "0"(t[i]), "1"(rem), "r"(TEN19) : "cc");
+            t[i] = qd;
+            rem = rd;
+#else
+            u128 cur = ((u128)rem << 64) | t[i];
             t[i] = (uint64_t)(cur / TEN19);
-            rem = cur % TEN19;
+            rem = (uint64_t)(cur % TEN19);
+#endif
         }
-        chunks[nc++] = (uint64_t)rem;
+        chunks[nc++] = rem;
         while (top >= 0 && t[top] == 0) top--;
     }
     if (nc == 0) { out.push_back('0'); return; }
@@ -108,7 +116,23 @@ struct Zkpt {
     bool no_random = false;
     uint64_t n_random = 0;
     size_t n_coms = 0;
-    std::string body;                 // concat of coords, NEWEST FIRST (cs' = xs ++ cs)
+    // concat of coords, NEWEST FIRST (cs' = xs ++ cs): kept at the END of `store` so that new
+    // commitments are written in front of it without moving what is already there
+    std::string store;
+    size_t start = 0;
+    const uint8_t* bdata() const { return (const uint8_t*)store.data() + start; }
+    size_t bsize() const { return store.size() - start; }
+    void prepend(const char* p, size_t len) {
+        if (len > start) {                                        // grow at the front
+            const size_t used = bsize(), cap = 2 * (used + len) + 8192;
+            std::string bigger(cap, '\0');
+            memcpy(&bigger[cap - used], bdata(), used);
+            store.swap(bigger);
+            start = cap - used;
+        }
+        start -= len;
+        memcpy(&store[start], p, len);
+    }
     uint64_t hashed_bytes = 0;
 
     // `random` (ZKP.hs:90-93) with h = hashToScalar rn . show (app/Main.hs:177)
@@ -169,10 +193,9 @@ struct Zkpt {
     // `oracle xs` -> first `count` scalars of shaOracle cs' (ZKP.hs:96-101, app/Main.hs:75-80)
     void absorb(const uint8_t* pts, size_t npts) {
         std::string add;
-        add.reserve(npts * 170 + body.size());
+        add.reserve(npts * 170);
         for (size_t i = 0; i < npts; i++) add += show_point(pts + 64 * i, fmt);
-        add += body;
-        body.swap(add);
+        prepend(add.data(), add.size());
         n_coms += npts;
     }
     // scalar i (1-based) of the current transcript: hash(show i <> show (length cs) <> coords)
@@ -192,17 +215,17 @@ struct Zkpt {
         for (; i + 1 <= count; i += 2) {                  // two challenges at a time (two-stream SHA)
             std::string p0 = prefix_of(i, n_coms), p1 = prefix_of(i + 1, n_coms);
             uint8_t d0[32], d1[32];
-            sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), (const uint8_t*)body.data(), body.size(), d1,
-                           (const uint8_t*)p1.data(), p1.size(), (const uint8_t*)body.data(), body.size());
-            hashed_bytes += p0.size() + p1.size() + 2 * body.size();
+            sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), bdata(), bsize(), d1,
+                           (const uint8_t*)p1.data(), p1.size(), bdata(), bsize());
+            hashed_bytes += p0.size() + p1.size() + 2 * bsize();
             out[i - 1] = digest_to_fr(d0);
             out[i] = digest_to_fr(d1);
         }
         if (i <= count) {
             std::string pre = prefix_of(i, n_coms);
             uint8_t d[32];
-            sha::digest3(d, (const uint8_t*)pre.data(), pre.size(), (const uint8_t*)body.data(), body.size(), nullptr, 0);
-            hashed_bytes += pre.size() + body.size();
+            sha::digest3(d, (const uint8_t*)pre.data(), pre.size(), bdata(), bsize(), nullptr, 0);
+            hashed_bytes += pre.size() + bsize();
             out[i - 1] = digest_to_fr(d);
         }
     }
@@ -216,10 +239,10 @@ struct Zkpt {
         b.absorb(pb, npts);
         std::string p0 = prefix_of(1, a.n_coms), p1 = prefix_of(1, b.n_coms);
         uint8_t d0[32], d1[32];
-        sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), (const uint8_t*)a.body.data(), a.body.size(), d1,
-                       (const uint8_t*)p1.data(), p1.size(), (const uint8_t*)b.body.data(), b.body.size());
-        a.hashed_bytes += p0.size() + a.body.size();
-        b.hashed_bytes += p1.size() + b.body.size();
+        sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), a.bdata(), a.bsize(), d1,
+                       (const uint8_t*)p1.data(), p1.size(), b.bdata(), b.bsize());
+        a.hashed_bytes += p0.size() + a.bsize();
+        b.hashed_bytes += p1.size() + b.bsize();
         *ea = digest_to_fr(d0);
         *eb = digest_to_fr(d1);
     }
@@ -228,36 +251,32 @@ struct Zkpt {
     // in hashing order (oldest round first); out[r] = challenge of round r.
     void oracle_rounds(const uint8_t* const* round_pts, size_t k, Fr* out) {
         if (!k) return;
-        std::vector<std::string> shown(k);
-        size_t total = body.size();
-        for (size_t r = 0; r < k; r++) {
-            shown[r] = show_point(round_pts[r], fmt) + show_point(round_pts[r] + 64, fmt);
-            total += shown[r].size();
+        // prepend the rounds in hashing order (oldest first): round r's transcript is the last len[r]
+        // bytes of the store (lengths from the end stay valid when the store grows at the front)
+        std::vector<size_t> len(k);
+        {
+            std::vector<std::string> shown(k);
+            for (size_t r = 0; r < k; r++) shown[r] = show_point(round_pts[r], fmt) + show_point(round_pts[r] + 64, fmt);
+            for (size_t r = 0; r < k; r++) { prepend(shown[r].data(), shown[r].size()); len[r] = bsize(); }
         }
-        std::string fin;
-        fin.reserve(total);
-        std::vector<size_t> off(k);                        // offset of round r's transcript inside fin
-        for (size_t r = k; r-- > 0;) { off[r] = fin.size(); fin += shown[r]; }
-        fin += body;
-        const uint8_t* base = (const uint8_t*)fin.data();
+        const uint8_t* end = (const uint8_t*)store.data() + store.size();
         size_t r = 0;
         for (; r + 1 < k; r += 2) {
             std::string p0 = prefix_of(1, n_coms + 2 * (r + 1)), p1 = prefix_of(1, n_coms + 2 * (r + 2));
             uint8_t d0[32], d1[32];
-            sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), base + off[r], fin.size() - off[r], d1,
-                           (const uint8_t*)p1.data(), p1.size(), base + off[r + 1], fin.size() - off[r + 1]);
-            hashed_bytes += p0.size() + p1.size() + 2 * fin.size() - off[r] - off[r + 1];
+            sha::digest2x2(d0, (const uint8_t*)p0.data(), p0.size(), end - len[r], len[r], d1,
+                           (const uint8_t*)p1.data(), p1.size(), end - len[r + 1], len[r + 1]);
+            hashed_bytes += p0.size() + p1.size() + len[r] + len[r + 1];
             out[r] = digest_to_fr(d0);
             out[r + 1] = digest_to_fr(d1);
         }
         if (r < k) {
             std::string pre = prefix_of(1, n_coms + 2 * (r + 1));
             uint8_t d[32];
-            sha::digest3(d, (const uint8_t*)pre.data(), pre.size(), base + off[r], fin.size() - off[r], nullptr, 0);
-            hashed_bytes += pre.size() + fin.size() - off[r];
+            sha::digest3(d, (const uint8_t*)pre.data(), pre.size(), end - len[r], len[r], nullptr, 0);
+            hashed_bytes += pre.size() + len[r];
             out[r] = digest_to_fr(d);
         }
-        body.swap(fin);
         n_coms += 2 * k;
     }
 };
