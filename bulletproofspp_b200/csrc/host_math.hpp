@@ -152,6 +152,83 @@ inline void euclid_step(SBig& n, SBig& ns, const SBig& d, const SBig& ds) {
         }
     }
 }
+// The same step with the quotient taken in one go (Knuth D with a 64-bit divisor digit): the
+// estimate from the leading 64 bits of d is at most 2 too large.  Falls back to the bitwise step
+// when the quotient may not fit 63 bits (only for tiny inputs).
+inline bool sb_mulsub_small(SBig& n, const SBig& d, uint64_t q) {      // |n| -= q*|d|; true if it went negative
+    u128 carry = 0;
+    uint64_t borrow = 0;
+    for (int i = 0; i < 5; i++) {
+        carry += (u128)d.m[i] * q;
+        uint64_t sub = (uint64_t)carry;
+        carry >>= 64;
+        uint64_t t = n.m[i] - sub;
+        uint64_t b1 = n.m[i] < sub;
+        uint64_t t2 = t - borrow;
+        uint64_t b2 = t < borrow;
+        n.m[i] = t2;
+        borrow = b1 | b2;
+    }
+    return borrow || carry;
+}
+inline void sb_addmul_small(SBig& r, const SBig& a, uint64_t q) {      // |r| += q*|a|
+    u128 carry = 0;
+    for (int i = 0; i < 5; i++) {
+        carry += (u128)a.m[i] * q + r.m[i];
+        r.m[i] = (uint64_t)carry;
+        carry >>= 64;
+    }
+}
+inline void euclid_step_fast(SBig& n, SBig& ns, const SBig& d, const SBig& ds) {
+    const int bn = sb_bitlen(n), bd = sb_bitlen(d);
+    if (bn < bd) return;                                   // quotient 0
+    if (bn - bd > 61 || bd == 0) { euclid_step(n, ns, d, ds); return; }
+    // leading 64 bits of d (normalised) and the matching window of n (at most 64 + 62 bits)
+    const int sh = bd > 64 ? bd - 64 : 0;
+    auto window = [&](const SBig& v) -> u128 {
+        // (v >> sh) truncated to 128 bits
+        const int w = sh / 64, b = sh % 64;
+        uint64_t x0 = w < 5 ? v.m[w] : 0, x1 = w + 1 < 5 ? v.m[w + 1] : 0, x2 = w + 2 < 5 ? v.m[w + 2] : 0;
+        uint64_t lo = b ? (x0 >> b) | (x1 << (64 - b)) : x0;
+        uint64_t hi = b ? (x1 >> b) | (x2 << (64 - b)) : x1;
+        return ((u128)hi << 64) | lo;
+    };
+    const uint64_t dt = (uint64_t)window(d);
+    const u128 nt = window(n);
+    // >= the true quotient, by at most 2 when dt is normalised; exact for bd <= 64 (sh = 0).
+    // nt >> 64 < dt in both cases, so the 128/64 division cannot overflow.
+    uint64_t q;
+#if defined(__x86_64__) && !defined(__CUDACC__)
+    {
+        uint64_t rem_;
+        asm("divq %4" : "=a"(q), "=d"(rem_) : "0"((uint64_t)nt), "1"((uint64_t)(nt >> 64)), "r"(dt) : "cc");
+    }
+#else
+    q = (uint64_t)(nt / dt);
+#endif
+    if (q == 0) return;
+    const bool nneg = n.neg, qneg = (n.neg != d.neg);
+    SBig saved = n;
+    while (sb_mulsub_small(n, d, q)) {                     // over-estimate: retry with q - 1
+        n = saved;
+        q--;
+        if (q == 0) return;
+    }
+    n.neg = sb_is_zero(n) ? false : nneg;
+    // ns -= (+-q) * ds
+    const bool uneg = (ds.neg != qneg);                    // sign of the term u = +-q*ds that is subtracted
+    if (ns.neg != uneg || sb_is_zero(ns)) {                // ns - u: signs differ -> magnitudes add, sign of ns (or of -u)
+        const bool rneg = sb_is_zero(ns) ? !uneg : ns.neg;
+        sb_addmul_small(ns, ds, q);
+        ns.neg = sb_is_zero(ns) ? false : rneg;
+    } else {                                               // same sign: |ns| - q|ds| may change sign
+        SBig u;
+        for (int i = 0; i < 5; i++) u.m[i] = 0;
+        u.neg = uneg;
+        sb_addmul_small(u, ds, q);
+        ns = sb_sub(ns, u);
+    }
+}
 struct Ratio {              // a = b * x (mod r), |a|,|b| about sqrt(r)
     u256 a, b;              // magnitudes
     bool a_neg, b_neg;
@@ -195,7 +272,7 @@ inline Ratio rational_reduce(const u256& x) {
         return false;
     };
     while (too_big(a1)) {
-        euclid_step(a0, s0, a1, s1);
+        euclid_step_fast(a0, s0, a1, s1);
         SBig t = a0; a0 = a1; a1 = t;
         t = s0; s0 = s1; s1 = t;
     }
