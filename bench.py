@@ -214,6 +214,8 @@ def main():
         if world > 1:
             dist.barrier()
 
+    prove_wall = []                     # wall seconds of every bppp_rp_prove_batch call, all legs (diagnostic)
+
     def run_steps(input_fn, steps):
         """prove `steps` batches; a second host thread verifies each batch as soon as it is proved.
         Returns the number of proofs that verified."""
@@ -233,7 +235,9 @@ def main():
         th.start()
         for k in range(steps):
             vals, tys, seeds = input_fn(k)
+            tk = time.time()
             q.put(setup.prove_batch_raw(B, vals, tys, None, seeds))
+            prove_wall.append(round(time.time() - tk, 4))
         q.put(None)
         th.join()
         if errs:
@@ -243,6 +247,13 @@ def main():
     base = rank * B
     inputs = make_inputs(B, base, n)
     assert run_steps(lambda k: inputs, args.warmup) == B * args.warmup, "a warm-up proof failed to verify"
+    # pools, pinned staging buffers and worker threads are sized on demand during the first steps; on a
+    # box that just ran something else three steps are sometimes not enough.  Keep warming up (untimed,
+    # at most 4 more steps) until a step is within 10 % of the one before it.
+    extra_warmup = 0
+    while extra_warmup < 4 and len(prove_wall) >= 2 and prove_wall[-1] > 0 and abs(prove_wall[-1] - prove_wall[-2]) > 0.10 * prove_wall[-1]:
+        assert run_steps(lambda k: inputs, 1) == B
+        extra_warmup += 1
     # ---- timed region 1: `value` -- inputs staged before the clock starts, device-timed
     for c in lanes:
         c.profile_reset()               # zero the H2D / D2H byte counters
@@ -345,7 +356,8 @@ def main():
             "config": {"workload": "examples/128by64 prove+verify (N=1024, M=261, 9 rounds), %d proofs per GPU per step" % B,
                        "batch_per_gpu": B, "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "working set per step (%.0f MB of generators+witness vectors) exceeds the 126 MB L2" % (B * 0.33),
-                       "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world), "lanes": len(lanes)},
+                       "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world), "lanes": len(lanes),
+                       "extra_warmup_steps": extra_warmup},
             "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": rep["h2d_bytes"] // args.steps,
                     "d2h_bytes_per_step": rep["d2h_bytes"] // args.steps,
                     "note": "host buffers in, proofs + verdicts out through bppp_rp_prove_batch/bppp_rp_verify_batch; "
@@ -357,6 +369,7 @@ def main():
                              "note": "one lane's share of a step (prove then verify) on a single stream with a CUDA-event pair "
                                      "around every launch, run after the timed regions; gpu_busy_estimate = kernel_ms x lanes / ms_per_step"},
             "imad_peak": {"wide_per_s": imad_wide, "lo32_per_s": imad_lo}, "wall_s_value_leg": wall,
+            "prove_call_wall_s": prove_wall,
             "host": {"cpu_ms_per_proof": 1e3 * host_cpu_s / (B * args.steps), "cores_busy": host_cpu_s / wall,
                      "cores_available": (os.cpu_count() or 1) / world,
                      "note": "rank 0's process CPU time over the value leg (transcript hashing, blinders, linear slots, "
