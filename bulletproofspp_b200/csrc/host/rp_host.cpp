@@ -1394,6 +1394,7 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
     std::atomic<int> bad(0);
     g_tm.start();
     const size_t in_terms = s->binary ? 2 : 3;
+    const bool dev_mode = s->dev_phases && ln.trrp && !s->binary;
     uint8_t* in_sc = lane_buf(s, ln, PB_IN, B * n * in_terms * 32);
     // ---------------- phase 1 (host): witnesses, input openings, digit commitments
     uint8_t* sc1 = lane_buf(s, ln, PB_SC1, B * (s->binary ? 1 : 2) * P0 * 32);
@@ -1456,6 +1457,91 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
         }
         std::vector<Ph1> digits_ph1;
         std::map<U128, std::vector<U128>> bm;                              // multiplicities summed as integers
+        if (dev_mode) {
+            // The norm part of the witness goes to the device: digits (small integers), types and inline
+            // multiplicities are written straight into the commitment scalar rows [sc | nrm | lin] of the
+            // dm and m witnesses -- no Phase-1 records, no field conversions for the digits.
+            uint8_t* dm_row = &sc1[32 * (2 * b) * P0];
+            uint8_t* m_row = &sc1[32 * (2 * b + 1) * P0];
+            memset(dm_row, 0, 32 * P0);
+            memset(m_row, 0, 32 * P0);
+            size_t ent = 0;
+            auto put_int = [](uint8_t* dst, U128 v) { memcpy(dst, &v, 16); };
+            if (s->flag)
+                for (size_t i = 0; i < n; i++, ent++)
+                    if (types) memcpy(dm_row + 32 * (1 + ent), types + 32 * (b * n + i), 32);
+            for (size_t i = 0; i < n; i++) {
+                const Range& rdi = s->rds[i];
+                if (rdi.is_shared && !rdi.is_assumed) {
+                    U128 left;
+                    if (!adjust_value(rdi, values + 32 * (b * n + i), left)) { p.ok = false; bad++; return; }
+                    std::vector<U128>& arr = bm[rdi.base];
+                    if (arr.empty()) arr.assign((size_t)rdi.base - 1, 0);
+                    for (size_t k = 0; k < rdi.coeffs.size(); k++, ent++) {
+                        const bool bit = rdi.has_bit && k == 0;
+                        const U128 basek = bit ? (U128)2 : rdi.base, cf = rdi.coeffs[k];
+                        U128 d = cf ? std::min<U128>(basek - 1, left / cf) : (basek - 1);
+                        left -= d * cf;
+                        put_int(dm_row + 32 * (1 + ent), d);
+                        if (bit) {
+                            std::vector<U128>& a2 = bm[2];
+                            if (a2.empty()) a2.assign(1, 0);
+                            a2[0] += d;
+                        } else if (d >= 1 && d < rdi.base) arr[(size_t)d - 1] += 1;
+                    }
+                    continue;
+                }
+                bool has_ms;
+                std::vector<U128> ms;
+                std::vector<Ph1> tmp;
+                if (!make_phase1s((int)i, rdi, values + 32 * (b * n + i), true, tmp, has_ms, ms)) { p.ok = false; bad++; return; }
+                for (auto& q : tmp) {
+                    h64::to_bytes(dm_row + 32 * (1 + ent), q.d);
+                    if (q.kind == 'I') h64::to_bytes(m_row + 32 * (1 + ent), q.m);
+                    ent++;
+                }
+                if (has_ms) {                                               // baseMss (:363-367)
+                    auto merge = [&](U128 base, const U128* v, size_t cnt) {
+                        auto it = bm.find(base);
+                        if (it == bm.end()) bm[base] = std::vector<U128>(v, v + cnt);
+                        else for (size_t k = 0; k < cnt && k < it->second.size(); k++) it->second[k] += v[k];
+                    };
+                    if (rdi.has_bit) {
+                        merge(2, ms.data(), 1);
+                        merge(rdi.base, ms.data() + 1, ms.size() - 1);
+                    } else merge(rdi.base, ms.data(), ms.size());
+                }
+            }
+            if (ent != N) { p.ok = false; bad++; return; }
+            sect.lap(S_WITNESS);
+            std::vector<Fr> ms_shared;
+            for (auto& kv : bm) {
+                std::vector<Fr> v;
+                for (auto m : kv.second) v.push_back(fr_small(m));
+                ms_shared.insert(ms_shared.end(), v.begin(), v.end());
+                p.base_mss.push_back({kv.first, v});
+            }
+            for (size_t i = 0; i < n; i++) {
+                RPW w; w.sc = vals[i]; w.lin = {tys[i], bls[i]};
+                p.n_wits.push_back(w);
+                memcpy(&in_sc[32 * ((b * n + i) * 3)], values + 32 * (b * n + i), 32);       // already canonical
+                h64::to_bytes(&in_sc[32 * ((b * n + i) * 3 + 1)], tys[i]);
+                h64::to_bytes(&in_sc[32 * ((b * n + i) * 3 + 2)], bls[i]);
+            }
+            sect.lap(S_TOBYTES);
+            p.dm = blind_witness(p.zk, 3, 2, ms_shared, {});                // scalar + linear slots (same blinder draws)
+            p.m = blind_witness(p.zk, 3, 1, {}, {});
+            sect.lap(S_RANDOM);
+            auto put_sclin = [&](uint8_t* row, const RPW& w) {
+                h64::to_bytes(row, w.sc);
+                for (size_t j = 0; j < w.lin.size() && j < M; j++)
+                    if (!w.lin[j].is_zero()) h64::to_bytes(row + 32 * (1 + N + j), w.lin[j]);
+            };
+            put_sclin(dm_row, p.dm);
+            put_sclin(m_row, p.m);
+            sect.lap(S_SCALARS);
+            return;
+        }
         digits_ph1.reserve(s->nrm_len);
         for (size_t i = 0; i < n; i++) {
             const Range& rdi = s->rds[i];
