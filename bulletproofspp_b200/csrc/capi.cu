@@ -686,8 +686,9 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
     }
     int nch = (int)((n_terms + GT_MAX_CHUNK - 1) / GT_MAX_CHUNK);
     size_t ctas = batch * n_out * nch;
-    DBuf<Jac> scratch, partsbuf;     // stream-ordered pool allocations: cheap, and safe across lanes
-    CK(scratch.alloc(ctas * GT_SCRATCH(GT_THREADS)));
+    DBuf<unsigned char> scratch;     // stream-ordered pool allocations: cheap, and safe across lanes
+    DBuf<Jac> partsbuf;
+    CK(scratch.alloc(ctas * GT_SCRATCH_BYTES(GT_THREADS)));
     Jac* parts = d_out;
     if (nch > 1) { CK(partsbuf.alloc(ctas)); parts = partsbuf.p; }
     int max_n = (int)std::min<size_t>(GT_MAX_CHUNK, n_terms);
@@ -696,7 +697,7 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         GtArgs A;
         A.tbl = g->tbl.p; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
         A.n_total = (int)n_terms; A.term0 = 0; A.chunk_terms = GT_MAX_CHUNK;
-        A.scratch = scratch.p + b0 * n_out * nch * GT_SCRATCH(GT_THREADS);
+        A.scratch = scratch.p + b0 * n_out * nch * GT_SCRATCH_BYTES(GT_THREADS);
         A.out = parts + b0 * n_out * nch; A.out_pstride = (size_t)n_out * nch; A.n_out = n_out; A.n_chunks = nch;
         g_work = work_per_proof * (double)nb;
         { ProfScope ps_(ctx, K_MSM_GENS, g_work);
@@ -705,7 +706,7 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         CK(cudaGetLastError());
         const size_t n_cta = nb * n_out * nch;
         { ProfScope ps_(ctx, K_MSM_REDUCE, 0);
-        k_msm_gens_reduce<<<(unsigned)((n_cta + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH(GT_THREADS), A.out, A.out_pstride,
+        k_msm_gens_reduce<<<(unsigned)((n_cta + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH_BYTES(GT_THREADS), A.out, A.out_pstride,
                                                                            n_out, nch, n_cta);
         }
         CK(cudaGetLastError());
@@ -738,8 +739,8 @@ int run_msm_groups(bppp_gens* g, const u256* sc, size_t sc_stride, size_t batch,
     // the per-CTA scratch is large (61 KB): launch in slices of proofs
     size_t per = std::max<size_t>(1, std::min<size_t>(batch, 4096 / std::max<size_t>(1, ng)));
     per = std::min<size_t>(per, 32768);
-    DBuf<Jac> scratch;
-    CK(scratch.alloc(per * ng * GT_SCRATCH(GT_THREADS_SMALL)));
+    DBuf<unsigned char> scratch;
+    CK(scratch.alloc(per * ng * GT_SCRATCH_BYTES(GT_THREADS_SMALL)));
     for (size_t b0 = 0; b0 < batch; b0 += per) {
         const size_t nb = std::min(per, batch - b0);
         GtArgs A;
@@ -751,7 +752,7 @@ int run_msm_groups(bppp_gens* g, const u256* sc, size_t sc_stride, size_t batch,
         }
         CK(cudaGetLastError());
         { ProfScope ps_(ctx, K_MSM_REDUCE, 0);
-        k_msm_gens_reduce<<<(unsigned)((nb * ng + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH(GT_THREADS_SMALL), A.out, A.out_pstride,
+        k_msm_gens_reduce<<<(unsigned)((nb * ng + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH_BYTES(GT_THREADS_SMALL), A.out, A.out_pstride,
                                                                             1, (int)ng, nb * ng);
         }
         CK(cudaGetLastError());

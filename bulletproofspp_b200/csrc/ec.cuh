@@ -122,6 +122,104 @@ BP_HD Jac jac_add(const Jac& p, const Jac& q) {
     return o;
 }
 
+// ---------------------------------------------------------------- XYZZ coordinates
+// (X, Y, ZZ, ZZZ) with x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity: ZZ = 0.  The mixed addition is
+// 8M + 2S (one squaring less than Jacobian + affine), which is what the bucket accumulation of the
+// fixed-base MSM spends nearly all its time in.  (madd-2008-s, add-2008-s, dbl-2008-s-1, mdbl-2008-s-1)
+struct Xyzz {
+    u256 X, Y, ZZ, ZZZ;
+};
+BP_HD Xyzz xyzz_inf() {
+    Xyzz r;
+    r.X = u256_one(); r.Y = u256_one(); r.ZZ = u256_zero(); r.ZZZ = u256_zero();
+    return r;
+}
+BP_HD bool xyzz_is_inf(const Xyzz& p) { return u256_is_zero(p.ZZ); }
+BP_HD Xyzz xyzz_neg(const Xyzz& p) {
+    Xyzz r = p;
+    r.Y = fq::neg(p.Y);
+    return r;
+}
+BP_HD Xyzz xyzz_dbl_aff(const Affine& q) {           // 2 * (affine point), never the identity on an odd-order curve
+    u256 U = fq::dbl(q.y), V = fq::sqr(U), W = fq::mul(U, V), S = fq::mul(q.x, V);
+    u256 x2 = fq::sqr(q.x), M = fq::add(fq::dbl(x2), x2);
+    Xyzz r;
+    r.X = fq::sub(fq::sqr(M), fq::dbl(S));
+    r.Y = fq::sub(fq::mul(M, fq::sub(S, r.X)), fq::mul(W, q.y));
+    r.ZZ = V;
+    r.ZZZ = W;
+    return r;
+}
+BP_HD Xyzz xyzz_dbl(const Xyzz& p) {
+    if (xyzz_is_inf(p)) return p;
+    u256 U = fq::dbl(p.Y), V = fq::sqr(U), W = fq::mul(U, V), S = fq::mul(p.X, V);
+    u256 x2 = fq::sqr(p.X), M = fq::add(fq::dbl(x2), x2);
+    Xyzz r;
+    r.X = fq::sub(fq::sqr(M), fq::dbl(S));
+    r.Y = fq::sub(fq::mul(M, fq::sub(S, r.X)), fq::mul(W, p.Y));
+    r.ZZ = fq::mul(V, p.ZZ);
+    r.ZZZ = fq::mul(W, p.ZZZ);
+    return r;
+}
+// XYZZ + affine, complete: 8M + 2S
+BP_HD Xyzz xyzz_madd(const Xyzz& p, const Affine& q) {
+    if (aff_is_inf(q)) return p;
+    if (xyzz_is_inf(p)) {
+        Xyzz r;
+        r.X = q.x; r.Y = q.y; r.ZZ = u256_one(); r.ZZZ = u256_one();
+        return r;
+    }
+    u256 U2 = fq::mul(q.x, p.ZZ);
+    u256 S2 = fq::mul(q.y, p.ZZZ);
+    u256 P = fq::sub(U2, p.X);
+    u256 R = fq::sub(S2, p.Y);
+    if (u256_is_zero(P)) {
+        if (u256_is_zero(R)) return xyzz_dbl_aff(q);
+        return xyzz_inf();
+    }
+    u256 PP = fq::sqr(P);
+    u256 PPP = fq::mul(P, PP);
+    u256 Q = fq::mul(p.X, PP);
+    Xyzz o;
+    o.X = fq::sub(fq::sub(fq::sqr(R), PPP), fq::dbl(Q));
+    o.Y = fq::sub(fq::mul(R, fq::sub(Q, o.X)), fq::mul(p.Y, PPP));
+    o.ZZ = fq::mul(p.ZZ, PP);
+    o.ZZZ = fq::mul(p.ZZZ, PPP);
+    return o;
+}
+// XYZZ + XYZZ, complete: 12M + 2S
+BP_HD Xyzz xyzz_add(const Xyzz& p, const Xyzz& q) {
+    if (xyzz_is_inf(p)) return q;
+    if (xyzz_is_inf(q)) return p;
+    u256 U1 = fq::mul(p.X, q.ZZ), U2 = fq::mul(q.X, p.ZZ);
+    u256 S1 = fq::mul(p.Y, q.ZZZ), S2 = fq::mul(q.Y, p.ZZZ);
+    u256 P = fq::sub(U2, U1);
+    u256 R = fq::sub(S2, S1);
+    if (u256_is_zero(P)) {
+        if (u256_is_zero(R)) return xyzz_dbl(p);
+        return xyzz_inf();
+    }
+    u256 PP = fq::sqr(P);
+    u256 PPP = fq::mul(P, PP);
+    u256 Q = fq::mul(U1, PP);
+    Xyzz o;
+    o.X = fq::sub(fq::sub(fq::sqr(R), PPP), fq::dbl(Q));
+    o.Y = fq::sub(fq::mul(R, fq::sub(Q, o.X)), fq::mul(S1, PPP));
+    o.ZZ = fq::mul(fq::mul(p.ZZ, q.ZZ), PP);
+    o.ZZZ = fq::mul(fq::mul(p.ZZZ, q.ZZZ), PPP);
+    return o;
+}
+// the same point in Jacobian form with Z = ZZ*ZZZ  (X/ZZ = X ZZ ZZZ^2 / Z^2,  Y/ZZZ = Y ZZ^3 ZZZ^2 / Z^3): 5M + 2S
+BP_HD Jac xyzz_to_jac(const Xyzz& p) {
+    if (xyzz_is_inf(p)) return jac_inf();
+    u256 w2 = fq::sqr(p.ZZZ), a = fq::mul(p.ZZ, w2);           // ZZ * ZZZ^2
+    Jac r;
+    r.X = fq::mul(p.X, a);
+    r.Y = fq::mul(p.Y, fq::mul(fq::sqr(p.ZZ), a));             // Y * ZZ^3 * ZZZ^2
+    r.Z = fq::mul(p.ZZ, p.ZZZ);
+    return r;
+}
+
 // single-point conversion (one field inversion); batch conversion lives in kernels.cu
 BP_HD Affine jac_to_aff(const Jac& p) {
     if (jac_is_inf(p)) return aff_inf();

@@ -48,6 +48,14 @@ __device__ __forceinline__ Jac ld_jac(const Jac* p) {
     r.Z = ld_u256(&p->Z);
     return r;
 }
+__device__ __forceinline__ Xyzz ld_xyzz(const Xyzz* p) {
+    Xyzz r;
+    r.X = ld_u256(&p->X); r.Y = ld_u256(&p->Y); r.ZZ = ld_u256(&p->ZZ); r.ZZZ = ld_u256(&p->ZZZ);
+    return r;
+}
+__device__ __forceinline__ void st_xyzz(Xyzz* p, const Xyzz& r) {
+    st_u256(&p->X, r.X); st_u256(&p->Y, r.Y); st_u256(&p->ZZ, r.ZZ); st_u256(&p->ZZZ, r.ZZZ);
+}
 __device__ __forceinline__ void st_jac(Jac* p, const Jac& r) {
     st_u256(&p->X, r.X);
     st_u256(&p->Y, r.Y);
@@ -725,13 +733,13 @@ struct GtArgs {
     int n_total;                       // terms of this launch: [term0, term0 + n_total)
     int term0;                         // first term (index into the generator list / scalar row)
     int chunk_terms;                   // terms per CTA (<= GT_MAX_CHUNK): chunk c covers [term0 + c*chunk_terms, ...)
-    Jac* scratch;                      // per CTA: [GT_KEYS] key sums + [GT_NB] bucket sums + [2*T] boundary run sums
+    unsigned char* scratch;            // per CTA (GT_SCRATCH_BYTES): [GT_NB] bucket sums (Jacobian) | [GT_KEYS] key sums + [2*T] boundary run sums (XYZZ)
     Jac* out;                          // out[p*out_pstride + o*n_chunks + chunk]
     size_t out_pstride;
     int n_out, n_chunks;
 };
 __device__ __forceinline__ int gt_digit(const u256& s, int j, int& carry) { return signed_digit(s, j, GT_C, carry); }
-#define GT_SCRATCH(T) (GT_KEYS + GT_NB + 2 * (T))
+#define GT_SCRATCH_BYTES(T) ((size_t)GT_NB * sizeof(Jac) + (size_t)(GT_KEYS + 2 * (T)) * sizeof(Xyzz))
 
 template <int T>
 __device__ __forceinline__ void msm_gens_body(const GtArgs& A) {
@@ -745,10 +753,10 @@ __device__ __forceinline__ void msm_gens_body(const GtArgs& A) {
     unsigned* cur = offs + GT_KEYS + 1;                                    // [GT_KEYS]
     unsigned short* list = reinterpret_cast<unsigned short*>(cur + GT_KEYS);
     const size_t cta = ((size_t)p * A.n_out + o) * A.n_chunks + chunk;
-    Jac* keysum = A.scratch + cta * GT_SCRATCH(T);
-    Jac* bsum = keysum + GT_KEYS;
-    Jac* slotF = bsum + GT_NB;
-    Jac* slotL = slotF + T;
+    Jac* bsum = reinterpret_cast<Jac*>(A.scratch + cta * GT_SCRATCH_BYTES(T));
+    Xyzz* keysum = reinterpret_cast<Xyzz*>(bsum + GT_NB);
+    Xyzz* slotF = keysum + GT_KEYS;
+    Xyzz* slotL = slotF + T;
     const int tid = threadIdx.x;
 
     for (int i = tid; i < GT_KEYS; i += T) cur[i] = 0;
@@ -810,42 +818,42 @@ __device__ __forceinline__ void msm_gens_body(const GtArgs& A) {
             int key = lo;
             while (offs[key + 1] <= a) key++;                              // skip empty keys
             unsigned run_end = min(offs[key + 1], b);
-            Jac acc = jac_inf();
+            Xyzz acc = xyzz_inf();
             for (unsigned pos = a; pos < b; pos++) {
                 if (pos == run_end) {                                      // flush the finished run
                     const bool first = offs[key] <= a;                     // (it cannot be the last run)
-                    st_jac(first ? (slotF + tid) : (keysum + key), acc);
-                    acc = jac_inf();
+                    st_xyzz(first ? (slotF + tid) : (keysum + key), acc);
+                    acc = xyzz_inf();
                     do { key++; } while (offs[key + 1] <= pos);
                     run_end = min(offs[key + 1], b);
                 }
-                acc = jac_madd(acc, ld_aff(tbl + list[pos]));   // sign of the key applied once, in (5a)
+                acc = xyzz_madd(acc, ld_aff(tbl + list[pos]));  // sign of the key applied once, in (5a)
             }
             const bool first = offs[key] <= a;
-            st_jac(first ? (slotF + tid) : (slotL + tid), acc);            // the last run ends at b
+            st_xyzz(first ? (slotF + tid) : (slotL + tid), acc);           // the last run ends at b
         }
     }
     __threadfence_block();
     __syncthreads();
 #pragma unroll 1
     for (int m = tid; m < GT_NB; m += T) {                                 // (5a) merge runs per key, combine signs
-        Jac bm = jac_inf();                                                // bucket magnitude m+1
+        Xyzz bm = xyzz_inf();                                              // bucket magnitude m+1
 #pragma unroll 1
         for (int sgn = 0; sgn < 2; sgn++) {
             const int key = m * 2 + sgn;
             const unsigned k0 = offs[key], k1 = offs[key + 1];
             if (k0 == k1) continue;
-            Jac sum = jac_inf();
+            Xyzz sum = xyzz_inf();
             const unsigned t0 = k0 / L, t1 = (k1 - 1) / L;
             for (unsigned t = t0; t <= t1; t++) {
                 const unsigned a = min(E, t * L), b = min(E, a + L);
                 const bool first = k0 <= a, last = k1 >= b;
-                const Jac* src = first ? (slotF + t) : (last ? (slotL + t) : (keysum + key));
-                sum = jac_add(sum, ld_jac(src));
+                const Xyzz* src = first ? (slotF + t) : (last ? (slotL + t) : (keysum + key));
+                sum = xyzz_add(sum, ld_xyzz(src));
             }
-            bm = jac_add(bm, sgn ? jac_neg(sum) : sum);
+            bm = xyzz_add(bm, sgn ? xyzz_neg(sum) : sum);
         }
-        st_jac(bsum + m, bm);
+        st_jac(bsum + m, xyzz_to_jac(bm));                                 // the reduction kernel works in Jacobian form
     }
     // (5b) sum_m m * B_m is a 30-addition dependency chain that only one warp can work on: it runs in
     // k_msm_gens_reduce (one warp per MSM, every SM full) instead of idling 7 of this CTA's 8 warps.
@@ -859,12 +867,12 @@ __global__ void __launch_bounds__(GT_THREADS_SMALL, 8) k_msm_gens_small(GtArgs A
 // Second half of the fixed-base MSM: out = sum_m m * B_m over the 256 bucket sums each k_msm_gens CTA
 // left in its scratch.  One WARP per MSM: 8 buckets per lane by running sums, then a shuffle
 // suffix-scan and a tree.  cta = (p*n_out + o)*n_chunks + chunk as in the first kernel.
-__global__ void __launch_bounds__(256) k_msm_gens_reduce(const Jac* __restrict__ scratch, size_t scratch_stride, Jac* __restrict__ out,
+__global__ void __launch_bounds__(256) k_msm_gens_reduce(const unsigned char* __restrict__ scratch, size_t scratch_stride, Jac* __restrict__ out,
                                                          size_t out_pstride, int n_out, int n_chunks, size_t n_cta) {
     const size_t cta = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (cta >= n_cta) return;
     const int tid = threadIdx.x & 31;
-    const Jac* bsum = scratch + cta * scratch_stride + GT_KEYS;
+    const Jac* bsum = reinterpret_cast<const Jac*>(scratch + cta * scratch_stride);     // stride in bytes
     Jac S = jac_inf(), Wt = jac_inf();                                     // over this lane's 8 buckets (top down)
 #pragma unroll 1
     for (int k = 7; k >= 0; k--) {
