@@ -156,7 +156,7 @@ def make_inputs(batch, offset, n_inputs):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/README.md)
-NCU_TRAFFIC_BYTES = {"k_msm_gens": 53561344 + 83139584}
+NCU_TRAFFIC_BYTES = {"k_msm_gens": 50440704 + 123794944}
 
 
 def main():
