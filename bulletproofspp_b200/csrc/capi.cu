@@ -7,6 +7,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -331,6 +332,23 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
             uint64_t thr = ~0ULL;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        // Grow the pool once, up front (BPPP_POOL_PREWARM_MB, default 8192, 0 = off): when many lanes
+        // overlap in a new way the pool otherwise grows in the middle of a batch, and mapping fresh
+        // device memory stalls every stream for a long time.
+        static std::mutex mu;
+        static bool done[64] = {false};
+        std::lock_guard<std::mutex> lk(mu);
+        if (device < 64 && !done[device]) {
+            done[device] = true;
+            const char* ev = getenv("BPPP_POOL_PREWARM_MB");
+            size_t mb = ev ? (size_t)atoll(ev) : 8192, free_b = 0, total_b = 0;
+            if (mb && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 4 > (mb << 20)) {
+                void* p = nullptr;
+                if (cudaMallocAsync(&p, mb << 20, c->st) == cudaSuccess) cudaFreeAsync(p, c->st);
+                cudaStreamSynchronize(c->st);
+                cudaGetLastError();
+            }
         }
     }
     *out = c;
