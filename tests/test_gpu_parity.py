@@ -295,3 +295,22 @@ def test_sharded_argument_equals_unsharded(ctx, gens, world):
     resp, s_fin, fw, fl = prove_sharded(shards, lambda vals: vals, k, oracle, q, M)
     assert resp == exp
     assert s_fin == com.s and fw == com.vec.norm.get_witness() and fl == com.vec.lin.get_witness()
+
+
+def test_non_canonical_inputs_are_rejected(ctx, gens):
+    """Error behaviour of the ABI: scalars must be < r and coordinates < q (status BPPP_ERR_RANGE, nothing
+    computed); the largest canonical values are accepted.  r - 1 and r share the all-ones top word, which
+    is the boundary of the quick canonical check."""
+    import bulletproofspp_b200 as bp
+    pts = gens(3)
+    assert ctx.msm([(R - 1, pts[0]), (1, pts[1])]) == G.add(G.neg(pts[0]), pts[1])
+    assert ctx.msm([((1 << 256) - (1 << 192) - 1, pts[0])]) == G.mul((1 << 256) - (1 << 192) - 1, pts[0])
+    for bad in (R, R + 5, (1 << 256) - 1):
+        with pytest.raises(bp.BpppError):
+            ctx.msm([(1, pts[0]), (bad, pts[1])])
+    with pytest.raises(bp.BpppError):
+        ctx.msm([(1, (Q, pts[0][1]))])
+    with pytest.raises(bp.BpppError):
+        ctx.msm_batch([[1, R]], pts[:2])
+    # the context is still usable afterwards
+    assert ctx.msm([(2, pts[2])]) == G.add(pts[2], pts[2])
