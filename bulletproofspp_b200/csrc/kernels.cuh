@@ -704,9 +704,12 @@ __global__ void __launch_bounds__(256) k_tensor_expand(TensorArgs A) {
 //   (3) the (term,window) entries are scattered into a shared-memory list sorted by key,
 //   (4) the sorted list is cut into EQUAL ranges, one per thread (balanced whatever the digit
 //       distribution -- reciprocal witnesses repeat scalars heavily); a thread accumulates each
-//       key-run of its range with mixed adds and flushes run sums to a per-CTA scratch,
-//   (5) per key the run sums are merged, +m and -m combined, and warp 0 forms sum_m m*B_m
-//       (8 buckets per lane by running sums, then a shuffle suffix-scan + tree).
+//       key-run of its range with mixed adds (XYZZ accumulator: 8M + 2S per add) and flushes run
+//       sums to a per-CTA scratch,
+//   (5a) per key the run sums are merged, +m and -m combined -> 256 bucket sums B_m per MSM (Jacobian),
+//   (5b) in a second kernel (k_msm_gens_reduce), one warp per MSM forms sum_m m*B_m (8 buckets per
+//       lane by running sums, then a shuffle suffix-scan + tree): a 30-addition dependency chain
+//       that would otherwise idle 7 of the 8 warps of the CTA for a fifth of its life.
 // ------------------------------------------------------------------------------------------
 #define GT_C 9
 #define GT_W 29                        // 29 * 9 = 261 >= 257 bits (signed-digit carry)
