@@ -79,20 +79,21 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- reference arm
-def _ref_worker(args):
+def _ref_worker(args, pippenger=False):
     idx, n = args
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from example_configs import batched
-    from oracle.curve import SecpRef
+    from oracle.curve import SecpPip, SecpRef
     from oracle.rangeproof import load_schema, load_witness, prove, verify
     from oracle.transcript import ZKPT
+    Grp = SecpPip if pippenger else SecpRef
     schema, wits, seeds = batched("128by64", idx + n)
     ok = True
     for b in range(idx, idx + n):
-        s = load_schema(dict(schema, randomSeed=seeds[b]), SecpRef, points=_ref_worker.points)
-        proof = prove(s, ZKPT(SecpRef, s.random_seed), load_witness(s, wits[b]))
-        ok = ok and verify(s, ZKPT(SecpRef, None), proof)
+        s = load_schema(dict(schema, randomSeed=seeds[b]), Grp, points=_ref_worker.points)
+        proof = prove(s, ZKPT(Grp, s.random_seed), load_witness(s, wits[b]))
+        ok = ok and verify(s, ZKPT(Grp, None), proof)
     return ok
 
 
@@ -141,9 +142,15 @@ def cpu_baseline_sample(n_proofs=4):
     t0 = time.time()
     assert _ref_worker((0, n_proofs))
     dt = time.time() - t0
+    t1 = time.time()
+    assert _ref_worker((0, n_proofs), pippenger=True)
+    dt2 = time.time() - t1
     return {"value": n_proofs / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": "%d proofs of 128by64 prove+verify, oracle port of the reference algorithm "
-                      "(256-row Straus MSM, 129-row pair folds, zero-padded openings), single thread" % n_proofs}
+                      "(256-row Straus MSM, 129-row pair folds, zero-padded openings), single thread" % n_proofs,
+            "pippenger": {"value": n_proofs / dt2, "unit": UNIT, "cores": 1,
+                          "sample": "the same %d proofs with an honest CPU MSM (Pippenger, signed windows, no padding; "
+                                    "oracle/c/ref_ec.c pip_msm) in place of the reference's Straus loop" % n_proofs}}
 
 
 # --------------------------------------------------------------------------- our arm

@@ -170,6 +170,87 @@ static void straus(size_t n, const uint8_t* mags, const uint8_t* neg, const uint
     to_affine(out, &v);
     free(xs); free(ys); free(inf);
 }
+/* ---- an honest CPU algorithm for the same sum (baseline (ii)): Pippenger's bucket
+ * method with signed windows over the same projective formulas -- what a CPU implementer would
+ * write instead of the reference's 256-row Straus.  Complete additions (the bucket method adds
+ * points that may coincide). */
+static void pp_add(pp* r, const pp* a, const pp* b) {                /* add-1998-cmo-2, complete */
+    if (fe_is_zero(&a->z)) { *r = *b; return; }
+    if (fe_is_zero(&b->z)) { *r = *a; return; }
+    fe y1z2, x1z2, z1z2, u, uu, v, vv, vvv, R, A, t, t2;
+    fe_mul(&y1z2, &a->y, &b->z); fe_mul(&x1z2, &a->x, &b->z); fe_mul(&z1z2, &a->z, &b->z);
+    fe_mul(&t, &b->y, &a->z); fe_sub(&u, &t, &y1z2);
+    fe_mul(&t, &b->x, &a->z); fe_sub(&v, &t, &x1z2);
+    if (fe_is_zero(&v)) {
+        if (fe_is_zero(&u)) { *r = *a; pp_dbl(r); return; }
+        memset(r, 0, sizeof *r); r->y.v[0] = 1; return;
+    }
+    fe_sqr(&uu, &u); fe_sqr(&vv, &v); fe_mul(&vvv, &v, &vv); fe_mul(&R, &vv, &x1z2);
+    fe_mul(&t, &uu, &z1z2); fe_sub(&t, &t, &vvv); fe_add(&t2, &R, &R); fe_sub(&A, &t, &t2);
+    fe_mul(&r->x, &v, &A);
+    fe_sub(&t, &R, &A); fe_mul(&t, &u, &t); fe_mul(&t2, &vvv, &y1z2); fe_sub(&r->y, &t, &t2);
+    fe_mul(&r->z, &vvv, &z1z2);
+}
+static void pp_madd(pp* v, const fe* x2, const fe* y2) {             /* mixed, complete */
+    if (!fe_is_zero(&v->z)) {
+        fe t, u, w;
+        fe_mul(&t, y2, &v->z); fe_sub(&u, &t, &v->y);
+        fe_mul(&t, x2, &v->z); fe_sub(&w, &t, &v->x);
+        if (fe_is_zero(&w)) {
+            if (fe_is_zero(&u)) { pp_dbl(v); return; }
+            memset(v, 0, sizeof *v); v->y.v[0] = 1; return;
+        }
+    }
+    nrml_add(v, x2, y2);
+}
+/* same interface as ref_msm (magnitudes of the centred lift + signs, affine points, identity = zeros) */
+int pip_msm(size_t n, const uint8_t* mags, const uint8_t* neg, const uint8_t* pts, uint8_t out[64]) {
+    int c = 4;
+    while (c < 14 && ((size_t)1 << (c + 3)) <= n) c++;               /* c ~ log2(n) - 2 */
+    const int windows = (256 + c - 1) / c + 1;                       /* +1 for the signed-digit carry */
+    const size_t nb = (size_t)1 << (c - 1);
+    fe* xs = (fe*)malloc((n + 1) * sizeof(fe));
+    fe* ys = (fe*)malloc((n + 1) * sizeof(fe));
+    fe* nys = (fe*)malloc((n + 1) * sizeof(fe));
+    int* dig = (int*)malloc((n + 1) * windows * sizeof(int));
+    for (size_t i = 0; i < n; i++) {
+        load_fe(&xs[i], pts + 64 * i); load_fe(&ys[i], pts + 64 * i + 32);
+        if (neg[i]) fe_neg(&ys[i], &ys[i]);
+        fe_neg(&nys[i], &ys[i]);
+        const int inf = fe_is_zero(&xs[i]) && fe_is_zero(&ys[i]);
+        int carry = 0;
+        for (int w = 0; w < windows; w++) {                           /* signed digits in [-2^(c-1), 2^(c-1)] */
+            int d = carry;
+            for (int k = 0; k < c; k++) {
+                int bit = w * c + k;
+                if (bit < 256) d += ((mags[32 * i + (bit >> 3)] >> (bit & 7)) & 1) << k;
+            }
+            carry = 0;
+            if (d > (int)nb) { d -= 1 << c; carry = 1; }
+            dig[i * windows + w] = inf ? 0 : d;
+        }
+    }
+    pp* bucket = (pp*)malloc(nb * sizeof(pp));
+    pp acc;
+    memset(&acc, 0, sizeof acc); acc.y.v[0] = 1;
+    for (int w = windows - 1; w >= 0; w--) {
+        for (int k = 0; k < c; k++) pp_dbl(&acc);
+        for (size_t m = 0; m < nb; m++) { memset(&bucket[m], 0, sizeof(pp)); bucket[m].y.v[0] = 1; }
+        for (size_t i = 0; i < n; i++) {
+            int d = dig[i * windows + w];
+            if (d > 0) pp_madd(&bucket[d - 1], &xs[i], &ys[i]);
+            else if (d < 0) pp_madd(&bucket[-d - 1], &xs[i], &nys[i]);
+        }
+        pp run, sum;                                                  /* sum_m m * B_m by running sums */
+        memset(&run, 0, sizeof run); run.y.v[0] = 1;
+        sum = run;
+        for (size_t m = nb; m-- > 0;) { pp_add(&run, &run, &bucket[m]); pp_add(&sum, &sum, &run); }
+        pp_add(&acc, &acc, &sum);
+    }
+    to_affine(out, &acc);
+    free(xs); free(ys); free(nys); free(dig); free(bucket);
+    return 0;
+}
 int ref_msm(size_t n, const uint8_t* mags, const uint8_t* neg, const uint8_t* pts, size_t n_pad, uint8_t out[64]) {
     straus(n, mags, neg, pts, 256, n_pad, out);
     return 0;

@@ -326,6 +326,25 @@ class SecpRef(Secp256k1):
         return [cls._unpt(out.raw[64 * i:64 * i + 64]) for i in range(n)]
 
 
+class SecpPip(SecpRef):
+    """The same group with an honest CPU multi-scalar multiplication (Pippenger, signed windows;
+    pip_msm in oracle/c/ref_ec.c) instead of the reference's 256-row Straus -- baseline (ii) of
+    SURVEY 8(d).  Generator folds keep the reference's 129-row pair product."""
+
+    @classmethod
+    def msm(cls, pairs):
+        import ctypes
+        nz = [(reduce_scalar(s, R), p) for s, p in pairs if s % R and p is not None]
+        if not nz:
+            return None
+        L = cls.lib()
+        L.pip_msm.argtypes = [ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
+        out = ctypes.create_string_buffer(64)
+        L.pip_msm(len(nz), b"".join(abs(s).to_bytes(32, "little") for s, _ in nz), bytes(1 if s < 0 else 0 for s, _ in nz),
+                  b"".join(cls._pt(p) for _, p in nz), out)
+        return cls._unpt(out.raw)
+
+
 class Toy:
     """F_r as a vector space over itself (WrapV, src/Utils.hs:117-133)."""
     name = "toy"

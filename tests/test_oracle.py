@@ -13,7 +13,7 @@ import pytest
 
 from example_configs import EXAMPLES, batched
 from oracle import bulletproof as obp
-from oracle.curve import Secp256k1 as G, SecpRef, Toy, straus_reference
+from oracle.curve import Secp256k1 as G, SecpPip, SecpRef, Toy, straus_reference
 from oracle.field import BETA, LAMBDA, Q, R, GX, GY, batch_inverse, rational_reduce_scalar
 from oracle.rangeproof import load_schema, load_witness, prove, verify, run_example
 from oracle.transcript import ZKPT, digest_to_int, get_points, hash_to, input_blinds, show_field
@@ -59,6 +59,22 @@ def test_reference_straus_matches_complete_group_law():
     a, b = rational_reduce_scalar(rnd.randrange(R))
     prs = [(pts[i], pts[i + 1]) for i in range(0, 10, 2)] + [(pts[10], None)]
     assert SecpRef.pair_ip_many(b, a, prs) == G.pair_ip_many(b, a, prs)
+
+
+def test_cpu_pippenger_baseline_matches_group_law():
+    """pip_msm (oracle/c/ref_ec.c): the honest CPU MSM timed beside the reference's Straus loop in
+    bench.py's cpu_baseline -- repeated points, P and -P, zero scalars, the identity, extreme scalars."""
+    pts = get_points(G, "test points", 140)
+    rnd = random.Random(9)
+    for n in (1, 2, 3, 17, 64, 140):
+        pairs = [(rnd.randrange(R), pts[i]) for i in range(n)]
+        if n >= 3:
+            pairs[1] = pairs[0]
+            pairs[2] = (R - pairs[0][0], pairs[0][1])
+        if n >= 17:
+            pairs[5], pairs[6], pairs[7], pairs[8] = (0, pts[5]), (7, None), (R - 1, pts[7]), (1 << 255, pts[8])
+        assert SecpPip.msm(pairs) == G.msm(pairs)
+    assert SecpPip.msm([(3, pts[0]), (R - 3, pts[0])]) is None
 
 
 def test_generators_are_on_curve_and_deterministic():
