@@ -932,7 +932,7 @@ const char* ctx_err(const Lane& ln) { return bppp_last_error(ln.ctx); }
 int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t rounds, const uint8_t* q, const uint8_t* sc,
                  const uint8_t* w, const uint8_t* l, const uint8_t* c,
                  uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l, bool device_witness = false) {
-    const size_t B = P.size(), N = s->nrm_len, M = s->lin_len;
+    const size_t B = P.size();
     bppp_nl* h = nullptr;
     int rc = device_witness ? bppp_nl_create_trrp(ln.trrp, q, sc, l, c, &h) : bppp_nl_create_gens(ln.gens, s->arg, B, q, sc, w, l, c, &h);
     if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(ln));
@@ -1910,7 +1910,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         zk.fmt = s->fmt;
         zk.no_random = true;
         const uint8_t* cm = coms + 64 * b * NC;
-        Fr q, sp;
+        Fr q;
         RPW pub;
         std::vector<Fr> cs, init_s;
         if (s->binary) {                                                    // verifyBRPM (Binary.hs:205-220)
