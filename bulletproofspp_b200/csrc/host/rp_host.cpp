@@ -2229,6 +2229,26 @@ int bppp_host_transcript(const char* seed, int show_format, size_t n_random, con
     }
     return BPPP_OK;
 }
+// The host job scheduler under load: `lanes` threads each submit `jobs` jobs of `items` items with
+// rising priorities (like lanes advancing through their phases).  Every item must run exactly once
+// and every submitter must come back.  Returns 0, or the number of items with a wrong count.
+int bppp_host_scheduler_selftest(int lanes, int jobs, int items) {
+    if (lanes <= 0 || jobs <= 0 || items <= 0) return -1;
+    std::vector<std::atomic<int>> hits((size_t)lanes * jobs * items);
+    for (auto& h : hits) h.store(0);
+    std::vector<std::thread> th;
+    for (int l = 0; l < lanes; l++)
+        th.emplace_back([&, l] {
+            for (int j = 0; j < jobs; j++) {
+                std::function<void(size_t)> f = [&, l, j](size_t i) { hits[((size_t)l * jobs + j) * items + i]++; };
+                pool().run((size_t)items, (int64_t)j * 1024 - l, f);
+            }
+        });
+    for (auto& t : th) t.join();
+    int bad = 0;
+    for (auto& h : hits) bad += h.load() != 1;
+    return bad;
+}
 int bppp_host_fr(int op, const uint8_t* a, const uint8_t* b, uint8_t* out) {
     if (!h64::host_cpu_ok()) return BPPP_ERR_STATE;
     Fr x = h64::from_bytes(a), y = h64::from_bytes(b), r;

@@ -16,7 +16,7 @@ EXPORTS = [
     "bppp_fb_create", "bppp_fb_msm_batch", "bppp_fb_destroy",
     "bppp_rp_setup", "bppp_rp_free", "bppp_rp_last_error", "bppp_rp_info", "bppp_rp_points", "bppp_input_blind",
     "bppp_set_host_threads", "bppp_rp_prove_batch", "bppp_rp_verify_batch",
-    "bppp_host_sha256", "bppp_host_oracle", "bppp_host_fr", "bppp_host_get_points", "bppp_host_transcript",
+    "bppp_host_sha256", "bppp_host_oracle", "bppp_host_fr", "bppp_host_get_points", "bppp_host_transcript", "bppp_host_scheduler_selftest",
     "bppp_profile_enable", "bppp_profile_reset", "bppp_profile_report", "bppp_timer_start", "bppp_timer_stop",
     "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",

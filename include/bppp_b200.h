@@ -236,6 +236,8 @@ int bppp_rp_contexts(bppp_rp* s, bppp_ctx** out, size_t cap, size_t* count);
 int bppp_host_sha256(const uint8_t* data, size_t n, uint8_t out[32]);
 int bppp_host_oracle(const uint8_t* pts, size_t npts, int count, int show_format, uint8_t* out);
 int bppp_host_fr(int op, const uint8_t* a, const uint8_t* b, uint8_t* out);
+/* the host job scheduler under concurrent submitters: 0 when every item of every job ran exactly once */
+int bppp_host_scheduler_selftest(int lanes, int jobs, int items);
 /* the batched transcript paths (two-stream SHA-256): n_random values of `random`, commitments `pts`,
  * then `rounds` (X,R) pairs (128 B each); out = randoms | round challenges | the same via the paired path */
 int bppp_host_transcript(const char* seed, int show_format, size_t n_random, const uint8_t* pts, size_t npts,

@@ -187,3 +187,11 @@ def test_batched_transcript_paths_match_oracle(lib):
             assert got[:n_random] == exp
             assert got[n_random:n_random + rounds] == es
             assert got[n_random + rounds:] == es
+
+
+def test_host_job_scheduler_runs_every_item_once(lib):
+    """The priority job scheduler that runs the lanes' host phases (rp_host.cpp): many concurrent
+    submitters, jobs of 1..300 items, repeated."""
+    for lanes, jobs, items in [(1, 3, 1), (4, 20, 7), (16, 30, 64), (8, 10, 300), (16, 200, 3)]:
+        assert lib.bppp_host_scheduler_selftest(lanes, jobs, items) == 0
+    assert lib.bppp_host_scheduler_selftest(0, 1, 1) == -1
