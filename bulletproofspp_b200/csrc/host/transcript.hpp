@@ -35,19 +35,19 @@ inline void append_decimal(std::string& out, const uint64_t v[4]) {
     int top = 3;
     while (top >= 0 && t[top] == 0) top--;
     while (top >= 0) {
+        // (rem, t[i]) / 10^19 by multiplication with the precomputed reciprocal of the (normalised)
+        // divisor -- Moeller & Granlund, "Improved division by invariant integers", algorithm 4
+        const uint64_t RECIP = 0xd83c94fb6d2ac34aULL;             // floor((2^128 - 1) / 10^19) - 2^64
         uint64_t rem = 0;
         for (int i = top; i >= 0; i--) {
-#if defined(__x86_64__)
-            // 128 / 64 -> 64 division in one instruction (rem < 10^19, so the quotient fits)
-            uint64_t qd, rd;
-            asm("divq %4" : "=a"(qd), "=d"(rd) : "0"(t[i]), "1"(rem), "r"(TEN19) : "cc");
-            t[i] = qd;
-            rem = rd;
-#else
-            u128 cur = ((u128)rem << 64) | t[i];
-            t[i] = (uint64_t)(cur / TEN19);
-            rem = (uint64_t)(cur % TEN19);
-#endif
+            const uint64_t u1 = rem, u0 = t[i];
+            u128 q = (u128)RECIP * u1 + (((u128)u1 << 64) | u0);
+            uint64_t q1 = (uint64_t)(q >> 64) + 1, q0 = (uint64_t)q;
+            uint64_t r = u0 - q1 * TEN19;
+            if (r > q0) { q1--; r += TEN19; }
+            if (r >= TEN19) { q1++; r -= TEN19; }
+            t[i] = q1;
+            rem = r;
         }
         chunks[nc++] = rem;
         while (top >= 0 && t[top] == 0) top--;
