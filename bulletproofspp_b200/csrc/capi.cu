@@ -23,11 +23,11 @@ using namespace bppp;
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
-                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce"};
+                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce", "k_check_points"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -140,6 +140,7 @@ static double fold_alg_imads(double n_points) { return n_points * 0.5 * 3.9e3 * 
 #define WORK_K_DBG_EC 0
 static thread_local double g_work = 0;           // set by the caller right before a launch
 
+int g_bppp_tune_device = 0;     // set by bppp_tune_process (rp_host.cpp)
 int g_capi_threads = 0;
 static thread_local int t_capi_threads = 0;
 extern "C" void bppp_set_device_host_threads(int n) { g_capi_threads = n; }
@@ -305,6 +306,32 @@ int to_affine(bppp_ctx* ctx, const Jac* in, size_t in_stride, Affine* out, size_
     return BPPP_OK;
 }
 
+
+// every point of pts[0..n) on the curve (or the identity)?  `flags` gets one int per group of `per`
+// consecutive points (non-zero = an off-curve point in the group); no synchronisation here.
+int check_points_async(bppp_ctx* ctx, const Affine* pts, size_t n, size_t per, DBuf<int>& flags) {
+    const size_t groups = (n + per - 1) / per;
+    CK(flags.alloc(std::max<size_t>(groups, 1)));
+    CK(cudaMemsetAsync(flags.p, 0, std::max<size_t>(groups, 1) * sizeof(int), ctx->st));
+    if (n == 0) return BPPP_OK;
+    { ProfScope ps_(ctx, K_CHECK, 0);
+    k_check_points<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(pts, n, per, flags.p);
+    }
+    CK(cudaGetLastError());
+    return BPPP_OK;
+}
+// the same for one group, synchronously: BPPP_ERR_RANGE when a point is off the curve
+int check_points_sync(bppp_ctx* ctx, const Affine* pts, size_t n, const char* what) {
+    DBuf<int> flags;
+    int rc = check_points_async(ctx, pts, n, std::max<size_t>(n, 1), flags);
+    if (rc) return rc;
+    int bad = 0;
+    CK(cudaMemcpyAsync(&bad, flags.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->st));
+    CK(ctx_sync(ctx));
+    if (bad) FAIL(BPPP_ERR_RANGE, std::string(what) + ": point not on the curve");
+    return BPPP_OK;
+}
+
 }  // namespace
 
 // =============================================================================== context
@@ -315,10 +342,14 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
     *out = nullptr;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return BPPP_ERR_CUDA;
-    // host threads waiting for the device sleep instead of spinning: the cores are needed by the
-    // host phases of the other lanes (ignored if the primary context is already active)
-    cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
-    cudaGetLastError();
+    // bppp_tune_process(BPPP_TUNE_DEVICE) only: host threads waiting for the device sleep instead of
+    // spinning (the cores are needed by the host phases of the other lanes; ignored if the primary
+    // context is already active).  Without it the process-wide device flags are left alone; waits still
+    // sleep on the context's blocking-sync event.
+    if (g_bppp_tune_device) {
+        cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
+        cudaGetLastError();
+    }
     if (cudaSetDevice(device) != cudaSuccess) return BPPP_ERR_CUDA;
     bppp_ctx* c = new bppp_ctx();
     c->dev = device;
@@ -333,7 +364,8 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
             uint64_t thr = ~0ULL;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
         }
-        // Grow the pool once, up front (BPPP_POOL_PREWARM_MB, default 8192, 0 = off): when many lanes
+        // Grow the pool once, up front (BPPP_POOL_PREWARM_MB; default 8192 after bppp_tune_process(BPPP_TUNE_DEVICE),
+        // else off): when many lanes
         // overlap in a new way the pool otherwise grows in the middle of a batch, and mapping fresh
         // device memory stalls every stream for a long time.
         static std::mutex mu;
@@ -342,7 +374,7 @@ extern "C" int bppp_init(int device, bppp_ctx** out) {
         if (device < 64 && !done[device]) {
             done[device] = true;
             const char* ev = getenv("BPPP_POOL_PREWARM_MB");
-            size_t mb = ev ? (size_t)atoll(ev) : 8192, free_b = 0, total_b = 0;
+            size_t mb = ev ? (size_t)atoll(ev) : (g_bppp_tune_device ? 8192 : 0), free_b = 0, total_b = 0;
             if (mb && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b / 4 > (mb << 20)) {
                 void* p = nullptr;
                 if (cudaMallocAsync(&p, mb << 20, c->st) == cudaSuccess) cudaFreeAsync(p, c->st);
@@ -525,6 +557,7 @@ extern "C" int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8
     CK(d_aff.alloc(batch));
     CK(H2D(d_sc.p, scalars, batch * n * 32));
     CK(H2D(d_pts.p, points, npts * 64));
+    { int rc0 = check_points_sync(ctx, d_pts.p, npts, "bppp_msm_batch"); if (rc0) return rc0; }
     MsmPlan plan;
     plan.add(d_pts.p, shared_points ? 0 : n, d_sc.p, n, 0, n);
     int rc = run_msm(ctx, plan, batch, 1, d_res.p, msm_alg_imads((double)n));
@@ -563,6 +596,7 @@ extern "C" int bppp_fb_create(bppp_ctx* ctx, size_t n_bases, const uint8_t* poin
         return BPPP_ERR_CUDA;
     }
     H2D(d_b.p, points, n_bases * 64);
+    { int rc0 = check_points_sync(ctx, d_b.p, n_bases, "bppp_fb_create"); if (rc0) { delete fb; return rc0; } }
     int nt = (int)(n_bases * FB_WINDOWS);
     { ProfScope ps_(ctx, K_FB_BUILD, WORK_K_FB_BUILD);
     k_fb_build<<<(nt + 31) / 32, 32, 0, ctx->st>>>(d_b.p, (int)n_bases, d_j.p);
@@ -659,6 +693,7 @@ extern "C" int bppp_pair_fold(bppp_ctx* ctx, size_t n_in, const uint8_t a[32], i
     CK(H2D(d_in.p, points_in, n_in * 64));
     CK(H2D(d_k.p, ks, 64));
     CK(H2D(d_s.p, &sg, 1));
+    { int rc0 = check_points_sync(ctx, d_in.p, n_in, "bppp_pair_fold"); if (rc0) return rc0; }
     PairFoldSeg seg = {0, (int)n_in, 0};
     int rc = launch_pair_fold(ctx, d_in.p, 0, d_j.p, 0, &seg, 1, d_k.p, d_k.p + 1, d_s.p, 1);
     if (rc) return rc;
@@ -801,6 +836,7 @@ extern "C" int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t
         return BPPP_ERR_CUDA;
     }
     H2D(gg->base.p, gg->host.data(), gg->P0 * 64);
+    { int rc0 = check_points_sync(ctx, gg->base.p, gg->P0, "bppp_gens_create"); if (rc0) { delete gg; return rc0; } }
     { ProfScope ps_(ctx, K_GT_BUILD, 0);
     k_gt_build<<<(unsigned)((gg->P0 + 63) / 64), 64, 0, ctx->st>>>(gg->base.p, gg->P0, tj.p);
     }
@@ -1914,6 +1950,15 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     bppp_ctx* ctx = gens->ctx;
     const size_t N = gens->N, M = gens->M;
     const size_t B = batch, P0 = 1 + N + M, NX = n_init + 2 * k;
+    if (k > 30) FAIL(BPPP_ERR_ARG, "too many rounds");
+    {   // the final witness has exactly the lengths k rounds leave (roundReduce, src/Bulletproof.hs:300-304; the
+        // reference's decodeProof' derives them from the setup, src/RangeProof.hs:70-71): a surplus final scalar
+        // would enter the scalar check sum (wgt * v^2) without being bound to any generator
+        size_t en = kind == BPPP_ARG_IP ? (N + 1) / 2 : N, el = M;
+        for (size_t r = 0; r < k; r++) { en = en / 2 + en % 2; el = el / 2 + el % 2; }
+        if (kind == BPPP_ARG_IP) en *= 2;
+        if (n_norm != en || n_lin != el) FAIL(BPPP_ERR_ARG, "final witness lengths do not match the number of rounds");
+    }
     if (!check_fq(XR, 4 * k * B) || !check_fq(init_p, 2 * n_init * B)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
     if (!check_fr(q, B) || !check_fr(s_pub, B) || (!pub_dev && !check_fr(pub_w, B * N)) || !check_fr(c, B * M) || !check_fr(es, B * k) ||
         !check_fr(fw, B * n_norm) || !check_fr(fl, B * n_lin) || !check_fr(init_s, B * n_init))
@@ -2014,9 +2059,12 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     }
     if (nvs) CK(H2D(vs_n.p, hvn.data(), B * nvs * 32));
     if (n_lin) CK(H2D(vs_l.p, hvl.data(), B * n_lin * 32));
+    DBuf<int> offcurve;                                      // per proof: a commitment / response point is off the curve
     if (NX) {
         CK(H2D(xsc.p, hx.data(), B * NX * 32));
         CK(H2D(extra.p, hp.data(), B * NX * 64));
+        int rc0 = check_points_async(ctx, extra.p, B * NX, NX, offcurve);
+        if (rc0) return rc0;
     }
     if (N && ip) {
         IpVerifyArgs A;
@@ -2075,9 +2123,11 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     }
     if ((rc = to_affine(ctx, NX ? res2.p : res.p, 1, aff.p, 1, 0, 1, B))) return rc;
     std::vector<Affine> out(B);
+    std::vector<int> bad(B, 0);
     CK(D2H(out.data(), aff.p, B * 64));
+    if (NX) CK(D2H(bad.data(), offcurve.p, B * sizeof(int)));
     CK(ctx_sync(ctx));
-    for (size_t b = 0; b < B; b++) ok[b] = aff_is_inf(out[b]) ? 1 : 0;
+    for (size_t b = 0; b < B; b++) ok[b] = (aff_is_inf(out[b]) && !bad[b]) ? 1 : 0;
     return BPPP_OK;
 }
 }  // namespace

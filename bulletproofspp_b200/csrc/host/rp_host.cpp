@@ -327,7 +327,10 @@ struct bppp_rp {
     // extra lanes: sub-batches of one call run concurrently, each on its own context (stream) and
     // driver thread, so the host phases of one lane overlap the device work of another
     // page-locked staging buffers, one set per lane, grown on demand and reused across calls
-    struct Pinned { void* p = nullptr; size_t cap = 0; };
+    struct Pinned {
+        void* p = nullptr; size_t cap = 0; bool pageable = false;
+        void release() { if (p) { if (pageable) free(p); else bppp_pinned_free(p); } p = nullptr; cap = 0; }
+    };
     std::vector<std::vector<Pinned>> pinned;
     std::vector<bppp_ctx*> lane_ctx;
     std::vector<bppp_fb*> lane_fb;
@@ -914,12 +917,15 @@ enum { PB_IN = 0, PB_SC1, PB_SC2, PB_C1, PB_C2, PB_NCOMS, PB_Q, PB_S, PB_W, PB_L
 uint8_t* lane_buf(bppp_rp* s, const Lane& ln, int slot, size_t bytes) {
     auto& pb = s->pinned[ln.index][slot];
     if (pb.cap < bytes) {
-        bppp_pinned_free(pb.p);
-        pb.p = nullptr;
+        pb.release();
         pb.cap = 0;
         size_t want = bytes + bytes / 8 + 4096;
-        if (bppp_pinned_alloc(want, &pb.p)) { pb.p = malloc(want); }     // fall back to pageable memory
-        pb.cap = want;
+        pb.pageable = false;
+        if (bppp_pinned_alloc(want, &pb.p)) {                             // fall back to pageable memory
+            pb.p = malloc(want);
+            pb.pageable = true;
+        }
+        pb.cap = pb.p ? want : 0;
     }
     return (uint8_t*)pb.p;
 }
@@ -989,7 +995,10 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
 // BPPP_SAMPLE=file: a SIGPROF sampling profiler of the whole process (1 kHz of CPU time, program
 // counters only) for finding where the host cores go on a box without perf; tools/sample_report.py
 // resolves the counts against the library's symbol table.
+// Compiled only with -DBPPP_SAMPLER (a development build): a release library installs no signal handler
+// and no interval timer -- SIGPROF / ITIMER_PROF belong to the host application (GHC's RTS uses them).
 namespace {
+#ifdef BPPP_SAMPLER
 std::atomic<size_t> g_ns{0};
 void** g_samples = nullptr;
 const size_t kMaxSamples = 1 << 20;
@@ -1026,6 +1035,9 @@ void sample_start() {
         atexit(sample_dump);
     });
 }
+#else
+void sample_start() {}
+#endif
 }  // namespace
 
 // =================================================================================== C ABI
@@ -1034,6 +1046,27 @@ extern "C" {
 void bppp_set_host_threads(int n) {
     g_threads = n;
     bppp_set_device_host_threads(n);
+}
+
+// Process-wide tuning for a batch-proving process, OPT-IN (nothing here happens unless the embedding
+// application asks for it -- a library loaded under a GHC RTS or next to torch must not change global
+// state behind its host's back):
+//   BPPP_TUNE_MALLOC    keep freed memory in the malloc arenas (the per-proof scratch vectors of 16 host
+//                       threads add up to ~1 MB per proof: no mmap/munmap + page faults per proof)
+//   BPPP_TUNE_DEVICE    contexts created afterwards ask for cudaDeviceScheduleBlockingSync and pre-grow
+//                       the stream-ordered memory pool (BPPP_POOL_PREWARM_MB, default 8192)
+extern int g_bppp_tune_device;
+int bppp_tune_process(int flags) {
+    if (flags & BPPP_TUNE_MALLOC) {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            mallopt(M_MMAP_THRESHOLD, 1 << 30);
+            mallopt(M_TRIM_THRESHOLD, 0x7fffffff);
+            mallopt(M_TOP_PAD, 256 << 20);
+        });
+    }
+    if (flags & BPPP_TUNE_DEVICE) g_bppp_tune_device = 1;
+    return BPPP_OK;
 }
 
 int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserved, const char* basis_seed, int show_format,
@@ -1045,15 +1078,6 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
     if (!h64::host_cpu_ok()) {
         fprintf(stderr, "bppp_rp_setup: this build's host field arithmetic needs BMI2 + ADX (rebuild with -DBPPP_HOST_PORTABLE_FR)\n");
         return BPPP_ERR_STATE;
-    }
-    {   // the per-proof scratch vectors of 16 host threads add up to ~1 MB per proof: keep freed
-        // memory in the arenas instead of mmap/munmap + page-faulting it back for every proof
-        static std::once_flag once;
-        std::call_once(once, [] {
-            mallopt(M_MMAP_THRESHOLD, 1 << 30);
-            mallopt(M_TRIM_THRESHOLD, 0x7fffffff);
-            mallopt(M_TOP_PAD, 256 << 20);
-        });
     }
     bppp_rp* s = new bppp_rp();
     s->ctx = ctx; s->binary = binary != 0; s->arg = arg_kind; s->flag = typed_or_conserved != 0;
@@ -1191,7 +1215,7 @@ void bppp_rp_free(bppp_rp* s) {
     bppp_fb_destroy(s->fb);
     bppp_gens_destroy(s->gens);
     for (auto& lane : s->pinned)
-        for (auto& pb : lane) bppp_pinned_free(pb.p);
+        for (auto& pb : lane) pb.release();
     for (size_t i = 0; i < s->lane_ctx.size(); i++) {
         bppp_fb_destroy(s->lane_fb[i]);
         bppp_gens_destroy(s->lane_gens[i]);
@@ -2049,6 +2073,12 @@ int bppp_rp_verify_batch(bppp_rp* s, size_t batch, size_t rounds, size_t n_norm,
                          const uint8_t* responses, const uint8_t* finals, int* ok) {
     if (!s) return BPPP_ERR_ARG;
     if (!coms || !finals || !ok || batch == 0 || (rounds && !responses)) return fail(s, BPPP_ERR_ARG, "null/empty argument");
+    // The shape of a proof is fixed by the setup (decodeProof' derives it with optimalWitnessSize,
+    // src/RangeProof.hs:70-71); the Binary prover's own round rule (Binary.hs:195) is accepted as well.
+    // Anything else is refused: extra rounds / final scalars would not be bound by the check.
+    const bool shape_prover = rounds == s->prover_rounds && n_norm == s->prover_fin_n && n_lin == s->prover_fin_l;
+    const bool shape_decoder = rounds == s->rounds && n_norm == s->fin_n && n_lin == s->fin_l;
+    if (!shape_prover && !shape_decoder) return fail(s, BPPP_ERR_ARG, "proof shape (rounds, final witness lengths) differs from the setup's");
     const size_t NC = s->num_rp_coms + s->n_inputs;
     return run_lanes(s, batch, [&](const Lane& ln, size_t b0, size_t nb) {
         return verify_impl(s, ln, nb, rounds, n_norm, n_lin, coms + 64 * b0 * NC, responses + 128 * b0 * rounds,
@@ -2120,7 +2150,7 @@ int bppp_rp_encode_batch(bppp_rp* s, size_t batch, const uint8_t* coms, const ui
 }
 // decodeProof' (src/RangeProof.hs:68-85) + decodeCommitments / fromXWithSign (Encoding.hs:97-128):
 // x-only points are decompressed with one Fq square root each (host; batchable on the device later).
-// ok[b] = 0 when some x is not on the curve or a scalar is not canonical.
+// ok[b] = 0 when some x is not on the curve; scalars are reduced mod r like the reference's toP (Encoding.hs:75-79).
 int bppp_rp_decode_batch(bppp_rp* s, size_t batch, const uint8_t* proof_bin, const uint8_t* commits_bin, uint8_t* coms,
                          uint8_t* responses, uint8_t* finals, int* ok) {
     if (!s || !proof_bin || !commits_bin || !coms || !responses || !finals || !ok) return BPPP_ERR_ARG;

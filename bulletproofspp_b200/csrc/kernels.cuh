@@ -1400,6 +1400,25 @@ __global__ void __launch_bounds__(TRRP_THREADS) k_trrp_verify_pub(TrrpVArgs A) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Input validation: every caller-supplied point must satisfy y^2 = x^3 + 7 or be the identity
+// (0, 0).  The a = 0 group law never uses b, so an off-curve point would be added on some OTHER curve
+// y^2 = x^3 + b' (possibly with small subgroups) -- the reference cannot construct such a point
+// because every decoded point goes through pointX / fromA (app/Main.hs:72, src/Encoding.hs:99-116).
+// bad[i / per] |= 1 for an off-curve point i.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_check_points(const Affine* __restrict__ pts, size_t n, size_t per, int* __restrict__ bad) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Affine p = ld_aff(pts + i);
+    if (aff_is_inf(p)) return;
+    u256 rhs = fq::mul(fq::sqr(p.x), p.x);
+    u256 seven = u256_zero();
+    seven.v[0] = 7;
+    rhs = fq::add(rhs, seven);
+    if (!u256_eq(fq::sqr(p.y), rhs)) atomicOr(bad + i / per, 1);
+}
+
+// ------------------------------------------------------------------------------------------
 // debug / self-test kernels (exercised by tests/ through bppp_dbg_*)
 // ------------------------------------------------------------------------------------------
 __global__ void k_dbg_field(const u256* a, const u256* b, u256* out, size_t n, int op) {

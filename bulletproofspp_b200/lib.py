@@ -9,7 +9,7 @@ _LIB = None
 
 # every symbol include/bppp_b200.h declares (tests check the library exports all of them)
 EXPORTS = [
-    "bppp_init", "bppp_free", "bppp_last_error", "bppp_abi_version", "bppp_launch_count", "bppp_sync",
+    "bppp_init", "bppp_free", "bppp_last_error", "bppp_tune_process", "bppp_abi_version", "bppp_launch_count", "bppp_sync",
     "bppp_msm", "bppp_msm_batch", "bppp_pair_fold", "bppp_rational_reduce",
     "bppp_nl_create", "bppp_nl_round_commit", "bppp_nl_round_fold", "bppp_nl_lengths", "bppp_nl_final",
     "bppp_nl_destroy", "bppp_nl_verify", "bppp_dbg_field", "bppp_dbg_ec",
@@ -114,6 +114,11 @@ def load_library():
     lib.bppp_host_oracle.argtypes = [u8p, sz, ip, ip, u8p]
     lib.bppp_host_fr.argtypes = [ip, u8p, u8p, u8p]
     lib.bppp_host_get_points.argtypes = [C.c_char_p, sz, ip, u8p]
+    lib.bppp_tune_process.argtypes = [ip]
+    # this harness drives dedicated batch-proving processes (tests, bench.py): opt in to the process-wide
+    # tuning (malloc arenas, blocking-sync device flags, pool pre-growth); BPPP_NO_TUNE=1 leaves the process alone
+    if not os.environ.get("BPPP_NO_TUNE"):
+        lib.bppp_tune_process(3)
     _LIB = lib
     return lib
 
@@ -534,10 +539,19 @@ class RangeProofSetup:
         return [bool(v) for v in ok]
 
     def verify_batch(self, proofs):
-        coms = b"".join(points_to_bytes(p["coms"]) for p in proofs)
-        resp = b"".join(point_to_bytes(x) + point_to_bytes(r) for p in proofs for x, r in p["responses"])
-        fin = b"".join(ints_to_bytes(p["finals"]) for p in proofs)
-        return self.verify_batch_raw(len(proofs), coms, resp, fin, rounds=len(proofs[0]["responses"]))
+        # the proof's shape comes from the setup, never from the proof (decodeProof', src/RangeProof.hs:70-71):
+        # a proof with another number of rounds / final scalars / commitments is rejected without a device call
+        nc, nf = self.num_rp_coms + self.n_inputs, self.fin_norm + self.fin_lin
+        shaped = [len(p["responses"]) == self.rounds and len(p["finals"]) == nf and len(p["coms"]) == nc for p in proofs]
+        good = [p for p, s in zip(proofs, shaped) if s]
+        res = []
+        if good:
+            coms = b"".join(points_to_bytes(p["coms"]) for p in good)
+            resp = b"".join(point_to_bytes(x) + point_to_bytes(r) for p in good for x, r in p["responses"])
+            fin = b"".join(ints_to_bytes(p["finals"]) for p in good)
+            res = self.verify_batch_raw(len(good), coms, resp, fin)
+        it = iter(res)
+        return [next(it) if s else False for s in shaped]
 
     def close(self):
         if getattr(self, "h", None):

@@ -34,6 +34,13 @@ enum { BPPP_ARG_NL = 0, BPPP_ARG_IP = 1 };
 int bppp_init(int device, bppp_ctx** out);
 void bppp_free(bppp_ctx* ctx);
 const char* bppp_last_error(bppp_ctx* ctx);
+/* OPT-IN process-wide tuning for a dedicated batch-proving process (bench.py and the Python harness
+ * call it; a library embedded under a GHC RTS should not): BPPP_TUNE_MALLOC keeps freed host memory
+ * in the malloc arenas (mallopt), BPPP_TUNE_DEVICE makes contexts created afterwards request
+ * cudaDeviceScheduleBlockingSync and pre-grow the device memory pool.  Nothing of this happens
+ * without the call. */
+enum { BPPP_TUNE_MALLOC = 1, BPPP_TUNE_DEVICE = 2 };
+int bppp_tune_process(int flags);
 /* ABI version; bumped on any signature change */
 int bppp_abi_version(void);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */

@@ -175,3 +175,58 @@ def test_hybrid_round_mode_is_bit_identical(ctx, monkeypatch):
     assert p["coms"] == g1["coms"] and p["responses"] == g1["responses"] and p["finals"] == g1["finals"]
     assert setup.verify_batch(proofs) == [True, True]
     setup.close()
+
+
+def test_wrong_shape_and_off_curve_points_are_rejected(ctx):
+    """the proof's shape comes from the setup, and every supplied point must be on the curve.
+    An extra round + an extra final scalar (a free, unbound term in the scalar check) must not verify."""
+    import ctypes as C
+    import bulletproofspp_b200 as bp
+    from bulletproofspp_b200 import lib as L
+    schema, wit = EXAMPLES["typed_nl"]
+    setup = bp.RangeProofSetup(ctx, schema)
+    proof = setup.prove_batch([wit])[0]
+    assert setup.verify_batch([proof]) == [True]
+    # one more round (a copy of the newest response) and one more final scalar
+    longer = dict(proof, responses=[proof["responses"][0]] + proof["responses"], finals=proof["finals"] + [1])
+    assert setup.verify_batch([longer, proof]) == [False, True]
+    # the raw C entry point refuses shapes that are not the setup's
+    coms = L.points_to_bytes(longer["coms"])
+    resp = b"".join(L.point_to_bytes(x) + L.point_to_bytes(r) for x, r in longer["responses"])
+    fin = L.ints_to_bytes(longer["finals"])
+    ok = (C.c_int * 1)()
+    rc = ctx.lib.bppp_rp_verify_batch(setup.h, 1, setup.rounds + 1, setup.fin_norm + 1, setup.fin_lin, coms, resp, fin, ok)
+    assert rc != 0 and not ok[0]
+    # an off-curve commitment / response point: same x, y + 1
+    x, y = proof["coms"][0]
+    off = dict(proof, coms=[(x, y + 1)] + proof["coms"][1:])
+    xr, yr = proof["responses"][0][0]
+    off2 = dict(proof, responses=[((xr, yr + 1), proof["responses"][0][1])] + proof["responses"][1:])
+    assert setup.verify_batch([off, proof, off2]) == [False, True, False]
+    setup.close()
+
+
+def test_argument_seam_validates_shapes_and_points(ctx, gens):
+    """bppp_nl_verify refuses final-witness lengths that k rounds cannot leave; bppp_msm / bppp_gens_create
+    refuse bases that are not on the curve (the reference's pointX / fromA cannot produce them)."""
+    import ctypes as C
+    import bulletproofspp_b200 as bp
+    from bulletproofspp_b200 import lib as L
+    pts = gens(8)
+    sc = L.ints_to_bytes([3, 5, 7])
+    good = L.points_to_bytes(pts[:3])
+    out = C.create_string_buffer(64)
+    assert ctx.lib.bppp_msm(ctx.h, 3, sc, good, out) == 0
+    bad = L.points_to_bytes([pts[0], (pts[1][0], pts[1][1] ^ 1), pts[2]])
+    assert ctx.lib.bppp_msm(ctx.h, 3, sc, bad, out) == 3            # BPPP_ERR_RANGE
+    h = C.c_void_p()
+    assert ctx.lib.bppp_gens_create(ctx.h, 2, 0, L.point_to_bytes(pts[0]), bad[64:], None, C.byref(h)) == 3
+    # N = 4, M = 0, k = 1 rounds leave 2 norm scalars: 3 is refused
+    N, k = 4, 1
+    z32 = bytes(32)
+    okv = (C.c_int * 1)()
+    args = lambda n_norm: (ctx.h, bp.ARG_NL, 1, N, 0, k, L.point_to_bytes(pts[0]), L.points_to_bytes(pts[1:1 + N]), None,
+                           L.int_to_le(2), z32, z32 * N, None, L.int_to_le(9),
+                           L.point_to_bytes(pts[5]) + L.point_to_bytes(pts[6]), n_norm, 0, z32 * n_norm, None, 0, None, None, okv)
+    assert ctx.lib.bppp_nl_verify(*args(3)) == 1
+    assert ctx.lib.bppp_nl_verify(*args(2)) == 0
