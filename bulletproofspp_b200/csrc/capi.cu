@@ -17,17 +17,19 @@
 #include <atomic>
 #include <thread>
 #include "kernels.cuh"
+#include "pippenger.cuh"
 
 using namespace bppp;
 
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
-                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce", "k_check_points"};
+                                                   "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce", "k_check_points",
+                                                   "k_pip_sort", "k_pip_accum", "k_pip_merge", "k_pip_reduce", "k_pip_horner"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -217,13 +219,111 @@ bool check_fq(const uint8_t* b, size_t n) {
     return true;
 }
 
+// ----------------------------------------------------------------------------- size-aware Pippenger (pippenger.cuh)
+struct PipWork {                     // scratch of one call; stream-ordered pool allocations, reused across rounds
+    DBuf<unsigned> off, cur, ent, bsum, heavy;
+    DBuf<u256> dec;
+    DBuf<unsigned char> dsgn;
+    DBuf<Xyzz> bucket, slots, seg;
+    DBuf<Jac> win;
+};
+// window width for n scalars = 2n half-length terms (GLV): a window has about 2n/32 buckets.  Widths whose
+// top window would hold nothing but the carry (c = 4, 8, 16: (W-1)*c = 128) are avoided.
+int pip_window_bits(size_t n) {
+    int l = 0;
+    while (((2 * n) >> l) > 1) l++;
+    int c = l - 4;
+    if (c < 5) c = 5;
+    if (c > 15) c = 15;
+    if (c == 8) c = 9;
+    return c;
+}
+// `batch` x `n_out` MSMs of n terms: bases pts[p*pts_stride + i] (stride 0: shared), canonical scalars
+// sc[p*sc_stride + o*sc_out_stride + i]; Jacobian results in d_res[p*n_out + o].
+int run_msm_pip(bppp_ctx* ctx, PipWork& wk, const Affine* pts, size_t pts_stride, const u256* sc, size_t sc_stride,
+                size_t sc_out_stride, size_t n, size_t batch, int n_out, Jac* d_res, double work_per_proof) {
+    if (n == 0 || batch == 0 || n_out <= 0) FAIL(BPPP_ERR_ARG, "empty MSM");
+    if (n >= ((size_t)1 << 30)) FAIL(BPPP_ERR_ARG, "MSM too long");
+    const int c = pip_window_bits(n), W = (129 + c - 1) / c, NBK = 1 << (c - 1);
+    const int SEG = 1 << std::max(0, (c - 1) / 2 - 2), NS = NBK / SEG;
+    // proofs per pass: bucket ids and entry positions are 32-bit, and the entry list is bounded to 2 GiB
+    const size_t ent_per_proof = (size_t)n_out * 2 * n * W, nt_per_proof = (size_t)n_out * W * NBK;
+    size_t slab = std::min<size_t>(batch, std::max<size_t>(1, ((size_t)1 << 29) / std::max(ent_per_proof, nt_per_proof)));
+    if (std::max(ent_per_proof, nt_per_proof) >= ((size_t)1 << 31)) FAIL(BPPP_ERR_ARG, "MSM too long for one pass");
+    for (size_t p0 = 0; p0 < batch; p0 += slab) {
+        const size_t nb = std::min(slab, batch - p0);
+        PipArgs A;
+        A.pts = pts + p0 * pts_stride; A.pts_stride = pts_stride;
+        A.sc = sc + p0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
+        A.n = (unsigned)n; A.n_out = (unsigned)n_out; A.n_prob = (unsigned)(nb * n_out);
+        A.c = c; A.W = W; A.NBK = NBK; A.NT = (unsigned)(nb * nt_per_proof);
+        A.SEG = SEG; A.NS = NS;
+        const size_t e_max = nb * ent_per_proof;
+        // entries per accumulation thread: enough threads for a few waves on 148 SMs, at least 4 entries each
+        size_t L = e_max / ((size_t)148 * 1024);
+        L = std::min<size_t>(64, std::max<size_t>(4, L));
+        A.L = (int)L;
+        const size_t n_thr = (e_max + L - 1) / L;
+        const unsigned n_scan = (unsigned)(((size_t)A.NT + PIP_SCAN_BLOCK - 1) / PIP_SCAN_BLOCK);
+        const size_t n_seg = (size_t)A.n_prob * W * NS, n_win = (size_t)A.n_prob * W;
+        CK(wk.off.ensure((size_t)A.NT + 1)); CK(wk.cur.ensure(A.NT)); CK(wk.ent.ensure(e_max)); CK(wk.bsum.ensure(n_scan));
+        CK(wk.heavy.ensure((size_t)A.NT + 1));
+        CK(wk.dec.ensure((size_t)A.n_prob * n)); CK(wk.dsgn.ensure((size_t)A.n_prob * n));
+        A.dec = wk.dec.p; A.dsgn = wk.dsgn.p;
+        CK(wk.bucket.ensure(A.NT)); CK(wk.slots.ensure(2 * n_thr)); CK(wk.seg.ensure(2 * n_seg)); CK(wk.win.ensure(n_win));
+        A.off = wk.off.p; A.cur = wk.cur.p; A.ent = wk.ent.p; A.bsum = wk.bsum.p; A.heavy = wk.heavy.p;
+        A.bucket = wk.bucket.p; A.slotF = wk.slots.p; A.slotL = wk.slots.p + n_thr;
+        A.segS = wk.seg.p; A.segT = wk.seg.p + n_seg; A.win = wk.win.p; A.out = d_res + p0 * n_out;
+        CK(cudaMemsetAsync(A.off, 0, ((size_t)A.NT + 1) * sizeof(unsigned), ctx->st));
+        CK(cudaMemsetAsync(A.heavy, 0, sizeof(unsigned), ctx->st));
+        const unsigned g_terms = (unsigned)(((size_t)A.n_prob * n + 255) / 256);
+        {   ProfScope ps_(ctx, K_PIP_SORT, 0);
+            k_pip_glv<<<g_terms, 256, 0, ctx->st>>>(A);
+            k_pip_count<<<g_terms, 256, 0, ctx->st>>>(A);
+            k_pip_scan_blocks<<<n_scan, 256, 0, ctx->st>>>(A);
+            k_pip_scan_top<<<1, 256, 0, ctx->st>>>(A, n_scan);
+            k_pip_scan_apply<<<n_scan, 256, 0, ctx->st>>>(A);
+            k_pip_scatter<<<g_terms, 256, 0, ctx->st>>>(A);
+            ctx->launches += 5;
+        }
+        CK(cudaGetLastError());
+        {   ProfScope ps_(ctx, K_PIP_ACCUM, work_per_proof * (double)nb);
+            k_pip_accum<<<(unsigned)((n_thr + 127) / 128), 128, 0, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+        {   ProfScope ps_(ctx, K_PIP_MERGE, 0);
+            k_pip_merge<<<(A.NT + 127) / 128, 128, 0, ctx->st>>>(A);
+            k_pip_merge_heavy<<<148, PIP_HEAVY_THREADS, 0, ctx->st>>>(A);
+            ctx->launches += 1;
+        }
+        CK(cudaGetLastError());
+        {   ProfScope ps_(ctx, K_PIP_REDUCE, 0);
+            k_pip_reduce1<<<(unsigned)((n_seg + 127) / 128), 128, 0, ctx->st>>>(A);
+            k_pip_reduce2<<<(unsigned)((n_win + 3) / 4), 128, 0, ctx->st>>>(A);
+            ctx->launches += 1;
+        }
+        CK(cudaGetLastError());
+        {   ProfScope ps_(ctx, K_PIP_HORNER, 0);
+            k_pip_horner<<<(A.n_prob + 31) / 32, 32, 0, ctx->st>>>(A);
+        }
+        CK(cudaGetLastError());
+    }
+    return BPPP_OK;
+}
+
 // ----------------------------------------------------------------------------- MSM driver
 struct MsmPlan {
     std::vector<MsmSlice> slices;
     DBuf<MsmSlice> d_slices;
     DBuf<Jac> d_partial;
     size_t smem = 0;
+    PipWork pip;
+    MsmSlice whole;                   // the undivided MSM (one add() per plan), for the size-aware path
+    size_t whole_n = 0;
     void add(const Affine* pts, size_t pts_stride, const u256* sc, size_t sc_stride, size_t sc_out_stride, size_t n) {
+        whole.pts = pts; whole.pts_stride = pts_stride; whole.sc = sc; whole.sc_stride = sc_stride;
+        whole.sc_out_stride = sc_out_stride; whole.n = 0;
+        whole_n = n;
         for (size_t off = 0; off < n; off += MSM_MAX_CHUNK) {
             MsmSlice s;
             s.pts = pts + off; s.pts_stride = pts_stride;
@@ -243,6 +343,11 @@ bool g_attr_set = false;
 int run_msm(bppp_ctx* ctx, MsmPlan& plan, size_t batch, int n_out, Jac* d_res, double work_per_proof = 0) {
     int nch = (int)plan.slices.size();
     if (nch == 0) FAIL(BPPP_ERR_ARG, "empty MSM");
+    // Few long MSMs (one large argument, bppp_msm): the size-aware global-memory Pippenger.  Many short ones
+    // (a batch of small proofs, <= 2048 terms each): one CTA per MSM with shared-memory bucket lists below.
+    if (nch > 1 || batch * (size_t)n_out <= 16)
+        return run_msm_pip(ctx, plan.pip, plan.whole.pts, plan.whole.pts_stride, plan.whole.sc, plan.whole.sc_stride,
+                           plan.whole.sc_out_stride, plan.whole_n, batch, n_out, d_res, work_per_proof);
     int max_n = 0;
     for (auto& s : plan.slices) max_n = std::max(max_n, s.n);
     CK(plan.d_slices.ensure(nch));
@@ -720,9 +825,14 @@ struct bppp_gens {
     bppp_ctx* ctx;
     size_t N, M, P0;
     DBuf<Affine> base;               // [g | G | H]
-    DBuf<Affine> tbl;                // [P0][GT_W]
+    DBuf<Affine> tbl;                // [P0][GT_W]; empty for long lists (P0 > GT_TABLE_MAX_TERMS)
     std::vector<uint8_t> host;       // P0 * 64 bytes (for the bucket-kernel fallback paths)
+    PipWork pip;                     // scratch of the size-aware MSM over `base` (long lists)
 };
+// The window table pays off for batches of short proofs (29 table points per generator, no doublings,
+// one bucket reduction per MSM).  For a long list the size-aware Pippenger over the bare generators needs
+// FEWER additions (16 windows of 16 bits at n = 2^20 against 29 of 9 bits) and no 1.9 GB table.
+#define GT_TABLE_MAX_TERMS 8192
 namespace {
 size_t gt_smem_bytes(int n) { return (size_t)(2 * GT_KEYS + 1) * 4 + (size_t)n * GT_W * 2 + 16; }
 
@@ -731,25 +841,30 @@ size_t gt_smem_bytes(int n) { return (size_t)(2 * GT_KEYS + 1) * 4 + (size_t)n *
 int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride, size_t sc_out_stride, size_t batch,
                  int n_out, Jac* d_out, double work_per_proof) {
     bppp_ctx* ctx = g->ctx;
+    if (!g->tbl.p)
+        return run_msm_pip(ctx, g->pip, g->base.p, 0, sc, sc_stride, sc_out_stride, n_terms, batch, n_out, d_out, work_per_proof);
     static bool attr = false;
     if (!attr) {
         CK(cudaFuncSetAttribute(k_msm_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bytes(GT_MAX_CHUNK)));
         CK(cudaFuncSetAttribute(k_msm_gens, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         attr = true;
     }
-    int nch = (int)((n_terms + GT_MAX_CHUNK - 1) / GT_MAX_CHUNK);
+    // terms per CTA: 2048 for batches; a lone proof is cut finer so that more SMs share its (latency-bound) work
+    size_t chunk_terms = GT_MAX_CHUNK;
+    if (batch * (size_t)n_out <= 8) chunk_terms = std::min<size_t>(GT_MAX_CHUNK, std::max<size_t>(128, (n_terms + 31) / 32));
+    int nch = (int)((n_terms + chunk_terms - 1) / chunk_terms);
     size_t ctas = batch * n_out * nch;
     DBuf<unsigned char> scratch;     // stream-ordered pool allocations: cheap, and safe across lanes
     DBuf<Jac> partsbuf;
     CK(scratch.alloc(ctas * GT_SCRATCH_BYTES(GT_THREADS)));
     Jac* parts = d_out;
     if (nch > 1) { CK(partsbuf.alloc(ctas)); parts = partsbuf.p; }
-    int max_n = (int)std::min<size_t>(GT_MAX_CHUNK, n_terms);
+    int max_n = (int)std::min<size_t>(chunk_terms, n_terms);
     for (size_t b0 = 0; b0 < batch; b0 += 32768) {
         size_t nb = std::min<size_t>(32768, batch - b0);
         GtArgs A;
         A.tbl = g->tbl.p; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
-        A.n_total = (int)n_terms; A.term0 = 0; A.chunk_terms = GT_MAX_CHUNK;
+        A.n_total = (int)n_terms; A.term0 = 0; A.chunk_terms = (int)chunk_terms;
         A.scratch = scratch.p + b0 * n_out * nch * GT_SCRATCH_BYTES(GT_THREADS);
         A.out = parts + b0 * n_out * nch; A.out_pstride = (size_t)n_out * nch; A.n_out = n_out; A.n_chunks = nch;
         g_work = work_per_proof * (double)nb;
@@ -814,6 +929,52 @@ int run_msm_groups(bppp_gens* g, const u256* sc, size_t sc_stride, size_t batch,
 }
 }  // namespace
 
+namespace {
+// the resident list [g | G | H] (+ window table when it is short enough) from host bytes, or from a
+// device array `d_src` of 1 + N + M affine points that is already in list order
+int gens_create_impl(bppp_ctx* ctx, size_t N, size_t M, const uint8_t* g, const uint8_t* G, const uint8_t* H,
+                     const Affine* d_src, bppp_gens** out) {
+    bppp_gens* gg = new bppp_gens();
+    gg->ctx = ctx; gg->N = N; gg->M = M; gg->P0 = 1 + N + M;
+    if (!d_src) {
+        gg->host.resize(gg->P0 * 64);
+        memcpy(&gg->host[0], g, 64);
+        if (N) memcpy(&gg->host[64], G, N * 64);
+        if (M) memcpy(&gg->host[64 * (1 + N)], H, M * 64);
+    }
+    DBuf<Jac> tj;
+    cudaError_t e;
+    const bool with_table = gg->P0 <= GT_TABLE_MAX_TERMS;
+    size_t total = with_table ? gg->P0 * GT_W : 0;
+    if ((e = gg->base.alloc(gg->P0)) || (with_table && ((e = gg->tbl.alloc(total)) || (e = tj.alloc(total))))) {
+        delete gg;
+        ctx->err = cudaGetErrorString(e);
+        return BPPP_ERR_CUDA;
+    }
+    if (d_src) {
+        if ((e = cudaMemcpyAsync(gg->base.p, d_src, gg->P0 * 64, cudaMemcpyDeviceToDevice, ctx->st)) != cudaSuccess) {
+            delete gg;
+            ctx->err = cudaGetErrorString(e);
+            return BPPP_ERR_CUDA;
+        }
+    } else {
+        H2D(gg->base.p, gg->host.data(), gg->P0 * 64);
+        int rc0 = check_points_sync(ctx, gg->base.p, gg->P0, "bppp_gens_create");
+        if (rc0) { delete gg; return rc0; }
+    }
+    int rc = BPPP_OK;
+    if (with_table) {
+        { ProfScope ps_(ctx, K_GT_BUILD, 0);
+        k_gt_build<<<(unsigned)((gg->P0 + 63) / 64), 64, 0, ctx->st>>>(gg->base.p, gg->P0, tj.p);
+        }
+        rc = to_affine(ctx, tj.p, total, gg->tbl.p, total, 0, (int)std::min<size_t>(total, 0x7fffffff), total);
+    }
+    if (rc == 0 && (e = ctx_sync(ctx)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
+    if (rc) { delete gg; return rc; }
+    *out = gg;
+    return BPPP_OK;
+}
+}  // namespace
 extern "C" int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t* g, const uint8_t* G, const uint8_t* H,
                                 bppp_gens** out) {
     if (!ctx) return BPPP_ERR_ARG;
@@ -821,30 +982,7 @@ extern "C" int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t
     *out = nullptr;
     ENTER(ctx);
     if (!check_fq(g, 2) || !check_fq(G, 2 * N) || !check_fq(H, 2 * M)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
-    bppp_gens* gg = new bppp_gens();
-    gg->ctx = ctx; gg->N = N; gg->M = M; gg->P0 = 1 + N + M;
-    gg->host.resize(gg->P0 * 64);
-    memcpy(&gg->host[0], g, 64);
-    if (N) memcpy(&gg->host[64], G, N * 64);
-    if (M) memcpy(&gg->host[64 * (1 + N)], H, M * 64);
-    DBuf<Jac> tj;
-    cudaError_t e;
-    size_t total = gg->P0 * GT_W;
-    if ((e = gg->base.alloc(gg->P0)) || (e = gg->tbl.alloc(total)) || (e = tj.alloc(total))) {
-        delete gg;
-        ctx->err = cudaGetErrorString(e);
-        return BPPP_ERR_CUDA;
-    }
-    H2D(gg->base.p, gg->host.data(), gg->P0 * 64);
-    { int rc0 = check_points_sync(ctx, gg->base.p, gg->P0, "bppp_gens_create"); if (rc0) { delete gg; return rc0; } }
-    { ProfScope ps_(ctx, K_GT_BUILD, 0);
-    k_gt_build<<<(unsigned)((gg->P0 + 63) / 64), 64, 0, ctx->st>>>(gg->base.p, gg->P0, tj.p);
-    }
-    int rc = to_affine(ctx, tj.p, total, gg->tbl.p, total, 0, (int)std::min<size_t>(total, 0x7fffffff), total);
-    if (rc == 0 && (e = ctx_sync(ctx)) != cudaSuccess) { ctx->err = cudaGetErrorString(e); rc = BPPP_ERR_CUDA; }
-    if (rc) { delete gg; return rc; }
-    *out = gg;
-    return BPPP_OK;
+    return gens_create_impl(ctx, N, M, g, G, H, nullptr, out);
 }
 extern "C" void bppp_gens_destroy(bppp_gens* g) {
     if (!g) return;
@@ -896,8 +1034,16 @@ struct bppp_nl {
     MsmPlan plan;
     int blocks_n = 1, blocks_l = 1;
     size_t shard_lo = 0;            // index of this handle's first norm element inside the whole (sharded) vector
-    // tensor mode: no generator folding; per-generator fold coefficients + folded opening scalars
+    // tensor mode: no generator folding; per-generator fold coefficients + folded opening scalars.
+    // The "original" generators of tensor mode are the list `tgens` of tN + tM (+ g) points: the shared
+    // list of the handle, or -- after a single large argument has folded down to a few thousand
+    // generators -- a table built over ITS current generators (nl_rebase_tensor); tround counts the rounds
+    // since then.
     bool tensor = false;
+    bppp_gens* tgens = nullptr;
+    bppp_gens* tail_gens = nullptr;     // owned: the re-based list
+    size_t tN = 0, tM = 0, tP0 = 0;
+    int tround = 0;
     DBuf<u256> coef, fsc;           // coef [B][N+M] (Montgomery); fsc [2][B][P0] (Montgomery)
     // IP argument (kind = BPPP_ARG_IP): w[] holds a (on G' = g1 + r g0), bv[] holds b (on H' = g1 - r g0);
     // Np = ceil(N/2) pairs; coef = [coefG (Np) | coefH (Np) | coefK (M)] per proof;
@@ -1267,10 +1413,12 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
         FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     bppp_nl* h = new bppp_nl();
     h->ctx = ctx; h->gens = gens; h->own_gens = own; h->kind = kind;
+    h->tgens = gens; h->tN = N; h->tM = M; h->tP0 = 1 + N + M; h->tround = 0;
     h->B = batch; h->N = N; h->M = M; h->curN = N; h->curM = M;
     h->N2 = (N + 1) / 2; h->M2 = (M + 1) / 2; h->P0 = 1 + N + M; h->P2 = 1 + h->N2 + h->M2;
     auto fail = [&](int rc) { h->own_gens = false; bppp_nl_destroy(h); return rc; };
     if (kind == BPPP_ARG_IP) {
+        if (!gens->tbl.p) { ctx->err = "IP argument: the generator list is too long for the window table"; return fail(BPPP_ERR_ARG); }
         int rc = ip_create(h, q, s, w, l, c);
         if (rc) return fail(rc);
         *out = h;
@@ -1281,7 +1429,8 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
         const char* ev = getenv("BPPP_ROUND_MODE");          // fold | tensor | auto (default)
         if (ev && !strcmp(ev, "fold")) h->tensor = false;
         else if (ev && !strcmp(ev, "tensor")) h->tensor = true;
-        else h->tensor = (h->P0 <= 8192);                     // few rounds: k fixed-base MSMs beat fold + bucket MSMs
+        else h->tensor = (h->P0 <= GT_TABLE_MAX_TERMS);       // few rounds: k fixed-base MSMs beat fold + bucket MSMs
+        if (!gens->tbl.p) h->tensor = false;                  // tensor mode needs the window table
     }
     if (h->tensor) {
         CKH(h->coef.alloc(batch * (N + M)));
@@ -1571,6 +1720,7 @@ extern "C" void bppp_nl_destroy(bppp_nl* h) {
     cudaSetDevice(h->ctx->dev);
     cudaStreamSynchronize(h->ctx->st);
     if (h->own_gens) bppp_gens_destroy(h->gens);
+    if (h->tail_gens) bppp_gens_destroy(h->tail_gens);
     delete h;
 }
 
@@ -1597,10 +1747,10 @@ extern "C" int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* poi
         // tensor mode keeps fold coefficients instead of folded generators: materialise
         // G^(r)_i = sum_{idx >> r == i} coef_idx * G_idx with fixed-base MSMs (meant for the few
         // elements left when a sharded argument is gathered)
-        const size_t P0 = h->P0, NO = cn + cl, NM = h->N + h->M;
+        const size_t P0 = h->tP0, NO = cn + cl, NM = h->tN + h->tM;
         if (B * NO * P0 > ((size_t)1 << 26)) FAIL(BPPP_ERR_ARG, "bppp_nl_export: state too large to materialise in tensor mode");
         std::vector<Fr> hc(B * NM);
-        if (h->round > 0) {
+        if (h->tround > 0) {
             CK(D2H(hc.data(), h->coef.p, B * NM * 32));
             CK(ctx_sync(ctx));
         } else {
@@ -1609,9 +1759,9 @@ extern "C" int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* poi
         std::vector<u256> sc(B * NO * P0, u256_zero());
         for (size_t b = 0; b < B; b++)
             for (size_t idx = 0; idx < NM; idx++) {
-                const bool lin = idx >= h->N;
-                const size_t local = lin ? idx - h->N : idx;
-                const size_t j = (local >> h->round) + (lin ? cn : 0);
+                const bool lin = idx >= h->tN;
+                const size_t local = lin ? idx - h->tN : idx;
+                const size_t j = (local >> h->tround) + (lin ? cn : 0);
                 sc[(b * NO + j) * P0 + 1 + idx] = fr_canon_u256(hc[b * NM + idx]);
             }
         DBuf<u256> d_sc;
@@ -1619,7 +1769,7 @@ extern "C" int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* poi
         DBuf<Affine> d_aff;
         CK(d_sc.alloc(sc.size())); CK(d_res.alloc(B * NO)); CK(d_aff.alloc(B * NO));
         CK(H2D(d_sc.p, sc.data(), sc.size() * 32));
-        int rc = run_msm_gens(h->gens, P0, d_sc.p, P0, 0, B * NO, 1, d_res.p, 0);
+        int rc = run_msm_gens(h->tgens, P0, d_sc.p, P0, 0, B * NO, 1, d_res.p, 0);
         if (rc) return rc;
         if ((rc = to_affine(ctx, d_res.p, 1, d_aff.p, 1, 0, 1, B * NO))) return rc;
         CK(D2H(points, d_aff.p, B * NO * 64));
@@ -1690,7 +1840,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     if ((rc = upload_consts(h, C_K1, k1))) return rc;
     if ((rc = upload_consts(h, C_K2, k2))) return rc;
     CK(H2D(cptr(h, C_COEF), coef.data(), B * 8 * 32));
-    const size_t P0 = h->P0;
+    const size_t P0 = h->tensor ? h->tP0 : h->P0;               // row length of the MSM scalar vectors
     u256* xs = h->sc.p;
     u256* rs = h->sc.p + B * P0;
     {
@@ -1706,7 +1856,7 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         CK(cudaGetLastError());
     }
     const int src = h->cur;
-    const bool expand = h->tensor && h->round > 0;              // folded scalars go through the coefficient vector
+    const bool expand = h->tensor && h->tround > 0;             // folded scalars go through the coefficient vector
     u256* fxs = expand ? h->fsc.p : xs;
     u256* frs = expand ? h->fsc.p + B * P0 : rs;
     if (h->curN) {
@@ -1733,13 +1883,13 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     }
     if (expand) {
         for (int seg = 0; seg < 2; seg++) {
-            const size_t n0 = seg ? h->M : h->N;
+            const size_t n0 = seg ? h->tM : h->tN;
             if (!n0) continue;
             ExpandArgs A;
             A.fx = fxs; A.fr_ = frs; A.f_stride = P0; A.f_off = seg ? 1 + (int)h->curN : 1;
-            A.coef = h->coef.p; A.coef_stride = h->N + h->M; A.coef_off = seg ? (int)h->N : 0;
-            A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = seg ? 1 + (int)h->N : 1;
-            A.n = (int)n0; A.shift = h->round;
+            A.coef = h->coef.p; A.coef_stride = h->tN + h->tM; A.coef_off = seg ? (int)h->tN : 0;
+            A.xs = xs; A.rs = rs; A.sc_stride = P0; A.off = seg ? 1 + (int)h->tN : 1;
+            A.n = (int)n0; A.shift = h->tround;
             { ProfScope ps_(ctx, K_EXPAND, 0);
             k_expand_scalars<<<dim3((unsigned)((n0 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
             }
@@ -1755,8 +1905,8 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     double work = msm_alg_imads(nX) + msm_alg_imads(nR);
     if (h->tensor && h->round > 0) work += fold_alg_imads((double)(h->curN + h->curM));
     if (h->curp < 0 || h->tensor) {
-        // the generators are the shared list -> fixed-base tables
-        if ((rc = run_msm_gens(h->gens, nterms, xs, P0, B * P0, B, 2, h->res.p, work))) return rc;
+        // the generators are the shared list (or the re-based one) -> fixed-base tables
+        if ((rc = run_msm_gens(h->tensor ? h->tgens : h->gens, nterms, xs, P0, B * P0, B, 2, h->res.p, work))) return rc;
     } else {
         h->plan.slices.clear();
         h->plan.add(h->pts[h->curp].p, h->P2, xs, P0, B * P0, nterms);
@@ -1792,7 +1942,7 @@ size_t hybrid_limit() {
 // small fixed-base MSM per block of 2^r original generators) and continue in fold mode.
 int nl_switch_to_fold(bppp_nl* h) {
     bppp_ctx* ctx = h->ctx;
-    const size_t B = h->B, N = h->N, M = h->M, P0 = h->P0, cn = h->curN, cl = h->curM, group = (size_t)1 << h->round;
+    const size_t B = h->B, N = h->tN, M = h->tM, P0 = h->tP0, cn = h->curN, cl = h->curM, group = (size_t)1 << h->tround;
     CK(h->pts[0].ensure(B * h->P2)); CK(h->pts[1].ensure(B * h->P2));
     CK(h->jscratch.ensure(B * (h->N2 + h->M2)));
     u256* sc = h->sc.p;                                   // free between rounds: canonical coefficients in scalar-row layout
@@ -1806,8 +1956,8 @@ int nl_switch_to_fold(bppp_nl* h) {
         CK(cudaGetLastError());
     }
     int rc;
-    if ((rc = run_msm_groups(h->gens, sc, P0, B, 1, N, group, h->jscratch.p, cn + cl))) return rc;
-    if ((rc = run_msm_groups(h->gens, sc, P0, B, 1 + N, M, group, h->jscratch.p + cn, cn + cl))) return rc;
+    if ((rc = run_msm_groups(h->tgens, sc, P0, B, 1, N, group, h->jscratch.p, cn + cl))) return rc;
+    if ((rc = run_msm_groups(h->tgens, sc, P0, B, 1 + N, M, group, h->jscratch.p + cn, cn + cl))) return rc;
     if ((rc = to_affine(ctx, h->jscratch.p, cn + cl, h->pts[0].p, h->P2, 1, (int)(cn + cl), B * (cn + cl)))) return rc;
     for (int k = 0; k < 2; k++) {
         { ProfScope ps_(ctx, K_BCAST, 0);
@@ -1817,6 +1967,35 @@ int nl_switch_to_fold(bppp_nl* h) {
     }
     h->tensor = false;
     h->curp = 0;
+    return BPPP_OK;
+}
+}  // namespace
+
+namespace {
+// A single large argument is latency-bound once a few thousand generators are left: a fold-mode round
+// then costs a 129-doubling chain per folded generator (k_pair_fold) plus a 128-doubling Horner per
+// commitment, whatever the length.  At that point the CURRENT generators become the base list of a
+// tensor-mode argument: one window table is built over them (252 doublings per point, all points in
+// parallel, once), and every remaining round is two fixed-base MSMs with no doublings and no generator
+// folds at all.  BPPP_REBASE_MAX=n moves the switch (default GT_TABLE_MAX_TERMS, 0 = never); results
+// are bit-identical (tests).
+size_t rebase_limit() {
+    const char* ev = getenv("BPPP_REBASE_MAX");
+    size_t v = ev ? (size_t)atoll(ev) : (size_t)GT_TABLE_MAX_TERMS;
+    return std::min<size_t>(v, GT_TABLE_MAX_TERMS);
+}
+int nl_rebase_tensor(bppp_nl* h) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, cn = h->curN, cl = h->curM;
+    bppp_gens* tg = nullptr;
+    // pts[curp] = [g | G^(k) (cn) | H^(k) (cl)] of the one proof: exactly a generator list
+    int rc = gens_create_impl(ctx, cn, cl, nullptr, nullptr, nullptr, h->pts[h->curp].p, &tg);
+    if (rc) return rc;
+    h->tail_gens = tg; h->tgens = tg;
+    h->tN = cn; h->tM = cl; h->tP0 = 1 + cn + cl; h->tround = 0;
+    CK(h->coef.ensure(B * (cn + cl)));
+    CK(h->fsc.ensure(2 * B * h->tP0));
+    h->tensor = true;
     return BPPP_OK;
 }
 }  // namespace
@@ -1884,12 +2063,12 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
             (rc = upload_consts(h, C_B0L, b0l)))
             return rc;
         for (int seg = 0; seg < 2; seg++) {
-            const size_t n0 = seg ? h->M : h->N;
+            const size_t n0 = seg ? h->tM : h->tN;
             if (!n0) continue;
             { ProfScope ps_(ctx, K_COEF, 0);
             k_coef_update<<<dim3((unsigned)((n0 + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(
-                h->coef.p, h->N + h->M, seg ? (int)h->N : 0, (int)n0, h->round, cptr(h, seg ? C_A0L : C_A0N),
-                cptr(h, seg ? C_B0L : C_B0N), 1, h->round == 0);
+                h->coef.p, h->tN + h->tM, seg ? (int)h->tN : 0, (int)n0, h->tround, cptr(h, seg ? C_A0L : C_A0N),
+                cptr(h, seg ? C_B0L : C_B0N), 1, h->tround == 0);
             }
             CK(cudaGetLastError());
         }
@@ -1897,7 +2076,8 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
         h->curN = nN;
         h->curM = nM;
         h->round++;
-        if (hybrid_limit() && !h->shard_lo && nN + nM <= hybrid_limit() && nN + nM >= 12 && h->round <= 9 && (rc = nl_switch_to_fold(h)))
+        h->tround++;
+        if (hybrid_limit() && !h->tail_gens && !h->shard_lo && nN + nM <= hybrid_limit() && nN + nM >= 12 && h->round <= 9 && (rc = nl_switch_to_fold(h)))
             return rc;
         CK(ctx_sync(ctx));
         return BPPP_OK;
@@ -1920,6 +2100,7 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     h->curM = nM;
     h->round++;
     CK(ctx_sync(ctx));   // host vectors above go out of scope
+    if (B == 1 && !h->tail_gens && 1 + nN + nM <= rebase_limit() && nN + nM >= 16) return nl_rebase_tensor(h);
     return BPPP_OK;
 }
 

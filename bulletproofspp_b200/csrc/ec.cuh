@@ -55,23 +55,26 @@ BP_HD Jac jac_neg(const Jac& p) {
     return r;
 }
 
-// dbl-2009-l (a = 0): 2M + 5S
-BP_HD Jac jac_dbl(const Jac& p) {
+// dbl-2009-l (a = 0): 2M + 5S.  F = FqCall (multiplications as calls: throughput kernels) or FqInl
+// (inlined: latency-bound chains, see fp.cuh)
+template <class F>
+BP_HD Jac jac_dbl_t(const Jac& p) {
     if (jac_is_inf(p)) return p;
-    u256 A = fq::sqr(p.X);
-    u256 B = fq::sqr(p.Y);
-    u256 C = fq::sqr(B);
+    u256 A = F::sqr(p.X);
+    u256 B = F::sqr(p.Y);
+    u256 C = F::sqr(B);
     u256 t = fq::add(p.X, B);
-    u256 D = fq::dbl(fq::sub(fq::sub(fq::sqr(t), A), C));
+    u256 D = fq::dbl(fq::sub(fq::sub(F::sqr(t), A), C));
     u256 E = fq::add(fq::dbl(A), A);
-    u256 F = fq::sqr(E);
+    u256 Fs = F::sqr(E);
     Jac r;
-    r.X = fq::sub(F, fq::dbl(D));
+    r.X = fq::sub(Fs, fq::dbl(D));
     u256 C8 = fq::dbl(fq::dbl(fq::dbl(C)));
-    r.Y = fq::sub(fq::mul(E, fq::sub(D, r.X)), C8);
-    r.Z = fq::dbl(fq::mul(p.Y, p.Z));
+    r.Y = fq::sub(F::mul(E, fq::sub(D, r.X)), C8);
+    r.Z = fq::dbl(F::mul(p.Y, p.Z));
     return r;
 }
+BP_HD Jac jac_dbl(const Jac& p) { return jac_dbl_t<FqCall>(p); }
 
 // Jacobian + affine, complete: 8M + 3S
 BP_HD Jac jac_madd(const Jac& p, const Affine& q) {
@@ -97,30 +100,32 @@ BP_HD Jac jac_madd(const Jac& p, const Affine& q) {
 }
 
 // Jacobian + Jacobian, complete: 12M + 4S
-BP_HD Jac jac_add(const Jac& p, const Jac& q) {
+template <class F>
+BP_HD Jac jac_add_t(const Jac& p, const Jac& q) {
     if (jac_is_inf(p)) return q;
     if (jac_is_inf(q)) return p;
-    u256 Z1Z1 = fq::sqr(p.Z);
-    u256 Z2Z2 = fq::sqr(q.Z);
-    u256 U1 = fq::mul(p.X, Z2Z2);
-    u256 U2 = fq::mul(q.X, Z1Z1);
-    u256 S1 = fq::mul(fq::mul(p.Y, q.Z), Z2Z2);
-    u256 S2 = fq::mul(fq::mul(q.Y, p.Z), Z1Z1);
+    u256 Z1Z1 = F::sqr(p.Z);
+    u256 Z2Z2 = F::sqr(q.Z);
+    u256 U1 = F::mul(p.X, Z2Z2);
+    u256 U2 = F::mul(q.X, Z1Z1);
+    u256 S1 = F::mul(F::mul(p.Y, q.Z), Z2Z2);
+    u256 S2 = F::mul(F::mul(q.Y, p.Z), Z1Z1);
     u256 H = fq::sub(U2, U1);
     u256 r = fq::sub(S2, S1);
     if (u256_is_zero(H)) {
-        if (u256_is_zero(r)) return jac_dbl(p);
+        if (u256_is_zero(r)) return jac_dbl_t<FqCall>(p);
         return jac_inf();
     }
-    u256 HH = fq::sqr(H);
-    u256 HHH = fq::mul(H, HH);
-    u256 V = fq::mul(U1, HH);
+    u256 HH = F::sqr(H);
+    u256 HHH = F::mul(H, HH);
+    u256 V = F::mul(U1, HH);
     Jac o;
-    o.X = fq::sub(fq::sub(fq::sqr(r), HHH), fq::dbl(V));
-    o.Y = fq::sub(fq::mul(r, fq::sub(V, o.X)), fq::mul(S1, HHH));
-    o.Z = fq::mul(fq::mul(p.Z, q.Z), H);
+    o.X = fq::sub(fq::sub(F::sqr(r), HHH), fq::dbl(V));
+    o.Y = fq::sub(F::mul(r, fq::sub(V, o.X)), F::mul(S1, HHH));
+    o.Z = F::mul(F::mul(p.Z, q.Z), H);
     return o;
 }
+BP_HD Jac jac_add(const Jac& p, const Jac& q) { return jac_add_t<FqCall>(p, q); }
 
 // ---------------------------------------------------------------- XYZZ coordinates
 // (X, Y, ZZ, ZZZ) with x = X/ZZ, y = Y/ZZZ, ZZ^3 = ZZZ^2; identity: ZZ = 0.  The mixed addition is
@@ -150,17 +155,19 @@ BP_HD Xyzz xyzz_dbl_aff(const Affine& q) {           // 2 * (affine point), neve
     r.ZZZ = W;
     return r;
 }
-BP_HD Xyzz xyzz_dbl(const Xyzz& p) {
+template <class F>
+BP_HD Xyzz xyzz_dbl_t(const Xyzz& p) {
     if (xyzz_is_inf(p)) return p;
-    u256 U = fq::dbl(p.Y), V = fq::sqr(U), W = fq::mul(U, V), S = fq::mul(p.X, V);
-    u256 x2 = fq::sqr(p.X), M = fq::add(fq::dbl(x2), x2);
+    u256 U = fq::dbl(p.Y), V = F::sqr(U), W = F::mul(U, V), S = F::mul(p.X, V);
+    u256 x2 = F::sqr(p.X), M = fq::add(fq::dbl(x2), x2);
     Xyzz r;
-    r.X = fq::sub(fq::sqr(M), fq::dbl(S));
-    r.Y = fq::sub(fq::mul(M, fq::sub(S, r.X)), fq::mul(W, p.Y));
-    r.ZZ = fq::mul(V, p.ZZ);
-    r.ZZZ = fq::mul(W, p.ZZZ);
+    r.X = fq::sub(F::sqr(M), fq::dbl(S));
+    r.Y = fq::sub(F::mul(M, fq::sub(S, r.X)), F::mul(W, p.Y));
+    r.ZZ = F::mul(V, p.ZZ);
+    r.ZZZ = F::mul(W, p.ZZZ);
     return r;
 }
+BP_HD Xyzz xyzz_dbl(const Xyzz& p) { return xyzz_dbl_t<FqCall>(p); }
 // XYZZ + affine, complete: 8M + 2S
 BP_HD Xyzz xyzz_madd(const Xyzz& p, const Affine& q) {
     if (aff_is_inf(q)) return p;
@@ -188,27 +195,29 @@ BP_HD Xyzz xyzz_madd(const Xyzz& p, const Affine& q) {
     return o;
 }
 // XYZZ + XYZZ, complete: 12M + 2S
-BP_HD Xyzz xyzz_add(const Xyzz& p, const Xyzz& q) {
+template <class F>
+BP_HD Xyzz xyzz_add_t(const Xyzz& p, const Xyzz& q) {
     if (xyzz_is_inf(p)) return q;
     if (xyzz_is_inf(q)) return p;
-    u256 U1 = fq::mul(p.X, q.ZZ), U2 = fq::mul(q.X, p.ZZ);
-    u256 S1 = fq::mul(p.Y, q.ZZZ), S2 = fq::mul(q.Y, p.ZZZ);
+    u256 U1 = F::mul(p.X, q.ZZ), U2 = F::mul(q.X, p.ZZ);
+    u256 S1 = F::mul(p.Y, q.ZZZ), S2 = F::mul(q.Y, p.ZZZ);
     u256 P = fq::sub(U2, U1);
     u256 R = fq::sub(S2, S1);
     if (u256_is_zero(P)) {
-        if (u256_is_zero(R)) return xyzz_dbl(p);
+        if (u256_is_zero(R)) return xyzz_dbl_t<FqCall>(p);
         return xyzz_inf();
     }
-    u256 PP = fq::sqr(P);
-    u256 PPP = fq::mul(P, PP);
-    u256 Q = fq::mul(U1, PP);
+    u256 PP = F::sqr(P);
+    u256 PPP = F::mul(P, PP);
+    u256 Q = F::mul(U1, PP);
     Xyzz o;
-    o.X = fq::sub(fq::sub(fq::sqr(R), PPP), fq::dbl(Q));
-    o.Y = fq::sub(fq::mul(R, fq::sub(Q, o.X)), fq::mul(S1, PPP));
-    o.ZZ = fq::mul(fq::mul(p.ZZ, q.ZZ), PP);
-    o.ZZZ = fq::mul(fq::mul(p.ZZZ, q.ZZZ), PPP);
+    o.X = fq::sub(fq::sub(F::sqr(R), PPP), fq::dbl(Q));
+    o.Y = fq::sub(F::mul(R, fq::sub(Q, o.X)), F::mul(S1, PPP));
+    o.ZZ = F::mul(F::mul(p.ZZ, q.ZZ), PP);
+    o.ZZZ = F::mul(F::mul(p.ZZZ, q.ZZZ), PPP);
     return o;
 }
+BP_HD Xyzz xyzz_add(const Xyzz& p, const Xyzz& q) { return xyzz_add_t<FqCall>(p, q); }
 // the same point in Jacobian form with Z = ZZ*ZZZ  (X/ZZ = X ZZ ZZZ^2 / Z^2,  Y/ZZZ = Y ZZ^3 ZZZ^2 / Z^3): 5M + 2S
 BP_HD Jac xyzz_to_jac(const Xyzz& p) {
     if (xyzz_is_inf(p)) return jac_inf();

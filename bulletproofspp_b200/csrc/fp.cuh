@@ -395,6 +395,25 @@ BP_HD u256 sqr(const u256& a) {
 #endif
 }
 #endif
+// Always-inlined product / square for the few LATENCY-bound kernels (one thread walking a chain of
+// dependent group operations: the Horner of a single large MSM, bucket-reduction running sums): inlined,
+// the independent multiplications of one group operation interleave their carry chains in the pipeline,
+// where a sequence of calls runs them back to back.  Throughput kernels keep the calls (code size).
+#if defined(__CUDA_ARCH__)
+BP_D u256 mul_inl(const u256& a, const u256& b) {
+    uint32_t t[16];
+    mul_wide_dev(t, a, b);
+    return reduce512(t);
+}
+BP_D u256 sqr_inl(const u256& a) {
+    uint32_t t[16];
+    sqr_wide_dev(t, a);
+    return reduce512(t);
+}
+#else
+BP_HD u256 mul_inl(const u256& a, const u256& b) { return mul(a, b); }
+BP_HD u256 sqr_inl(const u256& a) { return sqr(a); }
+#endif
 BP_HD u256 mul_small(const u256& a, uint32_t k) {   // k < 2^16
     uint64_t c = 0;
     u256 r;
@@ -437,6 +456,15 @@ BP_HD u256 inv(const u256& a) {
     return t;
 }
 }  // namespace fq
+// field-multiplication policies for the group law templates of ec.cuh
+struct FqCall {
+    static BP_HD u256 mul(const u256& a, const u256& b) { return fq::mul(a, b); }
+    static BP_HD u256 sqr(const u256& a) { return fq::sqr(a); }
+};
+struct FqInl {
+    static BP_HD u256 mul(const u256& a, const u256& b) { return fq::mul_inl(a, b); }
+    static BP_HD u256 sqr(const u256& a) { return fq::sqr_inl(a); }
+};
 
 // ============================================================================ Fr
 namespace fr {

@@ -2058,6 +2058,65 @@ int run_lanes(bppp_rp* s, size_t batch, F fn) {
 }  // namespace
 extern "C" {
 
+// proveBPM (src/Bulletproof.hs:357-359) over a device-resident argument: `rounds` times
+//   (X, R) <- the two commitments; e <- head <$> oracle [X, R] (Bulletproof.hs:351); collapse e
+// with the reference's Fiat-Shamir transcript (shaOracle over the commitment list, app/Main.hs:75-80,
+// src/ZKP.hs:96-101) kept on the host.  init_pts = [batch][n_init] commitments already in the transcript,
+// NEWEST FIRST (e.g. the range-proof commitments, or the initial commitment of a bare argument).
+// responses = [batch][rounds][2] points and es = [batch][rounds] challenges (may be NULL), newest first.
+int bppp_nl_prove(bppp_nl* h, size_t batch, int show_format, size_t n_init, const uint8_t* init_pts, size_t rounds,
+                  uint8_t* responses, uint8_t* es) {
+    if (!h || !responses || batch == 0 || (n_init && !init_pts)) return BPPP_ERR_ARG;
+    std::vector<tr::Zkpt> zk(batch);
+    std::vector<uint8_t> X(batch * 64), R(batch * 64), E(batch * 32);
+    for (size_t b = 0; b < batch; b++) {
+        zk[b].fmt = show_format;
+        zk[b].no_random = true;
+        if (n_init) zk[b].absorb(init_pts + 64 * b * n_init, n_init);
+    }
+    for (size_t r = 0; r < rounds; r++) {
+        int rc = bppp_nl_round_commit(h, X.data(), R.data());
+        if (rc) return rc;
+        parallel_for((batch + 1) / 2, [&](size_t pi) {                  // two transcripts per task (two-stream SHA)
+            const size_t b0 = 2 * pi, nb = std::min<size_t>(2, batch - b0);
+            uint8_t xr[2][128];
+            Fr e[2];
+            for (size_t j = 0; j < nb; j++) {
+                memcpy(xr[j], &X[64 * (b0 + j)], 64);
+                memcpy(xr[j] + 64, &R[64 * (b0 + j)], 64);
+            }
+            if (nb == 2) tr::Zkpt::oracle_pair(zk[b0], xr[0], zk[b0 + 1], xr[1], 2, &e[0], &e[1]);
+            else zk[b0].oracle(xr[0], 2, &e[0], 1);
+            for (size_t j = 0; j < nb; j++) {
+                h64::to_bytes(&E[32 * (b0 + j)], e[j]);
+                memcpy(responses + 128 * ((b0 + j) * rounds + (rounds - 1 - r)), xr[j], 128);
+                if (es) h64::to_bytes(es + 32 * ((b0 + j) * rounds + (rounds - 1 - r)), e[j]);
+            }
+        });
+        rc = bppp_nl_round_fold(h, E.data());
+        if (rc) return rc;
+    }
+    return BPPP_OK;
+}
+// The verifier's half of the same transcript (verifyBPM, src/Bulletproof.hs:370-378): the challenges of
+// `rounds` responses (newest first), es = [batch][rounds] newest first.
+int bppp_nl_challenges(size_t batch, int show_format, size_t n_init, const uint8_t* init_pts, size_t rounds,
+                       const uint8_t* responses, uint8_t* es) {
+    if (!es || batch == 0 || (n_init && !init_pts) || (rounds && !responses)) return BPPP_ERR_ARG;
+    parallel_for(batch, [&](size_t b) {
+        tr::Zkpt zk;
+        zk.fmt = show_format;
+        zk.no_random = true;
+        if (n_init) zk.absorb(init_pts + 64 * b * n_init, n_init);
+        std::vector<const uint8_t*> rp(rounds);
+        std::vector<Fr> e(rounds);
+        for (size_t r = 0; r < rounds; r++) rp[r] = responses + 128 * (b * rounds + (rounds - 1 - r));   // oldest round sits last
+        zk.oracle_rounds(rp.data(), rounds, e.data());
+        for (size_t r = 0; r < rounds; r++) h64::to_bytes(es + 32 * (b * rounds + (rounds - 1 - r)), e[r]);
+    });
+    return BPPP_OK;
+}
+
 int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
                         const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals) {
     if (!s) return BPPP_ERR_ARG;

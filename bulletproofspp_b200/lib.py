@@ -21,6 +21,7 @@ EXPORTS = [
     "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
     "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free", "bppp_nl_set_shard", "bppp_nl_export", "bppp_rp_encoded_sizes", "bppp_rp_encode_batch", "bppp_rp_decode_batch",
+    "bppp_nl_prove", "bppp_nl_challenges",
     "bppp_trrp_create", "bppp_trrp_destroy", "bppp_trrp_phase1", "bppp_trrp_phase2", "bppp_trrp_phase3", "bppp_trrp_commit_bl",
     "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
 ]
@@ -114,6 +115,8 @@ def load_library():
     lib.bppp_host_oracle.argtypes = [u8p, sz, ip, ip, u8p]
     lib.bppp_host_fr.argtypes = [ip, u8p, u8p, u8p]
     lib.bppp_host_get_points.argtypes = [C.c_char_p, sz, ip, u8p]
+    lib.bppp_nl_prove.argtypes = [vp, sz, ip, sz, u8p, sz, u8p, u8p]
+    lib.bppp_nl_challenges.argtypes = [sz, ip, sz, u8p, sz, u8p, u8p]
     lib.bppp_tune_process.argtypes = [ip]
     # this harness drives dedicated batch-proving processes (tests, bench.py): opt in to the process-wide
     # tuning (malloc arenas, blocking-sync device flags, pool pre-growth); BPPP_NO_TUNE=1 leaves the process alone

@@ -124,6 +124,15 @@ int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R);
 /* the rest of proveRoundM (src/Bulletproof.hs:351-355): s' = s + e0*sX + e1*sR and `collapse e`
  * (NormArgument.hs:64-71,123-129 / InnerProductArgument.hs:86-101,155-170) with challenge e[b]. */
 int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e);
+/* proveBPM (src/Bulletproof.hs:357-359): all `rounds` rounds on a device-resident argument with the
+ * reference's Fiat-Shamir transcript on the host (e <- head <$> oracle [X, R], Bulletproof.hs:351; shaOracle,
+ * app/Main.hs:75-80).  init_pts = [batch][n_init] commitments already in the transcript, newest first.
+ * Outputs newest first: responses [batch][rounds][2] points, es [batch][rounds] challenges (may be NULL). */
+int bppp_nl_prove(bppp_nl* h, size_t batch, int show_format, size_t n_init, const uint8_t* init_pts, size_t rounds,
+                  uint8_t* responses, uint8_t* es);
+/* the verifier's half of that transcript (verifyBPM, src/Bulletproof.hs:370-378): es from the responses */
+int bppp_nl_challenges(size_t batch, int show_format, size_t n_init, const uint8_t* init_pts, size_t rounds,
+                       const uint8_t* responses, uint8_t* es);
 /* sharding one large argument: this handle holds the slice of the norm vector that
  * starts at `first_element`; bppp_nl_export hands the stored-form state to the rank that finishes */
 int bppp_nl_set_shard(bppp_nl* h, size_t first_element);

@@ -314,3 +314,104 @@ def test_non_canonical_inputs_are_rejected(ctx, gens):
         ctx.msm_batch([[1, R]], pts[:2])
     # the context is still usable afterwards
     assert ctx.msm([(2, pts[2])]) == G.add(pts[2], pts[2])
+
+
+def _ref_group():
+    """the reference's own Straus / pair-fold loops in C when the oracle library is built, else pure Python"""
+    from oracle.curve import SecpRef
+    try:
+        SecpRef.lib()
+        return SecpRef
+    except RuntimeError:
+        return G
+
+
+@pytest.mark.parametrize("n,kind", [(2500, "uniform"), (20000, "uniform"), (20000, "equal"), (20000, "small"),
+                                    (9000, "halfzero"), (33000, "top")])
+def test_size_aware_pippenger_matches_oracle(ctx, gens, n, kind):
+    """bppp_msm over more terms than one shared-memory chunk -> the global-memory Pippenger (pippenger.cuh):
+    uniform scalars, and the skewed cases its balancing must survive (one repeated scalar, digits < 256,
+    half of the scalars zero like an R opening, scalars >= 2^255 that take the r - s branch)."""
+    base = gens(64)
+    Gr = _ref_group()
+    # bases: multiples of a few generators are expensive in Python; reuse 64 generators cyclically with
+    # different scalars (repeated points in one bucket exercise the doubling branch of the mixed addition)
+    pts = [base[i % 64] for i in range(n)]
+    if kind == "uniform":
+        sc = [H("pip", n, i) % R for i in range(n)]
+    elif kind == "equal":
+        sc = [H("pip-equal") % R] * n
+    elif kind == "small":
+        sc = [H("pip-small", i) % 256 for i in range(n)]
+    elif kind == "halfzero":
+        sc = [0 if i % 2 == 0 else H("pip-hz", i) % R for i in range(n)]
+    else:
+        sc = [R - 1 - (H("pip-top", i) % (2 ** 200)) for i in range(n)]
+    # collapse to 64 distinct bases for the oracle: sum_i s_i P_(i mod 64) = sum_j (sum s_i) P_j
+    agg = [0] * 64
+    for i, s in enumerate(sc):
+        agg[i % 64] = (agg[i % 64] + s) % R
+    assert ctx.msm(list(zip(sc, pts))) == Gr.msm(list(zip(agg, base)))
+
+
+@pytest.mark.parametrize("e,N", [(13, 8193), (16, 65536)])
+def test_large_argument_rounds_match_oracle_c_loops(ctx, e, N):
+    """One large norm argument in fold mode (P0 > 8192: no window table, size-aware Pippenger for every
+    round's X / R, k_pair_fold for the generators): rounds 1-3 against the oracle running the reference's
+    own loops in C (256-row Straus innerProduct, 129-row projectivePairIP), then prove -> verify of the whole
+    argument on the device.  N = 8193 is odd at every round; N = 2^16 is the VERDICT r1 size."""
+    import bulletproofspp_b200 as bp
+    from bulletproofspp_b200 import lib as L
+    M = 6
+    k = 0
+    n = N
+    while n >= 5:                                   # NormArgument.hs:165-178 for M = 6: rounds until (<= 4, 1)
+        n = (n + 1) // 2
+        k += 1
+    Gr = _ref_group()
+    # generators: hash-derived multiples of the base point made on the device (fixed-base kernel), checked on the curve
+    import ctypes as C
+    fb = C.c_void_p()
+    ctx._ck(ctx.lib.bppp_fb_create(ctx.h, 1, L.point_to_bytes(G.gen), C.byref(fb)), "bppp_fb_create")
+    P0 = 1 + N + M
+    gsc = b"".join(L.int_to_le(H("gen", e, i) % R) for i in range(P0))
+    out = C.create_string_buffer(64 * P0)
+    ctx._ck(ctx.lib.bppp_fb_msm_batch(fb, P0, gsc, out), "bppp_fb_msm_batch")
+    ctx.lib.bppp_fb_destroy(fb)
+    pts = L.bytes_to_points(out.raw[:64 * P0])
+    assert all(G.on_curve(p) for p in pts[:50])
+    q = H("q", e) % R
+    w = [H("w", e, i) % R for i in range(N)]
+    l = [H("l", e, i) % R for i in range(M)]
+    c = [H("c", e, i) % R for i in range(M)]
+    q2 = q * q % R
+    acc, wt = 0, q2
+    for x in w:
+        acc = (acc + wt * x % R * x) % R
+        wt = wt * q2 % R
+    s0 = (acc + sum(a * b for a, b in zip(c, l))) % R
+    com = obp.PSV(s0, pts[0], obp.NormLinear.make("NL", Gr, q, c, w, pts[1:1 + N], l, pts[1 + N:]))
+    arg = bp.NormLinearArgument(ctx, bp.ARG_NL, pts[0], pts[1:1 + N], pts[1 + N:], [q], [s0], [w], [l], [c])
+    zk = ZKPT(G)
+    es, xr = [], []
+    for r in range(k):
+        X, Rr = arg.round_commit()
+        if r < 3:
+            tr = []
+            com, _ = obp.prove_round(Gr, zk, com, tr)
+            assert (X[0], Rr[0]) == (tr[0]["X"], tr[0]["R"]), "round %d" % r
+            ev = tr[0]["e"]
+        else:
+            ev = H("e", e, r, X[0], Rr[0]) % R
+        es.insert(0, ev)
+        xr.insert(0, (X[0], Rr[0]))
+        arg.round_fold([ev])
+    s, fw, fl = arg.final()
+    assert (len(fw[0]), len(fl[0])) == (n, 1)
+    arg.close()
+    # verify: initCom = C0 = s0*g + <w,G> + <l,H> with public vector 0
+    C0 = ctx.msm(list(zip([s0] + w + l, pts)))
+    ok = ctx.nl_verify(bp.ARG_NL, pts[0], pts[1:1 + N], pts[1 + N:], [q], [0], [[0] * N], [c], [es], [xr], fw, fl, [[(1, C0)]])
+    assert ok == [True]
+    bad = ctx.nl_verify(bp.ARG_NL, pts[0], pts[1:1 + N], pts[1 + N:], [q], [1], [[0] * N], [c], [es], [xr], fw, fl, [[(1, C0)]])
+    assert bad == [False]

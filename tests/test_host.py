@@ -195,3 +195,41 @@ def test_host_job_scheduler_runs_every_item_once(lib):
     for lanes, jobs, items in [(1, 3, 1), (4, 20, 7), (16, 30, 64), (8, 10, 300), (16, 200, 3)]:
         assert lib.bppp_host_scheduler_selftest(lanes, jobs, items) == 0
     assert lib.bppp_host_scheduler_selftest(0, 1, 1) == -1
+
+
+def test_glv_constants_and_split_of_the_pippenger_kernel():
+    """The endomorphism constants of csrc/pippenger.cuh, parsed from the source, and its scalar split
+    restated with big integers: lambda^3 = 1 (mod r), beta^3 = 1 (mod q), lambda G = (beta Gx, Gy),
+    k = k1 + k2 lambda with |k1|, |k2| < 2^128 for edge values and random scalars."""
+    import random
+    from oracle.curve import Secp256k1 as G
+    from oracle.field import Q, R
+    src = open(os.path.join(ROOT, "bulletproofspp_b200", "csrc", "pippenger.cuh")).read()
+
+    def const(name):
+        m = re.search(r"#define %s glv_const\(([^)]*)\)" % name, src)
+        limbs = [int(x.strip().rstrip("u"), 16) for x in m.group(1).split(",")]
+        return sum(v << (32 * i) for i, v in enumerate(limbs))
+    g1, g2, mb1, b2, lam, beta = (const(n) for n in ("GLV_G1", "GLV_G2", "GLV_MB1", "GLV_B2", "GLV_LAMBDA", "GLV_BETA"))
+    assert pow(lam, 3, R) == 1 and lam != 1 and pow(beta, 3, Q) == 1 and beta != 1
+    assert G.mul(lam, G.gen) == (beta * G.gen[0] % Q, G.gen[1])
+    assert (b2 - mb1 * lam) % R == 0                      # (a1, b1) = (b2, -mb1) is a lattice vector
+    assert g1 == (b2 * (1 << 384) + R // 2) // R and g2 == (mb1 * (1 << 384) + R // 2) // R
+
+    def split(k):                                         # k_pip_glv, statement by statement
+        c1 = (k * g1 + (1 << 383)) >> 384
+        c2 = (k * g2 + (1 << 383)) >> 384
+        t1, t2 = c1 * mb1, c2 * b2
+        assert c1 < 1 << 128 and c2 < 1 << 128 and t1 < 1 << 256 and t2 < 1 << 256
+        neg2, m2 = t1 < t2, abs(t1 - t2)
+        prod = m2 * lam % R
+        k1 = (k + prod) % R if neg2 else (k - prod) % R
+        neg1 = k1 > (R - 1) // 2
+        return (R - k1 if neg1 else k1), neg1, m2, neg2
+    rnd = random.Random(7)
+    ks = [1, 2, R - 1, R - 2, (1 << 128) - 1, 1 << 128, 1 << 255, R // 2, R // 2 + 1, lam, R - lam, 255]
+    ks += [rnd.randrange(R) for _ in range(20000)]
+    for k in ks:
+        m1, s1, m2, s2 = split(k)
+        assert m1 < 1 << 128 and m2 < 1 << 128
+        assert ((-m1 if s1 else m1) + (-m2 if s2 else m2) * lam) % R == k

@@ -71,13 +71,18 @@ def run(ctx, e, M=6, verify=True, profile=True):
         kk = ctx.profile_report()["kernels"] if profile else {}
         return {n: (v["ms"], v["work"]) for n, v in kk.items()}
     t0 = time.time()
+    round_ms = []
     for r in range(k):
+        tc = time.time()
         X, Rr = arg.round_commit_raw()
+        tc = time.time() - tc
         ev = int.from_bytes(hashlib.sha256(X + Rr + bytes([r])).digest(), "big") % R
         es.insert(0, ev)
         xr.insert(0, (L.bytes_to_point(X), L.bytes_to_point(Rr)))
         before = snap() if profile and r < 4 else None
+        tf = time.time()
         arg.round_fold(L.int_to_le(ev))
+        round_ms.append((round(tc * 1e3, 3), round((time.time() - tf) * 1e3, 3)))
         if before is not None:
             after = snap()
             d = {n: (after[n][0] - before.get(n, (0, 0))[0], after[n][1] - before.get(n, (0, 0))[1]) for n in after}
@@ -86,7 +91,7 @@ def run(ctx, e, M=6, verify=True, profile=True):
     t_prove = time.time() - t0
     arg.close()
     out = {"e": e, "N": N, "M": M, "rounds": k, "final": [len(fw[0]), len(fl[0])], "setup_s": round(t_setup, 2),
-           "create_s": round(t_create, 3), "prove_s": round(t_prove, 4)}
+           "create_s": round(t_create, 3), "prove_s": round(t_prove, 4), "round_ms_commit_fold": round_ms}
     if verify:
         # initCom = the commitment C0 itself (public vector 0): C0 = s0*g + <w,G> + <l,H>
         sc = L.int_to_le(s0) + w + l
@@ -132,5 +137,6 @@ def run(ctx, e, M=6, verify=True, profile=True):
 
 if __name__ == "__main__":
     ctx = bp.Context(0)
+    prof = not os.environ.get("SWEEP_NOPROFILE")
     for e in [int(a) for a in sys.argv[1:]] or [10, 12, 14]:
-        print(json.dumps(run(ctx, e)), flush=True)
+        print(json.dumps(run(ctx, e, profile=prof)), flush=True)
