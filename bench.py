@@ -26,7 +26,6 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "128by64 range proofs proved+verified/sec"
 UNIT = "proofs/s"
@@ -34,7 +33,7 @@ R_ORDER = 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
 
 
 def workload_schema():
-    from example_configs import EXAMPLES
+    from bulletproofspp_b200.workloads import EXAMPLES
     return EXAMPLES["128by64"][0]
 
 
@@ -82,8 +81,7 @@ class ClockSampler:
 def _ref_worker(args, pippenger=False):
     idx, n = args
     sys.path.insert(0, ROOT)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from example_configs import batched
+    from bulletproofspp_b200.workloads import batched
     from oracle.curve import SecpPip, SecpRef
     from oracle.rangeproof import load_schema, load_witness, prove, verify
     from oracle.transcript import ZKPT
@@ -162,8 +160,15 @@ def make_inputs(batch, offset, n_inputs):
     return vals, tys, seeds
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures (profiles/README.md)
-NCU_TRAFFIC_BYTES = {"k_msm_gens": 50440704 + 123794944}
+def ncu_summary():
+    """per-kernel numbers that only a profiler can see (DRAM bytes per launch, pipe-active percentage), read from the
+    summary of the committed `ncu --set full` captures of this same command (profiles/ncu_summary.json; the raw
+    CSVs sit next to it).  bench.py cannot run under ncu itself: a number printed under a profiler is not a bench value."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 def main():
@@ -175,6 +180,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--host-threads", type=int, default=0)
+    ap.add_argument("--sweep-sizes", default="10,14,18,20", help="log2 N of the synthetic norm-argument sweep (N=1 only)")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,6 +260,8 @@ def main():
 
     base = rank * B
     inputs = make_inputs(B, base, n)
+    # the timed `value` leg proves DIFFERENT proofs every step; all of them are staged before the clock starts
+    staged = [make_inputs(B, base + (1000 + k) * world * B, n) for k in range(args.steps)]
     assert run_steps(lambda k: inputs, args.warmup) == B * args.warmup, "a warm-up proof failed to verify"
     # pools, pinned staging buffers and worker threads are sized on demand during the first steps; on a
     # box that just ran something else three steps are sometimes not enough.  Keep warming up (untimed,
@@ -271,7 +280,7 @@ def main():
     ctx.timer_start()
     t0 = time.time()
     cpu0 = os.times()
-    n_ok = run_steps(lambda k: inputs, args.steps)
+    n_ok = run_steps(lambda k: staged[k], args.steps)
     for c in lanes:
         c.sync()
     ms = ctx.timer_stop()
@@ -336,10 +345,15 @@ def main():
     top = max((name for name in kern if kern[name]["work"] > 0 and name != "k_fold_dots"), key=lambda nme: kern[nme]["ms"])
     kt = kern[top]
     ach = kt["work"] / (kt["ms"] * 1e-3) / 1e12
+    ncu = ncu_summary().get(top, {})
     roofline = {"kernel": top, "bound": "imad", "achieved": ach, "peak": imad_wide / 1e12, "unit": "TIMAD/s",
-                "frac": ach / (imad_wide / 1e12), "traffic": NCU_TRAFFIC_BYTES.get(top),
-                "traffic_note": "dram read+write bytes of one 512-proof launch, ncu --set full (profiles/), ~0.3 % of what HBM "
-                                "could move in the launch time: the kernel is integer-pipe bound",
+                "frac": ach / (imad_wide / 1e12), "frac_alg": ach / (imad_wide / 1e12),
+                "frac_pipe": ncu.get("pipe_fmaheavy_active_pct", 0) / 100.0 or None,
+                "traffic": ncu.get("dram_bytes_per_launch"),
+                "traffic_note": "frac / frac_alg = algorithmic IMADs of the reference's schedule per second / peak (measured live, CUDA "
+                                "events); frac_pipe = sm__pipe_fmaheavy_cycles_active and traffic = dram read+write bytes of one launch of "
+                                "this shape, both from the committed ncu --set full capture (%s): a profiler cannot run inside the "
+                                "timed bench" % ncu.get("source", "profiles/ncu_summary.json missing"),
                 "avg_launch_ms": kt["ms"] / kt["launches"], "share_of_gpu_time": shares[top],
                 "note": "integer-pipe bound (no hbm/tensor roofline applies): achieved = algorithmic 32x32->64 IMADs in the "
                         "reference's units (SURVEY 8(d): Pippenger MSMs over each round's CURRENT lengths + the half-length "
@@ -383,6 +397,12 @@ def main():
                              "round sequencing); the Fiat-Shamir transcript stays on the host by design"}}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()
+    if not args.no_sweep and world == 1:
+        # second half of BASELINE.json's metric ("norm-arg fold GB/s") and its config 5: the synthetic norm-argument
+        # sweep, one large argument per size, after the timed regions of the headline metric
+        from bulletproofspp_b200 import sweep
+        vsetup.close(); setup.close(); psetup.close()
+        line["norm_arg_sweep"] = sweep.run(ctx, [int(x) for x in args.sweep_sizes.split(",") if x], imad_wide, hbm_peak)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

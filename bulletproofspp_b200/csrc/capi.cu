@@ -18,18 +18,20 @@
 #include <thread>
 #include "kernels.cuh"
 #include "pippenger.cuh"
+#include "transcript.cuh"
 
 using namespace bppp;
 
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_TR_POINTS, K_TR_RENDER, K_TR_SQUEEZE, K_TR_RANDOM, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
                                                    "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce", "k_check_points",
-                                                   "k_pip_sort", "k_pip_accum", "k_pip_merge", "k_pip_reduce", "k_pip_horner"};
+                                                   "k_pip_sort", "k_pip_accum", "k_pip_merge", "k_pip_reduce", "k_pip_horner",
+                                                   "k_hash_to_curve", "k_tr_render", "k_tr_squeeze", "k_tr_random"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -45,6 +47,7 @@ struct bppp_ctx {
     std::vector<ProfRec> pending;
     std::vector<cudaEvent_t> pool;
     double k_ms[K_COUNT] = {0}, k_work[K_COUNT] = {0};
+    double k_top_ms[K_COUNT] = {0}, k_top_work[K_COUNT] = {0};   // the single launch with the most algorithmic work
     uint64_t k_n[K_COUNT] = {0};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEvent_t sync_ev = nullptr;   // blocking-sync event: waiting host threads sleep whatever the device's schedule flags
@@ -86,6 +89,7 @@ static void prof_collect(bppp_ctx* c) {
         float ms = 0;
         cudaEventElapsedTime(&ms, r.a, r.b);
         c->k_ms[r.id] += ms; c->k_work[r.id] += r.work; c->k_n[r.id]++;
+        if (r.work > c->k_top_work[r.id]) { c->k_top_work[r.id] = r.work; c->k_top_ms[r.id] = ms; }
         c->pool.push_back(r.a); c->pool.push_back(r.b);
     }
     c->pending.clear();
@@ -529,7 +533,7 @@ extern "C" int bppp_profile_reset(bppp_ctx* ctx) {
     if (!ctx) return BPPP_ERR_ARG;
     cudaSetDevice(ctx->dev);
     prof_collect(ctx);
-    for (int i = 0; i < K_COUNT; i++) { ctx->k_ms[i] = 0; ctx->k_work[i] = 0; ctx->k_n[i] = 0; }
+    for (int i = 0; i < K_COUNT; i++) { ctx->k_ms[i] = 0; ctx->k_work[i] = 0; ctx->k_n[i] = 0; ctx->k_top_ms[i] = 0; ctx->k_top_work[i] = 0; }
     ctx->h2d = ctx->d2h = 0;
     return BPPP_OK;
 }
@@ -543,8 +547,9 @@ extern "C" int bppp_profile_report(bppp_ctx* ctx, char* out, size_t cap) {
     char buf[256];
     for (int i = 0; i < K_COUNT; i++) {
         if (!ctx->k_n[i]) continue;
-        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"work\": %.6e}", first ? "" : ", ",
-                 kKernelNames[i], (unsigned long long)ctx->k_n[i], ctx->k_ms[i], ctx->k_work[i]);
+        snprintf(buf, sizeof buf, "%s\"%s\": {\"launches\": %llu, \"ms\": %.6f, \"work\": %.6e, \"top_ms\": %.6f, \"top_work\": %.6e}",
+                 first ? "" : ", ", kKernelNames[i], (unsigned long long)ctx->k_n[i], ctx->k_ms[i], ctx->k_work[i], ctx->k_top_ms[i],
+                 ctx->k_top_work[i]);
         j += buf;
         first = false;
     }
@@ -675,6 +680,156 @@ extern "C" int bppp_msm_batch(bppp_ctx* ctx, size_t batch, size_t n, const uint8
 }
 extern "C" int bppp_msm(bppp_ctx* ctx, size_t n, const uint8_t* scalars, const uint8_t* points, uint8_t out[64]) {
     return bppp_msm_batch(ctx, 1, n, scalars, points, 1, out);
+}
+
+// =============================================================================== generators, transcript (device)
+// getPoints seed (app/Main.hs:68-72) on the device: candidates n = 0, 1, ... are hashed and tested in
+// parallel, the survivors are compacted in order on the host.  Bit-identical to bppp_host_get_points.
+extern "C" int bppp_get_points(bppp_ctx* ctx, const char* seed, size_t count, int root_policy, uint8_t* out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!seed || !out) FAIL(BPPP_ERR_ARG, "bppp_get_points: null argument");
+    const size_t sl = strlen(seed);
+    if (sl > 200) FAIL(BPPP_ERR_ARG, "bppp_get_points: seed too long");
+    ENTER(ctx);
+    DBuf<unsigned char> d_seed;
+    DBuf<Affine> d_cand;
+    CK(d_seed.alloc(sl + 1));
+    CK(H2D(d_seed.p, seed, sl));
+    size_t found = 0;
+    uint64_t n0 = 0;
+    std::vector<Affine> cand;
+    while (found < count) {
+        // about half of the candidates are on the curve
+        const size_t chunk = std::min<size_t>((count - found) * 2 + (count - found) / 8 + 256, (size_t)1 << 22);
+        CK(d_cand.ensure(chunk));
+        cand.resize(chunk);
+        { ProfScope ps_(ctx, K_TR_POINTS, 0);
+        k_hash_to_curve<<<(unsigned)((chunk + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(d_seed.p, (int)sl, n0, chunk, root_policy, d_cand.p);
+        }
+        CK(cudaGetLastError());
+        CK(D2H(cand.data(), d_cand.p, chunk * sizeof(Affine)));
+        CK(ctx_sync(ctx));
+        for (size_t i = 0; i < chunk && found < count; i++)
+            if (!aff_is_inf(cand[i])) memcpy(out + 64 * found++, &cand[i], 64);
+        n0 += chunk;
+    }
+    return BPPP_OK;
+}
+
+// Device transcript of `batch` proofs in lock-step: the commitment list of ZKPT (src/ZKP.hs:68-101)
+// as decimal records in device memory, challenges by SHA-256 on the device (k_tr_squeeze).
+struct bppp_dtr {
+    bppp_ctx* ctx;
+    size_t B, cap;
+    int fmt;
+    size_t n_pts = 0;                   // commitments absorbed so far (per proof)
+    TrCalls calls;
+    DBuf<unsigned char> rec, len;
+    DBuf<u256> chal;
+    DBuf<Affine> stage;
+};
+extern "C" int bppp_dtr_create(bppp_ctx* ctx, size_t batch, size_t max_points, int show_format, bppp_dtr** out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!out || batch == 0 || max_points == 0 || max_points > 60000) FAIL(BPPP_ERR_ARG, "bppp_dtr_create: bad argument");
+    *out = nullptr;
+    ENTER(ctx);
+    bppp_dtr* t = new bppp_dtr();
+    t->ctx = ctx; t->B = batch; t->cap = max_points; t->fmt = show_format;
+    t->calls.n = 0;
+    cudaError_t e;
+    if ((e = t->rec.alloc(batch * max_points * TR_REC_BYTES)) || (e = t->len.alloc(batch * max_points)) || (e = t->chal.alloc(batch * 9))) {
+        delete t;
+        ctx->err = cudaGetErrorString(e);
+        return BPPP_ERR_CUDA;
+    }
+    *out = t;
+    return BPPP_OK;
+}
+extern "C" void bppp_dtr_destroy(bppp_dtr* t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->dev);
+    cudaStreamSynchronize(t->ctx->st);
+    delete t;
+}
+extern "C" int bppp_dtr_reset(bppp_dtr* t) {
+    if (!t) return BPPP_ERR_ARG;
+    t->n_pts = 0;
+    t->calls.n = 0;
+    return BPPP_OK;
+}
+namespace {
+// `oracle xs` part 1 (src/ZKP.hs:96-98): cs' = xs ++ cs, xs = npts points per proof already on the device
+int dtr_absorb_dev(bppp_dtr* t, const Affine* pts, size_t pts_stride, size_t npts) {
+    bppp_ctx* ctx = t->ctx;
+    if (npts == 0) return BPPP_OK;
+    if (t->n_pts + npts > t->cap || t->calls.n >= TR_MAX_CALLS) FAIL(BPPP_ERR_STATE, "device transcript: capacity exceeded");
+    { ProfScope ps_(ctx, K_TR_RENDER, 0);
+    k_tr_render<<<(unsigned)((t->B * npts + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(
+        pts, pts_stride, (int)npts, t->B, t->fmt, t->rec.p, t->len.p, t->cap, t->n_pts);
+    }
+    CK(cudaGetLastError());
+    t->calls.first[t->calls.n] = (unsigned short)t->n_pts;
+    t->calls.npts[t->calls.n] = (unsigned short)npts;
+    t->calls.n++;
+    t->n_pts += npts;
+    return BPPP_OK;
+}
+// part 2 (app/Main.hs:75-80): the first `count` scalars of shaOracle cs', left on the device (canonical, [batch][count])
+int dtr_squeeze_dev(bppp_dtr* t, int count) {
+    bppp_ctx* ctx = t->ctx;
+    if (count < 1 || count > 9) FAIL(BPPP_ERR_ARG, "device transcript: 1..9 challenges per call");
+    const size_t n = t->B * (size_t)count;
+    { ProfScope ps_(ctx, K_TR_SQUEEZE, 0);
+    k_tr_squeeze<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(t->rec.p, t->len.p, t->cap, t->calls, t->B, count,
+                                                                                          (unsigned)t->n_pts, t->chal.p);
+    }
+    CK(cudaGetLastError());
+    return BPPP_OK;
+}
+}  // namespace
+// `oracle xs` for host-resident commitments: pts = [batch][npts] points, out = [batch][count] challenges
+extern "C" int bppp_dtr_oracle(bppp_dtr* t, const uint8_t* pts, size_t npts, int count, uint8_t* out) {
+    if (!t) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = t->ctx;
+    if (!out || (npts && !pts)) FAIL(BPPP_ERR_ARG, "bppp_dtr_oracle: null argument");
+    ENTER(ctx);
+    if (npts) {
+        if (!check_fq(pts, 2 * npts * t->B)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+        CK(t->stage.ensure(t->B * npts));
+        CK(H2D(t->stage.p, pts, t->B * npts * 64));
+        int rc = dtr_absorb_dev(t, t->stage.p, npts, npts);
+        if (rc) return rc;
+    }
+    int rc = dtr_squeeze_dev(t, count);
+    if (rc) return rc;
+    CK(D2H(out, t->chal.p, t->B * (size_t)count * 32));
+    CK(ctx_sync(ctx));
+    return BPPP_OK;
+}
+// `random` (src/ZKP.hs:90-93, app/Main.hs:177): out[b][j] = hash(seed_b <> show (n0 + j)), j < count
+extern "C" int bppp_dev_random(bppp_ctx* ctx, size_t batch, const char* const* seeds, uint64_t n0, size_t count, uint8_t* out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!seeds || !out || batch == 0 || count == 0) FAIL(BPPP_ERR_ARG, "bppp_dev_random: null/empty argument");
+    ENTER(ctx);
+    std::vector<unsigned char> hs(batch * 64, 0), hl(batch);
+    for (size_t b = 0; b < batch; b++) {
+        const size_t l = strlen(seeds[b]);
+        if (l > 40) FAIL(BPPP_ERR_ARG, "bppp_dev_random: seed longer than 40 bytes");
+        memcpy(&hs[64 * b], seeds[b], l);
+        hl[b] = (unsigned char)l;
+    }
+    DBuf<unsigned char> ds, dl;
+    DBuf<u256> d_out;
+    CK(ds.alloc(batch * 64)); CK(dl.alloc(batch)); CK(d_out.alloc(batch * count));
+    CK(H2D(ds.p, hs.data(), batch * 64));
+    CK(H2D(dl.p, hl.data(), batch));
+    { ProfScope ps_(ctx, K_TR_RANDOM, 0);
+    k_tr_random<<<(unsigned)((batch * count + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(ds.p, dl.p, n0, batch, count, d_out.p);
+    }
+    CK(cudaGetLastError());
+    CK(D2H(out, d_out.p, batch * count * 32));
+    CK(ctx_sync(ctx));
+    return BPPP_OK;
 }
 
 // =============================================================================== fixed base
@@ -851,7 +1006,8 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
     }
     // terms per CTA: 2048 for batches; a lone proof is cut finer so that more SMs share its (latency-bound) work
     size_t chunk_terms = GT_MAX_CHUNK;
-    if (batch * (size_t)n_out <= 8) chunk_terms = std::min<size_t>(GT_MAX_CHUNK, std::max<size_t>(128, (n_terms + 31) / 32));
+    const bool lone = batch * (size_t)n_out <= 8;
+    if (lone) chunk_terms = std::min<size_t>(GT_MAX_CHUNK, std::max<size_t>(128, (n_terms + 31) / 32));
     int nch = (int)((n_terms + chunk_terms - 1) / chunk_terms);
     size_t ctas = batch * n_out * nch;
     DBuf<unsigned char> scratch;     // stream-ordered pool allocations: cheap, and safe across lanes
@@ -874,15 +1030,19 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         CK(cudaGetLastError());
         const size_t n_cta = nb * n_out * nch;
         { ProfScope ps_(ctx, K_MSM_REDUCE, 0);
-        k_msm_gens_reduce<<<(unsigned)((n_cta + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH_BYTES(GT_THREADS), A.out, A.out_pstride,
-                                                                           n_out, nch, n_cta);
+        if (lone)
+            k_msm_gens_reduce_lat<<<(unsigned)n_cta, 32, 0, ctx->st>>>(A.scratch, GT_SCRATCH_BYTES(GT_THREADS), A.out, A.out_pstride, n_out, nch, n_cta);
+        else
+            k_msm_gens_reduce<<<(unsigned)((n_cta + 7) / 8), 256, 0, ctx->st>>>(A.scratch, GT_SCRATCH_BYTES(GT_THREADS), A.out, A.out_pstride,
+                                                                               n_out, nch, n_cta);
         }
         CK(cudaGetLastError());
     }
     if (nch > 1) {
         size_t n_msm = batch * n_out;
         { ProfScope ps_(ctx, K_JAC_SUM, 0);
-        k_jac_sum<<<(unsigned)((n_msm + 127) / 128), 128, 0, ctx->st>>>(parts, nch, nullptr, 0, d_out, n_msm);
+        if (lone) k_jac_sum_warp<<<(unsigned)n_msm, 32, 0, ctx->st>>>(parts, nch, d_out, n_msm);
+        else k_jac_sum<<<(unsigned)((n_msm + 127) / 128), 128, 0, ctx->st>>>(parts, nch, nullptr, 0, d_out, n_msm);
         }
         CK(cudaGetLastError());
     }

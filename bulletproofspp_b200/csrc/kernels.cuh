@@ -870,8 +870,9 @@ __global__ void __launch_bounds__(GT_THREADS_SMALL, 8) k_msm_gens_small(GtArgs A
 // Second half of the fixed-base MSM: out = sum_m m * B_m over the 256 bucket sums each k_msm_gens CTA
 // left in its scratch.  One WARP per MSM: 8 buckets per lane by running sums, then a shuffle
 // suffix-scan and a tree.  cta = (p*n_out + o)*n_chunks + chunk as in the first kernel.
-__global__ void __launch_bounds__(256) k_msm_gens_reduce(const unsigned char* __restrict__ scratch, size_t scratch_stride, Jac* __restrict__ out,
-                                                         size_t out_pstride, int n_out, int n_chunks, size_t n_cta) {
+template <class F>
+__device__ __forceinline__ void msm_gens_reduce_body(const unsigned char* __restrict__ scratch, size_t scratch_stride, Jac* __restrict__ out,
+                                                     size_t out_pstride, int n_out, int n_chunks, size_t n_cta) {
     const size_t cta = blockIdx.x * (size_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (cta >= n_cta) return;
     const int tid = threadIdx.x & 31;
@@ -879,29 +880,40 @@ __global__ void __launch_bounds__(256) k_msm_gens_reduce(const unsigned char* __
     Jac S = jac_inf(), Wt = jac_inf();                                     // over this lane's 8 buckets (top down)
 #pragma unroll 1
     for (int k = 7; k >= 0; k--) {
-        S = jac_add(S, ld_jac(bsum + tid * 8 + k));
-        Wt = jac_add(Wt, S);                                               // sum_k (k+1) * B_{8 tid + k}
+        S = jac_add_t<F>(S, ld_jac(bsum + tid * 8 + k));
+        Wt = jac_add_t<F>(Wt, S);                                               // sum_k (k+1) * B_{8 tid + k}
     }
     // total = sum_t (8 t * S_t + Wt_t) = 8 * sum_t t*S_t + sum_t Wt_t ;  sum_t t*S_t = sum_{t>=1} suffix_t
     Jac suf = S;
 #pragma unroll 1
     for (int s2 = 1; s2 < 32; s2 <<= 1) {
         Jac other = shfl_jac(suf, (tid + s2) & 31);
-        if (tid + s2 < 32) suf = jac_add(suf, other);
+        if (tid + s2 < 32) suf = jac_add_t<F>(suf, other);
     }
     Jac acc = (tid == 0) ? jac_inf() : suf;                                // lanes 1..31 hold suffix sums
-    acc = jac_dbl(jac_dbl(jac_dbl(acc)));                                  // * 8
-    acc = jac_add(acc, Wt);
+    acc = jac_dbl_t<F>(jac_dbl_t<F>(jac_dbl_t<F>(acc)));                                  // * 8
+    acc = jac_add_t<F>(acc, Wt);
 #pragma unroll 1
     for (int s2 = 16; s2 >= 1; s2 >>= 1) {
         Jac other = shfl_jac(acc, (tid + s2) & 31);
-        if (tid < s2) acc = jac_add(acc, other);
+        if (tid < s2) acc = jac_add_t<F>(acc, other);
     }
     if (tid == 0) {
         const size_t chunk = cta % (size_t)n_chunks, t = cta / (size_t)n_chunks;
         const size_t o = t % (size_t)n_out, p = t / (size_t)n_out;
         st_jac(out + p * out_pstride + o * (size_t)n_chunks + chunk, acc);
     }
+}
+
+__global__ void __launch_bounds__(256) k_msm_gens_reduce(const unsigned char* __restrict__ scratch, size_t scratch_stride, Jac* __restrict__ out,
+                                                         size_t out_pstride, int n_out, int n_chunks, size_t n_cta) {
+    msm_gens_reduce_body<FqCall>(scratch, scratch_stride, out, out_pstride, n_out, n_chunks, n_cta);
+}
+// the same for a lone proof (a handful of warps on the whole chip): the 30-addition chain is pure latency,
+// so the field multiplications are inlined and the independent ones of an addition overlap
+__global__ void __launch_bounds__(32) k_msm_gens_reduce_lat(const unsigned char* __restrict__ scratch, size_t scratch_stride, Jac* __restrict__ out,
+                                                            size_t out_pstride, int n_out, int n_chunks, size_t n_cta) {
+    msm_gens_reduce_body<FqInl>(scratch, scratch_stride, out, out_pstride, n_out, n_chunks, n_cta);
 }
 
 // out[m] = sum_k a[m*na + k] + sum_k b[m*nb + k]  (chunk partials of the fixed-base kernel plus,
@@ -914,6 +926,21 @@ __global__ void k_jac_sum(const Jac* __restrict__ a, int na, const Jac* __restri
     for (int k = 0; k < na; k++) acc = jac_add(acc, ld_jac(a + m * na + k));
     for (int k = 0; k < nb; k++) acc = jac_add(acc, ld_jac(b + m * nb + k));
     st_jac(out + m, acc);
+}
+
+// the same sum for a lone proof: one warp per MSM, lane k adds partials k, k + 32, ..., then a shuffle tree
+__global__ void __launch_bounds__(32) k_jac_sum_warp(const Jac* __restrict__ a, int na, Jac* __restrict__ out, size_t n_msm) {
+    const size_t m = blockIdx.x;
+    if (m >= n_msm) return;
+    const int lane = threadIdx.x;
+    Jac acc = jac_inf();
+    for (int k = lane; k < na; k += 32) acc = jac_add_t<FqInl>(acc, ld_jac(a + m * na + k));
+#pragma unroll 1
+    for (int s2 = 16; s2 >= 1; s2 >>= 1) {
+        Jac other = shfl_jac(acc, (lane + s2) & 31);
+        if (lane < s2) acc = jac_add_t<FqInl>(acc, other);
+    }
+    if (lane == 0) st_jac(out + m, acc);
 }
 
 // ------------------------------------------------------------------------------------------

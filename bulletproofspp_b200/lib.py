@@ -21,7 +21,8 @@ EXPORTS = [
     "bppp_measure_imad_peak", "bppp_gens_create", "bppp_gens_destroy", "bppp_gens_msm_batch",
     "bppp_set_device_host_threads", "bppp_nl_create_gens", "bppp_nl_verify_gens",
     "bppp_set_thread_host_threads", "bppp_ctx_device", "bppp_rp_contexts", "bppp_pinned_alloc", "bppp_pinned_free", "bppp_nl_set_shard", "bppp_nl_export", "bppp_rp_encoded_sizes", "bppp_rp_encode_batch", "bppp_rp_decode_batch",
-    "bppp_nl_prove", "bppp_nl_challenges",
+    "bppp_nl_prove", "bppp_nl_challenges", "bppp_get_points", "bppp_dtr_create", "bppp_dtr_destroy", "bppp_dtr_reset",
+    "bppp_dtr_oracle", "bppp_dev_random",
     "bppp_trrp_create", "bppp_trrp_destroy", "bppp_trrp_phase1", "bppp_trrp_phase2", "bppp_trrp_phase3", "bppp_trrp_commit_bl",
     "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
 ]
@@ -117,6 +118,13 @@ def load_library():
     lib.bppp_host_get_points.argtypes = [C.c_char_p, sz, ip, u8p]
     lib.bppp_nl_prove.argtypes = [vp, sz, ip, sz, u8p, sz, u8p, u8p]
     lib.bppp_nl_challenges.argtypes = [sz, ip, sz, u8p, sz, u8p, u8p]
+    lib.bppp_get_points.argtypes = [vp, C.c_char_p, sz, ip, u8p]
+    lib.bppp_dtr_create.argtypes = [vp, sz, sz, ip, C.POINTER(vp)]
+    lib.bppp_dtr_destroy.argtypes = [vp]
+    lib.bppp_dtr_destroy.restype = None
+    lib.bppp_dtr_reset.argtypes = [vp]
+    lib.bppp_dtr_oracle.argtypes = [vp, u8p, sz, ip, u8p]
+    lib.bppp_dev_random.argtypes = [vp, sz, C.POINTER(C.c_char_p), C.c_uint64, sz, u8p]
     lib.bppp_tune_process.argtypes = [ip]
     # this harness drives dedicated batch-proving processes (tests, bench.py): opt in to the process-wide
     # tuning (malloc arenas, blocking-sync device flags, pool pre-growth); BPPP_NO_TUNE=1 leaves the process alone
@@ -229,8 +237,8 @@ class Context:
 
     def profile_report(self):
         import json
-        buf = _buf(8192)
-        self._ck(self.lib.bppp_profile_report(self.h, buf, 8192), "bppp_profile_report")
+        buf = _buf(16384)
+        self._ck(self.lib.bppp_profile_report(self.h, buf, 16384), "bppp_profile_report")
         return json.loads(buf.value.decode())
 
     def timer_start(self):

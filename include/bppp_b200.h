@@ -84,6 +84,21 @@ int bppp_ctx_device(bppp_ctx* ctx);
 int bppp_pinned_alloc(size_t bytes, void** out);
 void bppp_pinned_free(void* p);
 
+/* ---- the reference's hash-derived objects on the device ("transcript on device"); bit-identical
+ * to the host transcript (bppp_host_*) and the oracle.
+ * getPoints seed (app/Main.hs:68-72): the first `count` generators, out = count*64 bytes */
+int bppp_get_points(bppp_ctx* ctx, const char* seed, size_t count, int root_policy, uint8_t* out);
+/* ZKPT's commitment list (src/ZKP.hs:68-101) for `batch` proofs in lock-step, at most max_points commitments each */
+typedef struct bppp_dtr bppp_dtr;
+int bppp_dtr_create(bppp_ctx* ctx, size_t batch, size_t max_points, int show_format, bppp_dtr** out);
+void bppp_dtr_destroy(bppp_dtr* t);
+int bppp_dtr_reset(bppp_dtr* t);
+/* `oracle xs` / `oracle'` (src/ZKP.hs:96-101, 60-63; shaOracle app/Main.hs:75-80): prepend pts = [batch][npts]
+ * to every proof's list, then out = [batch][count] = the first `count` (<= 9) scalars of shaOracle */
+int bppp_dtr_oracle(bppp_dtr* t, const uint8_t* pts, size_t npts, int count, uint8_t* out);
+/* `random` (src/ZKP.hs:90-93 with hashToScalar randomSeed . show, app/Main.hs:177): out[b][j] = draw n0 + j of proof b */
+int bppp_dev_random(bppp_ctx* ctx, size_t batch, const char* const* seeds, uint64_t n0, size_t count, uint8_t* out);
+
 /* ---- fixed-base MSMs over a handful of generators shared by every call: the range proofs'
  * input commitments value*g + type*hs0 + blind*hs1 (scalarRPW' / scalarPairRPW' + commitRPW,
  * src/RangeProof/Internal.hs:43-57; app/Main.hs:287-288,315).  Precomputed 8-bit window tables. */

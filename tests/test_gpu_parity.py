@@ -232,31 +232,29 @@ def test_fixed_base_generator_msm(ctx, gens, n):
     assert got == [G.msm(zip(r, pts)) for r in rows]
 
 
-def test_large_argument_fold_mode_rounds_and_verify(ctx, gens):
-    """N = 4096 (+6 linear), fold mode with multi-chunk MSMs: first rounds against the oracle (the
-    reference's own Straus / pair-fold loops in C), then the whole 10-round argument prove -> verify
-    on the device (size-independent property)."""
-    import os
-    import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+def test_sweep_workload_rounds_and_verify(ctx, gens):
+    """The synthetic sweep workload of bench.py (bulletproofspp_b200/sweep.py) at N = 4096 (+6 linear): its
+    generators are getPoints "test points", its scalars SHA256("sweep" || e || tag || index) mod r (SURVEY 8(d));
+    prove -> verify through bppp_nl_prove / bppp_nl_verify_gens, a tampered proof is rejected, and rounds 1..3
+    equal the oracle's (the reference's own Straus / pair-fold loops in C) on the same inputs."""
     import bulletproofspp_b200 as bp
     from bulletproofspp_b200 import lib as L
-    from oracle.curve import SecpRef
-    import sweep
-    out = sweep.run(ctx, 12, profile=False)
-    assert out["verifies"] and out["rounds"] == 10 and out["final"] == [4, 1]
-    # oracle comparison of rounds 1..3 on the same inputs
-    N, M = 4096, 6
+    from bulletproofspp_b200 import sweep, workloads as W
+    from oracle.transcript import hash_to
+    e, N, M = 12, 4096, 6
+    points = W.sweep_generators(ctx, 1 + N + M)
     pts = gens(1 + N + M)
-    q = L.le_to_int(sweep.scalars("q12", 1))
-    w, l, c = (L.bytes_to_ints(sweep.scalars(t + "12", n)) for t, n in (("w", N), ("l", M), ("c", M)))
-    try:
-        SecpRef.lib()
-        Gr = SecpRef
-    except RuntimeError:
-        Gr = G
-    com = obp.PSV(0, pts[0], obp.NormLinear.make("NL", Gr, q, c, w, pts[1:1 + N], l, pts[1 + N:]))
-    arg = bp.NormLinearArgument(ctx, bp.ARG_NL, pts[0], pts[1:1 + N], pts[1 + N:], [q], [0], [w], [l], [c])
+    assert L.bytes_to_points(points) == pts
+    inp = W.sweep_inputs(ctx, e)
+    w, l, c = (L.bytes_to_ints(inp[t]) for t in "wlc")
+    q = L.le_to_int(inp["q"])
+    assert (q, w[0], w[N - 1], l[5], c[0]) == tuple(hash_to(m, R) for m in (b"sweep12q0", b"sweep12w0", b"sweep12w4095", b"sweep12l5", b"sweep12c0"))
+    out = sweep.run_one(ctx, e, points, 8.9e12, 6546.6, reps=1)
+    assert out["verifies"] and out["rejects_tampered"] and out["rounds"] == 10 and out["final"] == [4, 1]
+    assert "msm_prove" in out["rooflines"] and "k_fold_dots" in out["rooflines"]
+    Gr = _ref_group()
+    com = obp.PSV(L.le_to_int(inp["s"]), pts[0], obp.NormLinear.make("NL", Gr, q, c, w, pts[1:1 + N], l, pts[1 + N:]))
+    arg = bp.NormLinearArgument(ctx, bp.ARG_NL, pts[0], pts[1:1 + N], pts[1 + N:], [q], [L.le_to_int(inp["s"])], [w], [l], [c])
     zk = ZKPT(G)
     for r in range(3):
         X, Rr = arg.round_commit()
