@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--sweep-sizes", default="10,14,18,20", help="log2 N of the synthetic norm-argument sweep (N=1 only)")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--transcript", default="device", choices=["device", "host"],
+                    help="where the Fiat-Shamir transcript of the batch prover / verifier runs (bit-identical proofs either way)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -206,6 +208,9 @@ def main():
     setup = bp.RangeProofSetup(ctx, workload_schema())
     vctx = bp.Context(local)
     vsetup = bp.RangeProofSetup(vctx, workload_schema())
+    dev_tr = args.transcript == "device"
+    setup.set_device_transcript(dev_tr)
+    vsetup.set_device_transcript(dev_tr)
     lanes = setup.contexts() + vsetup.contexts()
     B, n = args.batch, setup.n_inputs
     assert (setup.nrm_len, setup.lin_len, setup.rounds) == (1024, 261, 9)
@@ -309,6 +314,7 @@ def main():
     os.environ["BPPP_LANES"] = "1"
     pctx = bp.Context(local)
     psetup = bp.RangeProofSetup(pctx, workload_schema())
+    psetup.set_device_transcript(dev_tr)
     pin = make_inputs(Bp, base, n)
     proof = psetup.prove_batch_raw(Bp, pin[0], pin[1], None, pin[2])            # warm-up (tables, pools)
     pctx.profile_enable(True)
@@ -378,6 +384,8 @@ def main():
                        "batch_per_gpu": B, "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "working set per step (%.0f MB of generators+witness vectors) exceeds the 126 MB L2" % (B * 0.33),
                        "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world), "lanes": len(lanes),
+                       "transcript": "device (SHA-256 + decimal show of the commitments in k_tr_prepend / k_tr_squeeze, challenges "
+                                     "bit-identical to the host transcript; SURVEY 8 f4)" if dev_tr else "host (the reference's arrangement)",
                        "extra_warmup_steps": extra_warmup},
             "e2e": {"value": total / t_e2e, "unit": UNIT, "h2d_bytes_per_step": rep["h2d_bytes"] // args.steps,
                     "d2h_bytes_per_step": rep["d2h_bytes"] // args.steps,
@@ -393,8 +401,8 @@ def main():
             "prove_call_wall_s": prove_wall,
             "host": {"cpu_ms_per_proof": 1e3 * host_cpu_s / (B * args.steps), "cores_busy": host_cpu_s / wall,
                      "cores_available": (os.cpu_count() or 1) / world,
-                     "note": "rank 0's process CPU time over the value leg (transcript hashing, blinders, linear slots, "
-                             "round sequencing); the Fiat-Shamir transcript stays on the host by design"}}
+                     "note": "rank 0's process CPU time over the value leg (blinders, linear slots, round sequencing"
+                             + ("" if dev_tr else ", transcript hashing") + ")"}}
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()
     if not args.no_sweep and world == 1:

@@ -717,15 +717,19 @@ extern "C" int bppp_get_points(bppp_ctx* ctx, const char* seed, size_t count, in
 }
 
 // Device transcript of `batch` proofs in lock-step: the commitment list of ZKPT (src/ZKP.hs:68-101)
-// as decimal records in device memory, challenges by SHA-256 on the device (k_tr_squeeze).
+// rendered in device memory (one right-aligned byte string per proof, k_tr_prepend), challenges by SHA-256 on the
+// device (k_tr_squeeze).  Bit-identical to the host transcript (csrc/host/transcript.hpp).
 struct bppp_dtr {
     bppp_ctx* ctx;
-    size_t B, cap;
+    size_t B, cap;                      // proofs, commitments per proof the store can hold
+    unsigned SC;                        // bytes per proof
     int fmt;
-    size_t n_pts = 0;                   // commitments absorbed so far (per proof)
-    TrCalls calls;
-    DBuf<unsigned char> rec, len;
-    DBuf<u256> chal;
+    int n_calls = 0;                    // absorb calls so far
+    unsigned ncoms[TR_MAX_CALLS + 1];   // commitments per proof after c calls
+    bool fresh = false;                 // start[.][0] initialised on the device
+    DBuf<unsigned char> buf;
+    DBuf<unsigned> start;               // [B][TR_MAX_CALLS + 1]
+    DBuf<u256> chal;                    // [B][TR_MAX_CHAL]
     DBuf<Affine> stage;
 };
 extern "C" int bppp_dtr_create(bppp_ctx* ctx, size_t batch, size_t max_points, int show_format, bppp_dtr** out) {
@@ -735,9 +739,10 @@ extern "C" int bppp_dtr_create(bppp_ctx* ctx, size_t batch, size_t max_points, i
     ENTER(ctx);
     bppp_dtr* t = new bppp_dtr();
     t->ctx = ctx; t->B = batch; t->cap = max_points; t->fmt = show_format;
-    t->calls.n = 0;
+    t->SC = (unsigned)((max_points * TR_PT_BYTES + 63) & ~(size_t)63);
+    t->ncoms[0] = 0;
     cudaError_t e;
-    if ((e = t->rec.alloc(batch * max_points * TR_REC_BYTES)) || (e = t->len.alloc(batch * max_points)) || (e = t->chal.alloc(batch * 9))) {
+    if ((e = t->buf.alloc(batch * (size_t)t->SC + 64)) || (e = t->start.alloc(batch * (TR_MAX_CALLS + 1))) || (e = t->chal.alloc(batch * TR_MAX_CHAL))) {
         delete t;
         ctx->err = cudaGetErrorString(e);
         return BPPP_ERR_CUDA;
@@ -749,12 +754,17 @@ extern "C" void bppp_dtr_destroy(bppp_dtr* t) {
     if (!t) return;
     cudaSetDevice(t->ctx->dev);
     cudaStreamSynchronize(t->ctx->st);
+    g_alloc_stream = t->ctx->st;
     delete t;
+}
+// can this transcript serve `batch` proofs of up to `max_points` commitments in format `show_format`?
+extern "C" int bppp_dtr_fits(bppp_dtr* t, size_t batch, size_t max_points, int show_format) {
+    return t && t->B == batch && t->cap >= max_points && t->fmt == show_format;
 }
 extern "C" int bppp_dtr_reset(bppp_dtr* t) {
     if (!t) return BPPP_ERR_ARG;
-    t->n_pts = 0;
-    t->calls.n = 0;
+    t->n_calls = 0;
+    t->ncoms[0] = 0;
     return BPPP_OK;
 }
 namespace {
@@ -762,31 +772,101 @@ namespace {
 int dtr_absorb_dev(bppp_dtr* t, const Affine* pts, size_t pts_stride, size_t npts) {
     bppp_ctx* ctx = t->ctx;
     if (npts == 0) return BPPP_OK;
-    if (t->n_pts + npts > t->cap || t->calls.n >= TR_MAX_CALLS) FAIL(BPPP_ERR_STATE, "device transcript: capacity exceeded");
+    if (t->ncoms[t->n_calls] + npts > t->cap || t->n_calls >= TR_MAX_CALLS) FAIL(BPPP_ERR_STATE, "device transcript: capacity exceeded");
+    if (!t->fresh) {                    // state 0 of every proof: the empty body at the end of its buffer
+        { ProfScope ps_(ctx, K_TR_RENDER, 0);
+        k_fill_u32_strided<<<(unsigned)((t->B + 127) / 128), 128, 0, ctx->st>>>(t->start.p, TR_MAX_CALLS + 1, t->SC, t->B);
+        }
+        CK(cudaGetLastError());
+        t->fresh = true;
+    }
     { ProfScope ps_(ctx, K_TR_RENDER, 0);
-    k_tr_render<<<(unsigned)((t->B * npts + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(
-        pts, pts_stride, (int)npts, t->B, t->fmt, t->rec.p, t->len.p, t->cap, t->n_pts);
+    k_tr_prepend<<<(unsigned)t->B, TR_PREPEND_THREADS, 0, ctx->st>>>(pts, pts_stride, (int)npts, t->fmt, t->buf.p, t->SC, t->start.p, t->n_calls);
     }
     CK(cudaGetLastError());
-    t->calls.first[t->calls.n] = (unsigned short)t->n_pts;
-    t->calls.npts[t->calls.n] = (unsigned short)npts;
-    t->calls.n++;
-    t->n_pts += npts;
+    t->ncoms[t->n_calls + 1] = t->ncoms[t->n_calls] + (unsigned)npts;
+    t->n_calls++;
     return BPPP_OK;
 }
-// part 2 (app/Main.hs:75-80): the first `count` scalars of shaOracle cs', left on the device (canonical, [batch][count])
-int dtr_squeeze_dev(bppp_dtr* t, int count) {
+// part 2 (app/Main.hs:75-80): challenge j = scalar idx[j] of the transcript after state[j] absorb calls
+// (state 0 = all calls so far); left on the device in t->chal, canonical, [batch][n_chal]
+int dtr_squeeze_dev(bppp_dtr* t, int n_chal, const unsigned char* idx, const unsigned char* state) {
     bppp_ctx* ctx = t->ctx;
-    if (count < 1 || count > 9) FAIL(BPPP_ERR_ARG, "device transcript: 1..9 challenges per call");
-    const size_t n = t->B * (size_t)count;
+    if (n_chal < 1 || n_chal > TR_MAX_CHAL) FAIL(BPPP_ERR_ARG, "device transcript: 1..48 challenges per call");
+    if (!t->fresh) {
+        k_fill_u32_strided<<<(unsigned)((t->B + 127) / 128), 128, 0, ctx->st>>>(t->start.p, TR_MAX_CALLS + 1, t->SC, t->B);
+        CK(cudaGetLastError());
+        t->fresh = true;
+    }
+    TrPlan plan;
+    plan.count = n_chal;
+    for (int j = 0; j < n_chal; j++) {
+        const int stt = state && state[j] ? state[j] : t->n_calls;
+        if (idx[j] < 1 || idx[j] > 9 || stt > t->n_calls) FAIL(BPPP_ERR_ARG, "device transcript: bad challenge plan");
+        plan.idx[j] = idx[j]; plan.state[j] = (unsigned char)stt; plan.ncoms[j] = t->ncoms[stt];
+    }
+    const size_t n = t->B * (size_t)n_chal;
     { ProfScope ps_(ctx, K_TR_SQUEEZE, 0);
-    k_tr_squeeze<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(t->rec.p, t->len.p, t->cap, t->calls, t->B, count,
-                                                                                          (unsigned)t->n_pts, t->chal.p);
+    k_tr_squeeze<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);
     }
     CK(cudaGetLastError());
     return BPPP_OK;
+}
+int dtr_squeeze_first(bppp_dtr* t, int count) {        // scalars 1..count of the current transcript
+    unsigned char idx[9];
+    if (count < 1 || count > 9) { t->ctx->err = "device transcript: 1..9 challenges per oracle call"; return BPPP_ERR_ARG; }
+    for (int j = 0; j < count; j++) idx[j] = (unsigned char)(j + 1);
+    return dtr_squeeze_dev(t, count, idx, nullptr);
 }
 }  // namespace
+// cs' = xs ++ cs without a challenge: pts = [batch] rows of `npts` points, row b at pts + 64 * stride_points * b
+extern "C" int bppp_dtr_absorb(bppp_dtr* t, const uint8_t* pts, size_t stride_points, size_t npts) {
+    if (!t) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = t->ctx;
+    if (!pts || npts == 0 || stride_points < npts) FAIL(BPPP_ERR_ARG, "bppp_dtr_absorb: bad argument");
+    ENTER(ctx);
+    for (size_t b = 0; b < t->B; b++)
+        if (!check_fq(pts + 64 * stride_points * b, 2 * npts)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+    // every call gets its own staging area: the copies of consecutive calls are queued behind each other
+    const size_t off = t->B * (size_t)t->ncoms[t->n_calls];
+    CK(t->stage.ensure(t->B * t->cap));
+    ctx->h2d += t->B * npts * 64;
+    CK(cudaMemcpy2DAsync(t->stage.p + off, npts * 64, pts, stride_points * 64, npts * 64, t->B, cudaMemcpyHostToDevice, ctx->st));
+    return dtr_absorb_dev(t, t->stage.p + off, npts, npts);
+}
+// the rendered commitment list of one proof as the hash sees it (concat of show x <> show y, newest first):
+// for tests that compare the device's `show` byte for byte with the reference's
+extern "C" int bppp_dtr_export(bppp_dtr* t, size_t proof, uint8_t* out, size_t cap, size_t* len) {
+    if (!t) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = t->ctx;
+    if (!out || !len || proof >= t->B) FAIL(BPPP_ERR_ARG, "bppp_dtr_export: bad argument");
+    ENTER(ctx);
+    unsigned st0 = t->SC;
+    if (t->n_calls) {
+        CK(cudaMemcpyAsync(&st0, t->start.p + proof * (TR_MAX_CALLS + 1) + t->n_calls, 4, cudaMemcpyDeviceToHost, ctx->st));
+        CK(ctx_sync(ctx));
+    }
+    if (st0 > t->SC) FAIL(BPPP_ERR_STATE, "bppp_dtr_export: corrupt transcript offset");
+    *len = t->SC - st0;
+    if (*len > cap) FAIL(BPPP_ERR_ARG, "bppp_dtr_export: buffer too small");
+    if (*len) {
+        CK(cudaMemcpyAsync(out, t->buf.p + proof * (size_t)t->SC + st0, *len, cudaMemcpyDeviceToHost, ctx->st));
+        CK(ctx_sync(ctx));
+    }
+    return BPPP_OK;
+}
+// challenges of any earlier stage: out[b][j] = scalar idx[j] after state[j] absorb calls (state NULL / 0: all calls)
+extern "C" int bppp_dtr_squeeze(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out) {
+    if (!t) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = t->ctx;
+    if (!idx || !out) FAIL(BPPP_ERR_ARG, "bppp_dtr_squeeze: null argument");
+    ENTER(ctx);
+    int rc = dtr_squeeze_dev(t, (int)n_chal, idx, state);
+    if (rc) return rc;
+    CK(D2H(out, t->chal.p, t->B * n_chal * 32));
+    CK(ctx_sync(ctx));
+    return BPPP_OK;
+}
 // `oracle xs` for host-resident commitments: pts = [batch][npts] points, out = [batch][count] challenges
 extern "C" int bppp_dtr_oracle(bppp_dtr* t, const uint8_t* pts, size_t npts, int count, uint8_t* out) {
     if (!t) return BPPP_ERR_ARG;
@@ -794,13 +874,10 @@ extern "C" int bppp_dtr_oracle(bppp_dtr* t, const uint8_t* pts, size_t npts, int
     if (!out || (npts && !pts)) FAIL(BPPP_ERR_ARG, "bppp_dtr_oracle: null argument");
     ENTER(ctx);
     if (npts) {
-        if (!check_fq(pts, 2 * npts * t->B)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
-        CK(t->stage.ensure(t->B * npts));
-        CK(H2D(t->stage.p, pts, t->B * npts * 64));
-        int rc = dtr_absorb_dev(t, t->stage.p, npts, npts);
+        int rc = bppp_dtr_absorb(t, pts, npts, npts);
         if (rc) return rc;
     }
-    int rc = dtr_squeeze_dev(t, count);
+    int rc = dtr_squeeze_first(t, count);
     if (rc) return rc;
     CK(D2H(out, t->chal.p, t->B * (size_t)count * 32));
     CK(ctx_sync(ctx));
@@ -824,7 +901,7 @@ extern "C" int bppp_dev_random(bppp_ctx* ctx, size_t batch, const char* const* s
     CK(H2D(ds.p, hs.data(), batch * 64));
     CK(H2D(dl.p, hl.data(), batch));
     { ProfScope ps_(ctx, K_TR_RANDOM, 0);
-    k_tr_random<<<(unsigned)((batch * count + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(ds.p, dl.p, n0, batch, count, d_out.p);
+    k_tr_random<<<(unsigned)((batch * count + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(ds.p, dl.p, n0, nullptr, batch, count, d_out.p, count);
     }
     CK(cudaGetLastError());
     CK(D2H(out, d_out.p, batch * count * 32));
@@ -1194,6 +1271,7 @@ struct bppp_nl {
     MsmPlan plan;
     int blocks_n = 1, blocks_l = 1;
     size_t shard_lo = 0;            // index of this handle's first norm element inside the whole (sharded) vector
+    bppp_dtr* dtr = nullptr;        // not owned: device transcript the round commitments are absorbed into
     // tensor mode: no generator folding; per-generator fold coefficients + folded opening scalars.
     // The "original" generators of tensor mode are the list `tgens` of tN + tM (+ g) points: the shared
     // list of the handle, or -- after a single large argument has folded down to a few thousand
@@ -1686,6 +1764,12 @@ struct bppp_trrp {
     DBuf<Jac> res;
     DBuf<Affine> aff;
     int phase = 0;
+    // device transcript (bppp_trrp_set_transcript): the commitments of every phase are absorbed where they are
+    // produced and the challenges come back with them
+    int tr_fmt = -1;
+    bppp_dtr* tr = nullptr;
+    DBuf<unsigned char> seeds, seed_len;
+    DBuf<unsigned long long> n0s;
 };
 namespace {
 TrrpStatic trrp_static(bppp_trrp* h) {
@@ -1694,8 +1778,11 @@ TrrpStatic trrp_static(bppp_trrp* h) {
     st.n_ent = (int)h->n_ent; st.n_ranges = (int)h->n_ranges; st.n_bases = (int)h->n_bases;
     return st;
 }
-// MSM of `n_msm` scalar rows of length P0 (device resident, canonical) over the lane's generators -> affine, host
-int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double scalar_bits = 256.0) {
+// MSM of `n_msm` scalar rows of length P0 (device resident, canonical) over the lane's generators -> affine, host.
+// With chal_out: the batch's `per` commitments per proof (followed by `n_extra` host-resident ones per proof) are
+// absorbed by the device transcript as ONE oracle call and the first `count` challenges returned, [batch][count].
+int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double scalar_bits = 256.0, uint8_t* chal_out = nullptr,
+                int count = 0, size_t per = 1, const uint8_t* extra = nullptr, size_t n_extra = 0) {
     bppp_ctx* ctx = h->gens->ctx;
     const size_t P0 = h->gens->P0;
     CK(h->res.ensure(n_msm)); CK(h->aff.ensure(n_msm));
@@ -1703,6 +1790,25 @@ int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double
     if (rc) return rc;
     if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, n_msm))) return rc;
     CK(D2H(out, h->aff.p, n_msm * 64));
+    if (chal_out) {
+        bppp_dtr* t = h->tr;
+        if (!t) FAIL(BPPP_ERR_STATE, "device transcript not enabled (bppp_trrp_set_transcript)");
+        const Affine* src = h->aff.p;
+        if (n_extra) {                  // rows [per device points | n_extra host points] staged side by side
+            const size_t row = per + n_extra, off = t->B * (size_t)t->ncoms[t->n_calls];
+            if (t->ncoms[t->n_calls] + row > t->cap) FAIL(BPPP_ERR_STATE, "device transcript: capacity exceeded");
+            CK(t->stage.ensure(t->B * t->cap));
+            Affine* st = t->stage.p + off;
+            CK(cudaMemcpy2DAsync(st, row * 64, h->aff.p, per * 64, per * 64, t->B, cudaMemcpyDeviceToDevice, ctx->st));
+            ctx->h2d += t->B * n_extra * 64;
+            CK(cudaMemcpy2DAsync(st + per, row * 64, extra, n_extra * 64, n_extra * 64, t->B, cudaMemcpyHostToDevice, ctx->st));
+            src = st;
+            per = row;
+        }
+        if ((rc = dtr_absorb_dev(t, src, per, per))) return rc;
+        if ((rc = dtr_squeeze_first(t, count))) return rc;
+        CK(D2H(chal_out, t->chal.p, t->B * (size_t)count * 32));
+    }
     CK(ctx_sync(ctx));
     return BPPP_OK;
 }
@@ -1741,16 +1847,31 @@ extern "C" int bppp_trrp_create(bppp_gens* gens, size_t n_entries, const uint8_t
 extern "C" void bppp_trrp_destroy(bppp_trrp* h) {
     if (!h) return;
     cudaSetDevice(h->gens->ctx->dev);
+    if (h->tr) bppp_dtr_destroy(h->tr);
     g_alloc_stream = h->gens->ctx->st;
     delete h;
 }
 // phase 1 (TypedReciprocal.hs:399-410): scalars of the digit/multiplicity commitments, [batch][2][P0]
 // canonical (dm row, m row), and the committed values [batch][n_ranges]; coms = [batch][2] points
-extern "C" int bppp_trrp_phase1(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, uint8_t* coms) {
+static int trrp_phase1_impl(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, uint8_t* coms,
+                           size_t n_inputs, const uint8_t* n_coms, uint8_t* chal_out) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->gens->ctx;
     if (!sc_dm_m || !amounts || !coms || batch == 0) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase1: null/empty argument");
     ENTER(ctx);
+    if (chal_out) {
+        if (h->tr_fmt < 0) FAIL(BPPP_ERR_STATE, "bppp_trrp_phase1_tr: call bppp_trrp_set_transcript first");
+        if (n_inputs && !n_coms) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase1_tr: null input commitments");
+        for (size_t i = 0; i < 2 * batch * n_inputs; i++)
+            if (!host::fq_is_canonical(host::from_bytes(n_coms + 32 * i))) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
+        const size_t cap = 4 + n_inputs + 2 * 64;              // bl, r, dm, m, inputs, (X, R) of up to 64 rounds
+        if (h->tr && (h->tr->B != batch || h->tr->cap < cap || h->tr->fmt != h->tr_fmt)) { bppp_dtr_destroy(h->tr); h->tr = nullptr; }
+        if (!h->tr) {
+            int rc = bppp_dtr_create(ctx, batch, cap, h->tr_fmt, &h->tr);
+            if (rc) return rc;
+        }
+        bppp_dtr_reset(h->tr);
+    }
     const size_t P0 = h->gens->P0;
     if (!check_fr(sc_dm_m, batch * 2 * P0) || !check_fr(amounts, batch * h->n_ranges)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     h->B = batch;
@@ -1763,13 +1884,30 @@ extern "C" int bppp_trrp_phase1(bppp_trrp* h, size_t batch, const uint8_t* sc_dm
     CK(H2D(h->scA.p, sc_dm_m, batch * 2 * P0 * 32));
     CK(H2D(h->amounts.p, amounts, batch * h->n_ranges * 32));
     h->phase = 1;
-    return trrp_commit(h, h->scA.p, 2 * batch, coms, 16.0);    // digits and multiplicities: short scalars
+    // digits and multiplicities: short scalars.  T3 e x r0 <- oracle' (dmCom : mCom : nComs)  (TypedReciprocal.hs:411)
+    return trrp_commit(h, h->scA.p, 2 * batch, coms, 16.0, chal_out, 3, 2, n_coms, n_inputs);
+}
+extern "C" int bppp_trrp_phase1(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, uint8_t* coms) {
+    return trrp_phase1_impl(h, batch, sc_dm_m, amounts, coms, 0, nullptr, nullptr);
+}
+// The same with the transcript on the device: n_coms = [batch][n_inputs] input commitments (host);
+// chal = [batch][3] (e, x, r0), the first oracle call of proveTRRPM.
+extern "C" int bppp_trrp_phase1_tr(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, size_t n_inputs,
+                                   const uint8_t* n_coms, uint8_t* coms, uint8_t* chal) {
+    if (!chal) return BPPP_ERR_ARG;
+    return trrp_phase1_impl(h, batch, sc_dm_m, amounts, coms, n_inputs, n_coms, chal);
+}
+// show_format >= 0 enables the device transcript of this handle (TR_PREFIXED_P / TR_BARE_DECIMAL), -1 disables it
+extern "C" int bppp_trrp_set_transcript(bppp_trrp* h, int show_format) {
+    if (!h || show_format > 1) return BPPP_ERR_ARG;
+    h->tr_fmt = show_format < 0 ? -1 : show_format;
+    return BPPP_OK;
 }
 // phase 2 (:412-419): chal = [batch][4] (e, 1/e, x, 1/r0); r_sclin = [batch][1 + M] scalar and linear
 // slots of the reciprocal witness with the err7 slot zero; err7_slot indexes the linear part.
 // Out: rcom [batch] points, err7 [batch] scalars.
-extern "C" int bppp_trrp_phase2(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
-                                uint8_t* err7) {
+static int trrp_phase2_impl(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
+                           uint8_t* err7, uint8_t* chal_out) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->gens->ctx;
     if (!chal || !r_sclin || !rcom || !err7 || err7_slot >= h->gens->M) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase2: bad argument");
@@ -1796,20 +1934,51 @@ extern "C" int bppp_trrp_phase2(bppp_trrp* h, const uint8_t* chal, const uint8_t
     CK(cudaGetLastError());
     CK(D2H(err7, h->small.p, B * 32));
     h->phase = 2;
-    return trrp_commit(h, h->scR.p, B, rcom);
+    return trrp_commit(h, h->scR.p, B, rcom, 256.0, chal_out, 3);     // T3 q x' r1 <- oracle' [rCom]  (:420)
+}
+extern "C" int bppp_trrp_phase2(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
+                                uint8_t* err7) {
+    return trrp_phase2_impl(h, chal, r_sclin, err7_slot, rcom, err7, nullptr);
+}
+// with the device transcript: chal_out = [batch][3] (q, x', r1)
+extern "C" int bppp_trrp_phase2_tr(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
+                                   uint8_t* err7, uint8_t* chal_out) {
+    if (!chal_out) return BPPP_ERR_ARG;
+    return trrp_phase2_impl(h, chal, r_sclin, err7_slot, rcom, err7, chal_out);
 }
 // phase 3, first half (:421-433): chal = [batch][2] (q-power base q0, x'); bls_nrm = [batch][N] blinders
 // of the norm part.  Out: errs [batch][6] error terms over the norm entries.
-extern "C" int bppp_trrp_phase3(bppp_trrp* h, const uint8_t* chal, const uint8_t* bls_nrm, uint8_t* errs) {
+static int trrp_phase3_impl(bppp_trrp* h, const uint8_t* chal, const uint8_t* bls_nrm, const char* const* seeds, const uint64_t* n0,
+                           uint8_t* errs) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->gens->ctx;
-    if (!chal || !bls_nrm || !errs) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase3: null argument");
+    if (!chal || (!bls_nrm && (!seeds || !n0)) || !errs) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase3: null argument");
     if (h->phase != 2) FAIL(BPPP_ERR_STATE, "bppp_trrp_phase3: call phase2 first");
     ENTER(ctx);
     const size_t B = h->B, P0 = h->gens->P0, N = h->gens->N;
-    if (!check_fr(chal, B * 2) || !check_fr(bls_nrm, B * N)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    if (!check_fr(chal, B * 2) || (bls_nrm && !check_fr(bls_nrm, B * N))) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     CK(H2D(h->chal3.p, chal, B * 2 * 32));
-    CK(H2D(h->bl.p, bls_nrm, B * N * 32));
+    if (bls_nrm) CK(H2D(h->bl.p, bls_nrm, B * N * 32));
+    else {
+        // blsNrm <- replicateM N random (TypedReciprocal.hs:425, src/ZKP.hs:90-93): hash(seed_b <> show (n0_b + i)) on the device
+        std::vector<unsigned char> hs(B * 64, 0), hl(B);
+        for (size_t b = 0; b < B; b++) {
+            const size_t l = strlen(seeds[b]);
+            if (l > 40) FAIL(BPPP_ERR_ARG, "bppp_trrp_phase3_rnd: seed longer than 40 bytes");
+            memcpy(&hs[64 * b], seeds[b], l);
+            hl[b] = (unsigned char)l;
+        }
+        CK(h->seeds.ensure(B * 64)); CK(h->seed_len.ensure(B)); CK(h->n0s.ensure(B));
+        CK(H2D(h->seeds.p, hs.data(), B * 64));
+        CK(H2D(h->seed_len.p, hl.data(), B));
+        CK(H2D(h->n0s.p, n0, B * 8));
+        { ProfScope ps_(ctx, K_TR_RANDOM, 0);
+        k_tr_random<<<(unsigned)((B * N + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(
+            h->seeds.p, h->seed_len.p, 0, h->n0s.p, B, N, h->bl.p, N);
+        }
+        CK(cudaGetLastError());
+        CK(ctx_sync(ctx));              // the staging vectors above go out of scope
+    }
     TrrpP3Args A;
     A.st = trrp_static(h); A.chal2 = h->chal2.p; A.chal3 = h->chal3.p; A.scA = h->scA.p; A.P0 = P0;
     A.r = h->r.p; A.c = h->c.p; A.bl = h->bl.p; A.xp = h->xp.p; A.vt = h->vt.p; A.errs = h->small.p;
@@ -1822,9 +1991,19 @@ extern "C" int bppp_trrp_phase3(bppp_trrp* h, const uint8_t* chal, const uint8_t
     h->phase = 3;
     return BPPP_OK;
 }
+extern "C" int bppp_trrp_phase3(bppp_trrp* h, const uint8_t* chal, const uint8_t* bls_nrm, uint8_t* errs) {
+    if (!bls_nrm) return BPPP_ERR_ARG;
+    return trrp_phase3_impl(h, chal, bls_nrm, nullptr, nullptr, errs);
+}
+// the same with the N norm blinders drawn on the device: proof b takes `random` values number n0[b] .. n0[b] + N - 1
+// of its randomSeed seeds[b] (at most 40 bytes); the caller advances its random counter by N
+extern "C" int bppp_trrp_phase3_rnd(bppp_trrp* h, const uint8_t* chal, const char* const* seeds, const uint64_t* n0, uint8_t* errs) {
+    if (!seeds || !n0) return BPPP_ERR_ARG;
+    return trrp_phase3_impl(h, chal, nullptr, seeds, n0, errs);
+}
 // phase 3, second half (:434): bl_sclin = [batch][1 + M] scalar and linear slots of the blinding
 // witness (its norm part is the bls_nrm of phase 3).  Out: blcom [batch] points.
-extern "C" int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom) {
+static int trrp_commit_bl_impl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom, uint8_t* chal_out) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->gens->ctx;
     if (!bl_sclin || !blcom) FAIL(BPPP_ERR_ARG, "bppp_trrp_commit_bl: null argument");
@@ -1837,7 +2016,15 @@ extern "C" int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_
     CK(cudaMemcpy2DAsync(h->scBL.p + 1, P0 * 32, h->bl.p, N * 32, N * 32, B, cudaMemcpyDeviceToDevice, ctx->st));
     ctx->h2d += B * (1 + M) * 32;
     h->phase = 4;
-    return trrp_commit(h, h->scBL.p, B, blcom);
+    return trrp_commit(h, h->scBL.p, B, blcom, 256.0, chal_out, 1);   // t <- oracle [blCom]  (:435)
+}
+extern "C" int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom) {
+    return trrp_commit_bl_impl(h, bl_sclin, blcom, nullptr);
+}
+// with the device transcript: chal_out = [batch] (t)
+extern "C" int bppp_trrp_commit_bl_tr(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom, uint8_t* chal_out) {
+    if (!chal_out) return BPPP_ERR_ARG;
+    return trrp_commit_bl_impl(h, bl_sclin, blcom, chal_out);
 }
 // phase 4 (:435-444): chal = [batch][2] (t, 1/q0).  The norm part of the argument witness stays on
 // the device; out: sums [batch][3] = (sum q2_i p_i^2, sum q2_i over digit entries, sum v_i over digit entries)
@@ -1872,7 +2059,9 @@ extern "C" int bppp_nl_create_trrp(bppp_trrp* h, const uint8_t* q, const uint8_t
     *out = nullptr;
     ENTER(ctx);
     h->phase = 0;
-    return nl_create_impl(h->gens, false, BPPP_ARG_NL, h->B, q, s, nullptr, l, c, out, h->w.p);
+    int rc = nl_create_impl(h->gens, false, BPPP_ARG_NL, h->B, q, s, nullptr, l, c, out, h->w.p);
+    if (rc == BPPP_OK && h->tr_fmt >= 0 && h->tr && h->tr->n_calls) (*out)->dtr = h->tr;   // the rounds continue the proof's transcript
+    return rc;
 }
 
 extern "C" void bppp_nl_destroy(bppp_nl* h) {
@@ -1969,11 +2158,12 @@ extern "C" int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin) {
     return BPPP_OK;
 }
 
-extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
+static int nl_round_commit_impl(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
     if (!X || !R) FAIL(BPPP_ERR_ARG, "bppp_nl_round_commit: null output");
     ENTER(ctx);
+    if (E && (!h->dtr || h->kind == BPPP_ARG_IP)) FAIL(BPPP_ERR_STATE, "bppp_nl_round_challenge: no device transcript attached to this argument");
     if (h->kind == BPPP_ARG_IP) return ip_round_commit(h, X, R);
     const size_t B = h->B;
     // per-proof constants of this round (NormArgument.hs:113): rho = q^4, k1 = 2 n^2 q^3, k2 = n^2 q^4
@@ -2077,6 +2267,11 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
     std::vector<Fr> dots(B * 2);
     CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
     CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
+    if (E) {                            // e <- head <$> oracle [X, R]  (src/Bulletproof.hs:351)
+        if ((rc = dtr_absorb_dev(h->dtr, h->aff.p, 2, 2))) return rc;
+        if ((rc = dtr_squeeze_first(h->dtr, 1))) return rc;
+        CK(D2H(E, h->dtr->chal.p, B * 32));
+    }
     CK(ctx_sync(ctx));
     for (size_t b = 0; b < B; b++) {
         memcpy(X + 64 * b, &xr[2 * b], 64);
@@ -2085,6 +2280,13 @@ extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) {
         h->sR[b] = dots[2 * b + 1];
     }
     return BPPP_OK;
+}
+extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) { return nl_round_commit_impl(h, X, R, nullptr); }
+// The commitments of the round and, from the device transcript the argument continues (bppp_nl_create_trrp after
+// bppp_trrp_*_tr), its challenge E = [batch] scalars: proveRoundM's `oracle [X, R]` without a host hash
+extern "C" int bppp_nl_round_challenge(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E) {
+    if (!E) return BPPP_ERR_ARG;
+    return nl_round_commit_impl(h, X, R, E);
 }
 
 namespace {

@@ -338,6 +338,11 @@ struct bppp_rp {
     bppp_trrp* trrp = nullptr;                 // device scalar phases, lane 0 / other lanes
     std::vector<bppp_trrp*> lane_trrp;
     bool dev_phases = false;
+    // Fiat-Shamir transcript on the device (bppp_rp_set_device_transcript / BPPP_DEVICE_TRANSCRIPT=1):
+    // commitments are rendered and hashed where they are produced, the host only reads the challenges.
+    // Needs the device scalar phases; bit-identical to the host transcript (tests).
+    bool dev_transcript = false;
+    std::vector<bppp_dtr*> lane_vtr;           // verifier transcripts, one per lane (created on first use)
     std::mutex err_mu;
     std::string err;
 };
@@ -912,7 +917,7 @@ struct Lane {
     bppp_trrp* trrp = nullptr;                 // device scalar phases (TypedReciprocal + norm-linear argument)
 };
 enum { PB_IN = 0, PB_SC1, PB_SC2, PB_C1, PB_C2, PB_NCOMS, PB_Q, PB_S, PB_W, PB_L, PB_C, PB_X, PB_R, PB_E, PB_V0, PB_V1, PB_V2, PB_V3,
-       PB_V4, PB_V5, PB_V6, PB_V7, PB_V8, PB_CH, PB_SCLIN, PB_BLN, PB_SMALL, PB_COUNT };
+       PB_V4, PB_V5, PB_V6, PB_V7, PB_V8, PB_CH, PB_SCLIN, PB_BLN, PB_SMALL, PB_CHT, PB_COUNT };
 // uninitialised page-locked buffer `slot` of the lane, at least `bytes` long
 uint8_t* lane_buf(bppp_rp* s, const Lane& ln, int slot, size_t bytes) {
     auto& pb = s->pinned[ln.index][slot];
@@ -937,7 +942,8 @@ const char* ctx_err(const Lane& ln) { return bppp_last_error(ln.ctx); }
 // run the argument (proveBPM, src/Bulletproof.hs:357-359) for the whole batch
 int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t rounds, const uint8_t* q, const uint8_t* sc,
                  const uint8_t* w, const uint8_t* l, const uint8_t* c,
-                 uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l, bool device_witness = false) {
+                 uint8_t* responses, uint8_t* finals, size_t fin_n, size_t fin_l, bool device_witness = false,
+                 bool device_transcript = false) {
     const size_t B = P.size();
     bppp_nl* h = nullptr;
     int rc = device_witness ? bppp_nl_create_trrp(ln.trrp, q, sc, l, c, &h) : bppp_nl_create_gens(ln.gens, s->arg, B, q, sc, w, l, c, &h);
@@ -947,9 +953,16 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
     uint8_t* E = lane_buf(s, ln, PB_E, B * 32);
     g_tm.lap("nl_create");
     for (size_t r = 0; r < rounds; r++) {
-        rc = bppp_nl_round_commit(h, X, R);
+        rc = device_transcript ? bppp_nl_round_challenge(h, X, R, E) : bppp_nl_round_commit(h, X, R);
         g_tm.lap("nl_commit");
         if (rc) { bppp_nl_destroy(h); return fail(s, rc, std::string("bppp_nl_round_commit: ") + ctx_err(ln)); }
+        if (device_transcript) {                                    // the challenge came back with the commitments
+            for (size_t b = 0; b < B; b++) {
+                uint8_t* o = responses + 128 * (b * rounds + (rounds - 1 - r));
+                memcpy(o, &X[64 * b], 64);
+                memcpy(o + 64, &R[64 * b], 64);
+            }
+        } else
         parallel_for((B + 1) / 2, [&](size_t pi) {                  // two transcripts per task (two-stream SHA)
             const size_t b0 = 2 * pi, nb = std::min<size_t>(2, B - b0);
             uint8_t xr[2][128];
@@ -1203,13 +1216,25 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
             }
             if (rc2) { bppp_rp_free(s); return rc2; }
             s->dev_phases = true;
+            const char* dv = getenv("BPPP_DEVICE_TRANSCRIPT");
+            s->dev_transcript = dv && atoi(dv);
         }
     }
     *out = s;
     return BPPP_OK;
 }
+// Fiat-Shamir transcript of bppp_rp_prove_batch / bppp_rp_verify_batch on the device (on != 0) or on the host
+// (default; app/Main.hs:75-80, src/ZKP.hs:96-101).  Proofs and verdicts are bit-identical either way.  Only setups
+// that run the device scalar phases (TypedReciprocal over the norm-linear argument) can move it.
+int bppp_rp_set_device_transcript(bppp_rp* s, int on) {
+    if (!s) return BPPP_ERR_ARG;
+    if (on && !s->dev_phases) return fail(s, BPPP_ERR_STATE, "device transcript needs the device scalar phases");
+    s->dev_transcript = on != 0;
+    return BPPP_OK;
+}
 void bppp_rp_free(bppp_rp* s) {
     if (!s) return;
+    for (auto t : s->lane_vtr) bppp_dtr_destroy(t);
     bppp_trrp_destroy(s->trrp);                 // before the generator sets / contexts they refer to
     for (auto t : s->lane_trrp) bppp_trrp_destroy(t);
     bppp_fb_destroy(s->fb);
@@ -1257,7 +1282,9 @@ int bppp_input_blind(const char* random_seed, uint64_t j, uint8_t out[32]) {
 // per-proof constants; reciprocals, error terms, public constants and the combined witness never
 // leave the GPU.
 static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, uint8_t* coms, uint8_t* responses, uint8_t* finals,
-                             const uint8_t* c1, const uint8_t* n_coms) {
+                             const uint8_t* c1, const uint8_t* n_coms, const char* const* random_seeds, uint8_t* cht) {
+    // cht != NULL: device transcript -- the challenges of the last oracle call, [batch][3]
+    const bool dt = cht != nullptr;
     const size_t B = P.size(), n = s->n_inputs, N = s->nrm_len, M = s->lin_len, NC = s->num_rp_coms + n;
     uint8_t* ch = lane_buf(s, ln, PB_CH, B * 4 * 32);
     uint8_t* sclin = lane_buf(s, ln, PB_SCLIN, B * (1 + M) * 32);
@@ -1285,7 +1312,8 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         memcpy(out + 256, &n_coms[64 * b * n], 64 * n);
         Fr chs[3];
         Sect sect;
-        p.zk.oracle(out + 128, 2 + n, chs, 3);                              // T3 e x r0 <- oracle' (dmCom:mCom:nComs)
+        if (dt) for (int i = 0; i < 3; i++) chs[i] = h64::from_bytes(cht + 32 * (3 * b + i));
+        else p.zk.oracle(out + 128, 2 + n, chs, 3);                         // T3 e x r0 <- oracle' (dmCom:mCom:nComs)
         sect.lap(S_ORACLE);
         p.e = chs[0]; p.x = chs[1]; p.r0 = chs[2];
         Fr iv[2] = {p.e, p.r0};
@@ -1301,10 +1329,13 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_SCALARS);
     });
     g_tm.lap("host_phase2");
-    int rc = bppp_trrp_phase2(ln.trrp, ch, sclin, ERR7_SLOT, c2, small);
+    int rc = dt ? bppp_trrp_phase2_tr(ln.trrp, ch, sclin, ERR7_SLOT, c2, small, cht) : bppp_trrp_phase2(ln.trrp, ch, sclin, ERR7_SLOT, c2, small);
     if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(ln));
     g_tm.lap("msm_phase2");
     // ---------------- phase 3
+    bool dev_rnd = dt;
+    for (size_t b = 0; dev_rnd && b < B; b++) dev_rnd = strlen(random_seeds[b]) <= 40;
+    std::vector<uint64_t> rnd_n0(dev_rnd ? B : 0);
     parallel_for(B, [&](size_t b) {
         Proof& p = P[b];
         uint8_t* out = coms + 64 * b * NC;
@@ -1312,7 +1343,8 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         p.r.lin[ERR7_SLOT] = h64::from_bytes(small + 32 * b);
         Fr chs[3];
         Sect sect;
-        p.zk.oracle(out + 64, 1, chs, 3);                                   // T3 q x' r1 <- oracle' [rCom]
+        if (dt) for (int i = 0; i < 3; i++) chs[i] = h64::from_bytes(cht + 32 * (3 * b + i));
+        else p.zk.oracle(out + 64, 1, chs, 3);                              // T3 q x' r1 <- oracle' [rCom]
         sect.lap(S_ORACLE);
         p.q = chs[0]; p.xq = chs[1]; p.r1 = chs[2];
         p.q0 = q0_of(s->arg, p.q);
@@ -1325,7 +1357,8 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_COEFFS);
         p.bls_lin.resize(M > 5 ? M - 5 : 0);
         p.zk.random_fill(p.bls_lin.data(), p.bls_lin.size());
-        p.zk.random_fill_canonical(bln + 32 * b * N, N);
+        if (dev_rnd) { rnd_n0[b] = p.zk.n_random; p.zk.n_random += N; }      // the N norm blinders are drawn on the device
+        else p.zk.random_fill_canonical(bln + 32 * b * N, N);
         sect.lap(S_RANDOM);
         h64::to_bytes(ch + 32 * (2 * b), p.q0); h64::to_bytes(ch + 32 * (2 * b + 1), p.xq);
         std::vector<Fr> ic = input_coeffs_trrp(s, p.x, p.q0);
@@ -1335,7 +1368,7 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_COMBINE);
     });
     g_tm.lap("host_phase3");
-    rc = bppp_trrp_phase3(ln.trrp, ch, bln, small);
+    rc = dev_rnd ? bppp_trrp_phase3_rnd(ln.trrp, ch, random_seeds, rnd_n0.data(), small) : bppp_trrp_phase3(ln.trrp, ch, bln, small);
     if (rc) return fail(s, rc, std::string("error terms: ") + ctx_err(ln));
     g_tm.lap("msm_phase3");
     parallel_for(B, [&](size_t b) {
@@ -1359,7 +1392,7 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_SCALARS);
     });
     g_tm.lap("host_phase3");
-    rc = bppp_trrp_commit_bl(ln.trrp, sclin, c2);
+    rc = dt ? bppp_trrp_commit_bl_tr(ln.trrp, sclin, c2, cht) : bppp_trrp_commit_bl(ln.trrp, sclin, c2);
     if (rc) return fail(s, rc, std::string("blinding commitment: ") + ctx_err(ln));
     g_tm.lap("msm_phase3");
     // ---------------- phase 4
@@ -1368,7 +1401,8 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         uint8_t* out = coms + 64 * b * NC;
         memcpy(out, &c2[64 * b], 64);                                       // blCom
         Sect sect;
-        p.zk.oracle(out, 1, &p.t, 1);
+        if (dt) p.t = h64::from_bytes(cht + 32 * b);
+        else p.zk.oracle(out, 1, &p.t, 1);
         sect.lap(S_ORACLE);
         h64::to_bytes(ch + 32 * (2 * b), p.t); h64::to_bytes(ch + 32 * (2 * b + 1), p.q0_inv);
     });
@@ -1401,7 +1435,7 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_TOBYTES);
     });
     g_tm.lap("host_phase4");
-    return run_argument(s, ln, P, s->prover_rounds, q_b, sc_b, nullptr, l_b, c_b, responses, finals, s->prover_fin_n, s->prover_fin_l, true);
+    return run_argument(s, ln, P, s->prover_rounds, q_b, sc_b, nullptr, l_b, c_b, responses, finals, s->prover_fin_n, s->prover_fin_l, true, dt);
 }
 
 // RangeProof.proveM (src/RangeProof.hs:95-97) for `batch` independent proofs.
@@ -1654,10 +1688,15 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
         if (rc) return fail(s, rc, std::string("input commitments: ") + ctx_err(ln));
     }
     const bool dev = s->dev_phases && ln.trrp;
-    rc = dev ? bppp_trrp_phase1(ln.trrp, B, sc1, values, c1) : bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1, c1);
+    const bool dt = dev && s->dev_transcript;
+    uint8_t* cht = dt ? lane_buf(s, ln, PB_CHT, B * 3 * 32) : nullptr;
+    if (dt) bppp_trrp_set_transcript(ln.trrp, s->fmt);
+    else if (dev) bppp_trrp_set_transcript(ln.trrp, -1);
+    rc = dt ? bppp_trrp_phase1_tr(ln.trrp, B, sc1, values, n, n_coms, c1, cht)
+            : dev ? bppp_trrp_phase1(ln.trrp, B, sc1, values, c1) : bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1, c1);
     if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(ln));
     g_tm.lap("msm_phase1");
-    if (dev) return prove_trrp_device(s, ln, P, coms, responses, finals, c1, n_coms);
+    if (dev) return prove_trrp_device(s, ln, P, coms, responses, finals, c1, n_coms, random_seeds, cht);
     uint8_t* q_b = lane_buf(s, ln, PB_Q, B * 32);
     uint8_t* sc_b = lane_buf(s, ln, PB_S, B * 32);
     uint8_t* w_b = lane_buf(s, ln, PB_W, B * N * 32);
@@ -1859,6 +1898,29 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         std::vector<VP> V(B);
         uint8_t* ch = lane_buf(s, ln, PB_CH, B * 8 * 32);
         uint8_t* small = lane_buf(s, ln, PB_SMALL, B * 6 * 32);
+        // device transcript: every commitment of the proofs is rendered once, then ONE launch squeezes the
+        // challenges of all stages (each stage's transcript is a suffix of the final one)
+        const uint8_t* dch = nullptr;
+        const size_t n_ch = 7 + k;
+        if (s->dev_transcript && k + 3 <= 64) {
+            if ((size_t)ln.index >= s->lane_vtr.size()) return fail(s, BPPP_ERR_STATE, "lane without a transcript slot");
+            bppp_dtr*& t = s->lane_vtr[ln.index];
+            if (t && !bppp_dtr_fits(t, B, NC + 2 * k, s->fmt)) { bppp_dtr_destroy(t); t = nullptr; }
+            int rc = t ? BPPP_OK : bppp_dtr_create(ln.ctx, B, NC + 2 * k, s->fmt, &t);
+            if (!rc) rc = bppp_dtr_reset(t);
+            if (!rc) rc = bppp_dtr_absorb(t, coms + 128, NC, 2 + n);        // dmCom : mCom : nComs
+            if (!rc) rc = bppp_dtr_absorb(t, coms + 64, NC, 1);              // rCom
+            if (!rc) rc = bppp_dtr_absorb(t, coms, NC, 1);                   // blCom
+            for (size_t r = 0; !rc && r < k; r++) rc = bppp_dtr_absorb(t, responses + 128 * (k - 1 - r), 2 * k, 2);   // oldest round first
+            std::vector<uint8_t> idx(n_ch, 1), st(n_ch);
+            idx[1] = 2; idx[2] = 3; idx[4] = 2; idx[5] = 3;
+            for (size_t j = 0; j < n_ch; j++) st[j] = (uint8_t)(j < 3 ? 1 : j < 6 ? 2 : j == 6 ? 3 : 4 + (j - 7));
+            uint8_t* out = lane_buf(s, ln, PB_CHT, B * n_ch * 32);
+            if (!rc) rc = bppp_dtr_squeeze(t, n_ch, idx.data(), st.data(), out);
+            if (rc) return fail(s, rc, std::string("device transcript: ") + ctx_err(ln));
+            dch = out;
+            g_tm.lap("verify_transcript");
+        }
         parallel_for(B, [&](size_t b) {
             tr::Zkpt zk;
             Sect sect;
@@ -1866,6 +1928,14 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             zk.no_random = true;
             const uint8_t* cm = coms + 64 * b * NC;
             VP& v = V[b];
+            if (dch) {
+                const uint8_t* c = dch + 32 * b * n_ch;
+                v.e = h64::from_bytes(c); v.x = h64::from_bytes(c + 32); v.r0 = h64::from_bytes(c + 64);
+                v.q = h64::from_bytes(c + 96); v.xq = h64::from_bytes(c + 128); v.r1 = h64::from_bytes(c + 160);
+                v.q0 = q0_of(s->arg, v.q);
+                v.t = h64::from_bytes(c + 192);
+                for (size_t r = 0; r < k; r++) memcpy(&es_b[32 * (b * k + (k - 1 - r))], c + 32 * (7 + r), 32);
+            } else {
             Fr c1[3], c2[3];
             zk.oracle(cm + 128, 2 + n, c1, 3);
             v.e = c1[0]; v.x = c1[1]; v.r0 = c1[2];
@@ -1879,6 +1949,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             for (size_t r = 0; r < k; r++) rp[r] = responses + 128 * (b * k + (k - 1 - r));
             zk.oracle_rounds(rp.data(), k, es.data());
             for (size_t r = 0; r < k; r++) h64::to_bytes(&es_b[32 * (b * k + (k - 1 - r))], es[r]);
+            }
             sect.lap(S_V_ORACLE);
             Fr iv[2] = {v.e, v.q0};
             h64::batch_inv(iv, 2);
@@ -2019,6 +2090,7 @@ std::vector<Lane> make_lanes(bppp_rp* s, size_t batch) {
     for (size_t i = 0; i < s->lane_ctx.size(); i++)
         L.push_back({s->lane_ctx[i], s->lane_fb[i], s->lane_gens[i], 0, (int)i + 1, i < s->lane_trrp.size() ? s->lane_trrp[i] : nullptr});
     if (s->pinned.size() < L.size()) s->pinned.resize(L.size(), std::vector<bppp_rp::Pinned>(PB_COUNT));
+    if (s->lane_vtr.size() < L.size()) s->lane_vtr.resize(L.size(), nullptr);
     size_t want = std::max<size_t>(1, std::min(L.size(), batch / 32));      // tiny batches: one lane
     L.resize(want);
     int total = g_threads > 0 ? g_threads : (int)std::thread::hardware_concurrency();

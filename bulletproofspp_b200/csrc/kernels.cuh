@@ -1040,6 +1040,11 @@ __global__ void __launch_bounds__(256) k_ip_verify_scalars(IpVerifyArgs A) {
     st_u256(o + 2 * j, fr::from_mont(fr::sub(ld_u256(pub + 2 * j), d)));
     if (2 * j + 1 < A.n) st_u256(o + 2 * j + 1, fr::from_mont(fr::sub(ld_u256(pub + 2 * j + 1), fr::add(tx, ty))));
 }
+// p[i * stride] = v
+__global__ void k_fill_u32_strided(unsigned* p, size_t stride, unsigned v, size_t n) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) p[i * stride] = v;
+}
 // fill with the Montgomery one
 __global__ void k_fill_one(u256* p, size_t n) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;

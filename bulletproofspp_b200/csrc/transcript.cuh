@@ -59,168 +59,243 @@ __global__ void __launch_bounds__(TR_THREADS) k_hash_to_curve(const unsigned cha
     st_aff(out + t, p);
 }
 
-// ---- transcript store: one record per commitment, `show x <> show y` as ASCII (app/Main.hs:78-80)
-#define TR_REC_BYTES 160             // 2 * (2 + 78); records are 4-byte aligned, readers mask the tail
-// rec[b][slot0 + j] = show of pts[b * pts_stride + j], j < npts; len likewise.  One thread per point.
-__global__ void __launch_bounds__(TR_THREADS) k_tr_render(const Affine* __restrict__ pts, size_t pts_stride, int npts, size_t batch,
-                                                          int fmt, unsigned char* __restrict__ rec, unsigned char* __restrict__ len,
-                                                          size_t cap, size_t slot0) {
-    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (t >= batch * (size_t)npts) return;
-    const size_t b = t / npts, j = t % npts;
-    const Affine p = ld_aff(pts + b * pts_stride + j);
-    const size_t slot = b * cap + slot0 + j;
-    unsigned char* o = rec + slot * TR_REC_BYTES;
-    int l = 0;
-#pragma unroll 1
-    for (int k = 0; k < 2; k++) {
-        if (fmt == TR_PREFIXED_P) { o[l++] = 'P'; o[l++] = ' '; }
-        l += dsha::decimal_u256(k ? p.y : p.x, o + l);
+// ---- transcript store.  `oracle xs` PREPENDS xs to the commitment list (cs' = xs ++ cs, src/ZKP.hs:98) and a
+// challenge hashes  show i <> show (length cs') <> concat [show x <> show y | A x y <- cs']  (app/Main.hs:75-80):
+// the newest commitments come FIRST, so no hash state can be carried from one call to the next -- every
+// challenge re-hashes the whole list.  The list is kept per proof as ONE contiguous byte string, right-aligned
+// in a fixed buffer of `SC` bytes: absorbing a call writes its rendering in front of what is there.  The body of
+// the message after call c is buf[start_c .. SC); every earlier transcript is a suffix of the latest one, which
+// is what lets the verifier render all commitments once and squeeze the challenges of all stages in one launch.
+#define TR_PT_BYTES 160              // 2 * (2 + 78): the longest rendering of one point
+#define TR_MAX_CALLS 80
+#define TR_PREPEND_THREADS 128
+
+// number of decimal digits of x (< 10^9)
+__device__ __forceinline__ int dec_len9(uint32_t x) {
+    int l = 1;
+    if (x >= 100000000u) l = 9; else if (x >= 10000000u) l = 8; else if (x >= 1000000u) l = 7; else if (x >= 100000u) l = 6;
+    else if (x >= 10000u) l = 5; else if (x >= 1000u) l = 4; else if (x >= 100u) l = 3; else if (x >= 10u) l = 2;
+    return l;
+}
+// a -> base-10^9 chunks, least significant first; returns the number of chunks (0 for a = 0).  Nine full passes
+// with static indices: everything stays in registers (two inlined copies of a variant with data-dependent
+// loop bounds and locally indexed arrays rendered the second coordinate wrongly on sm_100a, nvcc 12.9).
+__device__ __noinline__ int dec_chunks(const u256& a, uint32_t chunks[9]) {
+    uint32_t t[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) t[i] = a.v[i];
+#pragma unroll
+    for (int c = 0; c < 9; c++) {
+        uint64_t rem = 0;
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            const uint64_t cur = (rem << 32) | t[i];
+            t[i] = (uint32_t)(cur / 1000000000u);
+            rem = cur % 1000000000u;
+        }
+        chunks[c] = (uint32_t)rem;
     }
-    len[slot] = (unsigned char)l;
+    int nc = 0;
+#pragma unroll
+    for (int c = 0; c < 9; c++)
+        if (chunks[c]) nc = c + 1;
+    return nc;
+}
+__device__ __forceinline__ int dec_chunks_len(const uint32_t chunks[9], int nc) {
+    uint32_t topc = 0;
+#pragma unroll
+    for (int c = 0; c < 9; c++)
+        if (c == nc - 1) topc = chunks[c];
+    return nc ? 9 * (nc - 1) + dec_len9(topc) : 1;
+}
+// the digits of the chunk form, most significant first, no leading zeros ("0" for zero); returns the length
+__device__ __noinline__ int dec_chunks_write(const uint32_t chunks[9], int nc, unsigned char* out) {
+    if (nc == 0) { out[0] = '0'; return 1; }
+    int len = 0;
+#pragma unroll 1
+    for (int c = nc - 1; c >= 0; c--) {
+        uint32_t x = chunks[c];
+        const int nd = c == nc - 1 ? dec_len9(x) : 9;
+#pragma unroll 1
+        for (int k = nd - 1; k >= 0; k--) { out[len + k] = (unsigned char)('0' + x % 10); x /= 10; }
+        len += nd;
+    }
+    return len;
 }
 
-// The absorb calls of a transcript so far, oldest first: call c put `npts[c]` records at slot `first[c]`.
-// `oracle xs` PREPENDS xs to the commitment list (cs' = xs ++ cs, src/ZKP.hs:98), so a message walks the
-// calls from the newest to the oldest, and the points of one call in the order they were given.
-#define TR_MAX_CALLS 48
-struct TrCalls {
-    int n;
-    unsigned short first[TR_MAX_CALLS], npts[TR_MAX_CALLS];
+// One absorb call for every proof of the batch: CTA b renders the `npts` points pts[b * pts_stride + j] (in the
+// order given: they become the FRONT of the list) in front of proof b's transcript.  start = [B][TR_MAX_CALLS + 1]
+// body offsets; state `call` is read, state `call + 1` written.
+__global__ void __launch_bounds__(TR_PREPEND_THREADS) k_tr_prepend(const Affine* __restrict__ pts, size_t pts_stride, int npts, int fmt,
+                                                                   unsigned char* __restrict__ buf, unsigned SC,
+                                                                   unsigned* __restrict__ start, int call) {
+    __shared__ unsigned s_scan[TR_PREPEND_THREADS];
+    __shared__ unsigned s_total;
+    const size_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const unsigned prev = start[b * (TR_MAX_CALLS + 1) + call];
+    // pass 1: total length of the call
+    unsigned mine = 0;
+    for (int j = tid; j < npts; j += TR_PREPEND_THREADS) {
+        const Affine p = ld_aff(pts + b * pts_stride + j);
+        uint32_t ch[9];
+        int nc = dec_chunks(p.x, ch);
+        mine += dec_chunks_len(ch, nc);
+        nc = dec_chunks(p.y, ch);
+        mine += dec_chunks_len(ch, nc) + (fmt == TR_PREFIXED_P ? 4 : 0);
+    }
+    s_scan[tid] = mine;
+    __syncthreads();
+    if (tid == 0) {
+        unsigned t = 0;
+        for (int k = 0; k < TR_PREPEND_THREADS; k++) t += s_scan[k];
+        s_total = t;
+    }
+    __syncthreads();
+    const unsigned new_start = prev - s_total;
+    unsigned char* base = buf + b * (size_t)SC + new_start;
+    // pass 2: chunks of TR_PREPEND_THREADS consecutive points, offsets by a block scan with a running carry
+    unsigned carry = 0;
+    for (int j0 = 0; j0 < npts; j0 += TR_PREPEND_THREADS) {
+        const int j = j0 + tid;
+        uint32_t cx[9], cy[9];
+        int nx = 0, ny = 0;
+        unsigned len = 0;
+        if (j < npts) {
+            const Affine p = ld_aff(pts + b * pts_stride + j);
+            nx = dec_chunks(p.x, cx);
+            ny = dec_chunks(p.y, cy);
+            len = dec_chunks_len(cx, nx) + dec_chunks_len(cy, ny) + (fmt == TR_PREFIXED_P ? 4 : 0);
+        }
+        __syncthreads();
+        s_scan[tid] = len;
+        __syncthreads();
+        for (int d = 1; d < TR_PREPEND_THREADS; d <<= 1) {          // inclusive Hillis-Steele scan
+            const unsigned v = tid >= d ? s_scan[tid - d] : 0;
+            __syncthreads();
+            s_scan[tid] += v;
+            __syncthreads();
+        }
+        const unsigned off = carry + s_scan[tid] - len;
+        carry += s_scan[TR_PREPEND_THREADS - 1];
+        if (j < npts) {
+            unsigned char* o = base + off;
+            int l = 0;
+            if (fmt == TR_PREFIXED_P) { o[l++] = 'P'; o[l++] = ' '; }
+            l += dec_chunks_write(cx, nx, o + l);
+            if (fmt == TR_PREFIXED_P) { o[l++] = 'P'; o[l++] = ' '; }
+            l += dec_chunks_write(cy, ny, o + l);
+        }
+    }
+    if (tid == 0) start[b * (TR_MAX_CALLS + 1) + call + 1] = new_start;
+}
+
+// Which challenges one squeeze produces: challenge j is scalar `idx[j]` (1-based, <= 9) of the transcript after
+// `state[j]` absorb calls, which then holds `ncoms[j]` commitments.
+#define TR_MAX_CHAL 48
+struct TrPlan {
+    int count;
+    unsigned char idx[TR_MAX_CHAL], state[TR_MAX_CHAL];
+    unsigned ncoms[TR_MAX_CHAL];
 };
 
-// Reader of one message  show i <> show (length cs') <> concat [show x <> show y | A x y <- cs']  as
-// big-endian 32-bit words followed by the SHA-256 padding (0x80, zeros); the caller places the length.
-struct TrReader {
-    const unsigned char* rec; const unsigned char* len;        // this proof's records
-    const TrCalls* calls;
-    int ci, pj;                  // current call (descending), point inside it
-    const unsigned char* cur; unsigned cur_len, off;
-    unsigned long long pend; unsigned npend;                   // left-aligned pending bytes
-    unsigned long long total;                                   // message bytes consumed
-    bool src_done, pad_done;
-
-    __device__ __forceinline__ void open_record() {
-        const size_t slot = (size_t)calls->first[ci] + pj;
-        cur = rec + slot * TR_REC_BYTES;
-        cur_len = len[slot];
-        off = 0;
-    }
-    __device__ __forceinline__ void begin(const unsigned char* rec_, const unsigned char* len_, const TrCalls* calls_,
-                                          unsigned long long header, unsigned header_len) {
-        rec = rec_; len = len_; calls = calls_;
-        pend = header; npend = header_len; total = header_len;
-        src_done = false; pad_done = false;
-        ci = calls->n - 1; pj = 0; cur_len = 0; off = 0; cur = rec_;
-        while (ci >= 0 && calls->npts[ci] == 0) ci--;
-        if (ci < 0) src_done = true; else open_record();
-    }
-    __device__ __forceinline__ unsigned next_word() {
-        while (npend < 4 && !src_done) {
-            if (off >= cur_len) {                               // next record, newest call first
-                if (++pj >= (int)calls->npts[ci]) {
-                    pj = 0;
-                    do { ci--; } while (ci >= 0 && calls->npts[ci] == 0);
-                    if (ci < 0) { src_done = true; break; }
-                }
-                open_record();
-                continue;
-            }
-            const unsigned k = min(4u, cur_len - off);
-            unsigned w = __byte_perm(*reinterpret_cast<const unsigned*>(cur + off), 0, 0x0123);
-            if (k < 4) w &= 0xffffffffu << (8 * (4 - k));
-            off += 4;
-            pend |= (unsigned long long)w << (32 - 8 * npend);
-            npend += k;
-            total += k;
-        }
-        if (npend < 4 && !pad_done) {                           // the source is exhausted: one 0x80, then zeros
-            pend |= 0x8000000000000000ull >> (8 * npend);
-            npend += 1;
-            pad_done = true;
-        }
-        const unsigned out = (unsigned)(pend >> 32);
-        pend <<= 32;
-        npend = npend >= 4 ? npend - 4 : 0;
-        return out;
-    }
-};
-
-// challenge i (1-based, i <= 9) of proof b after the absorbs in `calls`: out[b * count + i - 1], canonical
-// scalar (digest -> Fr, Encoding.hs:75-79).  One thread per (proof, challenge); the threads of a warp fill
-// their blocks independently and compress in lock-step.
-__global__ void __launch_bounds__(TR_THREADS) k_tr_squeeze(const unsigned char* __restrict__ rec, const unsigned char* __restrict__ len,
-                                                           size_t cap, TrCalls calls, size_t batch, int count, unsigned n_coms,
-                                                           u256* __restrict__ out) {
+// out[b * count + j] = challenge j of proof b, canonical scalar (digest -> Fr, Encoding.hs:75-79).  One thread per
+// (proof, challenge).  A block that lies inside the body is read with 17 aligned word loads and byte
+// permutes (the body's alignment is fixed for the whole message); the first block (header) and the last
+// one or two (tail, 0x80, bit length) are assembled byte by byte.
+__global__ void __launch_bounds__(TR_THREADS) k_tr_squeeze(const unsigned char* __restrict__ buf, unsigned SC, const unsigned* __restrict__ start,
+                                                           TrPlan plan, size_t batch, u256* __restrict__ out) {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    const bool live = t < batch * (size_t)count;
-    const size_t b = live ? t / count : 0;
-    const unsigned i = live ? (unsigned)(t % count) + 1 : 1;
-    // header: show i <> show n_coms, at most 1 + 6 digits, left-aligned in 64 bits
-    unsigned long long header = (unsigned long long)('0' + i) << 56;
-    unsigned hl = 1;
+    if (t >= batch * (size_t)plan.count) return;
+    const size_t b = t / plan.count;
+    const int j = (int)(t % plan.count);
+    unsigned char hdr[8];
+    unsigned hl = 0;
+    hdr[hl++] = (unsigned char)('0' + plan.idx[j]);
     {
-        char buf[8];
+        char tmp[8];
         int n = 0;
-        unsigned x = n_coms;
-        do { buf[n++] = (char)('0' + x % 10); x /= 10; } while (x && n < 6);
-        while (n) { header |= (unsigned long long)(unsigned char)buf[--n] << (56 - 8 * hl); hl++; }
+        unsigned x = plan.ncoms[j];
+        do { tmp[n++] = (char)('0' + x % 10); x /= 10; } while (x && n < 7);
+        while (n) hdr[hl++] = (unsigned char)tmp[--n];
     }
-    TrReader rd;
-    rd.begin(rec + b * cap * TR_REC_BYTES, len + b * cap, &calls, header, hl);
+    const unsigned st0 = start[b * (TR_MAX_CALLS + 1) + plan.state[j]];
+    const unsigned char* body = buf + b * (size_t)SC + st0;
+    const unsigned L = SC - st0;
+    const unsigned long long T = (unsigned long long)hl + L;          // message bytes
+    const unsigned nblk = (unsigned)((T + 9 + 63) / 64);
     uint32_t st[8];
     dsha::init(st);
-    bool done = !live;
-    unsigned long long blocks = 0;
-    while (!__all_sync(0xffffffffu, done)) {
+    // alignment of message offset m (>= hl) inside the body: address body + (m - hl)
+    const size_t a0 = (size_t)(body - hl);                             // address of "message byte 0" (virtual)
+    const unsigned sh = (unsigned)(a0 & 3);
+    const unsigned sel = (sh + 3) | ((sh + 2) << 4) | ((sh + 1) << 8) | (sh << 12);
+    for (unsigned k = 0; k < nblk; k++) {
         uint32_t w[16];
-        bool last = false;
-        if (!done) {
+        const unsigned long long m0 = (unsigned long long)k * 64;
+        if (k >= 1 && m0 + 64 <= T) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>((a0 + m0) & ~(size_t)3);
+            uint32_t lo = q[0];
 #pragma unroll
-            for (int k = 0; k < 16; k++) w[k] = rd.next_word();
-            blocks++;
-            if (rd.pad_done && rd.total + 1 + 8 <= blocks * 64) {                 // message + 0x80 + length fit: final block
-                const unsigned long long bits = rd.total * 8;
+            for (int i = 0; i < 16; i++) {
+                const uint32_t hi = q[i + 1];
+                w[i] = __byte_perm(lo, hi, sel);
+                lo = hi;
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 16; i++) {
+                uint32_t x = 0;
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
+                    const unsigned long long m = m0 + 4 * i + c;
+                    unsigned byte = 0;
+                    if (m < hl) byte = hdr[m];
+                    else if (m < T) byte = body[m - hl];
+                    else if (m == T) byte = 0x80;
+                    x = (x << 8) | byte;
+                }
+                w[i] = x;
+            }
+            if (k == nblk - 1) {
+                const unsigned long long bits = T * 8;
                 w[14] = (uint32_t)(bits >> 32);
                 w[15] = (uint32_t)bits;
-                last = true;
             }
-            dsha::compress(st, w);
         }
-        if (last) done = true;
+        dsha::compress(st, w);
     }
-    if (live) st_u256(out + t, dsha::digest_to_fr(st));
+    st_u256(out + t, dsha::digest_to_fr(st));
 }
 
-// `random` (src/ZKP.hs:90-93 with h = hashToScalar rn . show, app/Main.hs:177): out[b * count + j] =
-// hash(seed_b <> show (n0 + j)) as a canonical scalar.  seeds = [batch][64] bytes, seed_len <= 40 so that the
-// message is a single block.
+// `random` (src/ZKP.hs:90-93 with h = hashToScalar rn . show, app/Main.hs:177): out[b * out_stride + j] =
+// hash(seed_b <> show (n0_b + j)) as a canonical scalar, n0_b = n0s[b] (or n0 for every proof when n0s is
+// null).  seeds = [batch][64] bytes, seed_len <= 40 so that the message is a single block.
 __global__ void __launch_bounds__(TR_THREADS) k_tr_random(const unsigned char* __restrict__ seeds, const unsigned char* __restrict__ seed_len,
-                                                          unsigned long long n0, size_t batch, size_t count, u256* __restrict__ out) {
+                                                          unsigned long long n0, const unsigned long long* __restrict__ n0s, size_t batch,
+                                                          size_t count, u256* __restrict__ out, size_t out_stride) {
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (t >= batch * count) return;
     const size_t b = t / count, j = t % count;
-    unsigned char m[64];
+    uint32_t w[16];
 #pragma unroll
-    for (int k = 0; k < 64; k++) m[k] = 0;
+    for (int k = 0; k < 16; k++) w[k] = 0;
     int l = seed_len[b];
-    for (int k = 0; k < l; k++) m[k] = seeds[b * 64 + k];
+    auto put = [&](int pos, unsigned byte) { w[pos >> 2] |= byte << (24 - 8 * (pos & 3)); };
+    for (int k = 0; k < l; k++) put(k, seeds[b * 64 + k]);
     {
         char buf[20];
         int n = 0;
-        unsigned long long x = n0 + j;
+        unsigned long long x = (n0s ? n0s[b] : n0) + j;
         do { buf[n++] = (char)('0' + (int)(x % 10)); x /= 10; } while (x);
-        while (n) m[l++] = (unsigned char)buf[--n];
+        while (n) put(l++, (unsigned char)buf[--n]);
     }
-    m[l] = 0x80;
-    uint32_t w[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++) w[k] = ((uint32_t)m[4 * k] << 24) | ((uint32_t)m[4 * k + 1] << 16) | ((uint32_t)m[4 * k + 2] << 8) | m[4 * k + 3];
+    put(l, 0x80);
     w[15] = (uint32_t)l * 8;
     uint32_t st[8];
     dsha::init(st);
     dsha::compress(st, w);
-    st_u256(out + t, dsha::digest_to_fr(st));
+    st_u256(out + b * out_stride + j, dsha::digest_to_fr(st));
 }
 
 }  // namespace bppp

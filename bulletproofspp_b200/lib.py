@@ -25,6 +25,8 @@ EXPORTS = [
     "bppp_dtr_oracle", "bppp_dev_random",
     "bppp_trrp_create", "bppp_trrp_destroy", "bppp_trrp_phase1", "bppp_trrp_phase2", "bppp_trrp_phase3", "bppp_trrp_commit_bl",
     "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
+    "bppp_dtr_absorb", "bppp_dtr_squeeze", "bppp_dtr_fits", "bppp_dtr_export", "bppp_rp_set_device_transcript", "bppp_nl_round_challenge",
+    "bppp_trrp_set_transcript", "bppp_trrp_phase1_tr", "bppp_trrp_phase2_tr", "bppp_trrp_phase3_rnd", "bppp_trrp_commit_bl_tr",
 ]
 
 
@@ -125,6 +127,12 @@ def load_library():
     lib.bppp_dtr_reset.argtypes = [vp]
     lib.bppp_dtr_oracle.argtypes = [vp, u8p, sz, ip, u8p]
     lib.bppp_dev_random.argtypes = [vp, sz, C.POINTER(C.c_char_p), C.c_uint64, sz, u8p]
+    lib.bppp_dtr_absorb.argtypes = [vp, u8p, sz, sz]
+    lib.bppp_dtr_squeeze.argtypes = [vp, sz, u8p, u8p, u8p]
+    lib.bppp_dtr_fits.argtypes = [vp, sz, sz, ip]
+    lib.bppp_dtr_export.argtypes = [vp, sz, u8p, sz, C.POINTER(sz)]
+    lib.bppp_rp_set_device_transcript.argtypes = [vp, ip]
+    lib.bppp_nl_round_challenge.argtypes = [vp, u8p, u8p, u8p]
     lib.bppp_tune_process.argtypes = [ip]
     # this harness drives dedicated batch-proving processes (tests, bench.py): opt in to the process-wide
     # tuning (malloc arenas, blocking-sync device flags, pool pre-growth); BPPP_NO_TUNE=1 leaves the process alone
@@ -472,6 +480,10 @@ class RangeProofSetup:
     def _ck(self, rc, what):
         if rc:
             raise BpppError("%s failed (%d): %s" % (what, rc, self.ctx.lib.bppp_rp_last_error(self.h).decode()))
+
+    def set_device_transcript(self, on=True):
+        """run the Fiat-Shamir transcript of prove_batch / verify_batch on the device; bit-identical"""
+        self._ck(self.ctx.lib.bppp_rp_set_device_transcript(self.h, int(bool(on))), "bppp_rp_set_device_transcript")
 
     def contexts(self):
         """the contexts of all concurrent lanes (lane 0 first)"""

@@ -96,6 +96,16 @@ int bppp_dtr_reset(bppp_dtr* t);
 /* `oracle xs` / `oracle'` (src/ZKP.hs:96-101, 60-63; shaOracle app/Main.hs:75-80): prepend pts = [batch][npts]
  * to every proof's list, then out = [batch][count] = the first `count` (<= 9) scalars of shaOracle */
 int bppp_dtr_oracle(bppp_dtr* t, const uint8_t* pts, size_t npts, int count, uint8_t* out);
+/* the two halves separately, for a verifier that knows every commitment up front (verifyBPM's `oracle'` calls,
+ * src/Bulletproof.hs:370-378): bppp_dtr_absorb is cs' = xs ++ cs alone -- row b of the call is the `npts` points at
+ * pts + 64 * stride_points * b; bppp_dtr_squeeze then hashes any number of stages in ONE launch: out[b][j] = scalar
+ * idx[j] (1-based, <= 9) of the transcript as it was after state[j] absorb calls (state NULL or 0: all of them).
+ * Every earlier transcript is a suffix of the latest one (newest commitments first). */
+int bppp_dtr_absorb(bppp_dtr* t, const uint8_t* pts, size_t stride_points, size_t npts);
+int bppp_dtr_squeeze(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out);
+int bppp_dtr_fits(bppp_dtr* t, size_t batch, size_t max_points, int show_format);
+/* the rendered list of one proof, concat [show x <> show y] newest first (what app/Main.hs:78-80 feeds the hash) */
+int bppp_dtr_export(bppp_dtr* t, size_t proof, uint8_t* out, size_t cap, size_t* len);
 /* `random` (src/ZKP.hs:90-93 with hashToScalar randomSeed . show, app/Main.hs:177): out[b][j] = draw n0 + j of proof b */
 int bppp_dev_random(bppp_ctx* ctx, size_t batch, const char* const* seeds, uint64_t n0, size_t count, uint8_t* out);
 
@@ -136,6 +146,9 @@ int bppp_nl_create_gens(bppp_gens* gens, int kind, size_t batch, const uint8_t* 
 /* makeScalarsComs + the two `commit`s of proveRoundM (src/Bulletproof.hs:346-350):
  * X[b], R[b] (64 bytes each; L, R for the IP argument). */
 int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R);
+/* the same plus E = [batch] challenges  e <- head <$> oracle [X, R]  (Bulletproof.hs:351) from the device
+ * transcript the argument continues (arguments made by bppp_nl_create_trrp after bppp_trrp_*_tr calls) */
+int bppp_nl_round_challenge(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E);
 /* the rest of proveRoundM (src/Bulletproof.hs:351-355): s' = s + e0*sX + e1*sR and `collapse e`
  * (NormArgument.hs:64-71,123-129 / InnerProductArgument.hs:86-101,155-170) with challenge e[b]. */
 int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e);
@@ -206,6 +219,21 @@ int bppp_trrp_phase2(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, 
 int bppp_trrp_phase3(bppp_trrp* h, const uint8_t* chal, const uint8_t* bls_nrm, uint8_t* errs);
 /* phase 3b (:434): bl_sclin = [batch][1+M] scalar and linear slots of the blinding witness. */
 int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom);
+/* The same phases with the Fiat-Shamir transcript on the device: after
+ * bppp_trrp_set_transcript(h, show_format >= 0) the commitments are absorbed where they are produced
+ * and each call also returns the challenges of the reference's next `oracle'` call --
+ *   phase1_tr: n_coms = [batch][n_inputs] input commitments; chal = [batch][3] (e, x, r0)   (:411)
+ *   phase2_tr: chal_out = [batch][3] (q, x', r1)                                            (:420)
+ *   commit_bl_tr: chal_out = [batch] (t)                                                    (:435)
+ * and bppp_nl_create_trrp hands the transcript on to the argument (bppp_nl_round_challenge).
+ * phase3_rnd draws the N norm blinders on the device: `random` values n0[b] .. n0[b]+N-1 of seeds[b]. */
+int bppp_trrp_set_transcript(bppp_trrp* h, int show_format);
+int bppp_trrp_phase1_tr(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, size_t n_inputs,
+                        const uint8_t* n_coms, uint8_t* coms, uint8_t* chal);
+int bppp_trrp_phase2_tr(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
+                        uint8_t* err7, uint8_t* chal_out);
+int bppp_trrp_phase3_rnd(bppp_trrp* h, const uint8_t* chal, const char* const* seeds, const uint64_t* n0, uint8_t* errs);
+int bppp_trrp_commit_bl_tr(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom, uint8_t* chal_out);
 /* phase 4 (:435-444): chal = [batch][2] = (t, 1/q0).  sums = [batch][3] = (sum q2_i p_i^2 over all
  * entries, sum q2_i and sum v_i over the digit entries); the combined witness stays on the device. */
 int bppp_trrp_phase4(bppp_trrp* h, const uint8_t* chal, uint8_t* sums);
@@ -248,6 +276,10 @@ int bppp_rp_info(bppp_rp* s, size_t* n_inputs, size_t* num_rp_coms, size_t* nrm_
 int bppp_rp_points(bppp_rp* s, size_t count, uint8_t* out);
 int bppp_input_blind(const char* random_seed, uint64_t j, uint8_t out[32]);
 void bppp_set_host_threads(int n);
+/* where bppp_rp_prove_batch / bppp_rp_verify_batch run the Fiat-Shamir transcript: 0 = host (default, the
+ * reference's arrangement), 1 = device (bit-identical proofs and verdicts; needs the device scalar
+ * phases, i.e. TypedReciprocal over the norm-linear argument).  Environment default: BPPP_DEVICE_TRANSCRIPT=1. */
+int bppp_rp_set_device_transcript(bppp_rp* s, int on);
 /* RangeProof.proveM for `batch` independent proofs (see rp_host.cpp for the buffer layout) */
 int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
                         const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals);

@@ -159,6 +159,72 @@ def test_device_scalar_phases_match_host_phases(ctx, name, monkeypatch):
     host.close()
 
 
+@pytest.mark.parametrize("name,count", [("typed_nl", 1), ("32by64", 70), ("128by64", 3)])
+def test_device_transcript_is_bit_identical(ctx, name, count):
+    """with bppp_rp_set_device_transcript the commitments are rendered (`show`) and hashed
+    (shaOracle) on the device and the norm blinders drawn there; the proofs must equal the host-transcript
+    ones bit for bit (and the golden vectors), verification must accept them and reject tampering."""
+    import bulletproofspp_b200 as bp
+    schema, wits, seeds = batched(name, count)
+    host = bp.RangeProofSetup(ctx, schema)
+    dev = bp.RangeProofSetup(ctx, schema)
+    dev.set_device_transcript(True)
+    p_host = host.prove_batch(wits, seeds)
+    p_dev = dev.prove_batch(wits, seeds)
+    assert p_dev == p_host
+    if name == "128by64":
+        g1 = load_golden("128by64#1")
+        assert p_dev[1]["coms"] == g1["coms"] and p_dev[1]["responses"] == g1["responses"] and p_dev[1]["finals"] == g1["finals"]
+    assert all(dev.verify_batch(p_host)) and all(host.verify_batch(p_dev))
+    p = p_dev[0]
+    bad = dict(p, finals=[(p["finals"][0] + 1) % (2 ** 200)] + p["finals"][1:])
+    bad2 = dict(p, coms=[p["coms"][1], p["coms"][0]] + p["coms"][2:])
+    bad3 = dict(p, responses=[p["responses"][1], p["responses"][0]] + p["responses"][2:])
+    assert dev.verify_batch([bad, p, bad2, bad3]) == [False, True, False, False]
+    # a second batch through the same setup (the transcripts are reset, the random counters restart)
+    assert dev.prove_batch(wits, seeds) == p_host
+    # back to the host transcript on the same setup
+    dev.set_device_transcript(False)
+    assert dev.prove_batch(wits[:1], seeds[:1]) == p_host[:1]
+    host.close()
+    dev.close()
+
+
+def test_device_transcript_stages_in_one_squeeze(ctx, gens):
+    """bppp_dtr_absorb + bppp_dtr_squeeze: the verifier's form -- all commitments absorbed first, then the
+    challenges of every stage in one launch; each equals the oracle's transcript at that stage."""
+    import ctypes as C
+    from bulletproofspp_b200 import lib as L
+    from oracle.curve import Secp256k1 as G
+    from oracle.transcript import ZKPT
+    B = 5
+    base = gens(60)
+    calls = [7, 1, 1, 2, 2, 2]
+    rows = [[[base[(11 * b + 5 * ci + j) % 60] for j in range(n)] for b in range(B)] for ci, n in enumerate(calls)]
+    t = C.c_void_p()
+    ctx._ck(ctx.lib.bppp_dtr_create(ctx.h, B, sum(calls), 0, C.byref(t)), "bppp_dtr_create")
+    for ci, n in enumerate(calls):
+        # rows padded to a stride of n + 3 points
+        raw = b"".join(b"".join(L.point_to_bytes(p) for p in rows[ci][b]) + bytes(64 * 3) for b in range(B))
+        ctx._ck(ctx.lib.bppp_dtr_absorb(t, raw, n + 3, n), "bppp_dtr_absorb")
+    plan = [(1, 1), (2, 1), (3, 1), (1, 2), (3, 2), (1, 3), (1, 4), (1, 5), (1, 6), (2, 0)]
+    idx = bytes(i for i, _ in plan)
+    st = bytes(s_ for _, s_ in plan)
+    out = C.create_string_buffer(32 * B * len(plan))
+    ctx._ck(ctx.lib.bppp_dtr_squeeze(t, len(plan), idx, st, out), "bppp_dtr_squeeze")
+    got = L.bytes_to_ints(out.raw[:32 * B * len(plan)])
+    for b in range(B):
+        zk = ZKPT(G, None)
+        want = {}
+        for ci in range(len(calls)):
+            ch = zk.oracle(rows[ci][b], 3)
+            for i in (1, 2, 3):
+                want[(i, ci + 1)] = ch[i - 1]
+        for j, (i, s_) in enumerate(plan):
+            assert got[b * len(plan) + j] == want[(i, s_ or len(calls))], (b, j)
+    ctx.lib.bppp_dtr_destroy(t)
+
+
 def test_hybrid_round_mode_is_bit_identical(ctx, monkeypatch):
     """BPPP_HYBRID_MAX switches a tensor-mode argument to generator folding for its last rounds (the
     folded generators are materialised by one small fixed-base MSM per block).  Same proof bits."""
