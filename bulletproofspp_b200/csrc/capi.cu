@@ -19,19 +19,20 @@
 #include "kernels.cuh"
 #include "pippenger.cuh"
 #include "transcript.cuh"
+#include "rounds.cuh"
 
 using namespace bppp;
 
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_TR_POINTS, K_TR_RENDER, K_TR_SQUEEZE, K_TR_RANDOM, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_TR_POINTS, K_TR_RENDER, K_TR_SQUEEZE, K_TR_RANDOM, K_ROUND_STATE, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
                                                    "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce", "k_check_points",
                                                    "k_pip_sort", "k_pip_accum", "k_pip_merge", "k_pip_reduce", "k_pip_horner",
-                                                   "k_hash_to_curve", "k_tr_render", "k_tr_squeeze", "k_tr_random"};
+                                                   "k_hash_to_curve", "k_tr_render", "k_tr_squeeze", "k_tr_random", "k_round_state"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -1295,7 +1296,8 @@ struct bppp_nl {
 
 namespace {
 enum { C_RHO = 0, C_K1, C_K2, C_AU, C_BU, C_AL, C_BL, C_AC, C_BC, C_COEF /* 8 */, C_KB = C_COEF + 8 /* 2 */,
-       C_KA = C_KB + 2 /* 2 */, C_A0N = C_KA + 2, C_B0N, C_A0L, C_B0L, C_AV, C_BV, C_A0H, C_B0H, C_RR, C_NX, C_NY, C_COUNT };
+       C_KA = C_KB + 2 /* 2 */, C_A0N = C_KA + 2, C_B0N, C_A0L, C_B0L, C_AV, C_BV, C_A0H, C_B0H, C_RR, C_NX, C_NY,
+       C_Q, C_QINV, C_NN, C_NL, C_S, C_INV /* 2 */, C_COUNT = C_INV + 2 };   // C_Q..C_INV: the device-resident round state (rounds.cuh)
 inline u256* cptr(bppp_nl* h, int which) { return h->consts.p + (size_t)which * h->B; }
 static_assert(sizeof(Fr) == sizeof(u256), "host and device field elements share one layout");
 
@@ -2158,6 +2160,7 @@ extern "C" int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin) {
     return BPPP_OK;
 }
 
+static int nl_enqueue_commit(bppp_nl* h);
 static int nl_round_commit_impl(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
@@ -2190,6 +2193,32 @@ static int nl_round_commit_impl(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E) 
     if ((rc = upload_consts(h, C_K1, k1))) return rc;
     if ((rc = upload_consts(h, C_K2, k2))) return rc;
     CK(H2D(cptr(h, C_COEF), coef.data(), B * 8 * 32));
+    if ((rc = nl_enqueue_commit(h))) return rc;
+    std::vector<Affine> xr(B * 2);
+    std::vector<Fr> dots(B * 2);
+    CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
+    CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
+    if (E) {                            // e <- head <$> oracle [X, R]  (src/Bulletproof.hs:351)
+        if ((rc = dtr_absorb_dev(h->dtr, h->aff.p, 2, 2))) return rc;
+        if ((rc = dtr_squeeze_first(h->dtr, 1))) return rc;
+        CK(D2H(E, h->dtr->chal.p, B * 32));
+    }
+    CK(ctx_sync(ctx));
+    for (size_t b = 0; b < B; b++) {
+        memcpy(X + 64 * b, &xr[2 * b], 64);
+        memcpy(R + 64 * b, &xr[2 * b + 1], 64);
+        h->sX[b] = dots[2 * b];
+        h->sR[b] = dots[2 * b + 1];
+    }
+    return BPPP_OK;
+}
+// The device work of a round's two commitments once the round constants (C_K1, C_K2, C_COEF; C_RHO and the dot
+// partials) are in place: opening scalars in MSM order, the two MSMs, affine results in h->aff ([B][2] = X, R),
+// the scalar parts sX, sR in h->dots.  No host synchronisation.
+static int nl_enqueue_commit(bppp_nl* h) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B;
+    int rc;
     const size_t P0 = h->tensor ? h->tP0 : h->P0;               // row length of the MSM scalar vectors
     u256* xs = h->sc.p;
     u256* rs = h->sc.p + B * P0;
@@ -2262,24 +2291,7 @@ static int nl_round_commit_impl(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E) 
         h->plan.add(h->pts[h->curp].p, h->P2, xs, P0, B * P0, nterms);
         if ((rc = run_msm(ctx, h->plan, B, 2, h->res.p, work))) return rc;
     }
-    if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2))) return rc;
-    std::vector<Affine> xr(B * 2);
-    std::vector<Fr> dots(B * 2);
-    CK(D2H(xr.data(), h->aff.p, B * 2 * 64));
-    CK(D2H(dots.data(), h->dots.p, B * 2 * 32));
-    if (E) {                            // e <- head <$> oracle [X, R]  (src/Bulletproof.hs:351)
-        if ((rc = dtr_absorb_dev(h->dtr, h->aff.p, 2, 2))) return rc;
-        if ((rc = dtr_squeeze_first(h->dtr, 1))) return rc;
-        CK(D2H(E, h->dtr->chal.p, B * 32));
-    }
-    CK(ctx_sync(ctx));
-    for (size_t b = 0; b < B; b++) {
-        memcpy(X + 64 * b, &xr[2 * b], 64);
-        memcpy(R + 64 * b, &xr[2 * b + 1], 64);
-        h->sX[b] = dots[2 * b];
-        h->sR[b] = dots[2 * b + 1];
-    }
-    return BPPP_OK;
+    return to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2);
 }
 extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) { return nl_round_commit_impl(h, X, R, nullptr); }
 // The commitments of the round and, from the device transcript the argument continues (bppp_nl_create_trrp after
@@ -2362,6 +2374,7 @@ int nl_rebase_tensor(bppp_nl* h) {
 }
 }  // namespace
 
+static int nl_enqueue_fold(bppp_nl* h);
 extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
@@ -2416,14 +2429,26 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
         return rc;
     CK(H2D(cptr(h, C_KB), kk.data(), B * 4 * 32));
     CK(H2D(h->sgn.p, sg.data(), B * 2));
+    if (h->tensor && ((rc = upload_consts(h, C_A0N, a0n)) || (rc = upload_consts(h, C_B0N, b0n)) || (rc = upload_consts(h, C_A0L, bc)) ||
+                      (rc = upload_consts(h, C_B0L, b0l))))
+        return rc;
+    if ((rc = nl_enqueue_fold(h))) return rc;
+    CK(ctx_sync(ctx));   // host vectors above go out of scope
+    return BPPP_OK;
+}
+// The device work of a fold once the fold factors (C_AU .. C_BC, C_RHO, C_KB / C_KA / sgn, C_A0N .. C_B0L) are in
+// place: scalar vectors folded (with the next round's dot partials), fold coefficients updated (tensor mode) or
+// generators folded (fold mode), lengths halved.  No host synchronisation except where a large single argument
+// re-bases to tensor mode.
+static int nl_enqueue_fold(bppp_nl* h) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B;
+    int rc;
     // scalar vectors (and the next round's dots)
     if ((rc = launch_fold_dots(h, 1))) return rc;
     const size_t nN = (h->curN + 1) / 2, nM = (h->curM + 1) / 2;
     if (h->tensor) {
         // generators are not folded: update the per-generator fold coefficients instead
-        if ((rc = upload_consts(h, C_A0N, a0n)) || (rc = upload_consts(h, C_B0N, b0n)) || (rc = upload_consts(h, C_A0L, bc)) ||
-            (rc = upload_consts(h, C_B0L, b0l)))
-            return rc;
         for (int seg = 0; seg < 2; seg++) {
             const size_t n0 = seg ? h->tM : h->tN;
             if (!n0) continue;
@@ -2441,7 +2466,6 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
         h->tround++;
         if (hybrid_limit() && !h->tail_gens && !h->shard_lo && nN + nM <= hybrid_limit() && nN + nM >= 12 && h->round <= 9 && (rc = nl_switch_to_fold(h)))
             return rc;
-        CK(ctx_sync(ctx));
         return BPPP_OK;
     }
     // generators
@@ -2461,7 +2485,6 @@ extern "C" int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e) {
     h->curN = nN;
     h->curM = nM;
     h->round++;
-    CK(ctx_sync(ctx));   // host vectors above go out of scope
     if (B == 1 && !h->tail_gens && 1 + nN + nM <= rebase_limit() && nN + nM >= 16) return nl_rebase_tensor(h);
     return BPPP_OK;
 }
@@ -2481,6 +2504,99 @@ extern "C" int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
         if (w) for (size_t i = 0; i < cn; i++) h64::to_bytes(w + 32 * (b * cn + i), h64::mul(h->nn[b], hw[b * cn + i]));
         if (l) for (size_t i = 0; i < cl; i++) h64::to_bytes(l + 32 * (b * cl + i), h64::mul(h->nl[b], hl[b * cl + i]));
     }
+    return BPPP_OK;
+}
+
+// Bare arguments (bppp_nl_create / bppp_nl_create_gens): continue the device transcript `t` (same context, same batch;
+// not owned) -- e.g. after bppp_dtr_absorb of the initial commitment.  NULL detaches.
+extern "C" int bppp_nl_attach_transcript(bppp_nl* h, bppp_dtr* t) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    if (t && (t->ctx != ctx || t->B != h->B)) FAIL(BPPP_ERR_ARG, "bppp_nl_attach_transcript: transcript of another context / batch size");
+    h->dtr = t;
+    return BPPP_OK;
+}
+
+// proveBPM (src/Bulletproof.hs:357-359) for the whole batch as ONE stream of launches: per round the two
+// commitments, `oracle [X, R]` on the device transcript, rationalReduceScalar and the fold factors in
+// k_round_ratio / k_round_post (rounds.cuh), the folds -- no host synchronisation until the results are read.
+// The handle must be fresh (no round taken yet) and have a transcript (bppp_nl_create_trrp after the _tr phases, or
+// bppp_nl_attach_transcript).  responses = [batch][rounds][2] points and es = [batch][rounds] challenges (may be
+// NULL), NEWEST FIRST; s / w / l as bppp_nl_final.  Bit-identical to the step-by-step calls (tests).
+extern "C" int bppp_nl_prove_device(bppp_nl* h, size_t rounds, uint8_t* responses, uint8_t* es, uint8_t* s, uint8_t* w, uint8_t* l) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    if (!responses || rounds == 0 || rounds > 64) FAIL(BPPP_ERR_ARG, "bppp_nl_prove_device: bad argument");
+    if (h->kind != BPPP_ARG_NL) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_device: norm-linear arguments only");
+    if (!h->dtr) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_device: no device transcript attached");
+    if (h->round != 0 || h->have_partials || h->shard_lo) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_device: needs a fresh, unsharded argument");
+    ENTER(ctx);
+    const size_t B = h->B;
+    // the per-proof round state moves to the device
+    CK(H2D(cptr(h, C_Q), h->q.data(), B * 32)); CK(H2D(cptr(h, C_QINV), h->qinv.data(), B * 32));
+    CK(H2D(cptr(h, C_NN), h->nn.data(), B * 32)); CK(H2D(cptr(h, C_NL), h->nl.data(), B * 32));
+    CK(H2D(cptr(h, C_S), h->s.data(), B * 32));
+    CK(cudaMemsetAsync(cptr(h, C_COEF), 0, B * 8 * 32, ctx->st));
+    DBuf<Affine> resp;
+    DBuf<u256> esd, fin;
+    CK(resp.alloc(B * rounds * 2)); CK(esd.alloc(B * rounds));
+    RoundState S;
+    S.q = cptr(h, C_Q); S.qinv = cptr(h, C_QINV); S.nn = cptr(h, C_NN); S.nl = cptr(h, C_NL); S.s = cptr(h, C_S);
+    S.rho = cptr(h, C_RHO); S.k1 = cptr(h, C_K1); S.k2 = cptr(h, C_K2); S.coef = cptr(h, C_COEF);
+    S.au = cptr(h, C_AU); S.bu = cptr(h, C_BU); S.al = cptr(h, C_AL); S.bl = cptr(h, C_BL); S.ac = cptr(h, C_AC); S.bc = cptr(h, C_BC);
+    S.a0n = cptr(h, C_A0N); S.b0n = cptr(h, C_B0N); S.a0l = cptr(h, C_A0L); S.b0l = cptr(h, C_B0L);
+    S.kb = cptr(h, C_KB); S.ka = cptr(h, C_KA); S.sgn = h->sgn.p; S.inv = cptr(h, C_INV);
+    S.chal = h->dtr->chal.p; S.dots = h->dots.p; S.B = (int)B; S.tensor = 0;
+    int rc;
+    for (size_t r = 0; r < rounds; r++) {
+        if (h->curN + h->curM == 0) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_device: nothing left to fold");
+        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+        k_round_pre<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(S);
+        }
+        CK(cudaGetLastError());
+        if (!h->have_partials) {
+            if ((rc = launch_fold_dots(h, 0))) return rc;
+            h->have_partials = true;
+        }
+        if ((rc = nl_enqueue_commit(h))) return rc;
+        // responses are consed: newest first (Bulletproof.hs:357-359)
+        CK(cudaMemcpy2DAsync(resp.p + 2 * (rounds - 1 - r), rounds * 128, h->aff.p, 128, 128, B, cudaMemcpyDeviceToDevice, ctx->st));
+        // e <- head <$> oracle [X, R]  (Bulletproof.hs:351)
+        if ((rc = dtr_absorb_dev(h->dtr, h->aff.p, 2, 2))) return rc;
+        if ((rc = dtr_squeeze_first(h->dtr, 1))) return rc;
+        CK(cudaMemcpy2DAsync(esd.p + (rounds - 1 - r), rounds * 32, h->dtr->chal.p, 32, 32, B, cudaMemcpyDeviceToDevice, ctx->st));
+        S.tensor = h->tensor ? 1 : 0;
+        if (!S.tensor) {
+            ProfScope ps_(ctx, K_ROUND_STATE, 0);
+            k_round_ratio<<<(unsigned)((2 * B + 63) / 64), 64, 0, ctx->st>>>(S);
+        }
+        CK(cudaGetLastError());
+        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+        k_round_post<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(S);
+        }
+        CK(cudaGetLastError());
+        if ((rc = nl_enqueue_fold(h))) return rc;
+    }
+    // getWitness: the final vectors with their normalisations, and the opening scalar
+    const size_t cn = h->curN, cl = h->curM;
+    CK(fin.alloc(B * (1 + cn + cl)));
+    u256* fs = fin.p; u256* fw = fin.p + B; u256* fl = fw + B * cn;
+    struct { const u256* v; size_t stride; const u256* sc; size_t n; u256* out; } jobs[3] = {
+        {cptr(h, C_S), 1, nullptr, 1, fs}, {h->w[h->cur].p, h->wstride[h->cur], cptr(h, C_NN), cn, fw},
+        {h->l[h->cur].p, h->lstride[h->cur], cptr(h, C_NL), cl, fl}};
+    for (auto& j : jobs) {
+        if (!j.n) continue;
+        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+        k_scale_rows<<<(unsigned)((j.n * B + 127) / 128), 128, 0, ctx->st>>>(j.v, j.stride, j.sc, (int)j.n, (int)B, j.out);
+        }
+        CK(cudaGetLastError());
+    }
+    CK(D2H(responses, resp.p, B * rounds * 128));
+    if (es) CK(D2H(es, esd.p, B * rounds * 32));
+    if (s) CK(D2H(s, fs, B * 32));
+    if (w && cn) CK(D2H(w, fw, B * cn * 32));
+    if (l && cl) CK(D2H(l, fl, B * cl * 32));
+    CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 

@@ -948,10 +948,30 @@ int run_argument(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, size_t round
     bppp_nl* h = nullptr;
     int rc = device_witness ? bppp_nl_create_trrp(ln.trrp, q, sc, l, c, &h) : bppp_nl_create_gens(ln.gens, s->arg, B, q, sc, w, l, c, &h);
     if (rc) return fail(s, rc, std::string("bppp_nl_create: ") + ctx_err(ln));
+    g_tm.lap("nl_create");
+    const bool dev_rounds = !(getenv("BPPP_DEVICE_ROUNDS") && !atoi(getenv("BPPP_DEVICE_ROUNDS")));
+    if (device_transcript && dev_rounds && s->arg == BPPP_ARG_NL) {
+        // the whole argument as one stream of launches (bppp_nl_prove_device): no per-round host work at all
+        size_t cn = 0, cl = 0;
+        lengths_after(s->nrm_len, s->lin_len, rounds, cn, cl);
+        if (cn != fin_n || cl != fin_l) { bppp_nl_destroy(h); return fail(s, BPPP_ERR_STATE, "final witness lengths differ from infoRP"); }
+        uint8_t* fw = lane_buf(s, ln, PB_X, B * cn * 32 + 32);
+        uint8_t* fl = lane_buf(s, ln, PB_R, B * cl * 32 + 32);
+        rc = bppp_nl_prove_device(h, rounds, responses, nullptr, nullptr, fw, fl);
+        bppp_nl_destroy(h);
+        g_tm.lap("nl_rounds_device");
+        g_tm.dump("prove");
+        if (t_lane_threads_is_main()) dump_sections("prove, all lanes", B);
+        if (rc) return fail(s, rc, std::string("bppp_nl_prove_device: ") + ctx_err(ln));
+        for (size_t b = 0; b < B; b++) {       // getWitness: norm scalars then linear scalars (RangeProof.hs:65)
+            memcpy(finals + 32 * b * (cn + cl), &fw[32 * b * cn], 32 * cn);
+            memcpy(finals + 32 * (b * (cn + cl) + cn), &fl[32 * b * cl], 32 * cl);
+        }
+        return BPPP_OK;
+    }
     uint8_t* X = lane_buf(s, ln, PB_X, B * 64);
     uint8_t* R = lane_buf(s, ln, PB_R, B * 64);
     uint8_t* E = lane_buf(s, ln, PB_E, B * 32);
-    g_tm.lap("nl_create");
     for (size_t r = 0; r < rounds; r++) {
         rc = device_transcript ? bppp_nl_round_challenge(h, X, R, E) : bppp_nl_round_commit(h, X, R);
         g_tm.lap("nl_commit");

@@ -10,6 +10,13 @@
 #include <vector>
 #include "fp.cuh"
 
+// the big-integer helpers and rationalReduceScalar also run on the device (the device-resident round loop)
+#ifdef __CUDACC__
+#define BP_HDN __host__ __device__ inline
+#else
+#define BP_HDN inline
+#endif
+
 namespace bppp {
 namespace host {
 
@@ -66,30 +73,34 @@ struct SBig {               // magnitude in 5 x 64-bit limbs (< 2^320), sign
     uint64_t m[5];
     bool neg;
 };
-inline SBig sb_from_u256(const u256& a, bool neg) {
+BP_HDN SBig sb_from_u256(const u256& a, bool neg) {
     SBig r;
     for (int i = 0; i < 4; i++) r.m[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
     r.m[4] = 0;
     r.neg = neg;
     return r;
 }
-inline u256 sb_to_u256(const SBig& a) {
+BP_HDN u256 sb_to_u256(const SBig& a) {
     u256 r;
     for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)a.m[i]; r.v[2 * i + 1] = (uint32_t)(a.m[i] >> 32); }
     return r;
 }
-inline bool sb_is_zero(const SBig& a) { return !(a.m[0] | a.m[1] | a.m[2] | a.m[3] | a.m[4]); }
-inline int sb_bitlen(const SBig& a) {
+BP_HDN bool sb_is_zero(const SBig& a) { return !(a.m[0] | a.m[1] | a.m[2] | a.m[3] | a.m[4]); }
+BP_HDN int sb_bitlen(const SBig& a) {
     for (int i = 4; i >= 0; i--)
+#ifdef __CUDA_ARCH__
+        if (a.m[i]) return 64 * i + 64 - __clzll((long long)a.m[i]);
+#else
         if (a.m[i]) return 64 * i + 64 - __builtin_clzll(a.m[i]);
+#endif
     return 0;
 }
-inline int sb_cmp_mag(const SBig& a, const SBig& b) {
+BP_HDN int sb_cmp_mag(const SBig& a, const SBig& b) {
     for (int i = 4; i >= 0; i--)
         if (a.m[i] != b.m[i]) return a.m[i] < b.m[i] ? -1 : 1;
     return 0;
 }
-inline void sb_sub_mag(SBig& r, const SBig& a, const SBig& b) {   // |a| >= |b|
+BP_HDN void sb_sub_mag(SBig& r, const SBig& a, const SBig& b) {   // |a| >= |b|
     u128 br = 0;
     for (int i = 0; i < 5; i++) {
         u128 d = (u128)a.m[i] - b.m[i] - br;
@@ -97,7 +108,7 @@ inline void sb_sub_mag(SBig& r, const SBig& a, const SBig& b) {   // |a| >= |b|
         br = (d >> 127) & 1;
     }
 }
-inline void sb_add_mag(SBig& r, const SBig& a, const SBig& b) {
+BP_HDN void sb_add_mag(SBig& r, const SBig& a, const SBig& b) {
     u128 c = 0;
     for (int i = 0; i < 5; i++) {
         c += (u128)a.m[i] + b.m[i];
@@ -105,7 +116,7 @@ inline void sb_add_mag(SBig& r, const SBig& a, const SBig& b) {
         c >>= 64;
     }
 }
-inline SBig sb_shl(const SBig& a, int s) {
+BP_HDN SBig sb_shl(const SBig& a, int s) {
     SBig r;
     r.neg = a.neg;
     int w = s / 64, b = s % 64;
@@ -120,7 +131,7 @@ inline SBig sb_shl(const SBig& a, int s) {
     return r;
 }
 // a - b with signs
-inline SBig sb_sub(const SBig& a, const SBig& b) {
+BP_HDN SBig sb_sub(const SBig& a, const SBig& b) {
     SBig r;
     if (a.neg != b.neg) {            // a - b = a + (-b): same sign as a, magnitudes add
         sb_add_mag(r, a, b);
@@ -135,7 +146,7 @@ inline SBig sb_sub(const SBig& a, const SBig& b) {
 }
 // one Euclid step with Haskell `quot` semantics:  q = n quot d;  (n, ns) -= q * (d, ds)
 // implemented as shift-subtract on magnitudes, applying the same steps to the cofactors.
-inline void euclid_step(SBig& n, SBig& ns, const SBig& d, const SBig& ds) {
+BP_HDN void euclid_step(SBig& n, SBig& ns, const SBig& d, const SBig& ds) {
     // remainder keeps the sign of n; |n| -= k*2^s*|d| for the bits of |q|
     bool qneg = (n.neg != d.neg);
     int sh = sb_bitlen(n) - sb_bitlen(d);
@@ -155,7 +166,7 @@ inline void euclid_step(SBig& n, SBig& ns, const SBig& d, const SBig& ds) {
 // The same step with the quotient taken in one go (Knuth D with a 64-bit divisor digit): the
 // estimate from the leading 64 bits of d is at most 2 too large.  Falls back to the bitwise step
 // when the quotient may not fit 63 bits (only for tiny inputs).
-inline bool sb_mulsub_small(SBig& n, const SBig& d, uint64_t q) {      // |n| -= q*|d|; true if it went negative
+BP_HDN bool sb_mulsub_small(SBig& n, const SBig& d, uint64_t q) {      // |n| -= q*|d|; true if it went negative
     u128 carry = 0;
     uint64_t borrow = 0;
     for (int i = 0; i < 5; i++) {
@@ -171,7 +182,7 @@ inline bool sb_mulsub_small(SBig& n, const SBig& d, uint64_t q) {      // |n| -=
     }
     return borrow || carry;
 }
-inline void sb_addmul_small(SBig& r, const SBig& a, uint64_t q) {      // |r| += q*|a|
+BP_HDN void sb_addmul_small(SBig& r, const SBig& a, uint64_t q) {      // |r| += q*|a|
     u128 carry = 0;
     for (int i = 0; i < 5; i++) {
         carry += (u128)a.m[i] * q + r.m[i];
@@ -179,7 +190,7 @@ inline void sb_addmul_small(SBig& r, const SBig& a, uint64_t q) {      // |r| +=
         carry >>= 64;
     }
 }
-inline void euclid_step_fast(SBig& n, SBig& ns, const SBig& d, const SBig& ds) {
+BP_HDN void euclid_step_fast(SBig& n, SBig& ns, const SBig& d, const SBig& ds) {
     const int bn = sb_bitlen(n), bd = sb_bitlen(d);
     if (bn < bd) return;                                   // quotient 0
     if (bn - bd > 61 || bd == 0) { euclid_step(n, ns, d, ds); return; }
@@ -234,7 +245,7 @@ struct Ratio {              // a = b * x (mod r), |a|,|b| about sqrt(r)
     bool a_neg, b_neg;
 };
 // x canonical (non-Montgomery) in [0, r)
-inline Ratio rational_reduce(const u256& x) {
+BP_HDN Ratio rational_reduce(const u256& x) {
     const u256 r = fr::modulus();
     // centred lift (src/Commitment.hs:276-279): n > r - n  ->  -(r - n)
     u256 rm;
@@ -282,7 +293,7 @@ inline Ratio rational_reduce(const u256& x) {
     return o;
 }
 // signed small integer -> Fr (Montgomery)
-inline u256 fr_from_signed(const u256& mag, bool neg) {
+BP_HDN u256 fr_from_signed(const u256& mag, bool neg) {
     u256 m = fr::to_mont(mag);
     return neg ? fr::neg(m) : m;
 }

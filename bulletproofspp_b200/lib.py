@@ -26,6 +26,7 @@ EXPORTS = [
     "bppp_trrp_create", "bppp_trrp_destroy", "bppp_trrp_phase1", "bppp_trrp_phase2", "bppp_trrp_phase3", "bppp_trrp_commit_bl",
     "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
     "bppp_dtr_absorb", "bppp_dtr_squeeze", "bppp_dtr_fits", "bppp_dtr_export", "bppp_rp_set_device_transcript", "bppp_nl_round_challenge",
+    "bppp_nl_attach_transcript", "bppp_nl_prove_device",
     "bppp_trrp_set_transcript", "bppp_trrp_phase1_tr", "bppp_trrp_phase2_tr", "bppp_trrp_phase3_rnd", "bppp_trrp_commit_bl_tr",
 ]
 
@@ -133,6 +134,8 @@ def load_library():
     lib.bppp_dtr_export.argtypes = [vp, sz, u8p, sz, C.POINTER(sz)]
     lib.bppp_rp_set_device_transcript.argtypes = [vp, ip]
     lib.bppp_nl_round_challenge.argtypes = [vp, u8p, u8p, u8p]
+    lib.bppp_nl_attach_transcript.argtypes = [vp, vp]
+    lib.bppp_nl_prove_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, u8p]
     lib.bppp_tune_process.argtypes = [ip]
     # this harness drives dedicated batch-proving processes (tests, bench.py): opt in to the process-wide
     # tuning (malloc arenas, blocking-sync device flags, pool pre-growth); BPPP_NO_TUNE=1 leaves the process alone

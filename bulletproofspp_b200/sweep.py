@@ -33,6 +33,29 @@ def _prove(ctx, gens, inp, C0):
     return dict(ms=ms, wall_ms=1e3 * wall, resp=resp.raw[:128 * k], es=es.raw[:32 * k], fw=fw.raw[:128], fl=fl.raw[:32])
 
 
+def _prove_device(ctx, gens, inp, C0):
+    """the same proof with the whole round loop on the device (bppp_nl_prove_device): the transcript (the initial
+    commitment, then every round's X, R) is rendered and hashed there, rationalReduceScalar and the fold factors
+    run in k_round_* -- one stream of launches, one synchronisation"""
+    lib, k = ctx.lib, inp["rounds"]
+    h, t = C.c_void_p(), C.c_void_p()
+    ctx._ck(lib.bppp_nl_create_gens(gens, ARG_NL, 1, inp["q"], inp["s"], inp["w"], inp["l"], inp["c"], C.byref(h)), "bppp_nl_create_gens")
+    ctx._ck(lib.bppp_dtr_create(ctx.h, 1, 1 + 2 * k, 0, C.byref(t)), "bppp_dtr_create")
+    resp, es = C.create_string_buffer(128 * k), C.create_string_buffer(32 * k)
+    s_out, fw, fl = C.create_string_buffer(32), C.create_string_buffer(32 * 4), C.create_string_buffer(32)
+    ctx.sync()
+    ctx.timer_start()
+    t0 = time.time()
+    ctx._ck(lib.bppp_dtr_absorb(t, C0, 1, 1), "bppp_dtr_absorb")
+    ctx._ck(lib.bppp_nl_attach_transcript(h, t), "bppp_nl_attach_transcript")
+    ctx._ck(lib.bppp_nl_prove_device(h, k, resp, es, s_out, fw, fl), "bppp_nl_prove_device")
+    ms = ctx.timer_stop()
+    wall = time.time() - t0
+    lib.bppp_nl_destroy(h)
+    lib.bppp_dtr_destroy(t)
+    return dict(ms=ms, wall_ms=1e3 * wall, resp=resp.raw[:128 * k], es=es.raw[:32 * k], fw=fw.raw[:128], fl=fl.raw[:32])
+
+
 def _verify(ctx, gens, inp, C0, pr):
     lib, k, N = ctx.lib, inp["rounds"], inp["N"]
     es = C.create_string_buffer(32 * k)
@@ -65,9 +88,13 @@ def run_one(ctx, e, points, imad_wide, hbm_gbs, reps=2, M=6):
     C0 = C0b.raw[:64]
     setup_s = time.time() - t0
     _prove(ctx, gens, inp, C0)                                   # warm-up (pools, lazily loaded kernels)
-    proves = [_prove(ctx, gens, inp, C0) for _ in range(reps)]
-    assert all(p["resp"] == proves[0]["resp"] and p["fw"] == proves[0]["fw"] for p in proves), "prover is not deterministic"
+    hosts = [_prove(ctx, gens, inp, C0) for _ in range(reps)]     # reference arrangement: transcript + round constants on the host
+    _prove_device(ctx, gens, inp, C0)
+    proves = [_prove_device(ctx, gens, inp, C0) for _ in range(reps)]
+    assert all(p["resp"] == hosts[0]["resp"] and p["fw"] == hosts[0]["fw"] and p["fl"] == hosts[0]["fl"] and p["es"] == hosts[0]["es"]
+               for p in proves + hosts), "device round loop and host sequencing disagree"
     pr = min(proves, key=lambda p: p["ms"])
+    ph = min(hosts, key=lambda p: p["ms"])
     _verify(ctx, gens, inp, C0, pr)
     verifies = [_verify(ctx, gens, inp, C0, pr) for _ in range(reps)]
     vr = min(verifies, key=lambda v: v["ms"])
@@ -77,7 +104,7 @@ def run_one(ctx, e, points, imad_wide, hbm_gbs, reps=2, M=6):
     # one more prove + verify with a CUDA-event pair around every launch: per-kernel times and algorithmic work
     ctx.profile_enable(True)
     ctx.profile_reset()
-    pp = _prove(ctx, gens, inp, C0)
+    pp = _prove_device(ctx, gens, inp, C0)
     rep_p = ctx.profile_report()["kernels"]
     ctx.profile_reset()
     _verify(ctx, gens, inp, C0, pp)
@@ -85,7 +112,8 @@ def run_one(ctx, e, points, imad_wide, hbm_gbs, reps=2, M=6):
     ctx.profile_enable(False)
     lib.bppp_gens_destroy(gens)
     out = {"e": e, "N": N, "M": M, "rounds": inp["rounds"], "final": [4, 1], "setup_s": round(setup_s, 3),
-           "prove_ms": round(pr["ms"], 3), "prove_wall_ms": round(pr["wall_ms"], 3), "verify_ms": round(vr["ms"], 3),
+           "prove_ms": round(pr["ms"], 3), "prove_wall_ms": round(pr["wall_ms"], 3),
+           "prove_host_sequenced_ms": round(ph["ms"], 3), "verify_ms": round(vr["ms"], 3),
            "verify_wall_ms": round(vr["wall_ms"], 3), "verifies": all(v["ok"] for v in verifies), "rejects_tampered": rejected,
            "proofs_per_s": round(1e3 / (pr["ms"] + vr["ms"]), 3)}
     kms = {n: round(v["ms"], 3) for n, v in sorted(rep_p.items(), key=lambda kv: -kv[1]["ms"])}
@@ -129,8 +157,10 @@ def run(ctx, sizes, imad_wide, hbm_gbs, reps=2):
     gen_s = time.time() - t0
     res = {"generators": {"count": 1 + (1 << sizes[-1]) + 6, "derive_s": round(gen_s, 3),
                           "how": "getPoints \"test points\" (app/Main.hs:68-72) on the device, bppp_get_points"},
-           "note": "one NormLinear argument per size, N = 2^e, M = 6; prove = bppp_nl_prove + bppp_nl_final (reference transcript on the "
-                   "host), verify = bppp_nl_challenges + bppp_nl_verify_gens; *_ms = CUDA events on the library's stream around the whole "
+           "note": "one NormLinear argument per size, N = 2^e, M = 6; prove = bppp_dtr_absorb (initial commitment) + bppp_nl_prove_device "
+                   "(round loop, transcript and round constants on the device, one synchronisation); prove_host_sequenced = the same proof "
+                   "(asserted bit-identical) by bppp_nl_prove + bppp_nl_final with the transcript and round constants on the host, two "
+                   "synchronisations per round; verify = bppp_nl_challenges + bppp_nl_verify_gens; *_ms = CUDA events on the library's stream around the whole "
                    "call sequence (witness / generators resident), best of %d; rooflines from one extra profiled pass; msm_* = algorithmic "
                    "IMADs of SURVEY 8(d) over all MSM kernels of the side" % reps,
            "sizes": []}

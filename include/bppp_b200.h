@@ -149,6 +149,13 @@ int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R);
 /* the same plus E = [batch] challenges  e <- head <$> oracle [X, R]  (Bulletproof.hs:351) from the device
  * transcript the argument continues (arguments made by bppp_nl_create_trrp after bppp_trrp_*_tr calls) */
 int bppp_nl_round_challenge(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E);
+/* proveBPM (Bulletproof.hs:357-359) as one stream of launches: commitments, `oracle [X, R]` on the device
+ * transcript, rationalReduceScalar and the fold factors (rounds.cuh), folds -- a single synchronisation at the end.
+ * Fresh norm-linear handle with a transcript (from bppp_nl_create_trrp after the _tr phases, or attached with
+ * bppp_nl_attach_transcript, e.g. after bppp_dtr_absorb of the initial commitment).  responses = [batch][rounds][2]
+ * points and es = [batch][rounds] challenges (may be NULL), newest first; s / w / l as bppp_nl_final. */
+int bppp_nl_attach_transcript(bppp_nl* h, bppp_dtr* t);
+int bppp_nl_prove_device(bppp_nl* h, size_t rounds, uint8_t* responses, uint8_t* es, uint8_t* s, uint8_t* w, uint8_t* l);
 /* the rest of proveRoundM (src/Bulletproof.hs:351-355): s' = s + e0*sX + e1*sR and `collapse e`
  * (NormArgument.hs:64-71,123-129 / InnerProductArgument.hs:86-101,155-170) with challenge e[b]. */
 int bppp_nl_round_fold(bppp_nl* h, const uint8_t* e);

@@ -265,6 +265,49 @@ def test_sweep_workload_rounds_and_verify(ctx, gens):
     arg.close()
 
 
+@pytest.mark.parametrize("e", [5, 10, 13])
+def test_device_round_loop_matches_host_sequencing(ctx, e):
+    """bppp_nl_prove_device (transcript, rationalReduceScalar and fold factors on the device, one synchronisation)
+    against bppp_nl_prove + bppp_nl_final (host transcript, host round constants): responses, challenges, final
+    witness and opening scalar bit for bit.  e = 5, 10: tensor mode; e = 13 (8199 generators): fold mode with
+    pair folds, size-aware Pippenger and the re-base to tensor mode of the tail."""
+    import ctypes as C
+    from bulletproofspp_b200 import sweep, workloads as W
+    from bulletproofspp_b200.lib import ARG_NL
+    lib = ctx.lib
+    N, M = 1 << e, 6
+    points = W.sweep_generators(ctx, 1 + N + M)
+    inp = W.sweep_inputs(ctx, e, M)
+    k = inp["rounds"]
+    gens_h = C.c_void_p()
+    ctx._ck(lib.bppp_gens_create(ctx.h, N, M, points[:64], points[64:64 * (1 + N)], points[64 * (1 + N):], C.byref(gens_h)), "bppp_gens_create")
+    C0b = C.create_string_buffer(64)
+    ctx._ck(lib.bppp_gens_msm_batch(gens_h, 1, 1 + N + M, inp["s"] + inp["w"] + inp["l"], C0b), "bppp_gens_msm_batch")
+    C0 = C0b.raw[:64]
+    host = sweep._prove(ctx, gens_h, inp, C0)
+    dev = sweep._prove_device(ctx, gens_h, inp, C0)
+    for key in ("resp", "es", "fw", "fl"):
+        assert dev[key] == host[key], key
+    # the opening scalar too (bppp_nl_final's s against bppp_nl_prove_device's)
+    h, t = C.c_void_p(), C.c_void_p()
+    ctx._ck(lib.bppp_nl_create_gens(gens_h, ARG_NL, 1, inp["q"], inp["s"], inp["w"], inp["l"], inp["c"], C.byref(h)), "create")
+    resp, s1, s2 = C.create_string_buffer(128 * k), C.create_string_buffer(32), C.create_string_buffer(32)
+    ctx._ck(lib.bppp_nl_prove(h, 1, 0, 1, C0, k, resp, None), "bppp_nl_prove")
+    ctx._ck(lib.bppp_nl_final(h, s1, None, None), "bppp_nl_final")
+    lib.bppp_nl_destroy(h)
+    ctx._ck(lib.bppp_nl_create_gens(gens_h, ARG_NL, 1, inp["q"], inp["s"], inp["w"], inp["l"], inp["c"], C.byref(h)), "create")
+    ctx._ck(lib.bppp_dtr_create(ctx.h, 1, 1 + 2 * k, 0, C.byref(t)), "bppp_dtr_create")
+    ctx._ck(lib.bppp_dtr_absorb(t, C0, 1, 1), "bppp_dtr_absorb")
+    # without a transcript the device loop refuses to run
+    assert lib.bppp_nl_prove_device(h, k, resp, None, s2, None, None) != 0
+    ctx._ck(lib.bppp_nl_attach_transcript(h, t), "attach")
+    ctx._ck(lib.bppp_nl_prove_device(h, k, resp, None, s2, None, None), "bppp_nl_prove_device")
+    assert s1.raw == s2.raw and resp.raw[:128 * k] == host["resp"]
+    lib.bppp_nl_destroy(h)
+    lib.bppp_dtr_destroy(t)
+    lib.bppp_gens_destroy(gens_h)
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_argument_equals_unsharded(ctx, gens, world):
     """one argument split into `world` contiguous shards (emulated as `world` handles on

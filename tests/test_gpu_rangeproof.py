@@ -159,12 +159,16 @@ def test_device_scalar_phases_match_host_phases(ctx, name, monkeypatch):
     host.close()
 
 
+@pytest.mark.parametrize("rounds_on_device", ["1", "0"])
 @pytest.mark.parametrize("name,count", [("typed_nl", 1), ("32by64", 70), ("128by64", 3)])
-def test_device_transcript_is_bit_identical(ctx, name, count):
+def test_device_transcript_is_bit_identical(ctx, name, count, rounds_on_device, monkeypatch):
     """with bppp_rp_set_device_transcript the commitments are rendered (`show`) and hashed
     (shaOracle) on the device and the norm blinders drawn there; the proofs must equal the host-transcript
     ones bit for bit (and the golden vectors), verification must accept them and reject tampering."""
     import bulletproofspp_b200 as bp
+    # BPPP_DEVICE_ROUNDS=0: per-round challenges from the device, round constants on the host
+    # (bppp_nl_round_challenge); default: the whole round loop on the device (bppp_nl_prove_device)
+    monkeypatch.setenv("BPPP_DEVICE_ROUNDS", rounds_on_device)
     schema, wits, seeds = batched(name, count)
     host = bp.RangeProofSetup(ctx, schema)
     dev = bp.RangeProofSetup(ctx, schema)
