@@ -182,6 +182,8 @@ def main():
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--sweep-sizes", default="10,14,18,20", help="log2 N of the synthetic norm-argument sweep (N=1 only)")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--verify", default="batch", choices=["batch", "per-proof"],
+                    help="batch: one random linear combination per lane sub-batch, per-proof checks only on failure (exact verdicts)")
     ap.add_argument("--transcript", default="device", choices=["device", "host"],
                     help="where the Fiat-Shamir transcript of the batch prover / verifier runs (bit-identical proofs either way)")
     args = ap.parse_args()
@@ -211,6 +213,7 @@ def main():
     dev_tr = args.transcript == "device"
     setup.set_device_transcript(dev_tr)
     vsetup.set_device_transcript(dev_tr)
+    vsetup.set_batch_verify(args.verify == "batch")
     lanes = setup.contexts() + vsetup.contexts()
     B, n = args.batch, setup.n_inputs
     assert (setup.nrm_len, setup.lin_len, setup.rounds) == (1024, 261, 9)
@@ -315,6 +318,7 @@ def main():
     pctx = bp.Context(local)
     psetup = bp.RangeProofSetup(pctx, workload_schema())
     psetup.set_device_transcript(dev_tr)
+    psetup.set_batch_verify(args.verify == "batch")
     pin = make_inputs(Bp, base, n)
     proof = psetup.prove_batch_raw(Bp, pin[0], pin[1], None, pin[2])            # warm-up (tables, pools)
     pctx.profile_enable(True)
@@ -384,6 +388,9 @@ def main():
                        "batch_per_gpu": B, "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "working set per step (%.0f MB of generators+witness vectors) exceeds the 126 MB L2" % (B * 0.33),
                        "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world), "lanes": len(lanes),
+                       "verify": "batch verification across proofs: one random linear combination per lane sub-batch of %d proofs (128-bit "
+                                 "weights from getrandom), per-proof checks locate failures (SURVEY 8 f2)" % max(1, B // (len(lanes) // 2))
+                                 if args.verify == "batch" else "per proof (the reference's verifyM)",
                        "transcript": "device (SHA-256 + decimal show of the commitments in k_tr_prepend / k_tr_squeeze, challenges "
                                      "bit-identical to the host transcript; SURVEY 8 f4)" if dev_tr else "host (the reference's arrangement)",
                        "extra_warmup_steps": extra_warmup},

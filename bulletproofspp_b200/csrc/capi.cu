@@ -26,13 +26,13 @@ using namespace bppp;
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_TR_POINTS, K_TR_RENDER, K_TR_SQUEEZE, K_TR_RANDOM, K_ROUND_STATE, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_TR_POINTS, K_TR_RENDER, K_TR_SQUEEZE, K_TR_RANDOM, K_ROUND_STATE, K_BATCH_WEIGHT, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
                                                    "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce", "k_check_points",
                                                    "k_pip_sort", "k_pip_accum", "k_pip_merge", "k_pip_reduce", "k_pip_horner",
-                                                   "k_hash_to_curve", "k_tr_render", "k_tr_squeeze", "k_tr_random", "k_round_state"};
+                                                   "k_hash_to_curve", "k_tr_render", "k_tr_squeeze", "k_tr_random", "k_round_state", "k_batch_weight"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -2605,10 +2605,11 @@ namespace {
 int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
                    const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR, size_t n_norm,
                    size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init, const uint8_t* init_s,
-                   const uint8_t* init_p, int* ok, const u256* pub_dev = nullptr) {
+                   const uint8_t* init_p, int* ok, const u256* pub_dev = nullptr, const uint8_t* weights = nullptr) {
     bppp_ctx* ctx = gens->ctx;
     const size_t N = gens->N, M = gens->M;
     const size_t B = batch, P0 = 1 + N + M, NX = n_init + 2 * k;
+    if (weights && !check_fr(weights, B)) FAIL(BPPP_ERR_RANGE, "batch weight >= group order");
     if (k > 30) FAIL(BPPP_ERR_ARG, "too many rounds");
     {   // the final witness has exactly the lengths k rounds leave (roundReduce, src/Bulletproof.hs:300-304; the
         // reference's decodeProof' derives them from the setup, src/RangeProof.hs:70-71): a surplus final scalar
@@ -2769,7 +2770,53 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     });
     ctx->h2d += B * 32;
     CK(cudaMemcpy2DAsync(sc.p, P0 * 32, s0.data(), 32, 32, B, cudaMemcpyHostToDevice, ctx->st));
-    int rc = run_msm_gens(gens, P0, sc.p, P0, 0, B, 1, res.p, msm_alg_imads((double)(P0 + NX)));
+    int rc;
+    if (weights && B > 1) {
+        // Batch verification across proofs: sum_b rho_b (sum_i sc[b][i] G_i + sum_j xsc[b][j] P[b][j]) = 0 -- ONE fixed-base
+        // MSM over the shared generators with the weighted column sums, ONE Pippenger over all B * NX per-proof points.
+        // A pass accepts every proof of the batch (a false proof survives with probability ~2^-128 over the weights);
+        // a failure says nothing about which proof is bad, so it falls through to the per-proof checks below.
+        DBuf<u256> rho, wsc, wx;
+        DBuf<Jac> r1, r2;
+        DBuf<Affine> a1;
+        CK(rho.alloc(B)); CK(wsc.alloc(P0)); CK(wx.alloc(B * std::max<size_t>(NX, 1))); CK(r1.alloc(3)); CK(a1.alloc(1));
+        CK(H2D(rho.p, weights, B * 32));
+        { ProfScope ps_(ctx, K_FR_CONVERT, 0);
+        k_fr_convert<<<(unsigned)((B + 255) / 256), 256, 0, ctx->st>>>(rho.p, rho.p, B, 1);
+        }
+        CK(cudaGetLastError());
+        { ProfScope ps_(ctx, K_BATCH_WEIGHT, 0);
+        k_weight_columns<<<(unsigned)P0, WCOL_THREADS, 0, ctx->st>>>(sc.p, P0, rho.p, (int)B, wsc.p);
+        }
+        CK(cudaGetLastError());
+        if ((rc = run_msm_gens(gens, P0, wsc.p, P0, 0, 1, 1, r1.p, msm_alg_imads((double)P0)))) return rc;
+        if (NX) {
+            { ProfScope ps_(ctx, K_BATCH_WEIGHT, 0);
+            k_weight_rows<<<(unsigned)((B * NX + 255) / 256), 256, 0, ctx->st>>>(xsc.p, rho.p, (int)NX, B * NX, wx.p);
+            }
+            CK(cudaGetLastError());
+            MsmPlan plan;
+            plan.add(extra.p, 0, wx.p, 0, 0, B * NX);
+            if ((rc = run_msm(ctx, plan, 1, 1, r1.p + 1, msm_alg_imads((double)(B * NX))))) return rc;
+            { ProfScope ps_(ctx, K_JAC_SUM, 0);
+            k_jac_sum<<<1, 128, 0, ctx->st>>>(r1.p, 1, r1.p + 1, 1, r1.p + 2, 1);
+            }
+            CK(cudaGetLastError());
+        }
+        if ((rc = to_affine(ctx, NX ? r1.p + 2 : r1.p, 1, a1.p, 1, 0, 1, 1))) return rc;
+        Affine total;
+        std::vector<int> bad(B, 0);
+        CK(D2H(&total, a1.p, 64));
+        if (NX) CK(D2H(bad.data(), offcurve.p, B * sizeof(int)));
+        CK(ctx_sync(ctx));
+        bool all_ok = aff_is_inf(total);
+        for (size_t b = 0; b < B; b++) all_ok = all_ok && !bad[b];
+        if (all_ok) {
+            for (size_t b = 0; b < B; b++) ok[b] = 1;
+            return BPPP_OK;
+        }
+    }
+    rc = run_msm_gens(gens, P0, sc.p, P0, 0, B, 1, res.p, msm_alg_imads((double)(P0 + NX)));
     if (rc) return rc;
     if (NX) {
         MsmPlan plan;
@@ -2831,6 +2878,39 @@ extern "C" int bppp_nl_verify_trrp(bppp_trrp* h, size_t k, const uint8_t* q, con
     ENTER(ctx);
     h->phase = 0;
     return nl_verify_impl(h->gens, BPPP_ARG_NL, h->B, k, q, s_pub, nullptr, c, es, XR, n_norm, n_lin, fw, fl, n_init, init_s, init_p, ok, h->w.p);
+}
+
+// Batch verification across proofs: the same inputs plus weights = [batch] scalars the caller drew at
+// random AFTER seeing the proofs (128 bits are enough).  One combined check; all-accept sets every ok[b] = 1, a
+// failure is resolved by the per-proof checks, so the verdicts are always exact per proof.
+extern "C" int bppp_nl_verify_trrp_rlc(bppp_trrp* h, size_t k, const uint8_t* q, const uint8_t* s_pub, const uint8_t* c,
+                                       const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin, const uint8_t* fw,
+                                       const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p,
+                                       const uint8_t* weights, int* ok) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (h->phase != 10) FAIL(BPPP_ERR_STATE, "bppp_nl_verify_trrp: call bppp_trrp_verify_pub first");
+    if (!q || !s_pub || !ok || !weights || (h->gens->M && !c) || (k && (!es || !XR)) || (n_norm && !fw) || (n_lin && !fl) ||
+        (n_init && (!init_s || !init_p)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_verify_trrp_rlc: null argument");
+    ENTER(ctx);
+    h->phase = 0;
+    return nl_verify_impl(h->gens, BPPP_ARG_NL, h->B, k, q, s_pub, nullptr, c, es, XR, n_norm, n_lin, fw, fl, n_init, init_s, init_p, ok,
+                          h->w.p, weights);
+}
+extern "C" int bppp_nl_verify_gens_rlc(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
+                                       const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR,
+                                       size_t n_norm, size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init,
+                                       const uint8_t* init_s, const uint8_t* init_p, const uint8_t* weights, int* ok) {
+    if (!gens) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = gens->ctx;
+    if (kind != BPPP_ARG_NL && kind != BPPP_ARG_IP) FAIL(BPPP_ERR_ARG, "bppp_nl_verify: unknown argument kind");
+    if (!q || !s_pub || !ok || !weights || batch == 0 || (gens->N && !pub_w) || (gens->M && !c) || (k && (!es || !XR)) ||
+        (n_norm && !fw) || (n_lin && !fl) || (n_init && (!init_s || !init_p)))
+        FAIL(BPPP_ERR_ARG, "bppp_nl_verify_gens_rlc: null/empty argument");
+    if (k > 30) FAIL(BPPP_ERR_ARG, "too many rounds");
+    ENTER(ctx);
+    return nl_verify_impl(gens, kind, batch, k, q, s_pub, pub_w, c, es, XR, n_norm, n_lin, fw, fl, n_init, init_s, init_p, ok, nullptr, weights);
 }
 
 extern "C" int bppp_nl_verify_gens(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,

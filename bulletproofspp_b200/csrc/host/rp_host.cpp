@@ -24,6 +24,7 @@
 #include <dlfcn.h>
 #include <signal.h>
 #include <sys/time.h>
+#include <sys/random.h>
 #include <ucontext.h>
 #include <map>
 #include <condition_variable>
@@ -342,6 +343,8 @@ struct bppp_rp {
     // commitments are rendered and hashed where they are produced, the host only reads the challenges.
     // Needs the device scalar phases; bit-identical to the host transcript (tests).
     bool dev_transcript = false;
+    // verify a lane's sub-batch by one random linear combination first, per-proof checks only if it fails
+    bool batch_verify = false;
     std::vector<bppp_dtr*> lane_vtr;           // verifier transcripts, one per lane (created on first use)
     std::mutex err_mu;
     std::string err;
@@ -1240,12 +1243,21 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
             s->dev_transcript = dv && atoi(dv);
         }
     }
+    {
+        const char* bv = getenv("BPPP_BATCH_VERIFY");
+        s->batch_verify = bv && atoi(bv);
+    }
     *out = s;
     return BPPP_OK;
 }
 // Fiat-Shamir transcript of bppp_rp_prove_batch / bppp_rp_verify_batch on the device (on != 0) or on the host
 // (default; app/Main.hs:75-80, src/ZKP.hs:96-101).  Proofs and verdicts are bit-identical either way.  Only setups
 // that run the device scalar phases (TypedReciprocal over the norm-linear argument) can move it.
+int bppp_rp_set_batch_verify(bppp_rp* s, int on) {
+    if (!s) return BPPP_ERR_ARG;
+    s->batch_verify = on != 0;
+    return BPPP_OK;
+}
 int bppp_rp_set_device_transcript(bppp_rp* s, int on) {
     if (!s) return BPPP_ERR_ARG;
     if (on && !s->dev_phases) return fail(s, BPPP_ERR_STATE, "device transcript needs the device scalar phases");
@@ -1899,6 +1911,25 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
 // RangeProof.verifyM (src/RangeProof.hs:99-101) for `batch` proofs; `rounds`, n_norm, n_lin
 // describe the proofs as encoded (for binary proofs the prover's round rule may differ from
 // optimalWitnessSize, src/RangeProof/Binary.hs:195 vs :218; verifyBPM ignores `rounds`).
+// weights of a random linear combination over `n` proofs: 128 random bits each from the OS entropy source, drawn
+// after the proofs are fixed (they are this call's inputs); canonical 32-byte scalars, the first one is 1
+static std::vector<uint8_t> batch_weights(size_t n) {
+    std::vector<uint8_t> w(32 * n, 0);
+    std::vector<uint8_t> rnd(16 * n);
+    size_t got = 0;
+    while (got < rnd.size()) {
+        ssize_t r = getrandom(rnd.data() + got, std::min<size_t>(rnd.size() - got, 256), 0);
+        if (r <= 0) {                                               // no entropy source: never silently predictable
+            fprintf(stderr, "bppp: getrandom failed, batch verification weights unavailable\n");
+            abort();
+        }
+        got += (size_t)r;
+    }
+    for (size_t i = 0; i < n; i++) memcpy(&w[32 * i], &rnd[16 * i], 16);
+    memset(&w[0], 0, 32);
+    w[0] = 1;
+    return w;
+}
 static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, size_t n_norm, size_t n_lin, const uint8_t* coms,
                        const uint8_t* responses, const uint8_t* finals, int* ok) {
     const size_t B = batch, n = s->n_inputs, N = s->nrm_len, M = s->lin_len, NC = s->num_rp_coms + n, k = rounds;
@@ -2010,6 +2041,10 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             sect.lap(S_TOBYTES);
         });
         g_tm.lap("verify_host");
+        if (s->batch_verify && B > 1) {
+            std::vector<uint8_t> wts = batch_weights(B);
+            rc = bppp_nl_verify_trrp_rlc(ln.trrp, k, q_b, sp_b, c_b, es_b, responses, n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, wts.data(), ok);
+        } else
         rc = bppp_nl_verify_trrp(ln.trrp, k, q_b, sp_b, c_b, es_b, responses, n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, ok);
         g_tm.lap("nl_verify");
         g_tm.dump("verify");
@@ -2093,8 +2128,14 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         sect.lap(S_TOBYTES);
     });
     g_tm.lap("verify_host");
-    int rc = bppp_nl_verify_gens(ln.gens, s->arg, B, k, q_b, sp_b, pw_b, c_b, es_b, responses,
-                                 n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, ok);
+    int rc;
+    if (s->batch_verify && B > 1) {
+        std::vector<uint8_t> wts = batch_weights(B);
+        rc = bppp_nl_verify_gens_rlc(ln.gens, s->arg, B, k, q_b, sp_b, pw_b, c_b, es_b, responses,
+                                     n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, wts.data(), ok);
+    } else
+    rc = bppp_nl_verify_gens(ln.gens, s->arg, B, k, q_b, sp_b, pw_b, c_b, es_b, responses,
+                             n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, ok);
     g_tm.lap("nl_verify");
     g_tm.dump("verify");
     if (t_lane_threads_is_main()) dump_sections("verify, all lanes", B);

@@ -85,6 +85,32 @@ __global__ void k_fr_convert(const u256* __restrict__ in, u256* __restrict__ out
     st_u256(out + i, to_mont ? fr::to_mont(a) : fr::from_mont(a));
 }
 
+// Batch verification across proofs (the reference's TODO at src/RangeProof/TypedReciprocal.hs:469-472,
+// src/RangeProof.hs:103-106): a random linear combination sum_b rho_b (check of proof b) collapses the B
+// generator-side MSMs into one.  sc = [B][stride] canonical verifier scalars, rho = [B] weights (Montgomery):
+// out[i] = sum_b rho_b sc[b][i] (canonical).  One CTA per column, threads stride over the proofs.
+#define WCOL_THREADS 64
+__global__ void __launch_bounds__(WCOL_THREADS) k_weight_columns(const u256* __restrict__ sc, size_t stride, const u256* __restrict__ rho,
+                                                                 int B, u256* __restrict__ out) {
+    __shared__ u256 sm[WCOL_THREADS];
+    const size_t i = blockIdx.x;
+    u256 acc = u256_zero();
+    for (int b = threadIdx.x; b < B; b += WCOL_THREADS) acc = fr::add(acc, fr::mul(ld_u256(sc + (size_t)b * stride + i), ld_u256(rho + b)));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int h = WCOL_THREADS / 2; h >= 1; h >>= 1) {
+        if ((int)threadIdx.x < h) sm[threadIdx.x] = fr::add(sm[threadIdx.x], sm[threadIdx.x + h]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_u256(out + i, sm[0]);
+}
+// out[b][j] = rho_b * in[b][j] for the per-proof points' scalars (rows of n)
+__global__ void k_weight_rows(const u256* __restrict__ in, const u256* __restrict__ rho, int n, size_t total, u256* __restrict__ out) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    st_u256(out + t, fr::mul(ld_u256(in + t), ld_u256(rho + t / n)));
+}
+
 // out[p*out_stride + out_off + i] = canonical(in[p*in_stride + i])   (Montgomery -> integer, strided rows)
 __global__ void k_fr_from_mont_rows(const u256* __restrict__ in, size_t in_stride, u256* __restrict__ out, size_t out_stride,
                                     int out_off, int n) {

@@ -26,7 +26,7 @@ EXPORTS = [
     "bppp_trrp_create", "bppp_trrp_destroy", "bppp_trrp_phase1", "bppp_trrp_phase2", "bppp_trrp_phase3", "bppp_trrp_commit_bl",
     "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
     "bppp_dtr_absorb", "bppp_dtr_squeeze", "bppp_dtr_fits", "bppp_dtr_export", "bppp_rp_set_device_transcript", "bppp_nl_round_challenge",
-    "bppp_nl_attach_transcript", "bppp_nl_prove_device",
+    "bppp_nl_attach_transcript", "bppp_nl_prove_device", "bppp_rp_set_batch_verify", "bppp_nl_verify_trrp_rlc", "bppp_nl_verify_gens_rlc",
     "bppp_trrp_set_transcript", "bppp_trrp_phase1_tr", "bppp_trrp_phase2_tr", "bppp_trrp_phase3_rnd", "bppp_trrp_commit_bl_tr",
 ]
 
@@ -135,6 +135,9 @@ def load_library():
     lib.bppp_rp_set_device_transcript.argtypes = [vp, ip]
     lib.bppp_nl_round_challenge.argtypes = [vp, u8p, u8p, u8p]
     lib.bppp_nl_attach_transcript.argtypes = [vp, vp]
+    lib.bppp_rp_set_batch_verify.argtypes = [vp, ip]
+    lib.bppp_nl_verify_gens_rlc.argtypes = [vp, ip, sz, sz, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz, u8p, u8p, sz, u8p, u8p, u8p,
+                                            C.POINTER(ip)]
     lib.bppp_nl_prove_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, u8p]
     lib.bppp_tune_process.argtypes = [ip]
     # this harness drives dedicated batch-proving processes (tests, bench.py): opt in to the process-wide
@@ -487,6 +490,10 @@ class RangeProofSetup:
     def set_device_transcript(self, on=True):
         """run the Fiat-Shamir transcript of prove_batch / verify_batch on the device; bit-identical"""
         self._ck(self.ctx.lib.bppp_rp_set_device_transcript(self.h, int(bool(on))), "bppp_rp_set_device_transcript")
+
+    def set_batch_verify(self, on=True):
+        """verify each lane's sub-batch by one random linear combination; per-proof checks locate failures"""
+        self._ck(self.ctx.lib.bppp_rp_set_batch_verify(self.h, int(bool(on))), "bppp_rp_set_batch_verify")
 
     def contexts(self):
         """the contexts of all concurrent lanes (lane 0 first)"""

@@ -248,6 +248,19 @@ int bppp_trrp_phase4(bppp_trrp* h, const uint8_t* chal, uint8_t* sums);
  * sums as in phase 4; the norm part of makePublicConsts stays on the device for bppp_nl_verify_trrp,
  * which is bppp_nl_verify_gens (norm-linear argument) without the pub_w argument. */
 int bppp_trrp_verify_pub(bppp_trrp* h, size_t batch, const uint8_t* chal, uint8_t* sums);
+/* Batch verification across proofs (the reference's TODO, src/RangeProof/TypedReciprocal.hs:469-472,
+ * src/RangeProof.hs:103-106): bppp_nl_verify_trrp / bppp_nl_verify_gens plus weights = [batch] scalars drawn at random
+ * by the caller after seeing the proofs.  sum_b weight_b * (check of proof b) is ONE fixed-base MSM over the shared
+ * generators plus ONE Pippenger over all per-proof points; if it is the identity every ok[b] = 1, otherwise the
+ * per-proof checks run and locate the bad proofs -- the verdicts are exact either way. */
+int bppp_nl_verify_trrp_rlc(bppp_trrp* h, size_t k, const uint8_t* q, const uint8_t* s_pub, const uint8_t* c,
+                            const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin, const uint8_t* fw,
+                            const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p,
+                            const uint8_t* weights, int* ok);
+int bppp_nl_verify_gens_rlc(bppp_gens* gens, int kind, size_t batch, size_t k, const uint8_t* q, const uint8_t* s_pub,
+                            const uint8_t* pub_w, const uint8_t* c, const uint8_t* es, const uint8_t* XR,
+                            size_t n_norm, size_t n_lin, const uint8_t* fw, const uint8_t* fl, size_t n_init,
+                            const uint8_t* init_s, const uint8_t* init_p, const uint8_t* weights, int* ok);
 int bppp_nl_verify_trrp(bppp_trrp* h, size_t k, const uint8_t* q, const uint8_t* s_pub, const uint8_t* c,
                         const uint8_t* es, const uint8_t* XR, size_t n_norm, size_t n_lin, const uint8_t* fw,
                         const uint8_t* fl, size_t n_init, const uint8_t* init_s, const uint8_t* init_p, int* ok);
@@ -287,6 +300,9 @@ void bppp_set_host_threads(int n);
  * reference's arrangement), 1 = device (bit-identical proofs and verdicts; needs the device scalar
  * phases, i.e. TypedReciprocal over the norm-linear argument).  Environment default: BPPP_DEVICE_TRANSCRIPT=1. */
 int bppp_rp_set_device_transcript(bppp_rp* s, int on);
+/* bppp_rp_verify_batch by one random linear combination per lane sub-batch (weights from the OS entropy source);
+ * falls back to the per-proof checks when a combination fails, so ok[] is exact.  Default off (BPPP_BATCH_VERIFY=1). */
+int bppp_rp_set_batch_verify(bppp_rp* s, int on);
 /* RangeProof.proveM for `batch` independent proofs (see rp_host.cpp for the buffer layout) */
 int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
                         const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals);

@@ -229,6 +229,39 @@ def test_device_transcript_stages_in_one_squeeze(ctx, gens):
     ctx.lib.bppp_dtr_destroy(t)
 
 
+@pytest.mark.parametrize("name,count", [("32by64", 70), ("128by64", 5), ("bin_test", 4)])
+def test_batch_verification_accepts_and_locates_bad_proofs(ctx, name, count):
+    """one random linear combination per lane sub-batch (one fixed-base MSM + one Pippenger over all
+    per-proof points).  All-good batches are accepted by the combination alone; with tampered proofs in the batch the
+    combination fails and the per-proof checks return exactly the verdicts of plain verification."""
+    import bulletproofspp_b200 as bp
+    if name == "bin_test":
+        schema, wit = EXAMPLES[name]
+        wits, seeds = [wit] * count, ["seed %d" % i for i in range(count)]
+    else:
+        schema, wits, seeds = batched(name, count)
+    setup = bp.RangeProofSetup(ctx, schema)
+    proofs = setup.prove_batch(wits, seeds)
+    plain = setup.verify_batch(proofs)
+    assert all(plain)
+    setup.set_batch_verify(True)
+    l0 = ctx.launch_count()
+    assert setup.verify_batch(proofs) == plain
+    p = proofs[1]
+    bad1 = dict(p, finals=[(p["finals"][0] + 1) % (2 ** 200)] + p["finals"][1:])
+    bad2 = dict(proofs[2], coms=[proofs[2]["coms"][1], proofs[2]["coms"][0]] + proofs[2]["coms"][2:])
+    mixed = [proofs[0], bad1, bad2] + proofs[3:]
+    want = [True, False, False] + [True] * (count - 3)
+    assert setup.verify_batch(mixed) == want
+    # a proof under another proof's commitments, last in the batch
+    swapped = proofs[:-1] + [dict(proofs[-1], coms=proofs[0]["coms"])]
+    if name != "bin_test":
+        assert setup.verify_batch(swapped) == [True] * (count - 1) + [False]
+    setup.set_batch_verify(False)
+    assert setup.verify_batch(mixed) == want
+    setup.close()
+
+
 def test_hybrid_round_mode_is_bit_identical(ctx, monkeypatch):
     """BPPP_HYBRID_MAX switches a tensor-mode argument to generator folding for its last rounds (the
     folded generators are materialised by one small fixed-base MSM per block).  Same proof bits."""
