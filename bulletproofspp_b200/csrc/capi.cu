@@ -6,6 +6,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdlib.h>
+#include <dlfcn.h>
 #include <algorithm>
 #include <mutex>
 #include <string>
@@ -1273,6 +1274,7 @@ struct bppp_nl {
     int blocks_n = 1, blocks_l = 1;
     size_t shard_lo = 0;            // index of this handle's first norm element inside the whole (sharded) vector
     bppp_dtr* dtr = nullptr;        // not owned: device transcript the round commitments are absorbed into
+    bool no_rebase = false;         // a shard of a larger argument keeps folding its own slice (bppp_nl_prove_sharded)
     // tensor mode: no generator folding; per-generator fold coefficients + folded opening scalars.
     // The "original" generators of tensor mode are the list `tgens` of tN + tM (+ g) points: the shared
     // list of the handle, or -- after a single large argument has folded down to a few thousand
@@ -1644,12 +1646,13 @@ int ip_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l) {
 
 namespace {
 int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint8_t* q, const uint8_t* s, const uint8_t* w,
-                   const uint8_t* l, const uint8_t* c, bppp_nl** out, const u256* w_dev = nullptr) {
+                   const uint8_t* l, const uint8_t* c, bppp_nl** out, const u256* w_dev = nullptr, const u256* l_dev = nullptr,
+                   const u256* c_dev = nullptr) {
     bppp_ctx* ctx = gens->ctx;
     const size_t N = gens->N, M = gens->M;
     if (N + M + 1 > 0x7fffffff) FAIL(BPPP_ERR_ARG, "vector too long");
-    if (!check_fr(q, batch) || !check_fr(s, batch) || (!w_dev && !check_fr(w, batch * N)) || !check_fr(l, batch * M) ||
-        !check_fr(c, batch * M))
+    if (!check_fr(q, batch) || !check_fr(s, batch) || (!w_dev && !check_fr(w, batch * N)) || (!l_dev && !check_fr(l, batch * M)) ||
+        (!c_dev && !check_fr(c, batch * M)))
         FAIL(BPPP_ERR_RANGE, "scalar >= group order");
     bppp_nl* h = new bppp_nl();
     h->ctx = ctx; h->gens = gens; h->own_gens = own; h->kind = kind;
@@ -1703,6 +1706,8 @@ int nl_create_impl(bppp_gens* gens, bool own, int kind, size_t batch, const uint
         CKH(cudaMemcpyAsync(h->w[0].p, w_dev, batch * N * 32, cudaMemcpyDeviceToDevice, ctx->st));
         up[0].n = 0;
     }
+    if (l_dev && M) { CKH(cudaMemcpyAsync(h->l[0].p, l_dev, batch * M * 32, cudaMemcpyDeviceToDevice, ctx->st)); up[1].n = 0; }
+    if (c_dev && M) { CKH(cudaMemcpyAsync(h->c[0].p, c_dev, batch * M * 32, cudaMemcpyDeviceToDevice, ctx->st)); up[2].n = 0; }
     for (auto& u : up) {
         if (!u.n) continue;
         CKH(H2D(h->sc.p, u.src, u.n * 32));
@@ -2160,7 +2165,7 @@ extern "C" int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin) {
     return BPPP_OK;
 }
 
-static int nl_enqueue_commit(bppp_nl* h);
+static int nl_enqueue_commit(bppp_nl* h, bool affine = true);
 static int nl_round_commit_impl(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E) {
     if (!h) return BPPP_ERR_ARG;
     bppp_ctx* ctx = h->ctx;
@@ -2215,7 +2220,7 @@ static int nl_round_commit_impl(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E) 
 // The device work of a round's two commitments once the round constants (C_K1, C_K2, C_COEF; C_RHO and the dot
 // partials) are in place: opening scalars in MSM order, the two MSMs, affine results in h->aff ([B][2] = X, R),
 // the scalar parts sX, sR in h->dots.  No host synchronisation.
-static int nl_enqueue_commit(bppp_nl* h) {
+static int nl_enqueue_commit(bppp_nl* h, bool affine) {
     bppp_ctx* ctx = h->ctx;
     const size_t B = h->B;
     int rc;
@@ -2291,7 +2296,7 @@ static int nl_enqueue_commit(bppp_nl* h) {
         h->plan.add(h->pts[h->curp].p, h->P2, xs, P0, B * P0, nterms);
         if ((rc = run_msm(ctx, h->plan, B, 2, h->res.p, work))) return rc;
     }
-    return to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2);
+    return affine ? to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2) : BPPP_OK;     // a shard's partial sums stay Jacobian
 }
 extern "C" int bppp_nl_round_commit(bppp_nl* h, uint8_t* X, uint8_t* R) { return nl_round_commit_impl(h, X, R, nullptr); }
 // The commitments of the round and, from the device transcript the argument continues (bppp_nl_create_trrp after
@@ -2485,7 +2490,7 @@ static int nl_enqueue_fold(bppp_nl* h) {
     h->curN = nN;
     h->curM = nM;
     h->round++;
-    if (B == 1 && !h->tail_gens && 1 + nN + nM <= rebase_limit() && nN + nM >= 16) return nl_rebase_tensor(h);
+    if (B == 1 && !h->tail_gens && !h->no_rebase && 1 + nN + nM <= rebase_limit() && nN + nM >= 16) return nl_rebase_tensor(h);
     return BPPP_OK;
 }
 
@@ -2517,6 +2522,207 @@ extern "C" int bppp_nl_attach_transcript(bppp_nl* h, bppp_dtr* t) {
     return BPPP_OK;
 }
 
+// ---- NCCL communicator for one argument sharded over several GPUs.  libnccl is loaded at run time
+// (dlopen): the library has no link-time dependency on it and single-GPU users never touch it.
+namespace {
+typedef struct { char internal[128]; } nccl_unique_id;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_unique_id*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_unique_id, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+bool nccl_load(const char* path) {
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return true;
+    void* lib = nullptr;
+    if (path && *path) lib = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);      // the copy the process already has (torch's)
+    if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { g_nccl.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+    NcclApi a;
+    a.lib = lib;
+    a.GetUniqueId = (int (*)(nccl_unique_id*))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, nccl_unique_id, int))dlsym(lib, "ncclCommInitRank");
+    a.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    a.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+    a.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.AllGather || !a.GetErrorString) {
+        g_nccl.err = "libnccl.so.2 lacks an expected symbol";
+        return false;
+    }
+    g_nccl = a;
+    return true;
+}
+}  // namespace
+struct bppp_comm {
+    bppp_ctx* ctx;
+    void* comm = nullptr;               // ncclComm_t; null for a one-rank communicator
+    int world = 1, rank = 0;
+};
+#define NCCL_UINT8 1                     // ncclUint8 (nccl.h)
+// path = the libnccl.so.2 to use (NULL: the one already in the process, else the system's)
+extern "C" int bppp_comm_load(const char* path) { return nccl_load(path) ? BPPP_OK : BPPP_ERR_STATE; }
+extern "C" const char* bppp_comm_last_error(void) { return g_nccl.err.c_str(); }
+// rank 0 draws the 128-byte id and hands it to the other ranks out of band (e.g. torch.distributed broadcast)
+extern "C" int bppp_comm_unique_id(uint8_t id[128]) {
+    if (!id || !nccl_load(nullptr)) return BPPP_ERR_STATE;
+    nccl_unique_id u;
+    int rc = g_nccl.GetUniqueId(&u);
+    if (rc) { g_nccl.err = g_nccl.GetErrorString(rc); return BPPP_ERR_CUDA; }
+    memcpy(id, u.internal, 128);
+    return BPPP_OK;
+}
+// one communicator per context (its collectives run on the context's stream); world == 1 needs no NCCL at all
+extern "C" int bppp_comm_create(bppp_ctx* ctx, int world, int rank, const uint8_t id[128], bppp_comm** out) {
+    if (!ctx) return BPPP_ERR_ARG;
+    if (!out || world < 1 || rank < 0 || rank >= world || (world > 1 && !id)) FAIL(BPPP_ERR_ARG, "bppp_comm_create: bad argument");
+    *out = nullptr;
+    ENTER(ctx);
+    bppp_comm* c = new bppp_comm();
+    c->ctx = ctx; c->world = world; c->rank = rank;
+    if (world > 1) {
+        if (!nccl_load(nullptr)) { delete c; FAIL(BPPP_ERR_STATE, g_nccl.err); }
+        nccl_unique_id u;
+        memcpy(u.internal, id, 128);
+        int rc = g_nccl.CommInitRank(&c->comm, world, u, rank);
+        if (rc) { delete c; FAIL(BPPP_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc)); }
+    }
+    *out = c;
+    return BPPP_OK;
+}
+extern "C" void bppp_comm_destroy(bppp_comm* c) {
+    if (!c) return;
+    if (c->comm) {
+        cudaSetDevice(c->ctx->dev);
+        cudaStreamSynchronize(c->ctx->st);
+        g_nccl.CommDestroy(c->comm);
+    }
+    delete c;
+}
+namespace {
+// all ranks contribute `bytes` bytes; recv holds world * bytes in rank order (a device copy when there is one rank)
+int comm_all_gather(bppp_comm* c, const void* send, void* recv, size_t bytes) {
+    bppp_ctx* ctx = c->ctx;
+    if (c->world == 1) {
+        CK(cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, ctx->st));
+        return BPPP_OK;
+    }
+    int rc = g_nccl.AllGather(send, recv, bytes, NCCL_UINT8, c->comm, ctx->st);
+    if (rc) FAIL(BPPP_ERR_CUDA, std::string("ncclAllGather: ") + g_nccl.GetErrorString(rc));
+    return BPPP_OK;
+}
+
+// ---- the device-resident round loop (rounds.cuh)
+struct DevRun {                          // outputs of all rounds, newest first
+    DBuf<Affine> resp;                   // [B][total][2]
+    DBuf<u256> esd;                      // [B][total]
+    size_t total = 0;
+    DBuf<unsigned char> send, recv;      // sharded runs: one record per rank
+};
+RoundState nl_round_state(bppp_nl* h) {
+    RoundState S;
+    S.q = cptr(h, C_Q); S.qinv = cptr(h, C_QINV); S.nn = cptr(h, C_NN); S.nl = cptr(h, C_NL); S.s = cptr(h, C_S);
+    S.rho = cptr(h, C_RHO); S.k1 = cptr(h, C_K1); S.k2 = cptr(h, C_K2); S.coef = cptr(h, C_COEF);
+    S.au = cptr(h, C_AU); S.bu = cptr(h, C_BU); S.al = cptr(h, C_AL); S.bl = cptr(h, C_BL); S.ac = cptr(h, C_AC); S.bc = cptr(h, C_BC);
+    S.a0n = cptr(h, C_A0N); S.b0n = cptr(h, C_B0N); S.a0l = cptr(h, C_A0L); S.b0l = cptr(h, C_B0L);
+    S.kb = cptr(h, C_KB); S.ka = cptr(h, C_KA); S.sgn = h->sgn.p; S.inv = cptr(h, C_INV);
+    S.chal = h->dtr->chal.p; S.dots = h->dots.p; S.B = (int)h->B; S.tensor = 0; S.pair_off = 0;
+    return S;
+}
+// the per-proof round state (host vectors of a fresh handle) moves to the device
+int nl_dev_upload_state(bppp_nl* h) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B;
+    CK(H2D(cptr(h, C_Q), h->q.data(), B * 32)); CK(H2D(cptr(h, C_QINV), h->qinv.data(), B * 32));
+    CK(H2D(cptr(h, C_NN), h->nn.data(), B * 32)); CK(H2D(cptr(h, C_NL), h->nl.data(), B * 32));
+    CK(H2D(cptr(h, C_S), h->s.data(), B * 32));
+    CK(cudaMemsetAsync(cptr(h, C_COEF), 0, B * 8 * 32, ctx->st));
+    return BPPP_OK;
+}
+// rounds [done, done + n) of R.total; with `comm` the handle is one rank's shard: partial commitments and scalar
+// parts are all-gathered (256 bytes per rank) and summed in rank order before the transcript sees them
+int nl_dev_rounds(bppp_nl* h, size_t n, size_t done, DevRun& R, bppp_comm* comm) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, total = R.total;
+    RoundState S = nl_round_state(h);
+    int rc;
+    for (size_t r = done; r < done + n; r++) {
+        if (h->curN + h->curM == 0 && !comm) FAIL(BPPP_ERR_STATE, "device round loop: nothing left to fold");
+        S.pair_off = h->shard_lo ? (unsigned long long)(h->shard_lo >> (h->round + 1)) : 0ull;
+        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+        k_round_pre<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(S);
+        }
+        CK(cudaGetLastError());
+        if (!h->have_partials) {
+            if ((rc = launch_fold_dots(h, 0))) return rc;
+            h->have_partials = true;
+        }
+        if ((rc = nl_enqueue_commit(h, comm == nullptr))) return rc;
+        if (comm) {
+            { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+            k_shard_pack<<<1, 32, 0, ctx->st>>>(h->res.p, h->dots.p, R.send.p);
+            }
+            CK(cudaGetLastError());
+            if ((rc = comm_all_gather(comm, R.send.p, R.recv.p, SHARD_REC_BYTES))) return rc;
+            { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+            k_shard_combine<<<1, 32, 0, ctx->st>>>(R.recv.p, comm->world, h->res.p, h->dots.p);
+            }
+            CK(cudaGetLastError());
+            if ((rc = to_affine(ctx, h->res.p, 1, h->aff.p, 1, 0, 1, B * 2))) return rc;
+        }
+        // responses are consed: newest first (Bulletproof.hs:357-359)
+        CK(cudaMemcpy2DAsync(R.resp.p + 2 * (total - 1 - r), total * 128, h->aff.p, 128, 128, B, cudaMemcpyDeviceToDevice, ctx->st));
+        // e <- head <$> oracle [X, R]  (Bulletproof.hs:351)
+        if ((rc = dtr_absorb_dev(h->dtr, h->aff.p, 2, 2))) return rc;
+        if ((rc = dtr_squeeze_first(h->dtr, 1))) return rc;
+        CK(cudaMemcpy2DAsync(R.esd.p + (total - 1 - r), total * 32, h->dtr->chal.p, 32, 32, B, cudaMemcpyDeviceToDevice, ctx->st));
+        S.tensor = h->tensor ? 1 : 0;
+        if (!S.tensor) {
+            ProfScope ps_(ctx, K_ROUND_STATE, 0);
+            k_round_ratio<<<(unsigned)((2 * B + 63) / 64), 64, 0, ctx->st>>>(S);
+        }
+        CK(cudaGetLastError());
+        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+        k_round_post<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(S);
+        }
+        CK(cudaGetLastError());
+        if ((rc = nl_enqueue_fold(h))) return rc;
+    }
+    return BPPP_OK;
+}
+// getWitness: the final vectors with their normalisations and the opening scalar; then everything goes to the host
+int nl_dev_finish(bppp_nl* h, DevRun& R, uint8_t* responses, uint8_t* es, uint8_t* s, uint8_t* w, uint8_t* l) {
+    bppp_ctx* ctx = h->ctx;
+    const size_t B = h->B, cn = h->curN, cl = h->curM;
+    DBuf<u256> fin;
+    CK(fin.alloc(B * (1 + cn + cl)));
+    u256* fs = fin.p; u256* fw = fin.p + B; u256* fl = fw + B * cn;
+    struct { const u256* v; size_t stride; const u256* sc; size_t n; u256* out; } jobs[3] = {
+        {cptr(h, C_S), 1, nullptr, 1, fs}, {h->w[h->cur].p, h->wstride[h->cur], cptr(h, C_NN), cn, fw},
+        {h->l[h->cur].p, h->lstride[h->cur], cptr(h, C_NL), cl, fl}};
+    for (auto& j : jobs) {
+        if (!j.n) continue;
+        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
+        k_scale_rows<<<(unsigned)((j.n * B + 127) / 128), 128, 0, ctx->st>>>(j.v, j.stride, j.sc, (int)j.n, (int)B, j.out);
+        }
+        CK(cudaGetLastError());
+    }
+    CK(D2H(responses, R.resp.p, B * R.total * 128));
+    if (es) CK(D2H(es, R.esd.p, B * R.total * 32));
+    if (s) CK(D2H(s, fs, B * 32));
+    if (w && cn) CK(D2H(w, fw, B * cn * 32));
+    if (l && cl) CK(D2H(l, fl, B * cl * 32));
+    CK(ctx_sync(ctx));
+    return BPPP_OK;
+}
+}  // namespace
+
 // proveBPM (src/Bulletproof.hs:357-359) for the whole batch as ONE stream of launches: per round the two
 // commitments, `oracle [X, R]` on the device transcript, rationalReduceScalar and the fold factors in
 // k_round_ratio / k_round_post (rounds.cuh), the folds -- no host synchronisation until the results are read.
@@ -2531,73 +2737,111 @@ extern "C" int bppp_nl_prove_device(bppp_nl* h, size_t rounds, uint8_t* response
     if (!h->dtr) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_device: no device transcript attached");
     if (h->round != 0 || h->have_partials || h->shard_lo) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_device: needs a fresh, unsharded argument");
     ENTER(ctx);
-    const size_t B = h->B;
-    // the per-proof round state moves to the device
-    CK(H2D(cptr(h, C_Q), h->q.data(), B * 32)); CK(H2D(cptr(h, C_QINV), h->qinv.data(), B * 32));
-    CK(H2D(cptr(h, C_NN), h->nn.data(), B * 32)); CK(H2D(cptr(h, C_NL), h->nl.data(), B * 32));
-    CK(H2D(cptr(h, C_S), h->s.data(), B * 32));
-    CK(cudaMemsetAsync(cptr(h, C_COEF), 0, B * 8 * 32, ctx->st));
-    DBuf<Affine> resp;
-    DBuf<u256> esd, fin;
-    CK(resp.alloc(B * rounds * 2)); CK(esd.alloc(B * rounds));
-    RoundState S;
-    S.q = cptr(h, C_Q); S.qinv = cptr(h, C_QINV); S.nn = cptr(h, C_NN); S.nl = cptr(h, C_NL); S.s = cptr(h, C_S);
-    S.rho = cptr(h, C_RHO); S.k1 = cptr(h, C_K1); S.k2 = cptr(h, C_K2); S.coef = cptr(h, C_COEF);
-    S.au = cptr(h, C_AU); S.bu = cptr(h, C_BU); S.al = cptr(h, C_AL); S.bl = cptr(h, C_BL); S.ac = cptr(h, C_AC); S.bc = cptr(h, C_BC);
-    S.a0n = cptr(h, C_A0N); S.b0n = cptr(h, C_B0N); S.a0l = cptr(h, C_A0L); S.b0l = cptr(h, C_B0L);
-    S.kb = cptr(h, C_KB); S.ka = cptr(h, C_KA); S.sgn = h->sgn.p; S.inv = cptr(h, C_INV);
-    S.chal = h->dtr->chal.p; S.dots = h->dots.p; S.B = (int)B; S.tensor = 0;
+    DevRun R;
+    R.total = rounds;
+    CK(R.resp.alloc(h->B * rounds * 2)); CK(R.esd.alloc(h->B * rounds));
     int rc;
-    for (size_t r = 0; r < rounds; r++) {
-        if (h->curN + h->curM == 0) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_device: nothing left to fold");
-        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
-        k_round_pre<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(S);
+    if ((rc = nl_dev_upload_state(h))) return rc;
+    if ((rc = nl_dev_rounds(h, rounds, 0, R, nullptr))) return rc;
+    return nl_dev_finish(h, R, responses, es, s, w, l);
+}
+
+// One large argument sharded over the GPUs of a box.  Every rank holds a contiguous slice of the norm
+// vector and of its generators (bppp_nl_create over the slice, then bppp_nl_set_shard with the slice's first index;
+// equal power-of-two slice lengths); the linear part lives on rank 0 (`lin_len` = its length, the other ranks create
+// their handles with M = 0); every rank passes the SAME q and opening scalar s, and a transcript in the same state.
+//   rounds 1 .. local_rounds: adjacent-pair folds keep a contiguous slice local (src/Bulletproof.hs:77-90); the
+//     commitments are sums of per-rank partial MSMs -- 256 bytes per rank all-gathered with NCCL on the context's
+//     stream and added in rank order on the device, so every rank's transcript absorbs the same X, R;
+//   then the folded slices (vectors, generators, rank 0's linear part) are all-gathered once and every rank finishes
+//     the remaining rounds on the whole (short) argument, re-based to tensor mode -- identical results on all ranks.
+// Outputs as bppp_nl_prove_device, on every rank.  The proof is bit-identical to the unsharded one (tests, tools).
+extern "C" int bppp_nl_prove_sharded(bppp_nl* h, bppp_comm* comm, size_t rounds, size_t local_rounds, size_t lin_len,
+                                     uint8_t* responses, uint8_t* es, uint8_t* s, uint8_t* w, uint8_t* l) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->ctx;
+    if (!comm || comm->ctx != ctx || !responses || rounds == 0 || rounds > 64 || local_rounds > rounds)
+        FAIL(BPPP_ERR_ARG, "bppp_nl_prove_sharded: bad argument");
+    if (h->kind != BPPP_ARG_NL || h->B != 1) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_sharded: one norm-linear argument");
+    if (!h->dtr) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_sharded: no device transcript attached");
+    if (h->round != 0 || h->have_partials) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_sharded: needs a fresh argument");
+    const size_t W = (size_t)comm->world, len0 = h->N;
+    if (len0 == 0 || (len0 & (len0 - 1)) || (len0 >> local_rounds) == 0) FAIL(BPPP_ERR_ARG, "bppp_nl_prove_sharded: slice length must be a power of two >= 2^local_rounds");
+    if (h->shard_lo != (size_t)comm->rank * len0) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_sharded: bppp_nl_set_shard(rank * slice length) first");
+    if ((comm->rank == 0) != (h->M == lin_len) && lin_len) FAIL(BPPP_ERR_ARG, "bppp_nl_prove_sharded: the linear part lives on rank 0 only");
+    ENTER(ctx);
+    int rc;
+    if (h->tensor) {                     // slices fold their generators for real: the gathered tail needs them
+        CK(h->pts[0].ensure(h->B * h->P2)); CK(h->pts[1].ensure(h->B * h->P2));
+        CK(h->jscratch.ensure(h->B * (h->N2 + h->M2)));
+        for (int k = 0; k < 2; k++) {
+            k_bcast_point<<<1, 128, 0, ctx->st>>>(h->gens->base.p, h->pts[k].p, h->P2, h->B);
+            CK(cudaGetLastError());
         }
-        CK(cudaGetLastError());
-        if (!h->have_partials) {
-            if ((rc = launch_fold_dots(h, 0))) return rc;
-            h->have_partials = true;
-        }
-        if ((rc = nl_enqueue_commit(h))) return rc;
-        // responses are consed: newest first (Bulletproof.hs:357-359)
-        CK(cudaMemcpy2DAsync(resp.p + 2 * (rounds - 1 - r), rounds * 128, h->aff.p, 128, 128, B, cudaMemcpyDeviceToDevice, ctx->st));
-        // e <- head <$> oracle [X, R]  (Bulletproof.hs:351)
-        if ((rc = dtr_absorb_dev(h->dtr, h->aff.p, 2, 2))) return rc;
-        if ((rc = dtr_squeeze_first(h->dtr, 1))) return rc;
-        CK(cudaMemcpy2DAsync(esd.p + (rounds - 1 - r), rounds * 32, h->dtr->chal.p, 32, 32, B, cudaMemcpyDeviceToDevice, ctx->st));
-        S.tensor = h->tensor ? 1 : 0;
-        if (!S.tensor) {
-            ProfScope ps_(ctx, K_ROUND_STATE, 0);
-            k_round_ratio<<<(unsigned)((2 * B + 63) / 64), 64, 0, ctx->st>>>(S);
-        }
-        CK(cudaGetLastError());
-        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
-        k_round_post<<<(unsigned)((B + 127) / 128), 128, 0, ctx->st>>>(S);
-        }
-        CK(cudaGetLastError());
-        if ((rc = nl_enqueue_fold(h))) return rc;
+        h->tensor = false;
+        h->curp = -1;
     }
-    // getWitness: the final vectors with their normalisations, and the opening scalar
-    const size_t cn = h->curN, cl = h->curM;
-    CK(fin.alloc(B * (1 + cn + cl)));
-    u256* fs = fin.p; u256* fw = fin.p + B; u256* fl = fw + B * cn;
-    struct { const u256* v; size_t stride; const u256* sc; size_t n; u256* out; } jobs[3] = {
-        {cptr(h, C_S), 1, nullptr, 1, fs}, {h->w[h->cur].p, h->wstride[h->cur], cptr(h, C_NN), cn, fw},
-        {h->l[h->cur].p, h->lstride[h->cur], cptr(h, C_NL), cl, fl}};
-    for (auto& j : jobs) {
-        if (!j.n) continue;
-        { ProfScope ps_(ctx, K_ROUND_STATE, 0);
-        k_scale_rows<<<(unsigned)((j.n * B + 127) / 128), 128, 0, ctx->st>>>(j.v, j.stride, j.sc, (int)j.n, (int)B, j.out);
-        }
-        CK(cudaGetLastError());
+    DevRun R;
+    R.total = rounds;
+    CK(R.resp.alloc(rounds * 2)); CK(R.esd.alloc(rounds));
+    CK(R.send.alloc(SHARD_REC_BYTES)); CK(R.recv.alloc(W * SHARD_REC_BYTES));
+    if ((rc = nl_dev_upload_state(h))) return rc;
+    // no re-base of a slice to tensor mode while it is a shard
+    h->no_rebase = true;
+    if ((rc = nl_dev_rounds(h, local_rounds, 0, R, comm))) return rc;
+    h->no_rebase = false;
+    // ---- gather: [w slice | G slice] of every rank, rank 0's [l | c | H]
+    const size_t L = h->curN;
+    size_t cl = lin_len;
+    for (size_t i = 0; i < local_rounds; i++) cl = (cl + 1) / 2;
+    if (L != (len0 >> local_rounds)) FAIL(BPPP_ERR_STATE, "bppp_nl_prove_sharded: unexpected slice length");
+    const size_t rec = L * 32 + L * 64 + cl * (32 + 32 + 64);
+    DBuf<unsigned char> snd, rcv;
+    CK(snd.alloc(rec)); CK(rcv.alloc(W * rec));
+    CK(cudaMemsetAsync(snd.p, 0, rec, ctx->st));
+    const Affine* cur_pts = h->curp < 0 ? h->gens->base.p : h->pts[h->curp].p;        // [g | G' | H']
+    CK(cudaMemcpyAsync(snd.p, h->w[h->cur].p, L * 32, cudaMemcpyDeviceToDevice, ctx->st));
+    CK(cudaMemcpyAsync(snd.p + L * 32, cur_pts + 1, L * 64, cudaMemcpyDeviceToDevice, ctx->st));
+    if (cl && comm->rank == 0) {
+        CK(cudaMemcpyAsync(snd.p + L * 96, h->l[h->cur].p, cl * 32, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(snd.p + L * 96 + cl * 32, h->c[h->cur].p, cl * 32, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(snd.p + L * 96 + cl * 64, cur_pts + 1 + L, cl * 64, cudaMemcpyDeviceToDevice, ctx->st));
     }
-    CK(D2H(responses, resp.p, B * rounds * 128));
-    if (es) CK(D2H(es, esd.p, B * rounds * 32));
-    if (s) CK(D2H(s, fs, B * 32));
-    if (w && cn) CK(D2H(w, fw, B * cn * 32));
-    if (l && cl) CK(D2H(l, fl, B * cl * 32));
+    if ((rc = comm_all_gather(comm, snd.p, rcv.p, rec))) return rc;
+    const size_t NT = W * L;
+    DBuf<Affine> tp;                     // [g | G (NT) | H (cl)]
+    DBuf<u256> tw, tl, tc;
+    CK(tp.alloc(1 + NT + cl)); CK(tw.alloc(std::max<size_t>(NT, 1))); CK(tl.alloc(std::max<size_t>(cl, 1))); CK(tc.alloc(std::max<size_t>(cl, 1)));
+    CK(cudaMemcpyAsync(tp.p, h->gens->base.p, 64, cudaMemcpyDeviceToDevice, ctx->st));
+    for (size_t r = 0; r < W; r++) {
+        CK(cudaMemcpyAsync(tw.p + r * L, rcv.p + r * rec, L * 32, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(tp.p + 1 + r * L, rcv.p + r * rec + L * 32, L * 64, cudaMemcpyDeviceToDevice, ctx->st));
+    }
+    if (cl) {
+        CK(cudaMemcpyAsync(tl.p, rcv.p + L * 96, cl * 32, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(tc.p, rcv.p + L * 96 + cl * 32, cl * 32, cudaMemcpyDeviceToDevice, ctx->st));
+        CK(cudaMemcpyAsync(tp.p + 1 + NT, rcv.p + L * 96 + cl * 64, cl * 64, cudaMemcpyDeviceToDevice, ctx->st));
+    }
+    // the round state is the same on every rank (same challenges): read it back once
+    std::vector<Fr> st(5);
+    const int slots[5] = {C_Q, C_QINV, C_NN, C_NL, C_S};
+    for (int i = 0; i < 5; i++) CK(D2H(&st[i], cptr(h, slots[i]), 32));
     CK(ctx_sync(ctx));
-    return BPPP_OK;
+    bppp_gens* tg = nullptr;
+    if ((rc = gens_create_impl(ctx, NT, cl, nullptr, nullptr, nullptr, tp.p, &tg))) return rc;
+    bppp_nl* t = nullptr;
+    uint8_t qb[32], sb[32];
+    h64::to_bytes(qb, st[0]); h64::to_bytes(sb, st[4]);
+    if ((rc = nl_create_impl(tg, true, BPPP_ARG_NL, 1, qb, sb, nullptr, nullptr, nullptr, &t, tw.p, tl.p, tc.p))) { bppp_gens_destroy(tg); return rc; }
+    t->q[0] = st[0]; t->qinv[0] = st[1]; t->nn[0] = st[2]; t->nl[0] = st[3]; t->s[0] = st[4];
+    t->dtr = h->dtr;
+    if ((rc = nl_dev_upload_state(t)) == BPPP_OK && (rc = nl_dev_rounds(t, rounds - local_rounds, local_rounds, R, nullptr)) == BPPP_OK)
+        rc = nl_dev_finish(t, R, responses, es, s, w, l);
+    if (rc) ctx->err = std::string("sharded tail: ") + ctx->err;
+    std::string keep = ctx->err;
+    bppp_nl_destroy(t);
+    ctx->err = keep;
+    return rc;
 }
 
 // =============================================================================== verifier

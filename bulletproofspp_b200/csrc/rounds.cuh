@@ -30,6 +30,8 @@ struct RoundState {             // device arrays, one entry per proof unless not
     // without rationalReduceScalar and without an inversion; the short (a', b') of src/Commitment.hs:242-288
     // only pays for itself where generators are really folded (k_pair_fold's half-length scalars).
     int tensor;
+    // a contiguous shard of a larger vector: the pair weights of this shard start at rho^pair_off
+    unsigned long long pair_off;
 };
 
 // constants of a round's commitments (NormArgument.hs:113): rho = q^4, k1 = 2 n^2 q^3, k2 = n^2 q^4;
@@ -40,8 +42,18 @@ __global__ void __launch_bounds__(128) k_round_pre(RoundState S) {
     const u256 q = ld_u256(S.q + b), nn = ld_u256(S.nn + b);
     const u256 q2 = fr::sqr(q), q3 = fr::mul(q2, q), q4 = fr::sqr(q2), n2 = fr::sqr(nn);
     st_u256(S.rho + b, q4);
-    st_u256(S.k1 + b, fr::dbl(fr::mul(n2, q3)));
-    st_u256(S.k2 + b, fr::mul(n2, q4));
+    u256 k1 = fr::dbl(fr::mul(n2, q3)), k2 = fr::mul(n2, q4);
+    if (S.pair_off) {                               // weights of a shard start at (q^4)^(first pair index)
+        u256 off = fr::one(), base = q4;
+        for (unsigned long long e = S.pair_off; e; e >>= 1) {
+            if (e & 1) off = fr::mul(off, base);
+            base = fr::sqr(base);
+        }
+        k1 = fr::mul(k1, off);
+        k2 = fr::mul(k2, off);
+    }
+    st_u256(S.k1 + b, k1);
+    st_u256(S.k2 + b, k2);
     st_u256(S.coef + (size_t)b * 8 + 1, q);
     st_u256(S.coef + (size_t)b * 8 + 2, ld_u256(S.qinv + b));
 }
@@ -99,6 +111,38 @@ __global__ void __launch_bounds__(128) k_round_post(RoundState S) {
     st_u256(S.q + b, qn);
     st_u256(S.qinv + b, fr::sqr(qinv));
     st_u256(S.rho + b, fr::sqr(fr::sqr(qn)));
+}
+
+// One large argument sharded over GPUs: a rank's partial commitments (X, R as Jacobian points) and
+// partial scalar parts (sX, sR) packed into one 256-byte record for the all-gather ...
+#define SHARD_REC_BYTES 256            // 2 * 96 + 2 * 32
+__global__ void k_shard_pack(const Jac* __restrict__ res, const u256* __restrict__ dots, unsigned char* __restrict__ rec) {
+    if (threadIdx.x || blockIdx.x) return;
+    Jac* o = reinterpret_cast<Jac*>(rec);
+    st_jac(o, ld_jac(res));
+    st_jac(o + 1, ld_jac(res + 1));
+    u256* d = reinterpret_cast<u256*>(rec + 192);
+    st_u256(d, ld_u256(dots));
+    st_u256(d + 1, ld_u256(dots + 1));
+}
+// ... and the sums over all ranks in rank order (EC addition is not an NCCL reduction): thread 0 -> X, 1 -> R, 2 -> sX, sR
+__global__ void k_shard_combine(const unsigned char* __restrict__ recs, int world, Jac* __restrict__ res, u256* __restrict__ dots) {
+    const int t = threadIdx.x;
+    if (blockIdx.x || t > 2) return;
+    if (t < 2) {
+        Jac acc = jac_inf();
+        for (int r = 0; r < world; r++) acc = jac_add(acc, ld_jac(reinterpret_cast<const Jac*>(recs + (size_t)r * SHARD_REC_BYTES) + t));
+        st_jac(res + t, acc);
+    } else {
+        u256 a = u256_zero(), b = u256_zero();
+        for (int r = 0; r < world; r++) {
+            const u256* d = reinterpret_cast<const u256*>(recs + (size_t)r * SHARD_REC_BYTES + 192);
+            a = fr::add(a, ld_u256(d));
+            b = fr::add(b, ld_u256(d + 1));
+        }
+        st_u256(dots, a);
+        st_u256(dots + 1, b);
+    }
 }
 
 // getWitness of the final round (NormArgument.hs:147-163 with the stored normalisation): out[b][i] = n_b * v[b][i],

@@ -27,6 +27,7 @@ EXPORTS = [
     "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
     "bppp_dtr_absorb", "bppp_dtr_squeeze", "bppp_dtr_fits", "bppp_dtr_export", "bppp_rp_set_device_transcript", "bppp_nl_round_challenge",
     "bppp_nl_attach_transcript", "bppp_nl_prove_device", "bppp_rp_set_batch_verify", "bppp_nl_verify_trrp_rlc", "bppp_nl_verify_gens_rlc",
+    "bppp_comm_load", "bppp_comm_last_error", "bppp_comm_unique_id", "bppp_comm_create", "bppp_comm_destroy", "bppp_nl_prove_sharded",
     "bppp_trrp_set_transcript", "bppp_trrp_phase1_tr", "bppp_trrp_phase2_tr", "bppp_trrp_phase3_rnd", "bppp_trrp_commit_bl_tr",
 ]
 
@@ -136,6 +137,13 @@ def load_library():
     lib.bppp_nl_round_challenge.argtypes = [vp, u8p, u8p, u8p]
     lib.bppp_nl_attach_transcript.argtypes = [vp, vp]
     lib.bppp_rp_set_batch_verify.argtypes = [vp, ip]
+    lib.bppp_comm_load.argtypes = [C.c_char_p]
+    lib.bppp_comm_last_error.restype = C.c_char_p
+    lib.bppp_comm_unique_id.argtypes = [u8p]
+    lib.bppp_comm_create.argtypes = [vp, ip, ip, u8p, C.POINTER(vp)]
+    lib.bppp_comm_destroy.argtypes = [vp]
+    lib.bppp_comm_destroy.restype = None
+    lib.bppp_nl_prove_sharded.argtypes = [vp, vp, sz, sz, sz, u8p, u8p, u8p, u8p, u8p]
     lib.bppp_nl_verify_gens_rlc.argtypes = [vp, ip, sz, sz, u8p, u8p, u8p, u8p, u8p, u8p, sz, sz, u8p, u8p, sz, u8p, u8p, u8p,
                                             C.POINTER(ip)]
     lib.bppp_nl_prove_device.argtypes = [vp, sz, u8p, u8p, u8p, u8p, u8p]

@@ -56,6 +56,67 @@ def _prove_device(ctx, gens, inp, C0):
     return dict(ms=ms, wall_ms=1e3 * wall, resp=resp.raw[:128 * k], es=es.raw[:32 * k], fw=fw.raw[:128], fl=fl.raw[:32])
 
 
+def sharded_local_rounds(e, world):
+    """fold locally until the gathered argument has at most 4096 norm elements (then it re-bases to tensor mode)"""
+    ln = e - (world.bit_length() - 1)                         # log2 of the slice length
+    return max(0, min(ln, e - 12))
+
+
+def make_comm(ctx, world, rank, broadcast=None):
+    """bppp_comm over NCCL: rank 0 draws the id, `broadcast(bytes_or_None) -> bytes` hands it to every rank"""
+    lib = ctx.lib
+    comm = C.c_void_p()
+    if world == 1:
+        ctx._ck(lib.bppp_comm_create(ctx.h, 1, 0, None, C.byref(comm)), "bppp_comm_create")
+        return comm
+    try:                                                      # the NCCL torch.distributed itself uses
+        import nvidia.nccl
+        import os
+        path = os.path.join(list(nvidia.nccl.__path__)[0], "lib", "libnccl.so.2").encode()
+    except Exception:
+        path = None
+    if lib.bppp_comm_load(path):
+        raise RuntimeError("bppp_comm_load: " + lib.bppp_comm_last_error().decode())
+    idb = C.create_string_buffer(128)
+    if rank == 0 and lib.bppp_comm_unique_id(idb):
+        raise RuntimeError("bppp_comm_unique_id: " + lib.bppp_comm_last_error().decode())
+    raw = broadcast(idb.raw[:128] if rank == 0 else None)
+    ctx._ck(lib.bppp_comm_create(ctx.h, world, rank, raw, C.byref(comm)), "bppp_comm_create")
+    return comm
+
+
+def _prove_sharded(ctx, comm, rank, world, inp, points, C0, local_rounds, barrier=None):
+    """one argument over `world` ranks (bppp_nl_prove_sharded): this rank's contiguous slice of the norm vector and its
+    generators, the linear part on rank 0; returns the same fields as _prove_device (identical on every rank)"""
+    lib, k, N, M = ctx.lib, inp["rounds"], inp["N"], inp["M"]
+    ln = N // world
+    lo = rank * ln
+    Mr = M if rank == 0 else 0
+    gens, h, t = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    Hs = points[64 * (1 + N):64 * (1 + N + M)] if Mr else None
+    ctx._ck(lib.bppp_gens_create(ctx.h, ln, Mr, points[:64], points[64 * (1 + lo):64 * (1 + lo + ln)], Hs, C.byref(gens)), "bppp_gens_create")
+    ctx._ck(lib.bppp_nl_create_gens(gens, ARG_NL, 1, inp["q"], inp["s"], inp["w"][32 * lo:32 * (lo + ln)],
+                                    inp["l"] if Mr else None, inp["c"] if Mr else None, C.byref(h)), "bppp_nl_create_gens")
+    ctx._ck(lib.bppp_nl_set_shard(h, lo), "bppp_nl_set_shard")
+    ctx._ck(lib.bppp_dtr_create(ctx.h, 1, 1 + 2 * k, 0, C.byref(t)), "bppp_dtr_create")
+    resp, es = C.create_string_buffer(128 * k), C.create_string_buffer(32 * k)
+    s_out, fw, fl = C.create_string_buffer(32), C.create_string_buffer(32 * 4), C.create_string_buffer(32)
+    ctx.sync()
+    if barrier:
+        barrier()
+    ctx.timer_start()
+    t0 = time.time()
+    ctx._ck(lib.bppp_dtr_absorb(t, C0, 1, 1), "bppp_dtr_absorb")
+    ctx._ck(lib.bppp_nl_attach_transcript(h, t), "bppp_nl_attach_transcript")
+    ctx._ck(lib.bppp_nl_prove_sharded(h, comm, k, local_rounds, M, resp, es, s_out, fw, fl), "bppp_nl_prove_sharded")
+    ms = ctx.timer_stop()
+    wall = time.time() - t0
+    lib.bppp_nl_destroy(h)
+    lib.bppp_dtr_destroy(t)
+    lib.bppp_gens_destroy(gens)
+    return dict(ms=ms, wall_ms=1e3 * wall, resp=resp.raw[:128 * k], es=es.raw[:32 * k], fw=fw.raw[:128], fl=fl.raw[:32], s=s_out.raw[:32])
+
+
 def _verify(ctx, gens, inp, C0, pr):
     lib, k, N = ctx.lib, inp["rounds"], inp["N"]
     es = C.create_string_buffer(32 * k)
@@ -148,6 +209,54 @@ def run_one(ctx, e, points, imad_wide, hbm_gbs, reps=2, M=6):
                                    "kernels": [n for n in MSM_KERNELS if n in rep]}
     out["rooflines"] = roof
     return out
+
+
+def run_sharded(ctx, e, rank, world, dist=None, reps=3, M=6):
+    """N = 2^e over `world` ranks (strong scaling): every rank derives the same generators and witness, proves its
+    slice with bppp_nl_prove_sharded and asserts the result equals the unsharded bppp_nl_prove_device proof.
+    `dist` = torch.distributed (initialised, NCCL) or None for one rank.  Times are the max over ranks."""
+    import hashlib
+    lib = ctx.lib
+    N = 1 << e
+    P0 = 1 + N + M
+    points = W.sweep_generators(ctx, P0)
+    inp = W.sweep_inputs(ctx, e, M)
+    gens = C.c_void_p()
+    ctx._ck(lib.bppp_gens_create(ctx.h, N, M, points[:64], points[64:64 * (1 + N)], points[64 * (1 + N):64 * P0], C.byref(gens)), "bppp_gens_create")
+    C0b = C.create_string_buffer(64)
+    ctx._ck(lib.bppp_gens_msm_batch(gens, 1, P0, inp["s"] + inp["w"] + inp["l"], C0b), "bppp_gens_msm_batch")
+    C0 = C0b.raw[:64]
+    _prove_device(ctx, gens, inp, C0)
+    singles = [_prove_device(ctx, gens, inp, C0) for _ in range(reps)]
+    lib.bppp_gens_destroy(gens)
+    one = min(singles, key=lambda p: p["ms"])
+
+    def bcast(raw):
+        obj = [raw]
+        dist.broadcast_object_list(obj, src=0)
+        return obj[0]
+    comm = make_comm(ctx, world, rank, bcast if dist else None)
+    lr = sharded_local_rounds(e, world)
+    barrier = dist.barrier if dist else None
+    _prove_sharded(ctx, comm, rank, world, inp, points, C0, lr, barrier)
+    runs = [_prove_sharded(ctx, comm, rank, world, inp, points, C0, lr, barrier) for _ in range(reps)]
+    lib.bppp_comm_destroy(comm)
+    same = all(r[k] == one[k] for r in runs for k in ("resp", "es", "fw", "fl"))
+    ms = [r["ms"] for r in runs]
+    if dist:
+        import torch
+        t = torch.tensor(ms + [0.0 if same else 1.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, same = t[:-1].tolist(), t[-1].item() == 0.0
+    assert same, "sharded proof differs from the unsharded one"
+    best = min(ms)
+    return {"workload": "one NormLinear argument, N = 2^%d, M = %d, sharded over the GPUs (bppp_nl_prove_sharded: NCCL all-gather of "
+                        "256 B per rank and round inside the library)" % (e, M),
+            "e": e, "N": N, "M": M, "rounds": inp["rounds"], "n_gpus": world, "scaling": "strong", "local_rounds": lr,
+            "gathered_norm_length": ((N // world) >> lr) * world,
+            "prove_ms": round(best, 3), "prove_ms_all": [round(x, 3) for x in ms], "single_gpu_prove_ms": round(one["ms"], 3),
+            "speedup_vs_single_gpu": round(one["ms"] / best, 3), "bit_identical_to_unsharded": same,
+            "proof_checksum": hashlib.sha256(one["resp"] + one["fw"] + one["fl"]).hexdigest()[:16]}
 
 
 def run(ctx, sizes, imad_wide, hbm_gbs, reps=2):

@@ -155,6 +155,23 @@ int bppp_nl_round_challenge(bppp_nl* h, uint8_t* X, uint8_t* R, uint8_t* E);
  * bppp_nl_attach_transcript, e.g. after bppp_dtr_absorb of the initial commitment).  responses = [batch][rounds][2]
  * points and es = [batch][rounds] challenges (may be NULL), newest first; s / w / l as bppp_nl_final. */
 int bppp_nl_attach_transcript(bppp_nl* h, bppp_dtr* t);
+/* ---- one large argument over several GPUs: NCCL inside the library.  libnccl.so.2 is loaded at run
+ * time (bppp_comm_load(path), or the copy already in the process / the system's), so single-GPU users never need it.
+ * bppp_comm_unique_id on rank 0 -> hand the 128 bytes to every rank -> bppp_comm_create(ctx, world, rank, id).
+ * bppp_nl_prove_sharded: rank r holds the contiguous slice [r * len, (r + 1) * len) of the norm vector and its
+ * generators (bppp_nl_create over the slice + bppp_nl_set_shard(r * len); len a power of two), rank 0 also the linear
+ * part (lin_len entries; the other ranks create M = 0); same q, s and transcript state everywhere.  `local_rounds`
+ * rounds fold locally with the per-round partial commitments all-gathered (256 B per rank) and summed on the device;
+ * then the slices are gathered once and every rank finishes on the short whole argument.  Outputs on every rank as
+ * bppp_nl_prove_device; the proof equals the unsharded one bit for bit. */
+typedef struct bppp_comm bppp_comm;
+int bppp_comm_load(const char* libnccl_path);
+const char* bppp_comm_last_error(void);
+int bppp_comm_unique_id(uint8_t id[128]);
+int bppp_comm_create(bppp_ctx* ctx, int world, int rank, const uint8_t id[128], bppp_comm** out);
+void bppp_comm_destroy(bppp_comm* c);
+int bppp_nl_prove_sharded(bppp_nl* h, bppp_comm* comm, size_t rounds, size_t local_rounds, size_t lin_len,
+                          uint8_t* responses, uint8_t* es, uint8_t* s, uint8_t* w, uint8_t* l);
 int bppp_nl_prove_device(bppp_nl* h, size_t rounds, uint8_t* responses, uint8_t* es, uint8_t* s, uint8_t* w, uint8_t* l);
 /* the rest of proveRoundM (src/Bulletproof.hs:351-355): s' = s + e0*sX + e1*sR and `collapse e`
  * (NormArgument.hs:64-71,123-129 / InnerProductArgument.hs:86-101,155-170) with challenge e[b]. */

@@ -308,6 +308,32 @@ def test_device_round_loop_matches_host_sequencing(ctx, e):
     lib.bppp_gens_destroy(gens_h)
 
 
+@pytest.mark.parametrize("e,local_rounds", [(6, 0), (10, 3), (10, 8), (13, 4)])
+def test_sharded_prover_in_library_one_rank(ctx, e, local_rounds):
+    """bppp_nl_prove_sharded with a one-rank communicator: `local_rounds` rounds through the
+    pack / all-gather / combine path on the slice, then the gather of the folded state and the tail on the re-created
+    argument -- the proof must equal bppp_nl_prove_device on the whole argument bit for bit.  (Several ranks need one
+    GPU each: tools/sweep_sharded.py under torchrun asserts the same equality over NCCL on 2/4/8 GPUs.)"""
+    import ctypes as C
+    from bulletproofspp_b200 import sweep, workloads as W
+    lib = ctx.lib
+    N, M = 1 << e, 6
+    points = W.sweep_generators(ctx, 1 + N + M)
+    inp = W.sweep_inputs(ctx, e, M)
+    gens_h = C.c_void_p()
+    ctx._ck(lib.bppp_gens_create(ctx.h, N, M, points[:64], points[64:64 * (1 + N)], points[64 * (1 + N):], C.byref(gens_h)), "bppp_gens_create")
+    C0b = C.create_string_buffer(64)
+    ctx._ck(lib.bppp_gens_msm_batch(gens_h, 1, 1 + N + M, inp["s"] + inp["w"] + inp["l"], C0b), "bppp_gens_msm_batch")
+    C0 = C0b.raw[:64]
+    want = sweep._prove_device(ctx, gens_h, inp, C0)
+    comm = sweep.make_comm(ctx, 1, 0)
+    got = sweep._prove_sharded(ctx, comm, 0, 1, inp, points, C0, local_rounds)
+    for key in ("resp", "es", "fw", "fl"):
+        assert got[key] == want[key], key
+    lib.bppp_comm_destroy(comm)
+    lib.bppp_gens_destroy(gens_h)
+
+
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_sharded_argument_equals_unsharded(ctx, gens, world):
     """one argument split into `world` contiguous shards (emulated as `world` handles on
