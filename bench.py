@@ -182,6 +182,7 @@ def main():
     ap.add_argument("--host-threads", type=int, default=0)
     ap.add_argument("--sweep-sizes", default="10,14,18,20", help="log2 N of the synthetic norm-argument sweep (N=1 only)")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--sharded-size", type=int, default=20, help="log2 N of the argument sharded over the GPUs (N > 1 only)")
     ap.add_argument("--verify", default="batch", choices=["batch", "per-proof"],
                     help="batch: one random linear combination per lane sub-batch, per-proof checks only on failure (exact verdicts)")
     ap.add_argument("--transcript", default="device", choices=["device", "host"],
@@ -335,6 +336,16 @@ def main():
         t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         t_dev, t_e2e = t.tolist()
+    sharded = None
+    if world > 1 and not args.no_sweep:
+        # BASELINE.json config 5 on several GPUs: ONE 2^20-element norm argument sharded over the ranks
+        # (strong scaling; NCCL all-gather inside the library, bppp_nl_prove_sharded), after the timed regions
+        from bulletproofspp_b200 import sweep
+        vsetup.close(); setup.close(); psetup.close()
+        try:
+            sharded = sweep.run_sharded(ctx, args.sharded_size, rank, world, dist)
+        except Exception as ex:                    # reported, never silently dropped
+            sharded = {"error": repr(ex)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -418,6 +429,8 @@ def main():
         from bulletproofspp_b200 import sweep
         vsetup.close(); setup.close(); psetup.close()
         line["norm_arg_sweep"] = sweep.run(ctx, [int(x) for x in args.sweep_sizes.split(",") if x], imad_wide, hbm_peak)
+    if sharded is not None:
+        line["norm_arg_sharded"] = sharded
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -732,6 +732,7 @@ struct bppp_dtr {
     DBuf<unsigned char> buf;
     DBuf<unsigned> start;               // [B][TR_MAX_CALLS + 1]
     DBuf<u256> chal;                    // [B][TR_MAX_CHAL]
+    DBuf<u256> chal_inv;                // the same challenges inverted (filled on request)
     DBuf<Affine> stage;
 };
 extern "C" int bppp_dtr_create(bppp_ctx* ctx, size_t batch, size_t max_points, int show_format, bppp_dtr** out) {
@@ -814,6 +815,19 @@ int dtr_squeeze_dev(bppp_dtr* t, int n_chal, const unsigned char* idx, const uns
     CK(cudaGetLastError());
     return BPPP_OK;
 }
+// 1 / challenge for the n_chal challenges of the last squeeze (canonical, [batch][n_chal]) in t->chal_inv: the
+// provers and verifiers need e^-1, r^-1, q^-1 right away, and a field inversion is the most expensive scalar
+// operation the host would otherwise do per proof
+int dtr_invert_dev(bppp_dtr* t, int n_chal) {
+    bppp_ctx* ctx = t->ctx;
+    const size_t n = t->B * (size_t)n_chal;
+    CK(t->chal_inv.ensure(t->B * TR_MAX_CHAL));
+    { ProfScope ps_(ctx, K_TR_SQUEEZE, 0);
+    k_fr_inv_rows<<<(unsigned)((n + 127) / 128), 128, 0, ctx->st>>>(t->chal.p, t->chal_inv.p, n);
+    }
+    CK(cudaGetLastError());
+    return BPPP_OK;
+}
 int dtr_squeeze_first(bppp_dtr* t, int count) {        // scalars 1..count of the current transcript
     unsigned char idx[9];
     if (count < 1 || count > 9) { t->ctx->err = "device transcript: 1..9 challenges per oracle call"; return BPPP_ERR_ARG; }
@@ -858,7 +872,7 @@ extern "C" int bppp_dtr_export(bppp_dtr* t, size_t proof, uint8_t* out, size_t c
     return BPPP_OK;
 }
 // challenges of any earlier stage: out[b][j] = scalar idx[j] after state[j] absorb calls (state NULL / 0: all calls)
-extern "C" int bppp_dtr_squeeze(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out) {
+static int dtr_squeeze_impl(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out, uint8_t* inv_out) {
     if (!t) return BPPP_ERR_ARG;
     bppp_ctx* ctx = t->ctx;
     if (!idx || !out) FAIL(BPPP_ERR_ARG, "bppp_dtr_squeeze: null argument");
@@ -866,8 +880,20 @@ extern "C" int bppp_dtr_squeeze(bppp_dtr* t, size_t n_chal, const uint8_t* idx, 
     int rc = dtr_squeeze_dev(t, (int)n_chal, idx, state);
     if (rc) return rc;
     CK(D2H(out, t->chal.p, t->B * n_chal * 32));
+    if (inv_out) {
+        if ((rc = dtr_invert_dev(t, (int)n_chal))) return rc;
+        CK(D2H(inv_out, t->chal_inv.p, t->B * n_chal * 32));
+    }
     CK(ctx_sync(ctx));
     return BPPP_OK;
+}
+extern "C" int bppp_dtr_squeeze(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out) {
+    return dtr_squeeze_impl(t, n_chal, idx, state, out, nullptr);
+}
+// the same plus inv_out[b][j] = 1 / out[b][j] (0 -> 0), inverted on the device
+extern "C" int bppp_dtr_squeeze_inv(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out, uint8_t* inv_out) {
+    if (!inv_out) return BPPP_ERR_ARG;
+    return dtr_squeeze_impl(t, n_chal, idx, state, out, inv_out);
 }
 // `oracle xs` for host-resident commitments: pts = [batch][npts] points, out = [batch][count] challenges
 extern "C" int bppp_dtr_oracle(bppp_dtr* t, const uint8_t* pts, size_t npts, int count, uint8_t* out) {
@@ -1775,6 +1801,10 @@ struct bppp_trrp {
     // produced and the challenges come back with them
     int tr_fmt = -1;
     bppp_dtr* tr = nullptr;
+    uint8_t* chal_inv_out = nullptr;   // host buffer the next _tr call also fills with the inverted challenges (one-shot)
+    size_t n_shared = 0;               // shared-multiplicity coefficient slots (bppp_trrp_set_shared)
+    DBuf<int> sh_bidx;
+    DBuf<u256> sh_sym, sh_out;
     DBuf<unsigned char> seeds, seed_len;
     DBuf<unsigned long long> n0s;
 };
@@ -1815,11 +1845,71 @@ int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double
         if ((rc = dtr_absorb_dev(t, src, per, per))) return rc;
         if ((rc = dtr_squeeze_first(t, count))) return rc;
         CK(D2H(chal_out, t->chal.p, t->B * (size_t)count * 32));
+        if (h->chal_inv_out) {
+            if ((rc = dtr_invert_dev(t, count))) return rc;
+            CK(D2H(h->chal_inv_out, t->chal_inv.p, t->B * (size_t)count * 32));
+            h->chal_inv_out = nullptr;
+        }
     }
     CK(ctx_sync(ctx));
     return BPPP_OK;
 }
 }  // namespace
+// one-shot: the next bppp_trrp_*_tr call also writes 1 / challenge for each of its challenges to `out` (same layout)
+extern "C" int bppp_trrp_want_inverses(bppp_trrp* h, uint8_t* out) {
+    if (!h) return BPPP_ERR_ARG;
+    h->chal_inv_out = out;
+    return BPPP_OK;
+}
+// makeSharedCoeffs on the device (TypedReciprocal.hs:204-206).  Static part, once per setup: slot i belongs to shared
+// base number base_idx[i] (index into the setup's sorted base list) and symbol sym[i] (canonical scalar).
+extern "C" int bppp_trrp_set_shared(bppp_trrp* h, size_t n_slots, const int32_t* base_idx, const uint8_t* sym) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (n_slots && (!base_idx || !sym)) FAIL(BPPP_ERR_ARG, "bppp_trrp_set_shared: null argument");
+    ENTER(ctx);
+    for (size_t i = 0; i < n_slots; i++)
+        if (base_idx[i] < 0 || (size_t)base_idx[i] >= h->n_bases) FAIL(BPPP_ERR_ARG, "bppp_trrp_set_shared: base index out of range");
+    if (!check_fr(sym, n_slots)) FAIL(BPPP_ERR_RANGE, "scalar >= group order");
+    h->n_shared = n_slots;
+    if (!n_slots) return BPPP_OK;
+    CK(h->sh_bidx.alloc(n_slots)); CK(h->sh_sym.alloc(n_slots));
+    CK(cudaMemcpyAsync(h->sh_bidx.p, base_idx, n_slots * sizeof(int), cudaMemcpyHostToDevice, ctx->st));
+    CK(cudaMemcpyAsync(h->sh_sym.p, sym, n_slots * 32, cudaMemcpyHostToDevice, ctx->st));
+    k_fr_convert<<<(unsigned)((n_slots + 255) / 256), 256, 0, ctx->st>>>(h->sh_sym.p, h->sh_sym.p, n_slots, 1);
+    CK(cudaGetLastError());
+    CK(ctx_sync(ctx));
+    return BPPP_OK;
+}
+// Per batch: out[b][i] = base power of slot i * (1/e - 1/(e + sym_i)) for the challenges e of the last bppp_trrp_phase2*
+// (prover) or bppp_trrp_verify_pub (verifier) call.  montgomery != 0: residues times 2^256 mod r (the library's
+// internal form, what the host layer multiplies with); else canonical scalars.
+extern "C" int bppp_trrp_shared_coeffs(bppp_trrp* h, int montgomery, uint8_t* out) {
+    if (!h) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = h->gens->ctx;
+    if (!out) FAIL(BPPP_ERR_ARG, "bppp_trrp_shared_coeffs: null output");
+    if (!h->n_shared) FAIL(BPPP_ERR_STATE, "bppp_trrp_shared_coeffs: bppp_trrp_set_shared first");
+    if (h->phase != 2 && h->phase != 10) FAIL(BPPP_ERR_STATE, "bppp_trrp_shared_coeffs: after bppp_trrp_phase2 or bppp_trrp_verify_pub");
+    ENTER(ctx);
+    const size_t B = h->B, S = h->n_shared;
+    const u256* chal = h->phase == 2 ? h->chal2.p : h->chalv.p;
+    const int stride = h->phase == 2 ? 4 : 8;
+    CK(h->sh_out.ensure(B * S));
+    const int per = (int)((S + 31) / 32);
+    { ProfScope ps_(ctx, K_TRRP, 0);
+    k_trrp_shared<<<(unsigned)((per * B + 3) / 4), 128, 0, ctx->st>>>(chal, stride, h->vt.p, (int)h->n_bases, h->sh_bidx.p, h->sh_sym.p, (int)S, (int)B, h->sh_out.p);
+    }
+    CK(cudaGetLastError());
+    if (!montgomery) {
+        { ProfScope ps_(ctx, K_FR_CONVERT, 0);
+        k_fr_convert<<<(unsigned)((B * S + 255) / 256), 256, 0, ctx->st>>>(h->sh_out.p, h->sh_out.p, B * S, 0);
+        }
+        CK(cudaGetLastError());
+    }
+    CK(D2H(out, h->sh_out.p, B * S * 32));
+    CK(ctx_sync(ctx));
+    return BPPP_OK;
+}
 
 extern "C" int bppp_trrp_create(bppp_gens* gens, size_t n_entries, const uint8_t* ent_desc, const uint8_t* ent_b,
                                 const uint8_t* ent_s, size_t n_ranges, size_t n_bases, bppp_trrp** out) {

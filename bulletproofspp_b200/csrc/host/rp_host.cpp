@@ -345,6 +345,7 @@ struct bppp_rp {
     bool dev_transcript = false;
     // verify a lane's sub-batch by one random linear combination first, per-proof checks only if it fails
     bool batch_verify = false;
+    size_t n_shared = 0;                       // shared-multiplicity coefficient slots computed on the device
     std::vector<bppp_dtr*> lane_vtr;           // verifier transcripts, one per lane (created on first use)
     std::mutex err_mu;
     std::string err;
@@ -920,7 +921,7 @@ struct Lane {
     bppp_trrp* trrp = nullptr;                 // device scalar phases (TypedReciprocal + norm-linear argument)
 };
 enum { PB_IN = 0, PB_SC1, PB_SC2, PB_C1, PB_C2, PB_NCOMS, PB_Q, PB_S, PB_W, PB_L, PB_C, PB_X, PB_R, PB_E, PB_V0, PB_V1, PB_V2, PB_V3,
-       PB_V4, PB_V5, PB_V6, PB_V7, PB_V8, PB_CH, PB_SCLIN, PB_BLN, PB_SMALL, PB_CHT, PB_COUNT };
+       PB_V4, PB_V5, PB_V6, PB_V7, PB_V8, PB_CH, PB_SCLIN, PB_BLN, PB_SMALL, PB_CHT, PB_CHI, PB_SHC, PB_COUNT };
 // uninitialised page-locked buffer `slot` of the lane, at least `bytes` long
 uint8_t* lane_buf(bppp_rp* s, const Lane& ln, int slot, size_t bytes) {
     auto& pb = s->pinned[ln.index][slot];
@@ -1237,6 +1238,24 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
                 rc2 = bppp_trrp_create(s->lane_gens[i], ne, desc.data(), eb.data(), es.data(), s->rds.size(), s->sorted_bases.size(), &t);
                 if (!rc2) s->lane_trrp.push_back(t);
             }
+            // makeSharedCoeffs' static part (TypedReciprocal.hs:204-206): slot -> (shared base, symbol)
+            std::vector<int32_t> sh_b;
+            std::vector<uint8_t> sh_s;
+            for (auto b : s->m_bases) {
+                int32_t bi = 0;
+                for (size_t j = 0; j < s->sorted_bases.size(); j++)
+                    if (s->sorted_bases[j] == b) bi = (int32_t)j;
+                for (U128 sv = 1; sv < b; sv++) {
+                    sh_b.push_back(bi);
+                    sh_s.resize(sh_s.size() + 32, 0);
+                    memcpy(&sh_s[sh_s.size() - 32], &sv, 16);
+                }
+            }
+            s->n_shared = sh_b.size();
+            if (!rc2 && s->n_shared) {
+                rc2 = bppp_trrp_set_shared(s->trrp, s->n_shared, sh_b.data(), sh_s.data());
+                for (size_t i = 0; !rc2 && i < s->lane_trrp.size(); i++) rc2 = bppp_trrp_set_shared(s->lane_trrp[i], s->n_shared, sh_b.data(), sh_s.data());
+            }
             if (rc2) { bppp_rp_free(s); return rc2; }
             s->dev_phases = true;
             const char* dv = getenv("BPPP_DEVICE_TRANSCRIPT");
@@ -1315,8 +1334,9 @@ int bppp_input_blind(const char* random_seed, uint64_t j, uint8_t out[32]) {
 // leave the GPU.
 static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, uint8_t* coms, uint8_t* responses, uint8_t* finals,
                              const uint8_t* c1, const uint8_t* n_coms, const char* const* random_seeds, uint8_t* cht) {
-    // cht != NULL: device transcript -- the challenges of the last oracle call, [batch][3]
+    // cht != NULL: device transcript -- the challenges of the last oracle call, [batch][3]; chi: their inverses
     const bool dt = cht != nullptr;
+    uint8_t* chi = dt ? lane_buf(s, ln, PB_CHI, P.size() * 3 * 32) : nullptr;
     const size_t B = P.size(), n = s->n_inputs, N = s->nrm_len, M = s->lin_len, NC = s->num_rp_coms + n;
     uint8_t* ch = lane_buf(s, ln, PB_CH, B * 4 * 32);
     uint8_t* sclin = lane_buf(s, ln, PB_SCLIN, B * (1 + M) * 32);
@@ -1348,9 +1368,13 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         else p.zk.oracle(out + 128, 2 + n, chs, 3);                         // T3 e x r0 <- oracle' (dmCom:mCom:nComs)
         sect.lap(S_ORACLE);
         p.e = chs[0]; p.x = chs[1]; p.r0 = chs[2];
-        Fr iv[2] = {p.e, p.r0};
-        h64::batch_inv(iv, 2);
-        p.e_inv = iv[0]; p.r0_inv = iv[1];
+        if (dt) {
+            p.e_inv = h64::from_bytes(chi + 32 * (3 * b)); p.r0_inv = h64::from_bytes(chi + 32 * (3 * b + 2));
+        } else {
+            Fr iv[2] = {p.e, p.r0};
+            h64::batch_inv(iv, 2);
+            p.e_inv = iv[0]; p.r0_inv = iv[1];
+        }
         p.base_map = make_base_map(s, p.x);
         p.dm.nrm.clear(); p.m.nrm.clear(); p.ph1s.clear();                  // the norm parts live on the device
         p.r = blind_err_witness(p.zk, 3, {h64::zero()}, {}, {});            // err7 is filled in by the device
@@ -1361,8 +1385,17 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_SCALARS);
     });
     g_tm.lap("host_phase2");
+    if (dt) bppp_trrp_want_inverses(ln.trrp, chi);                             // 1/q, 1/x', 1/r1
     int rc = dt ? bppp_trrp_phase2_tr(ln.trrp, ch, sclin, ERR7_SLOT, c2, small, cht) : bppp_trrp_phase2(ln.trrp, ch, sclin, ERR7_SLOT, c2, small);
     if (rc) return fail(s, rc, std::string("reciprocal commitment: ") + ctx_err(ln));
+    // the shared-multiplicity coefficients (255 reciprocals per proof for base 256) come from the device as well
+    const uint8_t* shc = nullptr;
+    if (dt && s->n_shared) {
+        uint8_t* o = lane_buf(s, ln, PB_SHC, B * s->n_shared * 32);
+        rc = bppp_trrp_shared_coeffs(ln.trrp, 1, o);
+        if (rc) return fail(s, rc, std::string("shared coefficients: ") + ctx_err(ln));
+        shc = o;
+    }
     g_tm.lap("msm_phase2");
     // ---------------- phase 3
     bool dev_rnd = dt;
@@ -1380,12 +1413,20 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_ORACLE);
         p.q = chs[0]; p.xq = chs[1]; p.r1 = chs[2];
         p.q0 = q0_of(s->arg, p.q);
-        Fr iv[3] = {p.q, p.q0, p.r1};
-        h64::batch_inv(iv, 3);
-        p.q_inv = iv[0]; p.q0_inv = iv[1]; p.r1_inv = iv[2];
+        if (dt) {
+            p.q_inv = h64::from_bytes(chi + 32 * (3 * b)); p.r1_inv = h64::from_bytes(chi + 32 * (3 * b + 2));
+            p.q0_inv = q0_of(s->arg, p.q_inv);                              // 1 / (+-q^2) = +-(1/q)^2
+        } else {
+            Fr iv[3] = {p.q, p.q0, p.r1};
+            h64::batch_inv(iv, 3);
+            p.q_inv = iv[0]; p.q0_inv = iv[1]; p.r1_inv = iv[2];
+        }
         std::vector<U128> mb;
         for (auto& kv : p.base_mss) mb.push_back(kv.first);
-        p.shared_cs = make_shared_coeffs(p.e, p.e_inv, mb, p.base_map);
+        if (shc && mb == s->m_bases) {                                      // Montgomery residues: the host's own form
+            p.shared_cs.resize(s->n_shared);
+            memcpy((void*)p.shared_cs.data(), shc + 32 * b * s->n_shared, 32 * s->n_shared);
+        } else p.shared_cs = make_shared_coeffs(p.e, p.e_inv, mb, p.base_map);
         sect.lap(S_COEFFS);
         p.bls_lin.resize(M > 5 ? M - 5 : 0);
         p.zk.random_fill(p.bls_lin.data(), p.bls_lin.size());
@@ -1722,8 +1763,10 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
     const bool dev = s->dev_phases && ln.trrp;
     const bool dt = dev && s->dev_transcript;
     uint8_t* cht = dt ? lane_buf(s, ln, PB_CHT, B * 3 * 32) : nullptr;
-    if (dt) bppp_trrp_set_transcript(ln.trrp, s->fmt);
-    else if (dev) bppp_trrp_set_transcript(ln.trrp, -1);
+    if (dt) {
+        bppp_trrp_set_transcript(ln.trrp, s->fmt);
+        bppp_trrp_want_inverses(ln.trrp, lane_buf(s, ln, PB_CHI, B * 3 * 32));      // 1/e, 1/x, 1/r0 come back inverted
+    } else if (dev) bppp_trrp_set_transcript(ln.trrp, -1);
     rc = dt ? bppp_trrp_phase1_tr(ln.trrp, B, sc1, values, n, n_coms, c1, cht)
             : dev ? bppp_trrp_phase1(ln.trrp, B, sc1, values, c1) : bppp_gens_msm_batch(ln.gens, B * (s->binary ? 1 : 2), P0, sc1, c1);
     if (rc) return fail(s, rc, std::string("digit commitments: ") + ctx_err(ln));
@@ -1952,6 +1995,7 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         // device transcript: every commitment of the proofs is rendered once, then ONE launch squeezes the
         // challenges of all stages (each stage's transcript is a suffix of the final one)
         const uint8_t* dch = nullptr;
+        const uint8_t* dchi = nullptr;
         const size_t n_ch = 7 + k;
         if (s->dev_transcript && k + 3 <= 64) {
             if ((size_t)ln.index >= s->lane_vtr.size()) return fail(s, BPPP_ERR_STATE, "lane without a transcript slot");
@@ -1967,9 +2011,11 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             idx[1] = 2; idx[2] = 3; idx[4] = 2; idx[5] = 3;
             for (size_t j = 0; j < n_ch; j++) st[j] = (uint8_t)(j < 3 ? 1 : j < 6 ? 2 : j == 6 ? 3 : 4 + (j - 7));
             uint8_t* out = lane_buf(s, ln, PB_CHT, B * n_ch * 32);
-            if (!rc) rc = bppp_dtr_squeeze(t, n_ch, idx.data(), st.data(), out);
+            uint8_t* outi = lane_buf(s, ln, PB_CHI, B * n_ch * 32);
+            if (!rc) rc = bppp_dtr_squeeze_inv(t, n_ch, idx.data(), st.data(), out, outi);
             if (rc) return fail(s, rc, std::string("device transcript: ") + ctx_err(ln));
             dch = out;
+            dchi = outi;
             g_tm.lap("verify_transcript");
         }
         parallel_for(B, [&](size_t b) {
@@ -2002,9 +2048,14 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             for (size_t r = 0; r < k; r++) h64::to_bytes(&es_b[32 * (b * k + (k - 1 - r))], es[r]);
             }
             sect.lap(S_V_ORACLE);
-            Fr iv[2] = {v.e, v.q0};
-            h64::batch_inv(iv, 2);
-            v.e_inv = iv[0]; v.q0_inv = iv[1];
+            if (dchi) {
+                v.e_inv = h64::from_bytes(dchi + 32 * b * n_ch);
+                v.q0_inv = q0_of(s->arg, h64::from_bytes(dchi + 32 * (b * n_ch + 3)));    // 1 / (+-q^2) = +-(1/q)^2
+            } else {
+                Fr iv[2] = {v.e, v.q0};
+                h64::batch_inv(iv, 2);
+                v.e_inv = iv[0]; v.q0_inv = iv[1];
+            }
             uint8_t* o = ch + 32 * 8 * b;
             h64::to_bytes(o, v.e); h64::to_bytes(o + 32, v.e_inv); h64::to_bytes(o + 64, v.x); h64::to_bytes(o + 96, v.xq);
             h64::to_bytes(o + 128, v.q0); h64::to_bytes(o + 160, v.q0_inv); h64::to_bytes(o + 192, v.t);
@@ -2014,6 +2065,13 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
         g_tm.lap("verify_host");
         int rc = bppp_trrp_verify_pub(ln.trrp, B, ch, small);
         if (rc) return fail(s, rc, std::string("bppp_trrp_verify_pub: ") + ctx_err(ln));
+        const uint8_t* shc = nullptr;
+        if (dch && s->n_shared) {
+            uint8_t* o = lane_buf(s, ln, PB_SHC, B * s->n_shared * 32);
+            rc = bppp_trrp_shared_coeffs(ln.trrp, 1, o);
+            if (rc) return fail(s, rc, std::string("shared coefficients: ") + ctx_err(ln));
+            shc = o;
+        }
         g_tm.lap("verify_pub");
         parallel_for(B, [&](size_t b) {
             using namespace h64;
@@ -2024,8 +2082,15 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             const Fr t2 = sqr(v.t), t3 = mul(t2, v.t), t5 = mul(sqr(t2), v.t), two_t5 = dbl(t5);
             const Fr sp = add(public_consts_z_trrp(s, v.e, v.x, two_t5), add(ts0, mul(two_t5, add(sum_q2, mul(v.e_inv, sum_v)))));
             sect.lap(S_V_PUB);
-            std::map<U128, Fr> bm = make_base_map(s, v.x);
-            std::vector<Fr> cs = make_bp_coeffs(s->flag, v.xq, v.r0, v.r1, v.t, make_shared_coeffs(v.e, v.e_inv, s->m_bases, bm));
+            std::vector<Fr> shared;
+            if (shc) {
+                shared.resize(s->n_shared);
+                memcpy((void*)shared.data(), shc + 32 * b * s->n_shared, 32 * s->n_shared);
+            } else {
+                std::map<U128, Fr> bm = make_base_map(s, v.x);
+                shared = make_shared_coeffs(v.e, v.e_inv, s->m_bases, bm);
+            }
+            std::vector<Fr> cs = make_bp_coeffs(s->flag, v.xq, v.r0, v.r1, v.t, shared);
             // TranscriptTRRP.openWith (TypedReciprocal.hs:279-282): [1,t,t^2,t^3] on [bl,m,dm,r]
             std::vector<Fr> init_s = {one(), t3, t2, v.t};                  // coms order: bl, r, dm, m
             for (auto& c : input_coeffs_trrp(s, v.x, v.q0)) init_s.push_back(mul(two_t5, c));

@@ -1172,6 +1172,55 @@ __global__ void k_trrp_tables(const u256* __restrict__ chal, int chal_stride, in
     cur = fr::mul(x2, x);
     for (int j = 0; j < n_bases; j++) { st_u256(vt + (size_t)p * n_bases + j, cur); cur = fr::mul(cur, x2); }
 }
+// Montgomery's trick across a warp: every lane gets 1 / v of its own v (0 -> 0, BatchInverse.hs:14-24) for ONE
+// field inversion per warp -- prefix and suffix products by shuffles, lane 0 inverts the total.
+__device__ __forceinline__ u256 warp_batch_inv(const u256& v) {
+    const int lane = threadIdx.x & 31;
+    const bool nz = !u256_is_zero(v);
+    const u256 x = nz ? v : fr::one();
+    u256 P = x, Q = x;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const u256 o = shfl_u256(P, (lane - d) & 31);
+        if (lane >= d) P = fr::mul(P, o);
+    }
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const u256 o = shfl_u256(Q, (lane + d) & 31);
+        if (lane + d < 32) Q = fr::mul(Q, o);
+    }
+    u256 it = u256_zero();
+    if (lane == 31) it = fr::inv(P);                                       // P of lane 31 = the product of all
+    it = shfl_u256(it, 31);
+    const u256 left = shfl_u256(P, (lane - 1) & 31), right = shfl_u256(Q, (lane + 1) & 31);
+    u256 r = it;
+    if (lane > 0) r = fr::mul(r, left);
+    if (lane < 31) r = fr::mul(r, right);
+    return nz ? r : u256_zero();
+}
+// makeSharedCoeffs (TypedReciprocal.hs:204-206): slot i of a proof belongs to shared base number bidx[i] and
+// symbol sv[i] (Montgomery): out[p][i] = x^(3 + 2 bidx) * (1/e - 1/(e + s)).  chal = [B][stride] canonical with e
+// at position 0 and 1/e at position 1; vt = the base powers of k_trrp_tables.  One warp per 32 slots.
+__global__ void __launch_bounds__(128) k_trrp_shared(const u256* __restrict__ chal, int chal_stride, const u256* __restrict__ vt, int n_bases,
+                                                     const int* __restrict__ bidx, const u256* __restrict__ sv, int n_slots, int B,
+                                                     u256* __restrict__ out) {
+    const int per = (n_slots + 31) / 32;                                   // warps per proof
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= per * B) return;
+    const int p = w / per, i = (w % per) * 32 + (threadIdx.x & 31);
+    const bool live = i < n_slots;
+    const u256 e = fr::to_mont(ld_u256(chal + (size_t)p * chal_stride)), e_inv = fr::to_mont(ld_u256(chal + (size_t)p * chal_stride + 1));
+    const u256 den = live ? fr::add(e, ld_u256(sv + i)) : u256_zero();
+    const u256 rec = warp_batch_inv(den);
+    if (live) st_u256(out + (size_t)p * n_slots + i, fr::mul(ld_u256(vt + (size_t)p * n_bases + bidx[i]), fr::sub(e_inv, rec)));
+}
+// out[i] = 1 / in[i] (canonical in, canonical out, 0 -> 0): the inverses of freshly squeezed challenges
+__global__ void __launch_bounds__(128) k_fr_inv_rows(const u256* __restrict__ in, u256* __restrict__ out, size_t n) {
+    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    const u256 v = t < n ? fr::to_mont(ld_u256(in + t)) : u256_zero();
+    const u256 r = warp_batch_inv(v);
+    if (t < n) st_u256(out + t, fr::from_mont(r));
+}
 struct TrrpEntry { u256 d, m, u, v; bool isT, live; };
 __device__ __forceinline__ void trrp_load_entry(TrrpEntry& o, const TrrpStatic& st, int i, const u256* scA_dm, const u256* scA_m,
                                                 const u256* xp, const u256* vt, const u256& x, bool want_m) {

@@ -27,6 +27,7 @@ EXPORTS = [
     "bppp_trrp_phase4", "bppp_nl_create_trrp", "bppp_trrp_verify_pub", "bppp_nl_verify_trrp",
     "bppp_dtr_absorb", "bppp_dtr_squeeze", "bppp_dtr_fits", "bppp_dtr_export", "bppp_rp_set_device_transcript", "bppp_nl_round_challenge",
     "bppp_nl_attach_transcript", "bppp_nl_prove_device", "bppp_rp_set_batch_verify", "bppp_nl_verify_trrp_rlc", "bppp_nl_verify_gens_rlc",
+    "bppp_dtr_squeeze_inv", "bppp_trrp_want_inverses", "bppp_trrp_set_shared", "bppp_trrp_shared_coeffs",
     "bppp_comm_load", "bppp_comm_last_error", "bppp_comm_unique_id", "bppp_comm_create", "bppp_comm_destroy", "bppp_nl_prove_sharded",
     "bppp_trrp_set_transcript", "bppp_trrp_phase1_tr", "bppp_trrp_phase2_tr", "bppp_trrp_phase3_rnd", "bppp_trrp_commit_bl_tr",
 ]

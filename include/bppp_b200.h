@@ -96,13 +96,16 @@ int bppp_dtr_reset(bppp_dtr* t);
 /* `oracle xs` / `oracle'` (src/ZKP.hs:96-101, 60-63; shaOracle app/Main.hs:75-80): prepend pts = [batch][npts]
  * to every proof's list, then out = [batch][count] = the first `count` (<= 9) scalars of shaOracle */
 int bppp_dtr_oracle(bppp_dtr* t, const uint8_t* pts, size_t npts, int count, uint8_t* out);
-/* the two halves separately, for a verifier that knows every commitment up front (verifyBPM's `oracle'` calls,
+/* (bppp_dtr_squeeze_inv also returns inv_out[b][j] = 1 / out[b][j], inverted on the device: the provers and verifiers
+ * need e^-1, q^-1, ... at once)
+ * the two halves separately, for a verifier that knows every commitment up front (verifyBPM's `oracle'` calls,
  * src/Bulletproof.hs:370-378): bppp_dtr_absorb is cs' = xs ++ cs alone -- row b of the call is the `npts` points at
  * pts + 64 * stride_points * b; bppp_dtr_squeeze then hashes any number of stages in ONE launch: out[b][j] = scalar
  * idx[j] (1-based, <= 9) of the transcript as it was after state[j] absorb calls (state NULL or 0: all of them).
  * Every earlier transcript is a suffix of the latest one (newest commitments first). */
 int bppp_dtr_absorb(bppp_dtr* t, const uint8_t* pts, size_t stride_points, size_t npts);
 int bppp_dtr_squeeze(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out);
+int bppp_dtr_squeeze_inv(bppp_dtr* t, size_t n_chal, const uint8_t* idx, const uint8_t* state, uint8_t* out, uint8_t* inv_out);
 int bppp_dtr_fits(bppp_dtr* t, size_t batch, size_t max_points, int show_format);
 /* the rendered list of one proof, concat [show x <> show y] newest first (what app/Main.hs:78-80 feeds the hash) */
 int bppp_dtr_export(bppp_dtr* t, size_t proof, uint8_t* out, size_t cap, size_t* len);
@@ -252,6 +255,14 @@ int bppp_trrp_commit_bl(bppp_trrp* h, const uint8_t* bl_sclin, uint8_t* blcom);
  * and bppp_nl_create_trrp hands the transcript on to the argument (bppp_nl_round_challenge).
  * phase3_rnd draws the N norm blinders on the device: `random` values n0[b] .. n0[b]+N-1 of seeds[b]. */
 int bppp_trrp_set_transcript(bppp_trrp* h, int show_format);
+/* one-shot: the next _tr call also writes 1 / challenge for each of its challenges to `out` (same layout) */
+int bppp_trrp_want_inverses(bppp_trrp* h, uint8_t* out);
+/* makeSharedCoeffs (TypedReciprocal.hs:204-206) on the device.  Once per setup: slot i belongs to shared base number
+ * base_idx[i] (index into the sorted base list) and symbol sym[i].  Then, after bppp_trrp_phase2* (prover) or
+ * bppp_trrp_verify_pub (verifier): out[b][i] = x^(3 + 2 base_idx[i]) * (1/e - 1/(e + sym[i])); montgomery != 0
+ * returns residues times 2^256 mod r (the library's internal form) instead of canonical scalars. */
+int bppp_trrp_set_shared(bppp_trrp* h, size_t n_slots, const int32_t* base_idx, const uint8_t* sym);
+int bppp_trrp_shared_coeffs(bppp_trrp* h, int montgomery, uint8_t* out);
 int bppp_trrp_phase1_tr(bppp_trrp* h, size_t batch, const uint8_t* sc_dm_m, const uint8_t* amounts, size_t n_inputs,
                         const uint8_t* n_coms, uint8_t* coms, uint8_t* chal);
 int bppp_trrp_phase2_tr(bppp_trrp* h, const uint8_t* chal, const uint8_t* r_sclin, size_t err7_slot, uint8_t* rcom,
