@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--sweep-sizes", default="10,14,18,20", help="log2 N of the synthetic norm-argument sweep (N=1 only)")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--sharded-size", type=int, default=20, help="log2 N of the argument sharded over the GPUs (N > 1 only)")
+    ap.add_argument("--lut-gb", type=float, default=48.0,
+                    help="memory budget of the generators' full-multiples table (csrc/lut.cuh); 0 = nine-bit bucket kernel")
     ap.add_argument("--verify", default="batch", choices=["batch", "per-proof"],
                     help="batch: one random linear combination per lane sub-batch, per-proof checks only on failure (exact verdicts)")
     ap.add_argument("--transcript", default="device", choices=["device", "host"],
@@ -215,6 +217,11 @@ def main():
     setup.set_device_transcript(dev_tr)
     vsetup.set_device_transcript(dev_tr)
     vsetup.set_batch_verify(args.verify == "batch")
+    t_lut = time.time()
+    lut_c = setup.enable_lut(args.lut_gb) if args.lut_gb > 0 else 0
+    if lut_c:
+        vsetup.enable_lut(args.lut_gb)
+    t_lut = time.time() - t_lut
     lanes = setup.contexts() + vsetup.contexts()
     B, n = args.batch, setup.n_inputs
     assert (setup.nrm_len, setup.lin_len, setup.rounds) == (1024, 261, 9)
@@ -320,6 +327,8 @@ def main():
     psetup = bp.RangeProofSetup(pctx, workload_schema())
     psetup.set_device_transcript(dev_tr)
     psetup.set_batch_verify(args.verify == "batch")
+    if lut_c:
+        psetup.enable_lut(args.lut_gb)
     pin = make_inputs(Bp, base, n)
     proof = psetup.prove_batch_raw(Bp, pin[0], pin[1], None, pin[2])            # warm-up (tables, pools)
     pctx.profile_enable(True)
@@ -399,6 +408,10 @@ def main():
                        "batch_per_gpu": B, "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "working set per step (%.0f MB of generators+witness vectors) exceeds the 126 MB L2" % (B * 0.33),
                        "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world), "lanes": len(lanes),
+                       "msm_table": ("full-multiples table in HBM, window %d bits: %d lookups + mixed additions per term, %.1f GB, built once "
+                                     "per process in %.2f s before the timed regions (csrc/lut.cuh)" % (
+                                         lut_c, (256 + lut_c - 1) // lut_c, 1286 * ((256 + lut_c - 1) // lut_c) * 2 ** (lut_c - 1) * 64 / 1e9, t_lut))
+                                    if lut_c else "nine-bit window table + bucket kernel (k_msm_gens)",
                        "verify": "batch verification across proofs: one random linear combination per lane sub-batch of %d proofs (128-bit "
                                  "weights from getrandom), per-proof checks locate failures (SURVEY 8 f2)" % max(1, B // (len(lanes) // 2))
                                  if args.verify == "batch" else "per proof (the reference's verifyM)",

@@ -21,19 +21,20 @@
 #include "pippenger.cuh"
 #include "transcript.cuh"
 #include "rounds.cuh"
+#include "lut.cuh"
 
 using namespace bppp;
 
 static thread_local cudaStream_t g_alloc_stream = nullptr;   // set at every API entry (ENTER)
 
 enum KernelId { K_FR_CONVERT = 0, K_FOLD_DOTS, K_DOTS_FINISH, K_MSM_SCALARS, K_PAIR_FOLD, K_TO_AFFINE, K_MSM_BUCKET,
-                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_TR_POINTS, K_TR_RENDER, K_TR_SQUEEZE, K_TR_RANDOM, K_ROUND_STATE, K_BATCH_WEIGHT, K_COUNT };
+                K_MSM_FINISH, K_TENSOR, K_FB_BUILD, K_FB_MSM, K_BCAST, K_DBG, K_MSM_GENS, K_JAC_SUM, K_GT_BUILD, K_EXPAND, K_COEF, K_IP_MISC, K_POW_TABLE, K_TRRP, K_MSM_GROUPS, K_MSM_REDUCE, K_CHECK, K_PIP_SORT, K_PIP_ACCUM, K_PIP_MERGE, K_PIP_REDUCE, K_PIP_HORNER, K_TR_POINTS, K_TR_RENDER, K_TR_SQUEEZE, K_TR_RANDOM, K_ROUND_STATE, K_BATCH_WEIGHT, K_MSM_LUT, K_LUT_BUILD, K_COUNT };
 static const char* const kKernelNames[K_COUNT] = {"k_fr_convert", "k_fold_dots", "k_dots_finish", "k_msm_scalars",
                                                    "k_pair_fold", "k_batch_to_affine", "k_msm_bucket", "k_msm_finish",
                                                    "k_tensor_expand", "k_fb_build", "k_fb_msm", "k_bcast_point", "k_dbg", "k_msm_gens",
                                                    "k_jac_sum", "k_gt_build", "k_expand_scalars", "k_coef_update", "k_ip_misc", "k_pow_table", "k_trrp_phases", "k_msm_gens_small", "k_msm_gens_reduce", "k_check_points",
                                                    "k_pip_sort", "k_pip_accum", "k_pip_merge", "k_pip_reduce", "k_pip_horner",
-                                                   "k_hash_to_curve", "k_tr_render", "k_tr_squeeze", "k_tr_random", "k_round_state", "k_batch_weight"};
+                                                   "k_hash_to_curve", "k_tr_render", "k_tr_squeeze", "k_tr_random", "k_round_state", "k_batch_weight", "k_msm_lut", "k_lut_build"};
 struct ProfRec {
     int id;
     double work;                 // algorithmic units of this launch: IMADs or bytes
@@ -1081,8 +1082,21 @@ extern "C" int bppp_rational_reduce(const uint8_t x[32], uint8_t a[32], int* a_n
 
 // =============================================================================== generator tables
 // The shared generator list [g | G | H] with its fixed-base window table, resident on the device.
+// full-multiples tables (lut.cuh) are large and depend only on the generator list: one per (device, list), shared by
+// every bppp_gens over that list (the lanes of a setup, prover and verifier setups of one process)
+struct LutTable {
+    int dev = 0;
+    LutDesc D;
+    std::vector<uint8_t> key;        // the generator list, P0 * 64 bytes
+    int refs = 0;
+    double build_ms = 0;
+};
+static std::mutex g_lut_mu;
+static std::vector<LutTable*> g_luts;
+
 struct bppp_gens {
     bppp_ctx* ctx;
+    LutTable* lut = nullptr;
     size_t N, M, P0;
     DBuf<Affine> base;               // [g | G | H]
     DBuf<Affine> tbl;                // [P0][GT_W]; empty for long lists (P0 > GT_TABLE_MAX_TERMS)
@@ -1103,6 +1117,34 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
     bppp_ctx* ctx = g->ctx;
     if (!g->tbl.p)
         return run_msm_pip(ctx, g->pip, g->base.p, 0, sc, sc_stride, sc_out_stride, n_terms, batch, n_out, d_out, work_per_proof);
+    if (g->lut && batch * (size_t)n_out > 8) {
+        // full-multiples table: W lookups + mixed additions per term, one CTA per (MSM, chunk), no reduction kernel
+        const size_t chunk_terms = GT_MAX_CHUNK;
+        const int nch = (int)((n_terms + chunk_terms - 1) / chunk_terms);
+        DBuf<Jac> partsbuf;
+        Jac* parts = d_out;
+        if (nch > 1) { CK(partsbuf.alloc(batch * n_out * nch)); parts = partsbuf.p; }
+        for (size_t b0 = 0; b0 < batch; b0 += 32768) {
+            const size_t nb = std::min<size_t>(32768, batch - b0);
+            LutMsmArgs A;
+            A.D = g->lut->D; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
+            A.n_terms = (int)n_terms; A.chunk_terms = (int)chunk_terms;
+            A.out = parts + b0 * n_out * nch; A.out_pstride = (size_t)n_out * nch; A.n_out = n_out; A.n_chunks = nch;
+            g_work = work_per_proof * (double)nb;
+            { ProfScope ps_(ctx, K_MSM_LUT, g_work);
+            k_msm_lut<<<dim3(nch, n_out, (unsigned)nb), LUT_THREADS, 0, ctx->st>>>(A);
+            }
+            CK(cudaGetLastError());
+        }
+        if (nch > 1) {
+            const size_t n_msm = batch * n_out;
+            { ProfScope ps_(ctx, K_JAC_SUM, 0);
+            k_jac_sum<<<(unsigned)((n_msm + 127) / 128), 128, 0, ctx->st>>>(parts, nch, nullptr, 0, d_out, n_msm);
+            }
+            CK(cudaGetLastError());
+        }
+        return BPPP_OK;
+    }
     static bool attr = false;
     if (!attr) {
         CK(cudaFuncSetAttribute(k_msm_gens, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gt_smem_bytes(GT_MAX_CHUNK)));
@@ -1249,10 +1291,91 @@ extern "C" int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t
     if (!check_fq(g, 2) || !check_fq(G, 2 * N) || !check_fq(H, 2 * M)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
     return gens_create_impl(ctx, N, M, g, G, H, nullptr, out);
 }
+// Give the generator list a full-multiples table (lut.cuh) of at most `budget_gb` gigabytes (and at most half of the
+// free device memory): window width c = 10 .. 16 by what fits; nothing happens when not even c = 10 fits.  Tables are
+// shared by all generator sets over the same list on the same device.  Returns the window width in *c_out (0 = none).
+extern "C" int bppp_gens_enable_lut(bppp_gens* g, double budget_gb, int* c_out) {
+    if (!g) return BPPP_ERR_ARG;
+    bppp_ctx* ctx = g->ctx;
+    if (c_out) *c_out = g->lut ? g->lut->D.c : 0;
+    if (g->lut || budget_gb <= 0) return BPPP_OK;
+    if (g->host.size() != g->P0 * 64 || !g->tbl.p) return BPPP_OK;       // long lists / device-made lists keep their paths
+    ENTER(ctx);
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    const double budget = std::min(budget_gb * 1e9, 0.5 * (double)free_b);
+    std::lock_guard<std::mutex> lk(g_lut_mu);
+    for (auto* t : g_luts)
+        if (t->dev == ctx->dev && t->key == g->host) {                   // built already (another lane / setup)
+            t->refs++;
+            g->lut = t;
+            if (c_out) *c_out = t->D.c;
+            return BPPP_OK;
+        }
+    int c = 0;
+    for (int cc = 16; cc >= 10; cc--) {
+        const double bytes = (double)g->P0 * ((256 + cc - 1) / cc) * (double)(1u << (cc - 1)) * 64.0;
+        if (bytes <= budget) { c = cc; break; }
+    }
+    if (!c) return BPPP_OK;
+    LutTable* t = new LutTable();
+    t->dev = ctx->dev; t->key = g->host; t->refs = 1;
+    LutDesc& D = t->D;
+    D.c = c; D.W = (256 + c - 1) / c; D.NB = 1 << (c - 1); D.P0 = g->P0; D.tbl = nullptr; D.carry = nullptr;
+    const size_t n_ent = g->P0 * (size_t)D.W * D.NB, n_base = g->P0 * (size_t)(D.W + 1);
+    Jac* bj = nullptr;
+    Affine* ba = nullptr;
+    auto fail = [&](cudaError_t e) {
+        ctx->err = std::string("bppp_gens_enable_lut: ") + cudaGetErrorString(e);
+        cudaFree(D.tbl); cudaFree(D.carry); cudaFree(bj); cudaFree(ba);
+        delete t;
+        return BPPP_ERR_CUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc((void**)&D.tbl, n_ent * 64)) || (e = cudaMalloc((void**)&D.carry, g->P0 * 64)) ||
+        (e = cudaMalloc((void**)&bj, n_base * sizeof(Jac))) || (e = cudaMalloc((void**)&ba, n_base * 64)))
+        return fail(e);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, ctx->st);
+    { ProfScope ps_(ctx, K_LUT_BUILD, 0);
+    k_lut_bases<<<(unsigned)((g->P0 + 63) / 64), 64, 0, ctx->st>>>(g->base.p, g->P0, c, D.W, bj);
+    }
+    if ((e = cudaGetLastError())) return fail(e);
+    int rc = to_affine(ctx, bj, n_base, ba, n_base, 0, (int)n_base, n_base);
+    if (rc) { fail(cudaErrorUnknown); return rc; }
+    if ((e = cudaMemcpy2DAsync(D.carry, 64, ba + D.W, (size_t)(D.W + 1) * 64, 64, g->P0, cudaMemcpyDeviceToDevice, ctx->st))) return fail(e);
+    const int run = std::min(LUT_RUN, D.NB);
+    const size_t n_thr = g->P0 * (size_t)D.W * (D.NB / run);
+    { ProfScope ps_(ctx, K_LUT_BUILD, 0);
+    k_lut_fill<<<(unsigned)((n_thr + 127) / 128), 128, 0, ctx->st>>>(D, ba, 0, n_thr, run);
+    }
+    if ((e = cudaGetLastError())) return fail(e);
+    cudaEventRecord(e1, ctx->st);
+    if ((e = ctx_sync(ctx))) return fail(e);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    t->build_ms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(bj); cudaFree(ba);
+    g_luts.push_back(t);
+    g->lut = t;
+    if (c_out) *c_out = c;
+    return BPPP_OK;
+}
 extern "C" void bppp_gens_destroy(bppp_gens* g) {
     if (!g) return;
     cudaSetDevice(g->ctx->dev);
     cudaStreamSynchronize(g->ctx->st);
+    if (g->lut) {
+        std::lock_guard<std::mutex> lk(g_lut_mu);
+        if (--g->lut->refs == 0) {
+            g_luts.erase(std::remove(g_luts.begin(), g_luts.end(), g->lut), g_luts.end());
+            cudaFree(g->lut->D.tbl);
+            cudaFree(g->lut->D.carry);
+            delete g->lut;
+        }
+    }
     delete g;
 }
 // `batch` MSMs over the first n generators of the list (commitRPW over [g | gs | hs])

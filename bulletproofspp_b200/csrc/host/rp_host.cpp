@@ -1265,6 +1265,11 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
     {
         const char* bv = getenv("BPPP_BATCH_VERIFY");
         s->batch_verify = bv && atoi(bv);
+        const char* lg = getenv("BPPP_LUT_GB");
+        if (lg && atof(lg) > 0) {
+            int rc3 = bppp_rp_enable_lut(s, atof(lg), nullptr);
+            if (rc3) { bppp_rp_free(s); return rc3; }
+        }
     }
     *out = s;
     return BPPP_OK;
@@ -1272,6 +1277,15 @@ int bppp_rp_setup(bppp_ctx* ctx, int binary, int arg_kind, int typed_or_conserve
 // Fiat-Shamir transcript of bppp_rp_prove_batch / bppp_rp_verify_batch on the device (on != 0) or on the host
 // (default; app/Main.hs:75-80, src/ZKP.hs:96-101).  Proofs and verdicts are bit-identical either way.  Only setups
 // that run the device scalar phases (TypedReciprocal over the norm-linear argument) can move it.
+int bppp_rp_enable_lut(bppp_rp* s, double budget_gb, int* c_out) {
+    if (!s) return BPPP_ERR_ARG;
+    int c = 0;
+    int rc = bppp_gens_enable_lut(s->gens, budget_gb, &c);
+    for (size_t i = 0; !rc && i < s->lane_gens.size(); i++) rc = bppp_gens_enable_lut(s->lane_gens[i], budget_gb, nullptr);
+    if (rc) return fail(s, rc, std::string("bppp_gens_enable_lut: ") + bppp_last_error(s->ctx));
+    if (c_out) *c_out = c;
+    return BPPP_OK;
+}
 int bppp_rp_set_batch_verify(bppp_rp* s, int on) {
     if (!s) return BPPP_ERR_ARG;
     s->batch_verify = on != 0;

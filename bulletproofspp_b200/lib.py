@@ -28,6 +28,7 @@ EXPORTS = [
     "bppp_dtr_absorb", "bppp_dtr_squeeze", "bppp_dtr_fits", "bppp_dtr_export", "bppp_rp_set_device_transcript", "bppp_nl_round_challenge",
     "bppp_nl_attach_transcript", "bppp_nl_prove_device", "bppp_rp_set_batch_verify", "bppp_nl_verify_trrp_rlc", "bppp_nl_verify_gens_rlc",
     "bppp_dtr_squeeze_inv", "bppp_trrp_want_inverses", "bppp_trrp_set_shared", "bppp_trrp_shared_coeffs",
+    "bppp_gens_enable_lut", "bppp_rp_enable_lut",
     "bppp_comm_load", "bppp_comm_last_error", "bppp_comm_unique_id", "bppp_comm_create", "bppp_comm_destroy", "bppp_nl_prove_sharded",
     "bppp_trrp_set_transcript", "bppp_trrp_phase1_tr", "bppp_trrp_phase2_tr", "bppp_trrp_phase3_rnd", "bppp_trrp_commit_bl_tr",
 ]
@@ -138,6 +139,8 @@ def load_library():
     lib.bppp_nl_round_challenge.argtypes = [vp, u8p, u8p, u8p]
     lib.bppp_nl_attach_transcript.argtypes = [vp, vp]
     lib.bppp_rp_set_batch_verify.argtypes = [vp, ip]
+    lib.bppp_gens_enable_lut.argtypes = [vp, C.c_double, C.POINTER(ip)]
+    lib.bppp_rp_enable_lut.argtypes = [vp, C.c_double, C.POINTER(ip)]
     lib.bppp_comm_load.argtypes = [C.c_char_p]
     lib.bppp_comm_last_error.restype = C.c_char_p
     lib.bppp_comm_unique_id.argtypes = [u8p]
@@ -499,6 +502,12 @@ class RangeProofSetup:
     def set_device_transcript(self, on=True):
         """run the Fiat-Shamir transcript of prove_batch / verify_batch on the device; bit-identical"""
         self._ck(self.ctx.lib.bppp_rp_set_device_transcript(self.h, int(bool(on))), "bppp_rp_set_device_transcript")
+
+    def enable_lut(self, budget_gb):
+        """full-multiples table for the setup's generators (csrc/lut.cuh); returns the window width (0 = none)"""
+        c = C.c_int()
+        self._ck(self.ctx.lib.bppp_rp_enable_lut(self.h, float(budget_gb), C.byref(c)), "bppp_rp_enable_lut")
+        return c.value
 
     def set_batch_verify(self, on=True):
         """verify each lane's sub-batch by one random linear combination; per-proof checks locate failures"""

@@ -76,6 +76,12 @@ int bppp_gens_create(bppp_ctx* ctx, size_t N, size_t M, const uint8_t* g, const 
 void bppp_gens_destroy(bppp_gens* g);
 /* `batch` MSMs over the first n generators of the list: scalars batch*n*32, out batch*64 */
 int bppp_gens_msm_batch(bppp_gens* g, size_t batch, size_t n, const uint8_t* scalars, uint8_t* out);
+/* Full-multiples table for the list (csrc/lut.cuh): every multiple m * 2^(c w) * P_i a signed c-bit window can ask for,
+ * resident in HBM -- an MSM over the list becomes ceil(256/c) table lookups + mixed additions per term (no buckets, no
+ * reduction).  budget_gb bounds the table (43 GB for 1286 generators at c = 16; c = 10 .. 16 by what fits, and at most
+ * half of the free device memory); tables are shared between generator sets over the same list on one device.
+ * *c_out = the window width in use (0: no table, the nine-bit bucket kernel stays).  Results are unchanged. */
+int bppp_gens_enable_lut(bppp_gens* g, double budget_gb, int* c_out);
 /* host threads used by the round sequencing inside the device entry points (0 = all cores) */
 void bppp_set_device_host_threads(int n);
 void bppp_set_thread_host_threads(int n);   /* same, for the calling thread only */
@@ -331,6 +337,8 @@ int bppp_rp_set_device_transcript(bppp_rp* s, int on);
 /* bppp_rp_verify_batch by one random linear combination per lane sub-batch (weights from the OS entropy source);
  * falls back to the per-proof checks when a combination fails, so ok[] is exact.  Default off (BPPP_BATCH_VERIFY=1). */
 int bppp_rp_set_batch_verify(bppp_rp* s, int on);
+/* bppp_gens_enable_lut for the setup's generator list (all lanes share one table).  Environment default: BPPP_LUT_GB. */
+int bppp_rp_enable_lut(bppp_rp* s, double budget_gb, int* c_out);
 /* RangeProof.proveM for `batch` independent proofs (see rp_host.cpp for the buffer layout) */
 int bppp_rp_prove_batch(bppp_rp* s, size_t batch, const uint8_t* values, const uint8_t* types, const uint8_t* blinds,
                         const char* const* random_seeds, uint8_t* coms, uint8_t* responses, uint8_t* finals);

@@ -262,6 +262,38 @@ def test_batch_verification_accepts_and_locates_bad_proofs(ctx, name, count):
     setup.close()
 
 
+@pytest.mark.parametrize("name,count,gb", [("128by64", 12, 2.5), ("32by64", 40, 1.4), ("typed_nl", 9, 6.0)])
+def test_full_multiples_table_is_bit_identical(ctx, name, count, gb):
+    """csrc/lut.cuh: with a full-multiples table for the generator list every fixed-base MSM of the batch prover and
+    verifier is table lookups + mixed additions (k_msm_lut) instead of the nine-bit bucket kernel.  Same proof bits,
+    same verdicts; the budgets here select window widths 11 and 12 (and the widest that fits for the small typed setup)."""
+    import bulletproofspp_b200 as bp
+    if name == "typed_nl":                                # typed proofs must stay balanced: same witness, different seeds
+        schema, wit = EXAMPLES[name]
+        wits, seeds = [wit] * count, ["typed seed %d" % i for i in range(count)]
+    else:
+        schema, wits, seeds = batched(name, count)
+    plain = bp.RangeProofSetup(ctx, schema)
+    lut = bp.RangeProofSetup(ctx, schema)
+    c = lut.enable_lut(gb)
+    p0 = 1 + lut.nrm_len + lut.lin_len
+    want = max(cc for cc in range(10, 17) if p0 * ((256 + cc - 1) // cc) * 2 ** (cc - 1) * 64 <= gb * 1e9)
+    assert c == want and (name, c) in (("128by64", 11), ("32by64", 12), ("typed_nl", c)), (c, want)
+    for dev_tr in (False, True):
+        plain.set_device_transcript(dev_tr)
+        lut.set_device_transcript(dev_tr)
+        p0 = plain.prove_batch(wits, seeds)
+        p1 = lut.prove_batch(wits, seeds)
+        assert p0 == p1
+        assert all(lut.verify_batch(p0)) and all(plain.verify_batch(p1))
+    bad = dict(p1[1], finals=[(p1[1]["finals"][0] + 1) % (2 ** 200)] + p1[1]["finals"][1:])
+    assert lut.verify_batch([p1[0], bad] + p1[2:]) == [True, False] + [True] * (count - 2)
+    lut.set_batch_verify(True)
+    assert lut.verify_batch([p1[0], bad] + p1[2:]) == [True, False] + [True] * (count - 2)
+    plain.close()
+    lut.close()
+
+
 def test_hybrid_round_mode_is_bit_identical(ctx, monkeypatch):
     """BPPP_HYBRID_MAX switches a tensor-mode argument to generator folding for its last rounds (the
     folded generators are materialised by one small fixed-base MSM per block).  Same proof bits."""
