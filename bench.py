@@ -376,19 +376,31 @@ def main():
     kt = kern[top]
     ach = kt["work"] / (kt["ms"] * 1e-3) / 1e12
     ncu = ncu_summary().get(top, {})
-    roofline = {"kernel": top, "bound": "imad", "achieved": ach, "peak": imad_wide / 1e12, "unit": "TIMAD/s",
-                "frac": ach / (imad_wide / 1e12), "frac_alg": ach / (imad_wide / 1e12),
-                "frac_pipe": ncu.get("pipe_fmaheavy_active_pct", 0) / 100.0 or None,
+    peak_t = imad_wide / 1e12
+    # IMAD.WIDE instructions the kernel really issues for its group arithmetic, counted live: every table lookup of
+    # k_msm_lut is one XYZZ mixed addition = 8 fq::mul + 2 fq::sqr = 8 x 72 + 2 x 43 IMAD.WIDE (SASS of this build)
+    issued = None
+    if top == "k_msm_lut" and rep.get("lut_lookups"):
+        issued = rep["lut_lookups"] * (8 * 72 + 2 * 43) / (kt["ms"] * 1e-3) / 1e12
+    frac_pipe = issued / peak_t if issued else None
+    roofline = {"kernel": top, "bound": "imad", "achieved": issued if issued else ach, "peak": peak_t, "unit": "TIMAD/s",
+                "frac": frac_pipe if frac_pipe else ach / peak_t,
+                "frac_pipe": frac_pipe, "frac_alg": ach / peak_t, "achieved_alg": ach,
+                "pipe_active_ncu": (ncu.get("pipe_fmaheavy_active_pct", 0) / 100.0) or None,
                 "traffic": ncu.get("dram_bytes_per_launch"),
-                "traffic_note": "frac / frac_alg = algorithmic IMADs of the reference's schedule per second / peak (measured live, CUDA "
-                                "events); frac_pipe = sm__pipe_fmaheavy_cycles_active and traffic = dram read+write bytes of one launch of "
-                                "this shape, both from the committed ncu --set full capture (%s): a profiler cannot run inside the "
-                                "timed bench" % ncu.get("source", "profiles/ncu_summary.json missing"),
+                "lookups_per_launch": (rep.get("lut_lookups", 0) / kt["launches"]) if issued else None,
                 "avg_launch_ms": kt["ms"] / kt["launches"], "share_of_gpu_time": shares[top],
-                "note": "integer-pipe bound (no hbm/tensor roofline applies): achieved = algorithmic 32x32->64 IMADs in the "
-                        "reference's units (SURVEY 8(d): Pippenger MSMs over each round's CURRENT lengths + the half-length "
-                        "generator folds this kernel absorbs) / CUDA-event time; peak = IMAD.WIDE issue rate measured in this run. "
-                        "The kernel executes ~1.5x that work (full-length fixed-base MSMs every round, DESIGN.md)"}
+                "note": "integer-pipe bound (no hbm/tensor roofline applies).  frac = frac_pipe = IMAD.WIDE instructions issued for the group "
+                        "arithmetic (counted live: lookups x 662 per mixed addition) / CUDA-event time / the IMAD.WIDE issue rate measured in "
+                        "this run.  pipe_active_ncu = sm__pipe_fmaheavy_cycles_active of the committed ncu --set full capture (%s): the "
+                        "carry handling of a field multiplication (IMAD.X, IMAD.MOV: 42 of its 114 IMAD-class instructions) occupies the "
+                        "same pipe, which is why %s of useful multiplies is %s of the pipe.  frac_alg = the reference schedule's IMADs "
+                        "(SURVEY 8(d): Pippenger MSMs over each round's CURRENT lengths + the generator folds this kernel absorbs, 136 IMAD "
+                        "per multiplication) / time / peak -- it exceeds 1 because a full-multiples table needs neither buckets nor "
+                        "reductions.  traffic = dram read + write bytes of one launch from the same capture (a profiler cannot run inside "
+                        "the timed bench)" % (ncu.get("source", "profiles/ncu_summary.json missing"),
+                                              "%.2f" % frac_pipe if frac_pipe else "this share",
+                                              "%.2f" % (ncu.get("pipe_fmaheavy_active_pct", 0) / 100.0) if ncu else "more")}
     rooflines = {}
     for name in ("k_msm_bucket", "k_pair_fold"):
         if name in kern and kern[name]["ms"] > 0 and kern[name]["work"] > 0:

@@ -54,6 +54,7 @@ struct bppp_ctx {
     uint64_t k_n[K_COUNT] = {0};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     cudaEvent_t sync_ev = nullptr;   // blocking-sync event: waiting host threads sleep whatever the device's schedule flags
+    unsigned long long* lut_count = nullptr;   // device counter: table lookups (= mixed additions) of k_msm_lut while profiling
 };
 // Wait for everything queued on the context's stream.  An event created with cudaEventBlockingSync
 // makes the calling thread sleep even when the primary context was created by someone else (torch,
@@ -502,6 +503,7 @@ extern "C" void bppp_free(bppp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->dev);
     if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+    if (ctx->lut_count) cudaFree(ctx->lut_count);
     if (ctx->st) cudaStreamDestroy(ctx->st);
     delete ctx;
 }
@@ -533,6 +535,7 @@ extern "C" int bppp_profile_enable(bppp_ctx* ctx, int on) {
     return BPPP_OK;
 }
 extern "C" int bppp_profile_reset(bppp_ctx* ctx) {
+    if (ctx && ctx->lut_count) { cudaSetDevice(ctx->dev); cudaMemsetAsync(ctx->lut_count, 0, 8, ctx->st); }
     if (!ctx) return BPPP_ERR_ARG;
     cudaSetDevice(ctx->dev);
     prof_collect(ctx);
@@ -556,8 +559,13 @@ extern "C" int bppp_profile_report(bppp_ctx* ctx, char* out, size_t cap) {
         j += buf;
         first = false;
     }
-    snprintf(buf, sizeof buf, "}, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"launches\": %llu}", (unsigned long long)ctx->h2d,
-             (unsigned long long)ctx->d2h, (unsigned long long)ctx->launches);
+    unsigned long long lookups = 0;
+    if (ctx->lut_count) {
+        cudaMemcpyAsync(&lookups, ctx->lut_count, 8, cudaMemcpyDeviceToHost, ctx->st);
+        cudaStreamSynchronize(ctx->st);
+    }
+    snprintf(buf, sizeof buf, "}, \"h2d_bytes\": %llu, \"d2h_bytes\": %llu, \"launches\": %llu, \"lut_lookups\": %llu}", (unsigned long long)ctx->h2d,
+             (unsigned long long)ctx->d2h, (unsigned long long)ctx->launches, lookups);
     j += buf;
     if (j.size() + 1 > cap) FAIL(BPPP_ERR_ARG, "report buffer too small");
     memcpy(out, j.c_str(), j.size() + 1);
@@ -811,7 +819,7 @@ int dtr_squeeze_dev(bppp_dtr* t, int n_chal, const unsigned char* idx, const uns
     }
     const size_t n = t->B * (size_t)n_chal;
     { ProfScope ps_(ctx, K_TR_SQUEEZE, 0);
-    k_tr_squeeze<<<(unsigned)((n + TR_THREADS - 1) / TR_THREADS), TR_THREADS, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);
+    k_tr_squeeze<<<(unsigned)((n + 31) / 32), 32, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);   // one warp per CTA: every warp gets an SM of its own
     }
     CK(cudaGetLastError());
     return BPPP_OK;
@@ -1119,7 +1127,13 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         return run_msm_pip(ctx, g->pip, g->base.p, 0, sc, sc_stride, sc_out_stride, n_terms, batch, n_out, d_out, work_per_proof);
     if (g->lut && batch * (size_t)n_out > 8) {
         // full-multiples table: W lookups + mixed additions per term, one CTA per (MSM, chunk), no reduction kernel
-        const size_t chunk_terms = GT_MAX_CHUNK;
+        // CTAs of 64 threads, 8 per SM: cut every MSM into enough chunks for about four waves of CTAs (CTAs that finish
+        // are replaced while others still add -- an R commitment has half the work of an X commitment), at least 64
+        // terms per chunk; the chunk sums are added by k_jac_sum
+        const size_t n_msm_all = batch * (size_t)n_out;
+        size_t want = (4 * 148 * 8 + n_msm_all - 1) / n_msm_all;
+        want = std::max<size_t>(1, std::min<size_t>(want, (n_terms + 63) / 64));
+        const size_t chunk_terms = (n_terms + want - 1) / want;
         const int nch = (int)((n_terms + chunk_terms - 1) / chunk_terms);
         DBuf<Jac> partsbuf;
         Jac* parts = d_out;
@@ -1130,6 +1144,14 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
             A.D = g->lut->D; A.sc = sc + b0 * sc_stride; A.sc_stride = sc_stride; A.sc_out_stride = sc_out_stride;
             A.n_terms = (int)n_terms; A.chunk_terms = (int)chunk_terms;
             A.out = parts + b0 * n_out * nch; A.out_pstride = (size_t)n_out * nch; A.n_out = n_out; A.n_chunks = nch;
+            A.count = nullptr;
+            if (ctx->prof) {                       // profiling pass: count the lookups actually made
+                if (!ctx->lut_count) {
+                    CK(cudaMalloc((void**)&ctx->lut_count, 8));
+                    CK(cudaMemsetAsync(ctx->lut_count, 0, 8, ctx->st));
+                }
+                A.count = ctx->lut_count;
+            }
             g_work = work_per_proof * (double)nb;
             { ProfScope ps_(ctx, K_MSM_LUT, g_work);
             k_msm_lut<<<dim3(nch, n_out, (unsigned)nb), LUT_THREADS, 0, ctx->st>>>(A);

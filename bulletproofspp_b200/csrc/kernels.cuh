@@ -169,7 +169,7 @@ __device__ __forceinline__ u256 fr_pow(u256 base, unsigned e) {
     return acc;
 }
 
-__global__ void __launch_bounds__(256) k_fold_dots(FoldDotsArgs A) {
+__global__ void __launch_bounds__(256, 2) k_fold_dots(FoldDotsArgs A) {
     const int p = blockIdx.y;
     const u256* u = A.u + (size_t)p * A.in_stride;
     const u256* v = A.v + (size_t)p * A.in_stride;

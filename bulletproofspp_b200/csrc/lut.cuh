@@ -15,8 +15,9 @@
 //   k_lut_bases   2^(c w) P_i for w = 0 .. W (Jacobian; made affine by k_batch_to_affine)
 //   k_lut_fill    one thread per run of LUT_RUN consecutive multiples of one base: start point by double-and-add,
 //                 then a chain of mixed additions, made affine 32 at a time (Montgomery trick in place)
-//   k_msm_lut     one CTA per (MSM, chunk): a thread recodes its scalars into signed c-bit digits, prefetches the W
-//                 entries, adds them (XYZZ accumulator), and the CTA tree-sums its threads' partial sums
+//   k_msm_lut     one CTA of 64 threads per (MSM, chunk): threads take (scalar, half of its windows) units from a shared
+//                 counter, recode the signed c-bit digits, prefetch the entries one unit ahead, add them (XYZZ
+//                 accumulator); the CTA tree-sums its threads' partial sums
 // Results are group elements, independent of the table layout: bit-identical to k_msm_gens (tests).
 #pragma once
 #include "kernels.cuh"
@@ -24,7 +25,7 @@
 namespace bppp {
 
 #define LUT_RUN 256                    // multiples per k_lut_fill thread (or NB when NB is smaller)
-#define LUT_THREADS 256
+#define LUT_THREADS 64                 // few threads per MSM: the tree sum at the end is 6 levels, 2 % of a thread's work
 
 struct LutDesc {
     Affine* tbl;                       // [P0][W][NB]
@@ -98,41 +99,85 @@ struct LutMsmArgs {
     int n_terms, chunk_terms;
     Jac* out; size_t out_pstride;                      // out[p * out_pstride + o * n_chunks + chunk]
     int n_out, n_chunks;
+    unsigned long long* count;                         // profiling: += lookups (mixed additions) made; may be null
 };
 
-__global__ void __launch_bounds__(LUT_THREADS, 2) k_msm_lut(LutMsmArgs A) {
+// Work unit = (scalar, half of its windows): units are handed out by a shared-memory counter, so the CTA stays balanced
+// whatever the pattern of zero scalars (the R commitment of a round uses every other generator), and the last thread
+// to finish is at most W/2 additions behind.  A thread recodes and prefetches its NEXT unit before it adds the current
+// one: the random HBM reads of a unit are in flight for the ~20 us the previous unit's additions take.
+#define LUT_HALF_MAX 13                // windows per unit: ceil(26 / 2) at c = 10
+struct LutUnit {
+    const Affine* row;                 // entries of window w0 start at row
+    int n;                             // windows in this unit
+    int term;                          // generator index, for the carry point; -1: no carry point in this unit
+    unsigned short mag[LUT_HALF_MAX];  // |digit| - 1 (0xffff: digit 0)
+    unsigned neg;                      // sign bits
+};
+__device__ __forceinline__ bool lut_next_unit(const LutMsmArgs& A, const u256* sc, int base, int n_units, int* counter, LutUnit& U) {
+    const int c = A.D.c, W = A.D.W, W0 = (W + 1) / 2;
+    const size_t NB = (size_t)A.D.NB;
+    for (;;) {
+        const int u = atomicAdd(counter, 1);
+        if (u >= n_units) return false;
+        const int i = u >> 1, h = u & 1;
+        const u256 s = ld_u256(sc + i);
+        if (u256_is_zero(s)) continue;
+        int carry = 0;
+        const int w0 = h ? W0 : 0, w1 = h ? W : W0;
+        for (int w = 0; w < w0; w++) (void)signed_digit(s, w, c, carry);      // the carry into this half
+        U.row = A.D.tbl + ((size_t)(base + i) * W + w0) * NB;
+        U.n = w1 - w0;
+        U.neg = 0;
+        bool any = false;
+#pragma unroll 1
+        for (int w = w0; w < w1; w++) {
+            const int d = signed_digit(s, w, c, carry);
+            const int m = d < 0 ? -d : d;
+            U.mag[w - w0] = (unsigned short)(m - 1);                           // 0xffff for a zero digit (m <= 32768)
+            if (d < 0) U.neg |= 1u << (w - w0);
+            if (d) {
+                any = true;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(U.row + (size_t)(w - w0) * NB + m - 1));
+            }
+        }
+        U.term = -1;
+        if (h && carry) {                                                      // top carry: the point 2^(c W) P_i
+            U.term = base + i;
+            any = true;
+        }
+        if (!any) continue;
+        return true;
+    }
+}
+__global__ void __launch_bounds__(LUT_THREADS, 8) k_msm_lut(LutMsmArgs A) {
     __shared__ Xyzz sm[LUT_THREADS / 2];
+    __shared__ int counter;
     const int chunk = blockIdx.x, o = blockIdx.y, p = blockIdx.z, tid = threadIdx.x;
     const int base = chunk * A.chunk_terms;
     const int n = min(A.chunk_terms, A.n_terms - base);
     const u256* sc = A.sc + (size_t)p * A.sc_stride + (size_t)o * A.sc_out_stride + base;
-    const int c = A.D.c, W = A.D.W;
     const size_t NB = (size_t)A.D.NB;
+    if (tid == 0) counter = 0;
+    __syncthreads();
     Xyzz acc = xyzz_inf();
+    LutUnit cur, nxt;
+    unsigned n_add = 0;
+    bool have = lut_next_unit(A, sc, base, 2 * n, &counter, cur);
+    while (have) {
+        const bool have_next = lut_next_unit(A, sc, base, 2 * n, &counter, nxt);
 #pragma unroll 1
-    for (int i = tid; i < n; i += LUT_THREADS) {
-        const u256 s = ld_u256(sc + i);
-        if (u256_is_zero(s)) continue;
-        const Affine* row = A.D.tbl + (size_t)(base + i) * W * NB;
-        // pass 1: the digits, and a prefetch of every entry this scalar needs (HBM latency hides behind the additions)
-        int carry = 0;
-        unsigned long long neg = 0;                     // sign bits of the W digits
-        int dig[32];                                    // W <= 26 (c >= 10)
-#pragma unroll 1
-        for (int w = 0; w < W; w++) {
-            const int d = signed_digit(s, w, c, carry);
-            dig[w] = d < 0 ? -d : d;
-            if (d < 0) neg |= 1ull << w;
-            if (d) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + (size_t)w * NB + dig[w] - 1));
-        }
-#pragma unroll 1
-        for (int w = 0; w < W; w++) {
-            if (!dig[w]) continue;
-            Affine P = ld_aff(row + (size_t)w * NB + dig[w] - 1);
-            if ((neg >> w) & 1ull) P.y = fq::neg(P.y);
+        for (int k = 0; k < cur.n; k++) {
+            const unsigned m = cur.mag[k];
+            if (m == 0xffffu) continue;
+            Affine P = ld_aff(cur.row + (size_t)k * NB + m);
+            if ((cur.neg >> k) & 1u) P.y = fq::neg(P.y);
             acc = xyzz_madd(acc, P);
+            n_add++;
         }
-        if (carry) acc = xyzz_madd(acc, ld_aff(A.D.carry + base + i));
+        if (cur.term >= 0) { acc = xyzz_madd(acc, ld_aff(A.D.carry + cur.term)); n_add++; }
+        cur = nxt;
+        have = have_next;
     }
     // CTA tree sum of the per-thread partial sums
 #pragma unroll 1
@@ -143,6 +188,11 @@ __global__ void __launch_bounds__(LUT_THREADS, 2) k_msm_lut(LutMsmArgs A) {
         if (tid < half) acc = xyzz_add(acc, sm[tid]);
     }
     if (tid == 0) st_jac(A.out + (size_t)p * A.out_pstride + (size_t)o * A.n_chunks + chunk, xyzz_to_jac(acc));
+    if (A.count) {
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) n_add += __shfl_down_sync(0xffffffffu, n_add, d);
+        if ((tid & 31) == 0) atomicAdd(A.count, (unsigned long long)n_add);
+    }
 }
 
 }  // namespace bppp

@@ -230,18 +230,26 @@ __global__ void __launch_bounds__(TR_THREADS) k_tr_squeeze(const unsigned char* 
     const size_t a0 = (size_t)(body - hl);                             // address of "message byte 0" (virtual)
     const unsigned sh = (unsigned)(a0 & 3);
     const unsigned sel = (sh + 3) | ((sh + 2) << 4) | ((sh + 1) << 8) | (sh << 12);
+    // the 17 words of the NEXT interior block are loaded before the current block is compressed: a lone warp per
+    // scheduler has nothing else to hide the ~1 us of an HBM read behind (long scoreboard was 2.3 stalls per issue)
+    uint32_t nx[17];
+    bool nx_valid = false;
+    auto interior = [&](unsigned k) { return k >= 1 && (unsigned long long)k * 64 + 64 <= T; };
+    auto fetch = [&](unsigned k) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>((a0 + (unsigned long long)k * 64) & ~(size_t)3);
+#pragma unroll
+        for (int i = 0; i < 17; i++) nx[i] = q[i];
+    };
+    if (nblk > 1 && interior(1)) { fetch(1); nx_valid = true; }
     for (unsigned k = 0; k < nblk; k++) {
         uint32_t w[16];
         const unsigned long long m0 = (unsigned long long)k * 64;
-        if (k >= 1 && m0 + 64 <= T) {
-            const uint32_t* q = reinterpret_cast<const uint32_t*>((a0 + m0) & ~(size_t)3);
-            uint32_t lo = q[0];
+        if (interior(k)) {
+            if (!nx_valid) fetch(k);
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const uint32_t hi = q[i + 1];
-                w[i] = __byte_perm(lo, hi, sel);
-                lo = hi;
-            }
+            for (int i = 0; i < 16; i++) w[i] = __byte_perm(nx[i], nx[i + 1], sel);
+            nx_valid = false;
+            if (interior(k + 1)) { fetch(k + 1); nx_valid = true; }
         } else {
 #pragma unroll 1
             for (int i = 0; i < 16; i++) {
