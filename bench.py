@@ -154,7 +154,10 @@ def cpu_baseline_sample(n_proofs=4):
 # --------------------------------------------------------------------------- our arm
 def make_inputs(batch, offset, n_inputs):
     """host buffers of one step: values (10000 + proof index), types (0), per-proof seeds"""
-    vals = b"".join(int(10000 + offset + b).to_bytes(32, "little") * n_inputs for b in range(batch))
+    import numpy as np
+    v = np.zeros((batch, n_inputs, 4), dtype="<u8")                 # 32-byte little-endian scalars
+    v[:, :, 0] = (10000 + offset + np.arange(batch, dtype=np.uint64))[:, None]
+    vals = v.tobytes()
     tys = bytes(32 * n_inputs * batch)
     seeds = ["default random seed#%d" % (offset + b) for b in range(batch)]
     return vals, tys, seeds
@@ -183,6 +186,9 @@ def main():
     ap.add_argument("--sweep-sizes", default="10,14,18,20", help="log2 N of the synthetic norm-argument sweep (N=1 only)")
     ap.add_argument("--no-sweep", action="store_true")
     ap.add_argument("--sharded-size", type=int, default=20, help="log2 N of the argument sharded over the GPUs (N > 1 only)")
+    ap.add_argument("--provers", type=int, default=2,
+                    help="prover setups whose bppp_rp_prove_batch calls overlap (consecutive batches in flight: the ramp-up of one "
+                         "call's lanes -- host phases first -- fills the ramp-down of the previous call's)")
     ap.add_argument("--lut-gb", type=float, default=48.0,
                     help="memory budget of the generators' full-multiples table (csrc/lut.cuh); 0 = nine-bit bucket kernel")
     ap.add_argument("--verify", default="batch", choices=["batch", "per-proof"],
@@ -222,7 +228,15 @@ def main():
     if lut_c:
         vsetup.enable_lut(args.lut_gb)
     t_lut = time.time() - t_lut
-    lanes = setup.contexts() + vsetup.contexts()
+    # further prover setups (own lanes, streams and staging buffers; the worker pool and the table are shared)
+    psetups = [setup]
+    for _ in range(max(1, args.provers) - 1):
+        s2 = bp.RangeProofSetup(bp.Context(local), workload_schema())
+        s2.set_device_transcript(dev_tr)
+        if lut_c:
+            s2.enable_lut(args.lut_gb)
+        psetups.append(s2)
+    lanes = [c for st in psetups for c in st.contexts()] + vsetup.contexts()
     B, n = args.batch, setup.n_inputs
     assert (setup.nrm_len, setup.lin_len, setup.rounds) == (1024, 261, 9)
 
@@ -263,11 +277,29 @@ def main():
                     errs.append(ex)
         th = threading.Thread(target=verifier)
         th.start()
-        for k in range(steps):
-            vals, tys, seeds = input_fn(k)
-            tk = time.time()
-            q.put(setup.prove_batch_raw(B, vals, tys, None, seeds))
-            prove_wall.append(round(time.time() - tk, 4))
+        nxt, lock = [0], threading.Lock()
+
+        def prover(st):
+            while True:
+                with lock:
+                    k = nxt[0]
+                    nxt[0] += 1
+                if k >= steps:
+                    return
+                try:
+                    vals, tys, seeds = input_fn(k)
+                    tk = time.time()
+                    proof = st.prove_batch_raw(B, vals, tys, None, seeds)
+                    prove_wall.append(round(time.time() - tk, 4))
+                    q.put(proof)
+                except Exception as ex:
+                    errs.append(ex)
+                    return
+        pth = [threading.Thread(target=prover, args=(st,)) for st in psetups[:max(1, min(len(psetups), steps))]]
+        for t in pth:
+            t.start()
+        for t in pth:
+            t.join()
         q.put(None)
         th.join()
         if errs:
@@ -353,7 +385,9 @@ def main():
         # BASELINE.json config 5 on several GPUs: ONE 2^20-element norm argument sharded over the ranks
         # (strong scaling; NCCL all-gather inside the library, bppp_nl_prove_sharded), after the timed regions
         from bulletproofspp_b200 import sweep
-        vsetup.close(); setup.close(); psetup.close()
+        vsetup.close(); psetup.close()
+        for st in psetups:
+            st.close()
         try:
             sharded = sweep.run_sharded(ctx, args.sharded_size, rank, world, dist)
         except Exception as ex:                    # reported, never silently dropped
@@ -423,6 +457,8 @@ def main():
                        "batch_per_gpu": B, "parallelism": "batch sharded over %d GPU(s), no data-path collective" % world,
                        "l2": "working set per step (%.0f MB of generators+witness vectors) exceeds the 126 MB L2" % (B * 0.33),
                        "host_threads": args.host_threads or max(1, (os.cpu_count() or 1) // world), "lanes": len(lanes),
+                       "batches_in_flight": "%d prover setups: consecutive bppp_rp_prove_batch calls overlap, a third thread verifies "
+                                            "finished batches" % len(psetups),
                        "msm_table": ("full-multiples table in HBM, window %d bits: %d lookups + mixed additions per term, %.1f GB, built once "
                                      "per process in %.2f s before the timed regions (csrc/lut.cuh)" % (
                                          lut_c, (256 + lut_c - 1) // lut_c, 1286 * ((256 + lut_c - 1) // lut_c) * 2 ** (lut_c - 1) * 64 / 1e9, t_lut))
@@ -455,7 +491,9 @@ def main():
         # second half of BASELINE.json's metric ("norm-arg fold GB/s") and its config 5: the synthetic norm-argument
         # sweep, one large argument per size, after the timed regions of the headline metric
         from bulletproofspp_b200 import sweep
-        vsetup.close(); setup.close(); psetup.close()
+        vsetup.close(); psetup.close()
+        for st in psetups:
+            st.close()
         line["norm_arg_sweep"] = sweep.run(ctx, [int(x) for x in args.sweep_sizes.split(",") if x], imad_wide, hbm_peak)
     if sharded is not None:
         line["norm_arg_sharded"] = sharded

@@ -1449,8 +1449,16 @@ static int prove_trrp_device(bppp_rp* s, const Lane& ln, std::vector<Proof>& P, 
         sect.lap(S_RANDOM);
         h64::to_bytes(ch + 32 * (2 * b), p.q0); h64::to_bytes(ch + 32 * (2 * b + 1), p.xq);
         std::vector<Fr> ic = input_coeffs_trrp(s, p.x, p.q0);
-        RPW nsum;
-        for (size_t i = 0; i < n; i++) rpw_add(nsum, rpw_scale(p.n_wits[i], ic[i]));
+        RPW nsum;                                                           // sum_i ic_i * nWit_i without temporaries
+        size_t nl = 0;
+        for (size_t i = 0; i < n; i++) nl = std::max(nl, p.n_wits[i].lin.size());
+        nsum.lin.assign(nl, h64::zero());
+        for (size_t i = 0; i < n; i++) {
+            const RPW& w = p.n_wits[i];
+            if (!w.sc.is_zero()) nsum.sc = h64::add(nsum.sc, h64::mul(w.sc, ic[i]));
+            for (size_t j = 0; j < w.lin.size(); j++)
+                if (!w.lin[j].is_zero()) nsum.lin[j] = h64::add(nsum.lin[j], h64::mul(w.lin[j], ic[i]));
+        }
         p.wit = nsum;                                                       // parked: nWitSum
         sect.lap(S_COMBINE);
     });
@@ -1552,7 +1560,29 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
         for (size_t i = 0; i < n; i++) {
             vals[i] = h64::from_bytes(values + 32 * (b * n + i));
             tys[i] = (types && !s->binary) ? h64::from_bytes(types + 32 * (b * n + i)) : h64::zero();
-            bls[i] = blinds ? h64::from_bytes(blinds + 32 * (b * n + i)) : tr::input_blind(p.zk.seed, i + 1);
+            if (blinds) bls[i] = h64::from_bytes(blinds + 32 * (b * n + i));
+        }
+        if (!blinds) {
+            // hashToScalars ("Blinding " <> rn), positions 1.. (app/Main.hs:86-87, 275-276): one-block messages, hashed
+            // two at a time when the seed is short enough
+            const std::string pre = "Blinding " + p.zk.seed;
+            size_t i = 0;
+            if (pre.size() + 20 <= 55) {
+                uint8_t m0[64], m1[64], d0[32], d1[32];
+                memcpy(m0, pre.data(), pre.size());
+                memcpy(m1, pre.data(), pre.size());
+                for (; i + 1 < n; i += 2) {
+                    const size_t l0 = pre.size() + tr::format_uint((char*)m0 + pre.size(), i + 1);
+                    const size_t l1 = pre.size() + tr::format_uint((char*)m1 + pre.size(), i + 2);
+                    sha::digest_short_x2(d0, m0, l0, d1, m1, l1);
+                    uint64_t w[4];
+                    tr::digest_to_words(w, d0);
+                    bls[i] = h64::from_wide(w);
+                    tr::digest_to_words(w, d1);
+                    bls[i + 1] = h64::from_wide(w);
+                }
+            }
+            for (; i < n; i++) bls[i] = tr::input_blind(p.zk.seed, i + 1);
         }
         if (s->binary) {
             // witnessBRP (Binary.hs:161-168): Nothing unless conserved and balanced
@@ -1625,7 +1655,12 @@ static int prove_impl(bppp_rp* s, const Lane& ln, size_t batch, const uint8_t* v
                     for (size_t k = 0; k < rdi.coeffs.size(); k++, ent++) {
                         const bool bit = rdi.has_bit && k == 0;
                         const U128 basek = bit ? (U128)2 : rdi.base, cf = rdi.coeffs[k];
-                        U128 d = cf ? std::min<U128>(basek - 1, left / cf) : (basek - 1);
+                        U128 d;
+                        if (!cf) d = basek - 1;
+                        else if (!(uint64_t)(left >> 64) && !(uint64_t)(cf >> 64)) {      // 64-bit operands: one hardware division
+                            const uint64_t qd = (uint64_t)left / (uint64_t)cf;
+                            d = std::min<U128>(basek - 1, qd);
+                        } else d = std::min<U128>(basek - 1, left / cf);
                         left -= d * cf;
                         put_int(dm_row + 32 * (1 + ent), d);
                         if (bit) {
