@@ -439,7 +439,7 @@ __device__ __forceinline__ Affine tbl_load(const uint32_t* tbl, int e) {
     return p;
 }
 
-__global__ void __launch_bounds__(PF_THREADS, 4) k_pair_fold(PairFoldArgs A) {
+__global__ void __launch_bounds__(PF_THREADS, 5) k_pair_fold(PairFoldArgs A) {
     extern __shared__ uint32_t pf_smem[];
     uint32_t* tbl = pf_smem;                                   // 4 * 16 * PF_THREADS words
     __shared__ unsigned char dig[PF_MAXDIG];

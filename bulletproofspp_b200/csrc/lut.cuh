@@ -150,7 +150,7 @@ __device__ __forceinline__ bool lut_next_unit(const LutMsmArgs& A, const u256* s
         return true;
     }
 }
-__global__ void __launch_bounds__(LUT_THREADS, 8) k_msm_lut(LutMsmArgs A) {
+__global__ void __launch_bounds__(LUT_THREADS, 10) k_msm_lut(LutMsmArgs A) {
     __shared__ Xyzz sm[LUT_THREADS / 2];
     __shared__ int counter;
     const int chunk = blockIdx.x, o = blockIdx.y, p = blockIdx.z, tid = threadIdx.x;

@@ -270,7 +270,7 @@ __device__ __forceinline__ const Affine* pip_bases(const PipArgs& A, unsigned g)
     return A.pts + (size_t)(prob / A.n_out) * A.pts_stride;
 }
 
-__global__ void __launch_bounds__(128, 4) k_pip_accum(PipArgs A) {
+__global__ void __launch_bounds__(128, 5) k_pip_accum(PipArgs A) {
     const unsigned E = A.off[A.NT];
     const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     const size_t a64 = t * (size_t)A.L;
