@@ -375,6 +375,15 @@ def main():
     prof_wall = time.time() - tp0
     rep = pctx.profile_report()
     pctx.profile_enable(False)
+    # one proof alone (the drop-in seams' batch size): prove + verify wall time through the same entry points
+    lat = []
+    one = make_inputs(1, base, n)
+    for _ in range(6):
+        tl0 = time.time()
+        pr1 = psetup.prove_batch_raw(1, one[0], one[1], None, one[2])
+        assert sum(psetup.verify_batch_raw(1, *pr1)) == 1
+        lat.append(1e3 * (time.time() - tl0))
+    single_ms = statistics.median(lat[1:])
     rep["h2d_bytes"], rep["d2h_bytes"] = h2d0["h2d_bytes"], h2d0["d2h_bytes"]
     if world > 1:
         t = torch.tensor([t_dev, t_e2e], device="cuda", dtype=torch.float64)
@@ -479,6 +488,9 @@ def main():
             "profile_pass": {"proofs": Bp, "kernel_ms": tot_ms, "wall_s": prof_wall,
                              "note": "one lane's share of a step (prove then verify) on a single stream with a CUDA-event pair "
                                      "around every launch, run after the timed regions; gpu_busy_estimate = kernel_ms x lanes / ms_per_step"},
+            "single_proof_latency_ms": {"prove_plus_verify": round(single_ms, 3),
+                                        "note": "batch of ONE 128by64 proof through bppp_rp_prove_batch + bppp_rp_verify_batch (one lane, "
+                                                "host buffers, wall clock, median of 5): the latency the per-proof Haskell seams see"},
             "imad_peak": {"wide_per_s": imad_wide, "lo32_per_s": imad_lo}, "wall_s_value_leg": wall,
             "prove_call_wall_s": prove_wall,
             "host": {"cpu_ms_per_proof": 1e3 * host_cpu_s / (B * args.steps), "cores_busy": host_cpu_s / wall,

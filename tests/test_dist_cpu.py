@@ -62,3 +62,24 @@ def test_two_rank_plumbing():
     assert [r[2] for r in res] == [0, 64]
     assert all(r[3] == 2.0 for r in res)
     assert all(r[4] == full for r in res)
+
+
+def test_sharded_argument_plan_is_consistent():
+    """host-side planning of bppp_nl_prove_sharded (bulletproofspp_b200/sweep.py): for every size and world the ranks'
+    slices tile the vector, are equal powers of two, the local rounds never fold a slice below one element, and the
+    gathered argument fits the window table (<= 4096 norm elements) whenever the argument is larger than that"""
+    from bulletproofspp_b200.sharding import shard_range
+    from bulletproofspp_b200.sweep import sharded_local_rounds
+    from bulletproofspp_b200.workloads import sweep_rounds
+    for e in range(6, 23):
+        for world in (1, 2, 4, 8):
+            N, ln = 1 << e, (1 << e) // world
+            spans = [shard_range(N, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == N and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(hi - lo == ln for lo, hi in spans) and ln & (ln - 1) == 0
+            lr = sharded_local_rounds(e, world)
+            assert 0 <= lr <= sweep_rounds(e) and (ln >> lr) >= 1
+            gathered = (ln >> lr) * world
+            assert gathered <= max(4096, world) or e <= 12
+            if e > 12:
+                assert gathered == 4096
