@@ -850,6 +850,7 @@ extern "C" int bppp_dtr_absorb(bppp_dtr* t, const uint8_t* pts, size_t stride_po
     bppp_ctx* ctx = t->ctx;
     if (!pts || npts == 0 || stride_points < npts) FAIL(BPPP_ERR_ARG, "bppp_dtr_absorb: bad argument");
     ENTER(ctx);
+    if (t->ncoms[t->n_calls] + npts > t->cap || t->n_calls >= TR_MAX_CALLS) FAIL(BPPP_ERR_STATE, "device transcript: capacity exceeded");
     for (size_t b = 0; b < t->B; b++)
         if (!check_fq(pts + 64 * stride_points * b, 2 * npts)) FAIL(BPPP_ERR_RANGE, "coordinate >= field modulus");
     // every call gets its own staging area: the copies of consecutive calls are queued behind each other
@@ -1966,6 +1967,8 @@ TrrpStatic trrp_static(bppp_trrp* h) {
 int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double scalar_bits = 256.0, uint8_t* chal_out = nullptr,
                 int count = 0, size_t per = 1, const uint8_t* extra = nullptr, size_t n_extra = 0) {
     bppp_ctx* ctx = h->gens->ctx;
+    uint8_t* inv_out = h->chal_inv_out;          // one-shot request: consumed by this call whatever its outcome
+    h->chal_inv_out = nullptr;
     const size_t P0 = h->gens->P0;
     CK(h->res.ensure(n_msm)); CK(h->aff.ensure(n_msm));
     int rc = run_msm_gens(h->gens, P0, sc, P0, 0, n_msm, 1, h->res.p, msm_alg_imads((double)P0, scalar_bits));
@@ -1990,10 +1993,9 @@ int trrp_commit(bppp_trrp* h, const u256* sc, size_t n_msm, uint8_t* out, double
         if ((rc = dtr_absorb_dev(t, src, per, per))) return rc;
         if ((rc = dtr_squeeze_first(t, count))) return rc;
         CK(D2H(chal_out, t->chal.p, t->B * (size_t)count * 32));
-        if (h->chal_inv_out) {
+        if (inv_out) {
             if ((rc = dtr_invert_dev(t, count))) return rc;
-            CK(D2H(h->chal_inv_out, t->chal_inv.p, t->B * (size_t)count * 32));
-            h->chal_inv_out = nullptr;
+            CK(D2H(inv_out, t->chal_inv.p, t->B * (size_t)count * 32));
         }
     }
     CK(ctx_sync(ctx));

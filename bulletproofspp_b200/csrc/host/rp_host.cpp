@@ -2011,10 +2011,7 @@ static std::vector<uint8_t> batch_weights(size_t n) {
     size_t got = 0;
     while (got < rnd.size()) {
         ssize_t r = getrandom(rnd.data() + got, std::min<size_t>(rnd.size() - got, 256), 0);
-        if (r <= 0) {                                               // no entropy source: never silently predictable
-            fprintf(stderr, "bppp: getrandom failed, batch verification weights unavailable\n");
-            abort();
-        }
+        if (r <= 0) return std::vector<uint8_t>();                  // no entropy source: never predictable weights -- the caller verifies per proof
         got += (size_t)r;
     }
     for (size_t i = 0; i < n; i++) memcpy(&w[32 * i], &rnd[16 * i], 16);
@@ -2155,8 +2152,9 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
             sect.lap(S_TOBYTES);
         });
         g_tm.lap("verify_host");
-        if (s->batch_verify && B > 1) {
-            std::vector<uint8_t> wts = batch_weights(B);
+        std::vector<uint8_t> wts;
+        if (s->batch_verify && B > 1) wts = batch_weights(B);
+        if (!wts.empty()) {
             rc = bppp_nl_verify_trrp_rlc(ln.trrp, k, q_b, sp_b, c_b, es_b, responses, n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, wts.data(), ok);
         } else
         rc = bppp_nl_verify_trrp(ln.trrp, k, q_b, sp_b, c_b, es_b, responses, n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, ok);
@@ -2243,8 +2241,9 @@ static int verify_impl(bppp_rp* s, const Lane& ln, size_t batch, size_t rounds, 
     });
     g_tm.lap("verify_host");
     int rc;
-    if (s->batch_verify && B > 1) {
-        std::vector<uint8_t> wts = batch_weights(B);
+    std::vector<uint8_t> wts;
+    if (s->batch_verify && B > 1) wts = batch_weights(B);
+    if (!wts.empty()) {
         rc = bppp_nl_verify_gens_rlc(ln.gens, s->arg, B, k, q_b, sp_b, pw_b, c_b, es_b, responses,
                                      n_norm, n_lin, fw_b, fl_b, NC, is_b, ip_b, wts.data(), ok);
     } else

@@ -138,7 +138,9 @@ __device__ __forceinline__ bool lut_next_unit(const LutMsmArgs& A, const u256* s
             if (d < 0) U.neg |= 1u << (w - w0);
             if (d) {
                 any = true;
+#ifdef BPPP_LUT_PREFETCH_UNIT
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(U.row + (size_t)(w - w0) * NB + m - 1));
+#endif
             }
         }
         U.term = -1;
@@ -169,6 +171,14 @@ __global__ void __launch_bounds__(LUT_THREADS, 10) k_msm_lut(LutMsmArgs A) {
 #pragma unroll 1
         for (int k = 0; k < cur.n; k++) {
             const unsigned m = cur.mag[k];
+#ifndef BPPP_LUT_PREFETCH_UNIT
+            {   // two additions (~6 us) ahead: the entry is in L2 when its turn comes, and it is still there
+                const int k2 = k + 2;
+                const unsigned m2 = k2 < cur.n ? cur.mag[k2] : (have_next && k2 - cur.n < nxt.n ? nxt.mag[k2 - cur.n] : 0xffffu);
+                const Affine* r2 = k2 < cur.n ? cur.row + (size_t)k2 * NB : nxt.row + (size_t)(k2 - cur.n) * NB;
+                if (m2 != 0xffffu) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + m2));
+            }
+#endif
             if (m == 0xffffu) continue;
             Affine P = ld_aff(cur.row + (size_t)k * NB + m);
             if ((cur.neg >> k) & 1u) P.y = fq::neg(P.y);
