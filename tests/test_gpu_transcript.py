@@ -78,3 +78,54 @@ def test_device_random_matches_zkpt(ctx):
         zk = ZKPT(G, s)
         zk.n = n0
         assert got[b * count:(b + 1) * count] == [zk.random() for _ in range(count)]
+
+
+def test_device_transcript_and_round_loop_refuse_misuse(ctx, gens):
+    """error behaviour of the round-2 entry points: capacity, stale handles, wrong shard -- an error code and a
+    message, never a crash or a silent wrong answer"""
+    from bulletproofspp_b200 import lib as L, sweep, workloads as W
+    from bulletproofspp_b200.lib import ARG_NL
+    lib = ctx.lib
+    base = gens(8)
+    t = C.c_void_p()
+    ctx._ck(lib.bppp_dtr_create(ctx.h, 2, 3, 0, C.byref(t)), "bppp_dtr_create")
+    raw = b"".join(L.point_to_bytes(p) for p in base[:2]) * 2
+    ctx._ck(lib.bppp_dtr_absorb(t, raw, 2, 2), "bppp_dtr_absorb")
+    assert lib.bppp_dtr_absorb(t, raw, 2, 2) != 0                       # 4 commitments > capacity 3
+    assert b"capacity" in lib.bppp_last_error(ctx.h)
+    out = C.create_string_buffer(64)
+    assert lib.bppp_dtr_squeeze(t, 1, bytes([10]), None, out) != 0      # scalar index > 9
+    assert lib.bppp_dtr_squeeze(t, 1, bytes([1]), bytes([5]), out) != 0  # a stage that does not exist yet
+    bad = bytearray(raw)
+    bad[0:32] = (2 ** 256 - 1).to_bytes(32, "little")                    # non-canonical coordinate
+    lib.bppp_dtr_reset(t)
+    assert lib.bppp_dtr_absorb(t, bytes(bad), 2, 2) != 0
+    lib.bppp_dtr_destroy(t)
+    # round loop: needs a transcript and a fresh handle
+    e, M = 5, 6
+    N = 1 << e
+    points = W.sweep_generators(ctx, 1 + N + M)
+    inp = W.sweep_inputs(ctx, e, M)
+    gh, h, t2 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    ctx._ck(lib.bppp_gens_create(ctx.h, N, M, points[:64], points[64:64 * (1 + N)], points[64 * (1 + N):], C.byref(gh)), "gens")
+    ctx._ck(lib.bppp_nl_create_gens(gh, ARG_NL, 1, inp["q"], inp["s"], inp["w"], inp["l"], inp["c"], C.byref(h)), "create")
+    k = inp["rounds"]
+    resp = C.create_string_buffer(128 * k)
+    assert lib.bppp_nl_prove_device(h, k, resp, None, None, None, None) != 0          # no transcript
+    ctx._ck(lib.bppp_dtr_create(ctx.h, 1, 1 + 2 * k, 0, C.byref(t2)), "bppp_dtr_create")
+    ctx._ck(lib.bppp_nl_attach_transcript(h, t2), "attach")
+    X, Rr = C.create_string_buffer(64), C.create_string_buffer(64)
+    ctx._ck(lib.bppp_nl_round_commit(h, X, Rr), "round_commit")
+    assert lib.bppp_nl_prove_device(h, k, resp, None, None, None, None) != 0          # a round was already taken
+    comm = sweep.make_comm(ctx, 1, 0)
+    assert lib.bppp_nl_prove_sharded(h, comm, k, 1, M, resp, None, None, None, None) != 0
+    lib.bppp_nl_destroy(h)
+    ctx._ck(lib.bppp_nl_create_gens(gh, ARG_NL, 1, inp["q"], inp["s"], inp["w"], inp["l"], inp["c"], C.byref(h)), "create")
+    ctx._ck(lib.bppp_nl_attach_transcript(h, t2), "attach")
+    ctx._ck(lib.bppp_nl_set_shard(h, N), "set_shard")                                  # rank 0 must start at element 0
+    assert lib.bppp_nl_prove_sharded(h, comm, k, 1, M, resp, None, None, None, None) != 0
+    assert lib.bppp_nl_prove_sharded(h, comm, k, k + 1, M, resp, None, None, None, None) != 0
+    lib.bppp_nl_destroy(h)
+    lib.bppp_comm_destroy(comm)
+    lib.bppp_dtr_destroy(t2)
+    lib.bppp_gens_destroy(gh)
