@@ -2042,9 +2042,9 @@ extern "C" int bppp_trrp_shared_coeffs(bppp_trrp* h, int montgomery, uint8_t* ou
     const u256* chal = h->phase == 2 ? h->chal2.p : h->chalv.p;
     const int stride = h->phase == 2 ? 4 : 8;
     CK(h->sh_out.ensure(B * S));
-    const int per = (int)((S + 31) / 32);
+    const int per = (int)((S + 255) / 256);
     { ProfScope ps_(ctx, K_TRRP, 0);
-    k_trrp_shared<<<(unsigned)((per * B + 3) / 4), 128, 0, ctx->st>>>(chal, stride, h->vt.p, (int)h->n_bases, h->sh_bidx.p, h->sh_sym.p, (int)S, (int)B, h->sh_out.p);
+    k_trrp_shared<<<(unsigned)(per * B), 256, 0, ctx->st>>>(chal, stride, h->vt.p, (int)h->n_bases, h->sh_bidx.p, h->sh_sym.p, (int)S, (int)B, h->sh_out.p);
     }
     CK(cudaGetLastError());
     if (!montgomery) {

@@ -1198,20 +1198,59 @@ __device__ __forceinline__ u256 warp_batch_inv(const u256& v) {
     if (lane < 31) r = fr::mul(r, right);
     return nz ? r : u256_zero();
 }
+// The same across a CTA of up to 8 warps: ONE field inversion per CTA (a lone active lane per warp made 8 inversions
+// per proof the whole cost of k_trrp_shared).  Every thread of the CTA must call it; v = 0 -> 0.
+__device__ __forceinline__ u256 block_batch_inv(const u256& v, u256* sm /* [2 * 8] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const bool nz = !u256_is_zero(v);
+    const u256 x = nz ? v : fr::one();
+    u256 P = x, Q = x;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const u256 o = shfl_u256(P, (lane - d) & 31);
+        if (lane >= d) P = fr::mul(P, o);
+    }
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        const u256 o = shfl_u256(Q, (lane + d) & 31);
+        if (lane + d < 32) Q = fr::mul(Q, o);
+    }
+    if (lane == 31) sm[warp] = P;                                          // the warp's total
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // inverse of every warp total from one inversion of the grand total
+        u256 pre[8], acc = fr::one();
+        for (int w = 0; w < nw; w++) { pre[w] = acc; acc = fr::mul(acc, sm[w]); }
+        u256 inv = fr::inv(acc);
+        for (int w = nw - 1; w >= 0; w--) {
+            const u256 t = sm[w];
+            sm[8 + w] = fr::mul(inv, pre[w]);
+            inv = fr::mul(inv, t);
+        }
+    }
+    __syncthreads();
+    const u256 it = sm[8 + warp];
+    const u256 left = shfl_u256(P, (lane - 1) & 31), right = shfl_u256(Q, (lane + 1) & 31);
+    u256 r = it;
+    if (lane > 0) r = fr::mul(r, left);
+    if (lane < 31) r = fr::mul(r, right);
+    __syncthreads();                                                       // sm may be reused by the caller's next call
+    return nz ? r : u256_zero();
+}
 // makeSharedCoeffs (TypedReciprocal.hs:204-206): slot i of a proof belongs to shared base number bidx[i] and
 // symbol sv[i] (Montgomery): out[p][i] = x^(3 + 2 bidx) * (1/e - 1/(e + s)).  chal = [B][stride] canonical with e
-// at position 0 and 1/e at position 1; vt = the base powers of k_trrp_tables.  One warp per 32 slots.
-__global__ void __launch_bounds__(128) k_trrp_shared(const u256* __restrict__ chal, int chal_stride, const u256* __restrict__ vt, int n_bases,
+// at position 0 and 1/e at position 1; vt = the base powers of k_trrp_tables.  One CTA of 256 threads per proof and
+// 256 slots (one field inversion per CTA).
+__global__ void __launch_bounds__(256) k_trrp_shared(const u256* __restrict__ chal, int chal_stride, const u256* __restrict__ vt, int n_bases,
                                                      const int* __restrict__ bidx, const u256* __restrict__ sv, int n_slots, int B,
                                                      u256* __restrict__ out) {
-    const int per = (n_slots + 31) / 32;                                   // warps per proof
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= per * B) return;
-    const int p = w / per, i = (w % per) * 32 + (threadIdx.x & 31);
+    __shared__ u256 sm[16];
+    const int per = (n_slots + 255) / 256;                                 // CTAs per proof
+    const int p = blockIdx.x / per, i = (blockIdx.x % per) * 256 + threadIdx.x;
     const bool live = i < n_slots;
     const u256 e = fr::to_mont(ld_u256(chal + (size_t)p * chal_stride)), e_inv = fr::to_mont(ld_u256(chal + (size_t)p * chal_stride + 1));
     const u256 den = live ? fr::add(e, ld_u256(sv + i)) : u256_zero();
-    const u256 rec = warp_batch_inv(den);
+    const u256 rec = block_batch_inv(den, sm);
     if (live) st_u256(out + (size_t)p * n_slots + i, fr::mul(ld_u256(vt + (size_t)p * n_bases + bidx[i]), fr::sub(e_inv, rec)));
 }
 // out[i] = 1 / in[i] (canonical in, canonical out, 0 -> 0): the inverses of freshly squeezed challenges
