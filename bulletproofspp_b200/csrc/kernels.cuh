@@ -1299,7 +1299,11 @@ __global__ void __launch_bounds__(TRRP_THREADS) k_trrp_phase2(TrrpP2Args A) {
     const u256* dm = A.scA + (size_t)p * 2 * A.P0;
     const u256* vt = A.vt + (size_t)p * A.st.n_bases;
     u256 e7 = u256_zero();
-    for (int i0 = tid * TRRP_PER; i0 < A.st.n_ent; i0 += TRRP_THREADS * TRRP_PER) {
+    __shared__ u256 sm_inv[16];
+    // every thread takes part in the CTA-wide batch inversion, so all threads run the same number of iterations
+    const int iters = (A.st.n_ent + TRRP_THREADS * TRRP_PER - 1) / (TRRP_THREADS * TRRP_PER);
+    for (int it = 0; it < iters; it++) {
+        const int i0 = (it * TRRP_THREADS + tid) * TRRP_PER;
         u256 den[2 * TRRP_PER], pre[2 * TRRP_PER];
         bool use[2 * TRRP_PER];
         u256 acc = fr::one();
@@ -1320,7 +1324,7 @@ __global__ void __launch_bounds__(TRRP_THREADS) k_trrp_phase2(TrrpP2Args A) {
 #pragma unroll
         for (int k = 0; k < 2 * TRRP_PER; k++)
             if (use[k]) { pre[k] = acc; acc = fr::mul(acc, den[k]); }
-        u256 inv = fr::inv(acc);
+        u256 inv = block_batch_inv(acc, sm_inv);                        // 1 / (product of this thread's denominators): ONE inversion per CTA
 #pragma unroll
         for (int k = 2 * TRRP_PER - 1; k >= 0; k--)
             if (use[k]) { u256 t = fr::mul(inv, pre[k]); inv = fr::mul(inv, den[k]); den[k] = t; }
