@@ -802,6 +802,7 @@ int dtr_absorb_dev(bppp_dtr* t, const Affine* pts, size_t pts_stride, size_t npt
 }
 // part 2 (app/Main.hs:75-80): challenge j = scalar idx[j] of the transcript after state[j] absorb calls
 // (state 0 = all calls so far); left on the device in t->chal, canonical, [batch][n_chal]
+#define TR_COOP_MAX 296           // hashes per launch up to which the CTA-per-hash kernel is used (two per SM)
 int dtr_squeeze_dev(bppp_dtr* t, int n_chal, const unsigned char* idx, const unsigned char* state) {
     bppp_ctx* ctx = t->ctx;
     if (n_chal < 1 || n_chal > TR_MAX_CHAL) FAIL(BPPP_ERR_ARG, "device transcript: 1..48 challenges per call");
@@ -819,7 +820,10 @@ int dtr_squeeze_dev(bppp_dtr* t, int n_chal, const unsigned char* idx, const uns
     }
     const size_t n = t->B * (size_t)n_chal;
     { ProfScope ps_(ctx, K_TR_SQUEEZE, 0);
-    k_tr_squeeze<<<(unsigned)((n + 31) / 32), 32, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);   // one warp per CTA: every warp gets an SM of its own
+    if (n <= TR_COOP_MAX)       // a few long hashes: latency is all that counts, a CTA per hash splits schedule and rounds
+        k_tr_squeeze_coop<<<(unsigned)n, 64, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);
+    else
+        k_tr_squeeze<<<(unsigned)((n + 31) / 32), 32, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);   // one warp per CTA: every warp gets an SM of its own
     }
     CK(cudaGetLastError());
     return BPPP_OK;
@@ -1126,14 +1130,17 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
     bppp_ctx* ctx = g->ctx;
     if (!g->tbl.p)
         return run_msm_pip(ctx, g->pip, g->base.p, 0, sc, sc_stride, sc_out_stride, n_terms, batch, n_out, d_out, work_per_proof);
-    if (g->lut && batch * (size_t)n_out > 8) {
+    if (g->lut) {
         // full-multiples table: W lookups + mixed additions per term, one CTA per (MSM, chunk), no reduction kernel
         // CTAs of 64 threads, 8 per SM: cut every MSM into enough chunks for about four waves of CTAs (CTAs that finish
         // are replaced while others still add -- an R commitment has half the work of an X commitment), at least 64
         // terms per chunk; the chunk sums are added by k_jac_sum
         const size_t n_msm_all = batch * (size_t)n_out;
-        size_t want = (4 * 148 * 8 + n_msm_all - 1) / n_msm_all;
-        want = std::max<size_t>(1, std::min<size_t>(want, (n_terms + 63) / 64));
+        static const int lut_waves = [] { const char* e = getenv("BPPP_LUT_WAVES"); return e && atoi(e) > 0 ? atoi(e) : 2; }();
+        size_t want = ((size_t)lut_waves * 148 * 8 + n_msm_all - 1) / n_msm_all;
+        // (a lone proof: 32 terms per chunk -- one (scalar, half) unit per thread, the latency of 8 additions and the tree)
+        const size_t min_chunk = n_msm_all <= 8 ? 32 : 64;
+        want = std::max<size_t>(1, std::min<size_t>(want, (n_terms + min_chunk - 1) / min_chunk));
         const size_t chunk_terms = (n_terms + want - 1) / want;
         const int nch = (int)((n_terms + chunk_terms - 1) / chunk_terms);
         DBuf<Jac> partsbuf;
@@ -1162,7 +1169,8 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         if (nch > 1) {
             const size_t n_msm = batch * n_out;
             { ProfScope ps_(ctx, K_JAC_SUM, 0);
-            k_jac_sum<<<(unsigned)((n_msm + 127) / 128), 128, 0, ctx->st>>>(parts, nch, nullptr, 0, d_out, n_msm);
+            if (n_msm <= 64) k_jac_sum_warp<<<(unsigned)n_msm, 32, 0, ctx->st>>>(parts, nch, d_out, n_msm);
+            else k_jac_sum<<<(unsigned)((n_msm + 127) / 128), 128, 0, ctx->st>>>(parts, nch, nullptr, 0, d_out, n_msm);
             }
             CK(cudaGetLastError());
         }

@@ -169,31 +169,33 @@ BP_HD Xyzz xyzz_dbl_t(const Xyzz& p) {
 }
 BP_HD Xyzz xyzz_dbl(const Xyzz& p) { return xyzz_dbl_t<FqCall>(p); }
 // XYZZ + affine, complete: 8M + 2S
-BP_HD Xyzz xyzz_madd(const Xyzz& p, const Affine& q) {
+template <class F>
+BP_HD Xyzz xyzz_madd_t(const Xyzz& p, const Affine& q) {
     if (aff_is_inf(q)) return p;
     if (xyzz_is_inf(p)) {
         Xyzz r;
         r.X = q.x; r.Y = q.y; r.ZZ = u256_one(); r.ZZZ = u256_one();
         return r;
     }
-    u256 U2 = fq::mul(q.x, p.ZZ);
-    u256 S2 = fq::mul(q.y, p.ZZZ);
+    u256 U2 = F::mul(q.x, p.ZZ);
+    u256 S2 = F::mul(q.y, p.ZZZ);
     u256 P = fq::sub(U2, p.X);
     u256 R = fq::sub(S2, p.Y);
     if (u256_is_zero(P)) {
         if (u256_is_zero(R)) return xyzz_dbl_aff(q);
         return xyzz_inf();
     }
-    u256 PP = fq::sqr(P);
-    u256 PPP = fq::mul(P, PP);
-    u256 Q = fq::mul(p.X, PP);
+    u256 PP = F::sqr(P);
+    u256 PPP = F::mul(P, PP);
+    u256 Q = F::mul(p.X, PP);
     Xyzz o;
-    o.X = fq::sub(fq::sub(fq::sqr(R), PPP), fq::dbl(Q));
-    o.Y = fq::sub(fq::mul(R, fq::sub(Q, o.X)), fq::mul(p.Y, PPP));
-    o.ZZ = fq::mul(p.ZZ, PP);
-    o.ZZZ = fq::mul(p.ZZZ, PPP);
+    o.X = fq::sub(fq::sub(F::sqr(R), PPP), fq::dbl(Q));
+    o.Y = fq::sub(F::mul(R, fq::sub(Q, o.X)), F::mul(p.Y, PPP));
+    o.ZZ = F::mul(p.ZZ, PP);
+    o.ZZZ = F::mul(p.ZZZ, PPP);
     return o;
 }
+BP_HD Xyzz xyzz_madd(const Xyzz& p, const Affine& q) { return xyzz_madd_t<FqCall>(p, q); }
 // XYZZ + XYZZ, complete: 12M + 2S
 template <class F>
 BP_HD Xyzz xyzz_add_t(const Xyzz& p, const Xyzz& q) {

@@ -363,39 +363,45 @@ BP_HD u256 reduce512(const uint32_t t[16]) {
     return cond_sub(out, (uint32_t)c);
 }
 #if defined(__CUDA_ARCH__)
-// The same reduction with explicit carry chains (device): hi * 977 as one 1 x 8 multiply-accumulate chain, the two
-// 9-limb additions (+ hi * 977, + hi << 32) as add.cc / addc.cc chains, the second fold likewise.  The C version above
-// compiles to ~130 SASS instructions with two dozen IMAD.X on the multiplier pipe; this one to about half of that.
+// The same reduction with explicit carry chains (device).  The eight products hi_i * 977 are independent 64-bit
+// multiplications (no addend, no carry between them: written as a multiply-accumulate chain, ptxas needs a zeroed
+// register pair per step -- 16 moves on the multiplier pipe, and the chain is serial).  The even ones laid end to end
+// are one 256-bit number, the odd ones another at limb 1, so r = lo + EVEN + ((ODD + hi) << 32) is three add chains
+// on the integer pipe.
 BP_D u256 reduce512_dev(const uint32_t t[16]) {
     const uint32_t K = BP_FQ_C0;
-    uint32_t p0, p1, p2, p3, p4, p5, p6, p7, p8;
-    asm("mul.lo.u32 %0,%9,%17; mul.hi.u32 %1,%9,%17;"
-        "mad.lo.cc.u32 %1,%10,%17,%1; madc.hi.u32 %2,%10,%17,0;"
-        "mad.lo.cc.u32 %2,%11,%17,%2; madc.hi.u32 %3,%11,%17,0;"
-        "mad.lo.cc.u32 %3,%12,%17,%3; madc.hi.u32 %4,%12,%17,0;"
-        "mad.lo.cc.u32 %4,%13,%17,%4; madc.hi.u32 %5,%13,%17,0;"
-        "mad.lo.cc.u32 %5,%14,%17,%5; madc.hi.u32 %6,%14,%17,0;"
-        "mad.lo.cc.u32 %6,%15,%17,%6; madc.hi.u32 %7,%15,%17,0;"
-        "mad.lo.cc.u32 %7,%16,%17,%7; madc.hi.u32 %8,%16,%17,0;"
-        : "=&r"(p0), "=&r"(p1), "=&r"(p2), "=&r"(p3), "=&r"(p4), "=&r"(p5), "=&r"(p6), "=&r"(p7), "=&r"(p8)
-        : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]), "r"(K));
-    // r = lo + p   (9 limbs)
+    uint32_t pl[8], ph[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint64_t p = (uint64_t)t[8 + i] * K;
+        pl[i] = (uint32_t)p;
+        ph[i] = (uint32_t)(p >> 32);
+    }
+    // r = lo + EVEN   (limbs 0 .. 7, carry into limb 8)
     uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8, r9;
     asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
         "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24;"
-        "addc.u32 %8,%25,0;"
+        "addc.u32 %8,0,0;"
         : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3), "=&r"(r4), "=&r"(r5), "=&r"(r6), "=&r"(r7), "=&r"(r8)
-        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(p0), "r"(p1), "r"(p2),
-          "r"(p3), "r"(p4), "r"(p5), "r"(p6), "r"(p7), "r"(p8));
-    // r += hi << 32   (limbs 1 .. 8, carry into limb 9)
+        : "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]), "r"(pl[0]), "r"(ph[0]), "r"(pl[2]),
+          "r"(ph[2]), "r"(pl[4]), "r"(ph[4]), "r"(pl[6]), "r"(ph[6]));
+    // s = ODD + hi   (8 limbs and a carry; they sit at limbs 1 .. 9 of r)
+    uint32_t s0, s1, s2, s3, s4, s5, s6, s7, s8;
+    asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,%19; addc.cc.u32 %3,%12,%20;"
+        "addc.cc.u32 %4,%13,%21; addc.cc.u32 %5,%14,%22; addc.cc.u32 %6,%15,%23; addc.cc.u32 %7,%16,%24;"
+        "addc.u32 %8,0,0;"
+        : "=&r"(s0), "=&r"(s1), "=&r"(s2), "=&r"(s3), "=&r"(s4), "=&r"(s5), "=&r"(s6), "=&r"(s7), "=&r"(s8)
+        : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]), "r"(pl[1]), "r"(ph[1]), "r"(pl[3]),
+          "r"(ph[3]), "r"(pl[5]), "r"(ph[5]), "r"(pl[7]), "r"(ph[7]));
+    // r += s << 32
     asm("add.cc.u32 %0,%0,%9; addc.cc.u32 %1,%1,%10; addc.cc.u32 %2,%2,%11; addc.cc.u32 %3,%3,%12;"
         "addc.cc.u32 %4,%4,%13; addc.cc.u32 %5,%5,%14; addc.cc.u32 %6,%6,%15; addc.cc.u32 %7,%7,%16;"
-        "addc.u32 %8,0,0;"
+        "addc.u32 %8,%17,0;"
         : "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(r8), "=r"(r9)
-        : "r"(t[8]), "r"(t[9]), "r"(t[10]), "r"(t[11]), "r"(t[12]), "r"(t[13]), "r"(t[14]), "r"(t[15]));
+        : "r"(s0), "r"(s1), "r"(s2), "r"(s3), "r"(s4), "r"(s5), "r"(s6), "r"(s7), "r"(s8));
     // fold 2: (r9:r8) < 2^34 times C = 2^32 + 977:  + (r9:r8) * 977 at limb 0, + (r9:r8) at limb 1
-    uint32_t vlo, vhi;
-    asm("mul.lo.u32 %0,%2,%4; mul.hi.u32 %1,%2,%4; mad.lo.u32 %1,%3,%4,%1;" : "=&r"(vlo), "=&r"(vhi) : "r"(r8), "r"(r9), "r"(K));
+    const uint64_t v = (uint64_t)r8 * K;
+    const uint32_t vlo = (uint32_t)v, vhi = (uint32_t)(v >> 32) + r9 * K;
     u256 out;
     uint32_t c1, c2;
     asm("add.cc.u32 %0,%9,%17; addc.cc.u32 %1,%10,%18; addc.cc.u32 %2,%11,0; addc.cc.u32 %3,%12,0;"

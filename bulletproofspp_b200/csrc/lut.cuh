@@ -26,6 +26,12 @@ namespace bppp {
 
 #define LUT_RUN 256                    // multiples per k_lut_fill thread (or NB when NB is smaller)
 #define LUT_THREADS 64                 // few threads per MSM: the tree sum at the end is 6 levels, 2 % of a thread's work
+#ifndef LUT_MIN_CTAS
+#define LUT_MIN_CTAS 10                // resident CTAs per SM the register allocation aims at
+#endif
+#ifndef LUT_FQ
+#define LUT_FQ FqCall                  // FqInl: the multiplications of the loop's one mixed addition inlined
+#endif
 
 struct LutDesc {
     Affine* tbl;                       // [P0][W][NB]
@@ -152,7 +158,7 @@ __device__ __forceinline__ bool lut_next_unit(const LutMsmArgs& A, const u256* s
         return true;
     }
 }
-__global__ void __launch_bounds__(LUT_THREADS, 10) k_msm_lut(LutMsmArgs A) {
+__global__ void __launch_bounds__(LUT_THREADS, LUT_MIN_CTAS) k_msm_lut(LutMsmArgs A) {
     __shared__ Xyzz sm[LUT_THREADS / 2];
     __shared__ int counter;
     const int chunk = blockIdx.x, o = blockIdx.y, p = blockIdx.z, tid = threadIdx.x;
@@ -168,24 +174,24 @@ __global__ void __launch_bounds__(LUT_THREADS, 10) k_msm_lut(LutMsmArgs A) {
     bool have = lut_next_unit(A, sc, base, 2 * n, &counter, cur);
     while (have) {
         const bool have_next = lut_next_unit(A, sc, base, 2 * n, &counter, nxt);
+        const int n_slots = cur.n + (cur.term >= 0 ? 1 : 0);              // the top carry 2^(c W) P_i is one more entry
 #pragma unroll 1
-        for (int k = 0; k < cur.n; k++) {
-            const unsigned m = cur.mag[k];
+        for (int k = 0; k < n_slots; k++) {
+            const unsigned m = k < cur.n ? cur.mag[k] : 0u;
 #ifndef BPPP_LUT_PREFETCH_UNIT
             {   // two additions (~6 us) ahead: the entry is in L2 when its turn comes, and it is still there
                 const int k2 = k + 2;
-                const unsigned m2 = k2 < cur.n ? cur.mag[k2] : (have_next && k2 - cur.n < nxt.n ? nxt.mag[k2 - cur.n] : 0xffffu);
-                const Affine* r2 = k2 < cur.n ? cur.row + (size_t)k2 * NB : nxt.row + (size_t)(k2 - cur.n) * NB;
+                const unsigned m2 = k2 < cur.n ? cur.mag[k2] : (have_next && k2 >= n_slots && k2 - n_slots < nxt.n ? nxt.mag[k2 - n_slots] : 0xffffu);
+                const Affine* r2 = k2 < cur.n ? cur.row + (size_t)k2 * NB : nxt.row + (size_t)(k2 - n_slots) * NB;
                 if (m2 != 0xffffu) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + m2));
             }
 #endif
             if (m == 0xffffu) continue;
-            Affine P = ld_aff(cur.row + (size_t)k * NB + m);
-            if ((cur.neg >> k) & 1u) P.y = fq::neg(P.y);
-            acc = xyzz_madd(acc, P);
+            Affine P = ld_aff(k < cur.n ? cur.row + (size_t)k * NB + m : A.D.carry + cur.term);
+            if ((cur.neg >> k) & 1u) P.y = fq::neg(P.y);                  // bit cur.n is never set
+            acc = xyzz_madd_t<LUT_FQ>(acc, P);                              // the ONE addition site of the loop
             n_add++;
         }
-        if (cur.term >= 0) { acc = xyzz_madd(acc, ld_aff(A.D.carry + cur.term)); n_add++; }
         cur = nxt;
         have = have_next;
     }

@@ -48,6 +48,44 @@ __device__ __forceinline__ void compress(uint32_t st[8], uint32_t w[16]) {
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
+// The two halves of `compress`, for hashing ONE long message as fast as one thread can (k_tr_squeeze_coop): the
+// message schedule of a block depends on the block alone, so other threads expand it ahead of time
+// (kw[i] = K[i] + W[i]) and the thread that owns the chaining value runs only the 64 rounds -- 15 instructions per
+// round with a dependent chain of three (funnel shift, xor3, three-input add) through e.
+__device__ __forceinline__ void expand_kw(uint32_t w[16], uint32_t* __restrict__ kw) {
+#pragma unroll
+    for (int i = 0; i < 64; i++) {
+        if (i >= 16) {
+            const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+            const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+            const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+            w[i & 15] += s0 + w[(i + 9) & 15] + s1;
+        }
+        kw[i] = w[i & 15] + K256[i];
+    }
+}
+__device__ __forceinline__ void rounds_kw(uint32_t st[8], const uint32_t* __restrict__ kw) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i4 = 0; i4 < 16; i4++) {
+        const uint4 q = *reinterpret_cast<const uint4*>(kw + 4 * i4);
+        const uint32_t k4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t x = h + k4[r];                              // off the chain: h was e three rounds ago
+            const uint32_t dx = d + x;
+            const uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            const uint32_t en = dx + S1 + ch;
+            const uint32_t an = (x + S0 + mj) + (S1 + ch);
+            h = g; g = f; f = e; e = en; d = c; c = b; b = a; a = an;
+        }
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
 // Streaming hasher of one thread.  The 64-byte block buffer lives in SHARED memory, word-major across the
 // CTA (blk[word * blockDim.x + tid]: conflict-free) so that the running word index can be dynamic; bytes
 // arrive through a 64-bit shift register, so pieces of any length and alignment can be appended.

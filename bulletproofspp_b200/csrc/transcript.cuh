@@ -276,6 +276,91 @@ __global__ void __launch_bounds__(TR_THREADS) k_tr_squeeze(const unsigned char* 
     st_u256(out + t, dsha::digest_to_fr(st));
 }
 
+// The same challenges for a FEW hashes (one proof alone: the drop-in seams' batch size).  A thread that hashes a
+// message by itself issues ~3000 instructions per 64-byte block, two thirds of them message assembly and schedule;
+// a 22 KB transcript takes 0.6 ms, and a proof has 14 of them in a row.  Here a CTA of two warps owns one hash:
+// warp 1 assembles and expands the blocks of the next tile (one block per lane, kw = K + W into shared memory),
+// lane 0 of warp 0 runs the rounds of the current tile.  Bit-identical to k_tr_squeeze.
+#define TRC_TILE 32                    // blocks per tile (one per lane of the scheduling warp)
+#define TRC_STRIDE 68                  // words per block in shared memory: 64 + 4 (16-byte rows, 4-way store conflicts)
+__global__ void __launch_bounds__(64) k_tr_squeeze_coop(const unsigned char* __restrict__ buf, unsigned SC, const unsigned* __restrict__ start,
+                                                        TrPlan plan, size_t batch, u256* __restrict__ out) {
+    __shared__ __align__(16) uint32_t kw[2][TRC_TILE * TRC_STRIDE];
+    const size_t t = blockIdx.x;
+    const size_t b = t / plan.count;
+    const int j = (int)(t % plan.count);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char hdr[8];
+    unsigned hl = 0;
+    hdr[hl++] = (unsigned char)('0' + plan.idx[j]);
+    {
+        char tmp[8];
+        int n = 0;
+        unsigned x = plan.ncoms[j];
+        do { tmp[n++] = (char)('0' + x % 10); x /= 10; } while (x && n < 7);
+        while (n) hdr[hl++] = (unsigned char)tmp[--n];
+    }
+    const unsigned st0 = start[b * (TR_MAX_CALLS + 1) + plan.state[j]];
+    const unsigned char* body = buf + b * (size_t)SC + st0;
+    const unsigned L = SC - st0;
+    const unsigned long long T = (unsigned long long)hl + L;
+    const unsigned nblk = (unsigned)((T + 9 + 63) / 64);
+    const unsigned ntile = (nblk + TRC_TILE - 1) / TRC_TILE;
+    const size_t a0 = (size_t)(body - hl);
+    const unsigned sh = (unsigned)(a0 & 3);
+    const unsigned sel = (sh + 3) | ((sh + 2) << 4) | ((sh + 1) << 8) | (sh << 12);
+    auto schedule = [&](unsigned tile) {
+        const unsigned k = tile * TRC_TILE + lane;
+        if (k >= nblk) return;
+        uint32_t w[16];
+        const unsigned long long m0 = (unsigned long long)k * 64;
+        if (k >= 1 && m0 + 64 <= T) {
+            const uint32_t* q = reinterpret_cast<const uint32_t*>((a0 + m0) & ~(size_t)3);
+            uint32_t nx[17];
+#pragma unroll
+            for (int i = 0; i < 17; i++) nx[i] = q[i];
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = __byte_perm(nx[i], nx[i + 1], sel);
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 16; i++) {
+                uint32_t x = 0;
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
+                    const unsigned long long m = m0 + 4 * i + c;
+                    unsigned byte = 0;
+                    if (m < hl) byte = hdr[m];
+                    else if (m < T) byte = body[m - hl];
+                    else if (m == T) byte = 0x80;
+                    x = (x << 8) | byte;
+                }
+                w[i] = x;
+            }
+            if (k == nblk - 1) {
+                const unsigned long long bits = T * 8;
+                w[14] = (uint32_t)(bits >> 32);
+                w[15] = (uint32_t)bits;
+            }
+        }
+        dsha::expand_kw(w, &kw[tile & 1][lane * TRC_STRIDE]);
+    };
+    uint32_t st[8];
+    dsha::init(st);
+    if (warp == 1) schedule(0);
+    __syncthreads();
+    for (unsigned tile = 0; tile < ntile; tile++) {
+        if (warp == 1) {
+            if (tile + 1 < ntile) schedule(tile + 1);
+        } else if (lane == 0) {
+            const unsigned nb = min((unsigned)TRC_TILE, nblk - tile * TRC_TILE);
+#pragma unroll 1
+            for (unsigned i = 0; i < nb; i++) dsha::rounds_kw(st, &kw[tile & 1][i * TRC_STRIDE]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) st_u256(out + t, dsha::digest_to_fr(st));
+}
+
 // `random` (src/ZKP.hs:90-93 with h = hashToScalar rn . show, app/Main.hs:177): out[b * out_stride + j] =
 // hash(seed_b <> show (n0_b + j)) as a canonical scalar, n0_b = n0s[b] (or n0 for every proof when n0s is
 // null).  seeds = [batch][64] bytes, seed_len <= 40 so that the message is a single block.

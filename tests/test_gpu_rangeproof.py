@@ -286,6 +286,8 @@ def test_full_multiples_table_is_bit_identical(ctx, name, count, gb):
         p1 = lut.prove_batch(wits, seeds)
         assert p0 == p1
         assert all(lut.verify_batch(p0)) and all(plain.verify_batch(p1))
+        # a lone proof takes the table too (32-term chunks, warp-level sum of the chunk partials)
+        assert lut.prove_batch(wits[:1], seeds[:1]) == p0[:1] and lut.verify_batch(p0[:1]) == [True]
     bad = dict(p1[1], finals=[(p1[1]["finals"][0] + 1) % (2 ** 200)] + p1[1]["finals"][1:])
     assert lut.verify_batch([p1[0], bad] + p1[2:]) == [True, False] + [True] * (count - 2)
     lut.set_batch_verify(True)
