@@ -66,6 +66,28 @@ def test_device_oracle_matches_transcript(ctx, gens, fmt, ofmt):
     ctx.lib.bppp_dtr_destroy(t)
 
 
+def test_both_squeeze_kernels_agree_with_the_oracle(ctx, gens):
+    """up to 296 hashes per launch take k_tr_squeeze_coop (a CTA per hash: schedule and rounds on separate warps),
+    larger launches k_tr_squeeze (a thread per hash); 110 proofs with 1, 2 and 3 challenges per call cross the
+    switch in both directions on one transcript, with bodies from one block to several tiles of 32 blocks"""
+    from bulletproofspp_b200 import lib as L
+    B = 110
+    base = gens(40)
+    calls = [(0, 1), (1, 3), (20, 3), (2, 1), (1, 2), (30, 2), (0, 3)]
+    t = C.c_void_p()
+    ctx._ck(ctx.lib.bppp_dtr_create(ctx.h, B, 60, 0, C.byref(t)), "bppp_dtr_create")
+    zks = [ZKPT(G, None, PREFIXED_P) for _ in range(B)]
+    for ci, (npts, count) in enumerate(calls):
+        pts = [[base[H("k", ci, b, j) % 40] for j in range(npts)] for b in range(B)]
+        raw = b"".join(b"".join(L.point_to_bytes(p) for p in row) for row in pts)
+        out = C.create_string_buffer(32 * B * count)
+        ctx._ck(ctx.lib.bppp_dtr_oracle(t, raw if npts else None, npts, count, out), "bppp_dtr_oracle")
+        got = L.bytes_to_ints(out.raw[:32 * B * count])
+        for b in range(B):
+            assert got[b * count:(b + 1) * count] == zks[b].oracle(pts[b], count), "call %d proof %d" % (ci, b)
+    ctx.lib.bppp_dtr_destroy(t)
+
+
 def test_device_random_matches_zkpt(ctx):
     from bulletproofspp_b200 import lib as L
     seeds = ["default random seed", "default random seed#17", "s", "x" * 40]
