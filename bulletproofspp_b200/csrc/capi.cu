@@ -3134,7 +3134,7 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
     const bool ip = kind == BPPP_ARG_IP;
     const size_t nvs = ip ? n_norm / 2 : n_norm;
     if (ip && (n_norm & 1)) FAIL(BPPP_ERR_ARG, "IP final norm witness has an even number of scalars");
-    std::vector<Fr> hf0n(B * k), hf1(B * k), hf0l(B * k, h64::one()), hvn(B * std::max<size_t>(nvs, 1)), hvl(B * n_lin), scn(B), hc(B * M);
+    std::vector<Fr> hf0n(B * k), hf1(B * k), hf0l(B * k, h64::one()), hvn(B * std::max<size_t>(nvs, 1)), hvl(B * n_lin), scn(B);
     std::vector<Fr> hf1y(B * k), hvy(B * std::max<size_t>(nvs, 1)), hr(B), einv(B * std::max<size_t>(k, 1));
     std::vector<u256> hx(B * std::max<size_t>(NX, 1));
     std::vector<Affine> hp(B * std::max<size_t>(NX, 1));
@@ -3176,7 +3176,6 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
         }
         scn[b] = acc;
         for (size_t i = 0; i < n_lin; i++) hvl[b * n_lin + i] = h64::from_bytes(fl + 32 * (b * n_lin + i));
-        for (size_t i = 0; i < M; i++) hc[b * M + i] = h64::from_bytes(c + 32 * (b * M + i));
         // extra terms: initCom opening, then (e0, X), (e1, R) per round, newest first (verifyWith)
         for (size_t i = 0; i < n_init; i++) {
             hx[b * NX + i] = host::from_bytes(init_s + 32 * (b * n_init + i));
@@ -3233,7 +3232,6 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
         }
         CK(cudaGetLastError());
     }
-    std::vector<u256> tl(B * M);
     if (M) {
         TensorArgs A;
         A.pub = nullptr; A.pub_stride = 0; A.vs = vs_l.p; A.n_vs = (int)n_lin; A.f0 = f0l.p; A.f1 = f1.p; A.k = (int)k;
@@ -3242,23 +3240,21 @@ int nl_verify_impl(bppp_gens* gens, int kind, size_t batch, size_t k, const uint
         k_tensor_expand<<<dim3((unsigned)((M + 255) / 256), (unsigned)B), 256, 0, ctx->st>>>(A);
         }
         CK(cudaGetLastError());
-        // sc_lin = sum_j c_j * tensor_j  (contract' . tensor', NormArgument.hs:75-78); the kernel wrote -tensor_j
-        ctx->d2h += B * M * 32;
-        CK(cudaMemcpy2DAsync(tl.data(), M * 32, sc.p + 1 + N, P0 * 32, M * 32, B, cudaMemcpyDeviceToHost, ctx->st));
     }
-    CK(ctx_sync(ctx));
-    std::vector<u256> s0(B);
-    host_parallel_for(B, [&](size_t b) {
-        Fr acc = scn[b];
-        for (size_t j = 0; j < M; j++) {
-            uint64_t cw[4];
-            memcpy(cw, tl[b * M + j].v, 32);
-            acc = h64::sub(acc, h64::mul(hc[b * M + j], h64::from_canon(cw)));
+    // the scalar on g: s_pub - (norm part) + sum_j c_j * (-tensor_j) -- sc_lin = contract' . tensor' (NormArgument.hs:75-78)
+    // is a dot product with what the kernel above just wrote, so it stays on the device (no synchronisation here)
+    {
+        std::vector<u256> d0(B);
+        for (size_t b = 0; b < B; b++) d0[b] = fr_canon_u256(h64::sub(h64::from_bytes(s_pub + 32 * b), scn[b]));
+        DBuf<u256> cdev, ddev;
+        CK(cdev.alloc(B * std::max<size_t>(M, 1))); CK(ddev.alloc(B));
+        if (M) CK(H2D(cdev.p, c, B * M * 32));
+        CK(H2D(ddev.p, d0.data(), B * 32));
+        { ProfScope ps_(ctx, K_TENSOR, 0);
+        k_verify_s0<<<(unsigned)B, VS0_THREADS, 0, ctx->st>>>(cdev.p, ddev.p, sc.p, P0, 1 + (int)N, (int)M);
         }
-        s0[b] = fr_canon_u256(h64::sub(h64::from_bytes(s_pub + 32 * b), acc));
-    });
-    ctx->h2d += B * 32;
-    CK(cudaMemcpy2DAsync(sc.p, P0 * 32, s0.data(), 32, 32, B, cudaMemcpyHostToDevice, ctx->st));
+        CK(cudaGetLastError());
+    }
     int rc;
     if (weights && B > 1) {
         // Batch verification across proofs: sum_b rho_b (sum_i sc[b][i] G_i + sum_j xsc[b][j] P[b][j]) = 0 -- ONE fixed-base

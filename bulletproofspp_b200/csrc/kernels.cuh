@@ -954,6 +954,29 @@ __global__ void k_jac_sum(const Jac* __restrict__ a, int na, const Jac* __restri
     st_jac(out + m, acc);
 }
 
+// The verifier's scalar on g (verifyWith: the opening scalar minus the scalar side of the collapsed argument):
+//   sc[b][0] = d[b] + sum_j c[b][j] * sc[b][off + j],   d = s_pub - (norm part), c canonical, and sc[b][off + j] =
+// -tensor_j as k_tensor_expand left it (contract' . tensor', NormArgument.hs:75-78).  One CTA per proof.
+#define VS0_THREADS 128
+__global__ void __launch_bounds__(VS0_THREADS) k_verify_s0(const u256* __restrict__ c, const u256* __restrict__ d, u256* __restrict__ sc,
+                                                           size_t stride, int off, int M) {
+    __shared__ u256 sm[VS0_THREADS / 32];
+    const size_t b = blockIdx.x;
+    const int tid = threadIdx.x;
+    u256 acc = u256_zero();
+    for (int j = tid; j < M; j += VS0_THREADS)       // to_mont(c) * canonical = canonical product
+        acc = fr::add(acc, fr::mul(fr::to_mont(ld_u256(c + b * (size_t)M + j)), ld_u256(sc + b * stride + off + j)));
+#pragma unroll 1
+    for (int s2 = 16; s2 >= 1; s2 >>= 1) acc = fr::add(acc, shfl_u256(acc, (tid + s2) & 31));   // every lane ends with the warp sum
+    if ((tid & 31) == 0) sm[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        u256 t = ld_u256(d + b);
+        for (int w = 0; w < VS0_THREADS / 32; w++) t = fr::add(t, sm[w]);
+        st_u256(sc + b * stride, t);
+    }
+}
+
 // the same sum for a lone proof: one warp per MSM, lane k adds partials k, k + 32, ..., then a shuffle tree
 __global__ void __launch_bounds__(32) k_jac_sum_warp(const Jac* __restrict__ a, int na, Jac* __restrict__ out, size_t n_msm) {
     const size_t m = blockIdx.x;
