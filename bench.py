@@ -429,10 +429,10 @@ def main():
     ncu = ncu_summary().get(top, {})
     peak_t = imad_wide / 1e12
     # IMAD.WIDE instructions the kernel really issues for its group arithmetic, counted live: every table lookup of
-    # k_msm_lut is one XYZZ mixed addition = 8 fq::mul + 2 fq::sqr = 8 x 71 + 2 x 43 IMAD.WIDE (SASS of this build)
+    # k_msm_lut is one XYZZ mixed addition = 8 fq::mul + 2 fq::sqr = 8 x 72 + 2 x 43 IMAD.WIDE (SASS of this build)
     issued = None
     if top == "k_msm_lut" and rep.get("lut_lookups"):
-        issued = rep["lut_lookups"] * (8 * 71 + 2 * 43) / (kt["ms"] * 1e-3) / 1e12
+        issued = rep["lut_lookups"] * (8 * 72 + 2 * 43) / (kt["ms"] * 1e-3) / 1e12
     frac_pipe = issued / peak_t if issued else None
     roofline = {"kernel": top, "bound": "imad", "achieved": issued if issued else ach, "peak": peak_t, "unit": "TIMAD/s",
                 "frac": frac_pipe if frac_pipe else ach / peak_t,
@@ -442,7 +442,7 @@ def main():
                 "lookups_per_launch": (rep.get("lut_lookups", 0) / kt["launches"]) if issued else None,
                 "avg_launch_ms": kt["ms"] / kt["launches"], "share_of_gpu_time": shares[top],
                 "note": "integer-pipe bound (no hbm/tensor roofline applies).  frac = frac_pipe = IMAD.WIDE instructions issued for the group "
-                        "arithmetic (counted live: lookups x 654 per mixed addition) / CUDA-event time / the IMAD.WIDE issue rate measured in "
+                        "arithmetic (counted live: lookups x 662 per mixed addition) / CUDA-event time / the IMAD.WIDE issue rate measured in "
                         "this run.  pipe_active_ncu = sm__pipe_fmaheavy_cycles_active of the committed ncu --set full capture (%s): the "
                         "carry handling and register moves of a field multiplication (IMAD.X, IMAD.MOV: a third of its IMAD-class "
                         "instructions) occupy the same pipe, which is why %s of useful multiplies is %s of the pipe.  frac_alg = the reference schedule's IMADs "
