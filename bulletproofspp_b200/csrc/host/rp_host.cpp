@@ -1038,10 +1038,15 @@ namespace {
 #ifdef BPPP_SAMPLER
 std::atomic<size_t> g_ns{0};
 void** g_samples = nullptr;
+void** g_callers = nullptr;           // the frame's return address (meaningful in a -fno-omit-frame-pointer build)
 const size_t kMaxSamples = 1 << 20;
 void sample_handler(int, siginfo_t*, void* uc) {
     size_t i = g_ns.fetch_add(1, std::memory_order_relaxed);
-    if (i < kMaxSamples) g_samples[i] = (void*)((ucontext_t*)uc)->uc_mcontext.gregs[REG_RIP];
+    if (i >= kMaxSamples) return;
+    const greg_t* r = ((ucontext_t*)uc)->uc_mcontext.gregs;
+    g_samples[i] = (void*)r[REG_RIP];
+    const uintptr_t bp = (uintptr_t)r[REG_RBP], sp = (uintptr_t)r[REG_RSP];
+    g_callers[i] = (bp >= sp && bp - sp < (1u << 20) && (bp & 7) == 0) ? ((void**)bp)[1] : nullptr;   // same stack, plausible frame
 }
 void sample_dump() {
     const char* path = getenv("BPPP_SAMPLE");
@@ -1052,9 +1057,13 @@ void sample_dump() {
     size_t n = std::min(g_ns.load(), kMaxSamples);
     for (size_t i = 0; i < n; i++) {
         Dl_info di;
+        Dl_info dc;
+        unsigned long coff = 0;
+        if (g_callers[i] && dladdr(g_callers[i], &dc) && dc.dli_fname && strstr(dc.dli_fname, "libbppp_b200"))
+            coff = (unsigned long)((char*)g_callers[i] - (char*)dc.dli_fbase);
         if (dladdr(g_samples[i], &di) && di.dli_fname)
-            fprintf(f, "%s %lx %s\n", di.dli_fname, (unsigned long)((char*)g_samples[i] - (char*)di.dli_fbase), di.dli_sname ? di.dli_sname : "?");
-        else fprintf(f, "? %lx ?\n", (unsigned long)g_samples[i]);
+            fprintf(f, "%s %lx@%lx %s\n", di.dli_fname, (unsigned long)((char*)g_samples[i] - (char*)di.dli_fbase), coff, di.dli_sname ? di.dli_sname : "?");
+        else fprintf(f, "? %lx@0 ?\n", (unsigned long)g_samples[i]);
     }
     fclose(f);
 }
@@ -1063,6 +1072,7 @@ void sample_start() {
     std::call_once(once, [] {
         if (!getenv("BPPP_SAMPLE")) return;
         g_samples = (void**)calloc(kMaxSamples, sizeof(void*));
+        g_callers = (void**)calloc(kMaxSamples, sizeof(void*));
         struct sigaction sa = {};
         sa.sa_sigaction = sample_handler;
         sa.sa_flags = SA_SIGINFO | SA_RESTART;
