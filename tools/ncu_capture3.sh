@@ -17,6 +17,14 @@ cap() {   # name, regex, skip, command...
     ncu -i $out/${tag}_ncu_$name.ncu-rep --page source --csv 2>/dev/null | gzip -9 > $out/${tag}_ncu_source_$name.csv.gz
     rm -f $out/${tag}_ncu_$name.ncu-rep
 }
-cap k_msm_lut '^k_msm_lut' 30 $B
-cap k_tr_squeeze_coop '^k_tr_squeeze_coop' 20 $L
-ls -la $out | tail -8
+if [ "$2" != "more" ]; then
+    cap k_msm_lut '^k_msm_lut' 30 $B
+    cap k_tr_squeeze_coop '^k_tr_squeeze_coop' 20 $L
+    ls -la $out | tail -8
+fi
+# the next kernels of the batch step by share (run with: bash tools/ncu_capture3.sh r2b more)
+if [ "$2" = "more" ]; then
+    cap k_trrp_phase2 '^k_trrp_phase2' 4 $B
+    cap k_batch_to_affine '^k_batch_to_affine' 8 $B
+    ls -la $out | tail -8
+fi
