@@ -1313,7 +1313,7 @@ struct TrrpP2Args {
     int err7_slot;                     // index inside a scR row
     u256* err7;                        // [B] canonical
 };
-__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_phase2(TrrpP2Args A) {
+__global__ void __launch_bounds__(TRRP_THREADS, 2) k_trrp_phase2(TrrpP2Args A) {
     __shared__ u256 sm[TRRP_THREADS / 32];
     const int p = blockIdx.x, tid = threadIdx.x;
     const u256 e = fr::to_mont(ld_u256(A.chal + (size_t)p * 4 + 0));
@@ -1389,7 +1389,7 @@ struct TrrpP3Args {
     u256* errs;                        // [B][6] canonical (without the shared-multiplicity term of err3)
 };
 // makeErrorTerms (TypedReciprocal.hs:217-233) over the norm entries
-__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_errterms(TrrpP3Args A) {
+__global__ void __launch_bounds__(TRRP_THREADS, 2) k_trrp_errterms(TrrpP3Args A) {
     __shared__ u256 sm[TRRP_THREADS / 32];
     const int p = blockIdx.x, tid = threadIdx.x;
     const u256 e = fr::to_mont(ld_u256(A.chal2 + (size_t)p * 4 + 0));
@@ -1461,7 +1461,7 @@ struct TrrpP4Args {
 };
 // makePublicConsts' norm part (TypedReciprocal.hs:236-263) fused with the witness combination
 //   wit = pub + bl + t m + t^2 dm + t^3 r   (:439; the inputs have no norm part)
-__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_phase4(TrrpP4Args A) {
+__global__ void __launch_bounds__(TRRP_THREADS, 2) k_trrp_phase4(TrrpP4Args A) {
     __shared__ u256 sm[TRRP_THREADS / 32];
     const int p = blockIdx.x, tid = threadIdx.x;
     const u256 e = fr::to_mont(ld_u256(A.chal2 + (size_t)p * 4 + 0));
@@ -1520,7 +1520,7 @@ struct TrrpVArgs {
 };
 // The verifier's makePublicConsts (TypedReciprocal.hs:236-263, called from verifyTRRPM :447-467):
 // the same p_i as the prover's phase 4, from public data only (u_i, v_i and the symbol term c_i)
-__global__ void __launch_bounds__(TRRP_THREADS) k_trrp_verify_pub(TrrpVArgs A) {
+__global__ void __launch_bounds__(TRRP_THREADS, 2) k_trrp_verify_pub(TrrpVArgs A) {
     __shared__ u256 sm[TRRP_THREADS / 32];
     const int p = blockIdx.x, tid = threadIdx.x;
     const u256* ch = A.chal + (size_t)p * 8;
