@@ -729,7 +729,7 @@ extern "C" int bppp_get_points(bppp_ctx* ctx, const char* seed, size_t count, in
 
 // Device transcript of `batch` proofs in lock-step: the commitment list of ZKPT (src/ZKP.hs:68-101)
 // rendered in device memory (one right-aligned byte string per proof, k_tr_prepend), challenges by SHA-256 on the
-// device (k_tr_squeeze).  Bit-identical to the host transcript (csrc/host/transcript.hpp).
+// device (k_tr_squeeze_pair / k_tr_squeeze_coop).  Bit-identical to the host transcript (csrc/host/transcript.hpp).
 struct bppp_dtr {
     bppp_ctx* ctx;
     size_t B, cap;                      // proofs, commitments per proof the store can hold
@@ -823,7 +823,7 @@ int dtr_squeeze_dev(bppp_dtr* t, int n_chal, const unsigned char* idx, const uns
     if (n <= TR_COOP_MAX)       // a few long hashes: latency is all that counts, a CTA per hash splits schedule and rounds
         k_tr_squeeze_coop<<<(unsigned)n, 64, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);
     else
-        k_tr_squeeze<<<(unsigned)((n + 31) / 32), 32, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);   // one warp per CTA: every warp gets an SM of its own
+        k_tr_squeeze_pair<<<(unsigned)((n + 31) / 32), 64, 0, ctx->st>>>(t->buf.p, t->SC, t->start.p, plan, t->B, t->chal.p);   // 32 hashes per CTA: every CTA gets an SM of its own
     }
     CK(cudaGetLastError());
     return BPPP_OK;

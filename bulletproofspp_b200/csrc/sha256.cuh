@@ -86,6 +86,48 @@ __device__ __forceinline__ void rounds_kw(uint32_t st[8], const uint32_t* __rest
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
+// ... and the same two halves for 32 hashes side by side: cell i4 of a lane holds K + W of rounds 4 i4 .. 4 i4 + 3, cells
+// of consecutive lanes are consecutive in shared memory (stride 32 cells between i4 and i4 + 1)
+__device__ __forceinline__ void expand_kw_cells(uint32_t w[16], uint4* __restrict__ cell) {
+#pragma unroll
+    for (int i4 = 0; i4 < 16; i4++) {
+        uint32_t o[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int i = 4 * i4 + r;
+            if (i >= 16) {
+                const uint32_t w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                const uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
+                const uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
+                w[i & 15] += s0 + w[(i + 9) & 15] + s1;
+            }
+            o[r] = w[i & 15] + K256[i];
+        }
+        cell[32 * i4] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+__device__ __forceinline__ void rounds_kw_cells(uint32_t st[8], const uint4* __restrict__ cell) {
+    uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
+#pragma unroll
+    for (int i4 = 0; i4 < 16; i4++) {
+        const uint4 q = cell[32 * i4];
+        const uint32_t k4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t x = h + k4[r];
+            const uint32_t dx = d + x;
+            const uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
+            const uint32_t ch = (e & f) ^ (~e & g);
+            const uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
+            const uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
+            const uint32_t en = dx + S1 + ch;
+            const uint32_t an = (x + S0 + mj) + (S1 + ch);
+            h = g; g = f; f = e; e = en; d = c; c = b; b = a; a = an;
+        }
+    }
+    st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
+}
+
 // Streaming hasher of one thread.  The 64-byte block buffer lives in SHARED memory, word-major across the
 // CTA (blk[word * blockDim.x + tid]: conflict-free) so that the running word index can be dynamic; bytes
 // arrive through a 64-bit shift register, so pieces of any length and alignment can be appended.

@@ -199,88 +199,20 @@ struct TrPlan {
     unsigned ncoms[TR_MAX_CHAL];
 };
 
-// out[b * count + j] = challenge j of proof b, canonical scalar (digest -> Fr, Encoding.hs:75-79).  One thread per
-// (proof, challenge).  A block that lies inside the body is read with 17 aligned word loads and byte
-// permutes (the body's alignment is fixed for the whole message); the first block (header) and the last
-// one or two (tail, 0x80, bit length) are assembled byte by byte.
-__global__ void __launch_bounds__(TR_THREADS) k_tr_squeeze(const unsigned char* __restrict__ buf, unsigned SC, const unsigned* __restrict__ start,
-                                                           TrPlan plan, size_t batch, u256* __restrict__ out) {
-    const size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (t >= batch * (size_t)plan.count) return;
-    const size_t b = t / plan.count;
-    const int j = (int)(t % plan.count);
-    unsigned char hdr[8];
-    unsigned hl = 0;
-    hdr[hl++] = (unsigned char)('0' + plan.idx[j]);
-    {
-        char tmp[8];
-        int n = 0;
-        unsigned x = plan.ncoms[j];
-        do { tmp[n++] = (char)('0' + x % 10); x /= 10; } while (x && n < 7);
-        while (n) hdr[hl++] = (unsigned char)tmp[--n];
-    }
-    const unsigned st0 = start[b * (TR_MAX_CALLS + 1) + plan.state[j]];
-    const unsigned char* body = buf + b * (size_t)SC + st0;
-    const unsigned L = SC - st0;
-    const unsigned long long T = (unsigned long long)hl + L;          // message bytes
-    const unsigned nblk = (unsigned)((T + 9 + 63) / 64);
-    uint32_t st[8];
-    dsha::init(st);
-    // alignment of message offset m (>= hl) inside the body: address body + (m - hl)
-    const size_t a0 = (size_t)(body - hl);                             // address of "message byte 0" (virtual)
-    const unsigned sh = (unsigned)(a0 & 3);
-    const unsigned sel = (sh + 3) | ((sh + 2) << 4) | ((sh + 1) << 8) | (sh << 12);
-    // the 17 words of the NEXT interior block are loaded before the current block is compressed: a lone warp per
-    // scheduler has nothing else to hide the ~1 us of an HBM read behind (long scoreboard was 2.3 stalls per issue)
-    uint32_t nx[17];
-    bool nx_valid = false;
-    auto interior = [&](unsigned k) { return k >= 1 && (unsigned long long)k * 64 + 64 <= T; };
-    auto fetch = [&](unsigned k) {
-        const uint32_t* q = reinterpret_cast<const uint32_t*>((a0 + (unsigned long long)k * 64) & ~(size_t)3);
-#pragma unroll
-        for (int i = 0; i < 17; i++) nx[i] = q[i];
-    };
-    if (nblk > 1 && interior(1)) { fetch(1); nx_valid = true; }
-    for (unsigned k = 0; k < nblk; k++) {
-        uint32_t w[16];
-        const unsigned long long m0 = (unsigned long long)k * 64;
-        if (interior(k)) {
-            if (!nx_valid) fetch(k);
-#pragma unroll
-            for (int i = 0; i < 16; i++) w[i] = __byte_perm(nx[i], nx[i + 1], sel);
-            nx_valid = false;
-            if (interior(k + 1)) { fetch(k + 1); nx_valid = true; }
-        } else {
-#pragma unroll 1
-            for (int i = 0; i < 16; i++) {
-                uint32_t x = 0;
-#pragma unroll 1
-                for (int c = 0; c < 4; c++) {
-                    const unsigned long long m = m0 + 4 * i + c;
-                    unsigned byte = 0;
-                    if (m < hl) byte = hdr[m];
-                    else if (m < T) byte = body[m - hl];
-                    else if (m == T) byte = 0x80;
-                    x = (x << 8) | byte;
-                }
-                w[i] = x;
-            }
-            if (k == nblk - 1) {
-                const unsigned long long bits = T * 8;
-                w[14] = (uint32_t)(bits >> 32);
-                w[15] = (uint32_t)bits;
-            }
-        }
-        dsha::compress(st, w);
-    }
-    st_u256(out + t, dsha::digest_to_fr(st));
-}
+// out[b * count + j] = challenge j of proof b, canonical scalar (digest -> Fr, Encoding.hs:75-79).  A block that lies
+// inside the body is read with 17 aligned word loads and byte permutes (the body's alignment is fixed for the whole
+// message); the first block (header) and the last one or two (tail, 0x80, bit length) are assembled byte by byte.
+// Hashing is a serial chain per message and a warp that runs it alone is bound by its own issue rate (~1.7 cycles per
+// instruction), so both kernels split a block's work over two warps: message schedule ahead, rounds behind.
+//   k_tr_squeeze_coop   launches of <= TR_COOP_MAX hashes: a CTA per hash (one lane runs the rounds)
+//   k_tr_squeeze_pair   larger launches: 32 hashes per CTA, lane = hash in both warps
+// (Round 2's first version, one thread per hash doing both halves, took 1.85x longer per launch.)
 
-// The same challenges for a FEW hashes (one proof alone: the drop-in seams' batch size).  A thread that hashes a
-// message by itself issues ~3000 instructions per 64-byte block, two thirds of them message assembly and schedule;
-// a 22 KB transcript takes 0.6 ms, and a proof has 14 of them in a row.  Here a CTA of two warps owns one hash:
+// A FEW hashes (one proof alone: the drop-in seams' batch size).  A thread that hashes a message by itself issues
+// ~1900 instructions per 64-byte block, half of them message assembly and schedule; a 22 KB transcript took 0.6 ms
+// that way, and a proof has 14 of them in a row.  Here a CTA of two warps owns one hash:
 // warp 1 assembles and expands the blocks of the next tile (one block per lane, kw = K + W into shared memory),
-// lane 0 of warp 0 runs the rounds of the current tile.  Bit-identical to k_tr_squeeze.
+// lane 0 of warp 0 runs the rounds of the current tile.
 #define TRC_TILE 32                    // blocks per tile (one per lane of the scheduling warp)
 #define TRC_STRIDE 68                  // words per block in shared memory: 64 + 4 (16-byte rows, 4-way store conflicts)
 __global__ void __launch_bounds__(64) k_tr_squeeze_coop(const unsigned char* __restrict__ buf, unsigned SC, const unsigned* __restrict__ start,
@@ -359,6 +291,93 @@ __global__ void __launch_bounds__(64) k_tr_squeeze_coop(const unsigned char* __r
         __syncthreads();
     }
     if (threadIdx.x == 0) st_u256(out + t, dsha::digest_to_fr(st));
+}
+
+// The batch form of the same split (launches of more than TR_COOP_MAX hashes): 32 hashes per CTA, lane = hash in both
+// warps.  Warp 1 assembles and expands block k + 1 of its 32 messages (the next block's words already in flight) while
+// warp 0 runs the rounds of block k; K + W goes through shared memory as [4 rounds][lane] 16-byte cells (conflict-free
+// either way).  The instruction count of one thread doing both halves, on two warps instead of one: a launch of 512 hashes is 16 warps
+// on 148 SMs, so its duration is one warp's issue time -- 1.85x less this way.
+__global__ void __launch_bounds__(64) k_tr_squeeze_pair(const unsigned char* __restrict__ buf, unsigned SC, const unsigned* __restrict__ start,
+                                                        TrPlan plan, size_t batch, u256* __restrict__ out) {
+    __shared__ uint4 kw[2][16][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n_hash = batch * (size_t)plan.count;
+    const size_t t = blockIdx.x * (size_t)32 + lane;
+    const bool live = t < n_hash;
+    const size_t b = live ? t / plan.count : 0;
+    const int j = live ? (int)(t % plan.count) : 0;
+    unsigned char hdr[8];
+    unsigned hl = 0;
+    hdr[hl++] = (unsigned char)('0' + plan.idx[j]);
+    {
+        char tmp[8];
+        int n = 0;
+        unsigned x = plan.ncoms[j];
+        do { tmp[n++] = (char)('0' + x % 10); x /= 10; } while (x && n < 7);
+        while (n) hdr[hl++] = (unsigned char)tmp[--n];
+    }
+    const unsigned st0 = start[b * (TR_MAX_CALLS + 1) + plan.state[j]];
+    const unsigned char* body = buf + b * (size_t)SC + st0;
+    const unsigned L = SC - st0;
+    const unsigned long long T = (unsigned long long)hl + L;
+    const unsigned nblk = live ? (unsigned)((T + 9 + 63) / 64) : 0;
+    const unsigned nblk_max = __reduce_max_sync(0xffffffffu, nblk);            // the same in both warps (lane = hash)
+    const size_t a0 = (size_t)(body - hl);
+    const unsigned sh = (unsigned)(a0 & 3);
+    const unsigned sel = (sh + 3) | ((sh + 2) << 4) | ((sh + 1) << 8) | (sh << 12);
+    uint32_t nx[17];
+    bool nx_valid = false;
+    auto interior = [&](unsigned k) { return k >= 1 && (unsigned long long)k * 64 + 64 <= T; };
+    auto fetch = [&](unsigned k) {
+        const uint32_t* q = reinterpret_cast<const uint32_t*>((a0 + (unsigned long long)k * 64) & ~(size_t)3);
+#pragma unroll
+        for (int i = 0; i < 17; i++) nx[i] = q[i];
+    };
+    auto schedule = [&](unsigned k) {                                          // block k of this lane's message -> kw[k & 1]
+        if (k >= nblk) return;
+        uint32_t w[16];
+        const unsigned long long m0 = (unsigned long long)k * 64;
+        if (interior(k)) {
+            if (!nx_valid) fetch(k);
+#pragma unroll
+            for (int i = 0; i < 16; i++) w[i] = __byte_perm(nx[i], nx[i + 1], sel);
+            nx_valid = false;
+            if (interior(k + 1)) { fetch(k + 1); nx_valid = true; }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < 16; i++) {
+                uint32_t x = 0;
+#pragma unroll 1
+                for (int c = 0; c < 4; c++) {
+                    const unsigned long long m = m0 + 4 * i + c;
+                    unsigned byte = 0;
+                    if (m < hl) byte = hdr[m];
+                    else if (m < T) byte = body[m - hl];
+                    else if (m == T) byte = 0x80;
+                    x = (x << 8) | byte;
+                }
+                w[i] = x;
+            }
+            if (k == nblk - 1) {
+                const unsigned long long bits = T * 8;
+                w[14] = (uint32_t)(bits >> 32);
+                w[15] = (uint32_t)bits;
+            }
+            if (interior(k + 1)) { fetch(k + 1); nx_valid = true; }
+        }
+        dsha::expand_kw_cells(w, &kw[k & 1][0][lane]);
+    };
+    uint32_t st[8];
+    dsha::init(st);
+    if (warp == 1) schedule(0);
+    __syncthreads();
+    for (unsigned k = 0; k < nblk_max; k++) {
+        if (warp == 1) schedule(k + 1);
+        else if (k < nblk) dsha::rounds_kw_cells(st, &kw[k & 1][0][lane]);
+        __syncthreads();
+    }
+    if (warp == 0 && live) st_u256(out + t, dsha::digest_to_fr(st));
 }
 
 // `random` (src/ZKP.hs:90-93 with h = hashToScalar rn . show, app/Main.hs:177): out[b * out_stride + j] =
