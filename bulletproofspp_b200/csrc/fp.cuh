@@ -631,6 +631,13 @@ static __device__ __noinline__ u256 mul_call(u256 a, u256 b) {      // a call, l
     return redc_dev(t);
 }
 BP_D u256 mul(const u256& a, const u256& b) { return mul_call(a, b); }
+// the squaring schedule of the Fq multiplier (36 products instead of 64): Fermat inversions are 252 squarings
+static __device__ __noinline__ u256 sqr_call(u256 a) {
+    uint32_t t[16];
+    sqr_wide_dev(t, a);
+    return redc_dev(t);
+}
+BP_D u256 sqr(const u256& a) { return sqr_call(a); }
 #else
 BP_HD u256 mul(const u256& a, const u256& b) {
     uint32_t t[16];
@@ -641,8 +648,8 @@ BP_HD u256 mul(const u256& a, const u256& b) {
     return redc(t);
 #endif
 }
-#endif
 BP_HD u256 sqr(const u256& a) { return mul(a, a); }
+#endif
 BP_HD u256 to_mont(const u256& a) { return mul(a, r2()); }
 BP_HD u256 from_mont(const u256& a) {
     uint32_t t[16];
