@@ -1136,7 +1136,7 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         // are replaced while others still add -- an R commitment has half the work of an X commitment), at least 64
         // terms per chunk; the chunk sums are added by k_jac_sum
         const size_t n_msm_all = batch * (size_t)n_out;
-        static const int lut_waves = [] { const char* e = getenv("BPPP_LUT_WAVES"); return e && atoi(e) > 0 ? atoi(e) : 2; }();
+        static const int lut_waves = [] { const char* e = getenv("BPPP_LUT_WAVES"); return e && atoi(e) > 0 ? atoi(e) : 3; }();
         size_t want = ((size_t)lut_waves * 148 * 8 + n_msm_all - 1) / n_msm_all;
         // (a lone proof: 32 terms per chunk -- one (scalar, half) unit per thread, the latency of 8 additions and the tree)
         const size_t min_chunk = n_msm_all <= 8 ? 32 : 64;
