@@ -1132,9 +1132,10 @@ int run_msm_gens(bppp_gens* g, size_t n_terms, const u256* sc, size_t sc_stride,
         return run_msm_pip(ctx, g->pip, g->base.p, 0, sc, sc_stride, sc_out_stride, n_terms, batch, n_out, d_out, work_per_proof);
     if (g->lut) {
         // full-multiples table: W lookups + mixed additions per term, one CTA per (MSM, chunk), no reduction kernel
-        // CTAs of 64 threads, 8 per SM: cut every MSM into enough chunks for about four waves of CTAs (CTAs that finish
-        // are replaced while others still add -- an R commitment has half the work of an X commitment), at least 64
-        // terms per chunk; the chunk sums are added by k_jac_sum
+        // CTAs of 64 threads: cut every MSM into enough chunks for BPPP_LUT_WAVES (default 3) x 148 x 8 CTAs -- 4 chunks for
+        // 1024 MSMs, i.e. 2.8 waves of the 10 CTAs per SM that fit (CTAs that finish are replaced while others still
+        // add: an R commitment has half the work of an X commitment).  Fewer chunks: less tree-summing of partials;
+        // more: a fuller last wave when the launch runs alone.  At least 64 terms per chunk; k_jac_sum adds the chunk sums
         const size_t n_msm_all = batch * (size_t)n_out;
         static const int lut_waves = [] { const char* e = getenv("BPPP_LUT_WAVES"); return e && atoi(e) > 0 ? atoi(e) : 3; }();
         size_t want = ((size_t)lut_waves * 148 * 8 + n_msm_all - 1) / n_msm_all;
