@@ -444,7 +444,7 @@ def main():
                 "note": "integer-pipe bound (no hbm/tensor roofline applies).  frac = frac_pipe = IMAD.WIDE instructions issued for the group "
                         "arithmetic (counted live: lookups x 662 per mixed addition) / CUDA-event time / the IMAD.WIDE issue rate measured in "
                         "this run.  pipe_active_ncu = sm__pipe_fmaheavy_cycles_active of the committed ncu --set full capture (%s): the "
-                        "carry handling and register moves of a field multiplication (IMAD.X, IMAD.MOV: a third of its IMAD-class "
+                        "carry handling and register moves of a field multiplication (IMAD.X, IMAD.MOV: a quarter of its IMAD-class "
                         "instructions) occupy the same pipe, which is why %s of useful multiplies is %s of the pipe.  frac_alg = the reference schedule's IMADs "
                         "(SURVEY 8(d): Pippenger MSMs over each round's CURRENT lengths + the generator folds this kernel absorbs, 136 IMAD "
                         "per multiplication) / time / peak -- it exceeds 1 because a full-multiples table needs neither buckets nor "
