@@ -201,12 +201,12 @@ int bppp_nl_set_shard(bppp_nl* h, size_t first_element);
 int bppp_nl_export(bppp_nl* h, uint8_t* nn, uint8_t* nl, uint8_t* points, uint8_t* c);
 /* current lengths after the folds so far (norm vector length as `getWitness` reports it) */
 int bppp_nl_lengths(bppp_nl* h, size_t* n_norm, size_t* n_lin);
-/* scalarCP s and getWitness (NormArgument.hs:62,121 / IPA.hs:154,222-223): s[b], w[b][n_norm], l[b][n_lin] */
+/* scalarCP s and getWitness (NormArgument.hs:62,121 / InnerProductArgument.hs:154,222-223): s[b], w[b][n_norm], l[b][n_lin] */
 int bppp_nl_final(bppp_nl* h, uint8_t* s, uint8_t* w, uint8_t* l);
 void bppp_nl_destroy(bppp_nl* h);
 
 /* verifyBPM's collapsed check (src/Bulletproof.hs:370-378, 362-368; expandChallenges
- * NormArgument.hs:73-81,131-145 / IPA.hs:103-124,172-181) for `batch` proofs over shared
+ * NormArgument.hs:73-81,131-145 / InnerProductArgument.hs:103-124,172-181) for `batch` proofs over shared
  * generators: ok[b] = [ (s_pub - sc)*g + sum (pub_i - tensor_i)*G_i + sum (0 - tensor_j)*H_j
  *                       + sum_k init_s[b][k]*init_p[b][k] + sum_rounds (e0*X + e1*R) == 0 ].
  * es[b][k]: challenges NEWEST FIRST (as verifyBPM builds them); XR[b][k][2]: responses newest

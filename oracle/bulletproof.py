@@ -346,7 +346,7 @@ class NormLinear:
 
     @classmethod
     def make(cls, kind, G, q, cs, nrm, gs, lin, hs, s=1):
-        """`makeNormLinearBP' s q cs nss ngs lss lgs` (NormArgument.hs:162; IPA.hs:248)."""
+        """`makeNormLinearBP' s q cs nss ngs lss lgs` (NormArgument.hs:162; InnerProductArgument.hs:248)."""
         if kind == "NL":
             return cls(kind, G, s, NLNorm(G, q, nrm, gs), NLLinear(G, cs, lin, hs))
         return cls(kind, G, s, IPNorm.make(G, q, nrm, gs), IPLinear(G, cs, lin, hs))
