@@ -233,3 +233,33 @@ def test_glv_constants_and_split_of_the_pippenger_kernel():
         m1, s1, m2, s2 = split(k)
         assert m1 < 1 << 128 and m2 < 1 << 128
         assert ((-m1 if s1 else m1) + (-m2 if s2 else m2) * lam) % R == k
+
+
+def test_haskell_shim_binds_only_declared_entry_points_with_the_right_arity():
+    """hs/ and INTEGRATION.md: every `foreign import ccall` names a function include/bppp_b200.h declares, and the
+    Haskell type has as many arguments as the C prototype (the shim cannot be compiled here: no GHC)."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "bppp_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|void|const char\*|size_t)\s+(bppp_\w+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = 0 if args in ("", "void") else len([a for a in args.split(",") if a.strip()])
+    assert len(protos) > 80
+    checked = 0
+    for rel in ("hs/Bulletproof/B200/FFI.hs", "INTEGRATION.md"):
+        text = open(os.path.join(root, rel)).read()
+        for m in re.finditer(r'foreign import ccall (?:safe|unsafe) "(\w+)"\s+\w+\s*::\s*((?:[^\n]|\n\s+->)*)', text):
+            name, ty = m.group(1), m.group(2)
+            ty = re.sub(r"--.*", "", ty)
+            assert name in protos, "%s binds %s, which the header does not declare" % (rel, name)
+            depth, arrows = 0, 0
+            for i, ch in enumerate(ty):
+                depth += ch == "("
+                depth -= ch == ")"
+                arrows += depth == 0 and ty[i:i + 2] == "->"
+            assert arrows == protos[name], "%s: %s has %d arguments in Haskell, %d in C" % (rel, name, arrows, protos[name])
+            checked += 1
+    assert checked >= 40
